@@ -1,0 +1,35 @@
+/*
+ * b2enc_kernels.h -- kernel-level C-ABI entry points of libb2enc.so (host buffers in, host
+ * buffers out, plain pointers and sizes).  They exist so that every CUDA kernel can be checked
+ * bit-exactly against "the reference's linked C functions" (BASELINE.json north_star): in the
+ * reference those are libx264's / libswscale's internal pixel, dct and quant functions reached
+ * through av_encode.c:545 (sws_scale) and av_encode.c:970 (x264_encoder_encode).
+ * All functions return 0 on success, a negative value on error (message on stderr), mirroring
+ * the reference's int/NULL error convention (av_encode.c:385,409,416,433,973).
+ */
+#ifndef B2ENC_KERNELS_H
+#define B2ENC_KERNELS_H
+#include "b2enc_types.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* number of CUDA devices visible; <= 0 when the CUDA path cannot run (no fallback exists) */
+int b2_device_count(void);
+
+/* K1: exhaustive full-pel SAD search (replaces the full-pel ME inside x264_encoder_encode,
+ * av_encode.c:970).  cur_y/ref_y: [nframes][h][w] unpadded luma, w and h multiples of 16.
+ * pmv: [nframes][mbh*mbw] quarter-pel predictors or NULL.  Outputs per MB, raster order.
+ * If kernel_ms != NULL the kernel is re-run `iters` times and the mean device time of one
+ * launch (CUDA events) is stored there. */
+int b2k_me_fullpel(const uint8_t *cur_y, const uint8_t *ref_y, int w, int h, int nframes, int merange,
+                   const b2_mv_t *pmv, int lambda, b2_mv_t *mv_out, uint32_t *cost_out,
+                   int iters, float *kernel_ms);
+
+/* sustained VABSDIFF4 lane-instructions/s of the chip (roofline denominator of K1) */
+double b2_bench_vabsdiff4_peak(int device, int outer, int reps, double *ms_best);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

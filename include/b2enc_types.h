@@ -1,0 +1,60 @@
+/*
+ * b2enc_types.h -- plain-C data layouts shared by the CUDA encode stage, the
+ * host entropy stage and the CPU oracle.  No CUDA / torch types.
+ *
+ * The reference (arkanis/video-encoder, av_encode.c) never sees these: they are
+ * the hand-off between the pixel-parallel stage (device) and the serial
+ * entropy/NAL stage (host), i.e. what lives *inside* x264_encoder_encode()
+ * (av_encode.c:970).
+ */
+#ifndef B2ENC_TYPES_H
+#define B2ENC_TYPES_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Replicated border kept around every luma plane held on the device (chroma: half).
+ * >= merange(32) + 16 + 3 (6-tap) so that no search/interpolation read, and no TMA
+ * box, ever leaves the allocation. */
+#define B2_PAD   64
+#define B2_PADC  32
+
+enum { B2_MB_P16x16 = 0, B2_MB_I16x16 = 1, B2_MB_I4x4 = 2 };
+enum { B2_FRAME_I = 0, B2_FRAME_P = 1 };
+
+/* intra 16x16 modes (H.264 Table 8-4) */
+enum { B2_I16_V = 0, B2_I16_H = 1, B2_I16_DC = 2, B2_I16_PLANE = 3 };
+/* intra chroma modes (H.264 Table 8-5) */
+enum { B2_IC_DC = 0, B2_IC_H = 1, B2_IC_V = 2, B2_IC_PLANE = 3 };
+/* intra 4x4 modes (H.264 Table 8-2) */
+enum { B2_I4_V = 0, B2_I4_H, B2_I4_DC, B2_I4_DDL, B2_I4_DDR, B2_I4_VR, B2_I4_HD, B2_I4_VL, B2_I4_HU };
+
+typedef struct { int16_t x, y; } b2_mv_t;
+
+/* One macroblock's decisions: 32 bytes. */
+typedef struct {
+    int16_t  mvx, mvy;      /* quarter-pel motion vector (P16x16), 0 for intra            */
+    uint8_t  mb_type;       /* B2_MB_*                                                     */
+    uint8_t  i16_mode;      /* B2_I16_*  (mb_type == I16x16)                               */
+    uint8_t  chroma_mode;   /* B2_IC_*   (intra MBs)                                       */
+    uint8_t  cbp;           /* bits 0-3: luma 8x8 quadrants, bits 4-5: chroma 0/1/2        */
+    uint8_t  i4_mode[16];   /* B2_I4_* per 4x4 block, H.264 block-index (z) order          */
+    uint32_t cost;          /* cost of the chosen mode (SATD + lambda*bits model)          */
+    uint32_t nnz_mask;      /* bit b (0-15 luma, 16-19 U AC, 20-23 V AC): block has a      */
+                            /* non-zero level; bit 24 luma DC, bit 25 U DC, bit 26 V DC    */
+} b2_mbinfo_t;
+
+/* Quantised levels of one macroblock, each block in zig-zag scan order.
+ *   blk 0..15  luma 4x4 (z order).  I16x16: index 0 is 0, DC lives in blk 24.
+ *   blk 16..19 U AC, 20..23 V AC (index 0 is 0, DC lives in blk 25)
+ *   blk 24     luma DC of an I16x16 MB (16 levels, zig-zag)
+ *   blk 25     chroma DC: [0..3] U, [4..7] V (raster 2x2)                               */
+#define B2_COEF_BLOCKS 26
+typedef struct { int16_t blk[B2_COEF_BLOCKS][16]; } b2_mbcoef_t;   /* 832 bytes */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

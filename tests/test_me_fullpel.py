@@ -1,0 +1,81 @@
+"""K1 parity: CUDA exhaustive full-pel SAD search (through the C-ABI b2k_me_fullpel) vs the C
+oracle b2o_me_fullpel -- bit-exact MVs and costs, identical tie-breaking (T1/T2 of SURVEY.md 4)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_me(oracle, cur, ref, R, pmv=None, lam=0):
+    h, w = cur.shape
+    z = np.zeros((h // 2, w // 2), np.uint8)
+    c = oracle.OFrame(w, h).load(cur, z, z)
+    r = oracle.OFrame(w, h).load(ref, z, z)
+    return oracle.me_fullpel(c, r, R, pmv, lam)
+
+
+def _check(oracle, b2, cur, ref, R, pmv=None, lam=0):
+    mv_g, cost_g, _ = b2.me_fullpel(cur, ref, R, pmv, lam)
+    for i in range(cur.shape[0]):
+        mv_o, cost_o = _oracle_me(oracle, cur[i], ref[i], R, None if pmv is None else pmv[i], lam)
+        assert np.array_equal(cost_g[i], cost_o), f"cost mismatch frame {i}"
+        assert np.array_equal(mv_g[i]["x"], mv_o["x"]) and np.array_equal(mv_g[i]["y"], mv_o["y"]), f"mv mismatch frame {i}"
+
+
+@pytest.mark.parametrize("R", [8, 16, 32])
+@pytest.mark.parametrize("wh", [(128, 64), (80, 48), (176, 144), (16, 16)])
+def test_random_frames(oracle, b2, R, wh):
+    w, h = wh
+    rng = np.random.default_rng(R * 1000 + w)
+    cur = rng.integers(0, 256, (2, h, w), dtype=np.uint8)
+    ref = rng.integers(0, 256, (2, h, w), dtype=np.uint8)
+    _check(oracle, b2, cur, ref, R)
+
+
+@pytest.mark.parametrize("R", [16, 32])
+def test_adversarial_ties(oracle, b2, R):
+    """flat, periodic and saturated content: many candidates tie, the lowest scan index must win."""
+    w, h = 192, 96
+    flat = np.full((h, w), 77, np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w]
+    periodic = (((xx // 4) + (yy // 4)) % 2 * 255).astype(np.uint8)
+    stripes = ((xx % 8) * 32).astype(np.uint8)
+    sat = np.where(xx > w // 2, 255, 0).astype(np.uint8)
+    cur = np.stack([flat, periodic, stripes, sat, flat])
+    ref = np.stack([flat, periodic, stripes, sat, np.full((h, w), 80, np.uint8)])
+    _check(oracle, b2, cur, ref, R)
+    mv, cost, _ = b2.me_fullpel(cur[:1], ref[:1], R)
+    assert (mv["x"] == -R).all() and (mv["y"] == -R).all() and (cost == 0).all()
+
+
+@pytest.mark.parametrize("R", [16, 32])
+def test_lambda_and_predictors(oracle, b2, R):
+    w, h = 256, 80
+    rng = np.random.default_rng(7 + R)
+    base = rng.integers(0, 256, (h + 80, w + 80), dtype=np.uint8)
+    ref = base[40:40 + h, 40:40 + w][None].copy()
+    cur = base[43:43 + h, 35:35 + w][None].copy()          # true motion (-5,+3)
+    pmv = np.zeros((1, (w // 16) * (h // 16)), b2.MV)
+    pmv["x"] = rng.integers(-140, 140, pmv.shape); pmv["y"] = rng.integers(-140, 140, pmv.shape)
+    for lam in (0, 4, 91):
+        _check(oracle, b2, cur, ref, R, pmv, lam)
+
+
+def test_synth_known_answer_1080p(oracle, b2):
+    """full C3 size: interior MBs of the panning synthetic sequence have the known MV (+3,+2);
+    a random sample of MBs is checked against the oracle (size-independent spot check)."""
+    w, h = 1920, 1088
+    y0, _, _ = oracle.synth_frame(w, h, 4)
+    y1, _, _ = oracle.synth_frame(w, h, 5)
+    mv, cost, _ = b2.me_fullpel(y1, y0, 32)
+    mbw, mbh = w // 16, h // 16
+    mvx = mv["x"].reshape(mbh, mbw); mvy = mv["y"].reshape(mbh, mbw)
+    assert (mvx[:-1, :-1] == 3).all() and (mvy[:-1, :-1] == 2).all()
+    z = np.zeros((h // 2, w // 2), np.uint8)
+    c = oracle.OFrame(w, h).load(y1, z, z); r = oracle.OFrame(w, h).load(y0, z, z)
+    rng = np.random.default_rng(1)
+    for _ in range(40):
+        mbx, mby = int(rng.integers(0, mbw)), int(rng.integers(0, mbh))
+        (ox, oy), oc = oracle.me_fullpel_mb(c, r, 32, mbx, mby)
+        i = mby * mbw + mbx
+        assert (int(mv["x"][0, i]), int(mv["y"][0, i]), int(cost[0, i])) == (ox, oy, oc)

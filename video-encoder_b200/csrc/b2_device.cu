@@ -1,0 +1,78 @@
+// b2_device.cu -- device plumbing shared by all kernels: TMA descriptors over padded plane
+// stacks and K6, the border-replication kernel (the device-side twin of what x264 does to
+// its internal frames so that unrestricted motion vectors may point outside the picture).
+#include "b2_common.cuh"
+#include "b2_internal.h"
+
+// ---- TMA descriptor ------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || p == nullptr) {
+        fprintf(stderr, "b2enc: cuTensorMapEncodeTiled not available from the driver\n");
+        return nullptr;
+    }
+    fn = (PFN_encodeTiled)p;
+    return fn;
+}
+
+int b2_make_plane_tmap(CUtensorMap *tm, const void *base, int pitch, int rows, int nplanes, int bw, int bh)
+{
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return -1;
+    cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)nplanes};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)pitch * rows};
+    cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "b2enc: cuTensorMapEncodeTiled failed (%d) pitch=%d rows=%d n=%d box=%dx%d\n", (int)r, pitch,
+                rows, nplanes, bw, bh);
+        return -1;
+    }
+    return 0;
+}
+
+// ---- K6: border replication -------------------------------------------------------------------
+// planes: [n][rows][pitch] with the picture origin at (pad,pad); every byte outside the
+// iw x ih interior becomes interior[clamp(y)][clamp(x)].  One thread per aligned 32-bit word.
+__global__ void k6_extend_border_kernel(uint8_t *planes, int pitch, int rows, int pad, int iw, int ih)
+{
+    const int wpr = pitch >> 2;
+    const int wx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (wx >= wpr) return;
+    uint8_t *plane = planes + (size_t)blockIdx.z * pitch * rows;
+    const int x0 = wx * 4 - pad, yy = y - pad;
+    if (yy >= 0 && yy < ih && x0 >= 0 && x0 + 3 < iw) return;       // interior word
+    const int cy = min(max(yy, 0), ih - 1);
+    const uint8_t *src = plane + (size_t)(cy + pad) * pitch + pad;
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        int cx = min(max(x0 + b, 0), iw - 1);
+        v |= (uint32_t)src[cx] << (8 * b);
+    }
+    *(uint32_t *)(plane + (size_t)y * pitch + wx * 4) = v;
+}
+
+int b2_launch_extend_border(uint8_t *d_planes, int pitch, int rows, int nplanes, int pad, int iw, int ih,
+                            cudaStream_t st)
+{
+    dim3 block(128);
+    dim3 grid((pitch / 4 + 127) / 128, rows, nplanes);
+    k6_extend_border_kernel<<<grid, block, 0, st>>>(d_planes, pitch, rows, pad, iw, ih);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+}

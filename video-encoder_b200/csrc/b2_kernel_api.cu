@@ -1,0 +1,79 @@
+// b2_kernel_api.cu -- kernel-level C-ABI (include/b2enc_kernels.h): host buffers in/out.
+#include "b2_common.cuh"
+#include "b2_internal.h"
+#include "../../include/b2enc_kernels.h"
+
+extern "C" int b2_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { return cudaMalloc(&p, n) == cudaSuccess ? 0 : -1; }
+};
+
+// upload [n][h][w] unpadded planes into a padded stack and replicate the border
+int upload_padded(DevBuf &buf, const uint8_t *host, int w, int h, int n, int pad, int *pitch, int *rows)
+{
+    *pitch = w + 2 * pad; *rows = h + 2 * pad;
+    if (buf.alloc((size_t)*pitch * *rows * n)) { fprintf(stderr, "b2enc: cudaMalloc failed\n"); return -1; }
+    for (int i = 0; i < n; i++) {
+        uint8_t *dst = (uint8_t *)buf.p + (size_t)i * *pitch * *rows + (size_t)pad * *pitch + pad;
+        B2_CUDA_OK(cudaMemcpy2D(dst, *pitch, host + (size_t)i * w * h, w, w, h, cudaMemcpyHostToDevice));
+    }
+    return b2_launch_extend_border((uint8_t *)buf.p, *pitch, *rows, n, pad, w, h, 0);
+}
+}  // namespace
+
+extern "C" int b2k_me_fullpel(const uint8_t *cur_y, const uint8_t *ref_y, int w, int h, int nframes, int merange,
+                              const b2_mv_t *pmv, int lambda, b2_mv_t *mv_out, uint32_t *cost_out,
+                              int iters, float *kernel_ms)
+{
+    if ((w & 15) || (h & 15) || w <= 0 || h <= 0 || nframes <= 0) {
+        fprintf(stderr, "b2enc: b2k_me_fullpel needs w,h multiples of 16\n");
+        return -1;
+    }
+    int bw, bh;
+    if (b2_k1_window_box(merange, &bw, &bh)) { fprintf(stderr, "b2enc: merange %d not supported\n", merange); return -1; }
+    const int mbw = w / 16, mbh = h / 16;
+    const size_t nmb = (size_t)mbw * mbh * nframes;
+    DevBuf d_cur, d_ref, d_pmv, d_mv, d_cost;
+    int pitch, rows;
+    if (upload_padded(d_cur, cur_y, w, h, nframes, B2_PAD, &pitch, &rows)) return -1;
+    if (upload_padded(d_ref, ref_y, w, h, nframes, B2_PAD, &pitch, &rows)) return -1;
+    if (d_mv.alloc(nmb * sizeof(b2_mv_t)) || d_cost.alloc(nmb * 4)) return -1;
+    if (pmv) {
+        if (d_pmv.alloc(nmb * sizeof(b2_mv_t))) return -1;
+        B2_CUDA_OK(cudaMemcpy(d_pmv.p, pmv, nmb * sizeof(b2_mv_t), cudaMemcpyHostToDevice));
+    }
+    CUtensorMap tm_cur, tm_ref;
+    if (b2_make_plane_tmap(&tm_cur, d_cur.p, pitch, rows, nframes, 128, 16)) return -1;
+    if (b2_make_plane_tmap(&tm_ref, d_ref.p, pitch, rows, nframes, bw, bh)) return -1;
+    if (b2_launch_me_fullpel(merange, &tm_cur, &tm_ref, mbw, mbh, nframes, (const b2_mv_t *)d_pmv.p, lambda,
+                             (b2_mv_t *)d_mv.p, (uint32_t *)d_cost.p, 0))
+        return -1;
+    B2_CUDA_OK(cudaDeviceSynchronize());
+    if (kernel_ms) {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        if (iters < 1) iters = 1;
+        cudaEventRecord(e0, 0);
+        for (int i = 0; i < iters; i++)
+            b2_launch_me_fullpel(merange, &tm_cur, &tm_ref, mbw, mbh, nframes, (const b2_mv_t *)d_pmv.p, lambda,
+                                 (b2_mv_t *)d_mv.p, (uint32_t *)d_cost.p, 0);
+        cudaEventRecord(e1, 0);
+        B2_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *kernel_ms = ms / iters;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    B2_CUDA_OK(cudaMemcpy(mv_out, d_mv.p, nmb * sizeof(b2_mv_t), cudaMemcpyDeviceToHost));
+    B2_CUDA_OK(cudaMemcpy(cost_out, d_cost.p, nmb * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}

@@ -1,0 +1,239 @@
+// k1_me_fullpel.cu -- K1: exhaustive full-pel SAD motion search, one MV per 16x16 macroblock.
+//
+// Replaces the full-pel half of the motion estimation that the reference reaches through
+// x264_encoder_encode() (av_encode.c:970); bit-exact against oracle/b2o_me.c:b2o_me_fullpel.
+//
+// Bound: integer ALU (VABSDIFF4.U8.ACC issue rate).  Algorithmic work per macroblock:
+// (2R+1)^2 candidates x 256 pixel-SADs = (2R+1)^2 x 64 VABSDIFF4 lane-instructions.
+//
+// Design:
+//  * One CTA searches a strip of 8 horizontally adjacent macroblocks of one frame.  The
+//    (128+2R) x (16+2R) search window of the *padded* reference plane and the 128x16 current
+//    tile are fetched by TMA (cp.async.bulk.tensor.3d), never leaving the allocation because
+//    every plane carries a 64-px replicated border.
+//  * Operand supply, not the ALU, is the first limiter (32 shared-memory words/clk/SM vs 64
+//    VABSDIFF4 lanes/clk/SM).  Two reuse tricks remove it:
+//      - the window is expanded once into "one 32-bit word per pixel position"
+//        (word x = pixels x..x+3), so every byte alignment is a plain conflict-free LDS.32;
+//      - register tiling: a lane owns one dx and K consecutive dy; the current macroblock sits
+//        in 64 registers, each reference row is loaded once (4 LDS.32) and applied to up to K
+//        current rows (K accumulators) -> (16+K-1)*4 loads per 64*K VABSDIFF4.
+//  * Lanes of a warp are 32 consecutive dx -> consecutive words -> no bank conflicts.
+//  * Winner: key = (cost << 13) | scan_index, CREDUX.MIN over the warp, atomicMin in smem.
+//    Lowest scan index wins ties by construction, exactly like the oracle's strict '<'.
+#include "b2_common.cuh"
+
+namespace {
+
+constexpr int NMB = 8;          // macroblocks per CTA strip
+constexpr int NTHREADS = 256;
+constexpr int NWARPS = NTHREADS / 32;
+
+template <int R> struct K1Cfg;
+template <> struct K1Cfg<32> { static constexpr int K = 13, NG = 5; };   // 65 = 5 x 13
+template <> struct K1Cfg<16> { static constexpr int K = 11, NG = 3; };   // 33 = 3 x 11
+template <> struct K1Cfg<8>  { static constexpr int K = 17, NG = 1; };   // 17 = 1 x 17
+
+template <int R> struct K1Smem {
+    static constexpr int ND = 2 * R + 1;
+    static constexpr int WIN_W = NMB * 16 + 2 * R;      // bytes per raw window row
+    static constexpr int WIN_H = 16 + 2 * R;
+    static constexpr int RAW_BYTES = WIN_W * WIN_H;
+    static constexpr int EXP_PITCH = WIN_W;             // words per expanded row
+    static constexpr int EXP_BYTES = EXP_PITCH * WIN_H * 4;
+    static constexpr int CUR_BYTES = NMB * 16 * 16;
+    // layout (all 128-B aligned)
+    static constexpr int OFF_RAW = 0;
+    static constexpr int OFF_CUR = (RAW_BYTES + 16 + 127) & ~127;
+    static constexpr int OFF_EXP = OFF_CUR + CUR_BYTES;
+    static constexpr int OFF_COSTX = OFF_EXP + EXP_BYTES;
+    static constexpr int OFF_COSTY = OFF_COSTX + NMB * ND * 4;
+    static constexpr int OFF_BEST = OFF_COSTY + NMB * ND * 4;
+    static constexpr int OFF_BAR = (OFF_BEST + NMB * 4 + 7) & ~7;
+    static constexpr int TOTAL = OFF_BAR + 8 + 128;     // +128: manual alignment slack
+};
+
+template <int R>
+__global__ void __launch_bounds__(NTHREADS, 2)
+k1_me_fullpel_kernel(const __grid_constant__ CUtensorMap tm_cur,
+                     const __grid_constant__ CUtensorMap tm_ref,
+                     int mbw, int mbh, const b2_mv_t *__restrict__ pmv, int lambda,
+                     b2_mv_t *__restrict__ mv_out, uint32_t *__restrict__ cost_out)
+{
+    using S = K1Smem<R>;
+    constexpr int K = K1Cfg<R>::K, NG = K1Cfg<R>::NG, ND = S::ND;
+    static_assert(K * NG == ND, "dy groups must tile the search range");
+
+    extern __shared__ uint8_t smem_raw_[];
+    uint8_t *smem = smem_raw_ + ((128u - (smem_u32(smem_raw_) & 127u)) & 127u);   // keeps the shared address space
+    uint8_t *s_raw = smem + S::OFF_RAW;
+    uint8_t *s_cur = smem + S::OFF_CUR;
+    uint32_t *s_exp = (uint32_t *)(smem + S::OFF_EXP);
+    uint32_t *s_costx = (uint32_t *)(smem + S::OFF_COSTX);
+    uint32_t *s_costy = (uint32_t *)(smem + S::OFF_COSTY);
+    uint32_t *s_best = (uint32_t *)(smem + S::OFF_BEST);
+    uint64_t *s_bar = (uint64_t *)(smem + S::OFF_BAR);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mb0 = blockIdx.x * NMB, mby = blockIdx.y, frame = blockIdx.z;
+    const int nmb = min(NMB, mbw - mb0);
+
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(s_bar, S::RAW_BYTES + S::CUR_BYTES);
+        tma_load_3d(s_raw, &tm_ref, B2_PAD + mb0 * 16 - R, B2_PAD + mby * 16 - R, frame, s_bar);
+        tma_load_3d(s_cur, &tm_cur, B2_PAD + mb0 * 16, B2_PAD + mby * 16, frame, s_bar);
+    }
+
+    // while the TMA is in flight: motion-vector cost tables and best-key init
+    const size_t mb_base = ((size_t)frame * mbh + mby) * mbw + mb0;
+    for (int i = tid; i < NMB * ND; i += NTHREADS) {
+        int m = i / ND, d = i - m * ND;
+        int px = 0, py = 0;
+        if (pmv != nullptr && m < nmb) { b2_mv_t p = pmv[mb_base + m]; px = p.x; py = p.y; }
+        s_costx[i] = (uint32_t)(lambda * b2_mvbits(4 * (d - R) - px));
+        s_costy[i] = (uint32_t)(lambda * b2_mvbits(4 * (d - R) - py));
+    }
+    if (tid < NMB) s_best[tid] = 0xffffffffu;
+
+    mbar_wait(s_bar, 0);
+
+    // expand: word x of a row = pixels x..x+3 (little endian), all 4 byte alignments
+    {
+        constexpr int WPR = S::WIN_W / 4;             // aligned words per raw row
+        const uint32_t *raw32 = (const uint32_t *)s_raw;
+        for (int i = tid; i < WPR * S::WIN_H; i += NTHREADS) {
+            int r = i / WPR, j = i - r * WPR;
+            uint32_t lo = raw32[i], hi = raw32[i + 1];    // last word of the buffer: 16 B slack
+            uint4 o;
+            o.x = lo;
+            o.y = __funnelshift_r(lo, hi, 8);
+            o.z = __funnelshift_r(lo, hi, 16);
+            o.w = __funnelshift_r(lo, hi, 24);
+            *(uint4 *)(s_exp + r * S::EXP_PITCH + 4 * j) = o;
+        }
+    }
+    __syncthreads();
+
+    const int total = nmb * NG * ND;                  // lane-tasks: (mb, dy-group, dx)
+    for (int t0 = warp * 32; t0 < total; t0 += NWARPS * 32) {
+        const int t = t0 + lane;
+        const bool active = t < total;
+        const int tt = active ? t : t0;               // idle lanes shadow lane 0's task
+        const int m = tt / (NG * ND);
+        const int rem = tt - m * (NG * ND);
+        const int g = rem / ND;
+        const int dxi = rem - g * ND;
+
+        // current macroblock -> 64 registers
+        uint32_t cur[64];
+        {
+            const uint4 *c4 = (const uint4 *)(s_cur + m * 16);
+#pragma unroll
+            for (int y = 0; y < 16; y++) {
+                uint4 v = c4[y * (NMB * 16 / 16)];
+                cur[y * 4 + 0] = v.x; cur[y * 4 + 1] = v.y; cur[y * 4 + 2] = v.z; cur[y * 4 + 3] = v.w;
+            }
+        }
+        uint32_t acc[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = 0;
+
+        const uint32_t *wp = s_exp + (g * K) * S::EXP_PITCH + m * 16 + dxi;
+#pragma unroll
+        for (int r = 0; r < K + 15; r++) {
+            const uint32_t w0 = wp[r * S::EXP_PITCH + 0];
+            const uint32_t w1 = wp[r * S::EXP_PITCH + 4];
+            const uint32_t w2 = wp[r * S::EXP_PITCH + 8];
+            const uint32_t w3 = wp[r * S::EXP_PITCH + 12];
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const int y = r - k;                  // current row that meets reference row r at dy = g*K+k
+                if (y >= 0 && y < 16) {
+                    acc[k] = vsad4_acc(w0, cur[y * 4 + 0], acc[k]);
+                    acc[k] = vsad4_acc(w1, cur[y * 4 + 1], acc[k]);
+                    acc[k] = vsad4_acc(w2, cur[y * 4 + 2], acc[k]);
+                    acc[k] = vsad4_acc(w3, cur[y * 4 + 3], acc[k]);
+                }
+            }
+        }
+
+        uint32_t key = 0xffffffffu;
+        if (active) {
+            const uint32_t cx = s_costx[m * ND + dxi];
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const int dyi = g * K + k;
+                const uint32_t cost = acc[k] + cx + s_costy[m * ND + dyi];
+                key = min(key, (cost << 13) | (uint32_t)(dyi * ND + dxi));
+            }
+        }
+        const int m0 = __shfl_sync(0xffffffffu, m, 0);
+        if (__all_sync(0xffffffffu, m == m0)) {
+            const uint32_t wmin = __reduce_min_sync(0xffffffffu, key);
+            if (lane == 0) atomicMin(&s_best[m0], wmin);
+        } else if (active) {
+            atomicMin(&s_best[m], key);
+        }
+    }
+    __syncthreads();
+
+    if (tid < nmb) {
+        const uint32_t key = s_best[tid];
+        const int idx = (int)(key & 8191u);
+        const int dyi = idx / ND, dxi = idx - dyi * ND;
+        b2_mv_t mv;
+        mv.x = (int16_t)(dxi - R);
+        mv.y = (int16_t)(dyi - R);
+        mv_out[mb_base + tid] = mv;
+        cost_out[mb_base + tid] = key >> 13;
+    }
+}
+
+template <int R>
+int launch_k1(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, int mbw, int mbh, int nframes,
+              const b2_mv_t *pmv, int lambda, b2_mv_t *mv_out, uint32_t *cost_out, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        B2_CUDA_OK(cudaFuncSetAttribute(k1_me_fullpel_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        K1Smem<R>::TOTAL));
+        attr_set = true;
+    }
+    dim3 grid((mbw + NMB - 1) / NMB, mbh, nframes);
+    k1_me_fullpel_kernel<R><<<grid, NTHREADS, K1Smem<R>::TOTAL, st>>>(tm_cur, tm_ref, mbw, mbh, pmv, lambda,
+                                                                      mv_out, cost_out);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// window/current-tile box sizes needed to build the tensor maps
+extern "C" int b2_k1_window_box(int R, int *bw, int *bh)
+{
+    if (R != 8 && R != 16 && R != 32) return -1;
+    *bw = NMB * 16 + 2 * R;
+    *bh = 16 + 2 * R;
+    return 0;
+}
+
+// d_* are device pointers; the tensor maps describe [nframes][rows][pitch] padded luma planes
+// with boxes {128+2R, 16+2R, 1} (ref) and {128, 16, 1} (cur).
+int b2_launch_me_fullpel(int R, const CUtensorMap *tm_cur, const CUtensorMap *tm_ref, int mbw, int mbh,
+                         int nframes, const b2_mv_t *d_pmv, int lambda, b2_mv_t *d_mv, uint32_t *d_cost,
+                         cudaStream_t st)
+{
+    switch (R) {
+    case 32: return launch_k1<32>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);
+    case 16: return launch_k1<16>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);
+    case 8:  return launch_k1<8>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);
+    default:
+        fprintf(stderr, "b2enc: merange %d not supported (8, 16 or 32)\n", R);
+        return -1;
+    }
+}
