@@ -113,3 +113,161 @@ def me_fullpel_mb(cur, ref, R, mbx, mby, pmv=(0, 0), lam=0):
     packed = int(p.view(np.uint32)[0])
     lib().b2o_me_fullpel_mb(C.addressof(cur.f), C.addressof(ref.f), R, mbx, mby, packed, lam, _p(mv), _p(cost))
     return (int(mv["x"][0]), int(mv["y"][0])), int(cost[0])
+
+
+# ---- frame-level oracle encoder + host entropy coder (linked into libb2oracle.so) ---------------
+class Seq(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("fps_num", C.c_int), ("fps_den", C.c_int),
+                ("sar_w", C.c_int), ("sar_h", C.c_int), ("qp", C.c_int)]
+
+
+def encode_frame(prm: Params, frame_type, cur: OFrame, ref, recon: OFrame, prev_mv=None):
+    n = cur.f.mbw * cur.f.mbh
+    info = np.zeros(n, MBINFO); coef = np.zeros(n, MBCOEF)
+    lib().b2o_encode_frame(C.byref(prm), frame_type, C.byref(cur.f), C.byref(ref.f) if ref is not None else None,
+                           C.byref(recon.f), _p(prev_mv) if prev_mv is not None else None, _p(info), _p(coef))
+    return info, coef
+
+
+class Entropy:
+    def __init__(self, w, h, qp, fps=(30, 1), sar=(1, 1)):
+        L = lib()
+        L.b2h_entropy_create.restype = C.c_void_p
+        L.b2h_write_sps.restype = C.c_size_t; L.b2h_write_pps.restype = C.c_size_t; L.b2h_write_slice.restype = C.c_size_t
+        L.b2h_write_slice.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.b2h_entropy_destroy.argtypes = [C.c_void_p]
+        self.seq = Seq(w, h, fps[0], fps[1], sar[0], sar[1], qp)
+        self.mbw, self.mbh = (w + 15) // 16, (h + 15) // 16
+        self.e = L.b2h_entropy_create(self.mbw, self.mbh)
+        self.buf = np.zeros(self.mbw * self.mbh * 3072 + 65536, np.uint8)
+
+    def __del__(self):
+        try:
+            lib().b2h_entropy_destroy(self.e)
+        except Exception:
+            pass
+
+    def sps(self):
+        n = lib().b2h_write_sps(C.byref(self.seq), _p(self.buf), self.buf.size)
+        assert n > 0
+        return self.buf[:n].tobytes()
+
+    def pps(self):
+        n = lib().b2h_write_pps(C.byref(self.seq), _p(self.buf), self.buf.size)
+        assert n > 0
+        return self.buf[:n].tobytes()
+
+    def slice(self, frame_type, frame_num, idr_id, info, coef):
+        info = np.ascontiguousarray(info, MBINFO); coef = np.ascontiguousarray(coef, MBCOEF)
+        n = lib().b2h_write_slice(self.e, C.addressof(self.seq), frame_type, frame_num, idr_id, _p(info), _p(coef),
+                                  _p(self.buf), self.buf.size)
+        assert n > 0, "slice writer overflow"
+        return self.buf[:n].tobytes()
+
+
+def encode_sequence(frames, w, h, qp=26, merange=16, subpel=1, intra_in_p=1, gop=32, fps=(30, 1)):
+    """frames: iterable of (y,u,v).  Returns (annexb_bytes, [recon OFrame], [info], [coef])."""
+    prm = Params(qp, merange, subpel, intra_in_p)
+    ent = Entropy(w, h, qp, fps)
+    out = bytearray()
+    sc = b"\x00\x00\x00\x01"
+    recons, infos, coefs = [], [], []
+    prev = None; prev_mv = None; idr = 0
+    for t, (y, u, v) in enumerate(frames):
+        cur = OFrame(w, h).load(y, u, v)
+        rec = OFrame(w, h)
+        is_i = (t % gop) == 0
+        if is_i:
+            out += sc + ent.sps() + sc + ent.pps()
+            info, coef = encode_frame(prm, 0, cur, None, rec, None)
+            out += sc + ent.slice(0, 0, idr, info, coef); idr += 1
+        else:
+            info, coef = encode_frame(prm, 1, cur, prev, rec, prev_mv)
+            out += sc + ent.slice(1, t % gop, 0, info, coef)
+        prev_mv = np.zeros(info.size, MV); prev_mv["x"] = info["mvx"]; prev_mv["y"] = info["mvy"]
+        prev = rec
+        recons.append(rec); infos.append(info); coefs.append(coef)
+    return bytes(out), recons, infos, coefs
+
+
+def decode_luma(annexb: bytes, path="/tmp/b2_dec.h264"):
+    """decode an Annex-B stream with libavcodec's H.264 decoder (through OpenCV); exact luma planes."""
+    import cv2
+    with open(path, "wb") as f:
+        f.write(annexb)
+    cap = cv2.VideoCapture(path, cv2.CAP_FFMPEG)
+    cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
+    out = []
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        out.append(fr.copy())
+    cap.release()
+    return out
+
+
+# ---- full YUV decode through libavcodec (ctypes), for chroma drift checks --------------------------
+def _avlibs():
+    import glob
+    import cv2  # noqa: F401  (loads the bundled FFmpeg libs so that siblings resolve)
+    d = os.path.join(os.path.dirname(cv2.__file__), "..", "opencv_python_headless.libs")
+    avutil = C.CDLL(glob.glob(os.path.join(d, "libavutil-*.so*"))[0])
+    avcodec = C.CDLL(glob.glob(os.path.join(d, "libavcodec-*.so*"))[0])
+    return avutil, avcodec
+
+
+def decode_yuv(access_units):
+    """access_units: list of Annex-B byte strings (one picture each, SPS/PPS may be prepended).
+    Returns a list of (y,u,v) uint8 arrays decoded by libavcodec's native H.264 decoder."""
+    avutil, avc = _avlibs()
+    avc.avcodec_find_decoder.restype = C.c_void_p
+    avc.avcodec_alloc_context3.restype = C.c_void_p; avc.avcodec_alloc_context3.argtypes = [C.c_void_p]
+    avc.avcodec_open2.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    avc.av_packet_alloc.restype = C.c_void_p
+    avutil.av_frame_alloc.restype = C.c_void_p
+    avc.avcodec_send_packet.argtypes = [C.c_void_p, C.c_void_p]
+    avc.avcodec_receive_frame.argtypes = [C.c_void_p, C.c_void_p]
+    avc.avcodec_free_context.argtypes = [C.c_void_p]
+    codec = avc.avcodec_find_decoder(27)            # AV_CODEC_ID_H264
+    assert codec
+    ctx = avc.avcodec_alloc_context3(codec)
+    assert avc.avcodec_open2(ctx, codec, None) == 0
+    pkt = avc.av_packet_alloc(); frm = avutil.av_frame_alloc()
+    out = []
+
+    def drain():
+        while avc.avcodec_receive_frame(ctx, frm) == 0:
+            data = (C.c_void_p * 8).from_address(frm)
+            ls = (C.c_int * 8).from_address(frm + 64)
+            w = C.c_int.from_address(frm + 104).value; h = C.c_int.from_address(frm + 108).value
+            planes = []
+            for i, (pw, ph) in enumerate([(w, h), ((w + 1) // 2, (h + 1) // 2), ((w + 1) // 2, (h + 1) // 2)]):
+                buf = (C.c_uint8 * (ls[i] * ph)).from_address(data[i])
+                planes.append(np.frombuffer(buf, np.uint8).reshape(ph, ls[i])[:, :pw].copy())
+            out.append(tuple(planes))
+
+    keep = []
+    for au in access_units:
+        b = np.frombuffer(au + b"\0" * 64, np.uint8).copy(); keep.append(b)
+        C.c_void_p.from_address(pkt + 24).value = b.ctypes.data      # AVPacket.data
+        C.c_int.from_address(pkt + 32).value = len(au)               # AVPacket.size
+        rc = avc.avcodec_send_packet(ctx, pkt)
+        assert rc == 0, "avcodec_send_packet failed %d" % rc
+        drain()
+    avc.avcodec_send_packet(ctx, None)
+    drain()
+    ctxp = C.c_void_p(ctx)
+    avc.avcodec_free_context(C.byref(ctxp))
+    return out
+
+
+def split_access_units(annexb: bytes):
+    """split an Annex-B stream into access units (each ends with a slice NAL type 1 or 5)."""
+    parts = annexb.split(b"\x00\x00\x00\x01")[1:]
+    aus, cur = [], b""
+    for p in parts:
+        cur += b"\x00\x00\x00\x01" + p
+        if (p[0] & 31) in (1, 5):
+            aus.append(cur); cur = b""
+    return aus

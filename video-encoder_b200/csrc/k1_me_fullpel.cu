@@ -32,7 +32,6 @@ constexpr int NWARPS = NTHREADS / 32;
 template <int R> struct K1Cfg;
 template <> struct K1Cfg<32> { static constexpr int K = 13, NG = 5; };   // 65 = 5 x 13
 template <> struct K1Cfg<16> { static constexpr int K = 11, NG = 3; };   // 33 = 3 x 11
-template <> struct K1Cfg<8>  { static constexpr int K = 17, NG = 1; };   // 17 = 1 x 17
 
 template <int R> struct K1Smem {
     static constexpr int ND = 2 * R + 1;
@@ -216,7 +215,7 @@ int launch_k1(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, int mbw, int
 // window/current-tile box sizes needed to build the tensor maps
 extern "C" int b2_k1_window_box(int R, int *bw, int *bh)
 {
-    if (R != 8 && R != 16 && R != 32) return -1;
+    if (R != 16 && R != 32) return -1;
     *bw = NMB * 16 + 2 * R;
     *bh = 16 + 2 * R;
     return 0;
@@ -231,9 +230,8 @@ int b2_launch_me_fullpel(int R, const CUtensorMap *tm_cur, const CUtensorMap *tm
     switch (R) {
     case 32: return launch_k1<32>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);
     case 16: return launch_k1<16>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);
-    case 8:  return launch_k1<8>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);
     default:
-        fprintf(stderr, "b2enc: merange %d not supported (8, 16 or 32)\n", R);
+        fprintf(stderr, "b2enc: merange %d not supported (16 or 32)\n", R);
         return -1;
     }
 }
