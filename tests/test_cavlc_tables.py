@@ -25,7 +25,7 @@ def _check_prefix_code(lens, bits, complete=True):
     kraft = sum(2.0 ** -l for l, _ in codes)
     if complete:
         # complete up to the reserved long all-zero prefixes (start-code emulation guard)
-        assert 0 <= 1.0 - kraft < 2.0 ** -9, f"Kraft sum {kraft}"
+        assert 0 <= 1.0 - kraft <= 2.0 ** -8, f"Kraft sum {kraft}"
     else:
         assert kraft <= 1.0
 
