@@ -1,0 +1,79 @@
+/*
+ * b2enc_engine.h -- C-ABI of the B200 encode-stage engine (libb2enc.so): the pixel-parallel part of
+ * what the reference does per frame between av_encode.c:545 (sws_scale into pic_in) and the entropy
+ * coder inside x264_encoder_encode (av_encode.c:970):
+ *     convert -> full-pel SAD search -> sub-pel SATD refine -> intra analysis -> decision ->
+ *     DCT/quant/dequant/IDCT/reconstruction -> border extension.
+ * One engine = one GPU.  It encodes `slots` independent units (closed GOPs of one stream, or live
+ * streams) in lock-step: every call advances all slots by one frame, so each kernel launch covers
+ * slots x macroblocks.  Frames inside a closed GOP are a serial chain (P needs the previous
+ * reconstruction); different GOPs / streams share nothing, hence no collective.
+ * Plain pointers and sizes only.  All int functions return 0 on success, <0 on error (stderr message).
+ */
+#ifndef B2ENC_ENGINE_H
+#define B2ENC_ENGINE_H
+#include <stddef.h>
+#include "b2enc_types.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2_engine b2_engine_t;
+
+typedef struct {
+    int device;        /* CUDA device ordinal                                             */
+    int width, height; /* picture size (any; coded size is rounded up to 16)              */
+    int slots;         /* units encoded in lock-step (closed GOPs or streams)             */
+    int in_fmt;        /* B2_FMT_* layout of the raw input pictures                       */
+    int in_ring;       /* raw input pictures kept resident per slot (>= 1)                */
+    int merange;       /* 16 or 32: exhaustive search +-merange                           */
+    int qp;            /* constant QP, 10..51                                             */
+    int subpel;        /* 1: half + quarter-pel SATD refinement                           */
+    int intra_in_p;    /* 1: intra/inter decision in P frames                             */
+    int profile;       /* 1: record per-kernel CUDA-event timings (b2_engine_kernel_ms)   */
+} b2_engine_cfg_t;
+
+b2_engine_t *b2_engine_create(const b2_engine_cfg_t *cfg);      /* NULL on error */
+void b2_engine_destroy(b2_engine_t *e);
+
+/* tight byte size of one raw input picture in cfg.in_fmt */
+size_t b2_engine_input_bytes(const b2_engine_t *e);
+/* pinned host staging for (slot, ring position); fill it directly or through b2_engine_put_frame */
+uint8_t *b2_engine_host_input(b2_engine_t *e, int slot, int ring);
+/* copy a strided picture (plane pointers + strides as sws_scale takes them, av_encode.c:545) into
+ * the pinned staging of (slot, ring); the source may be freed on return (cf. av_encode.c:550) */
+int b2_engine_put_frame(b2_engine_t *e, int slot, int ring, const uint8_t *const src[4], const int stride[4]);
+/* async pinned-host -> device copy of ring position `ring` for slots [slot0, slot0+nslots) */
+int b2_engine_h2d(b2_engine_t *e, int slot0, int nslots, int ring);
+/* async: encode ring position `ring` of slots [0,nslots) as one frame each (B2_FRAME_I / B2_FRAME_P) */
+int b2_engine_encode(b2_engine_t *e, int frame_type, int nslots, int ring);
+/* async device -> pinned-host copy of the last encode's per-MB results for slots [0,nslots) */
+int b2_engine_d2h(b2_engine_t *e, int nslots);
+int b2_engine_sync(b2_engine_t *e);
+/* host views of the results fetched by the last b2_engine_d2h (valid until the next but one d2h) */
+const b2_mbinfo_t *b2_engine_info(b2_engine_t *e, int slot);
+const b2_mbcoef_t *b2_engine_coef(b2_engine_t *e, int slot);
+size_t b2_engine_result_bytes(const b2_engine_t *e);           /* D2H bytes per slot per frame */
+
+/* parity / debugging (synchronous): coded-size planes, tight layout */
+int b2_engine_get_recon(b2_engine_t *e, int slot, uint8_t *y, uint8_t *u, uint8_t *v);
+int b2_engine_get_cur(b2_engine_t *e, int slot, uint8_t *y, uint8_t *u, uint8_t *v);
+enum { B2_STAGE_MV_FULL = 0, B2_STAGE_COST_FULL, B2_STAGE_MV_QPEL, B2_STAGE_COST_INTER, B2_STAGE_COST_I16, B2_STAGE_COST_I4 };
+int b2_engine_get_stage(b2_engine_t *e, int slot, int what, void *out);   /* 4 bytes per MB */
+void b2_engine_geometry(const b2_engine_t *e, int *mbw, int *mbh, int *w16, int *h16);
+
+/* timing on the engine's compute stream (CUDA events) */
+int b2_engine_timer_start(b2_engine_t *e);
+int b2_engine_timer_stop(b2_engine_t *e, float *ms);            /* synchronises */
+/* cfg.profile: accumulated device ms and launch count per kernel since the last reset.
+ * which: 0 K0 convert, 1 K6 border(cur), 2 K1 full-pel, 3 K2 sub-pel, 4 K3 intra, 5 K5 decide+inter,
+ *        6 K7 intra recon, 7 K6 border(recon) */
+enum { B2_NKERNELS = 8 };
+int b2_engine_kernel_ms(b2_engine_t *e, int which, double *ms_total, long *launches);
+void b2_engine_profile_reset(b2_engine_t *e);
+long b2_engine_launch_count(const b2_engine_t *e);              /* kernels launched since creation */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -23,6 +23,8 @@ extern "C" {
 
 enum { B2_MB_P16x16 = 0, B2_MB_I16x16 = 1, B2_MB_I4x4 = 2 };
 enum { B2_FRAME_I = 0, B2_FRAME_P = 1 };
+/* raw input layouts accepted by the conversion kernel (the sws_scale source formats, av_encode.c:427) */
+enum { B2_FMT_YUV420P = 0, B2_FMT_NV12 = 1, B2_FMT_YUYV422 = 2, B2_FMT_UYVY422 = 3 };
 
 /* intra 16x16 modes (H.264 Table 8-4) */
 enum { B2_I16_V = 0, B2_I16_H = 1, B2_I16_DC = 2, B2_I16_PLANE = 3 };

@@ -271,3 +271,21 @@ def split_access_units(annexb: bytes):
         if (p[0] & 31) in (1, 5):
             aus.append(cur); cur = b""
     return aus
+
+
+FMT = {"yuv420p": 0, "nv12": 1, "yuyv422": 2, "uyvy422": 3}
+
+
+def convert_to_i420(fmt, w, h, planes):
+    """planes: list of 2-D uint8 arrays (their row length is the stride).  Returns (y,u,v)."""
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    planes = [np.ascontiguousarray(p, np.uint8) for p in planes]
+    y = np.zeros((h, w), np.uint8); u = np.zeros((ch, cw), np.uint8); v = np.zeros((ch, cw), np.uint8)
+    sp = (C.c_void_p * 4)(*([p.ctypes.data for p in planes] + [None] * (4 - len(planes))))
+    ss = (C.c_int * 4)(*([p.shape[1] for p in planes] + [0] * (4 - len(planes))))
+    dp = (C.c_void_p * 3)(y.ctypes.data, u.ctypes.data, v.ctypes.data)
+    ds = (C.c_int * 3)(w, cw, cw)
+    rc = lib().b2o_convert_to_i420(FMT[fmt], w, h, sp, ss, dp, ds)
+    if rc != 0:
+        raise ValueError("unsupported conversion")
+    return y, u, v

@@ -1,0 +1,77 @@
+"""Whole encode stage on the GPU (through the C-ABI engine, include/b2enc_engine.h) against the C
+oracle, frame by frame: converted/padded current planes (K0/K6), full-pel MVs and costs (K1), sub-pel
+MVs and costs (K2), intra costs and modes (K3), decisions, quantised levels, cbp (K5/K7) and the
+reconstructed planes must all be bit-identical."""
+import numpy as np
+import pytest
+from test_oracle_decode import smooth_seq
+
+pytestmark = pytest.mark.gpu
+
+INFO_FIELDS = ["mb_type", "mvx", "mvy", "i16_mode", "chroma_mode", "cbp", "i4_mode", "cost", "nnz_mask"]
+
+
+def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="yuv420p"):
+    """seqs: list (one per slot) of lists of (y,u,v) frames"""
+    S, T = len(seqs), len(seqs[0])
+    eng = b2.Engine(w, h, slots=S, fmt=fmt, ring=2, merange=R, qp=qp, subpel=subpel, intra_in_p=intra_in_p)
+    prm = oracle.Params(qp, R, subpel, intra_in_p)
+    prev = [None] * S; prev_mv = [None] * S
+    for t in range(T):
+        for s in range(S):
+            eng.put_frame(s, t % 2, list(seqs[s][t]))
+        eng.h2d(ring=t % 2)
+        ft = b2.FRAME_I if t == 0 else b2.FRAME_P
+        eng.encode(ft, ring=t % 2)
+        eng.d2h()
+        eng.sync()
+        for s in range(S):
+            cur = oracle.OFrame(w, h).load(*seqs[s][t]); rec = oracle.OFrame(w, h)
+            info_o, coef_o = oracle.encode_frame(prm, ft, cur, prev[s], rec, prev_mv[s])
+            cy, cu, cv = eng.cur(s)
+            assert np.array_equal(cy, cur.y) and np.array_equal(cu, cur.u) and np.array_equal(cv, cur.v), f"cur planes t={t} s={s}"
+            info_g, coef_g = eng.results(s)
+            if ft == b2.FRAME_P:
+                mvf_o, cf_o = oracle.me_fullpel(cur, prev[s], R, prev_mv[s], oracle.lib().b2o_lambda(qp))
+                assert np.array_equal(eng.stage(s, 0), mvf_o), f"K1 mv t={t} s={s}"
+                assert np.array_equal(eng.stage(s, 1), cf_o), f"K1 cost t={t} s={s}"
+            for f in INFO_FIELDS:
+                assert np.array_equal(info_g[f], info_o[f]), f"info.{f} t={t} s={s}: {np.argwhere(info_g[f] != info_o[f])[:5].tolist()}"
+            assert np.array_equal(coef_g["blk"], coef_o["blk"]), f"levels t={t} s={s}"
+            ry, ru, rv = eng.recon(s)
+            assert np.array_equal(ry, rec.y), f"recon Y t={t} s={s}"
+            assert np.array_equal(ru, rec.u) and np.array_equal(rv, rec.v), f"recon UV t={t} s={s}"
+            prev[s] = rec
+            prev_mv[s] = np.zeros(info_o.size, oracle.MV); prev_mv[s]["x"] = info_o["mvx"]; prev_mv[s]["y"] = info_o["mvy"]
+    eng.close()
+
+
+@pytest.mark.parametrize("w,h,qp,R,cut", [(176, 144, 26, 16, None), (320, 240, 32, 32, 2), (208, 160, 18, 16, 1),
+                                          (318, 242, 28, 16, 3), (64, 48, 45, 32, 1)])
+def test_engine_matches_oracle(oracle, b2, w, h, qp, R, cut):
+    seqs = [smooth_seq(w, h, 5, seed=qp, cut=cut)]
+    run_and_compare(oracle, b2, seqs, w, h, qp, R)
+
+
+def test_engine_lockstep_slots(oracle, b2):
+    """several GOPs/streams in lock-step, different content per slot"""
+    w, h = 192, 112
+    seqs = [smooth_seq(w, h, 4, seed=s, cut=(2 if s == 1 else None)) for s in range(3)]
+    seqs.append([oracle.synth_frame(w, h, t, 3) for t in range(4)])
+    run_and_compare(oracle, b2, seqs, w, h, 30, 16)
+
+
+def test_engine_fullpel_only_no_intra(oracle, b2):
+    w, h = 160, 96
+    seqs = [smooth_seq(w, h, 4, seed=9)]
+    run_and_compare(oracle, b2, seqs, w, h, 26, 16, subpel=0, intra_in_p=0)
+
+
+def test_engine_extreme_content(oracle, b2):
+    w, h = 64, 64
+    rng = np.random.default_rng(3)
+    noise = [((rng.integers(0, 2, (h, w)) * 255).astype(np.uint8), (rng.integers(0, 2, (h // 2, w // 2)) * 255).astype(np.uint8),
+              (rng.integers(0, 2, (h // 2, w // 2)) * 255).astype(np.uint8)) for _ in range(3)]
+    flat = [(np.full((h, w), 90, np.uint8), np.full((h // 2, w // 2), 128, np.uint8), np.full((h // 2, w // 2), 128, np.uint8))] * 3
+    for qp in (10, 51):
+        run_and_compare(oracle, b2, [noise, flat], w, h, qp, 16)

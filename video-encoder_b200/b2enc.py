@@ -73,3 +73,142 @@ def vabsdiff4_peak(device=0, outer=256, reps=5):
     if rate <= 0:
         raise RuntimeError("vabsdiff4 microbenchmark failed")
     return rate, ms.value
+
+
+# ---- engine binding (include/b2enc_engine.h) ----------------------------------------------------------
+FMT = {"yuv420p": 0, "nv12": 1, "yuyv422": 2, "uyvy422": 3}
+FRAME_I, FRAME_P = 0, 1
+KERNEL_NAMES = ["K0 convert", "K6 border(cur)", "K1 full-pel SAD", "K2 sub-pel SATD", "K3 intra analyse",
+                "K5 decide+inter recon", "K7 intra recon", "K6 border(recon)"]
+
+
+class EngineCfg(C.Structure):
+    _fields_ = [("device", C.c_int), ("width", C.c_int), ("height", C.c_int), ("slots", C.c_int), ("in_fmt", C.c_int),
+                ("in_ring", C.c_int), ("merange", C.c_int), ("qp", C.c_int), ("subpel", C.c_int), ("intra_in_p", C.c_int),
+                ("profile", C.c_int)]
+
+
+class Engine:
+    """One GPU's encode-stage engine: `slots` closed GOPs / streams advanced in lock-step."""
+
+    def __init__(self, width, height, slots=1, fmt="yuv420p", ring=1, merange=16, qp=26, subpel=1, intra_in_p=1,
+                 device=0, profile=0):
+        require_gpu()
+        L = lib()
+        L.b2_engine_create.restype = C.c_void_p
+        L.b2_engine_host_input.restype = C.c_void_p
+        L.b2_engine_info.restype = C.c_void_p; L.b2_engine_coef.restype = C.c_void_p
+        L.b2_engine_input_bytes.restype = C.c_size_t; L.b2_engine_result_bytes.restype = C.c_size_t
+        L.b2_engine_launch_count.restype = C.c_long
+        for fn in ("b2_engine_destroy", "b2_engine_input_bytes", "b2_engine_result_bytes", "b2_engine_sync",
+                   "b2_engine_timer_start", "b2_engine_profile_reset", "b2_engine_launch_count"):
+            getattr(L, fn).argtypes = [C.c_void_p]
+        L.b2_engine_host_input.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.b2_engine_put_frame.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.b2_engine_h2d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.b2_engine_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.b2_engine_d2h.argtypes = [C.c_void_p, C.c_int]
+        L.b2_engine_info.argtypes = [C.c_void_p, C.c_int]; L.b2_engine_coef.argtypes = [C.c_void_p, C.c_int]
+        L.b2_engine_get_recon.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2_engine_get_cur.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2_engine_get_stage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.b2_engine_geometry.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4
+        L.b2_engine_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.b2_engine_kernel_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long)]
+        self.L = L
+        self.cfg = EngineCfg(device, width, height, slots, FMT[fmt] if isinstance(fmt, str) else fmt, ring, merange, qp,
+                             subpel, intra_in_p, profile)
+        self.h = L.b2_engine_create(C.byref(self.cfg))
+        if not self.h:
+            raise RuntimeError("b2_engine_create failed")
+        g = [C.c_int() for _ in range(4)]
+        L.b2_engine_geometry(self.h, *[C.byref(x) for x in g])
+        self.mbw, self.mbh, self.w16, self.h16 = [x.value for x in g]
+        self.nmb = self.mbw * self.mbh
+        self.width, self.height, self.slots, self.ring = width, height, slots, ring
+        self.in_bytes = L.b2_engine_input_bytes(self.h)
+        self.result_bytes = L.b2_engine_result_bytes(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.b2_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise RuntimeError("%s failed (%d)" % (what, rc))
+
+    def host_input(self, slot, ring=0):
+        """numpy view of the pinned staging buffer of (slot, ring)"""
+        p = self.L.b2_engine_host_input(self.h, slot, ring)
+        return np.frombuffer((C.c_uint8 * self.in_bytes).from_address(p), np.uint8)
+
+    def put_frame(self, slot, ring, planes):
+        planes = [np.ascontiguousarray(p, np.uint8) for p in planes]
+        sp = (C.c_void_p * 4)(*([p.ctypes.data for p in planes] + [None] * (4 - len(planes))))
+        ss = (C.c_int * 4)(*([p.shape[1] for p in planes] + [0] * (4 - len(planes))))
+        self._ck(self.L.b2_engine_put_frame(self.h, slot, ring, sp, ss), "put_frame")
+
+    def h2d(self, slot0=0, nslots=None, ring=0):
+        self._ck(self.L.b2_engine_h2d(self.h, slot0, self.slots if nslots is None else nslots, ring), "h2d")
+
+    def encode(self, frame_type, nslots=None, ring=0):
+        self._ck(self.L.b2_engine_encode(self.h, frame_type, self.slots if nslots is None else nslots, ring), "encode")
+
+    def d2h(self, nslots=None):
+        self._ck(self.L.b2_engine_d2h(self.h, self.slots if nslots is None else nslots), "d2h")
+
+    def sync(self):
+        self._ck(self.L.b2_engine_sync(self.h), "sync")
+
+    def results(self, slot):
+        """(info, coef) numpy views of the last fetched results of `slot`"""
+        pi = self.L.b2_engine_info(self.h, slot); pc = self.L.b2_engine_coef(self.h, slot)
+        info = np.frombuffer((C.c_uint8 * (self.nmb * 32)).from_address(pi), MBINFO)
+        coef = np.frombuffer((C.c_uint8 * (self.nmb * 832)).from_address(pc), MBCOEF)
+        return info, coef
+
+    def _planes(self, fn, slot):
+        y = np.zeros((self.h16, self.w16), np.uint8)
+        u = np.zeros((self.h16 // 2, self.w16 // 2), np.uint8); v = np.zeros_like(u)
+        self._ck(fn(self.h, slot, _p(y), _p(u), _p(v)), "get planes")
+        return y, u, v
+
+    def recon(self, slot=0):
+        return self._planes(self.L.b2_engine_get_recon, slot)
+
+    def cur(self, slot=0):
+        return self._planes(self.L.b2_engine_get_cur, slot)
+
+    def stage(self, slot, what):
+        out = np.zeros(self.nmb, MV if what in (0, 2) else np.uint32)
+        self._ck(self.L.b2_engine_get_stage(self.h, slot, what, _p(out)), "get_stage")
+        return out
+
+    def timer_start(self):
+        self._ck(self.L.b2_engine_timer_start(self.h), "timer_start")
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._ck(self.L.b2_engine_timer_stop(self.h, C.byref(ms)), "timer_stop")
+        return ms.value
+
+    def kernel_ms(self):
+        out = {}
+        for i, n in enumerate(KERNEL_NAMES):
+            ms = C.c_double(0); cnt = C.c_long(0)
+            self._ck(self.L.b2_engine_kernel_ms(self.h, i, C.byref(ms), C.byref(cnt)), "kernel_ms")
+            out[n] = (ms.value, cnt.value)
+        return out
+
+    def profile_reset(self):
+        self.L.b2_engine_profile_reset(self.h)
+
+    def launch_count(self):
+        return self.L.b2_engine_launch_count(self.h)

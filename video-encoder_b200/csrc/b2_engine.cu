@@ -1,0 +1,433 @@
+// b2_engine.cu -- the encode-stage engine behind include/b2enc_engine.h: device memory layout,
+// streams/events (pinned host -> device ring -> kernels -> pinned host results, double buffered) and
+// the per-frame kernel schedule.  This is the "frame queue" row (a0) of SURVEY.md 8a: the
+// reference's strictly synchronous one-AVFrame/one-pic_in loop (av_encode.c:968-975) becomes
+// copy-in stream || compute stream || copy-out stream over `slots` lock-stepped GOPs/streams.
+//
+// HBM layout per engine (S = slots):
+//   raw input ring      [S][ring][in_bytes]              tight pictures as uploaded
+//   cur Y/U/V           [S][rows][pitch] / [S][rowsc][pitchc]   64/32-px replicated border
+//   recon Y/U/V  x2     same shape; ping-pong reference / reconstruction
+//   per-MB scratch      mv_full, cost_full, mv_qpel, cost_inter, cost_i16, cost_i4, prev_mv  [S][nmb]
+//   results x2          b2_mbinfo_t [S][nmb] (32 B) + b2_mbcoef_t [S][nmb] (832 B), ping-pong
+#include <string.h>
+#include <vector>
+#include "b2_common.cuh"
+#include "b2_internal.h"
+#include "../../include/b2enc_engine.h"
+
+int b2_lambda_for_qp(int qp)
+{
+    static const uint8_t tab[52] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 4,
+                                    5, 6, 6, 7, 8, 9, 10, 11, 13, 14, 16, 18, 20, 23, 25, 29, 32, 36, 40, 45, 51, 57,
+                                    64, 72, 81, 91};
+    return tab[qp < 0 ? 0 : (qp > 51 ? 51 : qp)];
+}
+
+struct ProfRec { int k; cudaEvent_t e0, e1; };
+
+struct b2_engine {
+    b2_engine_cfg_t cfg;
+    int w16, h16, mbw, mbh, nmb;
+    int pitch, rows, pitchc, rowsc;
+    size_t stride_y, stride_c, in_bytes, in_stride;
+    int lambda;
+    uint8_t *d_in = nullptr, *h_in = nullptr;
+    uint8_t *d_cur[3] = {}, *d_rec[2][3] = {};
+    int ref_idx = 0;                       // d_rec[ref_idx] holds the latest reconstruction
+    b2_mv_t *d_mvf = nullptr, *d_mvq = nullptr, *d_prev_mv = nullptr;
+    uint32_t *d_cost_full = nullptr, *d_cost_inter = nullptr, *d_c16 = nullptr, *d_c4 = nullptr;
+    b2_mbinfo_t *d_info[2] = {}, *h_info[2] = {};
+    b2_mbcoef_t *d_coef[2] = {}, *h_coef[2] = {};
+    int res_set = 0;                       // result set written by the most recent encode
+    int host_set = 0;                      // result set most recently copied to the host
+    CUtensorMap tm_cur, tm_ref[2];
+    cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr;
+    std::vector<cudaEvent_t> ev_h2d, ev_k0;
+    std::vector<char> h2d_pending;
+    cudaEvent_t ev_enc[2] = {}, ev_d2h[2] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+    bool d2h_used[2] = {false, false};
+    long launches = 0;
+    double k_ms[B2_NKERNELS] = {};
+    long k_n[B2_NKERNELS] = {};
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+#define ENG_OK(expr)                                                                                 \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            fprintf(stderr, "b2enc: CUDA error %s at %s:%d: %s\n", cudaGetErrorName(_e), __FILE__,   \
+                    __LINE__, cudaGetErrorString(_e));                                               \
+            return -1;                                                                               \
+        }                                                                                            \
+    } while (0)
+
+static size_t input_bytes(int fmt, int w, int h)
+{
+    const size_t cw = (w + 1) / 2, ch = (h + 1) / 2;
+    switch (fmt) {
+    case B2_FMT_YUV420P: return (size_t)w * h + 2 * cw * ch;
+    case B2_FMT_NV12: return (size_t)w * h + 2 * cw * ch;
+    case B2_FMT_YUYV422: case B2_FMT_UYVY422: return (size_t)2 * w * h;
+    default: return 0;
+    }
+}
+
+static int engine_alloc(b2_engine *e)
+{
+    const b2_engine_cfg_t &c = e->cfg;
+    const size_t S = c.slots;
+    ENG_OK(cudaMalloc(&e->d_in, e->in_stride * c.in_ring * S));
+    ENG_OK(cudaHostAlloc(&e->h_in, e->in_stride * c.in_ring * S, cudaHostAllocDefault));
+    for (int p = 0; p < 3; p++) {
+        const size_t sz = (p ? e->stride_c : e->stride_y) * S;
+        ENG_OK(cudaMalloc(&e->d_cur[p], sz));
+        ENG_OK(cudaMalloc(&e->d_rec[0][p], sz));
+        ENG_OK(cudaMalloc(&e->d_rec[1][p], sz));
+        ENG_OK(cudaMemset(e->d_cur[p], 0, sz));
+        ENG_OK(cudaMemset(e->d_rec[0][p], 0, sz));
+        ENG_OK(cudaMemset(e->d_rec[1][p], 0, sz));
+    }
+    const size_t n = (size_t)e->nmb * S;
+    ENG_OK(cudaMalloc(&e->d_mvf, n * 4)); ENG_OK(cudaMalloc(&e->d_mvq, n * 4)); ENG_OK(cudaMalloc(&e->d_prev_mv, n * 4));
+    ENG_OK(cudaMalloc(&e->d_cost_full, n * 4)); ENG_OK(cudaMalloc(&e->d_cost_inter, n * 4));
+    ENG_OK(cudaMalloc(&e->d_c16, n * 4)); ENG_OK(cudaMalloc(&e->d_c4, n * 4));
+    ENG_OK(cudaMemset(e->d_prev_mv, 0, n * 4)); ENG_OK(cudaMemset(e->d_mvf, 0, n * 4)); ENG_OK(cudaMemset(e->d_mvq, 0, n * 4));
+    ENG_OK(cudaMemset(e->d_cost_full, 0, n * 4)); ENG_OK(cudaMemset(e->d_cost_inter, 0, n * 4));
+    ENG_OK(cudaMemset(e->d_c16, 0, n * 4)); ENG_OK(cudaMemset(e->d_c4, 0, n * 4));
+    for (int s = 0; s < 2; s++) {
+        ENG_OK(cudaMalloc(&e->d_info[s], n * sizeof(b2_mbinfo_t)));
+        ENG_OK(cudaMalloc(&e->d_coef[s], n * sizeof(b2_mbcoef_t)));
+        ENG_OK(cudaHostAlloc(&e->h_info[s], n * sizeof(b2_mbinfo_t), cudaHostAllocDefault));
+        ENG_OK(cudaHostAlloc(&e->h_coef[s], n * sizeof(b2_mbcoef_t), cudaHostAllocDefault));
+        ENG_OK(cudaEventCreateWithFlags(&e->ev_enc[s], cudaEventDisableTiming));
+        ENG_OK(cudaEventCreateWithFlags(&e->ev_d2h[s], cudaEventDisableTiming));
+    }
+    ENG_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    ENG_OK(cudaStreamCreateWithFlags(&e->st_in, cudaStreamNonBlocking));
+    ENG_OK(cudaStreamCreateWithFlags(&e->st_out, cudaStreamNonBlocking));
+    e->ev_h2d.resize(c.in_ring); e->ev_k0.resize(c.in_ring); e->h2d_pending.assign(c.in_ring, 0);
+    for (int r = 0; r < c.in_ring; r++) {
+        ENG_OK(cudaEventCreateWithFlags(&e->ev_h2d[r], cudaEventDisableTiming));
+        ENG_OK(cudaEventCreateWithFlags(&e->ev_k0[r], cudaEventDisableTiming));
+    }
+    ENG_OK(cudaEventCreate(&e->ev_t0)); ENG_OK(cudaEventCreate(&e->ev_t1));
+    int bw, bh;
+    if (b2_k1_window_box(c.merange, &bw, &bh)) { fprintf(stderr, "b2enc: merange must be 16 or 32\n"); return -1; }
+    if (b2_make_plane_tmap(&e->tm_cur, e->d_cur[0], e->pitch, e->rows, c.slots, 128, 16)) return -1;
+    if (b2_make_plane_tmap(&e->tm_ref[0], e->d_rec[0][0], e->pitch, e->rows, c.slots, bw, bh)) return -1;
+    if (b2_make_plane_tmap(&e->tm_ref[1], e->d_rec[1][0], e->pitch, e->rows, c.slots, bw, bh)) return -1;
+    return 0;
+}
+
+extern "C" b2_engine_t *b2_engine_create(const b2_engine_cfg_t *cfg)
+{
+    if (!cfg || cfg->width < 16 || cfg->height < 16 || cfg->slots < 1 || cfg->in_ring < 1) {
+        fprintf(stderr, "b2enc: bad engine configuration\n");
+        return nullptr;
+    }
+    if (cfg->qp < 10 || cfg->qp > 51) { fprintf(stderr, "b2enc: qp must be in 10..51\n"); return nullptr; }
+    if (cfg->merange != 16 && cfg->merange != 32) { fprintf(stderr, "b2enc: merange must be 16 or 32\n"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        fprintf(stderr, "b2enc: no CUDA device; the encode stage has no CPU fallback\n");
+        return nullptr;
+    }
+    if (cudaSetDevice(cfg->device) != cudaSuccess) { fprintf(stderr, "b2enc: cannot select device %d\n", cfg->device); return nullptr; }
+    b2_engine *e = new b2_engine();
+    e->cfg = *cfg;
+    e->w16 = (cfg->width + 15) & ~15; e->h16 = (cfg->height + 15) & ~15;
+    e->mbw = e->w16 / 16; e->mbh = e->h16 / 16; e->nmb = e->mbw * e->mbh;
+    e->pitch = e->w16 + 2 * B2_PAD; e->rows = e->h16 + 2 * B2_PAD;
+    e->pitchc = (e->w16 / 2 + 2 * B2_PADC + 15) & ~15; e->rowsc = e->h16 / 2 + 2 * B2_PADC;
+    e->stride_y = (size_t)e->pitch * e->rows; e->stride_c = (size_t)e->pitchc * e->rowsc;
+    e->in_bytes = input_bytes(cfg->in_fmt, cfg->width, cfg->height);
+    if (!e->in_bytes) { fprintf(stderr, "b2enc: unsupported input format %d\n", cfg->in_fmt); delete e; return nullptr; }
+    e->in_stride = (e->in_bytes + 255) & ~(size_t)255;
+    e->lambda = b2_lambda_for_qp(cfg->qp);
+    if (engine_alloc(e)) { b2_engine_destroy(e); return nullptr; }
+    return e;
+}
+
+extern "C" void b2_engine_destroy(b2_engine_t *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    cudaFree(e->d_in); cudaFreeHost(e->h_in);
+    for (int p = 0; p < 3; p++) { cudaFree(e->d_cur[p]); cudaFree(e->d_rec[0][p]); cudaFree(e->d_rec[1][p]); }
+    cudaFree(e->d_mvf); cudaFree(e->d_mvq); cudaFree(e->d_prev_mv); cudaFree(e->d_cost_full); cudaFree(e->d_cost_inter);
+    cudaFree(e->d_c16); cudaFree(e->d_c4);
+    for (int s = 0; s < 2; s++) {
+        cudaFree(e->d_info[s]); cudaFree(e->d_coef[s]); cudaFreeHost(e->h_info[s]); cudaFreeHost(e->h_coef[s]);
+        if (e->ev_enc[s]) cudaEventDestroy(e->ev_enc[s]);
+        if (e->ev_d2h[s]) cudaEventDestroy(e->ev_d2h[s]);
+    }
+    for (auto ev : e->ev_h2d) cudaEventDestroy(ev);
+    for (auto ev : e->ev_k0) cudaEventDestroy(ev);
+    for (auto ev : e->ev_pool) cudaEventDestroy(ev);
+    for (auto &r : e->prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    if (e->ev_t0) cudaEventDestroy(e->ev_t0);
+    if (e->ev_t1) cudaEventDestroy(e->ev_t1);
+    if (e->st) cudaStreamDestroy(e->st);
+    if (e->st_in) cudaStreamDestroy(e->st_in);
+    if (e->st_out) cudaStreamDestroy(e->st_out);
+    delete e;
+}
+
+extern "C" size_t b2_engine_input_bytes(const b2_engine_t *e) { return e->in_bytes; }
+extern "C" size_t b2_engine_result_bytes(const b2_engine_t *e) { return (size_t)e->nmb * (sizeof(b2_mbinfo_t) + sizeof(b2_mbcoef_t)); }
+extern "C" void b2_engine_geometry(const b2_engine_t *e, int *mbw, int *mbh, int *w16, int *h16)
+{
+    if (mbw) *mbw = e->mbw; if (mbh) *mbh = e->mbh; if (w16) *w16 = e->w16; if (h16) *h16 = e->h16;
+}
+
+static inline size_t in_off(const b2_engine *e, int slot, int ring) { return ((size_t)slot * e->cfg.in_ring + ring) * e->in_stride; }
+
+extern "C" uint8_t *b2_engine_host_input(b2_engine_t *e, int slot, int ring)
+{
+    if (slot < 0 || slot >= e->cfg.slots || ring < 0 || ring >= e->cfg.in_ring) return nullptr;
+    return e->h_in + in_off(e, slot, ring);
+}
+
+extern "C" int b2_engine_put_frame(b2_engine_t *e, int slot, int ring, const uint8_t *const src[4], const int stride[4])
+{
+    uint8_t *dst = b2_engine_host_input(e, slot, ring);
+    if (!dst) { fprintf(stderr, "b2enc: put_frame: bad slot/ring\n"); return -1; }
+    const int w = e->cfg.width, h = e->cfg.height, cw = (w + 1) / 2, ch = (h + 1) / 2;
+    switch (e->cfg.in_fmt) {
+    case B2_FMT_YUV420P:
+        for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * w, src[0] + (size_t)y * stride[0], w);
+        dst += (size_t)w * h;
+        for (int y = 0; y < ch; y++) memcpy(dst + (size_t)y * cw, src[1] + (size_t)y * stride[1], cw);
+        dst += (size_t)cw * ch;
+        for (int y = 0; y < ch; y++) memcpy(dst + (size_t)y * cw, src[2] + (size_t)y * stride[2], cw);
+        break;
+    case B2_FMT_NV12:
+        for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * w, src[0] + (size_t)y * stride[0], w);
+        dst += (size_t)w * h;
+        for (int y = 0; y < ch; y++) memcpy(dst + (size_t)y * 2 * cw, src[1] + (size_t)y * stride[1], 2 * cw);
+        break;
+    default:
+        for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * 2 * w, src[0] + (size_t)y * stride[0], 2 * w);
+        break;
+    }
+    return 0;
+}
+
+extern "C" int b2_engine_h2d(b2_engine_t *e, int slot0, int nslots, int ring)
+{
+    if (slot0 < 0 || nslots < 1 || slot0 + nslots > e->cfg.slots || ring < 0 || ring >= e->cfg.in_ring) return -1;
+    cudaSetDevice(e->cfg.device);
+    // do not overwrite a ring entry that a previously issued K0 still has to read
+    ENG_OK(cudaStreamWaitEvent(e->st_in, e->ev_k0[ring], 0));
+    if (e->cfg.in_ring == 1) {
+        const size_t off = in_off(e, slot0, 0);
+        ENG_OK(cudaMemcpyAsync(e->d_in + off, e->h_in + off, e->in_stride * nslots, cudaMemcpyHostToDevice, e->st_in));
+    } else {
+        for (int s = slot0; s < slot0 + nslots; s++) {
+            const size_t off = in_off(e, s, ring);
+            ENG_OK(cudaMemcpyAsync(e->d_in + off, e->h_in + off, e->in_bytes, cudaMemcpyHostToDevice, e->st_in));
+        }
+    }
+    ENG_OK(cudaEventRecord(e->ev_h2d[ring], e->st_in));
+    e->h2d_pending[ring] = 1;
+    return 0;
+}
+
+static cudaEvent_t pool_event(b2_engine *e)
+{
+    if (!e->ev_pool.empty()) { cudaEvent_t ev = e->ev_pool.back(); e->ev_pool.pop_back(); return ev; }
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    return ev;
+}
+struct KScope {
+    b2_engine *e; int k; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    KScope(b2_engine *e_, int k_) : e(e_), k(k_)
+    {
+        e->launches++;
+        if (e->cfg.profile) { e0 = pool_event(e); e1 = pool_event(e); cudaEventRecord(e0, e->st); }
+    }
+    ~KScope() { if (e->cfg.profile) { cudaEventRecord(e1, e->st); e->prof_pending.push_back({k, e0, e1}); } }
+};
+static void prof_collect(b2_engine *e)
+{
+    for (auto &r : e->prof_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { e->k_ms[r.k] += ms; e->k_n[r.k]++; }
+        e->ev_pool.push_back(r.e0); e->ev_pool.push_back(r.e1);
+    }
+    e->prof_pending.clear();
+}
+
+extern "C" int b2_engine_encode(b2_engine_t *e, int frame_type, int nslots, int ring)
+{
+    if (nslots < 1 || nslots > e->cfg.slots || ring < 0 || ring >= e->cfg.in_ring) return -1;
+    cudaSetDevice(e->cfg.device);
+    const b2_engine_cfg_t &c = e->cfg;
+    const int is_p = frame_type == B2_FRAME_P;
+    const int do_intra = !is_p || c.intra_in_p;
+    const int set = e->res_set ^ 1;
+    if (e->h2d_pending[ring]) { ENG_OK(cudaStreamWaitEvent(e->st, e->ev_h2d[ring], 0)); e->h2d_pending[ring] = 0; }
+    if (e->d2h_used[set]) ENG_OK(cudaStreamWaitEvent(e->st, e->ev_d2h[set], 0));     // result set still being copied out
+    const uint8_t *cur[3] = {e->d_cur[0], e->d_cur[1], e->d_cur[2]};
+    const uint8_t *ref[3] = {e->d_rec[e->ref_idx][0], e->d_rec[e->ref_idx][1], e->d_rec[e->ref_idx][2]};
+    uint8_t *rec[3] = {e->d_rec[e->ref_idx ^ 1][0], e->d_rec[e->ref_idx ^ 1][1], e->d_rec[e->ref_idx ^ 1][2]};
+    const size_t n = (size_t)e->nmb * nslots;
+
+    {   // K0: raw picture -> padded planes (slots are `in_ring` pictures apart in the ring buffer)
+        KScope k(e, 0);
+        if (b2_launch_convert(c.in_fmt, e->d_in + (size_t)ring * e->in_stride, e->in_stride * c.in_ring, e->d_cur[0], e->d_cur[1],
+                              e->d_cur[2], e->pitch, e->pitchc, e->stride_y, e->stride_c, c.width, c.height, nslots, e->st))
+            return -1;
+    }
+    ENG_OK(cudaEventRecord(e->ev_k0[ring], e->st));
+    {
+        KScope k(e, 1);
+        if (b2_launch_extend_border(e->d_cur[0], e->pitch, e->rows, nslots, B2_PAD, e->w16, e->h16, e->st)) return -1;
+        if (b2_launch_extend_border(e->d_cur[1], e->pitchc, e->rowsc, nslots, B2_PADC, e->w16 / 2, e->h16 / 2, e->st)) return -1;
+        if (b2_launch_extend_border(e->d_cur[2], e->pitchc, e->rowsc, nslots, B2_PADC, e->w16 / 2, e->h16 / 2, e->st)) return -1;
+        e->launches += 2;
+    }
+    ENG_OK(cudaMemsetAsync(e->d_info[set], 0, n * sizeof(b2_mbinfo_t), e->st));
+    if (is_p) {
+        {
+            KScope k(e, 2);
+            if (b2_launch_me_fullpel(c.merange, &e->tm_cur, &e->tm_ref[e->ref_idx], e->mbw, e->mbh, nslots, e->d_prev_mv,
+                                     e->lambda, e->d_mvf, e->d_cost_full, e->st))
+                return -1;
+        }
+        {
+            KScope k(e, 3);
+            if (b2_launch_me_subpel(e->d_cur[0], ref[0], e->pitch, e->stride_y, e->mbw, e->mbh, nslots, e->d_mvf, e->d_prev_mv,
+                                    e->lambda, c.subpel, e->d_mvq, e->d_cost_inter, e->st))
+                return -1;
+        }
+    }
+    if (do_intra) {
+        KScope k(e, 4);
+        if (b2_launch_intra_analyse(e->d_cur[0], e->d_cur[1], e->d_cur[2], e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw,
+                                    e->mbh, nslots, e->lambda, e->d_info[set], e->d_c16, e->d_c4, e->st))
+            return -1;
+    }
+    {
+        KScope k(e, 5);
+        if (b2_launch_decide_inter(cur, ref, rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, nslots, is_p,
+                                   do_intra, c.qp, e->d_mvq, e->d_cost_inter, e->d_c16, e->d_c4, e->d_info[set], e->d_coef[set],
+                                   e->d_prev_mv, e->st))
+            return -1;
+    }
+    if (do_intra) {
+        KScope k(e, 6);
+        if (b2_launch_intra_recon(cur, rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, nslots, c.qp,
+                                  e->d_info[set], e->d_coef[set], e->st))
+            return -1;
+    }
+    {
+        KScope k(e, 7);
+        if (b2_launch_extend_border(rec[0], e->pitch, e->rows, nslots, B2_PAD, e->w16, e->h16, e->st)) return -1;
+        if (b2_launch_extend_border(rec[1], e->pitchc, e->rowsc, nslots, B2_PADC, e->w16 / 2, e->h16 / 2, e->st)) return -1;
+        if (b2_launch_extend_border(rec[2], e->pitchc, e->rowsc, nslots, B2_PADC, e->w16 / 2, e->h16 / 2, e->st)) return -1;
+        e->launches += 2;
+    }
+    ENG_OK(cudaEventRecord(e->ev_enc[set], e->st));
+    e->ref_idx ^= 1;
+    e->res_set = set;
+    return 0;
+}
+
+extern "C" int b2_engine_d2h(b2_engine_t *e, int nslots)
+{
+    if (nslots < 1 || nslots > e->cfg.slots) return -1;
+    cudaSetDevice(e->cfg.device);
+    const int set = e->res_set;
+    const size_t n = (size_t)e->nmb * nslots;
+    ENG_OK(cudaStreamWaitEvent(e->st_out, e->ev_enc[set], 0));
+    ENG_OK(cudaMemcpyAsync(e->h_info[set], e->d_info[set], n * sizeof(b2_mbinfo_t), cudaMemcpyDeviceToHost, e->st_out));
+    ENG_OK(cudaMemcpyAsync(e->h_coef[set], e->d_coef[set], n * sizeof(b2_mbcoef_t), cudaMemcpyDeviceToHost, e->st_out));
+    ENG_OK(cudaEventRecord(e->ev_d2h[set], e->st_out));
+    e->d2h_used[set] = true;
+    e->host_set = set;
+    return 0;
+}
+
+extern "C" int b2_engine_sync(b2_engine_t *e)
+{
+    cudaSetDevice(e->cfg.device);
+    ENG_OK(cudaStreamSynchronize(e->st_in));
+    ENG_OK(cudaStreamSynchronize(e->st));
+    ENG_OK(cudaStreamSynchronize(e->st_out));
+    prof_collect(e);
+    return 0;
+}
+
+extern "C" const b2_mbinfo_t *b2_engine_info(b2_engine_t *e, int slot) { return e->h_info[e->host_set] + (size_t)slot * e->nmb; }
+extern "C" const b2_mbcoef_t *b2_engine_coef(b2_engine_t *e, int slot) { return e->h_coef[e->host_set] + (size_t)slot * e->nmb; }
+
+static int get_planes(b2_engine *e, uint8_t *const src[3], int slot, uint8_t *y, uint8_t *u, uint8_t *v)
+{
+    if (slot < 0 || slot >= e->cfg.slots) return -1;
+    cudaSetDevice(e->cfg.device);
+    if (b2_engine_sync(e)) return -1;
+    uint8_t *dst[3] = {y, u, v};
+    for (int p = 0; p < 3; p++) {
+        if (!dst[p]) continue;
+        const int pitch = p ? e->pitchc : e->pitch, pad = p ? B2_PADC : B2_PAD, w = p ? e->w16 / 2 : e->w16, h = p ? e->h16 / 2 : e->h16;
+        const uint8_t *s = src[p] + (size_t)slot * (p ? e->stride_c : e->stride_y) + (size_t)pad * pitch + pad;
+        ENG_OK(cudaMemcpy2D(dst[p], w, s, pitch, w, h, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+extern "C" int b2_engine_get_recon(b2_engine_t *e, int slot, uint8_t *y, uint8_t *u, uint8_t *v)
+{
+    return get_planes(e, e->d_rec[e->ref_idx], slot, y, u, v);
+}
+extern "C" int b2_engine_get_cur(b2_engine_t *e, int slot, uint8_t *y, uint8_t *u, uint8_t *v)
+{
+    return get_planes(e, e->d_cur, slot, y, u, v);
+}
+extern "C" int b2_engine_get_stage(b2_engine_t *e, int slot, int what, void *out)
+{
+    if (slot < 0 || slot >= e->cfg.slots) return -1;
+    if (b2_engine_sync(e)) return -1;
+    const void *src = nullptr;
+    switch (what) {
+    case B2_STAGE_MV_FULL: src = e->d_mvf; break;
+    case B2_STAGE_COST_FULL: src = e->d_cost_full; break;
+    case B2_STAGE_MV_QPEL: src = e->d_mvq; break;
+    case B2_STAGE_COST_INTER: src = e->d_cost_inter; break;
+    case B2_STAGE_COST_I16: src = e->d_c16; break;
+    case B2_STAGE_COST_I4: src = e->d_c4; break;
+    default: return -1;
+    }
+    ENG_OK(cudaMemcpy(out, (const uint8_t *)src + (size_t)slot * e->nmb * 4, (size_t)e->nmb * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int b2_engine_timer_start(b2_engine_t *e) { cudaSetDevice(e->cfg.device); ENG_OK(cudaEventRecord(e->ev_t0, e->st)); return 0; }
+extern "C" int b2_engine_timer_stop(b2_engine_t *e, float *ms)
+{
+    cudaSetDevice(e->cfg.device);
+    ENG_OK(cudaEventRecord(e->ev_t1, e->st));
+    ENG_OK(cudaEventSynchronize(e->ev_t1));
+    ENG_OK(cudaEventElapsedTime(ms, e->ev_t0, e->ev_t1));
+    return 0;
+}
+extern "C" int b2_engine_kernel_ms(b2_engine_t *e, int which, double *ms_total, long *launches)
+{
+    if (which < 0 || which >= B2_NKERNELS) return -1;
+    if (b2_engine_sync(e)) return -1;
+    if (ms_total) *ms_total = e->k_ms[which];
+    if (launches) *launches = e->k_n[which];
+    return 0;
+}
+extern "C" void b2_engine_profile_reset(b2_engine_t *e)
+{
+    b2_engine_sync(e);
+    for (int i = 0; i < B2_NKERNELS; i++) { e->k_ms[i] = 0; e->k_n[i] = 0; }
+}
+extern "C" long b2_engine_launch_count(const b2_engine_t *e) { return e->launches; }

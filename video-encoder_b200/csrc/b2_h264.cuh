@@ -1,0 +1,357 @@
+// b2_h264.cuh -- per-thread device building blocks of the H.264 arithmetic used by K2/K3/K5/K7.
+// One thread owns one 4x4 block in registers; warps cooperate through shuffles.
+// Normative pieces follow ITU-T H.264 (8.3 intra prediction, 8.4.2.2 interpolation, 8.5 transform
+// and scaling); encoder-side pieces (forward DCT, dead-zone quantiser, SATD) follow the frozen
+// definitions in oracle/ (SURVEY.md Appendix A).  In the reference all of it is inside
+// x264_encoder_encode (av_encode.c:970).
+#pragma once
+#include "b2_common.cuh"
+
+namespace b2 {
+
+__device__ __constant__ uint16_t c_quant_mf[6][3] = {{13107, 8066, 5243}, {11916, 7490, 4660}, {10082, 6554, 4194},
+                                                     {9362, 5825, 3647},  {8192, 5243, 3355},  {7282, 4559, 2893}};
+__device__ __constant__ uint8_t c_dequant_v[6][3] = {{10, 13, 16}, {11, 14, 18}, {13, 16, 20},
+                                                     {14, 18, 23}, {16, 20, 25}, {18, 23, 29}};
+__device__ __constant__ uint8_t c_zigzag[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+__device__ __constant__ uint8_t c_chroma_qp[22] = {29, 30, 31, 32, 32, 33, 34, 34, 35, 35, 36,
+                                                   36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39};
+
+// 4x4 block index (z order) <-> position in units of 4 pixels
+__device__ __forceinline__ int blk_x(int b) { return (b & 1) | ((b >> 1) & 2); }
+__device__ __forceinline__ int blk_y(int b) { return ((b >> 1) & 1) | ((b >> 2) & 2); }
+__device__ __forceinline__ int chroma_qp(int qp) { return qp < 30 ? qp : c_chroma_qp[qp - 30]; }
+
+struct QParams {
+    int qbits, f, mf[3];        // quantiser
+    int ls[3], s;               // dequantiser: LevelScale = 16*V, s = qp/6
+};
+__device__ __forceinline__ QParams make_qparams(int qp, bool intra)
+{
+    QParams q;
+    q.qbits = 15 + qp / 6;
+    q.f = ((1 << q.qbits) * (intra ? 21 : 11)) >> 6;
+    q.s = qp / 6;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { q.mf[i] = c_quant_mf[qp % 6][i]; q.ls[i] = 16 * c_dequant_v[qp % 6][i]; }
+    return q;
+}
+// position class of raster index i: 0 = (even,even), 2 = (odd,odd), 1 otherwise
+__device__ __forceinline__ constexpr int pos_class(int i)
+{
+    return (((i & 1) && ((i >> 2) & 1)) ? 2 : (((i | (i >> 2)) & 1) ? 1 : 0));
+}
+
+// ---- transforms on a register-resident 4x4 (raster order) ------------------------------------------
+__device__ __forceinline__ void dct4x4(int d[16])
+{
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        int s03 = d[y * 4 + 0] + d[y * 4 + 3], d03 = d[y * 4 + 0] - d[y * 4 + 3];
+        int s12 = d[y * 4 + 1] + d[y * 4 + 2], d12 = d[y * 4 + 1] - d[y * 4 + 2];
+        d[y * 4 + 0] = s03 + s12; d[y * 4 + 1] = 2 * d03 + d12; d[y * 4 + 2] = s03 - s12; d[y * 4 + 3] = d03 - 2 * d12;
+    }
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+        int s03 = d[x] + d[12 + x], d03 = d[x] - d[12 + x];
+        int s12 = d[4 + x] + d[8 + x], d12 = d[4 + x] - d[8 + x];
+        d[x] = s03 + s12; d[4 + x] = 2 * d03 + d12; d[8 + x] = s03 - s12; d[12 + x] = d03 - 2 * d12;
+    }
+}
+
+// normative inverse (8.5.12.2): rows, then columns, then (x+32)>>6.  In place: w -> residual.
+__device__ __forceinline__ void idct4x4(int w[16])
+{
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        int e0 = w[y * 4 + 0] + w[y * 4 + 2], e1 = w[y * 4 + 0] - w[y * 4 + 2];
+        int e2 = (w[y * 4 + 1] >> 1) - w[y * 4 + 3], e3 = w[y * 4 + 1] + (w[y * 4 + 3] >> 1);
+        w[y * 4 + 0] = e0 + e3; w[y * 4 + 1] = e1 + e2; w[y * 4 + 2] = e1 - e2; w[y * 4 + 3] = e0 - e3;
+    }
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+        int e0 = w[x] + w[8 + x], e1 = w[x] - w[8 + x];
+        int e2 = (w[4 + x] >> 1) - w[12 + x], e3 = w[4 + x] + (w[12 + x] >> 1);
+        w[x] = (e0 + e3 + 32) >> 6; w[4 + x] = (e1 + e2 + 32) >> 6;
+        w[8 + x] = (e1 - e2 + 32) >> 6; w[12 + x] = (e0 - e3 + 32) >> 6;
+    }
+}
+
+// dead-zone quantiser; z raster; returns number of non-zero levels
+__device__ __forceinline__ int quant4x4(const int w[16], int z[16], const QParams &q, bool skip_dc)
+{
+    int nnz = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if (i == 0 && skip_dc) { z[0] = 0; continue; }
+        int a = abs(w[i]);
+        int v = (int)(((long long)a * q.mf[pos_class(i)] + q.f) >> q.qbits);
+        z[i] = w[i] < 0 ? -v : v;
+        nnz += v != 0;
+    }
+    return nnz;
+}
+__device__ __forceinline__ int quant_dc(int x, const QParams &q)
+{
+    int a = abs(x);
+    int v = (int)(((long long)a * q.mf[0] + 2 * q.f) >> (q.qbits + 1));
+    return x < 0 ? -v : v;
+}
+// normative scaling (8.5.12.1), flat matrices; w[0] untouched when skip_dc
+__device__ __forceinline__ void dequant4x4(const int z[16], int w[16], const QParams &q, bool skip_dc)
+{
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if (i == 0 && skip_dc) continue;
+        int ls = q.ls[pos_class(i)];
+        w[i] = q.s >= 4 ? (z[i] * ls) << (q.s - 4) : (z[i] * ls + (1 << (3 - q.s))) >> (4 - q.s);
+    }
+}
+
+// SATD of a 4x4 difference block: (sum |H d H^T|) >> 1
+__device__ __forceinline__ uint32_t satd4x4(const int d[16])
+{
+    int t[16];
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        int s01 = d[y * 4 + 0] + d[y * 4 + 1], d01 = d[y * 4 + 0] - d[y * 4 + 1];
+        int s23 = d[y * 4 + 2] + d[y * 4 + 3], d23 = d[y * 4 + 2] - d[y * 4 + 3];
+        t[y * 4 + 0] = s01 + s23; t[y * 4 + 1] = s01 - s23; t[y * 4 + 2] = d01 - d23; t[y * 4 + 3] = d01 + d23;
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+        int s01 = t[x] + t[4 + x], d01 = t[x] - t[4 + x];
+        int s23 = t[8 + x] + t[12 + x], d23 = t[8 + x] - t[12 + x];
+        s += abs(s01 + s23) + abs(s01 - s23) + abs(d01 - d23) + abs(d01 + d23);
+    }
+    return s >> 1;
+}
+
+// sign (+1/-1) of entry [v][u] of H4 = rows ++++ / ++-- / +--+ / +-+-
+__device__ __forceinline__ int h4_sign(int v, int u)
+{
+    // bit u of row mask v is 1 where the entry is negative
+    const unsigned masks = 0x0u | (0xCu << 4) | (0x6u << 8) | (0xAu << 12);
+    return ((masks >> (4 * v + u)) & 1u) ? -1 : 1;
+}
+
+// store 16 raster levels of one block in zig-zag order as int16 (two 16-byte stores)
+__device__ __forceinline__ void store_levels_zigzag(int16_t *dst, const int z[16])
+{
+    uint32_t p[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        // c_zigzag is compile-time here
+        constexpr int zz[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+        p[i] = ((uint32_t)(uint16_t)(int16_t)z[zz[2 * i]]) | ((uint32_t)(uint16_t)(int16_t)z[zz[2 * i + 1]] << 16);
+    }
+    uint4 *d4 = (uint4 *)dst;
+    d4[0] = make_uint4(p[0], p[1], p[2], p[3]);
+    d4[1] = make_uint4(p[4], p[5], p[6], p[7]);
+}
+
+// ---- intra 4x4 prediction (8.3.1.2); T[-1..7], L[-1..3] passed as pointers offset by one ---------
+// avail bits: 1 left, 2 top, 4 top-left, 8 top-right (same as the oracle's B2O_AV_*)
+__device__ __forceinline__ bool i4_mode_ok(int mode, int avail)
+{
+    switch (mode) {
+    case B2_I4_V: case B2_I4_DDL: case B2_I4_VL: return (avail & 2) != 0;
+    case B2_I4_H: case B2_I4_HU: return (avail & 1) != 0;
+    case B2_I4_DC: return true;
+    default: return (avail & 7) == 7;
+    }
+}
+
+// E layout: E[0]=M (top-left), E[1..8]=T0..T7, E[9..12]=L0..L3, all already substituted
+// (128 for unavailable, T3 replicated when top-right is missing)
+__device__ __forceinline__ void pred4x4(int mode, const int E[13], int avail, int pred[16])
+{
+    const int *T = E + 1, *L = E + 9;
+    const int M = E[0];
+#define B2F3(a, b, c) (((a) + 2 * (b) + (c) + 2) >> 2)
+#define B2F2(a, b) (((a) + (b) + 1) >> 1)
+    switch (mode) {
+    case B2_I4_V:
+#pragma unroll
+        for (int i = 0; i < 16; i++) pred[i] = T[i & 3];
+        break;
+    case B2_I4_H:
+#pragma unroll
+        for (int i = 0; i < 16; i++) pred[i] = L[i >> 2];
+        break;
+    case B2_I4_DC: {
+        const bool hasT = avail & 2, hasL = avail & 1;
+        int s = 0;
+        if (hasT) s += T[0] + T[1] + T[2] + T[3];
+        if (hasL) s += L[0] + L[1] + L[2] + L[3];
+        const int dc = (hasT && hasL) ? (s + 4) >> 3 : (hasT || hasL) ? (s + 2) >> 2 : 128;
+#pragma unroll
+        for (int i = 0; i < 16; i++) pred[i] = dc;
+        break;
+    }
+    case B2_I4_DDL: {
+        int d[7];
+#pragma unroll
+        for (int k = 0; k < 6; k++) d[k] = B2F3(T[k], T[k + 1], T[k + 2]);
+        d[6] = (T[6] + 3 * T[7] + 2) >> 2;
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) pred[y * 4 + x] = d[x + y];
+        break;
+    }
+    case B2_I4_DDR: {
+        // diagonal index k = x - y + 3 in 0..6 over the edge sequence L3 L2 L1 L0 M T0 T1 T2 T3
+        const int e[9] = {L[3], L[2], L[1], L[0], M, T[0], T[1], T[2], T[3]};
+        int d[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) d[k] = B2F3(e[k], e[k + 1], e[k + 2]);
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) pred[y * 4 + x] = d[x - y + 3];
+        break;
+    }
+    case B2_I4_VR: {
+        const int e[9] = {L[3], L[2], L[1], L[0], M, T[0], T[1], T[2], T[3]};
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const int z = 2 * x - y;
+                int v;
+                if (z >= 0 && !(z & 1)) v = B2F2(e[4 + x - (y >> 1)], e[5 + x - (y >> 1)]);
+                else if (z >= 0) v = B2F3(e[3 + x - (y >> 1)], e[4 + x - (y >> 1)], e[5 + x - (y >> 1)]);
+                else if (z == -1) v = B2F3(L[0], M, T[0]);
+                else v = B2F3(e[4 - y], e[5 - y], e[6 - y]);      // L[y-1], L[y-2], L[y-3]
+                pred[y * 4 + x] = v;
+            }
+        break;
+    }
+    case B2_I4_HD: {
+        const int e[9] = {L[3], L[2], L[1], L[0], M, T[0], T[1], T[2], T[3]};
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const int z = 2 * y - x;
+                int v;
+                if (z >= 0 && !(z & 1)) v = B2F2(e[4 - (y - (x >> 1))], e[3 - (y - (x >> 1))]);   // L[y'-1], L[y']
+                else if (z >= 0) v = B2F3(e[5 - (y - (x >> 1))], e[4 - (y - (x >> 1))], e[3 - (y - (x >> 1))]);
+                else if (z == -1) v = B2F3(L[0], M, T[0]);
+                else v = B2F3(e[4 + x], e[3 + x], e[2 + x]);      // T[x-1], T[x-2], T[x-3]
+                pred[y * 4 + x] = v;
+            }
+        break;
+    }
+    case B2_I4_VL:
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const int k = x + (y >> 1);
+                pred[y * 4 + x] = (y & 1) ? B2F3(T[k], T[k + 1], T[k + 2]) : B2F2(T[k], T[k + 1]);
+            }
+        break;
+    default:   // HU
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const int z = x + 2 * y, k = y + (x >> 1);
+                int v;
+                if (z > 5) v = L[3];
+                else if (z == 5) v = (L[2] + 3 * L[3] + 2) >> 2;
+                else if (z & 1) v = B2F3(L[k], L[k + 1], L[k + 2]);
+                else v = B2F2(L[k], L[k + 1]);
+                pred[y * 4 + x] = v;
+            }
+        break;
+    }
+#undef B2F3
+#undef B2F2
+}
+
+// MB-level neighbour availability (one slice per frame: geometric)
+__device__ __forceinline__ int mb_avail(int mbx, int mby, int mbw)
+{
+    int a = 0;
+    if (mbx > 0) a |= 1;
+    if (mby > 0) a |= 2;
+    if (mbx > 0 && mby > 0) a |= 4;
+    if (mby > 0 && mbx < mbw - 1) a |= 8;
+    return a;
+}
+// availability of 4x4 block b (z order) given the MB's availability
+__device__ __forceinline__ int blk_avail(int b, int mba)
+{
+    const int bx = blk_x(b), by = blk_y(b);
+    int a = 0;
+    if (bx > 0 || (mba & 1)) a |= 1;
+    if (by > 0 || (mba & 2)) a |= 2;
+    if ((bx > 0 && by > 0) || (bx > 0 && by == 0 && (mba & 2)) || (bx == 0 && by > 0 && (mba & 1)) ||
+        (bx == 0 && by == 0 && (mba & 4)))
+        a |= 4;
+    if (by == 0) {
+        if (bx < 3 ? (mba & 2) : (mba & 8)) a |= 8;
+    } else if (bx < 3 && b != 3 && b != 11 && b != 7 && b != 13 && b != 15) {
+        a |= 8;
+    }
+    return a;
+}
+
+// gather the 13 edge samples of a 4x4 block from a plane (p -> block's top-left pixel)
+__device__ __forceinline__ void load_edge4x4(const uint8_t *p, int pitch, int avail, int E[13])
+{
+    const uint8_t *top = p - pitch;
+    E[0] = (avail & 4) ? top[-1] : 128;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        E[1 + i] = (avail & 2) ? top[i] : 128;
+        E[9 + i] = (avail & 1) ? p[i * pitch - 1] : 128;
+    }
+#pragma unroll
+    for (int i = 4; i < 8; i++) E[1 + i] = (avail & 8) ? top[i] : E[4];
+}
+
+// ---- luma quarter-pel sample (8.4.2.2.1) straight from a plane ------------------------------------
+__device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
+__device__ __forceinline__ int hb1(const uint8_t *q) { return tap6(q[-2], q[-1], q[0], q[1], q[2], q[3]); }
+__device__ __forceinline__ int vh1(const uint8_t *q, int p)
+{
+    return tap6(q[-2 * p], q[-p], q[0], q[p], q[2 * p], q[3 * p]);
+}
+__device__ __forceinline__ int half_b(const uint8_t *q) { return b2_clip255((hb1(q) + 16) >> 5); }
+__device__ __forceinline__ int half_h(const uint8_t *q, int p) { return b2_clip255((vh1(q, p) + 16) >> 5); }
+__device__ __forceinline__ int half_j(const uint8_t *q, int p)
+{
+    int j1 = tap6(hb1(q - 2 * p), hb1(q - p), hb1(q), hb1(q + p), hb1(q + 2 * p), hb1(q + 3 * p));
+    return b2_clip255((j1 + 512) >> 10);
+}
+// q -> integer sample G; (fx,fy) quarter-pel fraction
+__device__ __forceinline__ int qpel_sample(const uint8_t *q, int p, int fx, int fy)
+{
+#define B2AVG(a, b) (((a) + (b) + 1) >> 1)
+    switch (fy * 4 + fx) {
+    case 0: return q[0];
+    case 1: return B2AVG(q[0], half_b(q));
+    case 2: return half_b(q);
+    case 3: return B2AVG(q[1], half_b(q));
+    case 4: return B2AVG(q[0], half_h(q, p));
+    case 5: return B2AVG(half_b(q), half_h(q, p));
+    case 6: return B2AVG(half_b(q), half_j(q, p));
+    case 7: return B2AVG(half_b(q), half_h(q + 1, p));
+    case 8: return half_h(q, p);
+    case 9: return B2AVG(half_h(q, p), half_j(q, p));
+    case 10: return half_j(q, p);
+    case 11: return B2AVG(half_j(q, p), half_h(q + 1, p));
+    case 12: return B2AVG(q[p], half_h(q, p));
+    case 13: return B2AVG(half_h(q, p), half_b(q + p));
+    case 14: return B2AVG(half_j(q, p), half_b(q + p));
+    default: return B2AVG(half_h(q + 1, p), half_b(q + p));
+    }
+#undef B2AVG
+}
+
+}  // namespace b2

@@ -1,0 +1,199 @@
+// k3_intra_analyse.cu -- K3: intra mode analysis on SOURCE pixels (I16x16: 4 modes, I4x4: 9 modes per
+// block, chroma 8x8: 4 modes), SATD + lambda*bits costs.
+//
+// Replaces x264's intra analysis (behind x264_encoder_encode, av_encode.c:970); bit-exact against
+// oracle/b2o_intra.c:b2o_intra_analyse.  Because predictions are built from source neighbours, every
+// macroblock and every 4x4 block is independent: 16 threads per MB, one per
+// 4x4 block, 16-lane shuffle reductions for the MB-level sums.
+// Bound: integer ALU / L1; algorithmic bytes = 1.5*W*H source read + 32 B/MB written.
+#include "b2_h264.cuh"
+
+namespace {
+
+constexpr int K3_THREADS = 128;                 // 8 macroblocks per CTA
+
+__device__ __forceinline__ int sum16(int v)      // sum over the 16-lane group
+{
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);
+    return v;
+}
+
+__global__ void __launch_bounds__(K3_THREADS)
+k3_intra_analyse_kernel(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur_u,
+                        const uint8_t *__restrict__ cur_v, int pitch, int pitchc, size_t stride_y, size_t stride_c,
+                        int mbw, int mbh, int nmb_total, int lambda, b2_mbinfo_t *__restrict__ info,
+                        uint32_t *__restrict__ cost_i16, uint32_t *__restrict__ cost_i4)
+{
+    const int gt = blockIdx.x * K3_THREADS + threadIdx.x;
+    int mbi = gt >> 4;                            // global MB index over all frames
+    const int b = gt & 15;                        // 4x4 block (z order) owned by this lane
+    const bool valid = mbi < nmb_total;
+    if (!valid) mbi = nmb_total - 1;              // keep the lane in the shuffles
+    const int per_frame = mbw * mbh;
+    const int frame = mbi / per_frame, r = mbi - frame * per_frame;
+    const int mby = r / mbw, mbx = r - mby * mbw;
+    const int mba = b2::mb_avail(mbx, mby, mbw);
+    const int bx = b2::blk_x(b) * 4, by = b2::blk_y(b) * 4;
+
+    const uint8_t *sy = cur_y + frame * stride_y + (size_t)(B2_PAD + mby * 16) * pitch + B2_PAD + mbx * 16;
+    const uint8_t *sb = sy + (size_t)by * pitch + bx;
+
+    int src[16];
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        uint32_t w = *(const uint32_t *)(sb + (size_t)y * pitch);
+#pragma unroll
+        for (int x = 0; x < 4; x++) src[y * 4 + x] = (w >> (8 * x)) & 255;
+    }
+
+    // ---- I4x4: 9 modes on this lane's block --------------------------------------------------------
+    uint32_t best4 = 0xffffffffu; int mode4 = B2_I4_DC;
+    {
+        const int ba = b2::blk_avail(b, mba);
+        int E[13];
+        b2::load_edge4x4(sb, pitch, ba, E);
+#pragma unroll
+        for (int m = 0; m < 9; m++) {
+            if (!b2::i4_mode_ok(m, ba)) continue;
+            int pred[16], d[16];
+            b2::pred4x4(m, E, ba, pred);
+#pragma unroll
+            for (int i = 0; i < 16; i++) d[i] = src[i] - pred[i];
+            uint32_t c = b2::satd4x4(d) + (uint32_t)(lambda * (m == B2_I4_DC ? 1 : 4));
+            if (c < best4) { best4 = c; mode4 = m; }
+        }
+    }
+    const uint32_t sum4 = (uint32_t)sum16((int)best4) + (uint32_t)(lambda * 24);
+
+    // ---- I16x16: lane i holds top[i] and left[i] ----------------------------------------------------
+    const int lane16 = b;                        // 0..15 inside the group (group = 16 consecutive lanes)
+    const int grp_base = (threadIdx.x & 31) & 16;
+    const bool hasT = mba & 2, hasL = mba & 1;
+    const int topv = hasT ? sy[-(ptrdiff_t)pitch + lane16] : 0;
+    const int leftv = hasL ? sy[(size_t)lane16 * pitch - 1] : 0;
+    const int tlv = (mba & 4) ? sy[-(ptrdiff_t)pitch - 1] : 0;
+    uint32_t best16 = 0xffffffffu; int mode16 = B2_I16_DC;
+    {
+        // per-lane copies of the 4 top / 4 left samples this block needs
+        int t4[4], l4[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            t4[i] = __shfl_sync(0xffffffffu, topv, grp_base + bx + i);
+            l4[i] = __shfl_sync(0xffffffffu, leftv, grp_base + by + i);
+        }
+        const int sumT = sum16(topv), sumL = sum16(leftv);
+        // plane parameters: H = sum_{i<8} (i+1)(top[8+i]-top[6-i]) with top[-1] = top-left
+        int hterm = 0, vterm = 0;
+        {
+            const int i = lane16 & 7;
+            const int ta = __shfl_sync(0xffffffffu, topv, grp_base + 8 + i);
+            const int tb = __shfl_sync(0xffffffffu, topv, grp_base + ((6 - i) & 15));
+            const int la = __shfl_sync(0xffffffffu, leftv, grp_base + 8 + i);
+            const int lb = __shfl_sync(0xffffffffu, leftv, grp_base + ((6 - i) & 15));
+            if (lane16 < 8) {
+                hterm = (i + 1) * (ta - (i == 7 ? tlv : tb));
+                vterm = (i + 1) * (la - (i == 7 ? tlv : lb));
+            }
+        }
+        const int Hs = sum16(hterm), Vs = sum16(vterm);
+        const int t15 = __shfl_sync(0xffffffffu, topv, grp_base + 15), l15 = __shfl_sync(0xffffffffu, leftv, grp_base + 15);
+        const int pa = 16 * (l15 + t15), pb = (5 * Hs + 32) >> 6, pc = (5 * Vs + 32) >> 6;
+        const int dc = (hasT && hasL) ? (sumT + sumL + 16) >> 5 : (hasT || hasL) ? (sumT + sumL + 8) >> 4 : 128;
+        const int ue_bits[4] = {1, 3, 3, 5};
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const bool ok = m == B2_I16_V ? hasT : m == B2_I16_H ? hasL : m == B2_I16_DC ? true : (mba & 7) == 7;
+            int d[16];
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    int p;
+                    if (m == B2_I16_V) p = t4[x];
+                    else if (m == B2_I16_H) p = l4[y];
+                    else if (m == B2_I16_DC) p = dc;
+                    else p = b2_clip255((pa + pb * (bx + x - 7) + pc * (by + y - 7) + 16) >> 5);
+                    d[y * 4 + x] = src[y * 4 + x] - p;
+                }
+            const uint32_t c = (uint32_t)sum16((int)b2::satd4x4(d)) + (uint32_t)(lambda * ue_bits[m]);
+            if (ok && c < best16) { best16 = c; mode16 = m; }
+        }
+    }
+
+    // ---- chroma 8x8: lanes 0..7 own (plane, 4x4 block) ------------------------------------------------
+    uint32_t bestc = 0xffffffffu; int modec = B2_IC_DC;
+    {
+        const int pl = (b >> 2) & 1, k = b & 3, cbx = (k & 1) * 4, cby = (k >> 1) * 4;
+        const uint8_t *cp = (pl ? cur_v : cur_u) + frame * stride_c + (size_t)(B2_PADC + mby * 8) * pitchc + B2_PADC + mbx * 8;
+        int top[8], left[8], tl = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { top[i] = hasT ? cp[-(ptrdiff_t)pitchc + i] : 0; left[i] = hasL ? cp[(size_t)i * pitchc - 1] : 0; }
+        if (mba & 4) tl = cp[-(ptrdiff_t)pitchc - 1];
+        int csrc[16];
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            uint32_t w = *(const uint32_t *)(cp + (size_t)(cby + y) * pitchc + cbx);
+#pragma unroll
+            for (int x = 0; x < 4; x++) csrc[y * 4 + x] = (w >> (8 * x)) & 255;
+        }
+        const int t0 = top[0] + top[1] + top[2] + top[3], t1 = top[4] + top[5] + top[6] + top[7];
+        const int l0 = left[0] + left[1] + left[2] + left[3], l1 = left[4] + left[5] + left[6] + left[7];
+        int dcv;
+        if (k == 0) dcv = (hasT && hasL) ? (t0 + l0 + 4) >> 3 : hasT ? (t0 + 2) >> 2 : hasL ? (l0 + 2) >> 2 : 128;
+        else if (k == 1) dcv = hasT ? (t1 + 2) >> 2 : hasL ? (l0 + 2) >> 2 : 128;
+        else if (k == 2) dcv = hasL ? (l1 + 2) >> 2 : hasT ? (t0 + 2) >> 2 : 128;
+        else dcv = (hasT && hasL) ? (t1 + l1 + 4) >> 3 : hasT ? (t1 + 2) >> 2 : hasL ? (l1 + 2) >> 2 : 128;
+        int Hc = 0, Vc = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            Hc += (i + 1) * (top[4 + i] - (i == 3 ? tl : top[2 - i]));
+            Vc += (i + 1) * (left[4 + i] - (i == 3 ? tl : left[2 - i]));
+        }
+        const int pa = 16 * (left[7] + top[7]), pb = (34 * Hc + 32) >> 6, pc = (34 * Vc + 32) >> 6;
+        const int ue_bits[4] = {1, 3, 3, 5};
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+            const bool ok = m == B2_IC_DC ? true : m == B2_IC_H ? hasL : m == B2_IC_V ? hasT : (mba & 7) == 7;
+            int d[16];
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    int p;
+                    if (m == B2_IC_DC) p = dcv;
+                    else if (m == B2_IC_H) p = left[cby + y];
+                    else if (m == B2_IC_V) p = top[cbx + x];
+                    else p = b2_clip255((pa + pb * (cbx + x - 3) + pc * (cby + y - 3) + 16) >> 5);
+                    d[y * 4 + x] = csrc[y * 4 + x] - p;
+                }
+            const int part = b < 8 ? (int)b2::satd4x4(d) : 0;
+            const uint32_t c = (uint32_t)sum16(part) + (uint32_t)(lambda * ue_bits[m]);
+            if (ok && c < bestc) { bestc = c; modec = m; }
+        }
+    }
+
+    if (valid) {
+        info[mbi].i4_mode[b] = (uint8_t)mode4;
+        if (b == 0) {
+            info[mbi].i16_mode = (uint8_t)mode16;
+            info[mbi].chroma_mode = (uint8_t)modec;
+            cost_i16[mbi] = best16;
+            cost_i4[mbi] = sum4;
+        }
+    }
+}
+
+}  // namespace
+
+int b2_launch_intra_analyse(const uint8_t *d_y, const uint8_t *d_u, const uint8_t *d_v, int pitch, int pitchc,
+                            size_t stride_y, size_t stride_c, int mbw, int mbh, int nframes, int lambda,
+                            b2_mbinfo_t *d_info, uint32_t *d_c16, uint32_t *d_c4, cudaStream_t st)
+{
+    const int nmb = mbw * mbh * nframes;
+    const int blocks = (nmb * 16 + K3_THREADS - 1) / K3_THREADS;
+    k3_intra_analyse_kernel<<<blocks, K3_THREADS, 0, st>>>(d_y, d_u, d_v, pitch, pitchc, stride_y, stride_c, mbw, mbh, nmb,
+                                                           lambda, d_info, d_c16, d_c4);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
