@@ -1,0 +1,53 @@
+"""The C-ABI library loads and exports every function the headers in include/ declare (CPU only, no
+compute calls); the host entry points that need no GPU honour the reference's error convention."""
+import ctypes as C
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    names = set()
+    for hdr in ("b2enc.h", "b2enc_engine.h", "b2enc_kernels.h"):
+        src = open(os.path.join(ROOT, "include", hdr)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(b2k?_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
+
+
+def test_all_declared_symbols_exported(b2):
+    lib = b2.lib()
+    fns = declared_functions()
+    assert len(fns) >= 30
+    missing = [f for f in fns if not hasattr(lib, f)]
+    assert not missing, missing
+
+
+def test_param_and_error_conventions(b2):
+    L = b2._dropin_lib()
+    p = b2.Param()
+    assert L.b2_param_default_preset(C.byref(p), b"medium", b"film") == 0          # av_encode.c:102-103 defaults
+    assert (p.i_merange, p.b_subpel, p.i_keyint_max) == (16, 1, 32)
+    assert L.b2_param_default_preset(C.byref(p), b"slow", None) == 0 and p.i_merange == 32
+    assert L.b2_param_default_preset(C.byref(p), b"medium", b"zerolatency") == 0 and p.i_gop_slots == 1
+    assert L.b2_param_default_preset(C.byref(p), b"warp9", None) != 0              # av_encode.c:384-386
+    assert L.b2_param_default_preset(C.byref(p), b"medium", b"nosuchtune") != 0
+    assert L.b2_param_apply_profile(C.byref(p), None) == 0                          # av_encode.c:403 with profile NULL
+    assert L.b2_param_apply_profile(C.byref(p), b"high") == 0
+    assert L.b2_param_apply_profile(C.byref(p), b"ultra") != 0                      # av_encode.c:404-405
+
+
+def test_no_cpu_fallback(b2):
+    """without a GPU the product refuses to run instead of silently computing on the CPU"""
+    if b2.lib().b2_device_count() > 0:
+        return
+    L = b2._dropin_lib()
+    p = b2.Param()
+    L.b2_param_default_preset(C.byref(p), b"medium", None)
+    p.i_width, p.i_height = 64, 64
+    assert not L.b2_encoder_open(C.byref(p))                                        # NULL, like av_encode.c:408-411 expects
+    assert not L.b2_sws_getContext(64, 64, 0, 64, 64, 0, 1, None, None, None)
+    import pytest
+    with pytest.raises(RuntimeError):
+        b2.require_gpu()

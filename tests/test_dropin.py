@@ -1,0 +1,105 @@
+"""Drop-in boundary on the GPU: the b2_* mirror of the x264/swscale calls made by av_encode.c, driven with
+the reference's own call sequence; ABI contracts of SURVEY.md 8b (T6), bitstream identical to the oracle
+encoder's, decodable, N-slot output == 1-slot output (T5)."""
+import os
+import numpy as np
+import pytest
+from test_oracle_decode import smooth_seq
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "sws_golden.npz"))
+CASES = sorted({k.rsplit("_", 1)[0] for k in G.files})
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_sws_scale_matches_live_swscale_golden(b2, case):
+    fmt, size = case.split("_")
+    w, h = [int(a) for a in size.split("x")]
+    ins = [G[f"{case}_in{i}"] for i in range(3) if f"{case}_in{i}" in G.files]
+    y, u, v = b2.sws_convert(fmt, w, h, ins, dst_pad=5)
+    assert np.array_equal(y, G[f"{case}_out0"]) and np.array_equal(u, G[f"{case}_out1"]) and np.array_equal(v, G[f"{case}_out2"])
+
+
+def drive(b2, frames, w, h, **kw):
+    """the reference loop: encode every frame (av_encode.c:968-975), then drain (:1076-1083)"""
+    enc = b2.DropInEncoder(w, h, **kw)
+    out = []
+    for t, fr in enumerate(frames):
+        size, nals, pts, dts, key = enc.encode(fr, pts=1000 + 40 * t)
+        assert size >= 0
+        if size > 0:
+            out.append((nals, pts, dts, key))
+    guard = 0
+    while enc.delayed() > 0:
+        size, nals, pts, dts, key = enc.encode(None, 0)
+        assert size > 0
+        out.append((nals, pts, dts, key))
+        guard += 1
+        assert guard <= len(frames)
+    assert enc.encode(None, 0)[0] == 0
+    enc.close()
+    return out
+
+
+def to_annexb(out, length_prefixed):
+    bs = b""
+    for nals, *_ in out:
+        for _, data in nals:
+            if length_prefixed:
+                assert int.from_bytes(data[:4], "big") == len(data) - 4          # av_encode.c:722
+                bs += b"\x00\x00\x00\x01" + data[4:]
+            else:
+                assert data[:4] == b"\x00\x00\x00\x01"
+                bs += data
+    return bs
+
+
+def test_reference_call_sequence_and_bitstream(oracle, b2):
+    w, h, qp, gop, n = 176, 144, 27, 4, 11
+    frames = smooth_seq(w, h, n, seed=4, cut=6)
+    out = drive(b2, frames, w, h, preset="medium", tune="film", quality=qp, i_keyint_max=gop, i_gop_slots=2)
+    assert len(out) == n
+    assert [o[1] for o in out] == [1000 + 40 * t for t in range(n)]               # display order, pts passed through
+    assert [o[3] for o in out] == [int(t % gop == 0) for t in range(n)]           # keyframe flag (av_encode.c:783)
+    sps = out[0][0][0]
+    assert sps[0] == 7 and out[0][0][1][0] == 8 and out[0][0][2][0] == 5          # SPS, PPS, IDR slice (av_encode.c:683-736)
+    assert sps[1][5] == 66 and sps[1][7] in (12, 13, 20, 21, 30)                  # profile_idc / level_idc at [5],[7] (:703-705)
+    bs = to_annexb(out, length_prefixed=True)
+    ref_bs, recons, _, _ = oracle.encode_sequence(frames, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1))
+    assert bs == ref_bs, "GPU drop-in bitstream differs from the oracle encoder's"
+    dec = oracle.decode_yuv(oracle.split_access_units(bs))
+    assert len(dec) == n
+    for i, (dy, du, dv) in enumerate(dec):
+        assert np.array_equal(dy, recons[i].y[:h, :w]) and np.array_equal(du, recons[i].u[:h // 2, :w // 2])
+
+
+def test_slot_count_does_not_change_the_stream(b2):
+    """closed GOPs are independent: 1, 3 and 4 GOPs in flight give byte-identical output (T5)"""
+    w, h, n = 128, 96, 13
+    frames = smooth_seq(w, h, n, seed=8)
+    streams = []
+    for slots in (1, 3, 4):
+        out = drive(b2, frames, w, h, preset="slow", tune=None, quality=30, annexb=1, i_keyint_max=3, i_gop_slots=slots)
+        assert len(out) == n
+        streams.append(to_annexb(out, length_prefixed=False))
+    assert streams[0] == streams[1] == streams[2]
+
+
+def test_delay_contract(b2):
+    """0 while frames are delayed, delayed_frames() counts them, encode(NULL) drains one per call"""
+    w, h = 64, 64
+    frames = smooth_seq(w, h, 5, seed=2)
+    enc = b2.DropInEncoder(w, h, quality=30, i_keyint_max=4, i_gop_slots=2)
+    for t, fr in enumerate(frames):
+        assert enc.encode(fr, t)[0] == 0
+        assert enc.delayed() == t + 1
+    got = 0
+    while enc.delayed() > 0:
+        assert enc.encode(None, 0)[0] > 0
+        got += 1
+    assert got == 5
+    enc.close()
+    enc = b2.DropInEncoder(w, h, tune="zerolatency", quality=30)
+    for t, fr in enumerate(frames):
+        assert enc.encode(fr, t)[0] > 0 and enc.delayed() == 0
+    enc.close()

@@ -212,3 +212,128 @@ class Engine:
 
     def launch_count(self):
         return self.L.b2_engine_launch_count(self.h)
+
+
+# ---- drop-in boundary binding (include/b2enc.h): the x264 / swscale call subset of av_encode.c -------
+class Param(C.Structure):
+    class _Vui(C.Structure):
+        _fields_ = [("i_sar_width", C.c_int), ("i_sar_height", C.c_int)]
+
+    class _Rc(C.Structure):
+        _fields_ = [("i_rc_method", C.c_int), ("f_rf_constant", C.c_float), ("i_qp_constant", C.c_int)]
+    _fields_ = [("i_width", C.c_int), ("i_height", C.c_int), ("b_annexb", C.c_int), ("i_fps_num", C.c_int), ("i_fps_den", C.c_int),
+                ("vui", _Vui), ("rc", _Rc), ("i_keyint_max", C.c_int), ("i_gop_slots", C.c_int), ("i_merange", C.c_int),
+                ("b_subpel", C.c_int), ("b_intra_in_p", C.c_int), ("i_device", C.c_int), ("i_csp_in", C.c_int)]
+
+
+class Image(C.Structure):
+    _fields_ = [("i_csp", C.c_int), ("i_plane", C.c_int), ("i_stride", C.c_int * 4), ("plane", C.c_void_p * 4)]
+
+
+class Picture(C.Structure):
+    _fields_ = [("i_type", C.c_int), ("i_pts", C.c_int64), ("i_dts", C.c_int64), ("b_keyframe", C.c_int), ("img", Image),
+                ("opaque", C.c_void_p)]
+
+
+class Nal(C.Structure):
+    _fields_ = [("i_ref_idc", C.c_int), ("i_type", C.c_int), ("i_payload", C.c_int), ("p_payload", C.c_void_p)]
+
+
+def _dropin_lib():
+    L = lib()
+    L.b2_encoder_open.restype = C.c_void_p; L.b2_encoder_open.argtypes = [C.POINTER(Param)]
+    L.b2_encoder_encode.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Nal)), C.POINTER(C.c_int), C.POINTER(Picture), C.POINTER(Picture)]
+    L.b2_encoder_delayed_frames.argtypes = [C.c_void_p]; L.b2_encoder_close.argtypes = [C.c_void_p]
+    L.b2_param_default_preset.argtypes = [C.POINTER(Param), C.c_char_p, C.c_char_p]
+    L.b2_param_apply_profile.argtypes = [C.POINTER(Param), C.c_char_p]
+    L.b2_picture_alloc.argtypes = [C.POINTER(Picture), C.c_int, C.c_int, C.c_int]; L.b2_picture_clean.argtypes = [C.POINTER(Picture)]
+    L.b2_sws_getContext.restype = C.c_void_p
+    L.b2_sws_getContext.argtypes = [C.c_int] * 7 + [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.b2_sws_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.b2_sws_freeContext.argtypes = [C.c_void_p]
+    return L
+
+
+def sws_convert(fmt, w, h, planes, dst_pad=0):
+    """b2_sws_getContext + b2_sws_scale + b2_sws_freeContext, the way av_encode.c:427-430/545-547 uses them"""
+    require_gpu()
+    L = _dropin_lib()
+    ctx = L.b2_sws_getContext(w, h, FMT[fmt], w, h, FMT["yuv420p"], 1, None, None, None)
+    if not ctx:
+        raise RuntimeError("b2_sws_getContext failed")
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    planes = [np.ascontiguousarray(p, np.uint8) for p in planes]
+    y = np.zeros((h, w + dst_pad), np.uint8); u = np.zeros((ch, cw + dst_pad), np.uint8); v = np.zeros((ch, cw + dst_pad), np.uint8)
+    sp = (C.c_void_p * 4)(*([p.ctypes.data for p in planes] + [None] * (4 - len(planes))))
+    ss = (C.c_int * 4)(*([p.shape[1] for p in planes] + [0] * (4 - len(planes))))
+    dp = (C.c_void_p * 4)(y.ctypes.data, u.ctypes.data, v.ctypes.data, None)
+    ds = (C.c_int * 4)(y.shape[1], u.shape[1], v.shape[1], 0)
+    r = L.b2_sws_scale(ctx, sp, ss, 0, h, dp, ds)
+    L.b2_sws_freeContext(ctx)
+    if r != h:
+        raise RuntimeError("b2_sws_scale failed (%d)" % r)
+    return y[:, :w], u[:, :cw], v[:, :cw]
+
+
+class DropInEncoder:
+    """Drives the b2_* mirror of the x264 API exactly like av_encode.c does (open :378-438, loop :968-975,
+    drain :1076-1083)."""
+
+    def __init__(self, w, h, preset="medium", tune="film", quality=26, profile=None, fps=(30, 1), annexb=0, **ext):
+        require_gpu()
+        self.L = L = _dropin_lib()
+        self.w, self.h = w, h
+        p = Param()
+        if L.b2_param_default_preset(C.byref(p), preset.encode() if preset else None, tune.encode() if tune else None) != 0:
+            raise ValueError("bad preset/tune")
+        p.i_width, p.i_height, p.b_annexb = w, h, annexb
+        p.i_fps_num, p.i_fps_den = fps
+        p.vui.i_sar_width = p.vui.i_sar_height = 1
+        p.rc.i_rc_method = 1; p.rc.f_rf_constant = float(quality)
+        for k, v in ext.items():
+            setattr(p, k, v)
+        if L.b2_param_apply_profile(C.byref(p), profile.encode() if profile else None) != 0:
+            raise ValueError("bad profile")
+        self.h_enc = L.b2_encoder_open(C.byref(p))
+        if not self.h_enc:
+            raise RuntimeError("b2_encoder_open failed")
+        self.pic_in = Picture(); self.pic_out = Picture()
+        if L.b2_picture_alloc(C.byref(self.pic_in), 1, w, h) != 0:
+            raise MemoryError
+        self.param = p
+
+    def _fill(self, y, u, v):
+        cw, ch = (self.w + 1) // 2, (self.h + 1) // 2
+        for i, (a, ww, hh) in enumerate(((y, self.w, self.h), (u, cw, ch), (v, cw, ch))):
+            dst = np.frombuffer((C.c_uint8 * (ww * hh)).from_address(self.pic_in.img.plane[i]), np.uint8).reshape(hh, ww)
+            dst[:] = a
+
+    def encode(self, frame, pts):
+        """frame: (y,u,v) or None to flush.  Returns (size, [(type, bytes)], pts, dts, keyframe)."""
+        nal = C.POINTER(Nal)(); n = C.c_int(0)
+        if frame is not None:
+            self._fill(*frame)
+            self.pic_in.i_type = 0; self.pic_in.i_pts = pts
+            size = self.L.b2_encoder_encode(self.h_enc, C.byref(nal), C.byref(n), C.byref(self.pic_in), C.byref(self.pic_out))
+        else:
+            size = self.L.b2_encoder_encode(self.h_enc, C.byref(nal), C.byref(n), None, C.byref(self.pic_out))
+        nals = []
+        if size > 0:
+            base = nal[0].p_payload
+            whole = C.string_at(base, size)
+            off = 0
+            for i in range(n.value):
+                assert nal[i].p_payload == base + off, "NAL payloads are not contiguous"
+                nals.append((nal[i].i_type, whole[off:off + nal[i].i_payload]))
+                off += nal[i].i_payload
+            assert off == size
+        return size, nals, self.pic_out.i_pts, self.pic_out.i_dts, self.pic_out.b_keyframe
+
+    def delayed(self):
+        return self.L.b2_encoder_delayed_frames(self.h_enc)
+
+    def close(self):
+        if self.h_enc:
+            self.L.b2_picture_clean(C.byref(self.pic_in))
+            self.L.b2_encoder_close(self.h_enc)
+            self.h_enc = None

@@ -1,0 +1,277 @@
+/*
+ * b2h_encoder.c -- host side of the drop-in encoder boundary (include/b2enc.h): the x264 API subset
+ * that av_encode.c calls (enc_x264_open :378-438, the encode loop :968-975, the drain loop :1076-1083),
+ * implemented over the CUDA engine (include/b2enc_engine.h) and the host CAVLC stage (b2h_entropy.h).
+ *
+ * Frame queue (row a0 of SURVEY.md 8a): the caller still hands over one picture per call, but pictures
+ * are gathered into i_gop_slots closed GOPs of i_keyint_max frames; a full batch is advanced through
+ * the GPU in lock-step (one launch sequence per frame index covers all GOPs), the host entropy-codes
+ * the per-MB results and frames are then returned in display order, one per call -- exactly the
+ * "0 = no output yet / delayed_frames() / encode(NULL) drains" contract main() relies on
+ * (av_encode.c:971-974, :1076-1083).  i_gop_slots = 1 encodes every picture immediately (zero delay).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "b2enc.h"
+#include "b2enc_engine.h"
+#include "b2h_entropy.h"
+
+void *b2_pinned_alloc(size_t n);
+void b2_pinned_free(void *p);
+
+typedef struct {
+    uint8_t *data;
+    int size;
+    int nal_count;
+    int nal_off[3], nal_size[3], nal_type[3], nal_ref[3];
+    int64_t pts;
+    int key;
+} outframe_t;
+
+struct b2_encoder {
+    b2_param_t p;
+    int qp, S, L, mbw, mbh, nmb;
+    b2_engine_t *eng;
+    b2h_entropy_t *ent;
+    b2h_seq_t seq;
+    int64_t *pts;              /* [S*L] pts of the frames of the batch being gathered */
+    int batch_frames;
+    int gop_pos;               /* zero-delay mode: position inside the current GOP */
+    outframe_t *outq;          /* [S*L] finished frames of the last processed batch, display order */
+    int out_head, out_count;
+    int64_t gops_done;
+    uint8_t *scratch;
+    size_t scratch_cap;
+    uint8_t *ret_buf;          /* payload of the frame returned by the last call */
+    b2_nal_t nals[3];
+};
+
+static const struct { const char *name; int merange, subpel, intra_in_p; } presets[] = {
+    {"ultrafast", 16, 0, 0}, {"superfast", 16, 1, 1}, {"veryfast", 16, 1, 1}, {"faster", 16, 1, 1}, {"fast", 16, 1, 1},
+    {"medium", 16, 1, 1},    {"slow", 32, 1, 1},      {"slower", 32, 1, 1},   {"veryslow", 32, 1, 1}, {"placebo", 32, 1, 1}};
+static const char *tunes[] = {"film", "animation", "grain", "stillimage", "psnr", "ssim", "fastdecode", "zerolatency"};
+
+int b2_param_default_preset(b2_param_t *p, const char *preset, const char *tune)
+{
+    if (!p) return -1;
+    memset(p, 0, sizeof(*p));
+    p->i_fps_num = 25; p->i_fps_den = 1;
+    p->vui.i_sar_width = p->vui.i_sar_height = 0;
+    p->rc.i_rc_method = B2_RC_CRF; p->rc.f_rf_constant = 23.0f; p->rc.i_qp_constant = 26;
+    p->b_annexb = 1;
+    p->i_keyint_max = 32; p->i_gop_slots = 8; p->i_device = 0; p->i_csp_in = B2_FMT_YUV420P;
+    int found = preset == NULL;
+    p->i_merange = 16; p->b_subpel = 1; p->b_intra_in_p = 1;
+    for (unsigned i = 0; preset && i < sizeof(presets) / sizeof(presets[0]); i++)
+        if (!strcmp(preset, presets[i].name)) {
+            p->i_merange = presets[i].merange; p->b_subpel = presets[i].subpel; p->b_intra_in_p = presets[i].intra_in_p;
+            found = 1;
+        }
+    if (!found) { fprintf(stderr, "b2enc: invalid preset '%s'\n", preset); return -1; }
+    if (tune) {
+        int ok = 0;
+        for (unsigned i = 0; i < sizeof(tunes) / sizeof(tunes[0]); i++) ok |= !strcmp(tune, tunes[i]);
+        if (!ok) { fprintf(stderr, "b2enc: invalid tune '%s'\n", tune); return -1; }
+        if (!strcmp(tune, "zerolatency")) p->i_gop_slots = 1;
+    }
+    return 0;
+}
+
+int b2_param_apply_profile(b2_param_t *p, const char *profile)
+{
+    if (!p) return -1;
+    if (!profile) return 0;
+    /* the stream is always Constrained Baseline (CAVLC, no 8x8 transform), a subset of all three */
+    if (!strcmp(profile, "baseline") || !strcmp(profile, "main") || !strcmp(profile, "high")) return 0;
+    fprintf(stderr, "b2enc: invalid profile: %s\n", profile);
+    return -1;
+}
+
+int b2_picture_alloc(b2_picture_t *pic, int i_csp, int i_width, int i_height)
+{
+    if (!pic || i_csp != B2_CSP_I420 || i_width < 2 || i_height < 2) return -1;
+    memset(pic, 0, sizeof(*pic));
+    int cw = (i_width + 1) / 2, ch = (i_height + 1) / 2;
+    size_t ny = (size_t)i_width * i_height, nc = (size_t)cw * ch;
+    uint8_t *buf = (uint8_t *)b2_pinned_alloc(ny + 2 * nc);          /* pinned: H2D copies run at full PCIe rate */
+    if (!buf) return -1;
+    pic->img.i_csp = i_csp; pic->img.i_plane = 3;
+    pic->img.plane[0] = buf; pic->img.plane[1] = buf + ny; pic->img.plane[2] = buf + ny + nc;
+    pic->img.i_stride[0] = i_width; pic->img.i_stride[1] = cw; pic->img.i_stride[2] = cw;
+    pic->opaque = buf;
+    return 0;
+}
+
+void b2_picture_clean(b2_picture_t *pic)
+{
+    if (!pic) return;
+    b2_pinned_free(pic->opaque);
+    memset(pic, 0, sizeof(*pic));
+}
+
+b2_t *b2_encoder_open(b2_param_t *p)
+{
+    if (!p || p->i_width < 16 || p->i_height < 16) { fprintf(stderr, "b2enc: bad picture size\n"); return NULL; }
+    b2_t *h = (b2_t *)calloc(1, sizeof(*h));
+    if (!h) return NULL;
+    h->p = *p;
+    int qp = p->rc.i_rc_method == B2_RC_CQP ? p->rc.i_qp_constant : (int)(p->rc.f_rf_constant + 0.5f);
+    h->qp = qp < 10 ? 10 : (qp > 51 ? 51 : qp);      /* CRF is mapped to a constant QP (north_star: fixed QP) */
+    h->S = p->i_gop_slots > 0 ? p->i_gop_slots : 1;
+    h->L = p->i_keyint_max > 0 ? p->i_keyint_max : 32;
+    b2_engine_cfg_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.device = p->i_device; cfg.width = p->i_width; cfg.height = p->i_height; cfg.slots = h->S;
+    cfg.in_fmt = p->i_csp_in; cfg.in_ring = h->S == 1 ? 1 : h->L; cfg.merange = p->i_merange ? p->i_merange : 16; cfg.qp = h->qp;
+    cfg.subpel = p->b_subpel; cfg.intra_in_p = p->b_intra_in_p; cfg.profile = 0;
+    h->eng = b2_engine_create(&cfg);
+    if (!h->eng) { free(h); return NULL; }
+    int w16, h16;
+    b2_engine_geometry(h->eng, &h->mbw, &h->mbh, &w16, &h16);
+    h->nmb = h->mbw * h->mbh;
+    h->ent = b2h_entropy_create(h->mbw, h->mbh);
+    h->seq.width = p->i_width; h->seq.height = p->i_height; h->seq.fps_num = p->i_fps_num; h->seq.fps_den = p->i_fps_den;
+    h->seq.sar_w = p->vui.i_sar_width; h->seq.sar_h = p->vui.i_sar_height; h->seq.qp = h->qp;
+    h->pts = (int64_t *)calloc((size_t)h->S * h->L, sizeof(int64_t));
+    h->outq = (outframe_t *)calloc((size_t)h->S * h->L, sizeof(outframe_t));
+    h->scratch_cap = (size_t)h->nmb * 3072 + 65536;
+    h->scratch = (uint8_t *)malloc(h->scratch_cap);
+    if (!h->ent || !h->pts || !h->outq || !h->scratch) { b2_encoder_close(h); return NULL; }
+    return h;
+}
+
+void b2_encoder_close(b2_t *h)
+{
+    if (!h) return;
+    if (h->outq)
+        for (int i = 0; i < h->S * h->L; i++) free(h->outq[i].data);
+    free(h->outq); free(h->pts); free(h->scratch); free(h->ret_buf);
+    b2h_entropy_destroy(h->ent);
+    b2_engine_destroy(h->eng);
+    free(h);
+}
+
+static void put_prefix(uint8_t *d, int annexb, size_t nal_size)
+{
+    if (annexb) { d[0] = 0; d[1] = 0; d[2] = 0; d[3] = 1; }
+    else { d[0] = (uint8_t)(nal_size >> 24); d[1] = (uint8_t)(nal_size >> 16); d[2] = (uint8_t)(nal_size >> 8); d[3] = (uint8_t)nal_size; }
+}
+
+/* entropy-code one frame's results into outq[qi] */
+static int finish_frame(b2_t *h, int qi, int slot, int t, int64_t gop_index)
+{
+    outframe_t *o = &h->outq[qi];
+    uint8_t *s = h->scratch;
+    size_t pos = 0;
+    o->nal_count = 0;
+    const int is_idr = t == 0;
+    if (is_idr) {
+        for (int k = 0; k < 2; k++) {
+            size_t n = k == 0 ? b2h_write_sps(&h->seq, s + pos + 4, h->scratch_cap - pos - 4)
+                              : b2h_write_pps(&h->seq, s + pos + 4, h->scratch_cap - pos - 4);
+            if (!n) return -1;
+            put_prefix(s + pos, h->p.b_annexb, n);
+            o->nal_off[o->nal_count] = (int)pos; o->nal_size[o->nal_count] = (int)n + 4;
+            o->nal_type[o->nal_count] = k == 0 ? B2_NAL_SPS : B2_NAL_PPS; o->nal_ref[o->nal_count] = 3;
+            o->nal_count++;
+            pos += n + 4;
+        }
+    }
+    size_t n = b2h_write_slice(h->ent, &h->seq, is_idr ? B2_FRAME_I : B2_FRAME_P, t, (int)(gop_index & 0xffff),
+                               b2_engine_info(h->eng, slot), b2_engine_coef(h->eng, slot), s + pos + 4, h->scratch_cap - pos - 4);
+    if (!n) { fprintf(stderr, "b2enc: slice buffer overflow\n"); return -1; }
+    put_prefix(s + pos, h->p.b_annexb, n);
+    o->nal_off[o->nal_count] = (int)pos; o->nal_size[o->nal_count] = (int)n + 4;
+    o->nal_type[o->nal_count] = is_idr ? B2_NAL_SLICE_IDR : B2_NAL_SLICE; o->nal_ref[o->nal_count] = is_idr ? 3 : 2;
+    o->nal_count++;
+    pos += n + 4;
+    free(o->data);
+    o->data = (uint8_t *)malloc(pos);
+    if (!o->data) return -1;
+    memcpy(o->data, s, pos);
+    o->size = (int)pos;
+    o->key = is_idr;
+    return 0;
+}
+
+/* advance the gathered batch (possibly partial) through the GPU and the entropy stage */
+static int process_batch(b2_t *h)
+{
+    const int n = h->batch_frames, L = h->L;
+    const int ngop = (n + L - 1) / L, last_len = n - (ngop - 1) * L;
+    for (int t = 0; t < L; t++) {
+        const int nt = t < last_len ? ngop : ngop - 1;      /* GOPs that still have a frame t (a prefix of the slots) */
+        if (nt <= 0) break;
+        if (b2_engine_h2d(h->eng, 0, nt, h->S == 1 ? 0 : t)) return -1;
+        if (b2_engine_encode(h->eng, t == 0 ? B2_FRAME_I : B2_FRAME_P, nt, h->S == 1 ? 0 : t)) return -1;
+        if (b2_engine_d2h(h->eng, nt)) return -1;
+        if (b2_engine_sync(h->eng)) return -1;
+        for (int g = 0; g < nt; g++) {
+            const int qi = g * L + t;
+            if (finish_frame(h, qi, g, t, h->gops_done + g)) return -1;
+            h->outq[qi].pts = h->pts[qi];
+        }
+    }
+    h->gops_done += ngop;
+    h->out_head = 0; h->out_count = n;
+    h->batch_frames = 0;
+    return 0;
+}
+
+int b2_encoder_delayed_frames(b2_t *h) { return h ? h->batch_frames + h->out_count : 0; }
+
+int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic_in, b2_picture_t *pic_out)
+{
+    if (!h || !pp_nal || !pi_nal) return -1;
+    *pi_nal = 0; *pp_nal = NULL;
+    if (pic_in) {
+        if (h->S == 1) {
+            /* zero-delay mode: one slot, encode every picture as it arrives */
+            const int t = h->gop_pos;
+            if (b2_engine_put_frame(h->eng, 0, 0, (const uint8_t *const *)pic_in->img.plane, pic_in->img.i_stride)) return -1;
+            if (b2_engine_h2d(h->eng, 0, 1, 0) || b2_engine_encode(h->eng, t == 0 ? B2_FRAME_I : B2_FRAME_P, 1, 0) ||
+                b2_engine_d2h(h->eng, 1) || b2_engine_sync(h->eng))
+                return -1;
+            if (finish_frame(h, 0, 0, t, h->gops_done)) return -1;
+            h->outq[0].pts = pic_in->i_pts;
+            h->out_head = 0; h->out_count = 1;
+            h->gop_pos = t + 1;
+            if (h->gop_pos == h->L) { h->gop_pos = 0; h->gops_done++; }
+        } else {
+            if (h->out_count > 0 && h->batch_frames == h->S * h->L) {
+                fprintf(stderr, "b2enc: internal queue overflow\n");
+                return -1;
+            }
+            const int idx = h->batch_frames, g = idx / h->L, t = idx % h->L;
+            if (b2_engine_put_frame(h->eng, g, t, (const uint8_t *const *)pic_in->img.plane, pic_in->img.i_stride)) return -1;
+            h->pts[idx] = pic_in->i_pts;
+            h->batch_frames++;
+            /* a batch can only be processed once the previous one has been handed out completely */
+            if (h->batch_frames == h->S * h->L && h->out_count == 0)
+                if (process_batch(h)) return -1;
+        }
+    } else if (h->S > 1 && h->out_count == 0 && h->batch_frames > 0) {
+        if (process_batch(h)) return -1;                            /* flush: partial batch */
+    }
+    if (h->out_count == 0) return 0;
+    outframe_t *o = &h->outq[h->out_head];
+    free(h->ret_buf);
+    h->ret_buf = o->data; o->data = NULL;                           /* hand the payload over; valid until the next call */
+    for (int i = 0; i < o->nal_count; i++) {
+        h->nals[i].i_ref_idc = o->nal_ref[i]; h->nals[i].i_type = o->nal_type[i];
+        h->nals[i].i_payload = o->nal_size[i]; h->nals[i].p_payload = h->ret_buf + o->nal_off[i];
+    }
+    *pp_nal = h->nals; *pi_nal = o->nal_count;
+    if (pic_out) {
+        memset(pic_out, 0, sizeof(*pic_out));
+        pic_out->i_pts = o->pts; pic_out->i_dts = o->pts; pic_out->b_keyframe = o->key;
+        pic_out->i_type = o->key ? B2_TYPE_IDR : B2_TYPE_P;
+    }
+    const int ret = o->size;
+    h->out_head++; h->out_count--;
+    /* when a full batch was waiting for the queue to drain, process it now */
+    if (h->S > 1 && h->out_count == 0 && h->batch_frames == h->S * h->L)
+        if (process_batch(h)) return -1;
+    return ret;
+}
