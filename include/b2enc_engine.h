@@ -31,6 +31,8 @@ typedef struct {
     int subpel;        /* 1: half + quarter-pel SATD refinement                           */
     int intra_in_p;    /* 1: intra/inter decision in P frames                             */
     int profile;       /* 1: record per-kernel CUDA-event timings (b2_engine_kernel_ms)   */
+    int streams;       /* stream groups the slots are split into (0 = automatic); groups   */
+                       /* run on separate CUDA streams so that their kernels overlap       */
 } b2_engine_cfg_t;
 
 b2_engine_t *b2_engine_create(const b2_engine_cfg_t *cfg);      /* NULL on error */
@@ -47,6 +49,12 @@ int b2_engine_put_frame(b2_engine_t *e, int slot, int ring, const uint8_t *const
 int b2_engine_h2d(b2_engine_t *e, int slot0, int nslots, int ring);
 /* async: encode ring position `ring` of slots [0,nslots) as one frame each (B2_FRAME_I / B2_FRAME_P) */
 int b2_engine_encode(b2_engine_t *e, int frame_type, int nslots, int ring);
+/* stream groups: contiguous slot ranges with their own compute stream.  Groups may be advanced
+ * independently (e.g. with staggered GOP phases so that only one group is in an I frame at a time). */
+int b2_engine_groups(const b2_engine_t *e);
+int b2_engine_group_range(const b2_engine_t *e, int group, int *slot0, int *nslots);
+int b2_engine_encode_group(b2_engine_t *e, int group, int frame_type, int ring);
+int b2_engine_d2h_group(b2_engine_t *e, int group);
 /* async device -> pinned-host copy of the last encode's per-MB results for slots [0,nslots) */
 int b2_engine_d2h(b2_engine_t *e, int nslots);
 int b2_engine_sync(b2_engine_t *e);

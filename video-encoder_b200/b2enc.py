@@ -85,14 +85,14 @@ KERNEL_NAMES = ["K0 convert", "K6 border(cur)", "K1 full-pel SAD", "K2 sub-pel S
 class EngineCfg(C.Structure):
     _fields_ = [("device", C.c_int), ("width", C.c_int), ("height", C.c_int), ("slots", C.c_int), ("in_fmt", C.c_int),
                 ("in_ring", C.c_int), ("merange", C.c_int), ("qp", C.c_int), ("subpel", C.c_int), ("intra_in_p", C.c_int),
-                ("profile", C.c_int)]
+                ("profile", C.c_int), ("streams", C.c_int)]
 
 
 class Engine:
     """One GPU's encode-stage engine: `slots` closed GOPs / streams advanced in lock-step."""
 
     def __init__(self, width, height, slots=1, fmt="yuv420p", ring=1, merange=16, qp=26, subpel=1, intra_in_p=1,
-                 device=0, profile=0):
+                 device=0, profile=0, streams=0):
         require_gpu()
         L = lib()
         L.b2_engine_create.restype = C.c_void_p
@@ -108,6 +108,10 @@ class Engine:
         L.b2_engine_h2d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.b2_engine_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.b2_engine_d2h.argtypes = [C.c_void_p, C.c_int]
+        L.b2_engine_groups.argtypes = [C.c_void_p]
+        L.b2_engine_group_range.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.b2_engine_encode_group.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.b2_engine_d2h_group.argtypes = [C.c_void_p, C.c_int]
         L.b2_engine_info.argtypes = [C.c_void_p, C.c_int]; L.b2_engine_coef.argtypes = [C.c_void_p, C.c_int]
         L.b2_engine_get_recon.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2_engine_get_cur.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -117,7 +121,7 @@ class Engine:
         L.b2_engine_kernel_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long)]
         self.L = L
         self.cfg = EngineCfg(device, width, height, slots, FMT[fmt] if isinstance(fmt, str) else fmt, ring, merange, qp,
-                             subpel, intra_in_p, profile)
+                             subpel, intra_in_p, profile, streams)
         self.h = L.b2_engine_create(C.byref(self.cfg))
         if not self.h:
             raise RuntimeError("b2_engine_create failed")
@@ -160,6 +164,20 @@ class Engine:
 
     def encode(self, frame_type, nslots=None, ring=0):
         self._ck(self.L.b2_engine_encode(self.h, frame_type, self.slots if nslots is None else nslots, ring), "encode")
+
+    def groups(self):
+        out = []
+        for g in range(self.L.b2_engine_groups(self.h)):
+            a, b = C.c_int(), C.c_int()
+            self.L.b2_engine_group_range(self.h, g, C.byref(a), C.byref(b))
+            out.append((a.value, b.value))
+        return out
+
+    def encode_group(self, group, frame_type, ring=0):
+        self._ck(self.L.b2_engine_encode_group(self.h, group, frame_type, ring), "encode_group")
+
+    def d2h_group(self, group):
+        self._ck(self.L.b2_engine_d2h_group(self.h, group), "d2h_group")
 
     def d2h(self, nslots=None):
         self._ck(self.L.b2_engine_d2h(self.h, self.slots if nslots is None else nslots), "d2h")

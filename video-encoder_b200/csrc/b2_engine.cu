@@ -26,6 +26,22 @@ int b2_lambda_for_qp(int qp)
 
 struct ProfRec { int k; cudaEvent_t e0, e1; };
 
+// A stream group: a contiguous range of slots advanced together on its own compute stream.  Groups
+// share nothing, so their kernels overlap on the GPU: while one group sits in the latency-bound intra
+// wavefront (K7) the others keep the SMs busy with the ALU-bound search (K1).
+struct Group {
+    int slot0 = 0, n = 0;
+    cudaStream_t st = nullptr;
+    CUtensorMap tm_cur, tm_ref[2];
+    int ref_idx = 0;                       // d_rec[ref_idx] holds this group's latest reconstruction
+    int res_set = 0, host_set = 0;
+    int last_n = 0;                        // slots covered by the most recent encode
+    cudaEvent_t ev_enc[2] = {}, ev_d2h[2] = {}, ev_join = nullptr;
+    bool d2h_used[2] = {false, false};
+    std::vector<cudaEvent_t> ev_k0;
+    std::vector<char> h2d_pending;
+};
+
 struct b2_engine {
     b2_engine_cfg_t cfg;
     int w16, h16, mbw, mbh, nmb;
@@ -34,19 +50,14 @@ struct b2_engine {
     int lambda;
     uint8_t *d_in = nullptr, *h_in = nullptr;
     uint8_t *d_cur[3] = {}, *d_rec[2][3] = {};
-    int ref_idx = 0;                       // d_rec[ref_idx] holds the latest reconstruction
     b2_mv_t *d_mvf = nullptr, *d_mvq = nullptr, *d_prev_mv = nullptr;
     uint32_t *d_cost_full = nullptr, *d_cost_inter = nullptr, *d_c16 = nullptr, *d_c4 = nullptr;
     b2_mbinfo_t *d_info[2] = {}, *h_info[2] = {};
     b2_mbcoef_t *d_coef[2] = {}, *h_coef[2] = {};
-    int res_set = 0;                       // result set written by the most recent encode
-    int host_set = 0;                      // result set most recently copied to the host
-    CUtensorMap tm_cur, tm_ref[2];
-    cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr;
-    std::vector<cudaEvent_t> ev_h2d, ev_k0;
-    std::vector<char> h2d_pending;
-    cudaEvent_t ev_enc[2] = {}, ev_d2h[2] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
-    bool d2h_used[2] = {false, false};
+    std::vector<Group> groups;
+    cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr;     // st: timer / join stream
+    std::vector<cudaEvent_t> ev_h2d;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     long launches = 0;
     double k_ms[B2_NKERNELS] = {};
     long k_n[B2_NKERNELS] = {};
@@ -102,23 +113,36 @@ static int engine_alloc(b2_engine *e)
         ENG_OK(cudaMalloc(&e->d_coef[s], n * sizeof(b2_mbcoef_t)));
         ENG_OK(cudaHostAlloc(&e->h_info[s], n * sizeof(b2_mbinfo_t), cudaHostAllocDefault));
         ENG_OK(cudaHostAlloc(&e->h_coef[s], n * sizeof(b2_mbcoef_t), cudaHostAllocDefault));
-        ENG_OK(cudaEventCreateWithFlags(&e->ev_enc[s], cudaEventDisableTiming));
-        ENG_OK(cudaEventCreateWithFlags(&e->ev_d2h[s], cudaEventDisableTiming));
     }
     ENG_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     ENG_OK(cudaStreamCreateWithFlags(&e->st_in, cudaStreamNonBlocking));
     ENG_OK(cudaStreamCreateWithFlags(&e->st_out, cudaStreamNonBlocking));
-    e->ev_h2d.resize(c.in_ring); e->ev_k0.resize(c.in_ring); e->h2d_pending.assign(c.in_ring, 0);
-    for (int r = 0; r < c.in_ring; r++) {
-        ENG_OK(cudaEventCreateWithFlags(&e->ev_h2d[r], cudaEventDisableTiming));
-        ENG_OK(cudaEventCreateWithFlags(&e->ev_k0[r], cudaEventDisableTiming));
-    }
+    e->ev_h2d.resize(c.in_ring);
+    for (int r = 0; r < c.in_ring; r++) ENG_OK(cudaEventCreateWithFlags(&e->ev_h2d[r], cudaEventDisableTiming));
     ENG_OK(cudaEventCreate(&e->ev_t0)); ENG_OK(cudaEventCreate(&e->ev_t1));
     int bw, bh;
     if (b2_k1_window_box(c.merange, &bw, &bh)) { fprintf(stderr, "b2enc: merange must be 16 or 32\n"); return -1; }
-    if (b2_make_plane_tmap(&e->tm_cur, e->d_cur[0], e->pitch, e->rows, c.slots, 128, 16)) return -1;
-    if (b2_make_plane_tmap(&e->tm_ref[0], e->d_rec[0][0], e->pitch, e->rows, c.slots, bw, bh)) return -1;
-    if (b2_make_plane_tmap(&e->tm_ref[1], e->d_rec[1][0], e->pitch, e->rows, c.slots, bw, bh)) return -1;
+    // stream groups: contiguous, near-equal slot ranges
+    int G = c.streams > 0 ? c.streams : (c.slots >= 8 ? 4 : (c.slots >= 2 ? 2 : 1));
+    if (G > c.slots) G = c.slots;
+    e->groups.resize(G);
+    int s0 = 0;
+    for (int g = 0; g < G; g++) {
+        Group &gr = e->groups[g];
+        gr.slot0 = s0; gr.n = c.slots / G + (g < c.slots % G ? 1 : 0);
+        s0 += gr.n;
+        ENG_OK(cudaStreamCreateWithFlags(&gr.st, cudaStreamNonBlocking));
+        for (int s = 0; s < 2; s++) {
+            ENG_OK(cudaEventCreateWithFlags(&gr.ev_enc[s], cudaEventDisableTiming));
+            ENG_OK(cudaEventCreateWithFlags(&gr.ev_d2h[s], cudaEventDisableTiming));
+        }
+        ENG_OK(cudaEventCreateWithFlags(&gr.ev_join, cudaEventDisableTiming));
+        gr.ev_k0.resize(c.in_ring); gr.h2d_pending.assign(c.in_ring, 0);
+        for (int r = 0; r < c.in_ring; r++) ENG_OK(cudaEventCreateWithFlags(&gr.ev_k0[r], cudaEventDisableTiming));
+        if (b2_make_plane_tmap(&gr.tm_cur, e->d_cur[0] + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, 128, 16)) return -1;
+        if (b2_make_plane_tmap(&gr.tm_ref[0], e->d_rec[0][0] + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, bw, bh)) return -1;
+        if (b2_make_plane_tmap(&gr.tm_ref[1], e->d_rec[1][0] + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, bw, bh)) return -1;
+    }
     return 0;
 }
 
@@ -161,13 +185,14 @@ extern "C" void b2_engine_destroy(b2_engine_t *e)
     for (int p = 0; p < 3; p++) { cudaFree(e->d_cur[p]); cudaFree(e->d_rec[0][p]); cudaFree(e->d_rec[1][p]); }
     cudaFree(e->d_mvf); cudaFree(e->d_mvq); cudaFree(e->d_prev_mv); cudaFree(e->d_cost_full); cudaFree(e->d_cost_inter);
     cudaFree(e->d_c16); cudaFree(e->d_c4);
-    for (int s = 0; s < 2; s++) {
-        cudaFree(e->d_info[s]); cudaFree(e->d_coef[s]); cudaFreeHost(e->h_info[s]); cudaFreeHost(e->h_coef[s]);
-        if (e->ev_enc[s]) cudaEventDestroy(e->ev_enc[s]);
-        if (e->ev_d2h[s]) cudaEventDestroy(e->ev_d2h[s]);
+    for (int s = 0; s < 2; s++) { cudaFree(e->d_info[s]); cudaFree(e->d_coef[s]); cudaFreeHost(e->h_info[s]); cudaFreeHost(e->h_coef[s]); }
+    for (auto &gr : e->groups) {
+        for (int s = 0; s < 2; s++) { if (gr.ev_enc[s]) cudaEventDestroy(gr.ev_enc[s]); if (gr.ev_d2h[s]) cudaEventDestroy(gr.ev_d2h[s]); }
+        if (gr.ev_join) cudaEventDestroy(gr.ev_join);
+        for (auto ev : gr.ev_k0) cudaEventDestroy(ev);
+        if (gr.st) cudaStreamDestroy(gr.st);
     }
     for (auto ev : e->ev_h2d) cudaEventDestroy(ev);
-    for (auto ev : e->ev_k0) cudaEventDestroy(ev);
     for (auto ev : e->ev_pool) cudaEventDestroy(ev);
     for (auto &r : e->prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
@@ -182,10 +207,27 @@ extern "C" size_t b2_engine_input_bytes(const b2_engine_t *e) { return e->in_byt
 extern "C" size_t b2_engine_result_bytes(const b2_engine_t *e) { return (size_t)e->nmb * (sizeof(b2_mbinfo_t) + sizeof(b2_mbcoef_t)); }
 extern "C" void b2_engine_geometry(const b2_engine_t *e, int *mbw, int *mbh, int *w16, int *h16)
 {
-    if (mbw) *mbw = e->mbw; if (mbh) *mbh = e->mbh; if (w16) *w16 = e->w16; if (h16) *h16 = e->h16;
+    if (mbw) *mbw = e->mbw;
+    if (mbh) *mbh = e->mbh;
+    if (w16) *w16 = e->w16;
+    if (h16) *h16 = e->h16;
+}
+extern "C" int b2_engine_groups(const b2_engine_t *e) { return (int)e->groups.size(); }
+extern "C" int b2_engine_group_range(const b2_engine_t *e, int group, int *slot0, int *nslots)
+{
+    if (group < 0 || group >= (int)e->groups.size()) return -1;
+    if (slot0) *slot0 = e->groups[group].slot0;
+    if (nslots) *nslots = e->groups[group].n;
+    return 0;
 }
 
 static inline size_t in_off(const b2_engine *e, int slot, int ring) { return ((size_t)slot * e->cfg.in_ring + ring) * e->in_stride; }
+static inline Group *group_of(b2_engine *e, int slot)
+{
+    for (auto &gr : e->groups)
+        if (slot >= gr.slot0 && slot < gr.slot0 + gr.n) return &gr;
+    return nullptr;
+}
 
 extern "C" uint8_t *b2_engine_host_input(b2_engine_t *e, int slot, int ring)
 {
@@ -222,8 +264,9 @@ extern "C" int b2_engine_h2d(b2_engine_t *e, int slot0, int nslots, int ring)
 {
     if (slot0 < 0 || nslots < 1 || slot0 + nslots > e->cfg.slots || ring < 0 || ring >= e->cfg.in_ring) return -1;
     cudaSetDevice(e->cfg.device);
-    // do not overwrite a ring entry that a previously issued K0 still has to read
-    ENG_OK(cudaStreamWaitEvent(e->st_in, e->ev_k0[ring], 0));
+    // do not overwrite a ring entry that a previously issued K0 of an affected group still has to read
+    for (auto &gr : e->groups)
+        if (gr.slot0 < slot0 + nslots && slot0 < gr.slot0 + gr.n) ENG_OK(cudaStreamWaitEvent(e->st_in, gr.ev_k0[ring], 0));
     if (e->cfg.in_ring == 1) {
         const size_t off = in_off(e, slot0, 0);
         ENG_OK(cudaMemcpyAsync(e->d_in + off, e->h_in + off, e->in_stride * nslots, cudaMemcpyHostToDevice, e->st_in));
@@ -234,7 +277,8 @@ extern "C" int b2_engine_h2d(b2_engine_t *e, int slot0, int nslots, int ring)
         }
     }
     ENG_OK(cudaEventRecord(e->ev_h2d[ring], e->st_in));
-    e->h2d_pending[ring] = 1;
+    for (auto &gr : e->groups)
+        if (gr.slot0 < slot0 + nslots && slot0 < gr.slot0 + gr.n) gr.h2d_pending[ring] = 1;
     return 0;
 }
 
@@ -246,13 +290,13 @@ static cudaEvent_t pool_event(b2_engine *e)
     return ev;
 }
 struct KScope {
-    b2_engine *e; int k; cudaEvent_t e0 = nullptr, e1 = nullptr;
-    KScope(b2_engine *e_, int k_) : e(e_), k(k_)
+    b2_engine *e; cudaStream_t st; int k; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    KScope(b2_engine *e_, cudaStream_t st_, int k_) : e(e_), st(st_), k(k_)
     {
         e->launches++;
-        if (e->cfg.profile) { e0 = pool_event(e); e1 = pool_event(e); cudaEventRecord(e0, e->st); }
+        if (e->cfg.profile) { e0 = pool_event(e); e1 = pool_event(e); cudaEventRecord(e0, st); }
     }
-    ~KScope() { if (e->cfg.profile) { cudaEventRecord(e1, e->st); e->prof_pending.push_back({k, e0, e1}); } }
+    ~KScope() { if (e->cfg.profile) { cudaEventRecord(e1, st); e->prof_pending.push_back({k, e0, e1}); } }
 };
 static void prof_collect(b2_engine *e)
 {
@@ -264,94 +308,135 @@ static void prof_collect(b2_engine *e)
     e->prof_pending.clear();
 }
 
+// one frame for the first `ns` slots of group `gr`
+static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int ring)
+{
+    const b2_engine_cfg_t &c = e->cfg;
+    const int is_p = frame_type == B2_FRAME_P;
+    const int do_intra = !is_p || c.intra_in_p;
+    const int set = gr.res_set ^ 1;
+    cudaStream_t st = gr.st;
+    if (gr.h2d_pending[ring]) { ENG_OK(cudaStreamWaitEvent(st, e->ev_h2d[ring], 0)); gr.h2d_pending[ring] = 0; }
+    if (gr.d2h_used[set]) ENG_OK(cudaStreamWaitEvent(st, gr.ev_d2h[set], 0));        // result set still being copied out
+    const size_t oy = gr.slot0 * e->stride_y, oc = gr.slot0 * e->stride_c, om = (size_t)gr.slot0 * e->nmb;
+    uint8_t *curw[3] = {e->d_cur[0] + oy, e->d_cur[1] + oc, e->d_cur[2] + oc};
+    const uint8_t *cur[3] = {curw[0], curw[1], curw[2]};
+    const uint8_t *ref[3] = {e->d_rec[gr.ref_idx][0] + oy, e->d_rec[gr.ref_idx][1] + oc, e->d_rec[gr.ref_idx][2] + oc};
+    uint8_t *rec[3] = {e->d_rec[gr.ref_idx ^ 1][0] + oy, e->d_rec[gr.ref_idx ^ 1][1] + oc, e->d_rec[gr.ref_idx ^ 1][2] + oc};
+    b2_mbinfo_t *info = e->d_info[set] + om;
+    b2_mbcoef_t *coef = e->d_coef[set] + om;
+    const size_t n = (size_t)e->nmb * ns;
+
+    {   // K0: raw picture -> padded planes (consecutive slots are `in_ring` pictures apart in the ring buffer)
+        KScope k(e, st, 0);
+        if (b2_launch_convert(c.in_fmt, e->d_in + in_off(e, gr.slot0, ring), e->in_stride * c.in_ring, curw[0], curw[1], curw[2],
+                              e->pitch, e->pitchc, e->stride_y, e->stride_c, c.width, c.height, ns, st))
+            return -1;
+    }
+    ENG_OK(cudaEventRecord(gr.ev_k0[ring], st));
+    {
+        KScope k(e, st, 1);
+        if (b2_launch_extend_border(curw[0], e->pitch, e->rows, ns, B2_PAD, e->w16, e->h16, st)) return -1;
+        if (b2_launch_extend_border(curw[1], e->pitchc, e->rowsc, ns, B2_PADC, e->w16 / 2, e->h16 / 2, st)) return -1;
+        if (b2_launch_extend_border(curw[2], e->pitchc, e->rowsc, ns, B2_PADC, e->w16 / 2, e->h16 / 2, st)) return -1;
+        e->launches += 2;
+    }
+    ENG_OK(cudaMemsetAsync(info, 0, n * sizeof(b2_mbinfo_t), st));
+    if (is_p) {
+        {
+            KScope k(e, st, 2);
+            if (b2_launch_me_fullpel(c.merange, &gr.tm_cur, &gr.tm_ref[gr.ref_idx], e->mbw, e->mbh, ns, e->d_prev_mv + om, e->lambda,
+                                     e->d_mvf + om, e->d_cost_full + om, st))
+                return -1;
+        }
+        {
+            KScope k(e, st, 3);
+            if (b2_launch_me_subpel(cur[0], ref[0], e->pitch, e->stride_y, e->mbw, e->mbh, ns, e->d_mvf + om, e->d_prev_mv + om,
+                                    e->lambda, c.subpel, e->d_mvq + om, e->d_cost_inter + om, st))
+                return -1;
+        }
+    }
+    if (do_intra) {
+        KScope k(e, st, 4);
+        if (b2_launch_intra_analyse(cur[0], cur[1], cur[2], e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, ns,
+                                    e->lambda, info, e->d_c16 + om, e->d_c4 + om, st))
+            return -1;
+    }
+    {
+        KScope k(e, st, 5);
+        if (b2_launch_decide_inter(cur, ref, rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, ns, is_p, do_intra,
+                                   c.qp, e->d_mvq + om, e->d_cost_inter + om, e->d_c16 + om, e->d_c4 + om, info, coef,
+                                   e->d_prev_mv + om, st))
+            return -1;
+    }
+    if (do_intra) {
+        KScope k(e, st, 6);
+        if (b2_launch_intra_recon(cur, rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, ns, c.qp, info, coef, st))
+            return -1;
+    }
+    {
+        KScope k(e, st, 7);
+        if (b2_launch_extend_border(rec[0], e->pitch, e->rows, ns, B2_PAD, e->w16, e->h16, st)) return -1;
+        if (b2_launch_extend_border(rec[1], e->pitchc, e->rowsc, ns, B2_PADC, e->w16 / 2, e->h16 / 2, st)) return -1;
+        if (b2_launch_extend_border(rec[2], e->pitchc, e->rowsc, ns, B2_PADC, e->w16 / 2, e->h16 / 2, st)) return -1;
+        e->launches += 2;
+    }
+    ENG_OK(cudaEventRecord(gr.ev_enc[set], st));
+    gr.ref_idx ^= 1;
+    gr.res_set = set;
+    gr.last_n = ns;
+    return 0;
+}
+
+extern "C" int b2_engine_encode_group(b2_engine_t *e, int group, int frame_type, int ring)
+{
+    if (group < 0 || group >= (int)e->groups.size() || ring < 0 || ring >= e->cfg.in_ring) return -1;
+    cudaSetDevice(e->cfg.device);
+    return encode_group(e, e->groups[group], frame_type, e->groups[group].n, ring);
+}
+
 extern "C" int b2_engine_encode(b2_engine_t *e, int frame_type, int nslots, int ring)
 {
     if (nslots < 1 || nslots > e->cfg.slots || ring < 0 || ring >= e->cfg.in_ring) return -1;
     cudaSetDevice(e->cfg.device);
-    const b2_engine_cfg_t &c = e->cfg;
-    const int is_p = frame_type == B2_FRAME_P;
-    const int do_intra = !is_p || c.intra_in_p;
-    const int set = e->res_set ^ 1;
-    if (e->h2d_pending[ring]) { ENG_OK(cudaStreamWaitEvent(e->st, e->ev_h2d[ring], 0)); e->h2d_pending[ring] = 0; }
-    if (e->d2h_used[set]) ENG_OK(cudaStreamWaitEvent(e->st, e->ev_d2h[set], 0));     // result set still being copied out
-    const uint8_t *cur[3] = {e->d_cur[0], e->d_cur[1], e->d_cur[2]};
-    const uint8_t *ref[3] = {e->d_rec[e->ref_idx][0], e->d_rec[e->ref_idx][1], e->d_rec[e->ref_idx][2]};
-    uint8_t *rec[3] = {e->d_rec[e->ref_idx ^ 1][0], e->d_rec[e->ref_idx ^ 1][1], e->d_rec[e->ref_idx ^ 1][2]};
-    const size_t n = (size_t)e->nmb * nslots;
-
-    {   // K0: raw picture -> padded planes (slots are `in_ring` pictures apart in the ring buffer)
-        KScope k(e, 0);
-        if (b2_launch_convert(c.in_fmt, e->d_in + (size_t)ring * e->in_stride, e->in_stride * c.in_ring, e->d_cur[0], e->d_cur[1],
-                              e->d_cur[2], e->pitch, e->pitchc, e->stride_y, e->stride_c, c.width, c.height, nslots, e->st))
-            return -1;
+    for (auto &gr : e->groups) {
+        const int ns = nslots - gr.slot0 < gr.n ? nslots - gr.slot0 : gr.n;
+        if (ns <= 0) continue;
+        if (encode_group(e, gr, frame_type, ns, ring)) return -1;
     }
-    ENG_OK(cudaEventRecord(e->ev_k0[ring], e->st));
-    {
-        KScope k(e, 1);
-        if (b2_launch_extend_border(e->d_cur[0], e->pitch, e->rows, nslots, B2_PAD, e->w16, e->h16, e->st)) return -1;
-        if (b2_launch_extend_border(e->d_cur[1], e->pitchc, e->rowsc, nslots, B2_PADC, e->w16 / 2, e->h16 / 2, e->st)) return -1;
-        if (b2_launch_extend_border(e->d_cur[2], e->pitchc, e->rowsc, nslots, B2_PADC, e->w16 / 2, e->h16 / 2, e->st)) return -1;
-        e->launches += 2;
-    }
-    ENG_OK(cudaMemsetAsync(e->d_info[set], 0, n * sizeof(b2_mbinfo_t), e->st));
-    if (is_p) {
-        {
-            KScope k(e, 2);
-            if (b2_launch_me_fullpel(c.merange, &e->tm_cur, &e->tm_ref[e->ref_idx], e->mbw, e->mbh, nslots, e->d_prev_mv,
-                                     e->lambda, e->d_mvf, e->d_cost_full, e->st))
-                return -1;
-        }
-        {
-            KScope k(e, 3);
-            if (b2_launch_me_subpel(e->d_cur[0], ref[0], e->pitch, e->stride_y, e->mbw, e->mbh, nslots, e->d_mvf, e->d_prev_mv,
-                                    e->lambda, c.subpel, e->d_mvq, e->d_cost_inter, e->st))
-                return -1;
-        }
-    }
-    if (do_intra) {
-        KScope k(e, 4);
-        if (b2_launch_intra_analyse(e->d_cur[0], e->d_cur[1], e->d_cur[2], e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw,
-                                    e->mbh, nslots, e->lambda, e->d_info[set], e->d_c16, e->d_c4, e->st))
-            return -1;
-    }
-    {
-        KScope k(e, 5);
-        if (b2_launch_decide_inter(cur, ref, rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, nslots, is_p,
-                                   do_intra, c.qp, e->d_mvq, e->d_cost_inter, e->d_c16, e->d_c4, e->d_info[set], e->d_coef[set],
-                                   e->d_prev_mv, e->st))
-            return -1;
-    }
-    if (do_intra) {
-        KScope k(e, 6);
-        if (b2_launch_intra_recon(cur, rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, nslots, c.qp,
-                                  e->d_info[set], e->d_coef[set], e->st))
-            return -1;
-    }
-    {
-        KScope k(e, 7);
-        if (b2_launch_extend_border(rec[0], e->pitch, e->rows, nslots, B2_PAD, e->w16, e->h16, e->st)) return -1;
-        if (b2_launch_extend_border(rec[1], e->pitchc, e->rowsc, nslots, B2_PADC, e->w16 / 2, e->h16 / 2, e->st)) return -1;
-        if (b2_launch_extend_border(rec[2], e->pitchc, e->rowsc, nslots, B2_PADC, e->w16 / 2, e->h16 / 2, e->st)) return -1;
-        e->launches += 2;
-    }
-    ENG_OK(cudaEventRecord(e->ev_enc[set], e->st));
-    e->ref_idx ^= 1;
-    e->res_set = set;
     return 0;
+}
+
+static int d2h_group(b2_engine *e, Group &gr, int ns)
+{
+    const int set = gr.res_set;
+    const size_t om = (size_t)gr.slot0 * e->nmb, n = (size_t)e->nmb * ns;
+    ENG_OK(cudaStreamWaitEvent(e->st_out, gr.ev_enc[set], 0));
+    ENG_OK(cudaMemcpyAsync(e->h_info[set] + om, e->d_info[set] + om, n * sizeof(b2_mbinfo_t), cudaMemcpyDeviceToHost, e->st_out));
+    ENG_OK(cudaMemcpyAsync(e->h_coef[set] + om, e->d_coef[set] + om, n * sizeof(b2_mbcoef_t), cudaMemcpyDeviceToHost, e->st_out));
+    ENG_OK(cudaEventRecord(gr.ev_d2h[set], e->st_out));
+    gr.d2h_used[set] = true;
+    gr.host_set = set;
+    return 0;
+}
+
+extern "C" int b2_engine_d2h_group(b2_engine_t *e, int group)
+{
+    if (group < 0 || group >= (int)e->groups.size()) return -1;
+    cudaSetDevice(e->cfg.device);
+    Group &gr = e->groups[group];
+    return d2h_group(e, gr, gr.last_n > 0 ? gr.last_n : gr.n);
 }
 
 extern "C" int b2_engine_d2h(b2_engine_t *e, int nslots)
 {
     if (nslots < 1 || nslots > e->cfg.slots) return -1;
     cudaSetDevice(e->cfg.device);
-    const int set = e->res_set;
-    const size_t n = (size_t)e->nmb * nslots;
-    ENG_OK(cudaStreamWaitEvent(e->st_out, e->ev_enc[set], 0));
-    ENG_OK(cudaMemcpyAsync(e->h_info[set], e->d_info[set], n * sizeof(b2_mbinfo_t), cudaMemcpyDeviceToHost, e->st_out));
-    ENG_OK(cudaMemcpyAsync(e->h_coef[set], e->d_coef[set], n * sizeof(b2_mbcoef_t), cudaMemcpyDeviceToHost, e->st_out));
-    ENG_OK(cudaEventRecord(e->ev_d2h[set], e->st_out));
-    e->d2h_used[set] = true;
-    e->host_set = set;
+    for (auto &gr : e->groups) {
+        const int ns = nslots - gr.slot0 < gr.n ? nslots - gr.slot0 : gr.n;
+        if (ns <= 0) continue;
+        if (d2h_group(e, gr, ns)) return -1;
+    }
     return 0;
 }
 
@@ -359,18 +444,26 @@ extern "C" int b2_engine_sync(b2_engine_t *e)
 {
     cudaSetDevice(e->cfg.device);
     ENG_OK(cudaStreamSynchronize(e->st_in));
+    for (auto &gr : e->groups) ENG_OK(cudaStreamSynchronize(gr.st));
     ENG_OK(cudaStreamSynchronize(e->st));
     ENG_OK(cudaStreamSynchronize(e->st_out));
     prof_collect(e);
     return 0;
 }
 
-extern "C" const b2_mbinfo_t *b2_engine_info(b2_engine_t *e, int slot) { return e->h_info[e->host_set] + (size_t)slot * e->nmb; }
-extern "C" const b2_mbcoef_t *b2_engine_coef(b2_engine_t *e, int slot) { return e->h_coef[e->host_set] + (size_t)slot * e->nmb; }
+extern "C" const b2_mbinfo_t *b2_engine_info(b2_engine_t *e, int slot)
+{
+    Group *gr = group_of(e, slot);
+    return gr ? e->h_info[gr->host_set] + (size_t)slot * e->nmb : nullptr;
+}
+extern "C" const b2_mbcoef_t *b2_engine_coef(b2_engine_t *e, int slot)
+{
+    Group *gr = group_of(e, slot);
+    return gr ? e->h_coef[gr->host_set] + (size_t)slot * e->nmb : nullptr;
+}
 
 static int get_planes(b2_engine *e, uint8_t *const src[3], int slot, uint8_t *y, uint8_t *u, uint8_t *v)
 {
-    if (slot < 0 || slot >= e->cfg.slots) return -1;
     cudaSetDevice(e->cfg.device);
     if (b2_engine_sync(e)) return -1;
     uint8_t *dst[3] = {y, u, v};
@@ -384,10 +477,13 @@ static int get_planes(b2_engine *e, uint8_t *const src[3], int slot, uint8_t *y,
 }
 extern "C" int b2_engine_get_recon(b2_engine_t *e, int slot, uint8_t *y, uint8_t *u, uint8_t *v)
 {
-    return get_planes(e, e->d_rec[e->ref_idx], slot, y, u, v);
+    Group *gr = group_of(e, slot);
+    if (!gr) return -1;
+    return get_planes(e, e->d_rec[gr->ref_idx], slot, y, u, v);
 }
 extern "C" int b2_engine_get_cur(b2_engine_t *e, int slot, uint8_t *y, uint8_t *u, uint8_t *v)
 {
+    if (!group_of(e, slot)) return -1;
     return get_planes(e, e->d_cur, slot, y, u, v);
 }
 extern "C" int b2_engine_get_stage(b2_engine_t *e, int slot, int what, void *out)
@@ -408,10 +504,20 @@ extern "C" int b2_engine_get_stage(b2_engine_t *e, int slot, int what, void *out
     return 0;
 }
 
-extern "C" int b2_engine_timer_start(b2_engine_t *e) { cudaSetDevice(e->cfg.device); ENG_OK(cudaEventRecord(e->ev_t0, e->st)); return 0; }
+// The timer brackets ALL group streams: t0 is recorded after every group stream has reached this point
+// and every group stream then waits for t0; t1 is recorded after every group stream has drained.
+extern "C" int b2_engine_timer_start(b2_engine_t *e)
+{
+    cudaSetDevice(e->cfg.device);
+    for (auto &gr : e->groups) { ENG_OK(cudaEventRecord(gr.ev_join, gr.st)); ENG_OK(cudaStreamWaitEvent(e->st, gr.ev_join, 0)); }
+    ENG_OK(cudaEventRecord(e->ev_t0, e->st));
+    for (auto &gr : e->groups) ENG_OK(cudaStreamWaitEvent(gr.st, e->ev_t0, 0));
+    return 0;
+}
 extern "C" int b2_engine_timer_stop(b2_engine_t *e, float *ms)
 {
     cudaSetDevice(e->cfg.device);
+    for (auto &gr : e->groups) { ENG_OK(cudaEventRecord(gr.ev_join, gr.st)); ENG_OK(cudaStreamWaitEvent(e->st, gr.ev_join, 0)); }
     ENG_OK(cudaEventRecord(e->ev_t1, e->st));
     ENG_OK(cudaEventSynchronize(e->ev_t1));
     ENG_OK(cudaEventElapsedTime(ms, e->ev_t0, e->ev_t1));
