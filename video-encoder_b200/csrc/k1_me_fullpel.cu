@@ -94,8 +94,9 @@ k1_me_fullpel_kernel(const __grid_constant__ CUtensorMap tm_cur,
         int m = i / ND, d = i - m * ND;
         int px = 0, py = 0;
         if (pmv != nullptr && m < nmb) { b2_mv_t p = pmv[mb_base + m]; px = p.x; py = p.y; }
-        s_costx[i] = (uint32_t)(lambda * b2_mvbits(4 * (d - R) - px));
-        s_costy[i] = (uint32_t)(lambda * b2_mvbits(4 * (d - R) - py));
+        // pre-shifted so that key = (SAD << 13) + kx + ky = ((SAD + costx + costy) << 13) | scan index
+        s_costx[i] = ((uint32_t)(lambda * b2_mvbits(4 * (d - R) - px)) << 13) + (uint32_t)d;
+        s_costy[i] = ((uint32_t)(lambda * b2_mvbits(4 * (d - R) - py)) << 13) + (uint32_t)(d * ND);
     }
     if (tid < NMB) s_best[tid] = 0xffffffffu;
 
@@ -163,13 +164,10 @@ k1_me_fullpel_kernel(const __grid_constant__ CUtensorMap tm_cur,
 
         uint32_t key = 0xffffffffu;
         if (active) {
-            const uint32_t cx = s_costx[m * ND + dxi];
+            const uint32_t kx = s_costx[m * ND + dxi];
+            const uint32_t *ky = s_costy + m * ND + g * K;
 #pragma unroll
-            for (int k = 0; k < K; k++) {
-                const int dyi = g * K + k;
-                const uint32_t cost = acc[k] + cx + s_costy[m * ND + dyi];
-                key = min(key, (cost << 13) | (uint32_t)(dyi * ND + dxi));
-            }
+            for (int k = 0; k < K; k++) key = min(key, acc[k] * 8192u + (kx + ky[k]));
         }
         const int m0 = __shfl_sync(0xffffffffu, m, 0);
         if (__all_sync(0xffffffffu, m == m0)) {

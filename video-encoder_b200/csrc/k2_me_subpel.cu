@@ -17,49 +17,50 @@ namespace {
 
 constexpr int K2_THREADS = 160;
 
+// All four sample planes live in ONE shared byte array with a common row pitch, so that a candidate is
+// "average of two byte planes" with two base offsets chosen once per thread -- no per-pixel switch.
+constexpr int KP = 24;                                    // common row pitch (bytes)
+constexpr int OFF_G = 0;                                  // G : 22 rows, origin (X,Y) = (-3,-3)
+constexpr int OFF_B = OFF_G + 22 * KP;                    // b : 18 rows, origin (-1,-1)
+constexpr int OFF_H = OFF_B + 18 * KP;                    // h : 17 rows, origin (-1,-1)
+constexpr int OFF_J = OFF_H + 17 * KP;                    // j : 17 rows, origin (-1,-1)
+constexpr int PLANES_BYTES = OFF_J + 17 * KP;
+
 struct K2Smem {
-    uint8_t G[22][24];        // integer samples, rows/cols -3..18 around the full-pel position
+    uint8_t P[PLANES_BYTES];  // G | b | h | j
     int16_t B1[22][18];       // unrounded horizontal half samples: rows -3..18, cols -1..15
-    uint8_t Bq[18][20];       // b: rows -1..16, cols -1..15
-    uint8_t H[17][20];        // h: rows -1..15, cols -1..16
-    uint8_t J[17][20];        // j: rows -1..15, cols -1..15
     uint8_t cur[16][16];
     uint32_t cost[9];
     int best;
 };
 
-// sample at integer base (X,Y) in [-1,16] with quarter-pel fraction (fx,fy), from the planes
-__device__ __forceinline__ int plane_sample(const K2Smem &s, int X, int Y, int fx, int fy)
+// byte offset inside K2Smem::P of sample (X,Y) of plane p (0 G, 1 b, 2 h, 3 j)
+__device__ __forceinline__ int plane_off(int p, int X, int Y)
 {
-#define PG(x, y) ((int)s.G[(y) + 3][(x) + 3])
-#define PB(x, y) ((int)s.Bq[(y) + 1][(x) + 1])
-#define PH(x, y) ((int)s.H[(y) + 1][(x) + 1])
-#define PJ(x, y) ((int)s.J[(y) + 1][(x) + 1])
-#define AV(a, b) (((a) + (b) + 1) >> 1)
-    switch (fy * 4 + fx) {
-    case 0: return PG(X, Y);
-    case 1: return AV(PG(X, Y), PB(X, Y));
-    case 2: return PB(X, Y);
-    case 3: return AV(PG(X + 1, Y), PB(X, Y));
-    case 4: return AV(PG(X, Y), PH(X, Y));
-    case 5: return AV(PB(X, Y), PH(X, Y));
-    case 6: return AV(PB(X, Y), PJ(X, Y));
-    case 7: return AV(PB(X, Y), PH(X + 1, Y));
-    case 8: return PH(X, Y);
-    case 9: return AV(PH(X, Y), PJ(X, Y));
-    case 10: return PJ(X, Y);
-    case 11: return AV(PJ(X, Y), PH(X + 1, Y));
-    case 12: return AV(PG(X, Y + 1), PH(X, Y));
-    case 13: return AV(PH(X, Y), PB(X, Y + 1));
-    case 14: return AV(PJ(X, Y), PB(X, Y + 1));
-    default: return AV(PH(X + 1, Y), PB(X, Y + 1));
-    }
-#undef PG
-#undef PB
-#undef PH
-#undef PJ
-#undef AV
+    return p == 0 ? OFF_G + (Y + 3) * KP + X + 3
+         : (p == 1 ? OFF_B : p == 2 ? OFF_H : OFF_J) + (Y + 1) * KP + X + 1;
 }
+
+// The two planes (and their integer displacements) whose rounded average is the quarter-pel sample with
+// fraction (fx,fy) -- Table of 8.4.2.2.1; single-plane positions use the same plane twice ((a+a+1)>>1 = a).
+// Packed per entry: planeA | dxA<<2 | dyA<<3 | planeB<<4 | dxB<<6 | dyB<<7
+__device__ __constant__ uint8_t c_qpel_pair[16] = {
+    /* 0 G,G        */ 0 | (0 << 4),
+    /* 1 G,b        */ 0 | (1 << 4),
+    /* 2 b,b        */ 1 | (1 << 4),
+    /* 3 G(1,0),b   */ 0 | (1 << 2) | (1 << 4),
+    /* 4 G,h        */ 0 | (2 << 4),
+    /* 5 b,h        */ 1 | (2 << 4),
+    /* 6 b,j        */ 1 | (3 << 4),
+    /* 7 b,h(1,0)   */ 1 | (2 << 4) | (1 << 6),
+    /* 8 h,h        */ 2 | (2 << 4),
+    /* 9 h,j        */ 2 | (3 << 4),
+    /* 10 j,j       */ 3 | (3 << 4),
+    /* 11 j,h(1,0)  */ 3 | (2 << 4) | (1 << 6),
+    /* 12 G(0,1),h  */ 0 | (1 << 3) | (2 << 4),
+    /* 13 h,b(0,1)  */ 2 | (1 << 4) | (1 << 7),
+    /* 14 j,b(0,1)  */ 3 | (1 << 4) | (1 << 7),
+    /* 15 h(1,0),b(0,1) */ 2 | (1 << 2) | (1 << 4) | (1 << 7)};
 
 __device__ __constant__ int8_t c_subpel_off[9][2] = {{0, 0}, {-1, -1}, {0, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {0, 1}, {1, 1}};
 
@@ -67,14 +68,19 @@ __device__ __constant__ int8_t c_subpel_off[9][2] = {{0, 0}, {-1, -1}, {0, -1}, 
 // quarter-pels from the full-pel position
 __device__ __forceinline__ uint32_t cand_block_satd(const K2Smem &s, int blk, int cx, int cy)
 {
-    const int ix = cx >> 2, iy = cy >> 2, fx = cx & 3, fy = cy & 3;
+    const int ix = cx >> 2, iy = cy >> 2;
+    const int e = c_qpel_pair[(cy & 3) * 4 + (cx & 3)];
     const int bx = (blk & 3) * 4, by = (blk >> 2) * 4;
+    const uint8_t *pa = s.P + plane_off(e & 3, bx + ix + ((e >> 2) & 1), by + iy + ((e >> 3) & 1));
+    const uint8_t *pb = s.P + plane_off((e >> 4) & 3, bx + ix + ((e >> 6) & 1), by + iy + ((e >> 7) & 1));
     int d[16];
 #pragma unroll
-    for (int y = 0; y < 4; y++)
+    for (int y = 0; y < 4; y++) {
+        const uint32_t cw = *(const uint32_t *)&s.cur[by + y][bx];
 #pragma unroll
         for (int x = 0; x < 4; x++)
-            d[y * 4 + x] = (int)s.cur[by + y][bx + x] - plane_sample(s, bx + x + ix, by + y + iy, fx, fy);
+            d[y * 4 + x] = (int)((cw >> (8 * x)) & 255u) - (((int)pa[y * KP + x] + (int)pb[y * KP + x] + 1) >> 1);
+    }
     return b2::satd4x4(d);
 }
 
@@ -83,7 +89,7 @@ k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__
                     int mbw, int mbh, const b2_mv_t *__restrict__ mv_full, const b2_mv_t *__restrict__ pmv,
                     int lambda, int subpel, b2_mv_t *__restrict__ mv_out, uint32_t *__restrict__ cost_out)
 {
-    __shared__ K2Smem s;
+    __shared__ __align__(16) K2Smem s;
     const int tid = threadIdx.x;
     const int mbx = blockIdx.x, mby = blockIdx.y, frame = blockIdx.z;
     const size_t mbi = ((size_t)frame * mbh + mby) * mbw + mbx;
@@ -94,41 +100,46 @@ k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__
     const uint8_t *cplane = cur + frame * plane_stride + (size_t)(B2_PAD + mby * 16) * pitch + B2_PAD + mbx * 16;
     const uint8_t *rplane = ref + frame * plane_stride + (size_t)(B2_PAD + mby * 16 + mvf.y - 3) * pitch + B2_PAD +
                             mbx * 16 + mvf.x - 3;
-    for (int i = tid; i < 22 * 22; i += K2_THREADS) {
-        int r = i / 22, c = i - r * 22;
-        s.G[r][c] = rplane[(size_t)r * pitch + c];
+    uint8_t *PG = s.P + OFF_G, *PB = s.P + OFF_B, *PH = s.P + OFF_H, *PJ = s.P + OFF_J;
+    // 22x22 reference patch; thread -> (row, col) without divisions: 8 rows of 22 per pass (176 > 160: two passes of 11 rows)
+    {
+        const int c = tid % 22, r0 = tid / 22;              // r0 in 0..7 for tid < 154 (160 threads -> 7 full rows + 6)
+        if (tid < 154)
+            for (int r = r0; r < 22; r += 7) PG[r * KP + c] = rplane[(size_t)r * pitch + c];
     }
-    for (int i = tid; i < 64; i += K2_THREADS) {
-        int r = i >> 2, c = i & 3;
+    if (tid < 64) {
+        const int r = tid >> 2, c = tid & 3;
         *(uint32_t *)&s.cur[r][c * 4] = *(const uint32_t *)(cplane + (size_t)r * pitch + c * 4);
     }
     if (tid < 9) s.cost[tid] = 0;
     __syncthreads();
 
-    // horizontal unrounded half samples (all 22 rows) and vertical half samples
-    for (int i = tid; i < 22 * 17 + 17 * 18; i += K2_THREADS) {
-        if (i < 22 * 17) {
-            int r = i / 17, c = i - r * 17;               // row r <-> Y=r-3, col c <-> X=c-1 ; G col = X+3 = c+2
-            const uint8_t *q = &s.G[r][c + 2];
-            s.B1[r][c] = (int16_t)b2::tap6(q[-2], q[-1], q[0], q[1], q[2], q[3]);
-        } else {
-            int k = i - 22 * 17;
-            int r = k / 18, c = k - r * 18;               // Y=r-1, X=c-1 ; G[Y+3][X+3] = G[r+2][c+2]
-            int v = b2::tap6(s.G[r][c + 2], s.G[r + 1][c + 2], s.G[r + 2][c + 2], s.G[r + 3][c + 2], s.G[r + 4][c + 2],
-                             s.G[r + 5][c + 2]);
-            s.H[r][c] = (uint8_t)b2_clip255((v + 16) >> 5);
-        }
+    // horizontal unrounded half samples b1 (22 rows x 17 cols) and vertical half samples h (17 rows x 18 cols)
+    {
+        const int c = tid % 17, r0 = tid / 17;              // 153 threads -> 9 rows per pass
+        if (tid < 153)
+            for (int r = r0; r < 22; r += 9) {
+                const uint8_t *q = PG + r * KP + c + 2;       // row r <-> Y=r-3, col c <-> X=c-1
+                s.B1[r][c] = (int16_t)b2::tap6(q[-2], q[-1], q[0], q[1], q[2], q[3]);
+            }
+        const int c2 = tid % 18, r2 = tid / 18;             // 144 threads -> 8 rows per pass
+        if (tid < 144)
+            for (int r = r2; r < 17; r += 8) {                // Y=r-1, X=c2-1 ; G[Y+3][X+3] = G[r+2][c2+2]
+                const uint8_t *q = PG + r * KP + c2 + 2;
+                const int v = b2::tap6(q[0], q[KP], q[2 * KP], q[3 * KP], q[4 * KP], q[5 * KP]);
+                PH[r * KP + c2] = (uint8_t)b2_clip255((v + 16) >> 5);
+            }
     }
     __syncthreads();
-    for (int i = tid; i < 18 * 17 + 17 * 17; i += K2_THREADS) {
-        if (i < 18 * 17) {
-            int r = i / 17, c = i - r * 17;               // Y=r-1 -> B1 row Y+3 = r+2
-            s.Bq[r][c] = (uint8_t)b2_clip255((s.B1[r + 2][c] + 16) >> 5);
-        } else {
-            int k = i - 18 * 17;
-            int r = k / 17, c = k - r * 17;               // Y=r-1 -> B1 rows Y-2+3 .. Y+3+3 = r .. r+5
-            int v = b2::tap6(s.B1[r][c], s.B1[r + 1][c], s.B1[r + 2][c], s.B1[r + 3][c], s.B1[r + 4][c], s.B1[r + 5][c]);
-            s.J[r][c] = (uint8_t)b2_clip255((v + 512) >> 10);
+    {
+        const int c = tid % 17, r0 = tid / 17;              // 153 threads -> 9 rows per pass
+        if (tid < 153) {
+            for (int r = r0; r < 18; r += 9)                  // b: Y=r-1 -> B1 row r+2
+                PB[r * KP + c] = (uint8_t)b2_clip255((s.B1[r + 2][c] + 16) >> 5);
+            for (int r = r0; r < 17; r += 9) {                // j: Y=r-1 -> B1 rows r..r+5
+                const int v = b2::tap6(s.B1[r][c], s.B1[r + 1][c], s.B1[r + 2][c], s.B1[r + 3][c], s.B1[r + 4][c], s.B1[r + 5][c]);
+                PJ[r * KP + c] = (uint8_t)b2_clip255((v + 512) >> 10);
+            }
         }
     }
     __syncthreads();
