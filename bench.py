@@ -88,10 +88,12 @@ class ClockSampler:
 
 
 def fill_inputs(eng, b2oracle, rank):
+    import sharding
     n_y = W * H
+    streams = sharding.slot_streams(rank, eng.slots)            # disjoint synthetic streams per rank
     for s in range(eng.slots):
         for r in range(eng.ring):
-            y, u, v = b2oracle.synth_frame(W, H, r, rank * eng.slots + s)
+            y, u, v = b2oracle.synth_frame(W, H, r, streams[s])
             buf = eng.host_input(s, r)
             buf[:n_y] = y.ravel(); buf[n_y:n_y + u.size] = u.ravel(); buf[n_y + u.size:] = v.ravel()
 
