@@ -85,7 +85,8 @@ __device__ __forceinline__ int quant4x4(const int w[16], int z[16], const QParam
     for (int i = 0; i < 16; i++) {
         if (i == 0 && skip_dc) { z[0] = 0; continue; }
         int a = abs(w[i]);
-        int v = (int)(((long long)a * q.mf[pos_class(i)] + q.f) >> q.qbits);
+        // |w| <= 9180 and mf <= 13107: the product plus the dead-zone offset stays below 2^31
+        int v = (int)(((uint32_t)a * (uint32_t)q.mf[pos_class(i)] + (uint32_t)q.f) >> q.qbits);
         z[i] = w[i] < 0 ? -v : v;
         nnz += v != 0;
     }
@@ -94,7 +95,8 @@ __device__ __forceinline__ int quant4x4(const int w[16], int z[16], const QParam
 __device__ __forceinline__ int quant_dc(int x, const QParams &q)
 {
     int a = abs(x);
-    int v = (int)(((long long)a * q.mf[0] + 2 * q.f) >> (q.qbits + 1));
+    // |x| <= 16*4080/2 (luma DC Hadamard) -> a*mf <= 4.3e8 < 2^31
+    int v = (int)(((uint32_t)a * (uint32_t)q.mf[0] + 2u * (uint32_t)q.f) >> (q.qbits + 1));
     return x < 0 ? -v : v;
 }
 // normative scaling (8.5.12.1), flat matrices; w[0] untouched when skip_dc
