@@ -76,3 +76,53 @@ int b2_launch_extend_border(uint8_t *d_planes, int pitch, int rows, int nplanes,
     B2_CUDA_OK(cudaGetLastError());
     return 0;
 }
+
+// ---- K6 (frame form): borders of Y, U and V of every frame in ONE launch, visiting border words only -----------
+// Per plane the border is flattened into a 1-D list of 32-bit words: first the 2*pad full-width rows above and below
+// the picture, then the left+right pad words of the ih interior rows.  blockIdx.y = frame * 3 + plane.
+__global__ void __launch_bounds__(128)
+k6_extend_border_yuv_kernel(uint8_t *y, uint8_t *u, uint8_t *v, int pitch, int pitchc, size_t stride_y, size_t stride_c,
+                            int w16, int h16)
+{
+    const int plane = blockIdx.y % 3, frame = blockIdx.y / 3;
+    const int pt = plane ? pitchc : pitch, pad = plane ? B2_PADC : B2_PAD;
+    const int iw = plane ? w16 >> 1 : w16, ih = plane ? h16 >> 1 : h16;
+    uint8_t *base = (plane == 0 ? y + frame * stride_y : (plane == 1 ? u : v) + frame * stride_c);
+    const int wpr = pt >> 2, nfull = 2 * pad * wpr;
+    const int lw = pad >> 2, rw = (pt - pad - iw) >> 2, side = lw + rw;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int row, wx;
+    if (t < nfull) {
+        const int r = t / wpr;
+        wx = t - r * wpr;
+        row = r < pad ? r : ih + r;           // r in [pad,2pad) -> rows ih+pad .. ih+2pad-1
+    } else {
+        t -= nfull;
+        const int r = t / side, k = t - r * side;
+        if (r >= ih) return;
+        row = pad + r;
+        wx = k < lw ? k : ((pad + iw) >> 2) + (k - lw);
+    }
+    const int x0 = wx * 4 - pad, yy = row - pad;
+    const int cy = min(max(yy, 0), ih - 1);
+    const uint8_t *src = base + (size_t)(cy + pad) * pt + pad;
+    uint32_t w = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        const int cx = min(max(x0 + b, 0), iw - 1);
+        w |= (uint32_t)src[cx] << (8 * b);
+    }
+    *(uint32_t *)(base + (size_t)row * pt + wx * 4) = w;
+}
+
+int b2_launch_extend_border_yuv(uint8_t *d_y, uint8_t *d_u, uint8_t *d_v, int pitch, int rows, int pitchc, int rowsc,
+                                size_t stride_y, size_t stride_c, int w16, int h16, int nframes, cudaStream_t st)
+{
+    (void)rows; (void)rowsc;
+    const int words = 2 * B2_PAD * (pitch / 4) + h16 * ((pitch - w16) / 4);      // luma is the largest plane
+    dim3 block(128);
+    dim3 grid((words + 127) / 128, 3 * nframes);
+    k6_extend_border_yuv_kernel<<<grid, block, 0, st>>>(d_y, d_u, d_v, pitch, pitchc, stride_y, stride_c, w16, h16);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+}

@@ -52,6 +52,7 @@ struct b2_engine {
     uint8_t *d_cur[3] = {}, *d_rec[2][3] = {};
     b2_mv_t *d_mvf = nullptr, *d_mvq = nullptr, *d_prev_mv = nullptr;
     uint32_t *d_cost_full = nullptr, *d_cost_inter = nullptr, *d_c16 = nullptr, *d_c4 = nullptr;
+    uint8_t *d_pred = nullptr;             // [S][nmb][256] motion-compensated luma prediction (K2 -> K5)
     b2_mbinfo_t *d_info[2] = {}, *h_info[2] = {};
     b2_mbcoef_t *d_coef[2] = {}, *h_coef[2] = {};
     std::vector<Group> groups;
@@ -105,6 +106,7 @@ static int engine_alloc(b2_engine *e)
     ENG_OK(cudaMalloc(&e->d_mvf, n * 4)); ENG_OK(cudaMalloc(&e->d_mvq, n * 4)); ENG_OK(cudaMalloc(&e->d_prev_mv, n * 4));
     ENG_OK(cudaMalloc(&e->d_cost_full, n * 4)); ENG_OK(cudaMalloc(&e->d_cost_inter, n * 4));
     ENG_OK(cudaMalloc(&e->d_c16, n * 4)); ENG_OK(cudaMalloc(&e->d_c4, n * 4));
+    ENG_OK(cudaMalloc(&e->d_pred, n * 256));
     ENG_OK(cudaMemset(e->d_prev_mv, 0, n * 4)); ENG_OK(cudaMemset(e->d_mvf, 0, n * 4)); ENG_OK(cudaMemset(e->d_mvq, 0, n * 4));
     ENG_OK(cudaMemset(e->d_cost_full, 0, n * 4)); ENG_OK(cudaMemset(e->d_cost_inter, 0, n * 4));
     ENG_OK(cudaMemset(e->d_c16, 0, n * 4)); ENG_OK(cudaMemset(e->d_c4, 0, n * 4));
@@ -184,7 +186,7 @@ extern "C" void b2_engine_destroy(b2_engine_t *e)
     cudaFree(e->d_in); cudaFreeHost(e->h_in);
     for (int p = 0; p < 3; p++) { cudaFree(e->d_cur[p]); cudaFree(e->d_rec[0][p]); cudaFree(e->d_rec[1][p]); }
     cudaFree(e->d_mvf); cudaFree(e->d_mvq); cudaFree(e->d_prev_mv); cudaFree(e->d_cost_full); cudaFree(e->d_cost_inter);
-    cudaFree(e->d_c16); cudaFree(e->d_c4);
+    cudaFree(e->d_c16); cudaFree(e->d_c4); cudaFree(e->d_pred);
     for (int s = 0; s < 2; s++) { cudaFree(e->d_info[s]); cudaFree(e->d_coef[s]); cudaFreeHost(e->h_info[s]); cudaFreeHost(e->h_coef[s]); }
     for (auto &gr : e->groups) {
         for (int s = 0; s < 2; s++) { if (gr.ev_enc[s]) cudaEventDestroy(gr.ev_enc[s]); if (gr.ev_d2h[s]) cudaEventDestroy(gr.ev_d2h[s]); }
@@ -336,10 +338,9 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
     ENG_OK(cudaEventRecord(gr.ev_k0[ring], st));
     {
         KScope k(e, st, 1);
-        if (b2_launch_extend_border(curw[0], e->pitch, e->rows, ns, B2_PAD, e->w16, e->h16, st)) return -1;
-        if (b2_launch_extend_border(curw[1], e->pitchc, e->rowsc, ns, B2_PADC, e->w16 / 2, e->h16 / 2, st)) return -1;
-        if (b2_launch_extend_border(curw[2], e->pitchc, e->rowsc, ns, B2_PADC, e->w16 / 2, e->h16 / 2, st)) return -1;
-        e->launches += 2;
+        if (b2_launch_extend_border_yuv(curw[0], curw[1], curw[2], e->pitch, e->rows, e->pitchc, e->rowsc, e->stride_y, e->stride_c,
+                                        e->w16, e->h16, ns, st))
+            return -1;
     }
     ENG_OK(cudaMemsetAsync(info, 0, n * sizeof(b2_mbinfo_t), st));
     if (is_p) {
@@ -352,7 +353,7 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
         {
             KScope k(e, st, 3);
             if (b2_launch_me_subpel(cur[0], ref[0], e->pitch, e->stride_y, e->mbw, e->mbh, ns, e->d_mvf + om, e->d_prev_mv + om,
-                                    e->lambda, c.subpel, e->d_mvq + om, e->d_cost_inter + om, st))
+                                    e->lambda, c.subpel, e->d_mvq + om, e->d_cost_inter + om, e->d_pred + om * 256, st))
                 return -1;
         }
     }
@@ -366,7 +367,7 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
         KScope k(e, st, 5);
         if (b2_launch_decide_inter(cur, ref, rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, ns, is_p, do_intra,
                                    c.qp, e->d_mvq + om, e->d_cost_inter + om, e->d_c16 + om, e->d_c4 + om, info, coef,
-                                   e->d_prev_mv + om, st))
+                                   e->d_prev_mv + om, e->d_pred + om * 256, st))
             return -1;
     }
     if (do_intra) {
@@ -376,10 +377,9 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
     }
     {
         KScope k(e, st, 7);
-        if (b2_launch_extend_border(rec[0], e->pitch, e->rows, ns, B2_PAD, e->w16, e->h16, st)) return -1;
-        if (b2_launch_extend_border(rec[1], e->pitchc, e->rowsc, ns, B2_PADC, e->w16 / 2, e->h16 / 2, st)) return -1;
-        if (b2_launch_extend_border(rec[2], e->pitchc, e->rowsc, ns, B2_PADC, e->w16 / 2, e->h16 / 2, st)) return -1;
-        e->launches += 2;
+        if (b2_launch_extend_border_yuv(rec[0], rec[1], rec[2], e->pitch, e->rows, e->pitchc, e->rowsc, e->stride_y, e->stride_c,
+                                        e->w16, e->h16, ns, st))
+            return -1;
     }
     ENG_OK(cudaEventRecord(gr.ev_enc[set], st));
     gr.ref_idx ^= 1;

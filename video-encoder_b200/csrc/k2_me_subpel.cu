@@ -87,7 +87,8 @@ __device__ __forceinline__ uint32_t cand_block_satd(const K2Smem &s, int blk, in
 __global__ void __launch_bounds__(K2_THREADS)
 k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ ref, int pitch, size_t plane_stride,
                     int mbw, int mbh, const b2_mv_t *__restrict__ mv_full, const b2_mv_t *__restrict__ pmv,
-                    int lambda, int subpel, b2_mv_t *__restrict__ mv_out, uint32_t *__restrict__ cost_out)
+                    int lambda, int subpel, b2_mv_t *__restrict__ mv_out, uint32_t *__restrict__ cost_out,
+                    uint8_t *__restrict__ pred_out)
 {
     __shared__ __align__(16) K2Smem s;
     const int tid = threadIdx.x;
@@ -186,6 +187,23 @@ k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__
         o.x = (int16_t)bx; o.y = (int16_t)by;
         mv_out[mbi] = o;
         cost_out[mbi] = best;
+        s.best = ((bx - mvf.x * 4) & 0xff) | (((by - mvf.y * 4) & 0xff) << 8);     // winner relative to the full-pel position
+    }
+    // the winner's motion-compensated luma block (K5 subtracts it from the source instead of interpolating again)
+    if (pred_out != nullptr) {
+        __syncthreads();
+        const int cx = (int)(int8_t)(s.best & 0xff), cy = (int)(int8_t)((s.best >> 8) & 0xff);
+        const int ix = cx >> 2, iy = cy >> 2;
+        const int e = c_qpel_pair[(cy & 3) * 4 + (cx & 3)];
+        if (tid < 64) {                                               // 4 pixels per thread: row r, columns 4c..4c+3
+            const int r = tid >> 2, c = (tid & 3) * 4;
+            const uint8_t *pa = s.P + plane_off(e & 3, c + ix + ((e >> 2) & 1), r + iy + ((e >> 3) & 1));
+            const uint8_t *pb = s.P + plane_off((e >> 4) & 3, c + ix + ((e >> 6) & 1), r + iy + ((e >> 7) & 1));
+            uint32_t w = 0;
+#pragma unroll
+            for (int x = 0; x < 4; x++) w |= (uint32_t)(((int)pa[x] + (int)pb[x] + 1) >> 1) << (8 * x);
+            *(uint32_t *)(pred_out + mbi * 256 + r * 16 + c) = w;
+        }
     }
 }
 
@@ -193,11 +211,11 @@ k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__
 
 int b2_launch_me_subpel(const uint8_t *d_cur, const uint8_t *d_ref, int pitch, size_t plane_stride, int mbw, int mbh,
                         int nframes, const b2_mv_t *d_mv_full, const b2_mv_t *d_pmv, int lambda, int subpel,
-                        b2_mv_t *d_mv_out, uint32_t *d_cost_out, cudaStream_t st)
+                        b2_mv_t *d_mv_out, uint32_t *d_cost_out, uint8_t *d_pred_out, cudaStream_t st)
 {
     dim3 grid(mbw, mbh, nframes);
     k2_me_subpel_kernel<<<grid, K2_THREADS, 0, st>>>(d_cur, d_ref, pitch, plane_stride, mbw, mbh, d_mv_full, d_pmv,
-                                                     lambda, subpel, d_mv_out, d_cost_out);
+                                                     lambda, subpel, d_mv_out, d_cost_out, d_pred_out);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -24,7 +24,8 @@ __global__ void __launch_bounds__(K5_WARPS * 32)
 k5_decide_inter_kernel(FramePlanes fp, int mbw, int mbh, int nmb_total, int is_p, int do_intra, int qp,
                        const b2_mv_t *__restrict__ mvq, const uint32_t *__restrict__ cost_inter,
                        const uint32_t *__restrict__ c16, const uint32_t *__restrict__ c4,
-                       b2_mbinfo_t *__restrict__ info, b2_mbcoef_t *__restrict__ coef, b2_mv_t *__restrict__ prev_mv_out)
+                       b2_mbinfo_t *__restrict__ info, b2_mbcoef_t *__restrict__ coef, b2_mv_t *__restrict__ prev_mv_out,
+                       const uint8_t *__restrict__ pred_y)
 {
     const int lane = threadIdx.x & 31;
     const int mbi = blockIdx.x * K5_WARPS + (threadIdx.x >> 5);
@@ -56,12 +57,8 @@ k5_decide_inter_kernel(FramePlanes fp, int mbw, int mbh, int nmb_total, int is_p
         const size_t off = (size_t)(B2_PAD + mby * 16 + by) * fp.pitch + B2_PAD + mbx * 16 + bx;
         int src[16], pred[16];
         load_src4x4(fp.cur[0] + frame * fp.stride_y + off, fp.pitch, src);
-        const uint8_t *rp = fp.ref[0] + frame * fp.stride_y + off + (ptrdiff_t)(mv.y >> 2) * fp.pitch + (mv.x >> 2);
-        const int fx = mv.x & 3, fy = mv.y & 3;
-#pragma unroll
-        for (int y = 0; y < 4; y++)
-#pragma unroll
-            for (int x = 0; x < 4; x++) pred[y * 4 + x] = qpel_sample(rp + (size_t)y * fp.pitch + x, fp.pitch, fx, fy);
+        // motion-compensated prediction of the chosen MV, produced by K2 from its half-sample planes
+        load_src4x4(pred_y + (size_t)mbi * 256 + by * 16 + bx, 16, pred);
         flags = code_luma4x4(src, pred, q, cf->blk[lane], fp.rec[0] + frame * fp.stride_y + off, fp.pitch) ? 1 : 0;
     }
     {
@@ -109,14 +106,14 @@ int b2_launch_decide_inter(const uint8_t *const cur[3], const uint8_t *const ref
                            int pitchc, size_t stride_y, size_t stride_c, int mbw, int mbh, int nframes, int is_p,
                            int do_intra, int qp, const b2_mv_t *d_mvq, const uint32_t *d_cost_inter, const uint32_t *d_c16,
                            const uint32_t *d_c4, b2_mbinfo_t *d_info, b2_mbcoef_t *d_coef, b2_mv_t *d_prev_mv,
-                           cudaStream_t st)
+                           const uint8_t *d_pred_y, cudaStream_t st)
 {
     FramePlanes fp;
     for (int i = 0; i < 3; i++) { fp.cur[i] = cur[i]; fp.ref[i] = ref ? ref[i] : nullptr; fp.rec[i] = rec[i]; }
     fp.pitch = pitch; fp.pitchc = pitchc; fp.stride_y = stride_y; fp.stride_c = stride_c;
     const int nmb = mbw * mbh * nframes;
     k5_decide_inter_kernel<<<(nmb + K5_WARPS - 1) / K5_WARPS, K5_WARPS * 32, 0, st>>>(
-        fp, mbw, mbh, nmb, is_p, do_intra, qp, d_mvq, d_cost_inter, d_c16, d_c4, d_info, d_coef, d_prev_mv);
+        fp, mbw, mbh, nmb, is_p, do_intra, qp, d_mvq, d_cost_inter, d_c16, d_c4, d_info, d_coef, d_prev_mv, d_pred_y);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
 }
