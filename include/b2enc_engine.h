@@ -62,6 +62,12 @@ int b2_engine_sync(b2_engine_t *e);
 const b2_mbinfo_t *b2_engine_info(b2_engine_t *e, int slot);
 const b2_mbcoef_t *b2_engine_coef(b2_engine_t *e, int slot);
 size_t b2_engine_result_bytes(const b2_engine_t *e);           /* D2H bytes per slot per frame */
+/* pipelined consumption: the ticket of the last b2_engine_d2h stays valid until the next but one b2_engine_d2h, so
+ * the host can entropy-code step t while the GPU already runs step t+1 */
+int b2_engine_ticket(const b2_engine_t *e);
+int b2_engine_wait_ticket(b2_engine_t *e, int ticket);         /* waits for that copy only, not for later GPU work */
+const b2_mbinfo_t *b2_engine_info_ticket(b2_engine_t *e, int ticket, int slot);
+const b2_mbcoef_t *b2_engine_coef_ticket(b2_engine_t *e, int ticket, int slot);
 
 /* parity / debugging (synchronous): coded-size planes, tight layout */
 int b2_engine_get_recon(b2_engine_t *e, int slot, uint8_t *y, uint8_t *u, uint8_t *v);

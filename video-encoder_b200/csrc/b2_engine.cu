@@ -56,6 +56,9 @@ struct b2_engine {
     b2_mbinfo_t *d_info[2] = {}, *h_info[2] = {};
     b2_mbcoef_t *d_coef[2] = {}, *h_coef[2] = {};
     std::vector<Group> groups;
+    // result tickets: which result set each group copied out in one of the last two b2_engine_d2h calls
+    struct Ticket { std::vector<int> set; } ticket[2];
+    int cur_ticket = 0;
     cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr;     // st: timer / join stream
     std::vector<cudaEvent_t> ev_h2d;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
@@ -432,12 +435,48 @@ extern "C" int b2_engine_d2h(b2_engine_t *e, int nslots)
 {
     if (nslots < 1 || nslots > e->cfg.slots) return -1;
     cudaSetDevice(e->cfg.device);
-    for (auto &gr : e->groups) {
+    e->cur_ticket ^= 1;
+    auto &tk = e->ticket[e->cur_ticket];
+    tk.set.assign(e->groups.size(), -1);
+    for (size_t g = 0; g < e->groups.size(); g++) {
+        Group &gr = e->groups[g];
         const int ns = nslots - gr.slot0 < gr.n ? nslots - gr.slot0 : gr.n;
         if (ns <= 0) continue;
         if (d2h_group(e, gr, ns)) return -1;
+        tk.set[g] = gr.host_set;
     }
     return 0;
+}
+
+// ticket of the most recent b2_engine_d2h; stays valid until the next but one b2_engine_d2h
+extern "C" int b2_engine_ticket(const b2_engine_t *e) { return e->cur_ticket; }
+// block until the copies of that b2_engine_d2h have landed (later work may still be running on the GPU)
+extern "C" int b2_engine_wait_ticket(b2_engine_t *e, int ticket)
+{
+    if (ticket < 0 || ticket > 1) return -1;
+    cudaSetDevice(e->cfg.device);
+    auto &tk = e->ticket[ticket];
+    for (size_t g = 0; g < tk.set.size(); g++)
+        if (tk.set[g] >= 0) ENG_OK(cudaEventSynchronize(e->groups[g].ev_d2h[tk.set[g]]));
+    return 0;
+}
+extern "C" const b2_mbinfo_t *b2_engine_info_ticket(b2_engine_t *e, int ticket, int slot)
+{
+    if (ticket < 0 || ticket > 1) return nullptr;
+    for (size_t g = 0; g < e->groups.size(); g++)
+        if (slot >= e->groups[g].slot0 && slot < e->groups[g].slot0 + e->groups[g].n && g < e->ticket[ticket].set.size() &&
+            e->ticket[ticket].set[g] >= 0)
+            return e->h_info[e->ticket[ticket].set[g]] + (size_t)slot * e->nmb;
+    return nullptr;
+}
+extern "C" const b2_mbcoef_t *b2_engine_coef_ticket(b2_engine_t *e, int ticket, int slot)
+{
+    if (ticket < 0 || ticket > 1) return nullptr;
+    for (size_t g = 0; g < e->groups.size(); g++)
+        if (slot >= e->groups[g].slot0 && slot < e->groups[g].slot0 + e->groups[g].n && g < e->ticket[ticket].set.size() &&
+            e->ticket[ticket].set[g] >= 0)
+            return e->h_coef[e->ticket[ticket].set[g]] + (size_t)slot * e->nmb;
+    return nullptr;
 }
 
 extern "C" int b2_engine_sync(b2_engine_t *e)

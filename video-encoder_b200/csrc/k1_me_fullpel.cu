@@ -21,13 +21,12 @@
 //  * Lanes of a warp are 32 consecutive dx -> consecutive words -> no bank conflicts.
 //  * Winner: key = (cost << 13) | scan_index, CREDUX.MIN over the warp, atomicMin in smem.
 //    Lowest scan index wins ties by construction, exactly like the oracle's strict '<'.
+#include <stdlib.h>
 #include "b2_common.cuh"
 
 namespace {
 
 constexpr int NMB = 8;          // macroblocks per CTA strip
-constexpr int NTHREADS = 256;
-constexpr int NWARPS = NTHREADS / 32;
 
 template <int R> struct K1Cfg;
 template <> struct K1Cfg<32> { static constexpr int K = 13, NG = 5; };   // 65 = 5 x 13
@@ -52,7 +51,7 @@ template <int R> struct K1Smem {
     static constexpr int TOTAL = OFF_BAR + 8 + 128;     // +128: manual alignment slack
 };
 
-template <int R>
+template <int R, int NTHREADS>
 __global__ void __launch_bounds__(NTHREADS, 2)
 k1_me_fullpel_kernel(const __grid_constant__ CUtensorMap tm_cur,
                      const __grid_constant__ CUtensorMap tm_ref,
@@ -60,6 +59,7 @@ k1_me_fullpel_kernel(const __grid_constant__ CUtensorMap tm_cur,
                      b2_mv_t *__restrict__ mv_out, uint32_t *__restrict__ cost_out)
 {
     using S = K1Smem<R>;
+    constexpr int NWARPS = NTHREADS / 32;
     constexpr int K = K1Cfg<R>::K, NG = K1Cfg<R>::NG, ND = S::ND;
     static_assert(K * NG == ND, "dy groups must tile the search range");
 
@@ -191,21 +191,32 @@ k1_me_fullpel_kernel(const __grid_constant__ CUtensorMap tm_cur,
     }
 }
 
-template <int R>
+template <int R, int NT>
 int launch_k1(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, int mbw, int mbh, int nframes,
               const b2_mv_t *pmv, int lambda, b2_mv_t *mv_out, uint32_t *cost_out, cudaStream_t st)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        B2_CUDA_OK(cudaFuncSetAttribute(k1_me_fullpel_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        B2_CUDA_OK(cudaFuncSetAttribute(k1_me_fullpel_kernel<R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         K1Smem<R>::TOTAL));
         attr_set = true;
     }
     dim3 grid((mbw + NMB - 1) / NMB, mbh, nframes);
-    k1_me_fullpel_kernel<R><<<grid, NTHREADS, K1Smem<R>::TOTAL, st>>>(tm_cur, tm_ref, mbw, mbh, pmv, lambda,
-                                                                      mv_out, cost_out);
+    k1_me_fullpel_kernel<R, NT><<<grid, NT, K1Smem<R>::TOTAL, st>>>(tm_cur, tm_ref, mbw, mbh, pmv, lambda, mv_out, cost_out);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+// threads per CTA: 82 (R=32) / 41 (R=16) warp-tasks per full strip should divide evenly over the warps
+int k1_threads()
+{
+    static int nt = 0;
+    if (!nt) {
+        const char *e = getenv("B2_K1_THREADS");
+        nt = e ? atoi(e) : 256;
+        if (nt != 192 && nt != 256 && nt != 320 && nt != 384) nt = 256;
+    }
+    return nt;
 }
 
 }  // namespace
@@ -225,9 +236,16 @@ int b2_launch_me_fullpel(int R, const CUtensorMap *tm_cur, const CUtensorMap *tm
                          int nframes, const b2_mv_t *d_pmv, int lambda, b2_mv_t *d_mv, uint32_t *d_cost,
                          cudaStream_t st)
 {
+#define K1_DISPATCH(RR)                                                                                              \
+    switch (k1_threads()) {                                                                                          \
+    case 192: return launch_k1<RR, 192>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);       \
+    case 320: return launch_k1<RR, 320>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);       \
+    case 384: return launch_k1<RR, 384>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);       \
+    default: return launch_k1<RR, 256>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);        \
+    }
     switch (R) {
-    case 32: return launch_k1<32>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);
-    case 16: return launch_k1<16>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);
+    case 32: K1_DISPATCH(32)
+    case 16: K1_DISPATCH(16)
     default:
         fprintf(stderr, "b2enc: merange %d not supported (16 or 32)\n", R);
         return -1;

@@ -10,9 +10,12 @@
  * "0 = no output yet / delayed_frames() / encode(NULL) drains" contract main() relies on
  * (av_encode.c:971-974, :1076-1083).  i_gop_slots = 1 encodes every picture immediately (zero delay).
  */
+#define _POSIX_C_SOURCE 200809L
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include "b2enc.h"
 #include "b2enc_engine.h"
 #include "b2h_entropy.h"
@@ -29,12 +32,25 @@ typedef struct {
     int key;
 } outframe_t;
 
+#define B2_MAX_WORKERS 16
+
+typedef struct { int qi, slot, t, ticket; int64_t gop_index; } job_t;
+
 struct b2_encoder {
     b2_param_t p;
     int qp, S, L, mbw, mbh, nmb;
     b2_engine_t *eng;
     b2h_entropy_t *ent;
     b2h_seq_t seq;
+    /* entropy worker pool: one closed GOP / stream per job, each worker owns its neighbour-map scratch */
+    int nworkers;
+    pthread_t workers[B2_MAX_WORKERS];
+    b2h_entropy_t *went[B2_MAX_WORKERS];
+    uint8_t *wscratch[B2_MAX_WORKERS];
+    pthread_mutex_t mu;
+    pthread_cond_t cv_job, cv_done;
+    job_t *jobs;
+    int njobs, next_job, done_jobs, job_error, stop;
     int64_t *pts;              /* [S*L] pts of the frames of the batch being gathered */
     int batch_frames;
     int gop_pos;               /* zero-delay mode: position inside the current GOP */
@@ -110,6 +126,8 @@ void b2_picture_clean(b2_picture_t *pic)
     memset(pic, 0, sizeof(*pic));
 }
 
+static void *worker_main(void *arg);
+
 b2_t *b2_encoder_open(b2_param_t *p)
 {
     if (!p || p->i_width < 16 || p->i_height < 16) { fprintf(stderr, "b2enc: bad picture size\n"); return NULL; }
@@ -138,12 +156,39 @@ b2_t *b2_encoder_open(b2_param_t *p)
     h->scratch_cap = (size_t)h->nmb * 3072 + 65536;
     h->scratch = (uint8_t *)malloc(h->scratch_cap);
     if (!h->ent || !h->pts || !h->outq || !h->scratch) { b2_encoder_close(h); return NULL; }
+    pthread_mutex_init(&h->mu, NULL); pthread_cond_init(&h->cv_job, NULL); pthread_cond_init(&h->cv_done, NULL);
+    if (h->S > 1) {
+        long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+        int nw = h->S < B2_MAX_WORKERS ? h->S : B2_MAX_WORKERS;
+        if (ncpu > 0 && nw > ncpu) nw = (int)ncpu;
+        h->jobs = (job_t *)calloc((size_t)h->S, sizeof(job_t));
+        for (int i = 0; i < nw; i++) {
+            h->went[i] = b2h_entropy_create(h->mbw, h->mbh);
+            h->wscratch[i] = (uint8_t *)malloc(h->scratch_cap);
+            if (!h->jobs || !h->went[i] || !h->wscratch[i]) { b2_encoder_close(h); return NULL; }
+        }
+        pthread_mutex_lock(&h->mu);                      /* workers look themselves up in h->workers[] under the lock */
+        for (int i = 0; i < nw; i++) {
+            if (pthread_create(&h->workers[i], NULL, worker_main, h)) break;
+            h->nworkers++;
+        }
+        pthread_mutex_unlock(&h->mu);
+    }
     return h;
 }
 
 void b2_encoder_close(b2_t *h)
 {
     if (!h) return;
+    if (h->nworkers > 0) {
+        pthread_mutex_lock(&h->mu);
+        h->stop = 1;
+        pthread_cond_broadcast(&h->cv_job);
+        pthread_mutex_unlock(&h->mu);
+        for (int i = 0; i < h->nworkers; i++) pthread_join(h->workers[i], NULL);
+    }
+    for (int i = 0; i < B2_MAX_WORKERS; i++) { b2h_entropy_destroy(h->went[i]); free(h->wscratch[i]); }
+    free(h->jobs);
     if (h->outq)
         for (int i = 0; i < h->S * h->L; i++) free(h->outq[i].data);
     free(h->outq); free(h->pts); free(h->scratch); free(h->ret_buf);
@@ -159,10 +204,9 @@ static void put_prefix(uint8_t *d, int annexb, size_t nal_size)
 }
 
 /* entropy-code one frame's results into outq[qi] */
-static int finish_frame(b2_t *h, int qi, int slot, int t, int64_t gop_index)
+static int finish_frame(b2_t *h, b2h_entropy_t *ent, uint8_t *s, int ticket, int qi, int slot, int t, int64_t gop_index)
 {
     outframe_t *o = &h->outq[qi];
-    uint8_t *s = h->scratch;
     size_t pos = 0;
     o->nal_count = 0;
     const int is_idr = t == 0;
@@ -178,8 +222,11 @@ static int finish_frame(b2_t *h, int qi, int slot, int t, int64_t gop_index)
             pos += n + 4;
         }
     }
-    size_t n = b2h_write_slice(h->ent, &h->seq, is_idr ? B2_FRAME_I : B2_FRAME_P, t, (int)(gop_index & 0xffff),
-                               b2_engine_info(h->eng, slot), b2_engine_coef(h->eng, slot), s + pos + 4, h->scratch_cap - pos - 4);
+    const b2_mbinfo_t *info = ticket < 0 ? b2_engine_info(h->eng, slot) : b2_engine_info_ticket(h->eng, ticket, slot);
+    const b2_mbcoef_t *coef = ticket < 0 ? b2_engine_coef(h->eng, slot) : b2_engine_coef_ticket(h->eng, ticket, slot);
+    if (!info || !coef) return -1;
+    size_t n = b2h_write_slice(ent, &h->seq, is_idr ? B2_FRAME_I : B2_FRAME_P, t, (int)(gop_index & 0xffff), info, coef,
+                               s + pos + 4, h->scratch_cap - pos - 4);
     if (!n) { fprintf(stderr, "b2enc: slice buffer overflow\n"); return -1; }
     put_prefix(s + pos, h->p.b_annexb, n);
     o->nal_off[o->nal_count] = (int)pos; o->nal_size[o->nal_count] = (int)n + 4;
@@ -195,24 +242,77 @@ static int finish_frame(b2_t *h, int qi, int slot, int t, int64_t gop_index)
     return 0;
 }
 
-/* advance the gathered batch (possibly partial) through the GPU and the entropy stage */
+static void *worker_main(void *arg)
+{
+    b2_t *h = (b2_t *)arg;
+    int me = -1;
+    pthread_mutex_lock(&h->mu);
+    for (int i = 0; i < h->nworkers; i++)
+        if (pthread_equal(h->workers[i], pthread_self())) me = i;
+    for (;;) {
+        while (!h->stop && h->next_job >= h->njobs) pthread_cond_wait(&h->cv_job, &h->mu);
+        if (h->stop) break;
+        job_t j = h->jobs[h->next_job++];
+        pthread_mutex_unlock(&h->mu);
+        int rc = finish_frame(h, h->went[me], h->wscratch[me], j.ticket, j.qi, j.slot, j.t, j.gop_index);
+        pthread_mutex_lock(&h->mu);
+        if (rc) h->job_error = 1;
+        if (++h->done_jobs == h->njobs) pthread_cond_signal(&h->cv_done);
+    }
+    pthread_mutex_unlock(&h->mu);
+    return NULL;
+}
+
+/* entropy-code frame t of GOPs [0,nt) on the worker pool (or inline when there is none) */
+static int entropy_step(b2_t *h, int t, int nt, int ticket)
+{
+    if (h->nworkers == 0) {
+        for (int g = 0; g < nt; g++) {
+            if (finish_frame(h, h->ent, h->scratch, ticket, g * h->L + t, g, t, h->gops_done + g)) return -1;
+            h->outq[g * h->L + t].pts = h->pts[g * h->L + t];
+        }
+        return 0;
+    }
+    pthread_mutex_lock(&h->mu);
+    for (int g = 0; g < nt; g++) {
+        job_t j = {g * h->L + t, g, t, ticket, h->gops_done + g};
+        h->jobs[g] = j;
+    }
+    h->njobs = nt; h->next_job = 0; h->done_jobs = 0;
+    pthread_cond_broadcast(&h->cv_job);
+    while (h->done_jobs < h->njobs) pthread_cond_wait(&h->cv_done, &h->mu);
+    h->njobs = 0; h->next_job = 0;
+    int err = h->job_error;
+    pthread_mutex_unlock(&h->mu);
+    for (int g = 0; g < nt; g++) h->outq[g * h->L + t].pts = h->pts[g * h->L + t];
+    return err ? -1 : 0;
+}
+
+static int issue_step(b2_t *h, int t, int nt)
+{
+    const int ring = h->S == 1 ? 0 : t;
+    if (b2_engine_h2d(h->eng, 0, nt, ring)) return -1;
+    if (b2_engine_encode(h->eng, t == 0 ? B2_FRAME_I : B2_FRAME_P, nt, ring)) return -1;
+    return b2_engine_d2h(h->eng, nt);
+}
+
+/* advance the gathered batch (possibly partial) through the GPU and the entropy stage: while the host entropy-codes
+ * frame t of every GOP, the GPU already encodes frame t+1 (result sets are double buffered) */
 static int process_batch(b2_t *h)
 {
     const int n = h->batch_frames, L = h->L;
     const int ngop = (n + L - 1) / L, last_len = n - (ngop - 1) * L;
-    for (int t = 0; t < L; t++) {
-        const int nt = t < last_len ? ngop : ngop - 1;      /* GOPs that still have a frame t (a prefix of the slots) */
-        if (nt <= 0) break;
-        if (b2_engine_h2d(h->eng, 0, nt, h->S == 1 ? 0 : t)) return -1;
-        if (b2_engine_encode(h->eng, t == 0 ? B2_FRAME_I : B2_FRAME_P, nt, h->S == 1 ? 0 : t)) return -1;
-        if (b2_engine_d2h(h->eng, nt)) return -1;
-        if (b2_engine_sync(h->eng)) return -1;
-        for (int g = 0; g < nt; g++) {
-            const int qi = g * L + t;
-            if (finish_frame(h, qi, g, t, h->gops_done + g)) return -1;
-            h->outq[qi].pts = h->pts[qi];
-        }
+    int nt = ngop;                                         /* GOPs that have a frame 0 */
+    if (issue_step(h, 0, nt)) return -1;
+    for (int t = 0; t < L && nt > 0; t++) {
+        const int ticket = b2_engine_ticket(h->eng);
+        const int nt_next = t + 1 < L ? (t + 1 < last_len ? ngop : ngop - 1) : 0;     /* a prefix of the slots */
+        if (b2_engine_wait_ticket(h->eng, ticket)) return -1;
+        if (nt_next > 0 && issue_step(h, t + 1, nt_next)) return -1;
+        if (entropy_step(h, t, nt, ticket)) return -1;
+        nt = nt_next;
     }
+    if (b2_engine_sync(h->eng)) return -1;
     h->gops_done += ngop;
     h->out_head = 0; h->out_count = n;
     h->batch_frames = 0;
@@ -233,7 +333,7 @@ int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic
             if (b2_engine_h2d(h->eng, 0, 1, 0) || b2_engine_encode(h->eng, t == 0 ? B2_FRAME_I : B2_FRAME_P, 1, 0) ||
                 b2_engine_d2h(h->eng, 1) || b2_engine_sync(h->eng))
                 return -1;
-            if (finish_frame(h, 0, 0, t, h->gops_done)) return -1;
+            if (finish_frame(h, h->ent, h->scratch, -1, 0, 0, t, h->gops_done)) return -1;
             h->outq[0].pts = pic_in->i_pts;
             h->out_head = 0; h->out_count = 1;
             h->gop_pos = t + 1;
