@@ -68,6 +68,7 @@ typedef struct {
     int b_intra_in_p;
     int i_device;                       /* CUDA device ordinal                                  */
     int i_csp_in;                       /* B2_FMT_* of the pictures handed to b2_encoder_encode */
+    int b_deblocking_filter;            /* in-loop deblocking filter (x264 field of the same name; default 1) */
 } b2_param_t;
 
 typedef struct {

@@ -33,6 +33,7 @@ typedef struct {
     int profile;       /* 1: record per-kernel CUDA-event timings (b2_engine_kernel_ms)   */
     int streams;       /* stream groups the slots are split into (0 = automatic); groups   */
                        /* run on separate CUDA streams so that their kernels overlap       */
+    int deblock;       /* 1: in-loop deblocking filter (K8) on every reconstructed frame    */
 } b2_engine_cfg_t;
 
 b2_engine_t *b2_engine_create(const b2_engine_cfg_t *cfg);      /* NULL on error */
@@ -81,8 +82,8 @@ int b2_engine_timer_start(b2_engine_t *e);
 int b2_engine_timer_stop(b2_engine_t *e, float *ms);            /* synchronises */
 /* cfg.profile: accumulated device ms and launch count per kernel since the last reset.
  * which: 0 K0 convert, 1 K6 border(cur), 2 K1 full-pel, 3 K2 sub-pel, 4 K3 intra, 5 K5 decide+inter,
- *        6 K7 intra recon, 7 K6 border(recon) */
-enum { B2_NKERNELS = 8 };
+ *        6 K7 intra recon, 7 K6 border(recon), 8 K8 deblock */
+enum { B2_NKERNELS = 9 };
 int b2_engine_kernel_ms(b2_engine_t *e, int which, double *ms_total, long *launches);
 void b2_engine_profile_reset(b2_engine_t *e);
 long b2_engine_launch_count(const b2_engine_t *e);              /* kernels launched since creation */

@@ -10,7 +10,7 @@ W, H, N, QP, GOP, R = 640, 480, 300, 26, 32, 16
 frames = [o.synth_frame(W, H, t) for t in range(N)]
 
 t0 = time.time()
-ref_bs, ref_recons, _, _ = o.encode_sequence(frames, W, H, qp=QP, merange=R, gop=GOP, fps=(30, 1))
+ref_bs, ref_recons, _, _ = o.encode_sequence(frames, W, H, qp=QP, merange=R, gop=GOP, fps=(30, 1), deblock=1)
 t_cpu = time.time() - t0
 
 enc = b2enc.DropInEncoder(W, H, preset="medium", tune="film", quality=QP, fps=(30, 1), annexb=1, i_keyint_max=GOP, i_gop_slots=8)

@@ -65,7 +65,7 @@ def test_reference_call_sequence_and_bitstream(oracle, b2):
     assert sps[0] == 7 and out[0][0][1][0] == 8 and out[0][0][2][0] == 5          # SPS, PPS, IDR slice (av_encode.c:683-736)
     assert sps[1][5] == 66 and sps[1][7] in (12, 13, 20, 21, 30)                  # profile_idc / level_idc at [5],[7] (:703-705)
     bs = to_annexb(out, length_prefixed=True)
-    ref_bs, recons, _, _ = oracle.encode_sequence(frames, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1))
+    ref_bs, recons, _, _ = oracle.encode_sequence(frames, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1), deblock=1)
     assert bs == ref_bs, "GPU drop-in bitstream differs from the oracle encoder's"
     dec = oracle.decode_yuv(oracle.split_access_units(bs))
     assert len(dec) == n

@@ -11,11 +11,11 @@ pytestmark = pytest.mark.gpu
 INFO_FIELDS = ["mb_type", "mvx", "mvy", "i16_mode", "chroma_mode", "cbp", "i4_mode", "cost", "nnz_mask"]
 
 
-def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="yuv420p"):
+def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="yuv420p", deblock=0):
     """seqs: list (one per slot) of lists of (y,u,v) frames"""
     S, T = len(seqs), len(seqs[0])
-    eng = b2.Engine(w, h, slots=S, fmt=fmt, ring=2, merange=R, qp=qp, subpel=subpel, intra_in_p=intra_in_p)
-    prm = oracle.Params(qp, R, subpel, intra_in_p)
+    eng = b2.Engine(w, h, slots=S, fmt=fmt, ring=2, merange=R, qp=qp, subpel=subpel, intra_in_p=intra_in_p, deblock=deblock)
+    prm = oracle.Params(qp, R, subpel, intra_in_p, deblock)
     prev = [None] * S; prev_mv = [None] * S
     for t in range(T):
         for s in range(S):
@@ -75,3 +75,11 @@ def test_engine_extreme_content(oracle, b2):
     flat = [(np.full((h, w), 90, np.uint8), np.full((h // 2, w // 2), 128, np.uint8), np.full((h // 2, w // 2), 128, np.uint8))] * 3
     for qp in (10, 51):
         run_and_compare(oracle, b2, [noise, flat], w, h, qp, 16)
+
+
+@pytest.mark.parametrize("w,h,qp,R,cut", [(176, 144, 30, 16, None), (320, 240, 38, 32, 2), (208, 160, 20, 16, 1), (318, 242, 28, 16, 3),
+                                          (64, 48, 51, 16, 1), (96, 80, 12, 16, 2)])
+def test_engine_with_deblocking(oracle, b2, w, h, qp, R, cut):
+    """K8 in-loop deblocking: reconstruction and everything downstream stay bit-exact"""
+    seqs = [smooth_seq(w, h, 5, seed=qp + 1, cut=cut), smooth_seq(w, h, 5, seed=qp + 2)]
+    run_and_compare(oracle, b2, seqs, w, h, qp, R, deblock=1)

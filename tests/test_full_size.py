@@ -8,10 +8,10 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _encode_and_check(oracle, b2, w, h, R, qp, nslots, nframes, oracle_slots, subpel=1, intra_in_p=1):
-    eng = b2.Engine(w, h, slots=nslots, ring=1, merange=R, qp=qp, subpel=subpel, intra_in_p=intra_in_p)
-    prm = oracle.Params(qp, R, subpel, intra_in_p)
-    ents = [oracle.Entropy(w, h, qp) for _ in range(nslots)]
+def _encode_and_check(oracle, b2, w, h, R, qp, nslots, nframes, oracle_slots, subpel=1, intra_in_p=1, deblock=0):
+    eng = b2.Engine(w, h, slots=nslots, ring=1, merange=R, qp=qp, subpel=subpel, intra_in_p=intra_in_p, deblock=deblock)
+    prm = oracle.Params(qp, R, subpel, intra_in_p, deblock)
+    ents = [oracle.Entropy(w, h, qp, deblock=deblock) for _ in range(nslots)]
     streams = [bytearray() for _ in range(nslots)]
     recons = [[] for _ in range(nslots)]
     prev = {s: None for s in oracle_slots}; pmv = {s: None for s in oracle_slots}
@@ -65,3 +65,7 @@ def test_c5_many_720p_streams(oracle, b2):
     """one GPU's share of the 64-stream configuration: 8 live streams in lock-step, each with its own pan vector"""
     streams = _encode_and_check(oracle, b2, 1280, 720, 16, 28, nslots=8, nframes=3, oracle_slots=[3])
     assert len({bytes(s) for s in streams}) == 8            # different content -> different streams
+
+
+def test_c3_1080p_with_deblocking(oracle, b2):
+    _encode_and_check(oracle, b2, 1920, 1080, 32, 32, nslots=2, nframes=3, oracle_slots=[0], deblock=1)

@@ -89,3 +89,11 @@ def test_psnr_monotone_in_qp(oracle):
         psnr = oracle.lib().b2o_psnr_y(oracle.C.byref(src.f), oracle.C.byref(recons[-1].f))
         assert psnr < last_psnr and len(bs) < last_size
         last_psnr, last_size = psnr, len(bs)
+
+
+@pytest.mark.parametrize("w,h,qp,R,cut", [(176, 144, 26, 16, None), (320, 240, 36, 32, 3), (208, 160, 18, 16, 2), (96, 80, 51, 16, 2),
+                                          (318, 242, 30, 16, None), (64, 48, 12, 16, 1)])
+def test_decoder_matches_oracle_recon_with_deblocking(oracle, w, h, qp, R, cut):
+    """in-loop deblocking filter (8.7) of the oracle against libavcodec's"""
+    frames = smooth_seq(w, h, 6, seed=qp, cut=cut)
+    _roundtrip(oracle, frames, w, h, qp=qp, merange=R, gop=32, deblock=1)

@@ -79,20 +79,20 @@ def vabsdiff4_peak(device=0, outer=256, reps=5):
 FMT = {"yuv420p": 0, "nv12": 1, "yuyv422": 2, "uyvy422": 3}
 FRAME_I, FRAME_P = 0, 1
 KERNEL_NAMES = ["K0 convert", "K6 border(cur)", "K1 full-pel SAD", "K2 sub-pel SATD", "K3 intra analyse",
-                "K5 decide+inter recon", "K7 intra recon", "K6 border(recon)"]
+                "K5 decide+inter recon", "K7 intra recon", "K6 border(recon)", "K8 deblock"]
 
 
 class EngineCfg(C.Structure):
     _fields_ = [("device", C.c_int), ("width", C.c_int), ("height", C.c_int), ("slots", C.c_int), ("in_fmt", C.c_int),
                 ("in_ring", C.c_int), ("merange", C.c_int), ("qp", C.c_int), ("subpel", C.c_int), ("intra_in_p", C.c_int),
-                ("profile", C.c_int), ("streams", C.c_int)]
+                ("profile", C.c_int), ("streams", C.c_int), ("deblock", C.c_int)]
 
 
 class Engine:
     """One GPU's encode-stage engine: `slots` closed GOPs / streams advanced in lock-step."""
 
     def __init__(self, width, height, slots=1, fmt="yuv420p", ring=1, merange=16, qp=26, subpel=1, intra_in_p=1,
-                 device=0, profile=0, streams=0):
+                 device=0, profile=0, streams=0, deblock=0):
         require_gpu()
         L = lib()
         L.b2_engine_create.restype = C.c_void_p
@@ -121,7 +121,7 @@ class Engine:
         L.b2_engine_kernel_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long)]
         self.L = L
         self.cfg = EngineCfg(device, width, height, slots, FMT[fmt] if isinstance(fmt, str) else fmt, ring, merange, qp,
-                             subpel, intra_in_p, profile, streams)
+                             subpel, intra_in_p, profile, streams, deblock)
         self.h = L.b2_engine_create(C.byref(self.cfg))
         if not self.h:
             raise RuntimeError("b2_engine_create failed")
@@ -241,7 +241,8 @@ class Param(C.Structure):
         _fields_ = [("i_rc_method", C.c_int), ("f_rf_constant", C.c_float), ("i_qp_constant", C.c_int)]
     _fields_ = [("i_width", C.c_int), ("i_height", C.c_int), ("b_annexb", C.c_int), ("i_fps_num", C.c_int), ("i_fps_den", C.c_int),
                 ("vui", _Vui), ("rc", _Rc), ("i_keyint_max", C.c_int), ("i_gop_slots", C.c_int), ("i_merange", C.c_int),
-                ("b_subpel", C.c_int), ("b_intra_in_p", C.c_int), ("i_device", C.c_int), ("i_csp_in", C.c_int)]
+                ("b_subpel", C.c_int), ("b_intra_in_p", C.c_int), ("i_device", C.c_int), ("i_csp_in", C.c_int),
+                ("b_deblocking_filter", C.c_int)]
 
 
 class Image(C.Structure):

@@ -378,6 +378,10 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
         if (b2_launch_intra_recon(cur, rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, ns, c.qp, !is_p, info, coef, st))
             return -1;
     }
+    if (c.deblock) {
+        KScope k(e, st, 8);
+        if (b2_launch_deblock(rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, ns, c.qp, info, st)) return -1;
+    }
     {
         KScope k(e, st, 7);
         if (b2_launch_extend_border_yuv(rec[0], rec[1], rec[2], e->pitch, e->rows, e->pitchc, e->rowsc, e->stride_y, e->stride_c,

@@ -33,3 +33,5 @@ int b2_launch_intra_recon(const uint8_t *const cur[3], uint8_t *const rec[3], in
                           size_t stride_c, int mbw, int mbh, int nframes, int qp, int all_intra, b2_mbinfo_t *d_info,
                           b2_mbcoef_t *d_coef, cudaStream_t st);
 int b2_lambda_for_qp(int qp);
+int b2_launch_deblock(uint8_t *const rec[3], int pitch, int pitchc, size_t stride_y, size_t stride_c, int mbw, int mbh,
+                      int nframes, int qp, const b2_mbinfo_t *d_info, cudaStream_t st);

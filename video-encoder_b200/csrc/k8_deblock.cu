@@ -1,0 +1,231 @@
+// k8_deblock.cu -- K8: in-loop deblocking filter (ITU-T H.264 8.7) on the reconstructed frame.
+//
+// x264 runs the loop filter by default inside x264_encoder_encode (av_encode.c:970).
+// Bit-exact against oracle/b2o_deblock.c and, through the decoder drift test, against libavcodec.
+//
+// The filter is defined in macroblock raster order and every macroblock reads samples its left, top and
+// top-right neighbours have already modified, so macroblocks on one anti-diagonal d = mbx + 2*mby are
+// independent and diagonals are serial -- the same wavefront as intra reconstruction (K7).  One thread-block
+// cluster per frame, one warp per macroblock: the 20x20 luma and two 12x12 chroma neighbourhoods are staged
+// in shared memory, lanes 0-15 filter the luma lines (rows for vertical edges, columns for horizontal edges),
+// lanes 16-31 the U and V lines; the four edges of a line are filtered by the same lane in order, so the only
+// warp-level synchronisation is between the vertical and the horizontal pass.
+// Bound: latency of the wavefront; algorithmic bytes 1.5*W*H read + written.
+#include "b2_mbcode.cuh"
+
+namespace {
+
+using namespace b2;
+
+constexpr int K8_WARPS = 16;
+constexpr int LP = 24;      // luma tile pitch: rows -4..15, cols -4..15 -> tile[(y+4)*LP + x + 4]
+constexpr int CP = 16;      // chroma tile pitch: rows -2..7, cols -4..7 -> tile[(y+2)*CP + x + 4]
+
+__device__ __constant__ uint8_t c_alpha[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 5, 6, 7, 8, 9, 10, 12, 13,
+                                               15, 17, 20, 22, 25, 28, 32, 36, 40, 45, 50, 56, 63, 71, 80, 90, 101, 113, 127, 144,
+                                               162, 182, 203, 226, 255, 255};
+__device__ __constant__ uint8_t c_beta[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4,
+                                              6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 14, 14, 15, 15, 16, 16, 17, 17, 18, 18};
+__device__ __constant__ uint8_t c_tc0[52][3] = {
+    {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0},
+    {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 1, 1},
+    {0, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 2}, {1, 1, 2}, {1, 1, 2}, {1, 1, 2}, {1, 2, 3}, {1, 2, 3},
+    {2, 2, 3}, {2, 2, 4}, {2, 3, 4}, {2, 3, 4}, {3, 3, 5}, {3, 4, 6}, {3, 4, 6}, {4, 5, 7}, {4, 5, 8}, {4, 6, 9}, {5, 7, 10},
+    {6, 8, 11}, {6, 8, 13}, {7, 10, 14}, {8, 11, 16}, {9, 12, 18}, {10, 13, 20}, {11, 15, 23}, {13, 17, 25}};
+
+struct K8Warp {
+    __align__(16) uint8_t y[20 * LP];
+    __align__(16) uint8_t c[2][10 * CP];
+    int8_t bs[2][4][4];                  // [0 vertical | 1 horizontal][edge][4-sample segment]
+};
+
+__device__ __forceinline__ void cluster_barrier()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+
+__device__ __forceinline__ int clip3(int lo, int hi, int v) { return min(max(v, lo), hi); }
+
+struct FiltConst { int alpha, beta, tc0[3]; };
+
+// one line of samples across an edge; pix -> q0, step = distance between successive samples across the edge
+__device__ __forceinline__ void filter_line(uint8_t *pix, int step, int bs, const FiltConst &fc, bool chroma)
+{
+    if (bs == 0) return;
+    const int p0 = pix[-step], p1 = pix[-2 * step], q0 = pix[0], q1 = pix[step];
+    if (!(abs(p0 - q0) < fc.alpha && abs(p1 - p0) < fc.beta && abs(q1 - q0) < fc.beta)) return;
+    if (chroma) {
+        if (bs < 4) {
+            const int tc = fc.tc0[bs - 1] + 1;
+            const int d = clip3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+            pix[-step] = (uint8_t)b2_clip255(p0 + d); pix[0] = (uint8_t)b2_clip255(q0 - d);
+        } else {
+            pix[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+            pix[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+        }
+        return;
+    }
+    const int p2 = pix[-3 * step], q2 = pix[2 * step];
+    const int ap = abs(p2 - p0), aq = abs(q2 - q0);
+    if (bs < 4) {
+        const int tc0 = fc.tc0[bs - 1];
+        const int tc = tc0 + (ap < fc.beta) + (aq < fc.beta);
+        const int d = clip3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+        pix[-step] = (uint8_t)b2_clip255(p0 + d); pix[0] = (uint8_t)b2_clip255(q0 - d);
+        if (ap < fc.beta) pix[-2 * step] = (uint8_t)(p1 + clip3(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - (p1 << 1)) >> 1));
+        if (aq < fc.beta) pix[step] = (uint8_t)(q1 + clip3(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - (q1 << 1)) >> 1));
+    } else {
+        const int p3 = pix[-4 * step], q3 = pix[3 * step];
+        const bool strong = abs(p0 - q0) < ((fc.alpha >> 2) + 2);
+        if (ap < fc.beta && strong) {
+            pix[-step] = (uint8_t)((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+            pix[-2 * step] = (uint8_t)((p2 + p1 + p0 + q0 + 2) >> 2);
+            pix[-3 * step] = (uint8_t)((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+        } else {
+            pix[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
+        }
+        if (aq < fc.beta && strong) {
+            pix[0] = (uint8_t)((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+            pix[step] = (uint8_t)((p0 + q0 + q1 + q2 + 2) >> 2);
+            pix[2 * step] = (uint8_t)((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
+        } else {
+            pix[0] = (uint8_t)((2 * q1 + q0 + p1 + 2) >> 2);
+        }
+    }
+}
+
+__device__ __forceinline__ int zidx(int x, int y) { return (x & 1) | ((y & 1) << 1) | ((x >> 1) << 2) | ((y >> 1) << 3); }
+
+// boundary strength (8.7.2.1) between 4x4 block (pbx,pby) of MB p and block (qbx,qby) of MB q
+__device__ __forceinline__ int bs_of(uint32_t ptype, int pmvx, int pmvy, uint32_t pnnz, int pbx, int pby,
+                                     uint32_t qtype, int qmvx, int qmvy, uint32_t qnnz, int qbx, int qby, bool mb_edge)
+{
+    if (ptype != B2_MB_P16x16 || qtype != B2_MB_P16x16) return mb_edge ? 4 : 3;
+    if (((pnnz >> zidx(pbx, pby)) & 1u) || ((qnnz >> zidx(qbx, qby)) & 1u)) return 2;
+    if (abs(pmvx - qmvx) >= 4 || abs(pmvy - qmvy) >= 4) return 1;
+    return 0;
+}
+
+__device__ void k8_mb_task(int lane, K8Warp &ws, uint8_t *const rec[3], int pitch, int pitchc, size_t offy, size_t offc,
+                           int mbx, int mby, int mbw, const b2_mbinfo_t *mi, const FiltConst &fy, const FiltConst &fcc)
+{
+    uint8_t *gy = rec[0] + offy + (size_t)(B2_PAD + mby * 16) * pitch + B2_PAD + mbx * 16;
+    // ---- stage the neighbourhood: luma rows -4..15 x cols -4..15 (5 words per row), chroma rows -2..7 x cols -4..7 ----
+    for (int i = lane; i < 100; i += 32) {
+        const int r = i / 5, w = i - r * 5;
+        *(uint32_t *)&ws.y[r * LP + w * 4] = *(const uint32_t *)(gy + (ptrdiff_t)(r - 4) * pitch + (w - 1) * 4);
+    }
+    for (int i = lane; i < 60; i += 32) {
+        const int p = i / 30, k = i - p * 30, r = k / 3, w = k - r * 3;
+        const uint8_t *gc = rec[1 + p] + offc + (size_t)(B2_PADC + mby * 8) * pitchc + B2_PADC + mbx * 8;
+        *(uint32_t *)&ws.c[p][r * CP + w * 4] = *(const uint32_t *)(gc + (ptrdiff_t)(r - 2) * pitchc + (w - 1) * 4);
+    }
+    // ---- boundary strengths: lanes 0-15 vertical edges, 16-31 horizontal edges; lane -> (edge e, segment k) ----
+    {
+        const int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3;
+        const bool edge_ok = !(e == 0 && (dir == 0 ? mbx == 0 : mby == 0));
+        int bs = 0;
+        if (edge_ok) {
+            const b2_mbinfo_t *mp = e == 0 ? (dir == 0 ? mi - 1 : mi - mbw) : mi;
+            const int pbx = dir == 0 ? (e == 0 ? 3 : e - 1) : k, pby = dir == 0 ? k : (e == 0 ? 3 : e - 1);
+            const int qbx = dir == 0 ? e : k, qby = dir == 0 ? k : e;
+            bs = bs_of(mp->mb_type, mp->mvx, mp->mvy, mp->nnz_mask, pbx, pby, mi->mb_type, mi->mvx, mi->mvy, mi->nnz_mask, qbx,
+                       qby, e == 0);
+        }
+        ws.bs[dir][e][k] = (int8_t)bs;
+    }
+    __syncwarp();
+    // ---- vertical edges: luma lane = row, chroma lane-16 = (plane, row) ----
+    if (lane < 16) {
+        uint8_t *row = &ws.y[(lane + 4) * LP + 4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) filter_line(row + 4 * e, 1, ws.bs[0][e][lane >> 2], fy, false);
+    } else {
+        const int l = lane - 16, p = l >> 3, r = l & 7;
+        uint8_t *row = &ws.c[p][(r + 2) * CP + 4];
+#pragma unroll
+        for (int e = 0; e < 2; e++) filter_line(row + 4 * e, 1, ws.bs[0][2 * e][r >> 1], fcc, true);
+    }
+    __syncwarp();
+    // ---- horizontal edges: luma lane = column, chroma lane-16 = (plane, column) ----
+    if (lane < 16) {
+        uint8_t *col = &ws.y[4 * LP + lane + 4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) filter_line(col + 4 * e * LP, LP, ws.bs[1][e][lane >> 2], fy, false);
+    } else {
+        const int l = lane - 16, p = l >> 3, x = l & 7;
+        uint8_t *col = &ws.c[p][2 * CP + x + 4];
+#pragma unroll
+        for (int e = 0; e < 2; e++) filter_line(col + 4 * e * CP, CP, ws.bs[1][2 * e][x >> 1], fcc, true);
+    }
+    __syncwarp();
+    // ---- write back what can have changed: own MB, 3 (luma) / 1 (chroma) lines into the top MB, one word into the left MB ----
+    for (int i = lane; i < 95; i += 32) {                  // luma rows -3..15 (19 rows) x 5 words
+        const int r = i / 5 + 1, w = i - (i / 5) * 5;       // tile row r = y + 4, y = -3..15
+        const int y = r - 4;
+        if (w == 0 && (mbx == 0 || y < 0)) continue;        // nothing left of the picture; corner block is never modified
+        if (y < 0 && mby == 0) continue;
+        *(uint32_t *)(gy + (ptrdiff_t)y * pitch + (w - 1) * 4) = *(const uint32_t *)&ws.y[r * LP + w * 4];
+    }
+    for (int i = lane; i < 54; i += 32) {                  // chroma rows -1..7 (9 rows) x 3 words x 2 planes
+        const int p = i / 27, k = i - p * 27, r = k / 3 + 1, w = k - (k / 3) * 3;
+        const int y = r - 2;
+        if (w == 0 && (mbx == 0 || y < 0)) continue;
+        if (y < 0 && mby == 0) continue;
+        uint8_t *gc = rec[1 + p] + offc + (size_t)(B2_PADC + mby * 8) * pitchc + B2_PADC + mbx * 8;
+        *(uint32_t *)(gc + (ptrdiff_t)y * pitchc + (w - 1) * 4) = *(const uint32_t *)&ws.c[p][r * CP + w * 4];
+    }
+}
+
+__global__ void __launch_bounds__(K8_WARPS * 32)
+k8_deblock_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pitchc, size_t stride_y, size_t stride_c, int mbw, int mbh,
+                  int qp, const b2_mbinfo_t *__restrict__ info)
+{
+    __shared__ K8Warp s_warp[K8_WARPS];
+    const int frame = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ncta = (int)cluster_nctarank(), crank = (int)cluster_ctarank();
+    const int gwarp = crank * K8_WARPS + warp, nwarps = ncta * K8_WARPS;
+    const int ndiag = mbw + 2 * (mbh - 1);
+    const b2_mbinfo_t *finfo = info + (size_t)frame * mbw * mbh;
+    uint8_t *const rec[3] = {ry, ru, rv};
+    const int qpc = chroma_qp(qp);
+    FiltConst fy, fcc;
+    fy.alpha = c_alpha[qp]; fy.beta = c_beta[qp]; fcc.alpha = c_alpha[qpc]; fcc.beta = c_beta[qpc];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { fy.tc0[i] = c_tc0[qp][i]; fcc.tc0[i] = c_tc0[qpc][i]; }
+    for (int d = 0; d < ndiag; d++) {
+        const int y_lo = max(0, (d - mbw + 2) >> 1), y_hi = min(mbh - 1, d >> 1);
+        for (int t = y_lo + gwarp; t <= y_hi; t += nwarps) {
+            const int mby = t, mbx = d - 2 * mby;
+            k8_mb_task(lane, s_warp[warp], rec, pitch, pitchc, frame * stride_y, frame * stride_c, mbx, mby, mbw,
+                       &finfo[mby * mbw + mbx], fy, fcc);
+        }
+        if (ncta > 1) cluster_barrier();
+        else __syncthreads();
+    }
+}
+
+}  // namespace
+
+int b2_launch_deblock(uint8_t *const rec[3], int pitch, int pitchc, size_t stride_y, size_t stride_c, int mbw, int mbh,
+                      int nframes, int qp, const b2_mbinfo_t *d_info, cudaStream_t st)
+{
+    const int maxdiag = mbh < (mbw + 1) / 2 ? mbh : (mbw + 1) / 2;
+    int ncta = 1;
+    while (ncta < 8 && ncta * K8_WARPS < maxdiag) ncta *= 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ncta, nframes, 1);
+    cfg.blockDim = dim3(K8_WARPS * 32, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    B2_CUDA_OK(cudaLaunchKernelEx(&cfg, k8_deblock_kernel, rec[0], rec[1], rec[2], pitch, pitchc, stride_y, stride_c, mbw, mbh, qp,
+                                  d_info));
+    return 0;
+}

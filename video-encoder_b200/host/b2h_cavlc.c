@@ -416,7 +416,6 @@ size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int
     bs_t bs, *b = &bs;
     const int mbw = e->mbw, mbh = e->mbh, is_p = frame_type == B2_FRAME_P;
     const int ys = 4 * mbw, cs = 2 * mbw;
-    (void)s;
     bs_init(b, e->rbsp, e->rbsp_cap);
     /* slice_header() */
     bs_ue(b, 0);                                   /* first_mb_in_slice                   */
@@ -433,7 +432,12 @@ size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int
         bs_put(b, 1, 0);                           /* long_term_reference_flag            */
     }
     bs_se(b, 0);                                   /* slice_qp_delta                      */
-    bs_ue(b, 1);                                   /* disable_deblocking_filter_idc       */
+    if (s->deblock) {
+        bs_ue(b, 0);                               /* disable_deblocking_filter_idc = 0   */
+        bs_se(b, 0); bs_se(b, 0);                  /* slice_alpha_c0_offset_div2, slice_beta_offset_div2 */
+    } else {
+        bs_ue(b, 1);                               /* disable_deblocking_filter_idc = 1   */
+    }
 
     /* slice_data() */
     int skip_run = 0;

@@ -77,6 +77,7 @@ int b2_param_default_preset(b2_param_t *p, const char *preset, const char *tune)
     p->rc.i_rc_method = B2_RC_CRF; p->rc.f_rf_constant = 23.0f; p->rc.i_qp_constant = 26;
     p->b_annexb = 1;
     p->i_keyint_max = 32; p->i_gop_slots = 8; p->i_device = 0; p->i_csp_in = B2_FMT_YUV420P;
+    p->b_deblocking_filter = 1;
     int found = preset == NULL;
     p->i_merange = 16; p->b_subpel = 1; p->b_intra_in_p = 1;
     for (unsigned i = 0; preset && i < sizeof(presets) / sizeof(presets[0]); i++)
@@ -142,7 +143,7 @@ b2_t *b2_encoder_open(b2_param_t *p)
     memset(&cfg, 0, sizeof(cfg));
     cfg.device = p->i_device; cfg.width = p->i_width; cfg.height = p->i_height; cfg.slots = h->S;
     cfg.in_fmt = p->i_csp_in; cfg.in_ring = h->S == 1 ? 1 : h->L; cfg.merange = p->i_merange ? p->i_merange : 16; cfg.qp = h->qp;
-    cfg.subpel = p->b_subpel; cfg.intra_in_p = p->b_intra_in_p; cfg.profile = 0;
+    cfg.subpel = p->b_subpel; cfg.intra_in_p = p->b_intra_in_p; cfg.profile = 0; cfg.deblock = p->b_deblocking_filter;
     h->eng = b2_engine_create(&cfg);
     if (!h->eng) { free(h); return NULL; }
     int w16, h16;
@@ -151,6 +152,7 @@ b2_t *b2_encoder_open(b2_param_t *p)
     h->ent = b2h_entropy_create(h->mbw, h->mbh);
     h->seq.width = p->i_width; h->seq.height = p->i_height; h->seq.fps_num = p->i_fps_num; h->seq.fps_den = p->i_fps_den;
     h->seq.sar_w = p->vui.i_sar_width; h->seq.sar_h = p->vui.i_sar_height; h->seq.qp = h->qp;
+    h->seq.deblock = p->b_deblocking_filter;
     h->pts = (int64_t *)calloc((size_t)h->S * h->L, sizeof(int64_t));
     h->outq = (outframe_t *)calloc((size_t)h->S * h->L, sizeof(outframe_t));
     h->scratch_cap = (size_t)h->nmb * 3072 + 65536;

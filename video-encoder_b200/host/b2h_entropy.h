@@ -21,6 +21,7 @@ typedef struct {
     int fps_num, fps_den;
     int sar_w, sar_h;
     int qp;                     /* pic_init_qp (all slices use slice_qp_delta = 0) */
+    int deblock;                /* 1: disable_deblocking_filter_idc = 0 (filter on, offsets 0), 0: idc = 1 */
 } b2h_seq_t;
 
 typedef struct b2h_entropy b2h_entropy_t;   /* per-encoder scratch (neighbour maps) */
