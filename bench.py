@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--deblock", type=int, default=0, help="1: also run the in-loop deblocking filter K8 (row N2, outside the named path)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -220,7 +221,7 @@ def main():
         return float(t.item())
 
     eng = b2enc.Engine(W, H, slots=SLOTS, fmt="yuv420p", ring=RING, merange=MERANGE, qp=QP, subpel=1, intra_in_p=1,
-                       device=local, profile=0, streams=STREAMS)
+                       device=local, profile=0, streams=STREAMS, deblock=args.deblock)
     fill_inputs(eng, b2oracle, rank)
     for r in range(RING):
         eng.h2d(ring=r)
@@ -284,7 +285,7 @@ def main():
     if rank == 0:
         eng.close()
         eng1 = b2enc.Engine(W, H, slots=SLOTS, fmt="yuv420p", ring=2, merange=MERANGE, qp=QP, subpel=1, intra_in_p=1,
-                            device=local, profile=1, streams=1)
+                            device=local, profile=1, streams=1, deblock=args.deblock)
         fill_inputs(eng1, b2oracle, rank)
         eng1.h2d(ring=0); eng1.h2d(ring=1)
         eng1.encode(b2enc.FRAME_I, ring=0)
@@ -313,7 +314,7 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_step": SLOTS * world, "gop": GOP, "input_ring_frames": RING,
                        "l2": "no flush needed: per-step working set (cur+ref+recon planes of %d frames ~ %d MB + raw ring) exceeds the 126 MB L2"
                              % (SLOTS, int(SLOTS * 3 * 1.5 * w16 * h16 / 1e6)),
-                       "stream_groups": NG, "gop_phase_per_group": phase,
+                       "stream_groups": NG, "gop_phase_per_group": phase, "deblocking_filter": bool(args.deblock),
                        "parallelism": "closed-GOP sharding, %d GPUs x %d GOPs, no collective" % (world, SLOTS)},
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(SLOTS * in_bytes),
                     "d2h_bytes_per_step": int(SLOTS * mbs * (32 + 832)), "api": "b2_engine_h2d/encode/d2h (include/b2enc_engine.h), pinned host buffers",

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.join(ROOT, "video-encoder_b200")); sys.path.insert(0,
 import numpy as np, b2enc, b2oracle
 w, h, R, S, ring, steps = [int(a) for a in (sys.argv[1:7] if len(sys.argv) > 6 else "1920 1080 32 16 4 8".split())]
 streams = int(sys.argv[7]) if len(sys.argv) > 7 else 1
-eng = b2enc.Engine(w, h, slots=S, ring=ring, merange=R, qp=26, subpel=1, intra_in_p=1, profile=1, streams=streams)
+eng = b2enc.Engine(w, h, slots=S, ring=ring, merange=R, qp=26, subpel=1, intra_in_p=1, profile=1, streams=streams, deblock=int(os.environ.get('B2_DEBLOCK', '0')))
 t0 = time.time()
 for s in range(S):
     for r in range(ring):
