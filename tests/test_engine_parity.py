@@ -83,3 +83,53 @@ def test_engine_with_deblocking(oracle, b2, w, h, qp, R, cut):
     """K8 in-loop deblocking: reconstruction and everything downstream stay bit-exact"""
     seqs = [smooth_seq(w, h, 5, seed=qp + 1, cut=cut), smooth_seq(w, h, 5, seed=qp + 2)]
     run_and_compare(oracle, b2, seqs, w, h, qp, R, deblock=1)
+
+
+def _to_fmt(fmt, y, u, v):
+    """repack an I420 picture into the raw layout `fmt` (exact inverse for the formats whose conversion is a copy;
+    for packed 4:2:2 the chroma is duplicated on both lines so that the vertical average returns it)"""
+    h, w = y.shape
+    if fmt == "yuv420p":
+        return [y, u, v]
+    if fmt == "nv12":
+        uv = np.empty((u.shape[0], 2 * u.shape[1]), np.uint8); uv[:, 0::2] = u; uv[:, 1::2] = v
+        return [y, uv]
+    p = np.empty((h, 2 * w), np.uint8)
+    yo, uo, vo = (0, 1, 3) if fmt == "yuyv422" else (1, 0, 2)
+    p[:, yo::2] = y
+    p[:, uo::4] = np.repeat(u, 2, axis=0); p[:, vo::4] = np.repeat(v, 2, axis=0)
+    return [p]
+
+
+@pytest.mark.parametrize("fmt,w,h", [("nv12", 150, 98), ("yuyv422", 158, 82), ("uyvy422", 176, 144), ("yuv420p", 161, 99),
+                                     ("nv12", 64, 48)])
+def test_engine_input_formats_and_odd_sizes(oracle, b2, fmt, w, h):
+    """K0 inside the engine: every supported raw layout, widths/heights that are not multiples of 16 (or even odd),
+    checked against oracle conversion (pinned by live libswscale) + oracle frame encoder"""
+    S, T, qp, R = 2, 3, 29, 16
+    eng = b2.Engine(w, h, slots=S, fmt=fmt, ring=1, merange=R, qp=qp, subpel=1, intra_in_p=1, deblock=1)
+    prm = oracle.Params(qp, R, 1, 1, 1)
+    prev = [None] * S; prev_mv = [None] * S
+    seqs = [smooth_seq(w, h, T, seed=7 + s) for s in range(S)]
+    for t in range(T):
+        raws = []
+        for s in range(S):
+            y, u, v = seqs[s][t]
+            u = u[:(h + 1) // 2, :(w + 1) // 2]; v = v[:(h + 1) // 2, :(w + 1) // 2]
+            raws.append(_to_fmt(fmt, y, u, v))
+            eng.put_frame(s, 0, raws[-1])
+        ft = b2.FRAME_I if t == 0 else b2.FRAME_P
+        eng.h2d(); eng.encode(ft); eng.d2h(); eng.sync()
+        for s in range(S):
+            cy, cu, cv = oracle.convert_to_i420(fmt, w, h, raws[s])
+            cur = oracle.OFrame(w, h).load(cy, cu, cv); rec = oracle.OFrame(w, h)
+            info_o, coef_o = oracle.encode_frame(prm, ft, cur, prev[s], rec, prev_mv[s])
+            gy, gu, gv = eng.cur(s)
+            assert np.array_equal(gy, cur.y) and np.array_equal(gu, cur.u) and np.array_equal(gv, cur.v), f"K0 {fmt} t={t}"
+            info_g, coef_g = eng.results(s)
+            assert np.array_equal(info_g, info_o) and np.array_equal(coef_g["blk"], coef_o["blk"])
+            ry, ru, rv = eng.recon(s)
+            assert np.array_equal(ry, rec.y) and np.array_equal(ru, rec.u) and np.array_equal(rv, rec.v)
+            prev[s] = rec
+            prev_mv[s] = np.zeros(info_o.size, oracle.MV); prev_mv[s]["x"] = info_o["mvx"]; prev_mv[s]["y"] = info_o["mvy"]
+    eng.close()
