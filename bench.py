@@ -339,7 +339,7 @@ def main():
                        "stream_groups": NG, "gop_phase_per_group": phase, "deblocking_filter": bool(args.deblock),
                        "parallelism": "closed-GOP sharding, %d GPUs x %d GOPs, no collective" % (world, SLOTS)},
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(SLOTS * in_bytes),
-                    "d2h_bytes_per_step": int(SLOTS * mbs * (32 + 832)), "api": "b2_engine_h2d/encode/d2h (include/b2enc_engine.h), pinned host buffers",
+                    "d2h_bytes_per_step": int(SLOTS * mbs * (48 + 832)), "api": "b2_engine_h2d/encode/d2h (include/b2enc_engine.h), pinned host buffers",
                     "timing": "host wall clock around %d pipelined steps, synchronised on both sides" % n_e2e},
             "gpu_launches": int(launches),
             "clocks": clk,

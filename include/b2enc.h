@@ -17,6 +17,8 @@
  *   x264_encoder_encode(h,&nal,&n,in,out)    :970,:1078   b2_encoder_encode
  *   x264_encoder_delayed_frames(h)           :1076        b2_encoder_delayed_frames
  *   x264_encoder_close(h)                    :443         b2_encoder_close
+ *   MP4AddH264VideoTrack(.., profile, compat, level, 3) + MP4AddH264Sequence/PictureParameterSet
+ *                                            :638-640,:703-727  b2_avcc_write   (the avcC record itself)
  *
  * Error convention = the reference's: int 0 / non-zero (or <0), NULL handles, message on stderr
  * (av_encode.c:385,404,409,416,433,973).  No CPU fallback exists: without a CUDA device
@@ -69,6 +71,10 @@ typedef struct {
     int i_device;                       /* CUDA device ordinal                                  */
     int i_csp_in;                       /* B2_FMT_* of the pictures handed to b2_encoder_encode */
     int b_deblocking_filter;            /* in-loop deblocking filter (x264 field of the same name; default 1) */
+    int b_cabac;                        /* CABAC entropy coding (x264 field of the same name; default 1, cleared by
+                                           profile "baseline" exactly like x264_param_apply_profile)             */
+    int b_transform_8x8;                /* adaptive 8x8 transform (x264: analyse.b_transform_8x8; High profile;
+                                           cleared by profiles "baseline" and "main")                            */
 } b2_param_t;
 
 typedef struct {
@@ -107,6 +113,13 @@ void b2_picture_clean(b2_picture_t *pic);
 int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic_in, b2_picture_t *pic_out);
 int b2_encoder_delayed_frames(b2_t *h);
 void b2_encoder_close(b2_t *h);
+
+/* ---- MP4 side of the hand-off -----------------------------------------------------*/
+/* Writes the AVCDecoderConfigurationRecord (payload of the `avcC` box) for one SPS and one PPS NAL unit (without the
+ * 4-byte length prefix: nal.p_payload + 4, nal.i_payload - 4 -- what the reference passes to
+ * MP4AddH264SequenceParameterSet / MP4AddH264PictureParameterSet, av_encode.c:722, :727).  Replaces the libmp4v2 calls
+ * av_encode.c:638-640 and :703-727.  Returns the record size, < 0 on error (bad NALs or cap too small). */
+int b2_avcc_write(const uint8_t *sps, int sps_size, const uint8_t *pps, int pps_size, uint8_t *out, int cap);
 
 #ifdef __cplusplus
 }

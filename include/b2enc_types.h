@@ -21,7 +21,7 @@ extern "C" {
 #define B2_PAD   64
 #define B2_PADC  32
 
-enum { B2_MB_P16x16 = 0, B2_MB_I16x16 = 1, B2_MB_I4x4 = 2 };
+enum { B2_MB_P16x16 = 0, B2_MB_I16x16 = 1, B2_MB_I4x4 = 2, B2_MB_I8x8 = 3 };   /* P16x16 = any inter MB, see `part` */
 enum { B2_FRAME_I = 0, B2_FRAME_P = 1 };
 /* raw input layouts accepted by the conversion kernel (the sws_scale source formats, av_encode.c:427) */
 enum { B2_FMT_YUV420P = 0, B2_FMT_NV12 = 1, B2_FMT_YUYV422 = 2, B2_FMT_UYVY422 = 3 };
@@ -35,21 +35,32 @@ enum { B2_I4_V = 0, B2_I4_H, B2_I4_DC, B2_I4_DDL, B2_I4_DDR, B2_I4_VR, B2_I4_HD,
 
 typedef struct { int16_t x, y; } b2_mv_t;
 
-/* One macroblock's decisions: 32 bytes. */
+enum { B2_PART_16x16 = 0, B2_PART_16x8 = 1, B2_PART_8x16 = 2, B2_PART_8x8 = 3 };
+
+/* One macroblock's decisions: 48 bytes. */
 typedef struct {
-    int16_t  mvx, mvy;      /* quarter-pel motion vector (P16x16), 0 for intra            */
-    uint8_t  mb_type;       /* B2_MB_*                                                     */
-    uint8_t  i16_mode;      /* B2_I16_*  (mb_type == I16x16)                               */
-    uint8_t  chroma_mode;   /* B2_IC_*   (intra MBs)                                       */
-    uint8_t  cbp;           /* bits 0-3: luma 8x8 quadrants, bits 4-5: chroma 0/1/2        */
-    uint8_t  i4_mode[16];   /* B2_I4_* per 4x4 block, H.264 block-index (z) order          */
-    uint32_t cost;          /* cost of the chosen mode (SATD + lambda*bits model)          */
-    uint32_t nnz_mask;      /* bit b (0-15 luma, 16-19 U AC, 20-23 V AC): block has a      */
-                            /* non-zero level; bit 24 luma DC, bit 25 U DC, bit 26 V DC    */
+    int16_t  mvx, mvy;      /* quarter-pel motion vector of 8x8 quadrant 0 (= the MB's MV for      */
+                            /* P16x16); 0 for intra                                                */
+    uint8_t  mb_type;       /* B2_MB_*                                                             */
+    uint8_t  i16_mode;      /* B2_I16_*  (mb_type == I16x16)                                       */
+    uint8_t  chroma_mode;   /* B2_IC_*   (intra MBs)                                               */
+    uint8_t  cbp;           /* bits 0-3: luma 8x8 quadrants, bits 4-5: chroma 0/1/2                */
+    uint8_t  i4_mode[16];   /* B2_I4_* per 4x4 block, H.264 block-index (z) order; I8x8: the mode  */
+                            /* of 8x8 block k in all of i4_mode[4k..4k+3]                          */
+    uint32_t cost;          /* cost of the chosen mode (SATD + lambda*bits model)                  */
+    uint32_t nnz_mask;      /* bit b (0-15 luma, 16-19 U AC, 20-23 V AC): block has a non-zero     */
+                            /* level; bit 24 luma DC, bit 25 U DC, bit 26 V DC.  With the 8x8      */
+                            /* transform bit 4q+k is the k-th interleaved quarter of 8x8 block q   */
+    b2_mv_t  mv8[3];        /* quarter-pel MVs of 8x8 quadrants 1..3 (inter MBs; all equal to      */
+                            /* {mvx,mvy} for P16x16)                                               */
+    uint8_t  part;          /* B2_PART_* partition shape of an inter MB                            */
+    uint8_t  transform8x8;  /* 1: the luma residual uses the 8x8 transform (transform_size_8x8_flag) */
+    uint8_t  reserved[2];
 } b2_mbinfo_t;
 
 /* Quantised levels of one macroblock, each block in zig-zag scan order.
  *   blk 0..15  luma 4x4 (z order).  I16x16: index 0 is 0, DC lives in blk 24.
+ *              With the 8x8 transform, blk[4q..4q+3] hold the 64 levels of 8x8 block q in 8x8 zig-zag order.
  *   blk 16..19 U AC, 20..23 V AC (index 0 is 0, DC lives in blk 25)
  *   blk 24     luma DC of an I16x16 MB (16 levels, zig-zag)
  *   blk 25     chroma DC: [0..3] U, [4..7] V (raster 2x2)                               */

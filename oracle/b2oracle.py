@@ -26,9 +26,10 @@ class Params(C.Structure):
 MV = np.dtype([("x", "<i2"), ("y", "<i2")])
 MBINFO = np.dtype([("mvx", "<i2"), ("mvy", "<i2"), ("mb_type", "u1"), ("i16_mode", "u1"),
                    ("chroma_mode", "u1"), ("cbp", "u1"), ("i4_mode", "u1", (16,)),
-                   ("cost", "<u4"), ("nnz_mask", "<u4")])
+                   ("cost", "<u4"), ("nnz_mask", "<u4"), ("mv8", "<i2", (3, 2)), ("part", "u1"),
+                   ("transform8x8", "u1"), ("reserved", "u1", (2,))])
 MBCOEF = np.dtype([("blk", "<i2", (26, 16))])
-assert MBINFO.itemsize == 32 and MBCOEF.itemsize == 832
+assert MBINFO.itemsize == 48 and MBCOEF.itemsize == 832
 
 
 def build(force=False):
@@ -118,7 +119,8 @@ def me_fullpel_mb(cur, ref, R, mbx, mby, pmv=(0, 0), lam=0):
 # ---- frame-level oracle encoder + host entropy coder (linked into libb2oracle.so) ---------------
 class Seq(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("fps_num", C.c_int), ("fps_den", C.c_int),
-                ("sar_w", C.c_int), ("sar_h", C.c_int), ("qp", C.c_int), ("deblock", C.c_int)]
+                ("sar_w", C.c_int), ("sar_h", C.c_int), ("qp", C.c_int), ("deblock", C.c_int),
+                ("cabac", C.c_int), ("transform8x8", C.c_int)]
 
 
 def encode_frame(prm: Params, frame_type, cur: OFrame, ref, recon: OFrame, prev_mv=None):
@@ -130,13 +132,13 @@ def encode_frame(prm: Params, frame_type, cur: OFrame, ref, recon: OFrame, prev_
 
 
 class Entropy:
-    def __init__(self, w, h, qp, fps=(30, 1), sar=(1, 1), deblock=0):
+    def __init__(self, w, h, qp, fps=(30, 1), sar=(1, 1), deblock=0, cabac=0, transform8x8=0):
         L = lib()
         L.b2h_entropy_create.restype = C.c_void_p
         L.b2h_write_sps.restype = C.c_size_t; L.b2h_write_pps.restype = C.c_size_t; L.b2h_write_slice.restype = C.c_size_t
         L.b2h_write_slice.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.b2h_entropy_destroy.argtypes = [C.c_void_p]
-        self.seq = Seq(w, h, fps[0], fps[1], sar[0], sar[1], qp, deblock)
+        self.seq = Seq(w, h, fps[0], fps[1], sar[0], sar[1], qp, deblock, cabac, transform8x8)
         self.mbw, self.mbh = (w + 15) // 16, (h + 15) // 16
         self.e = L.b2h_entropy_create(self.mbw, self.mbh)
         self.buf = np.zeros(self.mbw * self.mbh * 3072 + 65536, np.uint8)
@@ -165,10 +167,10 @@ class Entropy:
         return self.buf[:n].tobytes()
 
 
-def encode_sequence(frames, w, h, qp=26, merange=16, subpel=1, intra_in_p=1, gop=32, fps=(30, 1), deblock=0):
+def encode_sequence(frames, w, h, qp=26, merange=16, subpel=1, intra_in_p=1, gop=32, fps=(30, 1), deblock=0, cabac=0):
     """frames: iterable of (y,u,v).  Returns (annexb_bytes, [recon OFrame], [info], [coef])."""
     prm = Params(qp, merange, subpel, intra_in_p, deblock)
-    ent = Entropy(w, h, qp, fps, deblock=deblock)
+    ent = Entropy(w, h, qp, fps, deblock=deblock, cabac=cabac)
     out = bytearray()
     sc = b"\x00\x00\x00\x01"
     recons, infos, coefs = [], [], []

@@ -1,0 +1,47 @@
+"""Row N3: the host CABAC slice writer (video-encoder_b200/host/b2h_cabac.c).  The oracle's per-MB
+decisions and levels are written as a Main-profile CABAC stream, decoded by libavcodec's native H.264 decoder and every
+decoded plane must equal the oracle's reconstruction bit for bit: one wrong context index, binarisation or table entry
+desynchronises the arithmetic decoder for the rest of the slice, so this pins the whole writer.  CPU only."""
+import collections
+import numpy as np
+import pytest
+from test_oracle_decode import smooth_seq, _roundtrip
+
+
+@pytest.mark.parametrize("w,h,qp,R,cut,deblock", [(176, 144, 26, 16, None, 0), (320, 240, 32, 32, 4, 1), (208, 160, 18, 16, 3, 0),
+                                                  (176, 144, 40, 16, 2, 1), (318, 242, 28, 16, None, 0), (64, 48, 12, 16, 1, 0),
+                                                  (96, 80, 51, 16, 2, 1)])
+def test_cabac_stream_decodes_to_oracle_recon(oracle, w, h, qp, R, cut, deblock):
+    frames = smooth_seq(w, h, 6, seed=qp, cut=cut)
+    bs, recons, infos = _roundtrip(oracle, frames, w, h, qp=qp, merange=R, gop=32, cabac=1, deblock=deblock)
+    types = collections.Counter()
+    for inf in infos[1:]:
+        types.update(inf["mb_type"].tolist())
+    assert types[0] > 0
+    if cut is not None:
+        assert types[1] + types[2] > 0
+
+
+def test_cabac_synthetic_pan_two_gops_and_size(oracle):
+    """bench content: skip runs, I16x16 + I4x4 + inter; CABAC must decode identically and be smaller than CAVLC"""
+    w, h = 192, 112
+    frames = [oracle.synth_frame(w, h, t) for t in range(8)]
+    bs_v, _, _ = _roundtrip(oracle, frames, w, h, qp=30, merange=16, gop=4, cabac=0)
+    bs_a, _, _ = _roundtrip(oracle, frames, w, h, qp=30, merange=16, gop=4, cabac=1)
+    assert len(bs_a) < len(bs_v)
+
+
+def test_cabac_noise_large_levels(oracle):
+    """saturated noise at low QP: long prefixes, Exp-Golomb escapes of coeff_abs_level_minus1 and of mvd"""
+    rng = np.random.default_rng(7)
+    w, h = 64, 48
+    frames = [(rng.integers(0, 256, (h, w), dtype=np.uint8), rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8),
+               rng.integers(0, 256, (h // 2, w // 2), dtype=np.uint8)) for _ in range(3)]
+    _roundtrip(oracle, frames, w, h, qp=10, merange=16, gop=32, cabac=1)
+
+
+def test_sps_profile_bytes(oracle):
+    """the reference reads profile_idc / compat / level straight from the SPS NAL (av_encode.c:703-705)"""
+    for cabac, t8, prof in ((0, 0, 66), (1, 0, 77), (1, 1, 100)):
+        sps = oracle.Entropy(320, 240, 26, cabac=cabac, transform8x8=t8).sps()
+        assert sps[0] == 0x67 and sps[1] == prof and sps[3] >= 13

@@ -25,7 +25,7 @@ def test_cli_y4m_to_h264(oracle, tmp_path):
     assert r.returncode == 0, r.stderr
     assert "9 frames in, 9 frames out" in r.stdout
     bs = open(out, "rb").read()
-    ref_bs, recons, _, _ = oracle.encode_sequence(frames, w, h, qp=24, merange=16, gop=4, fps=(30, 1), deblock=1)
+    ref_bs, recons, _, _ = oracle.encode_sequence(frames, w, h, qp=24, merange=16, gop=4, fps=(30, 1), deblock=1, cabac=1)
     assert bs == ref_bs                                  # same stream as the oracle encoder at the same settings
     dec = oracle.decode_yuv(oracle.split_access_units(bs))
     assert len(dec) == n

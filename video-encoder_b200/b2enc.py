@@ -12,7 +12,8 @@ _LIB = None
 MV = np.dtype([("x", "<i2"), ("y", "<i2")])
 MBINFO = np.dtype([("mvx", "<i2"), ("mvy", "<i2"), ("mb_type", "u1"), ("i16_mode", "u1"),
                    ("chroma_mode", "u1"), ("cbp", "u1"), ("i4_mode", "u1", (16,)),
-                   ("cost", "<u4"), ("nnz_mask", "<u4")])
+                   ("cost", "<u4"), ("nnz_mask", "<u4"), ("mv8", "<i2", (3, 2)), ("part", "u1"),
+                   ("transform8x8", "u1"), ("reserved", "u1", (2,))])
 MBCOEF = np.dtype([("blk", "<i2", (26, 16))])
 
 
@@ -188,7 +189,7 @@ class Engine:
     def results(self, slot):
         """(info, coef) numpy views of the last fetched results of `slot`"""
         pi = self.L.b2_engine_info(self.h, slot); pc = self.L.b2_engine_coef(self.h, slot)
-        info = np.frombuffer((C.c_uint8 * (self.nmb * 32)).from_address(pi), MBINFO)
+        info = np.frombuffer((C.c_uint8 * (self.nmb * MBINFO.itemsize)).from_address(pi), MBINFO)
         coef = np.frombuffer((C.c_uint8 * (self.nmb * 832)).from_address(pc), MBCOEF)
         return info, coef
 
@@ -242,7 +243,7 @@ class Param(C.Structure):
     _fields_ = [("i_width", C.c_int), ("i_height", C.c_int), ("b_annexb", C.c_int), ("i_fps_num", C.c_int), ("i_fps_den", C.c_int),
                 ("vui", _Vui), ("rc", _Rc), ("i_keyint_max", C.c_int), ("i_gop_slots", C.c_int), ("i_merange", C.c_int),
                 ("b_subpel", C.c_int), ("b_intra_in_p", C.c_int), ("i_device", C.c_int), ("i_csp_in", C.c_int),
-                ("b_deblocking_filter", C.c_int)]
+                ("b_deblocking_filter", C.c_int), ("b_cabac", C.c_int), ("b_transform_8x8", C.c_int)]
 
 
 class Image(C.Structure):

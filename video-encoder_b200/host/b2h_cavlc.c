@@ -8,63 +8,8 @@
  */
 #include <stdlib.h>
 #include <string.h>
-#include "b2h_entropy.h"
 
-/* ---- bit writer ----------------------------------------------------------------------------*/
-typedef struct {
-    uint8_t *buf;
-    size_t cap, pos;
-    uint64_t acc;
-    int nbits;
-    int overflow;
-} bs_t;
-
-static void bs_init(bs_t *b, uint8_t *buf, size_t cap) { b->buf = buf; b->cap = cap; b->pos = 0; b->acc = 0; b->nbits = 0; b->overflow = 0; }
-
-static inline void bs_put(bs_t *b, int n, uint32_t v)
-{
-    b->acc = (b->acc << n) | (v & (n == 32 ? 0xffffffffu : ((1u << n) - 1)));
-    b->nbits += n;
-    while (b->nbits >= 8) {
-        b->nbits -= 8;
-        if (b->pos < b->cap) b->buf[b->pos++] = (uint8_t)(b->acc >> b->nbits);
-        else b->overflow = 1;
-    }
-}
-static inline void bs_ue(bs_t *b, uint32_t v)
-{
-    uint32_t x = v + 1;
-    int len = 0;
-    while ((x >> len) > 1) len++;
-    if (len) bs_put(b, len, 0);
-    bs_put(b, len + 1, x);
-}
-static inline void bs_se(bs_t *b, int v) { bs_ue(b, v > 0 ? (uint32_t)(2 * v - 1) : (uint32_t)(-2 * v)); }
-static void bs_trailing(bs_t *b)
-{
-    bs_put(b, 1, 1);
-    if (b->nbits) bs_put(b, 8 - b->nbits, 0);
-}
-
-/* NAL = header + RBSP with emulation prevention (00 00 0x -> 00 00 03 0x) */
-static size_t nal_pack(int ref_idc, int type, const uint8_t *rbsp, size_t n, uint8_t *out, size_t cap)
-{
-    size_t o = 0;
-    int zeros = 0;
-    if (cap < 1) return 0;
-    out[o++] = (uint8_t)((ref_idc << 5) | type);
-    for (size_t i = 0; i < n; i++) {
-        if (zeros >= 2 && rbsp[i] <= 3) {
-            if (o >= cap) return 0;
-            out[o++] = 3;
-            zeros = 0;
-        }
-        if (o >= cap) return 0;
-        out[o++] = rbsp[i];
-        zeros = rbsp[i] == 0 ? zeros + 1 : 0;
-    }
-    return o;
-}
+#include "b2h_priv.h"
 
 /* ---- parameter sets --------------------------------------------------------------------------*/
 static int level_idc_for(int mbw, int mbh, int fps_num, int fps_den)
@@ -86,10 +31,19 @@ size_t b2h_write_sps(const b2h_seq_t *s, uint8_t *out, size_t cap)
     bs_t b;
     int mbw = (s->width + 15) >> 4, mbh = (s->height + 15) >> 4;
     bs_init(&b, rb, sizeof(rb));
-    bs_put(&b, 8, 66);                         /* profile_idc: Baseline                          */
-    bs_put(&b, 8, 0xC0);                       /* constraint_set0/1 -> Constrained Baseline      */
+    /* profile_idc / constraint flags: Constrained Baseline (CAVLC, 4x4), Main (CABAC) or High (8x8 transform);
+     * the reference reads these three bytes back from the SPS NAL (av_encode.c:703-705) */
+    const int profile = s->transform8x8 ? 100 : (s->cabac ? 77 : 66);
+    bs_put(&b, 8, (uint32_t)profile);
+    bs_put(&b, 8, profile == 66 ? 0xC0 : (profile == 77 ? 0x40 : 0x00));
     bs_put(&b, 8, (uint32_t)level_idc_for(mbw, mbh, s->fps_num, s->fps_den));
     bs_ue(&b, 0);                              /* seq_parameter_set_id                           */
+    if (profile == 100) {
+        bs_ue(&b, 1);                          /* chroma_format_idc 4:2:0                        */
+        bs_ue(&b, 0); bs_ue(&b, 0);            /* bit_depth_luma_minus8, bit_depth_chroma_minus8 */
+        bs_put(&b, 1, 0);                      /* qpprime_y_zero_transform_bypass_flag           */
+        bs_put(&b, 1, 0);                      /* seq_scaling_matrix_present_flag                */
+    }
     bs_ue(&b, 4);                              /* log2_max_frame_num_minus4 -> 8 bits            */
     bs_ue(&b, 2);                              /* pic_order_cnt_type 2: output order = decode order */
     bs_ue(&b, 1);                              /* max_num_ref_frames                             */
@@ -140,7 +94,7 @@ size_t b2h_write_pps(const b2h_seq_t *s, uint8_t *out, size_t cap)
     bs_t b;
     bs_init(&b, rb, sizeof(rb));
     bs_ue(&b, 0); bs_ue(&b, 0);                /* pps id, sps id                                  */
-    bs_put(&b, 1, 0);                          /* entropy_coding_mode_flag: CAVLC                 */
+    bs_put(&b, 1, s->cabac ? 1 : 0);           /* entropy_coding_mode_flag                        */
     bs_put(&b, 1, 0);                          /* bottom_field_pic_order_in_frame_present_flag    */
     bs_ue(&b, 0);                              /* num_slice_groups_minus1                         */
     bs_ue(&b, 0); bs_ue(&b, 0);                /* num_ref_idx_l0/l1_default_active_minus1         */
@@ -151,6 +105,11 @@ size_t b2h_write_pps(const b2h_seq_t *s, uint8_t *out, size_t cap)
     bs_put(&b, 1, 1);                          /* deblocking_filter_control_present_flag          */
     bs_put(&b, 1, 0);                          /* constrained_intra_pred_flag                     */
     bs_put(&b, 1, 0);                          /* redundant_pic_cnt_present_flag                  */
+    if (s->transform8x8) {
+        bs_put(&b, 1, 1);                      /* transform_8x8_mode_flag                         */
+        bs_put(&b, 1, 0);                      /* pic_scaling_matrix_present_flag                 */
+        bs_se(&b, 0);                          /* second_chroma_qp_index_offset                   */
+    }
     bs_trailing(&b);
     return b.overflow ? 0 : nal_pack(3, B2H_NAL_PPS, rb, b.pos, out, cap);
 }
@@ -237,8 +196,10 @@ static const uint8_t cbp_from_code_inter[48] = {0, 16, 1, 2, 4, 8, 32, 3, 5, 10,
                                                 14, 6, 9, 31, 35, 37, 42, 44, 33, 34, 36, 40, 39, 43, 45, 46,
                                                 17, 18, 20, 24, 19, 21, 26, 28, 23, 27, 29, 30, 22, 25, 38, 41};
 
-static const uint8_t blk_x[16] = {0, 1, 0, 1, 2, 3, 2, 3, 0, 1, 0, 1, 2, 3, 2, 3};
-static const uint8_t blk_y[16] = {0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3};
+const uint8_t b2h_blk_x[16] = {0, 1, 0, 1, 2, 3, 2, 3, 0, 1, 0, 1, 2, 3, 2, 3};
+const uint8_t b2h_blk_y[16] = {0, 0, 1, 1, 0, 0, 1, 1, 2, 2, 3, 3, 2, 2, 3, 3};
+#define blk_x b2h_blk_x
+#define blk_y b2h_blk_y
 
 /* exported for the table self-test (tests/test_cavlc_tables.py) */
 const uint8_t *b2h_table(int which, int *rows, int *cols)
@@ -260,19 +221,6 @@ const uint8_t *b2h_table(int which, int *rows, int *cols)
     }
 }
 
-/* ---- per-encoder scratch -----------------------------------------------------------------------*/
-struct b2h_entropy {
-    int mbw, mbh;
-    uint8_t *nnz_y;          /* [4mbh][4mbw] total_coeff of each luma 4x4                         */
-    uint8_t *nnz_c[2];       /* [2mbh][2mbw] total_coeff of each chroma AC 4x4                    */
-    int8_t *i4;              /* [4mbh][4mbw] intra4x4 pred mode (2 for non-I4x4 MBs)              */
-    int8_t *ref;             /* [mbh][mbw]   0 inter, -1 intra                                    */
-    b2_mv_t *mv;             /* [mbh][mbw]                                                        */
-    uint8_t cbp_code_intra[48], cbp_code_inter[48];
-    uint8_t *rbsp;
-    size_t rbsp_cap;
-};
-
 b2h_entropy_t *b2h_entropy_create(int mbw, int mbh)
 {
     b2h_entropy_t *e = (b2h_entropy_t *)calloc(1, sizeof(*e));
@@ -285,9 +233,12 @@ b2h_entropy_t *b2h_entropy_create(int mbw, int mbh)
     e->i4 = (int8_t *)malloc(n * 16);
     e->ref = (int8_t *)malloc(n);
     e->mv = (b2_mv_t *)malloc(n * sizeof(b2_mv_t));
+    e->mbf = (uint8_t *)calloc(n, 1); e->cbp = (uint8_t *)calloc(n, 1); e->cmode = (uint8_t *)calloc(n, 1);
+    e->mvd[0] = (uint8_t *)calloc(n, 16); e->mvd[1] = (uint8_t *)calloc(n, 16);
     e->rbsp_cap = n * 2048 + 4096;
     e->rbsp = (uint8_t *)malloc(e->rbsp_cap);
-    if (!e->nnz_y || !e->nnz_c[0] || !e->nnz_c[1] || !e->i4 || !e->ref || !e->mv || !e->rbsp) {
+    if (!e->nnz_y || !e->nnz_c[0] || !e->nnz_c[1] || !e->i4 || !e->ref || !e->mv || !e->rbsp || !e->mbf || !e->cbp || !e->cmode ||
+        !e->mvd[0] || !e->mvd[1]) {
         b2h_entropy_destroy(e);
         return NULL;
     }
@@ -302,6 +253,7 @@ void b2h_entropy_destroy(b2h_entropy_t *e)
 {
     if (!e) return;
     free(e->nnz_y); free(e->nnz_c[0]); free(e->nnz_c[1]); free(e->i4); free(e->ref); free(e->mv); free(e->rbsp);
+    free(e->mbf); free(e->cbp); free(e->cmode); free(e->mvd[0]); free(e->mvd[1]);
     free(e);
 }
 
@@ -388,7 +340,7 @@ static inline int median3(int a, int b, int c)
 }
 
 /* 8.4.1.3 median prediction for a 16x16 partition, single reference frame */
-static b2_mv_t mv_pred16x16(const b2h_entropy_t *e, int mbx, int mby, int *availA, int *availB,
+b2_mv_t b2h_mv_pred16x16(const b2h_entropy_t *e, int mbx, int mby, int *availA, int *availB,
                             b2_mv_t *mvA_o, int *refA_o, b2_mv_t *mvB_o, int *refB_o)
 {
     const int w = e->mbw;
@@ -409,15 +361,8 @@ static b2_mv_t mv_pred16x16(const b2h_entropy_t *e, int mbx, int mby, int *avail
     return p;
 }
 
-/* ---- slice ---------------------------------------------------------------------------------------*/
-size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int frame_num, int idr_pic_id,
-                       const b2_mbinfo_t *info, const b2_mbcoef_t *coef, uint8_t *out, size_t cap)
+void b2h_slice_header(bs_t *b, const b2h_seq_t *s, int is_p, int frame_num, int idr_pic_id)
 {
-    bs_t bs, *b = &bs;
-    const int mbw = e->mbw, mbh = e->mbh, is_p = frame_type == B2_FRAME_P;
-    const int ys = 4 * mbw, cs = 2 * mbw;
-    bs_init(b, e->rbsp, e->rbsp_cap);
-    /* slice_header() */
     bs_ue(b, 0);                                   /* first_mb_in_slice                   */
     bs_ue(b, is_p ? 5 : 7);                        /* slice_type: all slices P / all I    */
     bs_ue(b, 0);                                   /* pic_parameter_set_id                */
@@ -431,6 +376,7 @@ size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int
         bs_put(b, 1, 0);                           /* no_output_of_prior_pics_flag        */
         bs_put(b, 1, 0);                           /* long_term_reference_flag            */
     }
+    if (s->cabac && is_p) bs_ue(b, 0);             /* cabac_init_idc                      */
     bs_se(b, 0);                                   /* slice_qp_delta                      */
     if (s->deblock) {
         bs_ue(b, 0);                               /* disable_deblocking_filter_idc = 0   */
@@ -438,6 +384,18 @@ size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int
     } else {
         bs_ue(b, 1);                               /* disable_deblocking_filter_idc = 1   */
     }
+}
+
+/* ---- slice ---------------------------------------------------------------------------------------*/
+size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int frame_num, int idr_pic_id,
+                       const b2_mbinfo_t *info, const b2_mbcoef_t *coef, uint8_t *out, size_t cap)
+{
+    bs_t bs, *b = &bs;
+    const int mbw = e->mbw, mbh = e->mbh, is_p = frame_type == B2_FRAME_P;
+    const int ys = 4 * mbw, cs = 2 * mbw;
+    if (s->cabac) return b2h_write_slice_cabac(e, s, frame_type, frame_num, idr_pic_id, info, coef, out, cap);
+    bs_init(b, e->rbsp, e->rbsp_cap);
+    b2h_slice_header(b, s, is_p, frame_num, idr_pic_id);
 
     /* slice_data() */
     int skip_run = 0;
@@ -456,7 +414,7 @@ size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int
             if (m->mb_type == B2_MB_P16x16) {
                 int hasA, hasB, refA, refB;
                 b2_mv_t mvA, mvB;
-                b2_mv_t mvp = mv_pred16x16(e, mbx, mby, &hasA, &hasB, &mvA, &refA, &mvB, &refB);
+                b2_mv_t mvp = b2h_mv_pred16x16(e, mbx, mby, &hasA, &hasB, &mvA, &refA, &mvB, &refB);
                 b2_mv_t skipmv = mvp;
                 if (!hasA || !hasB || (refA == 0 && mvA.x == 0 && mvA.y == 0) || (refB == 0 && mvB.x == 0 && mvB.y == 0))
                     skipmv.x = skipmv.y = 0;

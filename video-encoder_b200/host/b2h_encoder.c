@@ -1,7 +1,7 @@
 /*
  * b2h_encoder.c -- host side of the drop-in encoder boundary (include/b2enc.h): the x264 API subset
  * that av_encode.c calls (enc_x264_open :378-438, the encode loop :968-975, the drain loop :1076-1083),
- * implemented over the CUDA engine (include/b2enc_engine.h) and the host CAVLC stage (b2h_entropy.h).
+ * implemented over the CUDA engine (include/b2enc_engine.h) and the host entropy stage (b2h_entropy.h: CABAC or CAVLC).
  *
  * Frame queue (row a0 of SURVEY.md 8a): the caller still hands over one picture per call, but pictures
  * are gathered into i_gop_slots closed GOPs of i_keyint_max frames; a full batch is advanced through
@@ -78,6 +78,8 @@ int b2_param_default_preset(b2_param_t *p, const char *preset, const char *tune)
     p->b_annexb = 1;
     p->i_keyint_max = 32; p->i_gop_slots = 8; p->i_device = 0; p->i_csp_in = B2_FMT_YUV420P;
     p->b_deblocking_filter = 1;
+    p->b_cabac = 1;                      /* x264 default at every preset but ultrafast */
+    p->b_transform_8x8 = 0;
     int found = preset == NULL;
     p->i_merange = 16; p->b_subpel = 1; p->b_intra_in_p = 1;
     for (unsigned i = 0; preset && i < sizeof(presets) / sizeof(presets[0]); i++)
@@ -86,6 +88,7 @@ int b2_param_default_preset(b2_param_t *p, const char *preset, const char *tune)
             found = 1;
         }
     if (!found) { fprintf(stderr, "b2enc: invalid preset '%s'\n", preset); return -1; }
+    if (preset && !strcmp(preset, "ultrafast")) { p->b_cabac = 0; p->b_deblocking_filter = 0; }     /* as x264's ultrafast */
     if (tune) {
         int ok = 0;
         for (unsigned i = 0; i < sizeof(tunes) / sizeof(tunes[0]); i++) ok |= !strcmp(tune, tunes[i]);
@@ -99,8 +102,10 @@ int b2_param_apply_profile(b2_param_t *p, const char *profile)
 {
     if (!p) return -1;
     if (!profile) return 0;
-    /* the stream is always Constrained Baseline (CAVLC, no 8x8 transform), a subset of all three */
-    if (!strcmp(profile, "baseline") || !strcmp(profile, "main") || !strcmp(profile, "high")) return 0;
+    /* like x264_param_apply_profile: a profile only removes tools.  baseline: CAVLC, 4x4 transform; main: no 8x8 transform */
+    if (!strcmp(profile, "baseline")) { p->b_cabac = 0; p->b_transform_8x8 = 0; return 0; }
+    if (!strcmp(profile, "main")) { p->b_transform_8x8 = 0; return 0; }
+    if (!strcmp(profile, "high")) return 0;
     fprintf(stderr, "b2enc: invalid profile: %s\n", profile);
     return -1;
 }
@@ -153,6 +158,7 @@ b2_t *b2_encoder_open(b2_param_t *p)
     h->seq.width = p->i_width; h->seq.height = p->i_height; h->seq.fps_num = p->i_fps_num; h->seq.fps_den = p->i_fps_den;
     h->seq.sar_w = p->vui.i_sar_width; h->seq.sar_h = p->vui.i_sar_height; h->seq.qp = h->qp;
     h->seq.deblock = p->b_deblocking_filter;
+    h->seq.cabac = p->b_cabac != 0; h->seq.transform8x8 = p->b_transform_8x8 != 0;
     h->pts = (int64_t *)calloc((size_t)h->S * h->L, sizeof(int64_t));
     h->outq = (outframe_t *)calloc((size_t)h->S * h->L, sizeof(outframe_t));
     h->scratch_cap = (size_t)h->nmb * 3072 + 65536;

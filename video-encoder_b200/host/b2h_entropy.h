@@ -1,6 +1,6 @@
 /*
- * b2h_entropy.h -- host-side serial stage: H.264 Baseline CAVLC slice writer + SPS/PPS + NAL
- * packing.  In the reference this stage is the tail of x264_encoder_encode (av_encode.c:970)
+ * b2h_entropy.h -- host-side serial stage: H.264 slice writer (CAVLC, b2h_cavlc.c, or CABAC,
+ * b2h_cabac.c) + SPS/PPS + NAL packing.  In the reference this stage is the tail of x264_encoder_encode (av_encode.c:970)
  * and is left on the host by BASELINE.json's north_star ("entropy coding and muxing left on
  * the serial stage").  libx264 is not available in this image, so a minimal writer is part of
  * the product; its output is pinned by decoding it with libavcodec's H.264 decoder.
@@ -22,6 +22,8 @@ typedef struct {
     int sar_w, sar_h;
     int qp;                     /* pic_init_qp (all slices use slice_qp_delta = 0) */
     int deblock;                /* 1: disable_deblocking_filter_idc = 0 (filter on, offsets 0), 0: idc = 1 */
+    int cabac;                  /* 1: entropy_coding_mode_flag = 1 (CABAC, Main profile), 0: CAVLC (Constrained Baseline) */
+    int transform8x8;           /* 1: transform_8x8_mode_flag = 1 (High profile)                            */
 } b2h_seq_t;
 
 typedef struct b2h_entropy b2h_entropy_t;   /* per-encoder scratch (neighbour maps) */

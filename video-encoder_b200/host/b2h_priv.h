@@ -1,0 +1,40 @@
+/*
+ * b2h_priv.h -- state shared by the host slice writers (b2h_cavlc.c: CAVLC, parameter sets, slice header;
+ * b2h_cabac.c: CABAC).  Internal to the host stage; not part of the C-ABI.
+ */
+#ifndef B2H_PRIV_H
+#define B2H_PRIV_H
+#include "b2h_bits.h"
+#include "b2h_entropy.h"
+
+/* per-encoder scratch: neighbour maps of the picture being written (one slice per picture, raster order) */
+struct b2h_entropy {
+    int mbw, mbh;
+    uint8_t *nnz_y;          /* [4mbh][4mbw] total_coeff of each luma 4x4                         */
+    uint8_t *nnz_c[2];       /* [2mbh][2mbw] total_coeff of each chroma AC 4x4                    */
+    int8_t *i4;              /* [4mbh][4mbw] intra4x4 pred mode (2 for non-I4x4 MBs)              */
+    int8_t *ref;             /* [mbh][mbw]   0 inter, -1 intra                                    */
+    b2_mv_t *mv;             /* [mbh][mbw]                                                        */
+    uint8_t cbp_code_intra[48], cbp_code_inter[48];
+    uint8_t *rbsp;
+    size_t rbsp_cap;
+    /* CABAC only (9.3.3.1.1: context increments read the left / top neighbours) */
+    uint8_t *mbf;            /* [mbh][mbw] B2H_MBF_* flags                                        */
+    uint8_t *cbp;            /* [mbh][mbw] coded_block_pattern (bits 0-3 luma, 4-5 chroma)        */
+    uint8_t *cmode;          /* [mbh][mbw] intra_chroma_pred_mode (0 for inter MBs)               */
+    uint8_t *mvd[2];         /* [4mbh][4mbw] |mvd_l0| per 4x4, x and y, saturated at 255          */
+};
+enum { B2H_MBF_SKIP = 1, B2H_MBF_INTRA = 2, B2H_MBF_I16 = 4, B2H_MBF_T8 = 8,
+       B2H_MBF_DC_Y = 16, B2H_MBF_DC_U = 32, B2H_MBF_DC_V = 64 };      /* DC_*: coded_block_flag of that DC block */
+
+/* 8.4.1.3 median prediction for a 16x16 partition, single reference frame; also returns the A / B neighbours
+ * (P_Skip inference 8.4.1.1) */
+b2_mv_t b2h_mv_pred16x16(const b2h_entropy_t *e, int mbx, int mby, int *availA, int *availB,
+                         b2_mv_t *mvA_o, int *refA_o, b2_mv_t *mvB_o, int *refB_o);
+/* slice_header() 7.3.3 up to and including the deblocking fields */
+void b2h_slice_header(bs_t *b, const b2h_seq_t *s, int is_p, int frame_num, int idr_pic_id);
+size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int frame_num, int idr_pic_id,
+                             const b2_mbinfo_t *info, const b2_mbcoef_t *coef, uint8_t *out, size_t cap);
+extern const uint8_t b2h_blk_x[16], b2h_blk_y[16];
+
+#endif
