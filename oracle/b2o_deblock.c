@@ -1,6 +1,7 @@
 /* b2o_deblock.c -- ORACLE (test infrastructure only; see b2o.h).
  * In-loop deblocking filter, ITU-T H.264 8.7 (normative; pinned by the libavcodec decoder drift test), restricted to
- * what the stage produces: frame macroblocks, 4x4 transform, one reference frame, constant QP, filter offsets 0.
+ * what the stage produces: frame macroblocks, 4x4 or 8x8 transform (8x8: only the 8-pel edges are transform edges),
+ * one reference frame, constant QP, filter offsets 0.
  * In the reference this is part of x264_encoder_encode (av_encode.c:970; x264 enables it by default, "film" tunes -1:-1
  * which is outside the named path).  SURVEY.md 8f row N2. */
 #include <stdlib.h>
@@ -71,11 +72,19 @@ static void filter_line(uint8_t *pix, int step, int bs, int qp, int chroma)
 /* z-order index of the 4x4 block at (bx,by) */
 static inline int zidx(int bx, int by) { return (bx & 1) | ((by & 1) << 1) | ((bx >> 1) << 2) | ((by >> 1) << 3); }
 
+/* does the transform block that contains 4x4 block (bx,by) hold non-zero coefficients?  With the 8x8 transform
+ * that is the whole 8x8 block (nnz_mask bits 4q..4q+3 are its interleaved quarters) */
+static inline int blk_coded(const b2_mbinfo_t *m, int bx, int by)
+{
+    if (m->transform8x8) return ((m->nnz_mask >> (4 * ((bx >> 1) | ((by >> 1) << 1)))) & 15u) != 0;
+    return (m->nnz_mask >> zidx(bx, by)) & 1u;
+}
+
 /* boundary strength between 4x4 block (pbx,pby) of MB `mp` and block (qbx,qby) of MB `mq` (8.7.2.1) */
 static int bs_of(const b2_mbinfo_t *mp, int pbx, int pby, const b2_mbinfo_t *mq, int qbx, int qby, int mb_edge)
 {
     if (mp->mb_type != B2_MB_P16x16 || mq->mb_type != B2_MB_P16x16) return mb_edge ? 4 : 3;
-    if (((mp->nnz_mask >> zidx(pbx, pby)) & 1u) || ((mq->nnz_mask >> zidx(qbx, qby)) & 1u)) return 2;
+    if (blk_coded(mp, pbx, pby) || blk_coded(mq, qbx, qby)) return 2;
     if (abs(mp->mvx - mq->mvx) >= 4 || abs(mp->mvy - mq->mvy) >= 4) return 1;
     return 0;
 }
@@ -91,7 +100,7 @@ void b2o_deblock_frame(b2o_frame_t *f, const b2_mbinfo_t *info, int qp)
             int bs[4][4];
             /* vertical edges (left to right) */
             for (int e = 0; e < 4; e++) {
-                if (e == 0 && mbx == 0) { for (int k = 0; k < 4; k++) bs[e][k] = 0; continue; }
+                if ((e == 0 && mbx == 0) || ((e & 1) && mq->transform8x8)) { for (int k = 0; k < 4; k++) bs[e][k] = 0; continue; }
                 const b2_mbinfo_t *mp = e == 0 ? mq - 1 : mq;
                 for (int k = 0; k < 4; k++) bs[e][k] = bs_of(mp, e == 0 ? 3 : e - 1, k, mq, e, k, e == 0);
                 for (int r = 0; r < 16; r++) filter_line(y + (size_t)r * f->pitch + 4 * e, 1, bs[e][r >> 2], qp, 0);
@@ -101,7 +110,7 @@ void b2o_deblock_frame(b2o_frame_t *f, const b2_mbinfo_t *info, int qp)
                     for (int r = 0; r < 8; r++) filter_line(c[p] + (size_t)r * f->pitchc + 4 * e, 1, bs[2 * e][r >> 1], qpc, 1);
             /* horizontal edges (top to bottom) */
             for (int e = 0; e < 4; e++) {
-                if (e == 0 && mby == 0) { for (int k = 0; k < 4; k++) bs[e][k] = 0; continue; }
+                if ((e == 0 && mby == 0) || ((e & 1) && mq->transform8x8)) { for (int k = 0; k < 4; k++) bs[e][k] = 0; continue; }
                 const b2_mbinfo_t *mp = e == 0 ? mq - f->mbw : mq;
                 for (int k = 0; k < 4; k++) bs[e][k] = bs_of(mp, k, e == 0 ? 3 : e - 1, mq, k, e, e == 0);
                 for (int x = 0; x < 16; x++) filter_line(y + (size_t)(4 * e) * f->pitch + x, f->pitch, bs[e][x >> 2], qp, 0);

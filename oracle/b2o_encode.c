@@ -48,11 +48,23 @@ void b2o_recon_inter_mb(const b2o_params_t *prm, const b2o_frame_t *cur, const b
     b2o_mc_chroma(ref->u, ref->pitchc, mbx * 8, mby * 8, mi->mvx, mi->mvy, 8, 8, recon->u + offc, recon->pitchc);
     b2o_mc_chroma(ref->v, ref->pitchc, mbx * 8, mby * 8, mi->mvx, mi->mvy, 8, 8, recon->v + offc, recon->pitchc);
     uint32_t mask = 0;
-    for (int b = 0; b < 16; b++) {
-        int o = b2o_blk_y[b] * 4 * cur->pitch + b2o_blk_x[b] * 4;
-        int orc = b2o_blk_y[b] * 4 * recon->pitch + b2o_blk_x[b] * 4;
-        if (b2o_code_luma4x4(sy + o, cur->pitch, ry + orc, recon->pitch, prm->qp, 0, coef->blk[b])) mask |= 1u << b;
+    /* transform size (row N1): like x264's non-RD analysis, the 8x8 transform is used when the 8x8-Hadamard cost of
+     * the prediction error is below its 4x4-Hadamard cost; ry holds the motion-compensated prediction here */
+    int t8 = prm->transform8x8 && b2o_sa8d16x16(sy, cur->pitch, ry, recon->pitch) < b2o_satd16x16(sy, cur->pitch, ry, recon->pitch);
+    if (t8) {
+        for (int q = 0; q < 4; q++) {
+            int o = (q >> 1) * 8 * cur->pitch + (q & 1) * 8, orc = (q >> 1) * 8 * recon->pitch + (q & 1) * 8;
+            mask |= (uint32_t)b2o_code_luma8x8(sy + o, cur->pitch, ry + orc, recon->pitch, prm->qp, 0, coef->blk[4 * q]) << (4 * q);
+        }
+        if (!(mask & 0xffffu)) t8 = 0;       /* transform_size_8x8_flag is only sent with coded luma: inferred 0 otherwise */
+    } else {
+        for (int b = 0; b < 16; b++) {
+            int o = b2o_blk_y[b] * 4 * cur->pitch + b2o_blk_x[b] * 4;
+            int orc = b2o_blk_y[b] * 4 * recon->pitch + b2o_blk_x[b] * 4;
+            if (b2o_code_luma4x4(sy + o, cur->pitch, ry + orc, recon->pitch, prm->qp, 0, coef->blk[b])) mask |= 1u << b;
+        }
     }
+    mi->transform8x8 = (uint8_t)t8;
     mask |= code_chroma(prm, cur, recon, mbx, mby, 0, coef);
     finish_cbp(mi, mask);
 }

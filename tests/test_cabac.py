@@ -45,3 +45,17 @@ def test_sps_profile_bytes(oracle):
     for cabac, t8, prof in ((0, 0, 66), (1, 0, 77), (1, 1, 100)):
         sps = oracle.Entropy(320, 240, 26, cabac=cabac, transform8x8=t8).sps()
         assert sps[0] == 0x67 and sps[1] == prof and sps[3] >= 13
+
+
+# ---- row N1: adaptive 8x8 transform of inter macroblocks (High profile), both entropy coders ------------------------
+@pytest.mark.parametrize("cabac", [0, 1])
+@pytest.mark.parametrize("w,h,qp,R,cut,deblock", [(176, 144, 26, 16, None, 1), (320, 240, 32, 32, 4, 1), (208, 160, 18, 16, 3, 0),
+                                                  (318, 242, 28, 16, None, 1), (64, 48, 12, 16, 1, 0), (96, 80, 44, 16, 2, 1)])
+def test_transform8x8_stream_decodes_to_oracle_recon(oracle, w, h, qp, R, cut, deblock, cabac):
+    frames = smooth_seq(w, h, 6, seed=qp, cut=cut)
+    bs, recons, infos = _roundtrip(oracle, frames, w, h, qp=qp, merange=R, gop=32, cabac=cabac, deblock=deblock, transform8x8=1)
+    t8 = sum(int(inf["transform8x8"].sum()) for inf in infos)
+    n4 = sum(int(((inf["mb_type"] == 0) & (inf["transform8x8"] == 0) & ((inf["cbp"] & 15) != 0)).sum()) for inf in infos)
+    assert t8 > 0, "no macroblock chose the 8x8 transform"
+    if qp < 40:
+        assert n4 > 0, "no coded inter macroblock kept the 4x4 transform"

@@ -425,11 +425,14 @@ size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int
                 bs_se(b, m->mvx - mvp.x);
                 bs_se(b, m->mvy - mvp.y);
                 bs_ue(b, e->cbp_code_inter[m->cbp]);
+                if (cbp_l && s->transform8x8) bs_put(b, 1, m->transform8x8 != 0);     /* transform_size_8x8_flag */
             } else {
                 if (is_p) { bs_ue(b, (uint32_t)skip_run); skip_run = 0; }
-                if (m->mb_type == B2_MB_I4x4) {
+                if (m->mb_type != B2_MB_I16x16) {
+                    const int i8 = m->mb_type == B2_MB_I8x8;
                     bs_ue(b, is_p ? 5 : 0);                    /* I_NxN */
-                    for (int k = 0; k < 16; k++) {
+                    if (s->transform8x8) bs_put(b, 1, (uint32_t)i8);                  /* transform_size_8x8_flag */
+                    for (int k = 0; k < 16; k += i8 ? 4 : 1) {
                         int x = mbx * 4 + blk_x[k], y = mby * 4 + blk_y[k];
                         int pred = 2;
                         if (x > 0 && y > 0) {
@@ -440,6 +443,7 @@ size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int
                         if (mode == pred) bs_put(b, 1, 1);
                         else bs_put(b, 4, (uint32_t)(mode < pred ? mode : mode - 1));   /* flag 0 + rem (3 bits) */
                         e->i4[y * ys + x] = (int8_t)mode;
+                        if (i8) e->i4[y * ys + x + 1] = e->i4[(y + 1) * ys + x] = e->i4[(y + 1) * ys + x + 1] = (int8_t)mode;
                     }
                     bs_ue(b, m->chroma_mode);
                     bs_ue(b, e->cbp_code_intra[m->cbp]);
@@ -458,6 +462,16 @@ size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int
                         int x = mbx * 4 + blk_x[k], y = mby * 4 + blk_y[k];
                         e->nnz_y[y * ys + x] = (uint8_t)write_residual(b, c->blk[k] + 1, 15, pred_nc(e->nnz_y, ys, x, y));
                     }
+            } else if (m->transform8x8 && s->transform8x8) {
+                /* 8x8 transform with CAVLC (7.3.5.3.2): the 64 levels are split into four interleaved 4x4 blocks */
+                for (int k = 0; k < 16; k++) {
+                    if (!(cbp_l & (1 << (k >> 2)))) continue;
+                    int x = mbx * 4 + blk_x[k], y = mby * 4 + blk_y[k];
+                    int16_t l4[16];
+                    const int16_t *l8 = c->blk[k & ~3];
+                    for (int i = 0; i < 16; i++) l4[i] = l8[4 * i + (k & 3)];
+                    e->nnz_y[y * ys + x] = (uint8_t)write_residual(b, l4, 16, pred_nc(e->nnz_y, ys, x, y));
+                }
             } else {
                 for (int k = 0; k < 16; k++) {
                     if (!(cbp_l & (1 << (k >> 2)))) continue;
