@@ -34,6 +34,7 @@ typedef struct {
     int streams;       /* stream groups the slots are split into (0 = automatic); groups   */
                        /* run on separate CUDA streams so that their kernels overlap       */
     int deblock;       /* 1: in-loop deblocking filter (K8) on every reconstructed frame    */
+    int transform8x8;  /* 1: adaptive 8x8 transform for inter macroblocks (SA8D < SATD), row N1 */
 } b2_engine_cfg_t;
 
 b2_engine_t *b2_engine_create(const b2_engine_cfg_t *cfg);      /* NULL on error */

@@ -54,12 +54,13 @@ def to_annexb(out, length_prefixed):
     return bs
 
 
-@pytest.mark.parametrize("profile,profile_idc,cabac", [(None, 77, 1), ("baseline", 66, 0)])
-def test_reference_call_sequence_and_bitstream(oracle, b2, profile, profile_idc, cabac):
+@pytest.mark.parametrize("profile,profile_idc,cabac,t8", [(None, 77, 1, 0), ("baseline", 66, 0, 0), ("high", 100, 1, 1)])
+def test_reference_call_sequence_and_bitstream(oracle, b2, profile, profile_idc, cabac, t8):
     """profile NULL is what the reference passes by default (av_encode.c:105, :403): x264's preset default = CABAC"""
     w, h, qp, gop, n = 176, 144, 27, 4, 11
     frames = smooth_seq(w, h, n, seed=4, cut=6)
-    out = drive(b2, frames, w, h, preset="medium", tune="film", quality=qp, profile=profile, i_keyint_max=gop, i_gop_slots=2)
+    out = drive(b2, frames, w, h, preset="medium", tune="film", quality=qp, profile=profile, i_keyint_max=gop, i_gop_slots=2,
+                b_transform_8x8=t8)
     assert len(out) == n
     assert [o[1] for o in out] == [1000 + 40 * t for t in range(n)]               # display order, pts passed through
     assert [o[3] for o in out] == [int(t % gop == 0) for t in range(n)]           # keyframe flag (av_encode.c:783)
@@ -67,7 +68,8 @@ def test_reference_call_sequence_and_bitstream(oracle, b2, profile, profile_idc,
     assert sps[0] == 7 and out[0][0][1][0] == 8 and out[0][0][2][0] == 5          # SPS, PPS, IDR slice (av_encode.c:683-736)
     assert sps[1][5] == profile_idc and sps[1][7] in (12, 13, 20, 21, 30)                  # profile_idc / level_idc at [5],[7] (:703-705)
     bs = to_annexb(out, length_prefixed=True)
-    ref_bs, recons, _, _ = oracle.encode_sequence(frames, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1), deblock=1, cabac=cabac)
+    ref_bs, recons, _, _ = oracle.encode_sequence(frames, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1), deblock=1, cabac=cabac,
+                                                   transform8x8=t8)
     assert bs == ref_bs, "GPU drop-in bitstream differs from the oracle encoder's"
     dec = oracle.decode_yuv(oracle.split_access_units(bs))
     assert len(dec) == n

@@ -8,14 +8,16 @@ from test_oracle_decode import smooth_seq
 
 pytestmark = pytest.mark.gpu
 
-INFO_FIELDS = ["mb_type", "mvx", "mvy", "i16_mode", "chroma_mode", "cbp", "i4_mode", "cost", "nnz_mask"]
+INFO_FIELDS = ["mb_type", "mvx", "mvy", "i16_mode", "chroma_mode", "cbp", "i4_mode", "cost", "nnz_mask", "mv8", "part", "transform8x8"]
 
 
-def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="yuv420p", deblock=0):
+def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="yuv420p", deblock=0, transform8x8=0):
     """seqs: list (one per slot) of lists of (y,u,v) frames"""
     S, T = len(seqs), len(seqs[0])
-    eng = b2.Engine(w, h, slots=S, fmt=fmt, ring=2, merange=R, qp=qp, subpel=subpel, intra_in_p=intra_in_p, deblock=deblock)
-    prm = oracle.Params(qp, R, subpel, intra_in_p, deblock)
+    eng = b2.Engine(w, h, slots=S, fmt=fmt, ring=2, merange=R, qp=qp, subpel=subpel, intra_in_p=intra_in_p, deblock=deblock,
+                    transform8x8=transform8x8)
+    prm = oracle.Params(qp, R, subpel, intra_in_p, deblock, transform8x8)
+    stats = {"t8": 0, "coded4": 0}
     prev = [None] * S; prev_mv = [None] * S
     for t in range(T):
         for s in range(S):
@@ -41,9 +43,12 @@ def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="
             ry, ru, rv = eng.recon(s)
             assert np.array_equal(ry, rec.y), f"recon Y t={t} s={s}"
             assert np.array_equal(ru, rec.u) and np.array_equal(rv, rec.v), f"recon UV t={t} s={s}"
+            stats["t8"] += int(info_o["transform8x8"].sum())
+            stats["coded4"] += int(((info_o["mb_type"] == 0) & (info_o["transform8x8"] == 0) & ((info_o["cbp"] & 15) != 0)).sum())
             prev[s] = rec
             prev_mv[s] = np.zeros(info_o.size, oracle.MV); prev_mv[s]["x"] = info_o["mvx"]; prev_mv[s]["y"] = info_o["mvy"]
     eng.close()
+    return stats
 
 
 @pytest.mark.parametrize("w,h,qp,R,cut", [(176, 144, 26, 16, None), (320, 240, 32, 32, 2), (208, 160, 18, 16, 1),
@@ -83,6 +88,17 @@ def test_engine_with_deblocking(oracle, b2, w, h, qp, R, cut):
     """K8 in-loop deblocking: reconstruction and everything downstream stay bit-exact"""
     seqs = [smooth_seq(w, h, 5, seed=qp + 1, cut=cut), smooth_seq(w, h, 5, seed=qp + 2)]
     run_and_compare(oracle, b2, seqs, w, h, qp, R, deblock=1)
+
+
+@pytest.mark.parametrize("w,h,qp,R,cut,deblock", [(176, 144, 26, 16, None, 1), (320, 240, 33, 32, 2, 1), (208, 160, 18, 16, 1, 0),
+                                                  (318, 242, 28, 16, 3, 1), (64, 48, 12, 16, 1, 0), (96, 80, 44, 16, 2, 1)])
+def test_engine_adaptive_8x8_transform(oracle, b2, w, h, qp, R, cut, deblock):
+    """row N1: SA8D/SATD transform-size decision, 8x8 DCT/quant/dequant/IDCT in K5, transform-aware edges in K8"""
+    seqs = [smooth_seq(w, h, 5, seed=qp + 3, cut=cut), smooth_seq(w, h, 5, seed=qp + 4)]
+    stats = run_and_compare(oracle, b2, seqs, w, h, qp, R, deblock=deblock, transform8x8=1)
+    assert stats["t8"] > 0
+    if qp < 40:
+        assert stats["coded4"] > 0
 
 
 def _to_fmt(fmt, y, u, v):

@@ -86,14 +86,14 @@ KERNEL_NAMES = ["K0 convert", "K6 border(cur)", "K1 full-pel SAD", "K2 sub-pel S
 class EngineCfg(C.Structure):
     _fields_ = [("device", C.c_int), ("width", C.c_int), ("height", C.c_int), ("slots", C.c_int), ("in_fmt", C.c_int),
                 ("in_ring", C.c_int), ("merange", C.c_int), ("qp", C.c_int), ("subpel", C.c_int), ("intra_in_p", C.c_int),
-                ("profile", C.c_int), ("streams", C.c_int), ("deblock", C.c_int)]
+                ("profile", C.c_int), ("streams", C.c_int), ("deblock", C.c_int), ("transform8x8", C.c_int)]
 
 
 class Engine:
     """One GPU's encode-stage engine: `slots` closed GOPs / streams advanced in lock-step."""
 
     def __init__(self, width, height, slots=1, fmt="yuv420p", ring=1, merange=16, qp=26, subpel=1, intra_in_p=1,
-                 device=0, profile=0, streams=0, deblock=0):
+                 device=0, profile=0, streams=0, deblock=0, transform8x8=0):
         require_gpu()
         L = lib()
         L.b2_engine_create.restype = C.c_void_p
@@ -122,7 +122,7 @@ class Engine:
         L.b2_engine_kernel_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long)]
         self.L = L
         self.cfg = EngineCfg(device, width, height, slots, FMT[fmt] if isinstance(fmt, str) else fmt, ring, merange, qp,
-                             subpel, intra_in_p, profile, streams, deblock)
+                             subpel, intra_in_p, profile, streams, deblock, transform8x8)
         self.h = L.b2_engine_create(C.byref(self.cfg))
         if not self.h:
             raise RuntimeError("b2_engine_create failed")

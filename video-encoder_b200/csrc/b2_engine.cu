@@ -370,7 +370,7 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
         KScope k(e, st, 5);
         if (b2_launch_decide_inter(cur, ref, rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, ns, is_p, do_intra,
                                    c.qp, e->d_mvq + om, e->d_cost_inter + om, e->d_c16 + om, e->d_c4 + om, info, coef,
-                                   e->d_prev_mv + om, e->d_pred + om * 256, st))
+                                   e->d_prev_mv + om, e->d_pred + om * 256, c.transform8x8, st))
             return -1;
     }
     if (do_intra) {

@@ -130,6 +130,63 @@ __device__ __forceinline__ uint32_t satd4x4(const int d[16])
     return s >> 1;
 }
 
+// ---- 8x8 transform path (High profile) -----------------------------------------------
+// normAdjust8x8 position classes [y&3][x&3] (8.5.9), quantiser / scaling constants per class
+__device__ __constant__ uint8_t c_cls8[16] = {0, 3, 4, 3, 3, 1, 5, 1, 4, 5, 2, 5, 3, 1, 5, 1};
+__device__ __constant__ uint16_t c_quant8_mf[6][6] = {
+    {13107, 11428, 20972, 12222, 16777, 15481}, {11916, 10826, 19174, 11058, 14980, 14290},
+    {10082, 8943, 15978, 9675, 12710, 11985},   {9362, 8228, 14913, 8931, 11984, 11259},
+    {8192, 7346, 13159, 7740, 10486, 9777},     {7282, 6428, 11570, 6830, 9118, 8640}};
+__device__ __constant__ uint8_t c_dequant8_v[6][6] = {{20, 18, 32, 19, 25, 24}, {22, 19, 35, 21, 28, 26}, {26, 23, 42, 24, 33, 31},
+                                                      {28, 25, 45, 26, 35, 33}, {32, 28, 51, 30, 40, 38}, {36, 32, 58, 34, 46, 43}};
+// 8x8 frame zig-zag (Figure 8-8): scan position -> raster index y*8+x
+__device__ __constant__ uint8_t c_zigzag8[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                                 41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                                 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// forward 8-point butterflies (encoder side; x264's dct8 form, frozen in oracle/b2o_transform8.c)
+__device__ __forceinline__ void fdct8_1d(const int s[8], int d[8])
+{
+    const int s07 = s[0] + s[7], s16 = s[1] + s[6], s25 = s[2] + s[5], s34 = s[3] + s[4];
+    const int a0 = s07 + s34, a1 = s16 + s25, a2 = s07 - s34, a3 = s16 - s25;
+    const int d07 = s[0] - s[7], d16 = s[1] - s[6], d25 = s[2] - s[5], d34 = s[3] - s[4];
+    const int a4 = d16 + d25 + (d07 + (d07 >> 1));
+    const int a5 = d07 - d34 - (d25 + (d25 >> 1));
+    const int a6 = d07 + d34 - (d16 + (d16 >> 1));
+    const int a7 = d16 - d25 + (d34 + (d34 >> 1));
+    d[0] = a0 + a1; d[1] = a4 + (a7 >> 2); d[2] = a2 + (a3 >> 1); d[3] = a5 + (a6 >> 2);
+    d[4] = a0 - a1; d[5] = a6 - (a5 >> 2); d[6] = (a2 >> 1) - a3; d[7] = (a4 >> 2) - a7;
+}
+// normative inverse 8-point butterflies (8.5.13)
+__device__ __forceinline__ void idct8_1d(const int d[8], int o[8])
+{
+    const int a0 = d[0] + d[4], a2 = d[0] - d[4], a4 = (d[2] >> 1) - d[6], a6 = d[2] + (d[6] >> 1);
+    const int b0 = a0 + a6, b2 = a2 + a4, b4 = a2 - a4, b6 = a0 - a6;
+    const int a1 = -d[3] + d[5] - d[7] - (d[7] >> 1);
+    const int a3 = d[1] + d[7] - d[3] - (d[3] >> 1);
+    const int a5 = -d[1] + d[7] + d[5] + (d[5] >> 1);
+    const int a7 = d[3] + d[5] + d[1] + (d[1] >> 1);
+    const int b1 = a1 + (a7 >> 2), b3 = a3 + (a5 >> 2), b5 = (a3 >> 2) - a5, b7 = a7 - (a1 >> 2);
+    o[0] = b0 + b7; o[1] = b2 + b5; o[2] = b4 + b3; o[3] = b6 + b1;
+    o[4] = b6 - b1; o[5] = b4 - b3; o[6] = b2 - b5; o[7] = b0 - b7;
+}
+// 2-D 4x4 Hadamard of a difference block, unnormalised (the SATD is (sum |t|) >> 1)
+__device__ __forceinline__ void hadamard4x4(const int d[16], int t[16])
+{
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        int s01 = d[y * 4 + 0] + d[y * 4 + 1], d01 = d[y * 4 + 0] - d[y * 4 + 1];
+        int s23 = d[y * 4 + 2] + d[y * 4 + 3], d23 = d[y * 4 + 2] - d[y * 4 + 3];
+        t[y * 4 + 0] = s01 + s23; t[y * 4 + 1] = s01 - s23; t[y * 4 + 2] = d01 - d23; t[y * 4 + 3] = d01 + d23;
+    }
+#pragma unroll
+    for (int x = 0; x < 4; x++) {
+        int s01 = t[x] + t[4 + x], d01 = t[x] - t[4 + x];
+        int s23 = t[8 + x] + t[12 + x], d23 = t[8 + x] - t[12 + x];
+        t[x] = s01 + s23; t[4 + x] = s01 - s23; t[8 + x] = d01 - d23; t[12 + x] = d01 + d23;
+    }
+}
+
 // sign (+1/-1) of entry [v][u] of H4 = rows ++++ / ++-- / +--+ / +-+-
 __device__ __forceinline__ int h4_sign(int v, int u)
 {

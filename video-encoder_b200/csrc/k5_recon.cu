@@ -20,6 +20,122 @@ using namespace b2;
 // ---- K5: decision + inter reconstruction ---------------------------------------------------------
 constexpr int K5_WARPS = 4;
 
+// 8x8 transform of one inter macroblock (row N1): lanes 4q..4q+3 cooperate on 8x8 block q through a per-warp
+// 16x16 int tile in shared memory (column pass, row pass + quantiser, zig-zag gather, inverse rows, inverse columns).
+// ALL 32 lanes must call; lanes >= 16 only take part in the warp barriers and shuffles.  Returns this lane's nnz flag
+// (bit of nnz_mask: the k-th interleaved quarter of the 8x8 block, k = lane & 3).
+__device__ __forceinline__ int code_luma8x8_quad(int lane, int *sm, const int src[16], const int pred[16], int qp, int16_t *lev,
+                                                 uint8_t *rec, int rpitch)
+{
+    const bool act = lane < 16;
+    const int q = (lane >> 2) & 3, r = lane & 3, qx = (q & 1) * 8, qy = (q >> 1) * 8;
+    const int bx = blk_x(lane & 15) * 4, by = blk_y(lane & 15) * 4;
+    if (act) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) sm[(by + (i >> 2)) * 16 + bx + (i & 3)] = src[i] - pred[i];
+    }
+    __syncwarp();
+    if (act) {                                            // forward, columns first (x264's order)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            int a[8], o[8];
+            const int x = qx + 2 * r + j;
+#pragma unroll
+            for (int y = 0; y < 8; y++) a[y] = sm[(qy + y) * 16 + x];
+            fdct8_1d(a, o);
+#pragma unroll
+            for (int y = 0; y < 8; y++) sm[(qy + y) * 16 + x] = o[y];
+        }
+    }
+    __syncwarp();
+    int z[2][8];
+    const int qbits = 16 + qp / 6, f = ((1 << qbits) * 11) >> 6, sh = qp / 6, rem = qp % 6;
+    if (act) {                                            // rows, then the dead-zone quantiser on the two rows this lane owns
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            int a[8], o[8];
+            const int y = 2 * r + j;
+#pragma unroll
+            for (int x = 0; x < 8; x++) a[x] = sm[(qy + y) * 16 + qx + x];
+            fdct8_1d(a, o);
+#pragma unroll
+            for (int x = 0; x < 8; x++) {
+                const uint32_t mf = c_quant8_mf[rem][c_cls8[(y & 3) * 4 + (x & 3)]];
+                const int v = (int)(((uint32_t)abs(o[x]) * mf + (uint32_t)f) >> qbits);
+                z[j][x] = o[x] < 0 ? -v : v;
+            }
+        }
+    }
+    __syncwarp();
+    if (act) {
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+#pragma unroll
+            for (int x = 0; x < 8; x++) sm[(qy + 2 * r + j) * 16 + qx + x] = z[j][x];
+    }
+    __syncwarp();
+    int mask4 = 0;
+    if (act) {                                            // levels 16r..16r+15 of the 8x8 zig-zag scan -> blk[4q + r]
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const int idx = c_zigzag8[16 * r + i];
+            const int v = sm[(qy + (idx >> 3)) * 16 + qx + (idx & 7)];
+            if (v) mask4 |= 1 << (i & 3);
+            if (i & 1) pk[i >> 1] |= (uint32_t)(uint16_t)(int16_t)v << 16;
+            else pk[i >> 1] = (uint32_t)(uint16_t)(int16_t)v;
+        }
+        uint4 *d4 = (uint4 *)lev;
+        d4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        d4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+    mask4 |= __shfl_xor_sync(0xffffffffu, mask4, 1);
+    mask4 |= __shfl_xor_sync(0xffffffffu, mask4, 2);
+    __syncwarp();
+    if (act && mask4) {                                   // normative scaling + inverse rows (8.5.13)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            int a[8], o[8];
+            const int y = 2 * r + j;
+#pragma unroll
+            for (int x = 0; x < 8; x++) {
+                const int ls = 16 * c_dequant8_v[rem][c_cls8[(y & 3) * 4 + (x & 3)]];
+                a[x] = sh >= 6 ? (z[j][x] * ls) << (sh - 6) : (z[j][x] * ls + (1 << (5 - sh))) >> (6 - sh);
+            }
+            idct8_1d(a, o);
+#pragma unroll
+            for (int x = 0; x < 8; x++) sm[(qy + y) * 16 + qx + x] = o[x];
+        }
+    }
+    __syncwarp();
+    if (act && mask4) {                                   // inverse columns, (x + 32) >> 6
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            int a[8], o[8];
+            const int x = qx + 2 * r + j;
+#pragma unroll
+            for (int y = 0; y < 8; y++) a[y] = sm[(qy + y) * 16 + x];
+            idct8_1d(a, o);
+#pragma unroll
+            for (int y = 0; y < 8; y++) sm[(qy + y) * 16 + x] = (o[y] + 32) >> 6;
+        }
+    }
+    __syncwarp();
+    if (act) {
+        if (mask4) {
+            int res[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) res[i] = sm[(by + (i >> 2)) * 16 + bx + (i & 3)];
+            store_rec4x4(rec, rpitch, pred, res);
+        } else {
+            store_rec4x4(rec, rpitch, pred, nullptr);
+        }
+    }
+    __syncwarp();
+    return act ? (mask4 >> r) & 1 : 0;
+}
+
+template <bool T8>
 __global__ void __launch_bounds__(K5_WARPS * 32)
 k5_decide_inter_kernel(FramePlanes fp, int mbw, int mbh, int nmb_total, int is_p, int do_intra, int qp,
                        const b2_mv_t *__restrict__ mvq, const uint32_t *__restrict__ cost_inter,
@@ -51,15 +167,48 @@ k5_decide_inter_kernel(FramePlanes fp, int mbw, int mbh, int nmb_total, int is_p
 
     b2_mbcoef_t *cf = &coef[mbi];
     int flags = 0;
+    int src[16], pred[16];
+    const int bx = blk_x(lane & 15) * 4, by = blk_y(lane & 15) * 4;
+    const size_t offy = (size_t)(B2_PAD + mby * 16 + by) * fp.pitch + B2_PAD + mbx * 16 + bx;
     if (lane < 16) {
-        const QParams q = make_qparams(qp, false);
-        const int bx = blk_x(lane) * 4, by = blk_y(lane) * 4;
-        const size_t off = (size_t)(B2_PAD + mby * 16 + by) * fp.pitch + B2_PAD + mbx * 16 + bx;
-        int src[16], pred[16];
-        load_src4x4(fp.cur[0] + frame * fp.stride_y + off, fp.pitch, src);
+        load_src4x4(fp.cur[0] + frame * fp.stride_y + offy, fp.pitch, src);
         // motion-compensated prediction of the chosen MV, produced by K2 from its half-sample planes
         load_src4x4(pred_y + (size_t)mbi * 256 + by * 16 + bx, 16, pred);
-        flags = code_luma4x4(src, pred, q, cf->blk[lane], fp.rec[0] + frame * fp.stride_y + off, fp.pitch) ? 1 : 0;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) src[i] = pred[i] = 0;
+    }
+    bool use8 = false;
+    if (T8) {
+        // transform size like x264's non-RD analysis: 8x8 iff SA8D(16x16) < SATD(16x16) of the prediction error.
+        // The 8x8 Hadamard of a quadrant = butterflies over the 4x4 Hadamards of its four sub-blocks (lanes 4q..4q+3).
+        int d[16], t[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) d[i] = src[i] - pred[i];
+        hadamard4x4(d, t);
+        uint32_t s4 = 0, s8 = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) s4 += abs(t[i]);
+        s4 >>= 1;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            int o = __shfl_xor_sync(0xffffffffu, t[i], 1);
+            int u = (lane & 1) ? o - t[i] : t[i] + o;
+            o = __shfl_xor_sync(0xffffffffu, u, 2);
+            u = (lane & 2) ? o - u : u + o;
+            s8 += abs(u);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s4 += __shfl_xor_sync(0xffffffffu, s4, o); s8 += __shfl_xor_sync(0xffffffffu, s8, o); }
+        use8 = ((s8 + 2) >> 2) < s4;
+    }
+    if (T8 && use8) {
+        __shared__ int s_t8[K5_WARPS][256];
+        flags = code_luma8x8_quad(lane, s_t8[threadIdx.x >> 5], src, pred, qp, cf->blk[lane & 15], fp.rec[0] + frame * fp.stride_y + offy,
+                                  fp.pitch);
+    } else if (lane < 16) {
+        const QParams q = make_qparams(qp, false);
+        flags = code_luma4x4(src, pred, q, cf->blk[lane], fp.rec[0] + frame * fp.stride_y + offy, fp.pitch) ? 1 : 0;
     }
     {
         const bool act = lane >= 16 && lane < 24;
@@ -68,7 +217,6 @@ k5_decide_inter_kernel(FramePlanes fp, int mbw, int mbh, int nmb_total, int is_p
         const QParams q = make_qparams(qpc, false);
         const int cbx = (k & 1) * 4, cby = (k >> 1) * 4;
         const size_t off = (size_t)(B2_PADC + mby * 8 + cby) * fp.pitchc + B2_PADC + mbx * 8 + cbx;
-        int src[16], pred[16];
         if (act) {
             load_src4x4(fp.cur[1 + pl] + frame * fp.stride_c + off, fp.pitchc, src);
             const uint8_t *rp = fp.ref[1 + pl] + frame * fp.stride_c + off + (ptrdiff_t)(mv.y >> 3) * fp.pitchc + (mv.x >> 3);
@@ -97,6 +245,8 @@ k5_decide_inter_kernel(FramePlanes fp, int mbw, int mbh, int nmb_total, int is_p
     if (lane == 0) {
         info[mbi].cbp = (uint8_t)cbp_from_mask(B2_MB_P16x16, mask);
         info[mbi].nnz_mask = mask;
+        // transform_size_8x8_flag is only sent with coded luma (7.3.5): inferred 0 otherwise
+        if (T8) info[mbi].transform8x8 = (uint8_t)(use8 && (mask & 0xffffu));
     }
 }
 
@@ -106,14 +256,18 @@ int b2_launch_decide_inter(const uint8_t *const cur[3], const uint8_t *const ref
                            int pitchc, size_t stride_y, size_t stride_c, int mbw, int mbh, int nframes, int is_p,
                            int do_intra, int qp, const b2_mv_t *d_mvq, const uint32_t *d_cost_inter, const uint32_t *d_c16,
                            const uint32_t *d_c4, b2_mbinfo_t *d_info, b2_mbcoef_t *d_coef, b2_mv_t *d_prev_mv,
-                           const uint8_t *d_pred_y, cudaStream_t st)
+                           const uint8_t *d_pred_y, int transform8x8, cudaStream_t st)
 {
     FramePlanes fp;
     for (int i = 0; i < 3; i++) { fp.cur[i] = cur[i]; fp.ref[i] = ref ? ref[i] : nullptr; fp.rec[i] = rec[i]; }
     fp.pitch = pitch; fp.pitchc = pitchc; fp.stride_y = stride_y; fp.stride_c = stride_c;
     const int nmb = mbw * mbh * nframes;
-    k5_decide_inter_kernel<<<(nmb + K5_WARPS - 1) / K5_WARPS, K5_WARPS * 32, 0, st>>>(
-        fp, mbw, mbh, nmb, is_p, do_intra, qp, d_mvq, d_cost_inter, d_c16, d_c4, d_info, d_coef, d_prev_mv, d_pred_y);
+    if (transform8x8)
+        k5_decide_inter_kernel<true><<<(nmb + K5_WARPS - 1) / K5_WARPS, K5_WARPS * 32, 0, st>>>(
+            fp, mbw, mbh, nmb, is_p, do_intra, qp, d_mvq, d_cost_inter, d_c16, d_c4, d_info, d_coef, d_prev_mv, d_pred_y);
+    else
+        k5_decide_inter_kernel<false><<<(nmb + K5_WARPS - 1) / K5_WARPS, K5_WARPS * 32, 0, st>>>(
+            fp, mbw, mbh, nmb, is_p, do_intra, qp, d_mvq, d_cost_inter, d_c16, d_c4, d_info, d_coef, d_prev_mv, d_pred_y);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -98,13 +98,20 @@ __device__ __forceinline__ void filter_line(uint8_t *pix, int step, int bs, cons
 
 __device__ __forceinline__ int zidx(int x, int y) { return (x & 1) | ((y & 1) << 1) | ((x >> 1) << 2) | ((y >> 1) << 3); }
 
-// boundary strength (8.7.2.1) between 4x4 block (pbx,pby) of MB p and block (qbx,qby) of MB q
-__device__ __forceinline__ int bs_of(uint32_t ptype, int pmvx, int pmvy, uint32_t pnnz, int pbx, int pby,
-                                     uint32_t qtype, int qmvx, int qmvy, uint32_t qnnz, int qbx, int qby, bool mb_edge)
+// does the transform block containing 4x4 block (bx,by) hold non-zero coefficients?  With the 8x8 transform that is the
+// whole 8x8 block (nnz_mask bits 4q..4q+3 = its interleaved quarters)
+__device__ __forceinline__ bool blk_coded(const b2_mbinfo_t *m, int bx, int by)
 {
-    if (ptype != B2_MB_P16x16 || qtype != B2_MB_P16x16) return mb_edge ? 4 : 3;
-    if (((pnnz >> zidx(pbx, pby)) & 1u) || ((qnnz >> zidx(qbx, qby)) & 1u)) return 2;
-    if (abs(pmvx - qmvx) >= 4 || abs(pmvy - qmvy) >= 4) return 1;
+    if (m->transform8x8) return ((m->nnz_mask >> (4 * ((bx >> 1) | ((by >> 1) << 1)))) & 15u) != 0;
+    return (m->nnz_mask >> zidx(bx, by)) & 1u;
+}
+
+// boundary strength (8.7.2.1) between 4x4 block (pbx,pby) of MB p and block (qbx,qby) of MB q
+__device__ __forceinline__ int bs_of(const b2_mbinfo_t *mp, int pbx, int pby, const b2_mbinfo_t *mq, int qbx, int qby, bool mb_edge)
+{
+    if (mp->mb_type != B2_MB_P16x16 || mq->mb_type != B2_MB_P16x16) return mb_edge ? 4 : 3;
+    if (blk_coded(mp, pbx, pby) || blk_coded(mq, qbx, qby)) return 2;
+    if (abs(mp->mvx - mq->mvx) >= 4 || abs(mp->mvy - mq->mvy) >= 4) return 1;
     return 0;
 }
 
@@ -125,14 +132,14 @@ __device__ void k8_mb_task(int lane, K8Warp &ws, uint8_t *const rec[3], int pitc
     // ---- boundary strengths: lanes 0-15 vertical edges, 16-31 horizontal edges; lane -> (edge e, segment k) ----
     {
         const int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3;
-        const bool edge_ok = !(e == 0 && (dir == 0 ? mbx == 0 : mby == 0));
+        // picture border; with the 8x8 transform only the 8-pel edges are transform-block edges (8.7)
+        const bool edge_ok = !(e == 0 && (dir == 0 ? mbx == 0 : mby == 0)) && !((e & 1) && mi->transform8x8);
         int bs = 0;
         if (edge_ok) {
             const b2_mbinfo_t *mp = e == 0 ? (dir == 0 ? mi - 1 : mi - mbw) : mi;
             const int pbx = dir == 0 ? (e == 0 ? 3 : e - 1) : k, pby = dir == 0 ? k : (e == 0 ? 3 : e - 1);
             const int qbx = dir == 0 ? e : k, qby = dir == 0 ? k : e;
-            bs = bs_of(mp->mb_type, mp->mvx, mp->mvy, mp->nnz_mask, pbx, pby, mi->mb_type, mi->mvx, mi->mvy, mi->nnz_mask, qbx,
-                       qby, e == 0);
+            bs = bs_of(mp, pbx, pby, mi, qbx, qby, e == 0);
         }
         ws.bs[dir][e][k] = (int8_t)bs;
     }

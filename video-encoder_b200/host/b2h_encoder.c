@@ -149,6 +149,7 @@ b2_t *b2_encoder_open(b2_param_t *p)
     cfg.device = p->i_device; cfg.width = p->i_width; cfg.height = p->i_height; cfg.slots = h->S;
     cfg.in_fmt = p->i_csp_in; cfg.in_ring = h->S == 1 ? 1 : h->L; cfg.merange = p->i_merange ? p->i_merange : 16; cfg.qp = h->qp;
     cfg.subpel = p->b_subpel; cfg.intra_in_p = p->b_intra_in_p; cfg.profile = 0; cfg.deblock = p->b_deblocking_filter;
+    cfg.transform8x8 = p->b_transform_8x8 != 0;
     h->eng = b2_engine_create(&cfg);
     if (!h->eng) { free(h); return NULL; }
     int w16, h16;
