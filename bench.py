@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--deblock", type=int, default=0, help="1: also run the in-loop deblocking filter K8 (row N2, outside the named path)")
+    ap.add_argument("--pack-levels", type=int, default=1, help="1: levels leave the GPU packed (K9: only blocks with a non-zero level); "
+                    "0: dense 832 B/MB array")
     ap.add_argument("--transform8x8", type=int, default=0, help="1: adaptive 8x8 transform for inter MBs (row N1, outside the named path)")
     args = ap.parse_args()
     select_workload(args.workload)
@@ -228,6 +230,7 @@ def main():
     import b2enc
     import b2oracle
     b2enc.require_gpu()
+    numa_cpus = b2enc.bind_to_gpu_numa(local)                  # pinned staging next to the GPU's PCIe root
 
     def barrier():
         if dist is not None:
@@ -244,7 +247,8 @@ def main():
         return float(t.item())
 
     eng = b2enc.Engine(W, H, slots=SLOTS, fmt="yuv420p", ring=RING, merange=MERANGE, qp=QP, subpel=1, intra_in_p=1,
-                       device=local, profile=0, streams=STREAMS, deblock=args.deblock, transform8x8=args.transform8x8)
+                       device=local, profile=0, streams=STREAMS, deblock=args.deblock, transform8x8=args.transform8x8,
+                       pack_levels=args.pack_levels)
     fill_inputs(eng, b2oracle, rank)
     for r in range(RING):
         eng.h2d(ring=r)
@@ -293,12 +297,14 @@ def main():
     for _ in range(2):                                             # warm the copy paths
         issue(step, True); step += 1
     eng.sync()
+    packed0 = eng.packed_bytes_total() if args.pack_levels else 0
     barrier()
     t0 = time.perf_counter()
     for _ in range(n_e2e):
         issue(step, True); step += 1
     eng.sync()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    packed_per_step = (eng.packed_bytes_total() - packed0) / n_e2e if args.pack_levels else 0
     barrier()
     clk = clocks.stop(mark)
     e2e = world * SLOTS * n_e2e / e2e_s
@@ -308,7 +314,8 @@ def main():
     if rank == 0:
         eng.close()
         eng1 = b2enc.Engine(W, H, slots=SLOTS, fmt="yuv420p", ring=2, merange=MERANGE, qp=QP, subpel=1, intra_in_p=1,
-                            device=local, profile=1, streams=1, deblock=args.deblock, transform8x8=args.transform8x8)
+                            device=local, profile=1, streams=1, deblock=args.deblock, transform8x8=args.transform8x8,
+                            pack_levels=args.pack_levels)
         fill_inputs(eng1, b2oracle, rank)
         eng1.h2d(ring=0); eng1.h2d(ring=1)
         eng1.encode(b2enc.FRAME_I, ring=0)
@@ -337,10 +344,12 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_step": SLOTS * world, "gop": GOP, "input_ring_frames": RING,
                        "l2": "no flush needed: per-step working set (cur+ref+recon planes of %d frames ~ %d MB + raw ring) exceeds the 126 MB L2"
                              % (SLOTS, int(SLOTS * 3 * 1.5 * w16 * h16 / 1e6)),
-                       "stream_groups": NG, "gop_phase_per_group": phase, "deblocking_filter": bool(args.deblock), "transform8x8": bool(args.transform8x8),
+                       "host_cpus_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None, "stream_groups": NG, "gop_phase_per_group": phase, "deblocking_filter": bool(args.deblock), "transform8x8": bool(args.transform8x8),
                        "parallelism": "closed-GOP sharding, %d GPUs x %d GOPs, no collective" % (world, SLOTS)},
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(SLOTS * in_bytes),
-                    "d2h_bytes_per_step": int(SLOTS * mbs * (48 + 832)), "api": "b2_engine_h2d/encode/d2h (include/b2enc_engine.h), pinned host buffers",
+                    "d2h_bytes_per_step": int(SLOTS * mbs * 48 + packed_per_step) if args.pack_levels else int(SLOTS * mbs * (48 + 832)),
+                    "d2h_note": ("per-MB decisions (48 B) + packed levels (K9: blocks with a non-zero level only; mean of this rank over the timed steps)"
+                                 if args.pack_levels else "per-MB decisions (48 B) + dense levels (832 B)"), "api": "b2_engine_h2d/encode/d2h (include/b2enc_engine.h), pinned host buffers",
                     "timing": "host wall clock around %d pipelined steps, synchronised on both sides" % n_e2e},
             "gpu_launches": int(launches),
             "clocks": clk,

@@ -35,6 +35,8 @@ typedef struct {
                        /* run on separate CUDA streams so that their kernels overlap       */
     int deblock;       /* 1: in-loop deblocking filter (K8) on every reconstructed frame    */
     int transform8x8;  /* 1: adaptive 8x8 transform for inter macroblocks (SA8D < SATD), row N1 */
+    int pack_levels;   /* 1: levels leave the GPU packed (only blocks with a non-zero level, K9):   */
+                       /* b2_engine_packed* replace b2_engine_coef*, which then return NULL         */
 } b2_engine_cfg_t;
 
 b2_engine_t *b2_engine_create(const b2_engine_cfg_t *cfg);      /* NULL on error */
@@ -63,7 +65,11 @@ int b2_engine_sync(b2_engine_t *e);
 /* host views of the results fetched by the last b2_engine_d2h (valid until the next but one d2h) */
 const b2_mbinfo_t *b2_engine_info(b2_engine_t *e, int slot);
 const b2_mbcoef_t *b2_engine_coef(b2_engine_t *e, int slot);
-size_t b2_engine_result_bytes(const b2_engine_t *e);           /* D2H bytes per slot per frame */
+size_t b2_engine_result_bytes(const b2_engine_t *e);           /* fixed D2H bytes per slot per frame (pack_levels: + the packed stream) */
+/* cfg.pack_levels: the slot's level stream (layout: b2enc_types.h, b2_coef_present) and its size in bytes */
+const uint8_t *b2_engine_packed(b2_engine_t *e, int slot, size_t *bytes);
+const uint8_t *b2_engine_packed_ticket(b2_engine_t *e, int ticket, int slot, size_t *bytes);
+long long b2_engine_packed_bytes_total(b2_engine_t *e);        /* packed bytes produced since creation (synchronises) */
 /* pipelined consumption: the ticket of the last b2_engine_d2h stays valid until the next but one b2_engine_d2h, so
  * the host can entropy-code step t while the GPU already runs step t+1 */
 int b2_engine_ticket(const b2_engine_t *e);
@@ -83,8 +89,8 @@ int b2_engine_timer_start(b2_engine_t *e);
 int b2_engine_timer_stop(b2_engine_t *e, float *ms);            /* synchronises */
 /* cfg.profile: accumulated device ms and launch count per kernel since the last reset.
  * which: 0 K0 convert, 1 K6 border(cur), 2 K1 full-pel, 3 K2 sub-pel, 4 K3 intra, 5 K5 decide+inter,
- *        6 K7 intra recon, 7 K6 border(recon), 8 K8 deblock */
-enum { B2_NKERNELS = 9 };
+ *        6 K7 intra recon, 7 K6 border(recon), 8 K8 deblock, 9 K9 pack levels */
+enum { B2_NKERNELS = 10 };
 int b2_engine_kernel_ms(b2_engine_t *e, int which, double *ms_total, long *launches);
 void b2_engine_profile_reset(b2_engine_t *e);
 long b2_engine_launch_count(const b2_engine_t *e);              /* kernels launched since creation */

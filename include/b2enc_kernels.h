@@ -17,6 +17,10 @@ extern "C" {
 /* number of CUDA devices visible; <= 0 when the CUDA path cannot run (no fallback exists) */
 int b2_device_count(void);
 
+/* PCI bus id ("0000:1b:00.0") of a CUDA device, so that a host process can pin itself to the GPU's NUMA node before
+ * allocating the pinned staging buffers */
+int b2_device_pci_bus_id(int device, char *out, int len);
+
 /* K1: exhaustive full-pel SAD search (replaces the full-pel ME inside x264_encoder_encode,
  * av_encode.c:970).  cur_y/ref_y: [nframes][h][w] unpadded luma, w and h multiples of 16.
  * pmv: [nframes][mbh*mbw] quarter-pel predictors or NULL.  Outputs per MB, raster order.

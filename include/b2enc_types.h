@@ -67,6 +67,21 @@ typedef struct {
 #define B2_COEF_BLOCKS 26
 typedef struct { int16_t blk[B2_COEF_BLOCKS][16]; } b2_mbcoef_t;   /* 832 bytes */
 
+/* Packed levels (engine option pack_levels): per frame, macroblocks in raster order, and for every macroblock the
+ * 32-byte blocks blk[b], b ascending, for which bit b of b2_coef_present() is set; absent blocks are all zero.
+ * Blocks of an 8x8-transformed quadrant travel together (64 contiguous levels). */
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline uint32_t b2_coef_present(const b2_mbinfo_t *m)
+{
+    uint32_t luma = m->nnz_mask & 0xffffu;
+    if (m->transform8x8)
+        for (int q = 0; q < 4; q++)
+            if ((luma >> (4 * q)) & 15u) luma |= 15u << (4 * q);
+    return luma | (m->nnz_mask & 0x01ff0000u) | ((m->nnz_mask & 0x06000000u) ? 1u << 25 : 0u);
+}
+
 #ifdef __cplusplus
 }
 #endif

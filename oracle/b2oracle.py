@@ -159,6 +159,18 @@ class Entropy:
         assert n > 0
         return self.buf[:n].tobytes()
 
+    def slice_packed(self, frame_type, frame_num, idr_id, info, packed):
+        """same slice from the packed level stream (b2h_write_slice_packed)"""
+        L = lib()
+        L.b2h_write_slice_packed.restype = C.c_size_t
+        L.b2h_write_slice_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                             C.c_void_p, C.c_size_t]
+        info = np.ascontiguousarray(info, MBINFO); packed = np.ascontiguousarray(packed, np.uint8)
+        n = L.b2h_write_slice_packed(self.e, C.addressof(self.seq), frame_type, frame_num, idr_id, _p(info), _p(packed), packed.size,
+                                     _p(self.buf), self.buf.size)
+        assert n > 0, "slice writer overflow"
+        return self.buf[:n].tobytes()
+
     def slice(self, frame_type, frame_num, idr_id, info, coef):
         info = np.ascontiguousarray(info, MBINFO); coef = np.ascontiguousarray(coef, MBCOEF)
         n = lib().b2h_write_slice(self.e, C.addressof(self.seq), frame_type, frame_num, idr_id, _p(info), _p(coef),

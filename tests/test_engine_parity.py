@@ -11,11 +11,11 @@ pytestmark = pytest.mark.gpu
 INFO_FIELDS = ["mb_type", "mvx", "mvy", "i16_mode", "chroma_mode", "cbp", "i4_mode", "cost", "nnz_mask", "mv8", "part", "transform8x8"]
 
 
-def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="yuv420p", deblock=0, transform8x8=0):
+def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="yuv420p", deblock=0, transform8x8=0, pack_levels=0):
     """seqs: list (one per slot) of lists of (y,u,v) frames"""
     S, T = len(seqs), len(seqs[0])
     eng = b2.Engine(w, h, slots=S, fmt=fmt, ring=2, merange=R, qp=qp, subpel=subpel, intra_in_p=intra_in_p, deblock=deblock,
-                    transform8x8=transform8x8)
+                    transform8x8=transform8x8, pack_levels=pack_levels)
     prm = oracle.Params(qp, R, subpel, intra_in_p, deblock, transform8x8)
     stats = {"t8": 0, "coded4": 0}
     prev = [None] * S; prev_mv = [None] * S
@@ -33,6 +33,8 @@ def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="
             cy, cu, cv = eng.cur(s)
             assert np.array_equal(cy, cur.y) and np.array_equal(cu, cur.u) and np.array_equal(cv, cur.v), f"cur planes t={t} s={s}"
             info_g, coef_g = eng.results(s)
+            if pack_levels:                            # K9's stream is exactly the host-side packing of the oracle's levels
+                assert np.array_equal(eng.packed(s), b2.pack_levels(info_o, coef_o)), f"packed stream t={t} s={s}"
             if ft == b2.FRAME_P:
                 mvf_o, cf_o = oracle.me_fullpel(cur, prev[s], R, prev_mv[s], oracle.lib().b2o_lambda(qp))
                 assert np.array_equal(eng.stage(s, 0), mvf_o), f"K1 mv t={t} s={s}"
@@ -99,6 +101,13 @@ def test_engine_adaptive_8x8_transform(oracle, b2, w, h, qp, R, cut, deblock):
     assert stats["t8"] > 0
     if qp < 40:
         assert stats["coded4"] > 0
+
+
+@pytest.mark.parametrize("w,h,qp,t8", [(176, 144, 26, 0), (320, 240, 34, 1), (64, 48, 12, 1), (318, 242, 45, 0)])
+def test_engine_packed_levels(oracle, b2, w, h, qp, t8):
+    """K9: only blocks with a non-zero level leave the GPU; stream == host packing of the oracle levels, several slots"""
+    seqs = [smooth_seq(w, h, 4, seed=qp + 5, cut=2), smooth_seq(w, h, 4, seed=qp + 6), [oracle.synth_frame(w, h, t, 2) for t in range(4)]]
+    run_and_compare(oracle, b2, seqs, w, h, qp, 16, deblock=1, transform8x8=t8, pack_levels=1)
 
 
 def _to_fmt(fmt, y, u, v):

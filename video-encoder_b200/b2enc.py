@@ -80,20 +80,77 @@ def vabsdiff4_peak(device=0, outer=256, reps=5):
 FMT = {"yuv420p": 0, "nv12": 1, "yuyv422": 2, "uyvy422": 3}
 FRAME_I, FRAME_P = 0, 1
 KERNEL_NAMES = ["K0 convert", "K6 border(cur)", "K1 full-pel SAD", "K2 sub-pel SATD", "K3 intra analyse",
-                "K5 decide+inter recon", "K7 intra recon", "K6 border(recon)", "K8 deblock"]
+                "K5 decide+inter recon", "K7 intra recon", "K6 border(recon)", "K8 deblock", "K9 pack levels"]
+
+
+def bind_to_gpu_numa(device):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI function), so that
+    the pinned staging buffers are allocated next to the PCIe root the copies go through.  Returns the cpu list or None."""
+    try:
+        L = lib()
+        buf = C.create_string_buffer(32)
+        L.b2_device_pci_bus_id.argtypes = [C.c_int, C.c_char_p, C.c_int]
+        if L.b2_device_pci_bus_id(device, buf, 32) != 0:
+            return None
+        bus = buf.value.decode().lower()
+        path = "/sys/bus/pci/devices/%s/local_cpulist" % bus
+        if not os.path.exists(path):
+            path = "/sys/bus/pci/devices/%s/local_cpulist" % bus[4:] if len(bus) > 12 else path
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
+def coef_present(info):
+    """vectorised b2_coef_present (include/b2enc_types.h): 26-bit block-presence mask per macroblock"""
+    m = info["nnz_mask"].astype(np.uint32)
+    luma = m & 0xffff
+    t8 = info["transform8x8"] != 0
+    for q in range(4):
+        quad = (luma >> (4 * q)) & 15
+        luma = np.where(t8 & (quad != 0), luma | (15 << (4 * q)), luma)
+    return (luma | (m & 0x01ff0000) | np.where((m & 0x06000000) != 0, 1 << 25, 0)).astype(np.uint32)
+
+
+def pack_levels(info, coef):
+    """test helper: the packed stream K9 produces, built on the host from a dense MBCOEF array"""
+    pm = coef_present(info)
+    bits = ((pm[:, None] >> np.arange(26, dtype=np.uint32)[None, :]) & 1).astype(bool)
+    return np.frombuffer(np.ascontiguousarray(coef["blk"][bits]).tobytes(), np.uint8)
+
+
+def unpack_levels(info, packed):
+    """test helper: dense MBCOEF array from the packed stream (harness only; the product's host stage reads it in place)"""
+    coef = np.zeros(info.size, MBCOEF)
+    pm = coef_present(info)
+    bits = ((pm[:, None] >> np.arange(26, dtype=np.uint32)[None, :]) & 1).astype(bool)
+    blocks = np.frombuffer(packed.tobytes(), "<i2").reshape(-1, 16)
+    assert blocks.shape[0] == int(bits.sum()), "packed stream size does not match the presence masks"
+    coef["blk"][bits] = blocks
+    return coef
 
 
 class EngineCfg(C.Structure):
     _fields_ = [("device", C.c_int), ("width", C.c_int), ("height", C.c_int), ("slots", C.c_int), ("in_fmt", C.c_int),
                 ("in_ring", C.c_int), ("merange", C.c_int), ("qp", C.c_int), ("subpel", C.c_int), ("intra_in_p", C.c_int),
-                ("profile", C.c_int), ("streams", C.c_int), ("deblock", C.c_int), ("transform8x8", C.c_int)]
+                ("profile", C.c_int), ("streams", C.c_int), ("deblock", C.c_int), ("transform8x8", C.c_int), ("pack_levels", C.c_int)]
 
 
 class Engine:
     """One GPU's encode-stage engine: `slots` closed GOPs / streams advanced in lock-step."""
 
     def __init__(self, width, height, slots=1, fmt="yuv420p", ring=1, merange=16, qp=26, subpel=1, intra_in_p=1,
-                 device=0, profile=0, streams=0, deblock=0, transform8x8=0):
+                 device=0, profile=0, streams=0, deblock=0, transform8x8=0, pack_levels=0):
         require_gpu()
         L = lib()
         L.b2_engine_create.restype = C.c_void_p
@@ -114,6 +171,8 @@ class Engine:
         L.b2_engine_encode_group.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.b2_engine_d2h_group.argtypes = [C.c_void_p, C.c_int]
         L.b2_engine_info.argtypes = [C.c_void_p, C.c_int]; L.b2_engine_coef.argtypes = [C.c_void_p, C.c_int]
+        L.b2_engine_packed.restype = C.c_void_p; L.b2_engine_packed.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]
+        L.b2_engine_packed_bytes_total.restype = C.c_longlong; L.b2_engine_packed_bytes_total.argtypes = [C.c_void_p]
         L.b2_engine_get_recon.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2_engine_get_cur.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2_engine_get_stage.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -122,7 +181,7 @@ class Engine:
         L.b2_engine_kernel_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long)]
         self.L = L
         self.cfg = EngineCfg(device, width, height, slots, FMT[fmt] if isinstance(fmt, str) else fmt, ring, merange, qp,
-                             subpel, intra_in_p, profile, streams, deblock, transform8x8)
+                             subpel, intra_in_p, profile, streams, deblock, transform8x8, pack_levels)
         self.h = L.b2_engine_create(C.byref(self.cfg))
         if not self.h:
             raise RuntimeError("b2_engine_create failed")
@@ -187,11 +246,25 @@ class Engine:
         self._ck(self.L.b2_engine_sync(self.h), "sync")
 
     def results(self, slot):
-        """(info, coef) numpy views of the last fetched results of `slot`"""
-        pi = self.L.b2_engine_info(self.h, slot); pc = self.L.b2_engine_coef(self.h, slot)
+        """(info, coef) numpy views of the last fetched results of `slot` (pack_levels: coef is unpacked from the stream)"""
+        pi = self.L.b2_engine_info(self.h, slot)
         info = np.frombuffer((C.c_uint8 * (self.nmb * MBINFO.itemsize)).from_address(pi), MBINFO)
+        if self.cfg.pack_levels:
+            return info, unpack_levels(info, self.packed(slot))
+        pc = self.L.b2_engine_coef(self.h, slot)
         coef = np.frombuffer((C.c_uint8 * (self.nmb * 832)).from_address(pc), MBCOEF)
         return info, coef
+
+    def packed(self, slot):
+        """the slot's packed level stream (cfg.pack_levels) as a uint8 array"""
+        n = C.c_size_t(0)
+        p = self.L.b2_engine_packed(self.h, slot, C.byref(n))
+        if not p:
+            raise RuntimeError("engine was not created with pack_levels")
+        return np.frombuffer((C.c_uint8 * n.value).from_address(p), np.uint8).copy() if n.value else np.zeros(0, np.uint8)
+
+    def packed_bytes_total(self):
+        return int(self.L.b2_engine_packed_bytes_total(self.h))
 
     def _planes(self, fn, slot):
         y = np.zeros((self.h16, self.w16), np.uint8)

@@ -9,7 +9,8 @@
 //   cur Y/U/V           [S][rows][pitch] / [S][rowsc][pitchc]   64/32-px replicated border
 //   recon Y/U/V  x2     same shape; ping-pong reference / reconstruction
 //   per-MB scratch      mv_full, cost_full, mv_qpel, cost_inter, cost_i16, cost_i4, prev_mv  [S][nmb]
-//   results x2          b2_mbinfo_t [S][nmb] (32 B) + b2_mbcoef_t [S][nmb] (832 B), ping-pong
+//   results x2          b2_mbinfo_t [S][nmb] (48 B) + b2_mbcoef_t [S][nmb] (832 B), ping-pong
+//   packed levels x2    [S][nmb*832] worst case, only the used prefix is copied out (cfg.pack_levels, K9)
 #include <string.h>
 #include <vector>
 #include "b2_common.cuh"
@@ -55,6 +56,11 @@ struct b2_engine {
     uint8_t *d_pred = nullptr;             // [S][nmb][256] motion-compensated luma prediction (K2 -> K5)
     b2_mbinfo_t *d_info[2] = {}, *h_info[2] = {};
     b2_mbcoef_t *d_coef[2] = {}, *h_coef[2] = {};
+    // cfg.pack_levels: packed level streams [S][pack_stride] per result set (device + pinned host), blocks used per slot
+    uint8_t *d_pack[2] = {}, *h_pack[2] = {};
+    uint32_t *d_pack_n[2] = {}, *h_pack_n[2] = {};
+    unsigned long long *d_pack_cum = nullptr;
+    size_t pack_stride = 0;
     std::vector<Group> groups;
     // result tickets: which result set each group copied out in one of the last two b2_engine_d2h calls
     struct Ticket { std::vector<int> set; } ticket[2];
@@ -117,7 +123,20 @@ static int engine_alloc(b2_engine *e)
         ENG_OK(cudaMalloc(&e->d_info[s], n * sizeof(b2_mbinfo_t)));
         ENG_OK(cudaMalloc(&e->d_coef[s], n * sizeof(b2_mbcoef_t)));
         ENG_OK(cudaHostAlloc(&e->h_info[s], n * sizeof(b2_mbinfo_t), cudaHostAllocDefault));
-        ENG_OK(cudaHostAlloc(&e->h_coef[s], n * sizeof(b2_mbcoef_t), cudaHostAllocDefault));
+        if (c.pack_levels) {
+            e->pack_stride = (size_t)e->nmb * sizeof(b2_mbcoef_t);
+            ENG_OK(cudaMalloc(&e->d_pack[s], e->pack_stride * S));
+            ENG_OK(cudaHostAlloc(&e->h_pack[s], e->pack_stride * S, cudaHostAllocDefault));     // UVA: the device writes it directly
+            ENG_OK(cudaMalloc(&e->d_pack_n[s], S * sizeof(uint32_t)));
+            ENG_OK(cudaHostAlloc(&e->h_pack_n[s], S * sizeof(uint32_t), cudaHostAllocDefault));
+            memset(e->h_pack_n[s], 0, S * sizeof(uint32_t));
+        } else {
+            ENG_OK(cudaHostAlloc(&e->h_coef[s], n * sizeof(b2_mbcoef_t), cudaHostAllocDefault));
+        }
+    }
+    if (c.pack_levels) {
+        ENG_OK(cudaMalloc(&e->d_pack_cum, sizeof(unsigned long long)));
+        ENG_OK(cudaMemset(e->d_pack_cum, 0, sizeof(unsigned long long)));
     }
     ENG_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     ENG_OK(cudaStreamCreateWithFlags(&e->st_in, cudaStreamNonBlocking));
@@ -190,7 +209,11 @@ extern "C" void b2_engine_destroy(b2_engine_t *e)
     for (int p = 0; p < 3; p++) { cudaFree(e->d_cur[p]); cudaFree(e->d_rec[0][p]); cudaFree(e->d_rec[1][p]); }
     cudaFree(e->d_mvf); cudaFree(e->d_mvq); cudaFree(e->d_prev_mv); cudaFree(e->d_cost_full); cudaFree(e->d_cost_inter);
     cudaFree(e->d_c16); cudaFree(e->d_c4); cudaFree(e->d_pred);
-    for (int s = 0; s < 2; s++) { cudaFree(e->d_info[s]); cudaFree(e->d_coef[s]); cudaFreeHost(e->h_info[s]); cudaFreeHost(e->h_coef[s]); }
+    for (int s = 0; s < 2; s++) {
+        cudaFree(e->d_info[s]); cudaFree(e->d_coef[s]); cudaFreeHost(e->h_info[s]); cudaFreeHost(e->h_coef[s]);
+        cudaFree(e->d_pack[s]); cudaFreeHost(e->h_pack[s]); cudaFree(e->d_pack_n[s]); cudaFreeHost(e->h_pack_n[s]);
+    }
+    cudaFree(e->d_pack_cum);
     for (auto &gr : e->groups) {
         for (int s = 0; s < 2; s++) { if (gr.ev_enc[s]) cudaEventDestroy(gr.ev_enc[s]); if (gr.ev_d2h[s]) cudaEventDestroy(gr.ev_d2h[s]); }
         if (gr.ev_join) cudaEventDestroy(gr.ev_join);
@@ -209,7 +232,10 @@ extern "C" void b2_engine_destroy(b2_engine_t *e)
 }
 
 extern "C" size_t b2_engine_input_bytes(const b2_engine_t *e) { return e->in_bytes; }
-extern "C" size_t b2_engine_result_bytes(const b2_engine_t *e) { return (size_t)e->nmb * (sizeof(b2_mbinfo_t) + sizeof(b2_mbcoef_t)); }
+extern "C" size_t b2_engine_result_bytes(const b2_engine_t *e)
+{
+    return (size_t)e->nmb * (sizeof(b2_mbinfo_t) + (e->cfg.pack_levels ? 0 : sizeof(b2_mbcoef_t)));      // + the packed stream when packing
+}
 extern "C" void b2_engine_geometry(const b2_engine_t *e, int *mbw, int *mbh, int *w16, int *h16)
 {
     if (mbw) *mbw = e->mbw;
@@ -388,6 +414,12 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
                                         e->w16, e->h16, ns, st))
             return -1;
     }
+    if (c.pack_levels) {
+        KScope k(e, st, 9);
+        if (b2_launch_pack_levels(info, coef, e->d_pack[set] + gr.slot0 * e->pack_stride, e->pack_stride, e->d_pack_n[set] + gr.slot0,
+                                  e->d_pack_cum, e->nmb, ns, st))
+            return -1;
+    }
     ENG_OK(cudaEventRecord(gr.ev_enc[set], st));
     gr.ref_idx ^= 1;
     gr.res_set = set;
@@ -420,7 +452,14 @@ static int d2h_group(b2_engine *e, Group &gr, int ns)
     const size_t om = (size_t)gr.slot0 * e->nmb, n = (size_t)e->nmb * ns;
     ENG_OK(cudaStreamWaitEvent(e->st_out, gr.ev_enc[set], 0));
     ENG_OK(cudaMemcpyAsync(e->h_info[set] + om, e->d_info[set] + om, n * sizeof(b2_mbinfo_t), cudaMemcpyDeviceToHost, e->st_out));
-    ENG_OK(cudaMemcpyAsync(e->h_coef[set] + om, e->d_coef[set] + om, n * sizeof(b2_mbcoef_t), cudaMemcpyDeviceToHost, e->st_out));
+    if (e->cfg.pack_levels) {
+        if (b2_launch_pack_copy_out(e->d_pack[set] + gr.slot0 * e->pack_stride, e->pack_stride, e->d_pack_n[set] + gr.slot0,
+                                    e->h_pack[set] + gr.slot0 * e->pack_stride, e->h_pack_n[set] + gr.slot0, ns, e->st_out))
+            return -1;
+        e->launches++;
+    } else {
+        ENG_OK(cudaMemcpyAsync(e->h_coef[set] + om, e->d_coef[set] + om, n * sizeof(b2_mbcoef_t), cudaMemcpyDeviceToHost, e->st_out));
+    }
     ENG_OK(cudaEventRecord(gr.ev_d2h[set], e->st_out));
     gr.d2h_used[set] = true;
     gr.host_set = set;
@@ -475,7 +514,7 @@ extern "C" const b2_mbinfo_t *b2_engine_info_ticket(b2_engine_t *e, int ticket, 
 }
 extern "C" const b2_mbcoef_t *b2_engine_coef_ticket(b2_engine_t *e, int ticket, int slot)
 {
-    if (ticket < 0 || ticket > 1) return nullptr;
+    if (ticket < 0 || ticket > 1 || e->cfg.pack_levels) return nullptr;
     for (size_t g = 0; g < e->groups.size(); g++)
         if (slot >= e->groups[g].slot0 && slot < e->groups[g].slot0 + e->groups[g].n && g < e->ticket[ticket].set.size() &&
             e->ticket[ticket].set[g] >= 0)
@@ -502,7 +541,35 @@ extern "C" const b2_mbinfo_t *b2_engine_info(b2_engine_t *e, int slot)
 extern "C" const b2_mbcoef_t *b2_engine_coef(b2_engine_t *e, int slot)
 {
     Group *gr = group_of(e, slot);
-    return gr ? e->h_coef[gr->host_set] + (size_t)slot * e->nmb : nullptr;
+    return gr && !e->cfg.pack_levels ? e->h_coef[gr->host_set] + (size_t)slot * e->nmb : nullptr;
+}
+// packed levels (cfg.pack_levels): stream of the slot's last fetched frame and its size in bytes
+extern "C" const uint8_t *b2_engine_packed(b2_engine_t *e, int slot, size_t *bytes)
+{
+    Group *gr = group_of(e, slot);
+    if (!gr || !e->cfg.pack_levels) return nullptr;
+    if (bytes) *bytes = (size_t)e->h_pack_n[gr->host_set][slot] * 32;
+    return e->h_pack[gr->host_set] + (size_t)slot * e->pack_stride;
+}
+extern "C" const uint8_t *b2_engine_packed_ticket(b2_engine_t *e, int ticket, int slot, size_t *bytes)
+{
+    if (ticket < 0 || ticket > 1 || !e->cfg.pack_levels) return nullptr;
+    for (size_t g = 0; g < e->groups.size(); g++)
+        if (slot >= e->groups[g].slot0 && slot < e->groups[g].slot0 + e->groups[g].n && g < e->ticket[ticket].set.size() &&
+            e->ticket[ticket].set[g] >= 0) {
+            const int set = e->ticket[ticket].set[g];
+            if (bytes) *bytes = (size_t)e->h_pack_n[set][slot] * 32;
+            return e->h_pack[set] + (size_t)slot * e->pack_stride;
+        }
+    return nullptr;
+}
+// bytes of packed levels produced since the engine was created (synchronises)
+extern "C" long long b2_engine_packed_bytes_total(b2_engine_t *e)
+{
+    if (!e->cfg.pack_levels || b2_engine_sync(e)) return -1;
+    unsigned long long v = 0;
+    if (cudaMemcpy(&v, e->d_pack_cum, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (long long)v;
 }
 
 static int get_planes(b2_engine *e, uint8_t *const src[3], int slot, uint8_t *y, uint8_t *u, uint8_t *v)

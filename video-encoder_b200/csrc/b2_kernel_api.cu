@@ -77,3 +77,12 @@ extern "C" int b2k_me_fullpel(const uint8_t *cur_y, const uint8_t *ref_y, int w,
     B2_CUDA_OK(cudaMemcpy(cost_out, d_cost.p, nmb * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
+
+// PCI bus id ("0000:1b:00.0") of a CUDA device: lets the host pin itself to the GPU's NUMA node before it allocates
+// the pinned staging buffers (bench.py / b2enc.bind_to_gpu_numa)
+extern "C" int b2_device_pci_bus_id(int device, char *out, int len)
+{
+    if (!out || len < 13) return -1;
+    if (cudaDeviceGetPCIBusId(out, len, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return 0;
+}

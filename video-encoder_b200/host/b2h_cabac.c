@@ -218,7 +218,7 @@ static void cabac_mb_type_intra(cabac_t *c, const b2_mbinfo_t *m, int is_p, int 
 
 /* ---- slice ---------------------------------------------------------------------------------------------------*/
 size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int frame_num, int idr_pic_id,
-                             const b2_mbinfo_t *info, const b2_mbcoef_t *coef, uint8_t *out, size_t cap)
+                             const b2_mbinfo_t *info, b2h_levels_t *lv, uint8_t *out, size_t cap)
 {
     bs_t bs, *b = &bs;
     cabac_t cb, *c = &cb;
@@ -234,7 +234,8 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
         for (int mbx = 0; mbx < mbw; mbx++) {
             const int mi = mby * mbw + mbx;
             const b2_mbinfo_t *m = &info[mi];
-            const b2_mbcoef_t *cf = &coef[mi];
+            const int16_t *cblk[B2_COEF_BLOCKS];
+            b2h_levels_mb(lv, m, mi, cblk);
             const int cbp_l = m->cbp & 15, cbp_c = m->cbp >> 4;
             const int intra = m->mb_type != B2_MB_P16x16;
             nb_t nb;
@@ -344,7 +345,7 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
             if (m->mb_type == B2_MB_I16x16) {
                 const int fa = nb.availA ? ((nb.fA & B2H_MBF_I16) ? ((nb.fA & B2H_MBF_DC_Y) != 0) : -1) : 0;
                 const int fb = nb.availB ? ((nb.fB & B2H_MBF_I16) ? ((nb.fB & B2H_MBF_DC_Y) != 0) : -1) : 0;
-                if (cabac_residual(c, 0, cf->blk[24], 16, cbf_term(nb.availA, fa, 1) + 2 * cbf_term(nb.availB, fb, 1))) flags |= B2H_MBF_DC_Y;
+                if (cabac_residual(c, 0, cblk[24], 16, cbf_term(nb.availA, fa, 1) + 2 * cbf_term(nb.availB, fb, 1))) flags |= B2H_MBF_DC_Y;
             }
             if (cbp_l) {
                 for (int k = 0; k < 16; k++) {
@@ -352,7 +353,7 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
                     const int x = mbx * 4 + blk_x[k], y = mby * 4 + blk_y[k];
                     if (t8) {
                         if (k & 3) continue;
-                        const int n = cabac_residual(c, 5, cf->blk[k], 64, -1);
+                        const int n = cabac_residual(c, 5, cblk[k], 64, -1);
                         const uint8_t v = (uint8_t)(n > 16 ? 16 : (n ? n : 1));        /* cbp bit set: coded_block_flag inferred 1 */
                         e->nnz_y[y * ys + x] = e->nnz_y[y * ys + x + 1] = e->nnz_y[(y + 1) * ys + x] = e->nnz_y[(y + 1) * ys + x + 1] = v;
                         continue;
@@ -361,9 +362,9 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
                     const int ta = cbf_term(x > 0, x > 0 ? e->nnz_y[y * ys + x - 1] : 0, intra);
                     const int tb = cbf_term(y > 0, y > 0 ? e->nnz_y[(y - 1) * ys + x] : 0, intra);
                     if (m->mb_type == B2_MB_I16x16)
-                        e->nnz_y[y * ys + x] = (uint8_t)cabac_residual(c, 1, cf->blk[k] + 1, 15, ta + 2 * tb);
+                        e->nnz_y[y * ys + x] = (uint8_t)cabac_residual(c, 1, cblk[k] + 1, 15, ta + 2 * tb);
                     else
-                        e->nnz_y[y * ys + x] = (uint8_t)cabac_residual(c, 2, cf->blk[k], 16, ta + 2 * tb);
+                        e->nnz_y[y * ys + x] = (uint8_t)cabac_residual(c, 2, cblk[k], 16, ta + 2 * tb);
                 }
             }
             if (cbp_c) {
@@ -371,7 +372,7 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
                     const int bit = p ? B2H_MBF_DC_V : B2H_MBF_DC_U;
                     const int fa = nb.availA ? ((nb.cbpA >> 4) ? ((nb.fA & bit) != 0) : -1) : 0;
                     const int fb = nb.availB ? ((nb.cbpB >> 4) ? ((nb.fB & bit) != 0) : -1) : 0;
-                    if (cabac_residual(c, 3, cf->blk[25] + 4 * p, 4, cbf_term(nb.availA, fa, intra) + 2 * cbf_term(nb.availB, fb, intra)))
+                    if (cabac_residual(c, 3, cblk[25] + 4 * p, 4, cbf_term(nb.availA, fa, intra) + 2 * cbf_term(nb.availB, fb, intra)))
                         flags |= bit;
                 }
                 if (cbp_c == 2)
@@ -380,7 +381,7 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
                             const int x = mbx * 2 + (k & 1), y = mby * 2 + (k >> 1);
                             const int ta = cbf_term(x > 0, x > 0 ? e->nnz_c[p][y * cs + x - 1] : 0, intra);
                             const int tb = cbf_term(y > 0, y > 0 ? e->nnz_c[p][(y - 1) * cs + x] : 0, intra);
-                            e->nnz_c[p][y * cs + x] = (uint8_t)cabac_residual(c, 4, cf->blk[16 + 4 * p + k] + 1, 15, ta + 2 * tb);
+                            e->nnz_c[p][y * cs + x] = (uint8_t)cabac_residual(c, 4, cblk[16 + 4 * p + k] + 1, 15, ta + 2 * tb);
                         }
             }
             e->mbf[mi] = (uint8_t)flags;

@@ -387,13 +387,32 @@ void b2h_slice_header(bs_t *b, const b2h_seq_t *s, int is_p, int frame_num, int 
 }
 
 /* ---- slice ---------------------------------------------------------------------------------------*/
+const int16_t b2h_zero_levels[64] = {0};
+
+static size_t write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int frame_num, int idr_pic_id,
+                          const b2_mbinfo_t *info, b2h_levels_t *lv, uint8_t *out, size_t cap);
+
 size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int frame_num, int idr_pic_id,
                        const b2_mbinfo_t *info, const b2_mbcoef_t *coef, uint8_t *out, size_t cap)
+{
+    b2h_levels_t lv = {coef, NULL, 0, 0};
+    return write_slice(e, s, frame_type, frame_num, idr_pic_id, info, &lv, out, cap);
+}
+
+size_t b2h_write_slice_packed(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int frame_num, int idr_pic_id,
+                              const b2_mbinfo_t *info, const uint8_t *packed, size_t packed_bytes, uint8_t *out, size_t cap)
+{
+    b2h_levels_t lv = {NULL, packed, 0, packed_bytes};
+    return write_slice(e, s, frame_type, frame_num, idr_pic_id, info, &lv, out, cap);
+}
+
+static size_t write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int frame_num, int idr_pic_id,
+                          const b2_mbinfo_t *info, b2h_levels_t *lv, uint8_t *out, size_t cap)
 {
     bs_t bs, *b = &bs;
     const int mbw = e->mbw, mbh = e->mbh, is_p = frame_type == B2_FRAME_P;
     const int ys = 4 * mbw, cs = 2 * mbw;
-    if (s->cabac) return b2h_write_slice_cabac(e, s, frame_type, frame_num, idr_pic_id, info, coef, out, cap);
+    if (s->cabac) return b2h_write_slice_cabac(e, s, frame_type, frame_num, idr_pic_id, info, lv, out, cap);
     bs_init(b, e->rbsp, e->rbsp_cap);
     b2h_slice_header(b, s, is_p, frame_num, idr_pic_id);
 
@@ -403,7 +422,8 @@ size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int
         for (int mbx = 0; mbx < mbw; mbx++) {
             const int mi = mby * mbw + mbx;
             const b2_mbinfo_t *m = &info[mi];
-            const b2_mbcoef_t *c = &coef[mi];
+            const int16_t *cblk[B2_COEF_BLOCKS];
+            b2h_levels_mb(lv, m, mi, cblk);
             const int cbp_l = m->cbp & 15, cbp_c = m->cbp >> 4;
             /* reset this MB's neighbour state; filled in below as blocks are coded */
             for (int r = 0; r < 4; r++) { memset(e->nnz_y + (mby * 4 + r) * ys + mbx * 4, 0, 4); memset(e->i4 + (mby * 4 + r) * ys + mbx * 4, 2, 4); }
@@ -456,11 +476,11 @@ size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int
 
             /* residual() */
             if (m->mb_type == B2_MB_I16x16) {
-                write_residual(b, c->blk[24], 16, pred_nc(e->nnz_y, ys, mbx * 4, mby * 4));
+                write_residual(b, cblk[24], 16, pred_nc(e->nnz_y, ys, mbx * 4, mby * 4));
                 if (cbp_l)
                     for (int k = 0; k < 16; k++) {
                         int x = mbx * 4 + blk_x[k], y = mby * 4 + blk_y[k];
-                        e->nnz_y[y * ys + x] = (uint8_t)write_residual(b, c->blk[k] + 1, 15, pred_nc(e->nnz_y, ys, x, y));
+                        e->nnz_y[y * ys + x] = (uint8_t)write_residual(b, cblk[k] + 1, 15, pred_nc(e->nnz_y, ys, x, y));
                     }
             } else if (m->transform8x8 && s->transform8x8) {
                 /* 8x8 transform with CAVLC (7.3.5.3.2): the 64 levels are split into four interleaved 4x4 blocks */
@@ -468,7 +488,7 @@ size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int
                     if (!(cbp_l & (1 << (k >> 2)))) continue;
                     int x = mbx * 4 + blk_x[k], y = mby * 4 + blk_y[k];
                     int16_t l4[16];
-                    const int16_t *l8 = c->blk[k & ~3];
+                    const int16_t *l8 = cblk[k & ~3];
                     for (int i = 0; i < 16; i++) l4[i] = l8[4 * i + (k & 3)];
                     e->nnz_y[y * ys + x] = (uint8_t)write_residual(b, l4, 16, pred_nc(e->nnz_y, ys, x, y));
                 }
@@ -476,18 +496,18 @@ size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int
                 for (int k = 0; k < 16; k++) {
                     if (!(cbp_l & (1 << (k >> 2)))) continue;
                     int x = mbx * 4 + blk_x[k], y = mby * 4 + blk_y[k];
-                    e->nnz_y[y * ys + x] = (uint8_t)write_residual(b, c->blk[k], 16, pred_nc(e->nnz_y, ys, x, y));
+                    e->nnz_y[y * ys + x] = (uint8_t)write_residual(b, cblk[k], 16, pred_nc(e->nnz_y, ys, x, y));
                 }
             }
             if (cbp_c) {
-                write_residual(b, c->blk[25], 4, -1);
-                write_residual(b, c->blk[25] + 4, 4, -1);
+                write_residual(b, cblk[25], 4, -1);
+                write_residual(b, cblk[25] + 4, 4, -1);
                 if (cbp_c == 2)
                     for (int p = 0; p < 2; p++)
                         for (int k = 0; k < 4; k++) {
                             int x = mbx * 2 + (k & 1), y = mby * 2 + (k >> 1);
                             e->nnz_c[p][y * cs + x] =
-                                (uint8_t)write_residual(b, c->blk[16 + 4 * p + k] + 1, 15, pred_nc(e->nnz_c[p], cs, x, y));
+                                (uint8_t)write_residual(b, cblk[16 + 4 * p + k] + 1, 15, pred_nc(e->nnz_c[p], cs, x, y));
                         }
             }
         }

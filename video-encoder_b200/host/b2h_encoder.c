@@ -150,6 +150,7 @@ b2_t *b2_encoder_open(b2_param_t *p)
     cfg.in_fmt = p->i_csp_in; cfg.in_ring = h->S == 1 ? 1 : h->L; cfg.merange = p->i_merange ? p->i_merange : 16; cfg.qp = h->qp;
     cfg.subpel = p->b_subpel; cfg.intra_in_p = p->b_intra_in_p; cfg.profile = 0; cfg.deblock = p->b_deblocking_filter;
     cfg.transform8x8 = p->b_transform_8x8 != 0;
+    cfg.pack_levels = 1;                              /* only blocks with non-zero levels cross PCIe (K9) */
     h->eng = b2_engine_create(&cfg);
     if (!h->eng) { free(h); return NULL; }
     int w16, h16;
@@ -232,10 +233,11 @@ static int finish_frame(b2_t *h, b2h_entropy_t *ent, uint8_t *s, int ticket, int
         }
     }
     const b2_mbinfo_t *info = ticket < 0 ? b2_engine_info(h->eng, slot) : b2_engine_info_ticket(h->eng, ticket, slot);
-    const b2_mbcoef_t *coef = ticket < 0 ? b2_engine_coef(h->eng, slot) : b2_engine_coef_ticket(h->eng, ticket, slot);
-    if (!info || !coef) return -1;
-    size_t n = b2h_write_slice(ent, &h->seq, is_idr ? B2_FRAME_I : B2_FRAME_P, t, (int)(gop_index & 0xffff), info, coef,
-                               s + pos + 4, h->scratch_cap - pos - 4);
+    size_t packed_bytes = 0;
+    const uint8_t *packed = ticket < 0 ? b2_engine_packed(h->eng, slot, &packed_bytes) : b2_engine_packed_ticket(h->eng, ticket, slot, &packed_bytes);
+    if (!info || !packed) return -1;
+    size_t n = b2h_write_slice_packed(ent, &h->seq, is_idr ? B2_FRAME_I : B2_FRAME_P, t, (int)(gop_index & 0xffff), info, packed,
+                                      packed_bytes, s + pos + 4, h->scratch_cap - pos - 4);
     if (!n) { fprintf(stderr, "b2enc: slice buffer overflow\n"); return -1; }
     put_prefix(s + pos, h->p.b_annexb, n);
     o->nal_off[o->nal_count] = (int)pos; o->nal_size[o->nal_count] = (int)n + 4;

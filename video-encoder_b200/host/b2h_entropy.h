@@ -38,6 +38,9 @@ size_t b2h_write_pps(const b2h_seq_t *s, uint8_t *out, size_t cap);
 size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type /* B2_FRAME_* */, int frame_num,
                        int idr_pic_id, const b2_mbinfo_t *info, const b2_mbcoef_t *coef,
                        uint8_t *out, size_t cap);
+/* same, reading the levels from the engine's packed stream (b2_engine_packed, layout in b2enc_types.h) */
+size_t b2h_write_slice_packed(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int frame_num, int idr_pic_id,
+                              const b2_mbinfo_t *info, const uint8_t *packed, size_t packed_bytes, uint8_t *out, size_t cap);
 
 #ifdef __cplusplus
 }

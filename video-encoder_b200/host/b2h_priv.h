@@ -27,6 +27,27 @@ struct b2h_entropy {
 enum { B2H_MBF_SKIP = 1, B2H_MBF_INTRA = 2, B2H_MBF_I16 = 4, B2H_MBF_T8 = 8,
        B2H_MBF_DC_Y = 16, B2H_MBF_DC_U = 32, B2H_MBF_DC_V = 64 };      /* DC_*: coded_block_flag of that DC block */
 
+/* where a slice writer reads the quantised levels of macroblock mi from: the dense array (832 B/MB) or the packed
+ * stream of include/b2enc_types.h (b2_coef_present), which is walked in macroblock order */
+typedef struct {
+    const b2_mbcoef_t *dense;
+    const uint8_t *packed;
+    size_t pos, size;
+} b2h_levels_t;
+extern const int16_t b2h_zero_levels[64];
+static inline void b2h_levels_mb(b2h_levels_t *lv, const b2_mbinfo_t *m, int mi, const int16_t *blk[B2_COEF_BLOCKS])
+{
+    if (lv->dense) {
+        for (int b = 0; b < B2_COEF_BLOCKS; b++) blk[b] = lv->dense[mi].blk[b];
+        return;
+    }
+    const uint32_t pm = b2_coef_present(m);
+    for (int b = 0; b < B2_COEF_BLOCKS; b++) {
+        if (((pm >> b) & 1u) && lv->pos + 32 <= lv->size) { blk[b] = (const int16_t *)(lv->packed + lv->pos); lv->pos += 32; }
+        else blk[b] = b2h_zero_levels;
+    }
+}
+
 /* 8.4.1.3 median prediction for a 16x16 partition, single reference frame; also returns the A / B neighbours
  * (P_Skip inference 8.4.1.1) */
 b2_mv_t b2h_mv_pred16x16(const b2h_entropy_t *e, int mbx, int mby, int *availA, int *availB,
@@ -34,7 +55,7 @@ b2_mv_t b2h_mv_pred16x16(const b2h_entropy_t *e, int mbx, int mby, int *availA, 
 /* slice_header() 7.3.3 up to and including the deblocking fields */
 void b2h_slice_header(bs_t *b, const b2h_seq_t *s, int is_p, int frame_num, int idr_pic_id);
 size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int frame_num, int idr_pic_id,
-                             const b2_mbinfo_t *info, const b2_mbcoef_t *coef, uint8_t *out, size_t cap);
+                             const b2_mbinfo_t *info, b2h_levels_t *lv, uint8_t *out, size_t cap);
 extern const uint8_t b2h_blk_x[16], b2h_blk_y[16];
 
 #endif
