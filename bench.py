@@ -346,9 +346,9 @@ def main():
                              % (SLOTS, int(SLOTS * 3 * 1.5 * w16 * h16 / 1e6)),
                        "host_cpus_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None, "stream_groups": NG, "gop_phase_per_group": phase, "deblocking_filter": bool(args.deblock), "transform8x8": bool(args.transform8x8),
                        "parallelism": "closed-GOP sharding, %d GPUs x %d GOPs, no collective" % (world, SLOTS)},
-            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(SLOTS * in_bytes),
-                    "d2h_bytes_per_step": int(SLOTS * mbs * 48 + packed_per_step) if args.pack_levels else int(SLOTS * mbs * (48 + 832)),
-                    "d2h_note": ("per-MB decisions (48 B) + packed levels (K9: blocks with a non-zero level only; mean of this rank over the timed steps)"
+            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(world * SLOTS * in_bytes),
+                    "d2h_bytes_per_step": int(world * (SLOTS * mbs * 48 + packed_per_step)) if args.pack_levels else int(world * SLOTS * mbs * (48 + 832)),
+                    "d2h_note": ("per-MB decisions (48 B) + packed levels (K9: blocks with a non-zero level only; mean over the timed steps, rank 0 x n_gpus)"
                                  if args.pack_levels else "per-MB decisions (48 B) + dense levels (832 B)"), "api": "b2_engine_h2d/encode/d2h (include/b2enc_engine.h), pinned host buffers",
                     "timing": "host wall clock around %d pipelined steps, synchronised on both sides" % n_e2e},
             "gpu_launches": int(launches),
