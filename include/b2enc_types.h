@@ -55,7 +55,8 @@ typedef struct {
                             /* {mvx,mvy} for P16x16)                                               */
     uint8_t  part;          /* B2_PART_* partition shape of an inter MB                            */
     uint8_t  transform8x8;  /* 1: the luma residual uses the 8x8 transform (transform_size_8x8_flag) */
-    uint8_t  reserved[2];
+    uint16_t i8_modes;      /* intra analysis with the 8x8 transform enabled: best B2_I4_* mode of 8x8 block k in    */
+                            /* bits 4k..4k+3 (kept for every MB the analysis ran on, whatever type was chosen)     */
 } b2_mbinfo_t;
 
 /* Quantised levels of one macroblock, each block in zig-zag scan order.

@@ -82,6 +82,18 @@ void b2o_recon_intra_mb(const b2o_params_t *prm, const b2o_frame_t *cur, b2o_fra
         b2o_pred16x16(mi->i16_mode, ry, recon->pitch, mba, pred);
         copy_block(ry, recon->pitch, pred, 16, 16, 16);
         mask |= b2o_code_luma16x16(sy, cur->pitch, ry, recon->pitch, prm->qp, coef);
+    } else if (mi->mb_type == B2_MB_I8x8) {
+        for (int q = 0; q < 4; q++) {
+            uint8_t pred[64];
+            int mode = (mi->i8_modes >> (4 * q)) & 15;
+            int o = (q >> 1) * 8 * cur->pitch + (q & 1) * 8;
+            uint8_t *rb = ry + (q >> 1) * 8 * recon->pitch + (q & 1) * 8;
+            b2o_pred8x8l(mode, rb, recon->pitch, b2o_blk8_avail(q, mba), pred);
+            copy_block(rb, recon->pitch, pred, 8, 8, 8);
+            mask |= (uint32_t)b2o_code_luma8x8(sy + o, cur->pitch, rb, recon->pitch, prm->qp, 1, coef->blk[4 * q]) << (4 * q);
+            for (int k = 0; k < 4; k++) mi->i4_mode[4 * q + k] = (uint8_t)mode;
+        }
+        mi->transform8x8 = 1;
     } else {
         for (int b = 0; b < 16; b++) {
             uint8_t pred[16];
@@ -110,11 +122,12 @@ void b2o_encode_frame(const b2o_params_t *prm, int frame_type,
     int lambda = b2o_lambda(prm->qp);
     uint32_t *c16 = (uint32_t *)malloc(sizeof(uint32_t) * n), *c4 = (uint32_t *)malloc(sizeof(uint32_t) * n);
     uint32_t *cinter = (uint32_t *)malloc(sizeof(uint32_t) * n);
+    uint32_t *c8 = prm->transform8x8 ? (uint32_t *)malloc(sizeof(uint32_t) * n) : NULL;
     b2_mv_t *mvf = (b2_mv_t *)malloc(sizeof(b2_mv_t) * n), *mvq = (b2_mv_t *)malloc(sizeof(b2_mv_t) * n);
     memset(info, 0, sizeof(b2_mbinfo_t) * n);
 
     int do_intra = frame_type == B2_FRAME_I || prm->intra_in_p;
-    if (do_intra) b2o_intra_analyse(cur, lambda, info, c16, c4);
+    if (do_intra) b2o_intra_analyse(cur, lambda, info, c16, c4, c8);
     if (frame_type == B2_FRAME_P) {
         b2o_me_fullpel(cur, ref, prm->merange, prev_mv, lambda, mvf, cinter);
         if (prm->subpel) {
@@ -134,7 +147,11 @@ void b2o_encode_frame(const b2o_params_t *prm, int frame_type,
     /* decision */
     for (int i = 0; i < n; i++) {
         uint32_t ci = 0xffffffffu; int it = B2_MB_I16x16;
-        if (do_intra) { ci = c16[i]; if (c4[i] < c16[i]) { ci = c4[i]; it = B2_MB_I4x4; } }
+        if (do_intra) {
+            ci = c16[i];
+            if (c4[i] < ci) { ci = c4[i]; it = B2_MB_I4x4; }
+            if (c8 && c8[i] < ci) { ci = c8[i]; it = B2_MB_I8x8; }
+        }
         if (frame_type == B2_FRAME_P && !(do_intra && ci < cinter[i])) {
             info[i].mb_type = B2_MB_P16x16; info[i].mvx = mvq[i].x; info[i].mvy = mvq[i].y; info[i].cost = cinter[i];
         } else {
@@ -150,5 +167,5 @@ void b2o_encode_frame(const b2o_params_t *prm, int frame_type,
         }
     if (prm->deblock) b2o_deblock_frame(recon, info, prm->qp);
     b2o_frame_extend(recon);
-    free(c16); free(c4); free(cinter); free(mvf); free(mvq);
+    free(c16); free(c4); free(cinter); free(mvf); free(mvq); free(c8);
 }

@@ -167,6 +167,109 @@ void b2o_pred4x4(int mode, const uint8_t *p, int pitch, int avail, uint8_t dst[1
 #undef F2
 }
 
+/* ---- intra 8x8 (High profile): reference sample filtering 8.3.2.2.1 + the nine predictors
+ * 8.3.2.2.2-8.3.2.2.10.  avail as for 4x4 blocks; TR missing -> p[7,-1] replicated. */
+void b2o_pred8x8l(int mode, const uint8_t *p, int pitch, int avail, uint8_t dst[64])
+{
+    int Tb[17], Lb[9];
+    int *T = Tb + 1, *L = Lb + 1;                 /* T[-1] = L[-1] = filtered top-left */
+    int t[16], l[8], m = 128;
+    const uint8_t *top = p - pitch;
+    const int hasT = (avail & B2O_AV_T) != 0, hasL = (avail & B2O_AV_L) != 0, hasTL = (avail & B2O_AV_TL) != 0;
+    for (int i = 0; i < 8; i++) { t[i] = hasT ? top[i] : 128; l[i] = hasL ? p[i * pitch - 1] : 128; }
+    for (int i = 8; i < 16; i++) t[i] = (avail & B2O_AV_TR) ? top[i] : t[7];
+    if (hasTL) m = top[-1];
+    /* filtered samples */
+    for (int i = 0; i < 16; i++) T[i] = 128;
+    for (int i = 0; i < 8; i++) L[i] = 128;
+    int M = 128;
+    if (hasT) {
+        T[0] = hasTL ? (m + 2 * t[0] + t[1] + 2) >> 2 : (3 * t[0] + t[1] + 2) >> 2;
+        for (int i = 1; i < 15; i++) T[i] = (t[i - 1] + 2 * t[i] + t[i + 1] + 2) >> 2;
+        T[15] = (t[14] + 3 * t[15] + 2) >> 2;
+    }
+    if (hasTL) {
+        if (!hasT) M = (3 * m + l[0] + 2) >> 2;            /* hasL is implied when the corner exists without the top */
+        else if (!hasL) M = (3 * m + t[0] + 2) >> 2;
+        else M = (t[0] + 2 * m + l[0] + 2) >> 2;
+    }
+    if (hasL) {
+        L[0] = hasTL ? (m + 2 * l[0] + l[1] + 2) >> 2 : (3 * l[0] + l[1] + 2) >> 2;
+        for (int i = 1; i < 7; i++) L[i] = (l[i - 1] + 2 * l[i] + l[i + 1] + 2) >> 2;
+        L[7] = (l[6] + 3 * l[7] + 2) >> 2;
+    }
+    T[-1] = L[-1] = M;
+#define F3(a, b, c) (((a) + 2 * (b) + (c) + 2) >> 2)
+#define F2(a, b) (((a) + (b) + 1) >> 1)
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++) {
+            int v;
+            switch (mode) {
+            case B2_I4_V: v = T[x]; break;
+            case B2_I4_H: v = L[y]; break;
+            case B2_I4_DC: {
+                int s = 0;
+                if (hasT) for (int i = 0; i < 8; i++) s += T[i];
+                if (hasL) for (int i = 0; i < 8; i++) s += L[i];
+                v = (hasT && hasL) ? (s + 8) >> 4 : (hasT || hasL) ? (s + 4) >> 3 : 128;
+                break;
+            }
+            case B2_I4_DDL:
+                v = (x == 7 && y == 7) ? (T[14] + 3 * T[15] + 2) >> 2 : F3(T[x + y], T[x + y + 1], T[x + y + 2]);
+                break;
+            case B2_I4_DDR:
+                if (x > y) v = F3(T[x - y - 2], T[x - y - 1], T[x - y]);
+                else if (x < y) v = F3(L[y - x - 2], L[y - x - 1], L[y - x]);
+                else v = F3(T[0], M, L[0]);
+                break;
+            case B2_I4_VR: {
+                int z = 2 * x - y, k = x - (y >> 1);
+                if (z >= 0 && !(z & 1)) v = F2(T[k - 1], T[k]);
+                else if (z >= 0) v = F3(T[k - 2], T[k - 1], T[k]);
+                else if (z == -1) v = F3(L[0], M, T[0]);
+                else v = F3(L[y - 2 * x - 1], L[y - 2 * x - 2], L[y - 2 * x - 3]);
+                break;
+            }
+            case B2_I4_HD: {
+                int z = 2 * y - x, k = y - (x >> 1);
+                if (z >= 0 && !(z & 1)) v = F2(L[k - 1], L[k]);
+                else if (z >= 0) v = F3(L[k - 2], L[k - 1], L[k]);
+                else if (z == -1) v = F3(L[0], M, T[0]);
+                else v = F3(T[x - 2 * y - 1], T[x - 2 * y - 2], T[x - 2 * y - 3]);
+                break;
+            }
+            case B2_I4_VL: {
+                int k = x + (y >> 1);
+                v = (y & 1) ? F3(T[k], T[k + 1], T[k + 2]) : F2(T[k], T[k + 1]);
+                break;
+            }
+            default: {                                   /* HU */
+                int z = x + 2 * y, k = y + (x >> 1);
+                if (z > 13) v = L[7];
+                else if (z == 13) v = (L[6] + 3 * L[7] + 2) >> 2;
+                else if (z & 1) v = F3(L[k], L[k + 1], L[k + 2]);
+                else v = F2(L[k], L[k + 1]);
+                break;
+            }
+            }
+            dst[y * 8 + x] = (uint8_t)v;
+        }
+#undef F3
+#undef F2
+}
+
+/* availability of 8x8 block q (raster 2x2) inside an MB with MB-level availability `mba` */
+int b2o_blk8_avail(int q, int mba)
+{
+    int qx = q & 1, qy = q >> 1, a = 0;
+    if (qx || (mba & B2O_AV_L)) a |= B2O_AV_L;
+    if (qy || (mba & B2O_AV_T)) a |= B2O_AV_T;
+    if ((qx && qy) || (qx && !qy && (mba & B2O_AV_T)) || (!qx && qy && (mba & B2O_AV_L)) || (!qx && !qy && (mba & B2O_AV_TL)))
+        a |= B2O_AV_TL;
+    if (q == 0 ? (mba & B2O_AV_T) : q == 1 ? (mba & B2O_AV_TR) : q == 2) a |= B2O_AV_TR;
+    return a;
+}
+
 /* neighbour availability of MB (mbx,mby): one slice per frame, so purely geometric */
 int b2o_mb_avail(int mbx, int mby, int mbw)
 {
@@ -198,7 +301,8 @@ int b2o_blk_avail(int b, int mba)
 
 static const uint8_t ue_bits4[4] = {1, 3, 3, 5};
 
-void b2o_intra_analyse(const b2o_frame_t *cur, int lambda, b2_mbinfo_t *info, uint32_t *cost_i16, uint32_t *cost_i4)
+void b2o_intra_analyse(const b2o_frame_t *cur, int lambda, b2_mbinfo_t *info, uint32_t *cost_i16, uint32_t *cost_i4,
+                       uint32_t *cost_i8)
 {
     for (int mby = 0; mby < cur->mbh; mby++)
         for (int mbx = 0; mbx < cur->mbw; mbx++) {
@@ -229,6 +333,27 @@ void b2o_intra_analyse(const b2o_frame_t *cur, int lambda, b2_mbinfo_t *info, ui
                 }
                 info[i].i4_mode[b] = (uint8_t)bm;
                 sum4 += best;
+            }
+            /* I8x8 (only with the 8x8 transform): SA8D (8x8 Hadamard) per block like x264's i8x8 analysis, same bit model as I4x4 */
+            if (cost_i8) {
+                uint32_t sum8 = (uint32_t)lambda * 8;
+                unsigned modes = 0;
+                for (int q = 0; q < 4; q++) {
+                    const uint8_t *sb = sy + (q >> 1) * 8 * cur->pitch + (q & 1) * 8;
+                    int ba = b2o_blk8_avail(q, mba);
+                    uint32_t best = 0xffffffffu; int bm = B2_I4_DC;
+                    for (int m = 0; m < 9; m++) {
+                        if (!b2o_i4_mode_ok(m, ba)) continue;
+                        uint8_t pred[64];
+                        b2o_pred8x8l(m, sb, cur->pitch, ba, pred);
+                        uint32_t c = b2o_sa8d8x8(sb, cur->pitch, pred, 8) + (uint32_t)lambda * (m == B2_I4_DC ? 1 : 4);
+                        if (c < best) { best = c; bm = m; }
+                    }
+                    modes |= (unsigned)bm << (4 * q);
+                    sum8 += best;
+                }
+                info[i].i8_modes = (uint16_t)modes;
+                cost_i8[i] = sum8;
             }
             /* chroma 8x8 */
             const uint8_t *su = cur->u + (size_t)(mby * 8) * cur->pitchc + mbx * 8;

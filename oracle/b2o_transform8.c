@@ -163,6 +163,9 @@ static uint32_t hadamard8_abs(const uint8_t *a, int pa, const uint8_t *b, int pb
     return s;
 }
 
+/* SA8D of one 8x8 block: (sum |H8 D H8^T| + 2) >> 2 (x264's sa8d_8x8 normalisation) */
+uint32_t b2o_sa8d8x8(const uint8_t *a, int pa, const uint8_t *b, int pb) { return (hadamard8_abs(a, pa, b, pb) + 2) >> 2; }
+
 /* SA8D of a 16x16 block: (sum over the four 8x8 Hadamards + 2) >> 2 */
 uint32_t b2o_sa8d16x16(const uint8_t *a, int pa, const uint8_t *b, int pb)
 {

@@ -5,7 +5,7 @@ desynchronises the arithmetic decoder for the rest of the slice, so this pins th
 import collections
 import numpy as np
 import pytest
-from test_oracle_decode import smooth_seq, _roundtrip
+from test_oracle_decode import smooth_seq, coarse_seq, _roundtrip
 
 
 @pytest.mark.parametrize("w,h,qp,R,cut,deblock", [(176, 144, 26, 16, None, 0), (320, 240, 32, 32, 4, 1), (208, 160, 18, 16, 3, 0),
@@ -59,3 +59,25 @@ def test_transform8x8_stream_decodes_to_oracle_recon(oracle, w, h, qp, R, cut, d
     assert t8 > 0, "no macroblock chose the 8x8 transform"
     if qp < 40:
         assert n4 > 0, "no coded inter macroblock kept the 4x4 transform"
+
+
+@pytest.mark.parametrize("cabac", [0, 1])
+@pytest.mark.parametrize("w,h,qp,scale,deblock", [(96, 80, 40, 10, 1), (176, 144, 44, 12, 0), (208, 160, 36, 16, 1), (70, 54, 46, 8, 1)])
+def test_intra8x8_stream_decodes_to_oracle_recon(oracle, w, h, qp, scale, deblock, cabac):
+    """row N1, intra 8x8: reference-sample filter + nine 8x8 predictors + intra 8x8 residual, I and P slices"""
+    frames = coarse_seq(w, h, 4, seed=qp, scale=scale)
+    bs, recons, infos = _roundtrip(oracle, frames, w, h, qp=qp, merange=16, gop=2, cabac=cabac, deblock=deblock, transform8x8=1)
+    i8 = [inf[inf["mb_type"] == 3] for inf in infos]
+    assert sum(x.size for x in i8) >= 8, "too few I8x8 macroblocks to mean anything"
+    for inf in infos:
+        m = inf[inf["mb_type"] == 3]
+        assert np.all(m["transform8x8"] == 1)
+        assert np.all(m["i4_mode"].reshape(-1, 4, 4) == ((m["i8_modes"][:, None] >> (4 * np.arange(4))[None, :]) & 15)[:, :, None])
+
+
+def test_intra8x8_all_nine_modes_are_exercised(oracle):
+    w, h, qp = 96, 80, 40
+    frames = coarse_seq(w, h, 4, seed=qp, scale=10)
+    _, _, infos = _roundtrip(oracle, frames, w, h, qp=qp, merange=16, gop=2, cabac=1, deblock=1, transform8x8=1)
+    modes = np.concatenate([((inf["i8_modes"][inf["mb_type"] == 3][:, None] >> (4 * np.arange(4))[None, :]) & 15).ravel() for inf in infos])
+    assert set(modes.tolist()) == set(range(9))

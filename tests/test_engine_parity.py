@@ -4,11 +4,11 @@ MVs and costs (K2), intra costs and modes (K3), decisions, quantised levels, cbp
 reconstructed planes must all be bit-identical."""
 import numpy as np
 import pytest
-from test_oracle_decode import smooth_seq
+from test_oracle_decode import smooth_seq, coarse_seq
 
 pytestmark = pytest.mark.gpu
 
-INFO_FIELDS = ["mb_type", "mvx", "mvy", "i16_mode", "chroma_mode", "cbp", "i4_mode", "cost", "nnz_mask", "mv8", "part", "transform8x8"]
+INFO_FIELDS = ["mb_type", "mvx", "mvy", "i16_mode", "chroma_mode", "cbp", "i4_mode", "cost", "nnz_mask", "mv8", "part", "transform8x8", "i8_modes"]
 
 
 def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="yuv420p", deblock=0, transform8x8=0, pack_levels=0):
@@ -17,7 +17,7 @@ def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="
     eng = b2.Engine(w, h, slots=S, fmt=fmt, ring=2, merange=R, qp=qp, subpel=subpel, intra_in_p=intra_in_p, deblock=deblock,
                     transform8x8=transform8x8, pack_levels=pack_levels)
     prm = oracle.Params(qp, R, subpel, intra_in_p, deblock, transform8x8)
-    stats = {"t8": 0, "coded4": 0}
+    stats = {"t8": 0, "coded4": 0, "i8": 0}
     prev = [None] * S; prev_mv = [None] * S
     for t in range(T):
         for s in range(S):
@@ -45,7 +45,7 @@ def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="
             ry, ru, rv = eng.recon(s)
             assert np.array_equal(ry, rec.y), f"recon Y t={t} s={s}"
             assert np.array_equal(ru, rec.u) and np.array_equal(rv, rec.v), f"recon UV t={t} s={s}"
-            stats["t8"] += int(info_o["transform8x8"].sum())
+            stats["t8"] += int(info_o["transform8x8"].sum()); stats["i8"] += int((info_o["mb_type"] == 3).sum())
             stats["coded4"] += int(((info_o["mb_type"] == 0) & (info_o["transform8x8"] == 0) & ((info_o["cbp"] & 15) != 0)).sum())
             prev[s] = rec
             prev_mv[s] = np.zeros(info_o.size, oracle.MV); prev_mv[s]["x"] = info_o["mvx"]; prev_mv[s]["y"] = info_o["mvy"]
@@ -108,6 +108,18 @@ def test_engine_packed_levels(oracle, b2, w, h, qp, t8):
     """K9: only blocks with a non-zero level leave the GPU; stream == host packing of the oracle levels, several slots"""
     seqs = [smooth_seq(w, h, 4, seed=qp + 5, cut=2), smooth_seq(w, h, 4, seed=qp + 6), [oracle.synth_frame(w, h, t, 2) for t in range(4)]]
     run_and_compare(oracle, b2, seqs, w, h, qp, 16, deblock=1, transform8x8=t8, pack_levels=1)
+
+
+@pytest.mark.parametrize("w,h,qp,scale,deblock,pack", [(96, 80, 40, 10, 1, 0), (176, 144, 44, 12, 0, 1), (208, 160, 36, 16, 1, 0),
+                                                       (70, 54, 46, 8, 1, 1), (320, 240, 30, 14, 1, 0)])
+def test_engine_intra8x8(oracle, b2, w, h, qp, scale, deblock, pack):
+    """row N1, intra 8x8: K3 analysis (edge tables, SA8D), K5 decision, K7 serial 8x8 reconstruction; I and P frames"""
+    seqs = [coarse_seq(w, h, 4, seed=qp, scale=scale), coarse_seq(w, h, 4, seed=qp + 1, scale=scale + 2)]
+    for s in seqs:                       # scene change in every sequence -> intra macroblocks inside the P frames too
+        s[2] = coarse_seq(w, h, 1, seed=qp + 9, scale=scale)[0]
+    stats = run_and_compare(oracle, b2, seqs, w, h, qp, 16, deblock=deblock, transform8x8=1, pack_levels=pack)
+    if qp >= 36:
+        assert stats["i8"] >= 8
 
 
 def _to_fmt(fmt, y, u, v):

@@ -29,6 +29,23 @@ def smooth_seq(w, h, n, seed=0, cut=None):
     return frames
 
 
+def coarse_seq(w, h, n, seed=0, scale=10, noise=1.0):
+    """large smooth structures (random field upsampled by `scale`) + a little noise, panning by (3,2) px per frame:
+    the content on which intra 8x8 prediction and the 8x8 transform win"""
+    import cv2
+    rng = np.random.default_rng(seed)
+    b = rng.integers(0, 256, ((h + 64) // scale + 4, (w + 64) // scale + 4)).astype(np.float32)
+    B = cv2.resize(b, (b.shape[1] * scale, b.shape[0] * scale), interpolation=cv2.INTER_CUBIC)
+    frames = []
+    for t in range(n):
+        ox, oy = 3 * t + 2, 2 * t + 1
+        img = np.clip(B[oy:oy + h, ox:ox + w] + rng.normal(0, noise, (h, w)), 0, 255).astype(np.uint8)
+        u = (img[::2, ::2] // 2 + 64).astype(np.uint8)[:(h + 1) // 2, :(w + 1) // 2]
+        v = (255 - img[::2, ::2] // 2 - 30).astype(np.uint8)[:(h + 1) // 2, :(w + 1) // 2]
+        frames.append((img, u, v))
+    return frames
+
+
 def _roundtrip(oracle, frames, w, h, **kw):
     bs, recons, infos, coefs = oracle.encode_sequence(frames, w, h, **kw)
     dec = oracle.decode_yuv(oracle.split_access_units(bs))

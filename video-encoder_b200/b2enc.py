@@ -13,7 +13,7 @@ MV = np.dtype([("x", "<i2"), ("y", "<i2")])
 MBINFO = np.dtype([("mvx", "<i2"), ("mvy", "<i2"), ("mb_type", "u1"), ("i16_mode", "u1"),
                    ("chroma_mode", "u1"), ("cbp", "u1"), ("i4_mode", "u1", (16,)),
                    ("cost", "<u4"), ("nnz_mask", "<u4"), ("mv8", "<i2", (3, 2)), ("part", "u1"),
-                   ("transform8x8", "u1"), ("reserved", "u1", (2,))])
+                   ("transform8x8", "u1"), ("i8_modes", "<u2")])
 MBCOEF = np.dtype([("blk", "<i2", (26, 16))])
 
 

@@ -332,6 +332,85 @@ __device__ __forceinline__ void pred4x4(int mode, const int E[13], int avail, in
 #undef B2F2
 }
 
+// ---- intra 8x8 prediction (8.3.2.2) from edge tables -------------------------------------------------------
+// Edge sequence of one 8x8 block after the reference-sample filter 8.3.2.2.1, bottom-left to top-right:
+//   E[7-y] = p'[-1,y] (y = 0..7), E[8] = p'[-1,-1], E[9+x] = p'[x,-1] (x = 0..15)
+// and its two smoothings  F2[i] = (E[i] + E[i+1] + 1) >> 1 (i = 0..23),  F3[i] = (E[i] + 2 E[i+1] + E[i+2] + 2) >> 2
+// (i = 0..22), F3[23] = (E[23] + 3 E[24] + 2) >> 2.  Every directional predictor is one lookup:
+struct I8Edge {
+    uint8_t E[25], F2[24], F3[24];
+    uint8_t hu13;                      // (E[1] + 3 E[0] + 2) >> 2, the z = 13 sample of Horizontal-Up
+    uint8_t dc;                        // DC value for this block's availability
+    uint8_t pad[5];
+};                                     // 80 bytes
+
+// filtered edge sample i (0..24) from the raw edge R (same indexing, unavailable samples already substituted:
+// 128, top-right replicated); avail bits as for 4x4 blocks
+__device__ __forceinline__ int i8_filter_edge(const uint8_t *R, int i, int avail)
+{
+    const bool hasL = avail & 1, hasT = avail & 2, hasTL = avail & 4;
+    if (i < 8) {                                           // left column, y = 7 - i
+        if (!hasL) return 128;
+        if (i == 0) return (R[1] + 3 * R[0] + 2) >> 2;     // y = 7: (p[-1,6] + 3 p[-1,7] + 2) >> 2
+        if (i == 7 && !hasTL) return (3 * R[7] + R[6] + 2) >> 2;
+        return (R[i - 1] + 2 * R[i] + R[i + 1] + 2) >> 2;
+    }
+    if (i == 8) {
+        if (!hasTL) return 128;
+        if (!hasT) return (3 * R[8] + R[7] + 2) >> 2;
+        if (!hasL) return (3 * R[8] + R[9] + 2) >> 2;
+        return (R[7] + 2 * R[8] + R[9] + 2) >> 2;
+    }
+    if (!hasT) return 128;
+    if (i == 24) return (R[23] + 3 * R[24] + 2) >> 2;
+    if (i == 9 && !hasTL) return (3 * R[9] + R[10] + 2) >> 2;
+    return (R[i - 1] + 2 * R[i] + R[i + 1] + 2) >> 2;
+}
+
+// one predicted sample (X,Y in 0..7) of mode `mode`
+__device__ __forceinline__ int pred8x8_px(int mode, const I8Edge &t, int X, int Y)
+{
+    switch (mode) {
+    case B2_I4_V: return t.E[9 + X];
+    case B2_I4_H: return t.E[7 - Y];
+    case B2_I4_DC: return t.dc;
+    case B2_I4_DDL: return t.F3[9 + X + Y];
+    case B2_I4_DDR: return t.F3[7 + X - Y];
+    case B2_I4_VR: {
+        const int z = 2 * X - Y, k = X - (Y >> 1);
+        if (z < -1) return t.F3[8 - Y + 2 * X];
+        return (z & 1) ? t.F3[7 + k] : t.F2[8 + k];
+    }
+    case B2_I4_HD: {
+        const int z = 2 * Y - X, k = Y - (X >> 1);
+        if (z < -1) return t.F3[6 + X - 2 * Y];
+        return (z & 1) ? t.F3[7 - k] : t.F2[7 - k];
+    }
+    case B2_I4_VL: {
+        const int k = X + (Y >> 1);
+        return (Y & 1) ? t.F3[9 + k] : t.F2[9 + k];
+    }
+    default: {                                             // HU
+        const int z = X + 2 * Y, k = Y + (X >> 1);
+        if (z > 13) return t.E[0];
+        if (z == 13) return t.hu13;
+        return (z & 1) ? t.F3[5 - k] : t.F2[6 - k];
+    }
+    }
+}
+
+// availability of 8x8 block q (raster 2x2) given the MB's availability
+__device__ __forceinline__ int blk8_avail(int q, int mba)
+{
+    const int qx = q & 1, qy = q >> 1;
+    int a = 0;
+    if (qx || (mba & 1)) a |= 1;
+    if (qy || (mba & 2)) a |= 2;
+    if ((qx && qy) || (qx && !qy && (mba & 2)) || (!qx && qy && (mba & 1)) || (!qx && !qy && (mba & 4))) a |= 4;
+    if (q == 0 ? (mba & 2) != 0 : q == 1 ? (mba & 8) != 0 : q == 2) a |= 8;
+    return a;
+}
+
 // MB-level neighbour availability (one slice per frame: geometric)
 __device__ __forceinline__ int mb_avail(int mbx, int mby, int mbw)
 {

@@ -19,11 +19,12 @@ __device__ __forceinline__ int sum16(int v)      // sum over the 16-lane group
     return v;
 }
 
+template <bool I8>
 __global__ void __launch_bounds__(K3_THREADS)
 k3_intra_analyse_kernel(const uint8_t *__restrict__ cur_y, const uint8_t *__restrict__ cur_u,
                         const uint8_t *__restrict__ cur_v, int pitch, int pitchc, size_t stride_y, size_t stride_c,
                         int mbw, int mbh, int nmb_total, int lambda, b2_mbinfo_t *__restrict__ info,
-                        uint32_t *__restrict__ cost_i16, uint32_t *__restrict__ cost_i4)
+                        uint32_t *__restrict__ cost_i16, uint32_t *__restrict__ cost_i4, uint32_t *__restrict__ cost_i8)
 {
     const int gt = blockIdx.x * K3_THREADS + threadIdx.x;
     int mbi = gt >> 4;                            // global MB index over all frames
@@ -65,6 +66,76 @@ k3_intra_analyse_kernel(const uint8_t *__restrict__ cur_y, const uint8_t *__rest
         }
     }
     const uint32_t sum4 = (uint32_t)sum16((int)best4) + (uint32_t)(lambda * 24);
+
+    // ---- I8x8 (row N1, only with the 8x8 transform): the four lanes of a quad (z-order blocks 4q..4q+3) share the 8x8
+    // block's filtered edge tables in shared memory; every mode is evaluated (no divergence around the shuffles) and
+    // illegal ones are masked when the minimum is taken.  Cost = SA8D (8x8 Hadamard = butterflies over the quad's four
+    // 4x4 Hadamards) + lambda * bits, as in oracle/b2o_intra.c.
+    uint32_t sum8 = 0; int modes8 = 0;
+    if (I8) {
+        __shared__ b2::I8Edge s_edge[K3_THREADS / 4];
+        __shared__ uint8_t s_raw[K3_THREADS / 4][32];
+        const int quad = threadIdx.x >> 2, k = b & 3, q = b >> 2;
+        const int qx = (q & 1) * 8, qy = (q >> 1) * 8, sx = (k & 1) * 4, sy4 = (k >> 1) * 4;
+        const int qa = b2::blk8_avail(q, mba);
+        b2::I8Edge &et = s_edge[quad];
+        uint8_t *R = s_raw[quad];
+        const uint8_t *qp0 = sy + (size_t)qy * pitch + qx;             // top-left pixel of the 8x8 block
+        {   // raw edge: lane k loads T[4k..4k+3], L[2k], L[2k+1]; lane 0 the corner
+            uint32_t tw = 0x80808080u;
+            if (qa & 2) {
+                if (k < 2 || (qa & 8)) tw = *(const uint32_t *)(qp0 - (ptrdiff_t)pitch + 4 * k);
+                else tw = 0x01010101u * qp0[-(ptrdiff_t)pitch + 7];   // top-right missing: replicate p[7,-1]
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) R[9 + 4 * k + i] = (uint8_t)(tw >> (8 * i));
+            R[7 - 2 * k] = (qa & 1) ? qp0[(size_t)(2 * k) * pitch - 1] : 128;
+            R[6 - 2 * k] = (qa & 1) ? qp0[(size_t)(2 * k + 1) * pitch - 1] : 128;
+            if (k == 0) R[8] = (qa & 4) ? qp0[-(ptrdiff_t)pitch - 1] : 128;
+        }
+        __syncwarp();
+        for (int i = k; i < 25; i += 4) et.E[i] = (uint8_t)b2::i8_filter_edge(R, i, qa);
+        __syncwarp();
+        for (int i = k; i < 24; i += 4) {
+            et.F2[i] = (uint8_t)((et.E[i] + et.E[i + 1] + 1) >> 1);
+            et.F3[i] = i < 23 ? (uint8_t)((et.E[i] + 2 * et.E[i + 1] + et.E[i + 2] + 2) >> 2) : (uint8_t)((et.E[23] + 3 * et.E[24] + 2) >> 2);
+        }
+        if (k == 0) {
+            int st = 0, sl = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) { st += et.E[9 + i]; sl += et.E[i]; }
+            const bool hT = qa & 2, hL = qa & 1;
+            et.dc = (uint8_t)((hT && hL) ? (st + sl + 8) >> 4 : hT ? (st + 4) >> 3 : hL ? (sl + 4) >> 3 : 128);
+            et.hu13 = (uint8_t)((et.E[1] + 3 * et.E[0] + 2) >> 2);
+        }
+        __syncwarp();
+        uint32_t best8 = 0xffffffffu; int mode8 = B2_I4_DC;
+#pragma unroll 1
+        for (int m = 0; m < 9; m++) {
+            int d[16], t[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) d[i] = src[i] - b2::pred8x8_px(m, et, sx + (i & 3), sy4 + (i >> 2));
+            b2::hadamard4x4(d, t);
+            uint32_t s8 = 0;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                int o = __shfl_xor_sync(0xffffffffu, t[i], 1);
+                int u = (k & 1) ? o - t[i] : t[i] + o;
+                o = __shfl_xor_sync(0xffffffffu, u, 2);
+                u = (k & 2) ? o - u : u + o;
+                s8 += abs(u);
+            }
+            s8 += __shfl_xor_sync(0xffffffffu, s8, 1);
+            s8 += __shfl_xor_sync(0xffffffffu, s8, 2);
+            const uint32_t c = ((s8 + 2) >> 2) + (uint32_t)(lambda * (m == B2_I4_DC ? 1 : 4));
+            if (b2::i4_mode_ok(m, qa) && c < best8) { best8 = c; mode8 = m; }
+        }
+        sum8 = (uint32_t)sum16(k == 0 ? (int)best8 : 0) + (uint32_t)(lambda * 8);
+        // modes of the four quads -> 16-bit word on every lane of the group
+        const int gb = (threadIdx.x & 31) & 16;
+        modes8 = __shfl_sync(0xffffffffu, mode8, gb + 0) | (__shfl_sync(0xffffffffu, mode8, gb + 4) << 4) |
+                 (__shfl_sync(0xffffffffu, mode8, gb + 8) << 8) | (__shfl_sync(0xffffffffu, mode8, gb + 12) << 12);
+    }
 
     // ---- I16x16: lane i holds top[i] and left[i] ----------------------------------------------------
     const int lane16 = b;                        // 0..15 inside the group (group = 16 consecutive lanes)
@@ -180,6 +251,7 @@ k3_intra_analyse_kernel(const uint8_t *__restrict__ cur_y, const uint8_t *__rest
             info[mbi].chroma_mode = (uint8_t)modec;
             cost_i16[mbi] = best16;
             cost_i4[mbi] = sum4;
+            if (I8) { cost_i8[mbi] = sum8; info[mbi].i8_modes = (uint16_t)modes8; }
         }
     }
 }
@@ -188,12 +260,16 @@ k3_intra_analyse_kernel(const uint8_t *__restrict__ cur_y, const uint8_t *__rest
 
 int b2_launch_intra_analyse(const uint8_t *d_y, const uint8_t *d_u, const uint8_t *d_v, int pitch, int pitchc,
                             size_t stride_y, size_t stride_c, int mbw, int mbh, int nframes, int lambda,
-                            b2_mbinfo_t *d_info, uint32_t *d_c16, uint32_t *d_c4, cudaStream_t st)
+                            b2_mbinfo_t *d_info, uint32_t *d_c16, uint32_t *d_c4, uint32_t *d_c8, cudaStream_t st)
 {
     const int nmb = mbw * mbh * nframes;
     const int blocks = (nmb * 16 + K3_THREADS - 1) / K3_THREADS;
-    k3_intra_analyse_kernel<<<blocks, K3_THREADS, 0, st>>>(d_y, d_u, d_v, pitch, pitchc, stride_y, stride_c, mbw, mbh, nmb,
-                                                           lambda, d_info, d_c16, d_c4);
+    if (d_c8)
+        k3_intra_analyse_kernel<true><<<blocks, K3_THREADS, 0, st>>>(d_y, d_u, d_v, pitch, pitchc, stride_y, stride_c, mbw, mbh, nmb,
+                                                                     lambda, d_info, d_c16, d_c4, d_c8);
+    else
+        k3_intra_analyse_kernel<false><<<blocks, K3_THREADS, 0, st>>>(d_y, d_u, d_v, pitch, pitchc, stride_y, stride_c, mbw, mbh, nmb,
+                                                                      lambda, d_info, d_c16, d_c4, nullptr);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
 }

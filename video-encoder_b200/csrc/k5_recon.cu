@@ -139,7 +139,7 @@ template <bool T8>
 __global__ void __launch_bounds__(K5_WARPS * 32)
 k5_decide_inter_kernel(FramePlanes fp, int mbw, int mbh, int nmb_total, int is_p, int do_intra, int qp,
                        const b2_mv_t *__restrict__ mvq, const uint32_t *__restrict__ cost_inter,
-                       const uint32_t *__restrict__ c16, const uint32_t *__restrict__ c4,
+                       const uint32_t *__restrict__ c16, const uint32_t *__restrict__ c4, const uint32_t *__restrict__ c8,
                        b2_mbinfo_t *__restrict__ info, b2_mbcoef_t *__restrict__ coef, b2_mv_t *__restrict__ prev_mv_out,
                        const uint8_t *__restrict__ pred_y)
 {
@@ -152,7 +152,12 @@ k5_decide_inter_kernel(FramePlanes fp, int mbw, int mbh, int nmb_total, int is_p
 
     // K4: decision (identical on all lanes)
     uint32_t ci = 0xffffffffu; int it = B2_MB_I16x16;
-    if (do_intra) { ci = c16[mbi]; const uint32_t c = c4[mbi]; if (c < ci) { ci = c; it = B2_MB_I4x4; } }
+    if (do_intra) {
+        ci = c16[mbi];
+        const uint32_t c = c4[mbi];
+        if (c < ci) { ci = c; it = B2_MB_I4x4; }
+        if (T8) { const uint32_t c8v = c8[mbi]; if (c8v < ci) { ci = c8v; it = B2_MB_I8x8; } }
+    }
     const uint32_t cinter = is_p ? cost_inter[mbi] : 0u;
     const bool inter = is_p && !(do_intra && ci < cinter);
     b2_mv_t mv = {0, 0};
@@ -255,7 +260,7 @@ k5_decide_inter_kernel(FramePlanes fp, int mbw, int mbh, int nmb_total, int is_p
 int b2_launch_decide_inter(const uint8_t *const cur[3], const uint8_t *const ref[3], uint8_t *const rec[3], int pitch,
                            int pitchc, size_t stride_y, size_t stride_c, int mbw, int mbh, int nframes, int is_p,
                            int do_intra, int qp, const b2_mv_t *d_mvq, const uint32_t *d_cost_inter, const uint32_t *d_c16,
-                           const uint32_t *d_c4, b2_mbinfo_t *d_info, b2_mbcoef_t *d_coef, b2_mv_t *d_prev_mv,
+                           const uint32_t *d_c4, const uint32_t *d_c8, b2_mbinfo_t *d_info, b2_mbcoef_t *d_coef, b2_mv_t *d_prev_mv,
                            const uint8_t *d_pred_y, int transform8x8, cudaStream_t st)
 {
     FramePlanes fp;
@@ -264,10 +269,10 @@ int b2_launch_decide_inter(const uint8_t *const cur[3], const uint8_t *const ref
     const int nmb = mbw * mbh * nframes;
     if (transform8x8)
         k5_decide_inter_kernel<true><<<(nmb + K5_WARPS - 1) / K5_WARPS, K5_WARPS * 32, 0, st>>>(
-            fp, mbw, mbh, nmb, is_p, do_intra, qp, d_mvq, d_cost_inter, d_c16, d_c4, d_info, d_coef, d_prev_mv, d_pred_y);
+            fp, mbw, mbh, nmb, is_p, do_intra, qp, d_mvq, d_cost_inter, d_c16, d_c4, d_c8, d_info, d_coef, d_prev_mv, d_pred_y);
     else
         k5_decide_inter_kernel<false><<<(nmb + K5_WARPS - 1) / K5_WARPS, K5_WARPS * 32, 0, st>>>(
-            fp, mbw, mbh, nmb, is_p, do_intra, qp, d_mvq, d_cost_inter, d_c16, d_c4, d_info, d_coef, d_prev_mv, d_pred_y);
+            fp, mbw, mbh, nmb, is_p, do_intra, qp, d_mvq, d_cost_inter, d_c16, d_c4, nullptr, d_info, d_coef, d_prev_mv, d_pred_y);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -26,8 +26,13 @@ constexpr int K7_WARPS = 16;
 constexpr int TP = 48;                      // tile pitch; pixel (x,y) of the MB sits at tile[(y+1)*TP + x + 16]
 
 struct K7Warp {
-    __align__(16) uint8_t tile[17 * TP];    // rows y=-1..15, cols x=-1..19 (top-right needs 4 extra)
+    __align__(16) uint8_t tile[17 * TP];    // rows y=-1..15, cols x=-1..23 (top-right: 4 extra for I4x4, 8 for I8x8)
     __align__(16) uint8_t src[16 * 16];
+    // I8x8 (row N1): edge tables of the current 8x8 block, its prediction and the residual / coefficient tile
+    I8Edge edge;
+    uint8_t raw[32];
+    uint8_t p8[64];
+    int d8[64];
 };
 
 __device__ __forceinline__ void cluster_barrier()
@@ -231,6 +236,141 @@ __device__ void k7_luma_task(int lane, K7Warp &ws, const FramePlanes &fp, int fr
         }
         bits = __ballot_sync(0xffffffffu, lane < 16 && nnz != 0) & 0xffffu;
         if (luma_dc) bits |= 1u << 24;
+    } else if (mb_type == B2_MB_I8x8) {
+        // ---- I8x8 (row N1): the four 8x8 blocks are a serial chain (each predicts from the previous ones); per block the
+        // warp filters the edge (8.3.2.2.1), predicts two samples per lane, and runs the 8x8 transform with one lane per
+        // column / row through the shared-memory tile d8 ----
+        if (lane < 25) {                                      // top row x = -1..23
+            const int x = lane - 1;
+            const bool ok = x < 0 ? (mba & 4) != 0 : x < 16 ? hasT : (mba & 8) != 0;
+            ws.tile[x + 16] = ok ? ry[-(ptrdiff_t)fp.pitch + x] : 0;
+        }
+        if (lane < 16) {
+            ws.tile[(lane + 1) * TP + 15] = hasL ? ry[(size_t)lane * fp.pitch - 1] : 0;
+            *(uint4 *)&ws.src[lane * 16] = *(const uint4 *)(sy + (size_t)lane * fp.pitch);
+        }
+        const int modes = mi->i8_modes;
+        const int qbits8 = 16 + qp / 6, f8 = ((1 << qbits8) * 21) >> 6, sh = qp / 6, rem = qp % 6;
+        __syncwarp();
+        uint32_t mask = 0;
+#pragma unroll 1
+        for (int q8 = 0; q8 < 4; q8++) {
+            const int qx = (q8 & 1) * 8, qy = (q8 >> 1) * 8, qa = blk8_avail(q8, mba), mode = (modes >> (4 * q8)) & 15;
+            const uint8_t *t0 = &ws.tile[qy * TP + qx + 16];              // sample (x = qx, y = qy-1)
+            if (lane < 25) {                                               // raw edge, substituted where unavailable
+                int v = 128;
+                if (lane < 8) { if (qa & 1) v = t0[(8 - lane) * TP - 1]; }                       // p[-1, 7-lane]
+                else if (lane == 8) { if (qa & 4) v = t0[-1]; }
+                else if (qa & 2) v = t0[(lane - 9 < 8 || (qa & 8)) ? lane - 9 : 7];
+                ws.raw[lane] = (uint8_t)v;
+            }
+            __syncwarp();
+            if (lane < 25) ws.edge.E[lane] = (uint8_t)i8_filter_edge(ws.raw, lane, qa);
+            __syncwarp();
+            if (lane < 24) {
+                const uint8_t *E = ws.edge.E;
+                ws.edge.F2[lane] = (uint8_t)((E[lane] + E[lane + 1] + 1) >> 1);
+                ws.edge.F3[lane] = lane < 23 ? (uint8_t)((E[lane] + 2 * E[lane + 1] + E[lane + 2] + 2) >> 2) : (uint8_t)((E[23] + 3 * E[24] + 2) >> 2);
+            } else if (lane == 24) {
+                const uint8_t *E = ws.edge.E;
+                int st = 0, sl = 0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) { st += E[9 + i]; sl += E[i]; }
+                const bool hT = qa & 2, hL = qa & 1;
+                ws.edge.dc = (uint8_t)((hT && hL) ? (st + sl + 8) >> 4 : hT ? (st + 4) >> 3 : hL ? (sl + 4) >> 3 : 128);
+                ws.edge.hu13 = (uint8_t)((E[1] + 3 * E[0] + 2) >> 2);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int p = lane + 32 * j, X = p & 7, Y = p >> 3;
+                const int pr = pred8x8_px(mode, ws.edge, X, Y);
+                ws.p8[p] = (uint8_t)pr;
+                ws.d8[p] = (int)ws.src[(qy + Y) * 16 + qx + X] - pr;
+            }
+            __syncwarp();
+            if (lane < 8) {                                                // forward: columns, then rows + quantiser
+                int a[8], o[8];
+#pragma unroll
+                for (int y = 0; y < 8; y++) a[y] = ws.d8[y * 8 + lane];
+                fdct8_1d(a, o);
+#pragma unroll
+                for (int y = 0; y < 8; y++) ws.d8[y * 8 + lane] = o[y];
+            }
+            __syncwarp();
+            int z[8];
+            if (lane < 8) {
+                int a[8], o[8];
+#pragma unroll
+                for (int x = 0; x < 8; x++) a[x] = ws.d8[lane * 8 + x];
+                fdct8_1d(a, o);
+#pragma unroll
+                for (int x = 0; x < 8; x++) {
+                    const uint32_t mf = c_quant8_mf[rem][c_cls8[(lane & 3) * 4 + (x & 3)]];
+                    const int v = (int)(((uint32_t)abs(o[x]) * mf + (uint32_t)f8) >> qbits8);
+                    z[x] = o[x] < 0 ? -v : v;
+                }
+            }
+            __syncwarp();
+            if (lane < 8) {
+#pragma unroll
+                for (int x = 0; x < 8; x++) ws.d8[lane * 8 + x] = z[x];
+            }
+            __syncwarp();
+            uint32_t mask4 = 0;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {                                  // levels in 8x8 zig-zag order -> blk[4q..4q+3]
+                const int sp = lane + 32 * j;
+                const int v = ws.d8[c_zigzag8[sp]];
+                ((int16_t *)cf->blk[4 * q8])[sp] = (int16_t)v;
+                const uint32_t nzb = __ballot_sync(0xffffffffu, v != 0);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (nzb & (0x11111111u << k)) mask4 |= 1u << k;       // interleaved quarter k = scan positions == k mod 4
+            }
+            __syncwarp();
+            if (mask4) {                                                   // normative scaling + inverse: rows, then columns
+                if (lane < 8) {
+                    int a[8], o[8];
+#pragma unroll
+                    for (int x = 0; x < 8; x++) {
+                        const int ls = 16 * c_dequant8_v[rem][c_cls8[(lane & 3) * 4 + (x & 3)]];
+                        a[x] = sh >= 6 ? (z[x] * ls) << (sh - 6) : (z[x] * ls + (1 << (5 - sh))) >> (6 - sh);
+                    }
+                    idct8_1d(a, o);
+#pragma unroll
+                    for (int x = 0; x < 8; x++) ws.d8[lane * 8 + x] = o[x];
+                }
+                __syncwarp();
+                if (lane < 8) {
+                    int a[8], o[8];
+#pragma unroll
+                    for (int y = 0; y < 8; y++) a[y] = ws.d8[y * 8 + lane];
+                    idct8_1d(a, o);
+#pragma unroll
+                    for (int y = 0; y < 8; y++) ws.d8[y * 8 + lane] = (o[y] + 32) >> 6;
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int p = lane + 32 * j, X = p & 7, Y = p >> 3;
+                const int v = (int)ws.p8[p] + (mask4 ? ws.d8[p] : 0);
+                ws.tile[(qy + Y + 1) * TP + qx + X + 16] = (uint8_t)b2_clip255(v);
+            }
+            __syncwarp();
+            mask |= mask4 << (4 * q8);
+        }
+        bits = mask & 0xffffu;
+        if (lane < 16) {
+            *(uint4 *)(ry + (size_t)lane * fp.pitch) = *(const uint4 *)&ws.tile[(lane + 1) * TP + 16];
+            mi->i4_mode[lane] = (uint8_t)((modes >> (4 * (lane >> 2))) & 15);
+        }
+        if (lane == 0) mi->transform8x8 = 1;
+        if (lane == 24) {
+            uint4 z4 = make_uint4(0, 0, 0, 0);
+            ((uint4 *)cf->blk[24])[0] = z4; ((uint4 *)cf->blk[24])[1] = z4;
+        }
     } else {
         // ---- I4x4: shared-memory tile, 10-step wavefront, two blocks per step, one lane per pixel ----
         if (lane < 21) {                                      // top row x = -1..19
