@@ -24,7 +24,40 @@ extern "C" {
 enum { B2_MB_P16x16 = 0, B2_MB_I16x16 = 1, B2_MB_I4x4 = 2, B2_MB_I8x8 = 3 };   /* P16x16 = any inter MB, see `part` */
 enum { B2_FRAME_I = 0, B2_FRAME_P = 1 };
 /* raw input layouts accepted by the conversion kernel (the sws_scale source formats, av_encode.c:427) */
-enum { B2_FMT_YUV420P = 0, B2_FMT_NV12 = 1, B2_FMT_YUYV422 = 2, B2_FMT_UYVY422 = 3 };
+enum { B2_FMT_YUV420P = 0, B2_FMT_NV12 = 1, B2_FMT_YUYV422 = 2, B2_FMT_UYVY422 = 3,
+       /* bgr24 is bit-exact against libswscale's dedicated converter; the other three go through
+        * libswscale's fast-bilinear scaler, whose x86 code drifts along the row -- they are implemented drift-free and
+        * pinned with a tolerance (oracle/b2o_convert.c) */
+       B2_FMT_BGR24 = 4, B2_FMT_RGB24 = 5, B2_FMT_YUV422P = 6, B2_FMT_YUV411P = 7, B2_FMT_COUNT = 8 };
+
+/* tight layout of one raw picture of format fmt: returns the number of planes (0: unknown format) and, per plane,
+ * the bytes per row and the number of rows */
+static inline int b2_fmt_layout(int fmt, int w, int h, int rowbytes[3], int rows[3])
+{
+    const int cw = (w + 1) / 2, ch = (h + 1) / 2;
+    switch (fmt) {
+    case B2_FMT_YUV420P: rowbytes[0] = w; rows[0] = h; rowbytes[1] = rowbytes[2] = cw; rows[1] = rows[2] = ch; return 3;
+    case B2_FMT_NV12: rowbytes[0] = w; rows[0] = h; rowbytes[1] = 2 * cw; rows[1] = ch; rowbytes[2] = rows[2] = 0; return 2;
+    case B2_FMT_YUYV422: case B2_FMT_UYVY422: rowbytes[0] = 2 * w; rows[0] = h; rowbytes[1] = rowbytes[2] = rows[1] = rows[2] = 0; return 1;
+    case B2_FMT_BGR24: case B2_FMT_RGB24: rowbytes[0] = 3 * w; rows[0] = h; rowbytes[1] = rowbytes[2] = rows[1] = rows[2] = 0; return 1;
+    case B2_FMT_YUV422P: rowbytes[0] = w; rows[0] = h; rowbytes[1] = rowbytes[2] = cw; rows[1] = rows[2] = h; return 3;
+    case B2_FMT_YUV411P: rowbytes[0] = w; rows[0] = h; rowbytes[1] = rowbytes[2] = (w + 3) / 4; rows[1] = rows[2] = h; return 3;
+    default: return 0;
+    }
+}
+/* sizes for which the conversion is the closed form of oracle/b2o_convert.c (beyond them libswscale resamples the
+ * chroma with a varying phase): packed 4:2:2 and rgb24 need even width and height, bgr24 an even width, planar 4:2:2 an
+ * even height, planar 4:1:1 a width that is a multiple of 4 and an even height */
+static inline int b2_fmt_size_ok(int fmt, int w, int h)
+{
+    switch (fmt) {
+    case B2_FMT_YUYV422: case B2_FMT_UYVY422: case B2_FMT_RGB24: return !((w | h) & 1);
+    case B2_FMT_BGR24: return !(w & 1);
+    case B2_FMT_YUV422P: return !(h & 1);
+    case B2_FMT_YUV411P: return !(w & 3) && !(h & 1);
+    default: return 1;
+    }
+}
 
 /* intra 16x16 modes (H.264 Table 8-4) */
 enum { B2_I16_V = 0, B2_I16_H = 1, B2_I16_DC = 2, B2_I16_PLANE = 3 };

@@ -287,7 +287,7 @@ def split_access_units(annexb: bytes):
     return aus
 
 
-FMT = {"yuv420p": 0, "nv12": 1, "yuyv422": 2, "uyvy422": 3}
+FMT = {"yuv420p": 0, "nv12": 1, "yuyv422": 2, "uyvy422": 3, "bgr24": 4, "rgb24": 5, "yuv422p": 6, "yuv411p": 7}
 
 
 def convert_to_i420(fmt, w, h, planes):

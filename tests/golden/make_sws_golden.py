@@ -59,8 +59,46 @@ def main():
                 o = run_sws(fmt, w, h, [p], [2 * w])
                 out[f"{fmt}_{w}x{h}_in0"] = p
                 for i in range(3): out[f"{fmt}_{w}x{h}_out{i}"] = o[i]
+            # bgr24: dedicated converter in libswscale (even widths), bit-exact closed form in the oracle
+            p = rng.integers(0, 256, (h, 3 * w), dtype=np.uint8)
+            o = run_sws("bgr24", w, h, [p], [3 * w])
+            out[f"bgr24_{w}x{h}_in0"] = p
+            for i in range(3): out[f"bgr24_{w}x{h}_out{i}"] = o[i]
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "sws_golden.npz"), **out)
     print("wrote", len(out), "arrays")
+    tolerance_set()
+
+
+def smooth(rng, h, w, scale=6):
+    """band-limited content: the tolerance-pinned formats run through libswscale's drifting fast-bilinear pass"""
+    b = rng.integers(0, 256, (h // scale + 3, w // scale + 3)).astype(np.float32)
+    B = cv2.resize(b, (b.shape[1] * scale, b.shape[0] * scale), interpolation=cv2.INTER_CUBIC)
+    return np.clip(B[:h, :w], 0, 255).astype(np.uint8)
+
+
+def tolerance_set():
+    """tests/golden/sws_tolerance.npz: rgb24 / yuv422p / yuv411p on small smooth pictures, where
+    the position drift of libswscale's SWS_FAST_BILINEAR pass stays below rounding (see oracle/b2o_convert.c)"""
+    rng = np.random.default_rng(20261019)
+    out = {}
+    for (w, h) in [(64, 48), (70, 38), (34, 18), (48, 36), (61, 20), (32, 18), (96, 20)]:
+        cw, cw4 = (w + 1) // 2, (w + 3) // 4
+        y = smooth(rng, h, w)
+        for fmt, scw in (("yuv422p", cw), ("yuv411p", cw4)):
+            if fmt == "yuv411p" and w % 32:       # chroma doubling: only the x86 path (output chroma width % 16 == 0) is centre-aligned;
+                continue                          # the C path maps (srcW-2)/(dstW-2), an endpoint-aligned stretch that is not reproduced
+            u = smooth(rng, h, scw, 4); v = smooth(rng, h, scw, 4)
+            o = run_sws(fmt, w, h, [y, u, v], [w, scw, scw])
+            out[f"{fmt}_{w}x{h}_in0"] = y; out[f"{fmt}_{w}x{h}_in1"] = u; out[f"{fmt}_{w}x{h}_in2"] = v
+            for i in range(3): out[f"{fmt}_{w}x{h}_out{i}"] = o[i]
+        if w % 2:
+            continue
+        rgb = np.ascontiguousarray(np.stack([smooth(rng, h, w), smooth(rng, h, w), smooth(rng, h, w)], axis=2).reshape(h, 3 * w))
+        o = run_sws("rgb24", w, h, [rgb], [3 * w])
+        out[f"rgb24_{w}x{h}_in0"] = rgb
+        for i in range(3): out[f"rgb24_{w}x{h}_out{i}"] = o[i]
+    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "sws_tolerance.npz"), **out)
+    print("wrote", len(out), "tolerance arrays")
 
 
 if __name__ == "__main__":

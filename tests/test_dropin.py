@@ -20,6 +20,33 @@ def test_sws_scale_matches_live_swscale_golden(b2, case):
     assert np.array_equal(y, G[f"{case}_out0"]) and np.array_equal(u, G[f"{case}_out1"]) and np.array_equal(v, G[f"{case}_out2"])
 
 
+T = np.load(os.path.join(os.path.dirname(__file__), "golden", "sws_tolerance.npz"))
+TCASES = sorted({k.rsplit("_", 1)[0] for k in T.files})
+
+
+@pytest.mark.parametrize("case", TCASES)
+def test_sws_scale_tolerance_formats(oracle, b2, case):
+    """row N4: rgb24 / yuv422p / yuv411p through b2_sws_scale (K0): identical to the oracle's drift-free closed form, and
+    within the pinned tolerance of the live libswscale output"""
+    fmt, size = case.split("_")
+    w, h = [int(a) for a in size.split("x")]
+    ins = [T[f"{case}_in{i}"] for i in range(3) if f"{case}_in{i}" in T.files]
+    y, u, v = b2.sws_convert(fmt, w, h, ins, dst_pad=3)
+    oy, ou, ov = oracle.convert_to_i420(fmt, w, h, ins)
+    assert np.array_equal(y, oy) and np.array_equal(u, ou) and np.array_equal(v, ov)
+    tol = {"rgb24": (1, 1), "yuv422p": (1, 1), "yuv411p": (1, 2)}[fmt]
+    assert np.abs(y.astype(int) - T[f"{case}_out0"]).max() <= tol[0]
+    assert np.abs(u.astype(int) - T[f"{case}_out1"]).max() <= tol[1] and np.abs(v.astype(int) - T[f"{case}_out2"]).max() <= tol[1]
+
+
+def test_sws_refuses_sizes_without_closed_form(b2):
+    L = b2._dropin_lib()
+    assert not L.b2_sws_getContext(70, 38, b2.FMT["yuv411p"], 70, 38, 0, 1, None, None, None)     # 4:1:1 needs w % 4 == 0
+    assert not L.b2_sws_getContext(61, 36, b2.FMT["bgr24"], 61, 36, 0, 1, None, None, None)       # odd width
+    assert not L.b2_sws_getContext(64, 35, b2.FMT["rgb24"], 64, 35, 0, 1, None, None, None)       # odd height
+    assert not L.b2_sws_getContext(64, 36, 99, 64, 36, 0, 1, None, None, None)
+
+
 def drive(b2, frames, w, h, **kw):
     """the reference loop: encode every frame (av_encode.c:968-975), then drain (:1076-1083)"""
     enc = b2.DropInEncoder(w, h, **kw)

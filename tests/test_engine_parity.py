@@ -138,8 +138,20 @@ def _to_fmt(fmt, y, u, v):
     return [p]
 
 
+def _raw_planes(fmt, w, h, seed):
+    """raw picture of the row-N4 layouts (band-limited content per plane)"""
+    def plane(hh, ww, k):
+        y = smooth_seq(max(ww, 16), max(hh, 16), 1, seed=seed + k)[0][0]
+        return np.ascontiguousarray(y[:hh, :ww])
+    if fmt in ("bgr24", "rgb24"):
+        return [np.ascontiguousarray(np.stack([plane(h, w, 0), plane(h, w, 1), plane(h, w, 2)], axis=2).reshape(h, 3 * w))]
+    scw = (w + 1) // 2 if fmt == "yuv422p" else (w + 3) // 4
+    return [plane(h, w, 0), plane(h, scw, 1), plane(h, scw, 2)]
+
+
 @pytest.mark.parametrize("fmt,w,h", [("nv12", 150, 98), ("yuyv422", 158, 82), ("uyvy422", 176, 144), ("yuv420p", 161, 99),
-                                     ("nv12", 64, 48)])
+                                     ("nv12", 64, 48), ("bgr24", 150, 99), ("rgb24", 158, 82), ("yuv422p", 161, 98), ("yuv411p", 176, 144),
+                                     ("yuv411p", 100, 50)])
 def test_engine_input_formats_and_odd_sizes(oracle, b2, fmt, w, h):
     """K0 inside the engine: every supported raw layout, widths/heights that are not multiples of 16 (or even odd),
     checked against oracle conversion (pinned by live libswscale) + oracle frame encoder"""
@@ -151,9 +163,12 @@ def test_engine_input_formats_and_odd_sizes(oracle, b2, fmt, w, h):
     for t in range(T):
         raws = []
         for s in range(S):
-            y, u, v = seqs[s][t]
-            u = u[:(h + 1) // 2, :(w + 1) // 2]; v = v[:(h + 1) // 2, :(w + 1) // 2]
-            raws.append(_to_fmt(fmt, y, u, v))
+            if fmt in ("bgr24", "rgb24", "yuv422p", "yuv411p"):
+                raws.append(_raw_planes(fmt, w, h, 100 * s + 10 * t))
+            else:
+                y, u, v = seqs[s][t]
+                u = u[:(h + 1) // 2, :(w + 1) // 2]; v = v[:(h + 1) // 2, :(w + 1) // 2]
+                raws.append(_to_fmt(fmt, y, u, v))
             eng.put_frame(s, 0, raws[-1])
         ft = b2.FRAME_I if t == 0 else b2.FRAME_P
         eng.h2d(); eng.encode(ft); eng.d2h(); eng.sync()

@@ -77,7 +77,7 @@ def vabsdiff4_peak(device=0, outer=256, reps=5):
 
 
 # ---- engine binding (include/b2enc_engine.h) ----------------------------------------------------------
-FMT = {"yuv420p": 0, "nv12": 1, "yuyv422": 2, "uyvy422": 3}
+FMT = {"yuv420p": 0, "nv12": 1, "yuyv422": 2, "uyvy422": 3, "bgr24": 4, "rgb24": 5, "yuv422p": 6, "yuv411p": 7}
 FRAME_I, FRAME_P = 0, 1
 KERNEL_NAMES = ["K0 convert", "K6 border(cur)", "K1 full-pel SAD", "K2 sub-pel SATD", "K3 intra analyse",
                 "K5 decide+inter recon", "K7 intra recon", "K6 border(recon)", "K8 deblock", "K9 pack levels"]

@@ -87,13 +87,11 @@ struct b2_engine {
 
 static size_t input_bytes(int fmt, int w, int h)
 {
-    const size_t cw = (w + 1) / 2, ch = (h + 1) / 2;
-    switch (fmt) {
-    case B2_FMT_YUV420P: return (size_t)w * h + 2 * cw * ch;
-    case B2_FMT_NV12: return (size_t)w * h + 2 * cw * ch;
-    case B2_FMT_YUYV422: case B2_FMT_UYVY422: return (size_t)2 * w * h;
-    default: return 0;
-    }
+    int rb[3], rows[3];
+    const int np = b2_fmt_layout(fmt, w, h, rb, rows);
+    size_t n = 0;
+    for (int p = 0; p < np; p++) n += (size_t)rb[p] * rows[p];
+    return np && b2_fmt_size_ok(fmt, w, h) ? n : 0;
 }
 
 static int engine_alloc(b2_engine *e)
@@ -271,23 +269,11 @@ extern "C" int b2_engine_put_frame(b2_engine_t *e, int slot, int ring, const uin
 {
     uint8_t *dst = b2_engine_host_input(e, slot, ring);
     if (!dst) { fprintf(stderr, "b2enc: put_frame: bad slot/ring\n"); return -1; }
-    const int w = e->cfg.width, h = e->cfg.height, cw = (w + 1) / 2, ch = (h + 1) / 2;
-    switch (e->cfg.in_fmt) {
-    case B2_FMT_YUV420P:
-        for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * w, src[0] + (size_t)y * stride[0], w);
-        dst += (size_t)w * h;
-        for (int y = 0; y < ch; y++) memcpy(dst + (size_t)y * cw, src[1] + (size_t)y * stride[1], cw);
-        dst += (size_t)cw * ch;
-        for (int y = 0; y < ch; y++) memcpy(dst + (size_t)y * cw, src[2] + (size_t)y * stride[2], cw);
-        break;
-    case B2_FMT_NV12:
-        for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * w, src[0] + (size_t)y * stride[0], w);
-        dst += (size_t)w * h;
-        for (int y = 0; y < ch; y++) memcpy(dst + (size_t)y * 2 * cw, src[1] + (size_t)y * stride[1], 2 * cw);
-        break;
-    default:
-        for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * 2 * w, src[0] + (size_t)y * stride[0], 2 * w);
-        break;
+    int rb[3], rows[3];
+    const int np = b2_fmt_layout(e->cfg.in_fmt, e->cfg.width, e->cfg.height, rb, rows);
+    for (int p = 0; p < np; p++) {                      // tight planes, one after the other
+        for (int y = 0; y < rows[p]; y++) memcpy(dst + (size_t)y * rb[p], src[p] + (size_t)y * stride[p], rb[p]);
+        dst += (size_t)rb[p] * rows[p];
     }
     return 0;
 }

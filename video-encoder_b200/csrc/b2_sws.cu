@@ -30,12 +30,13 @@ extern "C" b2_sws_context_t *b2_sws_getContext(int srcW, int srcH, int srcFormat
         fprintf(stderr, "b2enc: b2_sws_getContext supports same-size conversion to yuv420p only\n");
         return nullptr;
     }
-    if (srcFormat < B2_FMT_YUV420P || srcFormat > B2_FMT_UYVY422) {
+    int rb[3], rws[3];
+    if (!b2_fmt_layout(srcFormat, srcW, srcH, rb, rws)) {
         fprintf(stderr, "b2enc: unsupported source pixel format %d\n", srcFormat);
         return nullptr;
     }
-    if ((srcFormat == B2_FMT_YUYV422 || srcFormat == B2_FMT_UYVY422) && ((srcW | srcH) & 1)) {
-        fprintf(stderr, "b2enc: packed 4:2:2 input needs even width and height\n");
+    if (!b2_fmt_size_ok(srcFormat, srcW, srcH)) {
+        fprintf(stderr, "b2enc: source format %d cannot be converted at %dx%d (see b2_fmt_size_ok in b2enc_types.h)\n", srcFormat, srcW, srcH);
         return nullptr;
     }
     int ndev = 0;
@@ -49,8 +50,8 @@ extern "C" b2_sws_context_t *b2_sws_getContext(int srcW, int srcH, int srcFormat
     c->w16 = (srcW + 15) & ~15; c->h16 = (srcH + 15) & ~15;
     c->pitch = c->w16 + 2 * B2_PAD; c->rows = c->h16 + 2 * B2_PAD;
     c->pitchc = (c->w16 / 2 + 2 * B2_PADC + 15) & ~15; c->rowsc = c->h16 / 2 + 2 * B2_PADC;
-    const size_t cw = (srcW + 1) / 2, ch = (srcH + 1) / 2;
-    c->in_bytes = (srcFormat == B2_FMT_YUYV422 || srcFormat == B2_FMT_UYVY422) ? (size_t)2 * srcW * srcH : (size_t)srcW * srcH + 2 * cw * ch;
+    c->in_bytes = 0;
+    for (int p = 0; p < 3; p++) c->in_bytes += (size_t)rb[p] * rws[p];
     bool ok = cudaHostAlloc(&c->h_in, c->in_bytes, cudaHostAllocDefault) == cudaSuccess &&
               cudaMalloc(&c->d_in, c->in_bytes) == cudaSuccess && cudaMalloc(&c->d_y, (size_t)c->pitch * c->rows) == cudaSuccess &&
               cudaMalloc(&c->d_u, (size_t)c->pitchc * c->rowsc) == cudaSuccess &&
@@ -76,18 +77,11 @@ extern "C" int b2_sws_scale(b2_sws_context_t *c, const uint8_t *const src[], con
     }
     const int w = c->w, h = c->h, cw = (w + 1) / 2, ch = (h + 1) / 2;
     uint8_t *p = c->h_in;
-    if (c->fmt == B2_FMT_YUV420P || c->fmt == B2_FMT_NV12) {
-        for (int y = 0; y < h; y++) memcpy(p + (size_t)y * w, src[0] + (size_t)y * srcStride[0], w);
-        p += (size_t)w * h;
-        if (c->fmt == B2_FMT_YUV420P) {
-            for (int y = 0; y < ch; y++) memcpy(p + (size_t)y * cw, src[1] + (size_t)y * srcStride[1], cw);
-            p += (size_t)cw * ch;
-            for (int y = 0; y < ch; y++) memcpy(p + (size_t)y * cw, src[2] + (size_t)y * srcStride[2], cw);
-        } else {
-            for (int y = 0; y < ch; y++) memcpy(p + (size_t)y * 2 * cw, src[1] + (size_t)y * srcStride[1], 2 * cw);
-        }
-    } else {
-        for (int y = 0; y < h; y++) memcpy(p + (size_t)y * 2 * w, src[0] + (size_t)y * srcStride[0], 2 * w);
+    int rb[3], rws[3];
+    const int np = b2_fmt_layout(c->fmt, w, h, rb, rws);
+    for (int k = 0; k < np; k++) {                      // strided source planes -> tight pinned staging
+        for (int y = 0; y < rws[k]; y++) memcpy(p + (size_t)y * rb[k], src[k] + (size_t)y * srcStride[k], rb[k]);
+        p += (size_t)rb[k] * rws[k];
     }
     B2_CUDA_OK(cudaMemcpyAsync(c->d_in, c->h_in, c->in_bytes, cudaMemcpyHostToDevice, c->st));
     if (b2_launch_convert(c->fmt, c->d_in, c->in_bytes, c->d_y, c->d_u, c->d_v, c->pitch, c->pitchc, (size_t)c->pitch * c->rows,

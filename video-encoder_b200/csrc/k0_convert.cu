@@ -6,7 +6,8 @@
 // macroblock-aligned, border-padded planes the search kernels read.  Bit-exact against
 // oracle/b2o_convert.c (pinned by live libswscale golden vectors) followed by b2o_frame_load.
 //
-// Bound: HBM.  Algorithmic bytes per frame = input bytes (1.5*W*H for 4:2:0, 2*W*H for packed 4:2:2)
+// Row N4 adds bgr24 (bit-exact), rgb24, yuv422p and yuv411p (tolerance-pinned, see oracle/b2o_convert.c).
+// Bound: HBM.  Algorithmic bytes per frame = input bytes (1.5*W*H for 4:2:0, 2*W*H for 4:2:2, 3*W*H for RGB)
 // + 1.5*W16*H16 written.  Each thread produces 16 output pixels with 128-bit loads/stores when the
 // row is 16-byte aligned (all BASELINE.json resolutions), byte-wise otherwise.
 #include "b2_common.cuh"
@@ -59,6 +60,58 @@ k0_convert_kernel(K0Args a)
         const uint8_t *src = in + (size_t)a.w * a.h + (size_t)sy * (2 * cw) + (plane - 1);
 #pragma unroll
         for (int i = 0; i < 16; i++) px[i] = src[2 * min(x0 + i, pw - 1)];
+    } else if (a.fmt == B2_FMT_BGR24 || a.fmt == B2_FMT_RGB24) {
+        // row N4: 15-bit BT.601 limited-range coefficients.  bgr24 = libswscale's dedicated converter (bit-exact:
+        // truncating, chroma from the truncated 2x2 mean); rgb24 rounded, chroma from the 2x2 sum (tolerance-pinned)
+        const bool exact = a.fmt == B2_FMT_BGR24;
+        const int ro = exact ? 2 : 0, bo = 2 - ro;
+        if (plane == 0) {
+            const uint8_t *src = in + (size_t)sy * (3 * a.w);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const uint8_t *p = src + 3 * min(x0 + i, pw - 1);
+                const int v = 8414 * p[ro] + 16519 * p[1] + 3208 * p[bo];
+                px[i] = (uint8_t)(exact ? (v >> 15) + 16 : (v + (16 << 15) + (1 << 14)) >> 15);
+            }
+        } else {
+            const uint8_t *l0 = in + (size_t)(2 * sy) * (3 * a.w), *l1 = in + (size_t)min(2 * sy + 1, a.h - 1) * (3 * a.w);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int x = min(x0 + i, pw - 1);
+                const uint8_t *p0 = l0 + 6 * x, *p1 = l1 + 6 * x;
+                int r = p0[ro] + p0[3 + ro] + p1[ro] + p1[3 + ro], g = p0[1] + p0[4] + p1[1] + p1[4];
+                int b = p0[bo] + p0[3 + bo] + p1[bo] + p1[3 + bo];
+                const int cr = plane == 1 ? -4865 : 14392, cg = plane == 1 ? -9528 : -12061, cb = plane == 1 ? 14392 : -2332;
+                if (exact) { r >>= 2; g >>= 2; b >>= 2; px[i] = (uint8_t)(((cr * r + cg * g + cb * b) >> 15) + 128); }
+                else px[i] = (uint8_t)((cr * r + cg * g + cb * b + (128 << 17) + (1 << 16)) >> 17);
+            }
+        }
+    } else if (a.fmt == B2_FMT_YUV422P || a.fmt == B2_FMT_YUV411P) {
+        // row N4: planar 4:2:2 / 4:1:1 (DV): luma copied, chroma = rounded mean of the two source lines; 4:1:1 is then
+        // doubled horizontally (even samples copied, odd samples the rounded mean of their neighbours)
+        const int scw = a.fmt == B2_FMT_YUV422P ? cw : (a.w + 3) >> 2;
+        if (plane == 0) {
+            const uint8_t *src = in + (size_t)sy * a.w;
+            if (x0 + 16 <= pw && (((uintptr_t)(src + x0)) & 15) == 0) {
+                *(uint4 *)px = *(const uint4 *)(src + x0);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; i++) px[i] = src[min(x0 + i, pw - 1)];
+            }
+        } else {
+            const uint8_t *pl = in + (size_t)a.w * a.h + (plane == 2 ? (size_t)scw * a.h : 0);
+            const uint8_t *l0 = pl + (size_t)(2 * sy) * scw, *l1 = pl + (size_t)min(2 * sy + 1, a.h - 1) * scw;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int x = min(x0 + i, pw - 1);
+                if (a.fmt == B2_FMT_YUV422P) px[i] = avg_r(l0[x], l1[x], 1);
+                else {
+                    const int k = x >> 1, k1 = min(k + 1, scw - 1);
+                    const int va = (l0[k] + l1[k] + 1) >> 1, vb = (l0[k1] + l1[k1] + 1) >> 1;
+                    px[i] = (uint8_t)((x & 1) ? (va + vb + 1) >> 1 : va);
+                }
+            }
+        }
     } else {                                           // packed 4:2:2
         const int yo = a.fmt == B2_FMT_YUYV422 ? 0 : 1, uo = a.fmt == B2_FMT_YUYV422 ? 1 : 0;
         if (plane == 0) {
@@ -87,8 +140,8 @@ int b2_launch_convert(int fmt, const uint8_t *d_in, size_t in_stride, uint8_t *d
     K0Args a;
     a.in = d_in; a.in_stride = in_stride; a.y = d_y; a.u = d_u; a.v = d_v; a.pitch = pitch; a.pitchc = pitchc;
     a.stride_y = stride_y; a.stride_c = stride_c; a.w = w; a.h = h; a.w16 = (w + 15) & ~15; a.h16 = (h + 15) & ~15; a.fmt = fmt;
-    if ((fmt == B2_FMT_YUYV422 || fmt == B2_FMT_UYVY422) && ((w | h) & 1)) {
-        fprintf(stderr, "b2enc: packed 4:2:2 input needs even width and height\n");
+    if (fmt < 0 || fmt >= B2_FMT_COUNT || !b2_fmt_size_ok(fmt, w, h)) {
+        fprintf(stderr, "b2enc: unsupported raw format / size for conversion (format %d, %dx%d; see b2_fmt_size_ok)\n", fmt, w, h);
         return -1;
     }
     dim3 block(128);
