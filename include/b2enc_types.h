@@ -84,8 +84,8 @@ typedef struct {
     uint32_t nnz_mask;      /* bit b (0-15 luma, 16-19 U AC, 20-23 V AC): block has a non-zero     */
                             /* level; bit 24 luma DC, bit 25 U DC, bit 26 V DC.  With the 8x8      */
                             /* transform bit 4q+k is the k-th interleaved quarter of 8x8 block q   */
-    b2_mv_t  mv8[3];        /* quarter-pel MVs of 8x8 quadrants 1..3 (inter MBs; all equal to      */
-                            /* {mvx,mvy} for P16x16)                                               */
+    b2_mv_t  mv8[3];        /* quarter-pel MVs of 8x8 quadrants 1..3 when part != B2_PART_16x16    */
+                            /* (zero otherwise: the whole MB moves by {mvx,mvy})                   */
     uint8_t  part;          /* B2_PART_* partition shape of an inter MB                            */
     uint8_t  transform8x8;  /* 1: the luma residual uses the 8x8 transform (transform_size_8x8_flag) */
     uint16_t i8_modes;      /* intra analysis with the 8x8 transform enabled: best B2_I4_* mode of 8x8 block k in    */

@@ -85,7 +85,8 @@ static int bs_of(const b2_mbinfo_t *mp, int pbx, int pby, const b2_mbinfo_t *mq,
 {
     if (mp->mb_type != B2_MB_P16x16 || mq->mb_type != B2_MB_P16x16) return mb_edge ? 4 : 3;
     if (blk_coded(mp, pbx, pby) || blk_coded(mq, qbx, qby)) return 2;
-    if (abs(mp->mvx - mq->mvx) >= 4 || abs(mp->mvy - mq->mvy) >= 4) return 1;
+    const b2_mv_t a = b2o_quad_mv(mp, (pbx >> 1) | ((pby >> 1) << 1)), b = b2o_quad_mv(mq, (qbx >> 1) | ((qby >> 1) << 1));
+    if (abs(a.x - b.x) >= 4 || abs(a.y - b.y) >= 4) return 1;
     return 0;
 }
 

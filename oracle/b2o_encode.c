@@ -44,9 +44,15 @@ void b2o_recon_inter_mb(const b2o_params_t *prm, const b2o_frame_t *cur, const b
     const uint8_t *sy = cur->y + (size_t)(mby * 16) * cur->pitch + mbx * 16;
     size_t offc = (size_t)(mby * 8) * recon->pitchc + mbx * 8;
     memset(coef, 0, sizeof(*coef));
-    b2o_mc_luma(ref->y, ref->pitch, mbx * 16, mby * 16, mi->mvx, mi->mvy, 16, 16, ry, recon->pitch);
-    b2o_mc_chroma(ref->u, ref->pitchc, mbx * 8, mby * 8, mi->mvx, mi->mvy, 8, 8, recon->u + offc, recon->pitchc);
-    b2o_mc_chroma(ref->v, ref->pitchc, mbx * 8, mby * 8, mi->mvx, mi->mvy, 8, 8, recon->v + offc, recon->pitchc);
+    for (int q = 0; q < 4; q++) {             /* inter prediction per 8x8 quadrant (all four vectors are equal for 16x16) */
+        const b2_mv_t mv = b2o_quad_mv(mi, q);
+        const int qx = (q & 1) * 8, qy = (q >> 1) * 8;
+        b2o_mc_luma(ref->y, ref->pitch, mbx * 16 + qx, mby * 16 + qy, mv.x, mv.y, 8, 8, ry + qy * recon->pitch + qx, recon->pitch);
+        b2o_mc_chroma(ref->u, ref->pitchc, mbx * 8 + qx / 2, mby * 8 + qy / 2, mv.x, mv.y, 4, 4,
+                      recon->u + offc + (qy / 2) * recon->pitchc + qx / 2, recon->pitchc);
+        b2o_mc_chroma(ref->v, ref->pitchc, mbx * 8 + qx / 2, mby * 8 + qy / 2, mv.x, mv.y, 4, 4,
+                      recon->v + offc + (qy / 2) * recon->pitchc + qx / 2, recon->pitchc);
+    }
     uint32_t mask = 0;
     /* transform size (row N1): like x264's non-RD analysis, the 8x8 transform is used when the 8x8-Hadamard cost of
      * the prediction error is below its 4x4-Hadamard cost; ry holds the motion-compensated prediction here */
@@ -124,13 +130,19 @@ void b2o_encode_frame(const b2o_params_t *prm, int frame_type,
     uint32_t *cinter = (uint32_t *)malloc(sizeof(uint32_t) * n);
     uint32_t *c8 = prm->transform8x8 ? (uint32_t *)malloc(sizeof(uint32_t) * n) : NULL;
     b2_mv_t *mvf = (b2_mv_t *)malloc(sizeof(b2_mv_t) * n), *mvq = (b2_mv_t *)malloc(sizeof(b2_mv_t) * n);
+    const int parts = prm->partitions && prm->subpel && frame_type == B2_FRAME_P;
+    b2_mv_t (*mv4)[4] = parts ? (b2_mv_t (*)[4])malloc(sizeof(b2_mv_t) * 4 * n) : NULL;
+    uint8_t *part = parts ? (uint8_t *)malloc(n) : NULL;
     memset(info, 0, sizeof(b2_mbinfo_t) * n);
 
     int do_intra = frame_type == B2_FRAME_I || prm->intra_in_p;
     if (do_intra) b2o_intra_analyse(cur, lambda, info, c16, c4, c8);
     if (frame_type == B2_FRAME_P) {
         b2o_me_fullpel(cur, ref, prm->merange, prev_mv, lambda, mvf, cinter);
-        if (prm->subpel) {
+        if (parts) {
+            b2o_me_subpel_part(cur, ref, mvf, prev_mv, lambda, part, mv4, cinter);
+            for (int i = 0; i < n; i++) mvq[i] = mv4[i][0];
+        } else if (prm->subpel) {
             b2o_me_subpel(cur, ref, mvf, prev_mv, lambda, mvq, cinter);
         } else {
             for (int i = 0; i < n; i++) {       /* SATD-domain cost at the full-pel winner */
@@ -154,6 +166,10 @@ void b2o_encode_frame(const b2o_params_t *prm, int frame_type,
         }
         if (frame_type == B2_FRAME_P && !(do_intra && ci < cinter[i])) {
             info[i].mb_type = B2_MB_P16x16; info[i].mvx = mvq[i].x; info[i].mvy = mvq[i].y; info[i].cost = cinter[i];
+            if (parts && part[i] != B2_PART_16x16) {
+                info[i].part = part[i];
+                for (int q = 1; q < 4; q++) info[i].mv8[q - 1] = mv4[i][q];
+            }
         } else {
             info[i].mb_type = (uint8_t)it; info[i].mvx = info[i].mvy = 0; info[i].cost = ci;
         }
@@ -167,5 +183,5 @@ void b2o_encode_frame(const b2o_params_t *prm, int frame_type,
         }
     if (prm->deblock) b2o_deblock_frame(recon, info, prm->qp);
     b2o_frame_extend(recon);
-    free(c16); free(c4); free(cinter); free(mvf); free(mvq); free(c8);
+    free(c16); free(c4); free(cinter); free(mvf); free(mvq); free(c8); free(mv4); free(part);
 }

@@ -74,3 +74,79 @@ void b2o_me_subpel(const b2o_frame_t *cur, const b2o_frame_t *ref, const b2_mv_t
             cost_out[i] = best;
         }
 }
+
+/* ---- sub-pel refinement with inter partitions (16x8, 8x16, 8x8) -----------------------------
+ * Same candidate pattern as b2o_me_subpel, evaluated per 8x8 quadrant:
+ *   stage 1: the 9 half-pel candidates; for every shape part P (16x16 | 16x8 top,bottom | 8x16 left,right | four 8x8)
+ *            cost_P[k] = sum of its quadrants' SATD + lambda*mvbits(mv_k - pmv), first minimum wins;
+ *   shape  : 16x16, 16x8, 8x16, 8x8 cost the sum of their parts + lambda * {0, 2, 2, 8} (mb_type / sub_mb_type bits
+ *            beyond P_L0_16x16), first minimum wins;
+ *   stage 2: every part of the chosen shape tries the 8 quarter-pel neighbours of ITS half-pel winner.
+ * All parts therefore stay within +-3 quarter-pels of the 16x16 full-pel vector (a local partition refinement; the
+ * full-pel search itself is per macroblock, BASELINE.json north_star).  For shape 16x16 the result equals b2o_me_subpel. */
+static const uint8_t part_quads[4][4] = {{0xf, 0, 0, 0}, {0x3, 0xc, 0, 0}, {0x5, 0xa, 0, 0}, {0x1, 0x2, 0x4, 0x8}};   /* quadrant masks per part */
+static const uint8_t part_count[4] = {1, 2, 2, 4};
+static const uint8_t part_bits[4] = {0, 2, 2, 8};
+
+static void quad_satd(const b2o_frame_t *cur, const b2o_frame_t *ref, int mbx, int mby, int mvx, int mvy, uint32_t out[4])
+{
+    uint8_t pred[256];
+    const uint8_t *c = cur->y + (size_t)(mby * 16) * cur->pitch + mbx * 16;
+    b2o_mc_luma(ref->y, ref->pitch, mbx * 16, mby * 16, mvx, mvy, 16, 16, pred, 16);
+    for (int q = 0; q < 4; q++)
+        out[q] = b2o_satd8x8(c + (q >> 1) * 8 * cur->pitch + (q & 1) * 8, cur->pitch, pred + (q >> 1) * 8 * 16 + (q & 1) * 8, 16);
+}
+
+void b2o_me_subpel_part(const b2o_frame_t *cur, const b2o_frame_t *ref, const b2_mv_t *mv_full, const b2_mv_t *pmv, int lambda,
+                        uint8_t *part_out, b2_mv_t (*mv_out)[4], uint32_t *cost_out)
+{
+    for (int mby = 0; mby < cur->mbh; mby++)
+        for (int mbx = 0; mbx < cur->mbw; mbx++) {
+            const int i = mby * cur->mbw + mbx;
+            b2_mv_t p = {0, 0};
+            if (pmv) p = pmv[i];
+            const int cx = mv_full[i].x * 4, cy = mv_full[i].y * 4;
+            uint32_t sq[9][4];
+            for (int k = 0; k < 9; k++)
+                quad_satd(cur, ref, mbx, mby, cx + 2 * b2o_subpel_offsets[k][0], cy + 2 * b2o_subpel_offsets[k][1], sq[k]);
+            /* stage 1: best half-pel candidate of every part of every shape */
+            uint32_t pc[4][4]; int pk[4][4];
+            uint32_t shape_cost[4]; int shape = 0;
+            for (int sh = 0; sh < 4; sh++) {
+                shape_cost[sh] = (uint32_t)lambda * part_bits[sh];
+                for (int a = 0; a < part_count[sh]; a++) {
+                    uint32_t best = 0xffffffffu; int bk = 0;
+                    for (int k = 0; k < 9; k++) {
+                        const int mx = cx + 2 * b2o_subpel_offsets[k][0], my = cy + 2 * b2o_subpel_offsets[k][1];
+                        uint32_t c = (uint32_t)lambda * (uint32_t)(b2o_mvbits(mx - p.x) + b2o_mvbits(my - p.y));
+                        for (int q = 0; q < 4; q++)
+                            if (part_quads[sh][a] & (1 << q)) c += sq[k][q];
+                        if (c < best) { best = c; bk = k; }
+                    }
+                    pc[sh][a] = best; pk[sh][a] = bk;
+                    shape_cost[sh] += best;
+                }
+                if (shape_cost[sh] < shape_cost[shape]) shape = sh;
+            }
+            /* stage 2: quarter-pel neighbours of each part's winner */
+            uint32_t total = (uint32_t)lambda * part_bits[shape];
+            for (int a = 0; a < part_count[shape]; a++) {
+                const int hx = cx + 2 * b2o_subpel_offsets[pk[shape][a]][0], hy = cy + 2 * b2o_subpel_offsets[pk[shape][a]][1];
+                uint32_t best = pc[shape][a]; int bx = hx, by = hy;
+                for (int k = 1; k < 9; k++) {
+                    const int mx = hx + b2o_subpel_offsets[k][0], my = hy + b2o_subpel_offsets[k][1];
+                    uint32_t s4[4];
+                    quad_satd(cur, ref, mbx, mby, mx, my, s4);
+                    uint32_t c = (uint32_t)lambda * (uint32_t)(b2o_mvbits(mx - p.x) + b2o_mvbits(my - p.y));
+                    for (int q = 0; q < 4; q++)
+                        if (part_quads[shape][a] & (1 << q)) c += s4[q];
+                    if (c < best) { best = c; bx = mx; by = my; }
+                }
+                total += best;
+                for (int q = 0; q < 4; q++)
+                    if (part_quads[shape][a] & (1 << q)) { mv_out[i][q].x = (int16_t)bx; mv_out[i][q].y = (int16_t)by; }
+            }
+            part_out[i] = (uint8_t)shape;
+            cost_out[i] = total;
+        }
+}

@@ -20,7 +20,7 @@ class Frame(C.Structure):
 
 
 class Params(C.Structure):
-    _fields_ = [("qp", C.c_int), ("merange", C.c_int), ("subpel", C.c_int), ("intra_in_p", C.c_int), ("deblock", C.c_int), ("transform8x8", C.c_int)]
+    _fields_ = [("qp", C.c_int), ("merange", C.c_int), ("subpel", C.c_int), ("intra_in_p", C.c_int), ("deblock", C.c_int), ("transform8x8", C.c_int), ("partitions", C.c_int)]
 
 
 MV = np.dtype([("x", "<i2"), ("y", "<i2")])
@@ -179,9 +179,9 @@ class Entropy:
         return self.buf[:n].tobytes()
 
 
-def encode_sequence(frames, w, h, qp=26, merange=16, subpel=1, intra_in_p=1, gop=32, fps=(30, 1), deblock=0, cabac=0, transform8x8=0):
+def encode_sequence(frames, w, h, qp=26, merange=16, subpel=1, intra_in_p=1, gop=32, fps=(30, 1), deblock=0, cabac=0, transform8x8=0, partitions=0):
     """frames: iterable of (y,u,v).  Returns (annexb_bytes, [recon OFrame], [info], [coef])."""
-    prm = Params(qp, merange, subpel, intra_in_p, deblock, transform8x8)
+    prm = Params(qp, merange, subpel, intra_in_p, deblock, transform8x8, partitions)
     ent = Entropy(w, h, qp, fps, deblock=deblock, cabac=cabac, transform8x8=transform8x8)
     out = bytearray()
     sc = b"\x00\x00\x00\x01"

@@ -81,3 +81,31 @@ def test_intra8x8_all_nine_modes_are_exercised(oracle):
     _, _, infos = _roundtrip(oracle, frames, w, h, qp=qp, merange=16, gop=2, cabac=1, deblock=1, transform8x8=1)
     modes = np.concatenate([((inf["i8_modes"][inf["mb_type"] == 3][:, None] >> (4 * np.arange(4))[None, :]) & 15).ravel() for inf in infos])
     assert set(modes.tolist()) == set(range(9))
+
+
+# ---- row N1: inter partitions 16x8 / 8x16 / 8x8 (local refinement around the 16x16 vector) ---------------------------
+from test_oracle_decode import shear_seq
+
+
+@pytest.mark.parametrize("cabac,t8", [(0, 0), (1, 0), (1, 1)])
+@pytest.mark.parametrize("w,h,qp,deblock", [(176, 144, 26, 1), (320, 240, 30, 1), (208, 160, 20, 0), (96, 80, 36, 1), (70, 54, 30, 1)])
+def test_partition_stream_decodes_to_oracle_recon(oracle, w, h, qp, deblock, cabac, t8):
+    """mb_type / sub_mb_type, directional + median MV prediction per partition, mvd contexts, per-partition luma and
+    chroma MC, boundary strengths from per-quadrant vectors: all pinned by the decoder round trip"""
+    frames = shear_seq(w, h, 5, seed=qp)
+    bs, recons, infos = _roundtrip(oracle, frames, w, h, qp=qp, merange=16, gop=32, cabac=cabac, deblock=deblock, transform8x8=t8,
+                                   partitions=1)
+    parts = np.bincount(np.concatenate([i["part"][i["mb_type"] == 0] for i in infos[1:]]), minlength=4)
+    assert np.all(parts[1:] > 0), "every partition shape must occur: %s" % parts
+    bs0, _, _ = _roundtrip(oracle, frames, w, h, qp=qp, merange=16, gop=32, cabac=cabac, deblock=deblock, transform8x8=t8)
+    assert len(bs) < len(bs0)                                  # on sheared content partitions must pay off
+
+
+def test_partitions_do_not_change_uniform_motion(oracle):
+    """a pure pan has nothing to gain: the stream with partitions enabled stays the 16x16 stream"""
+    w, h = 192, 112
+    frames = [oracle.synth_frame(w, h, t) for t in range(4)]
+    a, _, infos = _roundtrip(oracle, frames, w, h, qp=28, merange=16, gop=32, cabac=1, partitions=1)
+    b, _, _ = _roundtrip(oracle, frames, w, h, qp=28, merange=16, gop=32, cabac=1, partitions=0)
+    frac = np.mean(np.concatenate([i["part"][i["mb_type"] == 0] for i in infos[1:]]) != 0)
+    assert frac < 0.2 and len(a) <= len(b) * 1.02

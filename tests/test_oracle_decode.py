@@ -46,6 +46,26 @@ def coarse_seq(w, h, n, seed=0, scale=10, noise=1.0):
     return frames
 
 
+def shear_seq(w, h, n, seed=0, stripe=24, band=24):
+    """content whose vertical stripes / horizontal bands move by different quarter-pel amounts per frame: macroblocks
+    that straddle a boundary are better predicted with 8x16 / 16x8 / 8x8 partitions (row N1)"""
+    import cv2
+    rng = np.random.default_rng(seed)
+    b = rng.integers(0, 256, ((h + 64) // 5 + 8, (w + 64) // 5 + 8)).astype(np.float32)
+    B = cv2.resize(b, ((w + 64) * 4, (h + 64) * 4), interpolation=cv2.INTER_CUBIC)
+    X = np.arange(w); Y = np.arange(h)
+    sx = (X // stripe) % 3 - 1; sy = (Y // band) % 3 - 1              # -1, 0, +1 quarter-pels per frame
+    frames = []
+    for t in range(n):
+        xi = 4 * X + 64 + t * 2 * sx + 3 * t                           # common pan + per-stripe shear
+        yi = 4 * Y + 64 + t * 2 * sy + 2 * t
+        img = np.clip(B[np.ix_(yi, xi)] + rng.normal(0, 0.8, (h, w)), 0, 255).astype(np.uint8)
+        u = (img[::2, ::2] // 2 + 64).astype(np.uint8)[:(h + 1) // 2, :(w + 1) // 2]
+        v = (255 - img[::2, ::2] // 2 - 30).astype(np.uint8)[:(h + 1) // 2, :(w + 1) // 2]
+        frames.append((img, u, v))
+    return frames
+
+
 def _roundtrip(oracle, frames, w, h, **kw):
     bs, recons, infos, coefs = oracle.encode_sequence(frames, w, h, **kw)
     dec = oracle.decode_yuv(oracle.split_access_units(bs))

@@ -249,7 +249,7 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
             }
             for (int p = 0; p < 2; p++)
                 for (int r = 0; r < 2; r++) memset(e->nnz_c[p] + (mby * 2 + r) * cs + mbx * 2, 0, 2);
-            e->ref[mi] = -1; e->mv[mi].x = e->mv[mi].y = 0;
+            { b2_mv_t z = {0, 0}; b2h_fill_mv(e, mbx * 4, mby * 4, 4, 4, z, -1); }
             e->mbf[mi] = 0; e->cbp[mi] = 0; e->cmode[mi] = 0;
             int flags = intra ? B2H_MBF_INTRA : 0;
             if (m->mb_type == B2_MB_I16x16) flags |= B2H_MBF_I16;
@@ -257,29 +257,43 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
             if (t8) flags |= B2H_MBF_T8;
 
             if (!intra) {
-                int hasA, hasB, refA, refB;
-                b2_mv_t mvA, mvB;
-                b2_mv_t mvp = b2h_mv_pred16x16(e, mbx, mby, &hasA, &hasB, &mvA, &refA, &mvB, &refB);
-                b2_mv_t skipmv = mvp;
-                if (!hasA || !hasB || (refA == 0 && mvA.x == 0 && mvA.y == 0) || (refB == 0 && mvB.x == 0 && mvB.y == 0))
-                    skipmv.x = skipmv.y = 0;
-                e->ref[mi] = 0; e->mv[mi].x = m->mvx; e->mv[mi].y = m->mvy;
-                const int skip = m->cbp == 0 && m->mvx == skipmv.x && m->mvy == skipmv.y;
+                int skip = 0;
+                if (m->part == B2_PART_16x16 && m->cbp == 0) {
+                    const b2_mv_t skipmv = b2h_skip_mv(e, mbx, mby);
+                    skip = m->mvx == skipmv.x && m->mvy == skipmv.y;
+                    if (skip) b2h_fill_mv(e, mbx * 4, mby * 4, 4, 4, skipmv, 0);
+                }
                 cabac_encode(c, 11 + (nb.availA && !(nb.fA & B2H_MBF_SKIP)) + (nb.availB && !(nb.fB & B2H_MBF_SKIP)), skip);
                 if (skip) {
                     e->mbf[mi] = B2H_MBF_SKIP;
                     cabac_terminate(c, mi == nmb - 1);                  /* end_of_slice_flag */
                     continue;
                 }
-                cabac_encode(c, 14, 0); cabac_encode(c, 15, 0); cabac_encode(c, 16, 0);      /* P_L0_16x16 */
-                const int x4 = mbx * 4, y4 = mby * 4;
-                const int dx = m->mvx - mvp.x, dy = m->mvy - mvp.y;
-                for (int k = 0; k < 2; k++) {
-                    const int sum = (nb.availA ? e->mvd[k][y4 * ys + x4 - 1] : 0) + (nb.availB ? e->mvd[k][(y4 - 1) * ys + x4] : 0);
-                    cabac_mvd(c, k ? 47 : 40, sum, k ? dy : dx);
+                /* mb_type (Table 9-36, P slices): 16x16 "000", 8x8 "001", 16x8 "011", 8x16 "010" */
+                cabac_encode(c, 14, 0);
+                if (m->part == B2_PART_16x16 || m->part == B2_PART_8x8) { cabac_encode(c, 15, 0); cabac_encode(c, 16, m->part == B2_PART_8x8); }
+                else { cabac_encode(c, 15, 1); cabac_encode(c, 17, m->part == B2_PART_16x8); }
+                if (m->part == B2_PART_8x8)
+                    for (int k = 0; k < 4; k++) cabac_encode(c, 21, 1);                      /* sub_mb_type P_L0_8x8 */
+                {
+                    int px, py, pw, ph, dir;
+                    const int np = b2h_part_geom(m->part, 0, &px, &py, &pw, &ph, &dir);
+                    for (int a = 0; a < np; a++) {
+                        b2h_part_geom(m->part, a, &px, &py, &pw, &ph, &dir);
+                        const int x4 = mbx * 4 + px, y4 = mby * 4 + py;
+                        const b2_mv_t mv = b2h_mb_mv(m, px, py);
+                        const b2_mv_t mvp = b2h_mv_pred(e, x4, y4, pw, dir);
+                        const int d[2] = {mv.x - mvp.x, mv.y - mvp.y};
+                        for (int k = 0; k < 2; k++) {
+                            /* |mvd| of the 4x4 blocks left of / above the partition (0 outside the picture, in intra and skipped MBs) */
+                            const int sum = (x4 > 0 ? e->mvd[k][y4 * ys + x4 - 1] : 0) + (y4 > 0 ? e->mvd[k][(y4 - 1) * ys + x4] : 0);
+                            cabac_mvd(c, k ? 47 : 40, sum, d[k]);
+                        }
+                        const int ax = abs(d[0]) > 255 ? 255 : abs(d[0]), ay = abs(d[1]) > 255 ? 255 : abs(d[1]);
+                        for (int r = 0; r < ph; r++) { memset(e->mvd[0] + (y4 + r) * ys + x4, ax, (size_t)pw); memset(e->mvd[1] + (y4 + r) * ys + x4, ay, (size_t)pw); }
+                        b2h_fill_mv(e, x4, y4, pw, ph, mv, 0);
+                    }
                 }
-                const int ax = abs(dx) > 255 ? 255 : abs(dx), ay = abs(dy) > 255 ? 255 : abs(dy);
-                for (int r = 0; r < 4; r++) { memset(e->mvd[0] + (y4 + r) * ys + x4, ax, 4); memset(e->mvd[1] + (y4 + r) * ys + x4, ay, 4); }
             } else {
                 if (is_p) {
                     cabac_encode(c, 11 + (nb.availA && !(nb.fA & B2H_MBF_SKIP)) + (nb.availB && !(nb.fB & B2H_MBF_SKIP)), 0);

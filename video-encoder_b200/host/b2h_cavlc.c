@@ -231,13 +231,13 @@ b2h_entropy_t *b2h_entropy_create(int mbw, int mbh)
     e->nnz_c[0] = (uint8_t *)malloc(n * 4);
     e->nnz_c[1] = (uint8_t *)malloc(n * 4);
     e->i4 = (int8_t *)malloc(n * 16);
-    e->ref = (int8_t *)malloc(n);
-    e->mv = (b2_mv_t *)malloc(n * sizeof(b2_mv_t));
+    e->ref4 = (int8_t *)malloc(n * 16);
+    e->mv4 = (b2_mv_t *)malloc(n * 16 * sizeof(b2_mv_t));
     e->mbf = (uint8_t *)calloc(n, 1); e->cbp = (uint8_t *)calloc(n, 1); e->cmode = (uint8_t *)calloc(n, 1);
     e->mvd[0] = (uint8_t *)calloc(n, 16); e->mvd[1] = (uint8_t *)calloc(n, 16);
     e->rbsp_cap = n * 2048 + 4096;
     e->rbsp = (uint8_t *)malloc(e->rbsp_cap);
-    if (!e->nnz_y || !e->nnz_c[0] || !e->nnz_c[1] || !e->i4 || !e->ref || !e->mv || !e->rbsp || !e->mbf || !e->cbp || !e->cmode ||
+    if (!e->nnz_y || !e->nnz_c[0] || !e->nnz_c[1] || !e->i4 || !e->ref4 || !e->mv4 || !e->rbsp || !e->mbf || !e->cbp || !e->cmode ||
         !e->mvd[0] || !e->mvd[1]) {
         b2h_entropy_destroy(e);
         return NULL;
@@ -252,7 +252,7 @@ b2h_entropy_t *b2h_entropy_create(int mbw, int mbh)
 void b2h_entropy_destroy(b2h_entropy_t *e)
 {
     if (!e) return;
-    free(e->nnz_y); free(e->nnz_c[0]); free(e->nnz_c[1]); free(e->i4); free(e->ref); free(e->mv); free(e->rbsp);
+    free(e->nnz_y); free(e->nnz_c[0]); free(e->nnz_c[1]); free(e->i4); free(e->ref4); free(e->mv4); free(e->rbsp);
     free(e->mbf); free(e->cbp); free(e->cmode); free(e->mvd[0]); free(e->mvd[1]);
     free(e);
 }
@@ -339,26 +339,47 @@ static inline int median3(int a, int b, int c)
     return c < mn ? mn : (c > mx ? mx : c);
 }
 
-/* 8.4.1.3 median prediction for a 16x16 partition, single reference frame */
-b2_mv_t b2h_mv_pred16x16(const b2h_entropy_t *e, int mbx, int mby, int *availA, int *availB,
-                            b2_mv_t *mvA_o, int *refA_o, b2_mv_t *mvB_o, int *refB_o)
+b2_mv_t b2h_mv_pred(const b2h_entropy_t *e, int x4, int y4, int w4, int dir)
 {
-    const int w = e->mbw;
+    const int st = 4 * e->mbw;
     b2_mv_t z = {0, 0}, mvA = z, mvB = z, mvC = z;
     int refA = -1, refB = -1, refC = -1;
-    int hasA = mbx > 0, hasB = mby > 0, hasC = mby > 0 && mbx < w - 1;
-    if (hasA) { refA = e->ref[mby * w + mbx - 1]; mvA = e->mv[mby * w + mbx - 1]; }
-    if (hasB) { refB = e->ref[(mby - 1) * w + mbx]; mvB = e->mv[(mby - 1) * w + mbx]; }
-    if (hasC) { refC = e->ref[(mby - 1) * w + mbx + 1]; mvC = e->mv[(mby - 1) * w + mbx + 1]; }
-    else if (mby > 0 && mbx > 0) { hasC = 1; refC = e->ref[(mby - 1) * w + mbx - 1]; mvC = e->mv[(mby - 1) * w + mbx - 1]; }
-    *availA = hasA; *availB = hasB; *mvA_o = mvA; *refA_o = refA; *mvB_o = mvB; *refB_o = refB;
+    const int hasA = x4 > 0, hasB = y4 > 0;
+    /* C = block above and to the right of the partition; it must lie inside the picture and precede the partition in
+     * decoding order: always true in the macroblock row above, inside the current row only left of the MB's right edge */
+    int hasC = y4 > 0 && x4 + w4 < st && ((y4 & 3) == 0 || (x4 & 3) + w4 < 4);
+    if (hasA) { refA = e->ref4[y4 * st + x4 - 1]; mvA = e->mv4[y4 * st + x4 - 1]; }
+    if (hasB) { refB = e->ref4[(y4 - 1) * st + x4]; mvB = e->mv4[(y4 - 1) * st + x4]; }
+    if (hasC) { refC = e->ref4[(y4 - 1) * st + x4 + w4]; mvC = e->mv4[(y4 - 1) * st + x4 + w4]; }
+    else if (x4 > 0 && y4 > 0) { hasC = 1; refC = e->ref4[(y4 - 1) * st + x4 - 1]; mvC = e->mv4[(y4 - 1) * st + x4 - 1]; }   /* D */
+    if (dir == B2H_PRED_A && refA == 0) return mvA;
+    if (dir == B2H_PRED_B && refB == 0) return mvB;
+    if (dir == B2H_PRED_C && refC == 0) return mvC;
     if (!hasB && !hasC && hasA) { mvB = mvA; mvC = mvA; refB = refA; refC = refA; }
-    int n = (refA == 0) + (refB == 0) + (refC == 0);
+    const int n = (refA == 0) + (refB == 0) + (refC == 0);
     if (n == 1) return refA == 0 ? mvA : (refB == 0 ? mvB : mvC);
     b2_mv_t p;
     p.x = (int16_t)median3(mvA.x, mvB.x, mvC.x);
     p.y = (int16_t)median3(mvA.y, mvB.y, mvC.y);
     return p;
+}
+
+b2_mv_t b2h_skip_mv(const b2h_entropy_t *e, int mbx, int mby)
+{
+    const int st = 4 * e->mbw, x4 = 4 * mbx, y4 = 4 * mby;
+    b2_mv_t z = {0, 0};
+    if (mbx == 0 || mby == 0) return z;
+    const int iA = y4 * st + x4 - 1, iB = (y4 - 1) * st + x4;
+    if (e->ref4[iA] == 0 && e->mv4[iA].x == 0 && e->mv4[iA].y == 0) return z;
+    if (e->ref4[iB] == 0 && e->mv4[iB].x == 0 && e->mv4[iB].y == 0) return z;
+    return b2h_mv_pred(e, x4, y4, 4, B2H_PRED_MEDIAN);
+}
+
+void b2h_fill_mv(b2h_entropy_t *e, int x4, int y4, int w4, int h4, b2_mv_t mv, int ref)
+{
+    const int st = 4 * e->mbw;
+    for (int y = y4; y < y4 + h4; y++)
+        for (int x = x4; x < x4 + w4; x++) { e->mv4[y * st + x] = mv; e->ref4[y * st + x] = (int8_t)ref; }
 }
 
 void b2h_slice_header(bs_t *b, const b2h_seq_t *s, int is_p, int frame_num, int idr_pic_id)
@@ -429,21 +450,33 @@ static size_t write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, 
             for (int r = 0; r < 4; r++) { memset(e->nnz_y + (mby * 4 + r) * ys + mbx * 4, 0, 4); memset(e->i4 + (mby * 4 + r) * ys + mbx * 4, 2, 4); }
             for (int p = 0; p < 2; p++)
                 for (int r = 0; r < 2; r++) memset(e->nnz_c[p] + (mby * 2 + r) * cs + mbx * 2, 0, 2);
-            e->ref[mi] = -1; e->mv[mi].x = e->mv[mi].y = 0;
+            { b2_mv_t z = {0, 0}; b2h_fill_mv(e, mbx * 4, mby * 4, 4, 4, z, -1); }
 
             if (m->mb_type == B2_MB_P16x16) {
-                int hasA, hasB, refA, refB;
-                b2_mv_t mvA, mvB;
-                b2_mv_t mvp = b2h_mv_pred16x16(e, mbx, mby, &hasA, &hasB, &mvA, &refA, &mvB, &refB);
-                b2_mv_t skipmv = mvp;
-                if (!hasA || !hasB || (refA == 0 && mvA.x == 0 && mvA.y == 0) || (refB == 0 && mvB.x == 0 && mvB.y == 0))
-                    skipmv.x = skipmv.y = 0;
-                e->ref[mi] = 0; e->mv[mi].x = m->mvx; e->mv[mi].y = m->mvy;
-                if (m->cbp == 0 && m->mvx == skipmv.x && m->mvy == skipmv.y) { skip_run++; continue; }   /* P_Skip */
+                if (m->part == B2_PART_16x16 && m->cbp == 0) {
+                    const b2_mv_t skipmv = b2h_skip_mv(e, mbx, mby);
+                    if (m->mvx == skipmv.x && m->mvy == skipmv.y) {                          /* P_Skip */
+                        b2h_fill_mv(e, mbx * 4, mby * 4, 4, 4, skipmv, 0);
+                        skip_run++;
+                        continue;
+                    }
+                }
                 bs_ue(b, (uint32_t)skip_run); skip_run = 0;
-                bs_ue(b, 0);                                   /* mb_type P_L0_16x16 */
-                bs_se(b, m->mvx - mvp.x);
-                bs_se(b, m->mvy - mvp.y);
+                bs_ue(b, m->part);                             /* mb_type P_L0_16x16 / P_L0_L0_16x8 / P_L0_L0_8x16 / P_8x8 */
+                if (m->part == B2_PART_8x8)
+                    for (int k = 0; k < 4; k++) bs_ue(b, 0);   /* sub_mb_type P_L0_8x8 */
+                {
+                    int px, py, pw, ph, dir;
+                    const int np = b2h_part_geom(m->part, 0, &px, &py, &pw, &ph, &dir);
+                    for (int a = 0; a < np; a++) {             /* mvd_l0 per partition; ref_idx is not sent with one reference */
+                        b2h_part_geom(m->part, a, &px, &py, &pw, &ph, &dir);
+                        const b2_mv_t mv = b2h_mb_mv(m, px, py);
+                        const b2_mv_t mvp = b2h_mv_pred(e, mbx * 4 + px, mby * 4 + py, pw, dir);
+                        bs_se(b, mv.x - mvp.x);
+                        bs_se(b, mv.y - mvp.y);
+                        b2h_fill_mv(e, mbx * 4 + px, mby * 4 + py, pw, ph, mv, 0);
+                    }
+                }
                 bs_ue(b, e->cbp_code_inter[m->cbp]);
                 if (cbp_l && s->transform8x8) bs_put(b, 1, m->transform8x8 != 0);     /* transform_size_8x8_flag */
             } else {

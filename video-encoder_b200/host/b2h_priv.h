@@ -13,8 +13,8 @@ struct b2h_entropy {
     uint8_t *nnz_y;          /* [4mbh][4mbw] total_coeff of each luma 4x4                         */
     uint8_t *nnz_c[2];       /* [2mbh][2mbw] total_coeff of each chroma AC 4x4                    */
     int8_t *i4;              /* [4mbh][4mbw] intra4x4 pred mode (2 for non-I4x4 MBs)              */
-    int8_t *ref;             /* [mbh][mbw]   0 inter, -1 intra                                    */
-    b2_mv_t *mv;             /* [mbh][mbw]                                                        */
+    int8_t *ref4;            /* [4mbh][4mbw] reference index per 4x4: 0 inter, -1 intra           */
+    b2_mv_t *mv4;            /* [4mbh][4mbw] motion vector per 4x4                                */
     uint8_t cbp_code_intra[48], cbp_code_inter[48];
     uint8_t *rbsp;
     size_t rbsp_cap;
@@ -48,10 +48,34 @@ static inline void b2h_levels_mb(b2h_levels_t *lv, const b2_mbinfo_t *m, int mi,
     }
 }
 
-/* 8.4.1.3 median prediction for a 16x16 partition, single reference frame; also returns the A / B neighbours
- * (P_Skip inference 8.4.1.1) */
-b2_mv_t b2h_mv_pred16x16(const b2h_entropy_t *e, int mbx, int mby, int *availA, int *availB,
-                         b2_mv_t *mvA_o, int *refA_o, b2_mv_t *mvB_o, int *refB_o);
+/* Motion-vector prediction 8.4.1.3 (single reference frame) for the partition whose top-left 4x4 block is (x4,y4) in
+ * picture coordinates and that is w4 blocks wide.  dir: B2H_PRED_MEDIAN, or the directional rule of 16x8 / 8x16
+ * partitions (prefer neighbour A, B or C when it is inter).  The partitions of the macroblock being written must
+ * already be in the maps (b2h_fill_mv) in coding order. */
+enum { B2H_PRED_MEDIAN = 0, B2H_PRED_A = 1, B2H_PRED_B = 2, B2H_PRED_C = 3 };
+b2_mv_t b2h_mv_pred(const b2h_entropy_t *e, int x4, int y4, int w4, int dir);
+/* inferred motion vector of P_Skip (8.4.1.1) for macroblock (mbx,mby) */
+b2_mv_t b2h_skip_mv(const b2h_entropy_t *e, int mbx, int mby);
+void b2h_fill_mv(b2h_entropy_t *e, int x4, int y4, int w4, int h4, b2_mv_t mv, int ref);
+/* geometry of partition `idx` of shape `part` (B2_PART_*) inside the macroblock, in 4x4 units, and its prediction rule;
+ * returns the number of partitions of the shape */
+static inline int b2h_part_geom(int part, int idx, int *x, int *y, int *w, int *h, int *dir)
+{
+    switch (part) {
+    case B2_PART_16x8: *x = 0; *y = 2 * idx; *w = 4; *h = 2; *dir = idx ? B2H_PRED_A : B2H_PRED_B; return 2;
+    case B2_PART_8x16: *x = 2 * idx; *y = 0; *w = 2; *h = 4; *dir = idx ? B2H_PRED_C : B2H_PRED_A; return 2;
+    case B2_PART_8x8: *x = 2 * (idx & 1); *y = 2 * (idx >> 1); *w = 2; *h = 2; *dir = B2H_PRED_MEDIAN; return 4;
+    default: *x = 0; *y = 0; *w = 4; *h = 4; *dir = B2H_PRED_MEDIAN; return 1;
+    }
+}
+/* motion vector of the 8x8 quadrant that contains 4x4 block (x,y) of macroblock m */
+static inline b2_mv_t b2h_mb_mv(const b2_mbinfo_t *m, int x, int y)
+{
+    const int q = (x >> 1) | ((y >> 1) << 1);
+    b2_mv_t mv = {m->mvx, m->mvy};
+    if (q && m->part != B2_PART_16x16) mv = m->mv8[q - 1];
+    return mv;
+}
 /* slice_header() 7.3.3 up to and including the deblocking fields */
 void b2h_slice_header(bs_t *b, const b2h_seq_t *s, int is_p, int frame_num, int idr_pic_id);
 size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int frame_num, int idr_pic_id,
