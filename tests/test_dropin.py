@@ -4,7 +4,7 @@ encoder's, decodable, N-slot output == 1-slot output (T5)."""
 import os
 import numpy as np
 import pytest
-from test_oracle_decode import smooth_seq
+from test_oracle_decode import smooth_seq, shear_seq
 
 pytestmark = pytest.mark.gpu
 G = np.load(os.path.join(os.path.dirname(__file__), "golden", "sws_golden.npz"))
@@ -102,6 +102,21 @@ def test_reference_call_sequence_and_bitstream(oracle, b2, profile, profile_idc,
     assert len(dec) == n
     for i, (dy, du, dv) in enumerate(dec):
         assert np.array_equal(dy, recons[i].y[:h, :w]) and np.array_equal(du, recons[i].u[:h // 2, :w // 2])
+
+
+def test_dropin_high_profile_with_partitions(oracle, b2):
+    """everything of row N1 at once through the x264-mirror: CABAC + 8x8 transform + intra 8x8 + inter partitions"""
+    w, h, qp, gop, n = 176, 144, 28, 5, 10
+    frames = shear_seq(w, h, n, seed=12)
+    out = drive(b2, frames, w, h, preset="medium", tune="film", quality=qp, profile="high", i_keyint_max=gop, i_gop_slots=2,
+                b_transform_8x8=1, b_partitions=1)
+    bs = to_annexb(out, length_prefixed=True)
+    ref_bs, recons, infos, _ = oracle.encode_sequence(frames, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1), deblock=1, cabac=1,
+                                                      transform8x8=1, partitions=1)
+    assert bs == ref_bs
+    assert sum(int((i["part"] != 0).sum()) for i in infos) > 20
+    dec = oracle.decode_yuv(oracle.split_access_units(bs))
+    assert len(dec) == n and all(np.array_equal(d[0], r.y[:h, :w]) for d, r in zip(dec, recons))
 
 
 def test_slot_count_does_not_change_the_stream(b2):

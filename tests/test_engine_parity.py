@@ -4,20 +4,21 @@ MVs and costs (K2), intra costs and modes (K3), decisions, quantised levels, cbp
 reconstructed planes must all be bit-identical."""
 import numpy as np
 import pytest
-from test_oracle_decode import smooth_seq, coarse_seq
+from test_oracle_decode import smooth_seq, coarse_seq, shear_seq
 
 pytestmark = pytest.mark.gpu
 
 INFO_FIELDS = ["mb_type", "mvx", "mvy", "i16_mode", "chroma_mode", "cbp", "i4_mode", "cost", "nnz_mask", "mv8", "part", "transform8x8", "i8_modes"]
 
 
-def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="yuv420p", deblock=0, transform8x8=0, pack_levels=0):
+def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="yuv420p", deblock=0, transform8x8=0, pack_levels=0,
+                    partitions=0):
     """seqs: list (one per slot) of lists of (y,u,v) frames"""
     S, T = len(seqs), len(seqs[0])
     eng = b2.Engine(w, h, slots=S, fmt=fmt, ring=2, merange=R, qp=qp, subpel=subpel, intra_in_p=intra_in_p, deblock=deblock,
-                    transform8x8=transform8x8, pack_levels=pack_levels)
-    prm = oracle.Params(qp, R, subpel, intra_in_p, deblock, transform8x8)
-    stats = {"t8": 0, "coded4": 0, "i8": 0}
+                    transform8x8=transform8x8, pack_levels=pack_levels, partitions=partitions)
+    prm = oracle.Params(qp, R, subpel, intra_in_p, deblock, transform8x8, partitions)
+    stats = {"t8": 0, "coded4": 0, "i8": 0, "parts": np.zeros(4, int)}
     prev = [None] * S; prev_mv = [None] * S
     for t in range(T):
         for s in range(S):
@@ -45,6 +46,7 @@ def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="
             ry, ru, rv = eng.recon(s)
             assert np.array_equal(ry, rec.y), f"recon Y t={t} s={s}"
             assert np.array_equal(ru, rec.u) and np.array_equal(rv, rec.v), f"recon UV t={t} s={s}"
+            stats["parts"] += np.bincount(info_o["part"][info_o["mb_type"] == 0], minlength=4)
             stats["t8"] += int(info_o["transform8x8"].sum()); stats["i8"] += int((info_o["mb_type"] == 3).sum())
             stats["coded4"] += int(((info_o["mb_type"] == 0) & (info_o["transform8x8"] == 0) & ((info_o["cbp"] & 15) != 0)).sum())
             prev[s] = rec
@@ -120,6 +122,15 @@ def test_engine_intra8x8(oracle, b2, w, h, qp, scale, deblock, pack):
     stats = run_and_compare(oracle, b2, seqs, w, h, qp, 16, deblock=deblock, transform8x8=1, pack_levels=pack)
     if qp >= 36:
         assert stats["i8"] >= 8
+
+
+@pytest.mark.parametrize("w,h,qp,deblock,t8,pack", [(176, 144, 26, 1, 0, 0), (320, 240, 30, 1, 1, 1), (208, 160, 20, 0, 1, 0), (96, 80, 36, 1, 0, 1),
+                                                    (70, 54, 30, 1, 0, 0)])
+def test_engine_inter_partitions(oracle, b2, w, h, qp, deblock, t8, pack):
+    """row N1: K2 per-quadrant refinement + shape decision, K5 per-quadrant chroma MC, K8 vector-aware boundary strengths"""
+    seqs = [shear_seq(w, h, 4, seed=qp), shear_seq(w, h, 4, seed=qp + 1, stripe=40, band=16)]
+    stats = run_and_compare(oracle, b2, seqs, w, h, qp, 16, deblock=deblock, transform8x8=t8, pack_levels=pack, partitions=1)
+    assert np.all(stats["parts"][1:] > 0), stats["parts"]
 
 
 def _to_fmt(fmt, y, u, v):

@@ -143,14 +143,14 @@ def unpack_levels(info, packed):
 class EngineCfg(C.Structure):
     _fields_ = [("device", C.c_int), ("width", C.c_int), ("height", C.c_int), ("slots", C.c_int), ("in_fmt", C.c_int),
                 ("in_ring", C.c_int), ("merange", C.c_int), ("qp", C.c_int), ("subpel", C.c_int), ("intra_in_p", C.c_int),
-                ("profile", C.c_int), ("streams", C.c_int), ("deblock", C.c_int), ("transform8x8", C.c_int), ("pack_levels", C.c_int)]
+                ("profile", C.c_int), ("streams", C.c_int), ("deblock", C.c_int), ("transform8x8", C.c_int), ("partitions", C.c_int), ("pack_levels", C.c_int)]
 
 
 class Engine:
     """One GPU's encode-stage engine: `slots` closed GOPs / streams advanced in lock-step."""
 
     def __init__(self, width, height, slots=1, fmt="yuv420p", ring=1, merange=16, qp=26, subpel=1, intra_in_p=1,
-                 device=0, profile=0, streams=0, deblock=0, transform8x8=0, pack_levels=0):
+                 device=0, profile=0, streams=0, deblock=0, transform8x8=0, pack_levels=0, partitions=0):
         require_gpu()
         L = lib()
         L.b2_engine_create.restype = C.c_void_p
@@ -181,7 +181,7 @@ class Engine:
         L.b2_engine_kernel_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long)]
         self.L = L
         self.cfg = EngineCfg(device, width, height, slots, FMT[fmt] if isinstance(fmt, str) else fmt, ring, merange, qp,
-                             subpel, intra_in_p, profile, streams, deblock, transform8x8, pack_levels)
+                             subpel, intra_in_p, profile, streams, deblock, transform8x8, partitions, pack_levels)
         self.h = L.b2_engine_create(C.byref(self.cfg))
         if not self.h:
             raise RuntimeError("b2_engine_create failed")
@@ -316,7 +316,7 @@ class Param(C.Structure):
     _fields_ = [("i_width", C.c_int), ("i_height", C.c_int), ("b_annexb", C.c_int), ("i_fps_num", C.c_int), ("i_fps_den", C.c_int),
                 ("vui", _Vui), ("rc", _Rc), ("i_keyint_max", C.c_int), ("i_gop_slots", C.c_int), ("i_merange", C.c_int),
                 ("b_subpel", C.c_int), ("b_intra_in_p", C.c_int), ("i_device", C.c_int), ("i_csp_in", C.c_int),
-                ("b_deblocking_filter", C.c_int), ("b_cabac", C.c_int), ("b_transform_8x8", C.c_int)]
+                ("b_deblocking_filter", C.c_int), ("b_cabac", C.c_int), ("b_transform_8x8", C.c_int), ("b_partitions", C.c_int)]
 
 
 class Image(C.Structure):

@@ -54,6 +54,8 @@ struct b2_engine {
     b2_mv_t *d_mvf = nullptr, *d_mvq = nullptr, *d_prev_mv = nullptr;
     uint32_t *d_cost_full = nullptr, *d_cost_inter = nullptr, *d_c16 = nullptr, *d_c4 = nullptr, *d_c8 = nullptr;
     uint8_t *d_pred = nullptr;             // [S][nmb][256] motion-compensated luma prediction (K2 -> K5)
+    uint8_t *d_part = nullptr;             // cfg.partitions: [S][nmb] partition shape chosen by K2
+    b2_mv_t *d_mv8 = nullptr;              //                 [S][nmb][3] vectors of quadrants 1..3
     b2_mbinfo_t *d_info[2] = {}, *h_info[2] = {};
     b2_mbcoef_t *d_coef[2] = {}, *h_coef[2] = {};
     // cfg.pack_levels: packed level streams [S][pack_stride] per result set (device + pinned host), blocks used per slot
@@ -118,6 +120,10 @@ static int engine_alloc(b2_engine *e)
     ENG_OK(cudaMemset(e->d_cost_full, 0, n * 4)); ENG_OK(cudaMemset(e->d_cost_inter, 0, n * 4));
     ENG_OK(cudaMemset(e->d_c16, 0, n * 4)); ENG_OK(cudaMemset(e->d_c4, 0, n * 4));
     if (c.transform8x8) { ENG_OK(cudaMalloc(&e->d_c8, n * 4)); ENG_OK(cudaMemset(e->d_c8, 0, n * 4)); }
+    if (c.partitions && c.subpel) {
+        ENG_OK(cudaMalloc(&e->d_part, n)); ENG_OK(cudaMemset(e->d_part, 0, n));
+        ENG_OK(cudaMalloc(&e->d_mv8, n * 3 * sizeof(b2_mv_t))); ENG_OK(cudaMemset(e->d_mv8, 0, n * 3 * sizeof(b2_mv_t)));
+    }
     for (int s = 0; s < 2; s++) {
         ENG_OK(cudaMalloc(&e->d_info[s], n * sizeof(b2_mbinfo_t)));
         ENG_OK(cudaMalloc(&e->d_coef[s], n * sizeof(b2_mbcoef_t)));
@@ -207,7 +213,7 @@ extern "C" void b2_engine_destroy(b2_engine_t *e)
     cudaFree(e->d_in); cudaFreeHost(e->h_in);
     for (int p = 0; p < 3; p++) { cudaFree(e->d_cur[p]); cudaFree(e->d_rec[0][p]); cudaFree(e->d_rec[1][p]); }
     cudaFree(e->d_mvf); cudaFree(e->d_mvq); cudaFree(e->d_prev_mv); cudaFree(e->d_cost_full); cudaFree(e->d_cost_inter);
-    cudaFree(e->d_c16); cudaFree(e->d_c4); cudaFree(e->d_c8); cudaFree(e->d_pred);
+    cudaFree(e->d_c16); cudaFree(e->d_c4); cudaFree(e->d_c8); cudaFree(e->d_pred); cudaFree(e->d_part); cudaFree(e->d_mv8);
     for (int s = 0; s < 2; s++) {
         cudaFree(e->d_info[s]); cudaFree(e->d_coef[s]); cudaFreeHost(e->h_info[s]); cudaFreeHost(e->h_coef[s]);
         cudaFree(e->d_pack[s]); cudaFreeHost(e->h_pack[s]); cudaFree(e->d_pack_n[s]); cudaFreeHost(e->h_pack_n[s]);
@@ -369,7 +375,8 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
         {
             KScope k(e, st, 3);
             if (b2_launch_me_subpel(cur[0], ref[0], e->pitch, e->stride_y, e->mbw, e->mbh, ns, e->d_mvf + om, e->d_prev_mv + om,
-                                    e->lambda, c.subpel, e->d_mvq + om, e->d_cost_inter + om, e->d_pred + om * 256, st))
+                                    e->lambda, c.subpel, e->d_mvq + om, e->d_cost_inter + om, e->d_pred + om * 256,
+                                    e->d_part ? e->d_part + om : nullptr, e->d_mv8 ? e->d_mv8 + om * 3 : nullptr, st))
                 return -1;
         }
     }
@@ -383,7 +390,8 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
         KScope k(e, st, 5);
         if (b2_launch_decide_inter(cur, ref, rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, ns, is_p, do_intra,
                                    c.qp, e->d_mvq + om, e->d_cost_inter + om, e->d_c16 + om, e->d_c4 + om, e->d_c8 ? e->d_c8 + om : nullptr, info, coef,
-                                   e->d_prev_mv + om, e->d_pred + om * 256, c.transform8x8, st))
+                                   e->d_prev_mv + om, e->d_pred + om * 256, c.transform8x8, e->d_part ? e->d_part + om : nullptr,
+                                   e->d_mv8 ? e->d_mv8 + om * 3 : nullptr, st))
             return -1;
     }
     if (do_intra) {

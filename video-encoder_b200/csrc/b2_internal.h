@@ -20,7 +20,8 @@ int b2_launch_convert(int fmt, const uint8_t *d_in, size_t in_stride, uint8_t *d
                       int pitchc, size_t stride_y, size_t stride_c, int w, int h, int nframes, cudaStream_t st);
 int b2_launch_me_subpel(const uint8_t *d_cur, const uint8_t *d_ref, int pitch, size_t plane_stride, int mbw, int mbh,
                         int nframes, const b2_mv_t *d_mv_full, const b2_mv_t *d_pmv, int lambda, int subpel,
-                        b2_mv_t *d_mv_out, uint32_t *d_cost_out, uint8_t *d_pred_out, cudaStream_t st);
+                        b2_mv_t *d_mv_out, uint32_t *d_cost_out, uint8_t *d_pred_out, uint8_t *d_part_out /* NULL: 16x16 only */,
+                        b2_mv_t *d_mv8_out /* [nmb][3] */, cudaStream_t st);
 int b2_launch_intra_analyse(const uint8_t *d_y, const uint8_t *d_u, const uint8_t *d_v, int pitch, int pitchc,
                             size_t stride_y, size_t stride_c, int mbw, int mbh, int nframes, int lambda,
                             b2_mbinfo_t *d_info, uint32_t *d_c16, uint32_t *d_c4, uint32_t *d_c8 /* NULL: no I8x8 analysis */,
@@ -29,7 +30,7 @@ int b2_launch_decide_inter(const uint8_t *const cur[3], const uint8_t *const ref
                            int pitchc, size_t stride_y, size_t stride_c, int mbw, int mbh, int nframes, int is_p,
                            int do_intra, int qp, const b2_mv_t *d_mvq, const uint32_t *d_cost_inter, const uint32_t *d_c16,
                            const uint32_t *d_c4, const uint32_t *d_c8, b2_mbinfo_t *d_info, b2_mbcoef_t *d_coef, b2_mv_t *d_prev_mv,
-                           const uint8_t *d_pred_y, int transform8x8, cudaStream_t st);
+                           const uint8_t *d_pred_y, int transform8x8, const uint8_t *d_part, const b2_mv_t *d_mv8, cudaStream_t st);
 int b2_launch_intra_recon(const uint8_t *const cur[3], uint8_t *const rec[3], int pitch, int pitchc, size_t stride_y,
                           size_t stride_c, int mbw, int mbh, int nframes, int qp, int all_intra, b2_mbinfo_t *d_info,
                           b2_mbcoef_t *d_coef, cudaStream_t st);

@@ -32,7 +32,20 @@ struct K2Smem {
     uint8_t cur[16][16];
     uint32_t cost[9];
     int best;
+    // inter partitions (row N1): SATD per candidate and 8x8 quadrant, winners per shape part, final quadrant vectors
+    uint32_t costq[9][4];
+    uint32_t pcost[9];        // best stage-1 cost of part p: 0 16x16 | 1,2 16x8 top,bottom | 3,4 8x16 left,right | 5..8 quadrants
+    int pk[9];                // its half-pel candidate
+    int shape;
+    int qk[4];                // half-pel winner (candidate index) of the chosen shape's part that owns quadrant q
+    int qmv[4];               // final displacement of quadrant q from the full-pel position: (dx & 0xff) | (dy & 0xff) << 8
 };
+
+// quadrant masks of the nine shape parts and the parts of each shape
+__device__ __constant__ uint8_t c_part_mask[9] = {0xf, 0x3, 0xc, 0x5, 0xa, 0x1, 0x2, 0x4, 0x8};
+__device__ __constant__ uint8_t c_shape_first[4] = {0, 1, 3, 5};
+__device__ __constant__ uint8_t c_shape_n[4] = {1, 2, 2, 4};
+__device__ __constant__ uint8_t c_shape_bits[4] = {0, 2, 2, 8};
 
 // byte offset inside K2Smem::P of sample (X,Y) of plane p (0 G, 1 b, 2 h, 3 j)
 __device__ __forceinline__ int plane_off(int p, int X, int Y)
@@ -84,11 +97,12 @@ __device__ __forceinline__ uint32_t cand_block_satd(const K2Smem &s, int blk, in
     return b2::satd4x4(d);
 }
 
+template <bool PART>
 __global__ void __launch_bounds__(K2_THREADS)
 k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ ref, int pitch, size_t plane_stride,
                     int mbw, int mbh, const b2_mv_t *__restrict__ mv_full, const b2_mv_t *__restrict__ pmv,
                     int lambda, int subpel, b2_mv_t *__restrict__ mv_out, uint32_t *__restrict__ cost_out,
-                    uint8_t *__restrict__ pred_out)
+                    uint8_t *__restrict__ pred_out, uint8_t *__restrict__ part_out, b2_mv_t *__restrict__ mv8_out)
 {
     __shared__ __align__(16) K2Smem s;
     const int tid = threadIdx.x;
@@ -113,6 +127,7 @@ k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__
         *(uint32_t *)&s.cur[r][c * 4] = *(const uint32_t *)(cplane + (size_t)r * pitch + c * 4);
     }
     if (tid < 9) s.cost[tid] = 0;
+    if (PART && tid < 36) s.costq[tid >> 2][tid & 3] = 0;
     __syncthreads();
 
     // horizontal unrounded half samples b1 (22 rows x 17 cols) and vertical half samples h (17 rows x 18 cols)
@@ -145,6 +160,85 @@ k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__
     }
     __syncthreads();
 
+    if (PART) {
+        // ---- partitions: SATD per (candidate, quadrant); every shape part picks its half-pel winner, the cheapest shape
+        // is kept and each of its parts tries the 8 quarter-pel neighbours of ITS winner (oracle: b2o_me_subpel_part) ----
+        if (tid < 9 * 16) {
+            const int cand = tid >> 4, blk = tid & 15;
+            const uint32_t v = cand_block_satd(s, blk, 2 * c_subpel_off[cand][0], 2 * c_subpel_off[cand][1]);
+            atomicAdd(&s.costq[cand][((blk >> 1) & 1) | ((blk >> 3) << 1)], v);
+        }
+        __syncthreads();
+        if (tid < 9) {                                   // one thread per shape part
+            const int mask = c_part_mask[tid];
+            uint32_t best = 0xffffffffu; int bk = 0;
+            for (int k = 0; k < 9; k++) {
+                const int mx = mvf.x * 4 + 2 * c_subpel_off[k][0], my = mvf.y * 4 + 2 * c_subpel_off[k][1];
+                uint32_t c = (uint32_t)(lambda * (b2_mvbits(mx - pm.x) + b2_mvbits(my - pm.y)));
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (mask & (1 << q)) c += s.costq[k][q];
+                if (c < best) { best = c; bk = k; }
+            }
+            s.pcost[tid] = best; s.pk[tid] = bk;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t bc = 0xffffffffu; int shape = 0;
+            for (int sh = 0; sh < 4; sh++) {
+                uint32_t c = (uint32_t)(lambda * c_shape_bits[sh]);
+                for (int a = 0; a < c_shape_n[sh]; a++) c += s.pcost[c_shape_first[sh] + a];
+                if (c < bc) { bc = c; shape = sh; }
+            }
+            s.shape = shape;
+            for (int a = 0; a < c_shape_n[shape]; a++) {
+                const int p = c_shape_first[shape] + a;
+                for (int q = 0; q < 4; q++)
+                    if (c_part_mask[p] & (1 << q)) s.qk[q] = s.pk[p];
+            }
+        }
+        if (tid < 36) s.costq[tid >> 2][tid & 3] = 0;    // reused for stage 2 (entries 1..8); stage-1 sums are folded into pcost
+        __syncthreads();
+        if (tid < 8 * 16) {
+            const int cand = 1 + (tid >> 4), blk = tid & 15, q = ((blk >> 1) & 1) | ((blk >> 3) << 1);
+            const int hk = s.qk[q];
+            const uint32_t v = cand_block_satd(s, blk, 2 * c_subpel_off[hk][0] + c_subpel_off[cand][0], 2 * c_subpel_off[hk][1] + c_subpel_off[cand][1]);
+            atomicAdd(&s.costq[cand][q], v);
+        }
+        __syncthreads();
+        if (tid < c_shape_n[s.shape]) {                   // one thread per part of the chosen shape
+            const int p = c_shape_first[s.shape] + tid, mask = c_part_mask[p], hk = s.pk[p];
+            const int hx = 2 * c_subpel_off[hk][0], hy = 2 * c_subpel_off[hk][1];
+            uint32_t best = s.pcost[p]; int bx = hx, by = hy;
+            for (int k = 1; k < 9; k++) {
+                const int dx = hx + c_subpel_off[k][0], dy = hy + c_subpel_off[k][1];
+                uint32_t c = (uint32_t)(lambda * (b2_mvbits(mvf.x * 4 + dx - pm.x) + b2_mvbits(mvf.y * 4 + dy - pm.y)));
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (mask & (1 << q)) c += s.costq[k][q];
+                if (c < best) { best = c; bx = dx; by = dy; }
+            }
+            s.pcost[p] = best;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (mask & (1 << q)) s.qmv[q] = (bx & 0xff) | ((by & 0xff) << 8);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int shape = s.shape;
+            uint32_t total = (uint32_t)(lambda * c_shape_bits[shape]);
+            for (int a = 0; a < c_shape_n[shape]; a++) total += s.pcost[c_shape_first[shape] + a];
+            cost_out[mbi] = total;
+            part_out[mbi] = (uint8_t)shape;
+            for (int q = 0; q < 4; q++) {
+                b2_mv_t o;
+                o.x = (int16_t)(mvf.x * 4 + (int)(int8_t)(s.qmv[q] & 0xff));
+                o.y = (int16_t)(mvf.y * 4 + (int)(int8_t)((s.qmv[q] >> 8) & 0xff));
+                if (q == 0) mv_out[mbi] = o;
+                else mv8_out[mbi * 3 + q - 1] = o;
+            }
+        }
+    } else {
     // stage 1: centre + 8 half-pel neighbours (offsets x2 quarter units); without sub-pel: centre only
     const int n1 = subpel ? 9 : 1;
     if (tid < n1 * 16) {
@@ -189,14 +283,17 @@ k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__
         cost_out[mbi] = best;
         s.best = ((bx - mvf.x * 4) & 0xff) | (((by - mvf.y * 4) & 0xff) << 8);     // winner relative to the full-pel position
     }
+    if (tid == 0) { s.qmv[0] = s.qmv[1] = s.qmv[2] = s.qmv[3] = s.best; }
+    }
     // the winner's motion-compensated luma block (K5 subtracts it from the source instead of interpolating again)
     if (pred_out != nullptr) {
         __syncthreads();
-        const int cx = (int)(int8_t)(s.best & 0xff), cy = (int)(int8_t)((s.best >> 8) & 0xff);
-        const int ix = cx >> 2, iy = cy >> 2;
-        const int e = c_qpel_pair[(cy & 3) * 4 + (cx & 3)];
         if (tid < 64) {                                               // 4 pixels per thread: row r, columns 4c..4c+3
             const int r = tid >> 2, c = (tid & 3) * 4;
+            const int qm = s.qmv[(c >> 3) | ((r >> 3) << 1)];         // displacement of the quadrant this word lies in
+            const int cx = (int)(int8_t)(qm & 0xff), cy = (int)(int8_t)((qm >> 8) & 0xff);
+            const int ix = cx >> 2, iy = cy >> 2;
+            const int e = c_qpel_pair[(cy & 3) * 4 + (cx & 3)];
             const uint8_t *pa = s.P + plane_off(e & 3, c + ix + ((e >> 2) & 1), r + iy + ((e >> 3) & 1));
             const uint8_t *pb = s.P + plane_off((e >> 4) & 3, c + ix + ((e >> 6) & 1), r + iy + ((e >> 7) & 1));
             uint32_t w = 0;
@@ -211,11 +308,16 @@ k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__
 
 int b2_launch_me_subpel(const uint8_t *d_cur, const uint8_t *d_ref, int pitch, size_t plane_stride, int mbw, int mbh,
                         int nframes, const b2_mv_t *d_mv_full, const b2_mv_t *d_pmv, int lambda, int subpel,
-                        b2_mv_t *d_mv_out, uint32_t *d_cost_out, uint8_t *d_pred_out, cudaStream_t st)
+                        b2_mv_t *d_mv_out, uint32_t *d_cost_out, uint8_t *d_pred_out, uint8_t *d_part_out, b2_mv_t *d_mv8_out,
+                        cudaStream_t st)
 {
     dim3 grid(mbw, mbh, nframes);
-    k2_me_subpel_kernel<<<grid, K2_THREADS, 0, st>>>(d_cur, d_ref, pitch, plane_stride, mbw, mbh, d_mv_full, d_pmv,
-                                                     lambda, subpel, d_mv_out, d_cost_out, d_pred_out);
+    if (d_part_out && subpel)
+        k2_me_subpel_kernel<true><<<grid, K2_THREADS, 0, st>>>(d_cur, d_ref, pitch, plane_stride, mbw, mbh, d_mv_full, d_pmv,
+                                                               lambda, subpel, d_mv_out, d_cost_out, d_pred_out, d_part_out, d_mv8_out);
+    else
+        k2_me_subpel_kernel<false><<<grid, K2_THREADS, 0, st>>>(d_cur, d_ref, pitch, plane_stride, mbw, mbh, d_mv_full, d_pmv,
+                                                                lambda, subpel, d_mv_out, d_cost_out, d_pred_out, nullptr, nullptr);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
 }

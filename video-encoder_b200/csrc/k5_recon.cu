@@ -141,7 +141,7 @@ k5_decide_inter_kernel(FramePlanes fp, int mbw, int mbh, int nmb_total, int is_p
                        const b2_mv_t *__restrict__ mvq, const uint32_t *__restrict__ cost_inter,
                        const uint32_t *__restrict__ c16, const uint32_t *__restrict__ c4, const uint32_t *__restrict__ c8,
                        b2_mbinfo_t *__restrict__ info, b2_mbcoef_t *__restrict__ coef, b2_mv_t *__restrict__ prev_mv_out,
-                       const uint8_t *__restrict__ pred_y)
+                       const uint8_t *__restrict__ pred_y, const uint8_t *__restrict__ part, const b2_mv_t *__restrict__ mv8)
 {
     const int lane = threadIdx.x & 31;
     const int mbi = blockIdx.x * K5_WARPS + (threadIdx.x >> 5);
@@ -162,7 +162,13 @@ k5_decide_inter_kernel(FramePlanes fp, int mbw, int mbh, int nmb_total, int is_p
     const bool inter = is_p && !(do_intra && ci < cinter);
     b2_mv_t mv = {0, 0};
     if (inter) mv = mvq[mbi];
+    // inter partitions (row N1): K2 chose the shape and one vector per 8x8 quadrant; quadrant 0 is `mv`
+    const int shape = (inter && part != nullptr) ? part[mbi] : B2_PART_16x16;
     if (lane == 0) {
+        if (shape != B2_PART_16x16) {
+            info[mbi].part = (uint8_t)shape;
+            info[mbi].mv8[0] = mv8[(size_t)mbi * 3 + 0]; info[mbi].mv8[1] = mv8[(size_t)mbi * 3 + 1]; info[mbi].mv8[2] = mv8[(size_t)mbi * 3 + 2];
+        }
         info[mbi].mvx = mv.x; info[mbi].mvy = mv.y;
         info[mbi].mb_type = (uint8_t)(inter ? B2_MB_P16x16 : it);
         info[mbi].cost = inter ? cinter : ci;
@@ -224,8 +230,10 @@ k5_decide_inter_kernel(FramePlanes fp, int mbw, int mbh, int nmb_total, int is_p
         const size_t off = (size_t)(B2_PADC + mby * 8 + cby) * fp.pitchc + B2_PADC + mbx * 8 + cbx;
         if (act) {
             load_src4x4(fp.cur[1 + pl] + frame * fp.stride_c + off, fp.pitchc, src);
-            const uint8_t *rp = fp.ref[1 + pl] + frame * fp.stride_c + off + (ptrdiff_t)(mv.y >> 3) * fp.pitchc + (mv.x >> 3);
-            const int fx = mv.x & 7, fy = mv.y & 7;
+            // chroma 4x4 block k lies under luma quadrant k and moves with that quadrant's vector
+            const b2_mv_t cmv = (shape != B2_PART_16x16 && k > 0) ? mv8[(size_t)mbi * 3 + k - 1] : mv;
+            const uint8_t *rp = fp.ref[1 + pl] + frame * fp.stride_c + off + (ptrdiff_t)(cmv.y >> 3) * fp.pitchc + (cmv.x >> 3);
+            const int fx = cmv.x & 7, fy = cmv.y & 7;
 #pragma unroll
             for (int y = 0; y < 4; y++)
 #pragma unroll
@@ -261,7 +269,7 @@ int b2_launch_decide_inter(const uint8_t *const cur[3], const uint8_t *const ref
                            int pitchc, size_t stride_y, size_t stride_c, int mbw, int mbh, int nframes, int is_p,
                            int do_intra, int qp, const b2_mv_t *d_mvq, const uint32_t *d_cost_inter, const uint32_t *d_c16,
                            const uint32_t *d_c4, const uint32_t *d_c8, b2_mbinfo_t *d_info, b2_mbcoef_t *d_coef, b2_mv_t *d_prev_mv,
-                           const uint8_t *d_pred_y, int transform8x8, cudaStream_t st)
+                           const uint8_t *d_pred_y, int transform8x8, const uint8_t *d_part, const b2_mv_t *d_mv8, cudaStream_t st)
 {
     FramePlanes fp;
     for (int i = 0; i < 3; i++) { fp.cur[i] = cur[i]; fp.ref[i] = ref ? ref[i] : nullptr; fp.rec[i] = rec[i]; }
@@ -269,10 +277,10 @@ int b2_launch_decide_inter(const uint8_t *const cur[3], const uint8_t *const ref
     const int nmb = mbw * mbh * nframes;
     if (transform8x8)
         k5_decide_inter_kernel<true><<<(nmb + K5_WARPS - 1) / K5_WARPS, K5_WARPS * 32, 0, st>>>(
-            fp, mbw, mbh, nmb, is_p, do_intra, qp, d_mvq, d_cost_inter, d_c16, d_c4, d_c8, d_info, d_coef, d_prev_mv, d_pred_y);
+            fp, mbw, mbh, nmb, is_p, do_intra, qp, d_mvq, d_cost_inter, d_c16, d_c4, d_c8, d_info, d_coef, d_prev_mv, d_pred_y, d_part, d_mv8);
     else
         k5_decide_inter_kernel<false><<<(nmb + K5_WARPS - 1) / K5_WARPS, K5_WARPS * 32, 0, st>>>(
-            fp, mbw, mbh, nmb, is_p, do_intra, qp, d_mvq, d_cost_inter, d_c16, d_c4, nullptr, d_info, d_coef, d_prev_mv, d_pred_y);
+            fp, mbw, mbh, nmb, is_p, do_intra, qp, d_mvq, d_cost_inter, d_c16, d_c4, nullptr, d_info, d_coef, d_prev_mv, d_pred_y, d_part, d_mv8);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -111,7 +111,10 @@ __device__ __forceinline__ int bs_of(const b2_mbinfo_t *mp, int pbx, int pby, co
 {
     if (mp->mb_type != B2_MB_P16x16 || mq->mb_type != B2_MB_P16x16) return mb_edge ? 4 : 3;
     if (blk_coded(mp, pbx, pby) || blk_coded(mq, qbx, qby)) return 2;
-    if (abs(mp->mvx - mq->mvx) >= 4 || abs(mp->mvy - mq->mvy) >= 4) return 1;
+    const int pq = (pbx >> 1) | ((pby >> 1) << 1), qq = (qbx >> 1) | ((qby >> 1) << 1);      // 8x8 quadrants: one vector each
+    const b2_mv_t a = (pq && mp->part != B2_PART_16x16) ? mp->mv8[pq - 1] : b2_mv_t{mp->mvx, mp->mvy};
+    const b2_mv_t b = (qq && mq->part != B2_PART_16x16) ? mq->mv8[qq - 1] : b2_mv_t{mq->mvx, mq->mvy};
+    if (abs(a.x - b.x) >= 4 || abs(a.y - b.y) >= 4) return 1;
     return 0;
 }
 
