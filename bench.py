@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--deblock", type=int, default=0, help="1: also run the in-loop deblocking filter K8 (row N2, outside the named path)")
     ap.add_argument("--pack-levels", type=int, default=1, help="1: levels leave the GPU packed (K9: only blocks with a non-zero level); "
                     "0: dense 832 B/MB array")
+    ap.add_argument("--partitions", type=int, default=0, help="1: inter partitions 16x8/8x16/8x8 (row N1, outside the named path)")
     ap.add_argument("--transform8x8", type=int, default=0, help="1: adaptive 8x8 transform for inter MBs (row N1, outside the named path)")
     args = ap.parse_args()
     select_workload(args.workload)
@@ -248,7 +249,7 @@ def main():
 
     eng = b2enc.Engine(W, H, slots=SLOTS, fmt="yuv420p", ring=RING, merange=MERANGE, qp=QP, subpel=1, intra_in_p=1,
                        device=local, profile=0, streams=STREAMS, deblock=args.deblock, transform8x8=args.transform8x8,
-                       pack_levels=args.pack_levels)
+                       pack_levels=args.pack_levels, partitions=args.partitions)
     fill_inputs(eng, b2oracle, rank)
     for r in range(RING):
         eng.h2d(ring=r)
@@ -315,7 +316,7 @@ def main():
         eng.close()
         eng1 = b2enc.Engine(W, H, slots=SLOTS, fmt="yuv420p", ring=2, merange=MERANGE, qp=QP, subpel=1, intra_in_p=1,
                             device=local, profile=1, streams=1, deblock=args.deblock, transform8x8=args.transform8x8,
-                            pack_levels=args.pack_levels)
+                            pack_levels=args.pack_levels, partitions=args.partitions)
         fill_inputs(eng1, b2oracle, rank)
         eng1.h2d(ring=0); eng1.h2d(ring=1)
         eng1.encode(b2enc.FRAME_I, ring=0)
@@ -344,7 +345,7 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_step": SLOTS * world, "gop": GOP, "input_ring_frames": RING,
                        "l2": "no flush needed: per-step working set (cur+ref+recon planes of %d frames ~ %d MB + raw ring) exceeds the 126 MB L2"
                              % (SLOTS, int(SLOTS * 3 * 1.5 * w16 * h16 / 1e6)),
-                       "host_cpus_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None, "stream_groups": NG, "gop_phase_per_group": phase, "deblocking_filter": bool(args.deblock), "transform8x8": bool(args.transform8x8),
+                       "host_cpus_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None, "stream_groups": NG, "gop_phase_per_group": phase, "deblocking_filter": bool(args.deblock), "transform8x8": bool(args.transform8x8), "partitions": bool(args.partitions),
                        "parallelism": "closed-GOP sharding, %d GPUs x %d GOPs, no collective" % (world, SLOTS)},
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(world * SLOTS * in_bytes),
                     "d2h_bytes_per_step": int(world * (SLOTS * mbs * 48 + packed_per_step)) if args.pack_levels else int(world * SLOTS * mbs * (48 + 832)),
