@@ -8,16 +8,19 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _encode_and_check(oracle, b2, w, h, R, qp, nslots, nframes, oracle_slots, subpel=1, intra_in_p=1, deblock=0):
-    eng = b2.Engine(w, h, slots=nslots, ring=1, merange=R, qp=qp, subpel=subpel, intra_in_p=intra_in_p, deblock=deblock)
-    prm = oracle.Params(qp, R, subpel, intra_in_p, deblock)
-    ents = [oracle.Entropy(w, h, qp, deblock=deblock) for _ in range(nslots)]
+def _encode_and_check(oracle, b2, w, h, R, qp, nslots, nframes, oracle_slots, subpel=1, intra_in_p=1, deblock=0, cabac=0, t8=0,
+                      partitions=0, pack=0, frame_fn=None):
+    eng = b2.Engine(w, h, slots=nslots, ring=1, merange=R, qp=qp, subpel=subpel, intra_in_p=intra_in_p, deblock=deblock,
+                    transform8x8=t8, partitions=partitions, pack_levels=pack)
+    prm = oracle.Params(qp, R, subpel, intra_in_p, deblock, t8, partitions)
+    ents = [oracle.Entropy(w, h, qp, deblock=deblock, cabac=cabac, transform8x8=t8) for _ in range(nslots)]
+    frame_fn = frame_fn or (lambda t, s: oracle.synth_frame(w, h, t, s))
     streams = [bytearray() for _ in range(nslots)]
     recons = [[] for _ in range(nslots)]
     prev = {s: None for s in oracle_slots}; pmv = {s: None for s in oracle_slots}
     sc = b"\x00\x00\x00\x01"
     for t in range(nframes):
-        frames = [oracle.synth_frame(w, h, t, s) for s in range(nslots)]
+        frames = [frame_fn(t, s) for s in range(nslots)]
         for s in range(nslots):
             eng.put_frame(s, 0, list(frames[s]))
         ft = b2.FRAME_I if t == 0 else b2.FRAME_P
@@ -69,3 +72,13 @@ def test_c5_many_720p_streams(oracle, b2):
 
 def test_c3_1080p_with_deblocking(oracle, b2):
     _encode_and_check(oracle, b2, 1920, 1080, 32, 32, nslots=2, nframes=3, oracle_slots=[0], deblock=1)
+
+
+def test_c3_1080p_all_features(oracle, b2):
+    """rows N1-N3 together at full size: CABAC, adaptive 8x8 transform + intra 8x8, inter partitions, deblocking, packed
+    levels -- oracle-exact on one stream and decoder-exact on both (content: sheared motion so that partitions occur)"""
+    from test_oracle_decode import shear_seq
+    w, h = 1920, 1080
+    seqs = [shear_seq(w, h, 3, seed=31, stripe=72, band=56), shear_seq(w, h, 3, seed=32, stripe=40, band=88)]
+    _encode_and_check(oracle, b2, w, h, 32, 30, nslots=2, nframes=3, oracle_slots=[0], deblock=1, cabac=1, t8=1, partitions=1, pack=1,
+                      frame_fn=lambda t, s: seqs[s][t])

@@ -110,8 +110,8 @@ k3_intra_analyse_kernel(const uint8_t *__restrict__ cur_y, const uint8_t *__rest
         }
         __syncwarp();
         uint32_t best8 = 0xffffffffu; int mode8 = B2_I4_DC;
-#pragma unroll 1
-        for (int m = 0; m < 9; m++) {
+#pragma unroll
+        for (int m = 0; m < 9; m++) {                    // unrolled: the predictor switch and the parity tests fold per mode
             int d[16], t[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) d[i] = src[i] - b2::pred8x8_px(m, et, sx + (i & 3), sy4 + (i >> 2));
