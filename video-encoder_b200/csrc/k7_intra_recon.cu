@@ -22,7 +22,7 @@ namespace {
 
 using namespace b2;
 
-constexpr int K7_WARPS = 16;
+constexpr int K7_WARPS_I = 16, K7_WARPS_P = 16;
 constexpr int TP = 48;                      // tile pitch; pixel (x,y) of the MB sits at tile[(y+1)*TP + x + 16]
 
 struct K7Warp {
@@ -485,10 +485,15 @@ __device__ void k7_chroma_task(int lane, const FramePlanes &fp, int frame, int m
     if (lane == 0) publish_mask(mi, bits, false);
 }
 
-__global__ void __launch_bounds__(K7_WARPS * 32)
+// WARPS = warps per CTA.  Measured: shrinking the P-frame CTA to 4 warps (so that it fits beside two K1 CTAs in the register
+// file) LOSES 16 % of the stage throughput -- P frames after a scene change hold thousands of intra MBs and the chain of a
+// stream group then waits on K7 -- so both variants use 16
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 k7_intra_wavefront_kernel(FramePlanes fp, int mbw, int mbh, int qp, b2_mbinfo_t *__restrict__ info,
                           b2_mbcoef_t *__restrict__ coef)
 {
+    constexpr int K7_WARPS = WARPS;
     extern __shared__ int s_diag_cnt[];                 // intra MBs per anti-diagonal
     __shared__ K7Warp s_warp[K7_WARPS];
     const int frame = blockIdx.y;
@@ -535,16 +540,17 @@ int b2_launch_intra_recon(const uint8_t *const cur[3], uint8_t *const rec[3], in
     // scattered intra MBs: one CTA per frame keeps the footprint at one SM so that other streams' kernels keep the rest.
     int ncta = 1;
     if (all_intra)
-        while (ncta < 8 && ncta * K7_WARPS < 2 * maxdiag) ncta *= 2;
+        while (ncta < 8 && ncta * K7_WARPS_I < 2 * maxdiag) ncta *= 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ncta, nframes, 1);
-    cfg.blockDim = dim3(K7_WARPS * 32, 1, 1);
+    cfg.blockDim = dim3((all_intra ? K7_WARPS_I : K7_WARPS_P) * 32, 1, 1);
     cfg.dynamicSmemBytes = ndiag * sizeof(int);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    B2_CUDA_OK(cudaLaunchKernelEx(&cfg, k7_intra_wavefront_kernel, fp, mbw, mbh, qp, d_info, d_coef));
+    if (all_intra) B2_CUDA_OK(cudaLaunchKernelEx(&cfg, k7_intra_wavefront_kernel<K7_WARPS_I>, fp, mbw, mbh, qp, d_info, d_coef));
+    else B2_CUDA_OK(cudaLaunchKernelEx(&cfg, k7_intra_wavefront_kernel<K7_WARPS_P>, fp, mbw, mbh, qp, d_info, d_coef));
     return 0;
 }
