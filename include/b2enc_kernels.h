@@ -30,6 +30,11 @@ int b2k_me_fullpel(const uint8_t *cur_y, const uint8_t *ref_y, int w, int h, int
                    const b2_mv_t *pmv, int lambda, b2_mv_t *mv_out, uint32_t *cost_out,
                    int iters, float *kernel_ms);
 
+/* K1, partition variant (row N1, partitions = 2): best full-pel vector and cost of each of the nine shape parts per MB
+ * (16x16 | 16x8 top,bottom | 8x16 left,right | four 8x8), outputs [nframes][mbs][9] */
+int b2k_me_fullpel_parts(const uint8_t *cur_y, const uint8_t *ref_y, int w, int h, int nframes, int merange,
+                         const b2_mv_t *pmv, int lambda, b2_mv_t *mv9_out, uint32_t *cost9_out, int iters, float *kernel_ms);
+
 /* sustained VABSDIFF4 lane-instructions/s of the chip (roofline denominator of K1) */
 double b2_bench_vabsdiff4_peak(int device, int outer, int reps, double *ms_best);
 

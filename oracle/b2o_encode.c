@@ -138,8 +138,12 @@ void b2o_encode_frame(const b2o_params_t *prm, int frame_type,
     int do_intra = frame_type == B2_FRAME_I || prm->intra_in_p;
     if (do_intra) b2o_intra_analyse(cur, lambda, info, c16, c4, c8);
     if (frame_type == B2_FRAME_P) {
-        b2o_me_fullpel(cur, ref, prm->merange, prev_mv, lambda, mvf, cinter);
-        if (parts) {
+        if (parts && prm->partitions == 2) {
+            uint32_t *cfull = (uint32_t *)malloc(sizeof(uint32_t) * n);
+            b2o_me_parts_wide(cur, ref, prm->merange, prev_mv, lambda, 1, mvf, cfull, part, mv4, cinter);
+            for (int i = 0; i < n; i++) mvq[i] = mv4[i][0];
+            free(cfull);
+        } else if (b2o_me_fullpel(cur, ref, prm->merange, prev_mv, lambda, mvf, cinter), parts) {
             b2o_me_subpel_part(cur, ref, mvf, prev_mv, lambda, part, mv4, cinter);
             for (int i = 0; i < n; i++) mvq[i] = mv4[i][0];
         } else if (prm->subpel) {

@@ -116,6 +116,19 @@ def me_fullpel_mb(cur, ref, R, mbx, mby, pmv=(0, 0), lam=0):
     return (int(mv["x"][0]), int(mv["y"][0])), int(cost[0])
 
 
+def me_fullpel_parts(cur: OFrame, ref: OFrame, R, pmv=None, lam=0):
+    """best full-pel vector / cost of the nine shape parts of every MB (b2o_me_fullpel_parts_mb): mv[mbs,9], cost[mbs,9]"""
+    L = lib()
+    L.b2o_me_fullpel_parts_mb.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+    mbw, mbh = cur.f.mbw, cur.f.mbh
+    mv = np.zeros((mbw * mbh, 9), MV); cost = np.zeros((mbw * mbh, 9), np.uint32)
+    for i in range(mbw * mbh):
+        packed = int(np.ascontiguousarray(pmv[i:i + 1]).view(np.uint32)[0]) if pmv is not None else 0
+        L.b2o_me_fullpel_parts_mb(C.addressof(cur.f), C.addressof(ref.f), R, i % mbw, i // mbw, packed, lam,
+                                  mv[i].ctypes.data_as(C.c_void_p), cost[i].ctypes.data_as(C.c_void_p))
+    return mv, cost
+
+
 # ---- frame-level oracle encoder + host entropy coder (linked into libb2oracle.so) ---------------
 class Seq(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("fps_num", C.c_int), ("fps_den", C.c_int),

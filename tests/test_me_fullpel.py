@@ -79,3 +79,46 @@ def test_synth_known_answer_1080p(oracle, b2):
         (ox, oy), oc = oracle.me_fullpel_mb(c, r, 32, mbx, mby)
         i = mby * mbw + mbx
         assert (int(mv["x"][0, i]), int(mv["y"][0, i]), int(cost[0, i])) == (ox, oy, oc)
+
+
+# ---- K1 partition variant (row N1, partitions = 2): best vector of each of the nine shape parts -------------------------
+def _check_parts(oracle, b2, cur, ref, R, pmv=None, lam=0):
+    mv_g, cost_g, _ = b2.me_fullpel_parts(cur, ref, R, pmv, lam)
+    for i in range(cur.shape[0]):
+        h, w = cur[i].shape
+        z = np.zeros((h // 2, w // 2), np.uint8)
+        c = oracle.OFrame(w, h).load(cur[i], z, z); r = oracle.OFrame(w, h).load(ref[i], z, z)
+        mv_o, cost_o = oracle.me_fullpel_parts(c, r, R, None if pmv is None else pmv[i], lam)
+        assert np.array_equal(cost_g[i], cost_o), f"part costs differ, frame {i}: {np.argwhere(cost_g[i] != cost_o)[:4].tolist()}"
+        assert np.array_equal(mv_g[i], mv_o), f"part vectors differ, frame {i}"
+        # part 0 is the plain 16x16 search
+        mv16, c16 = oracle.me_fullpel(c, r, R, None if pmv is None else pmv[i], lam)
+        assert np.array_equal(mv_g[i][:, 0], mv16) and np.array_equal(cost_g[i][:, 0], c16)
+
+
+@pytest.mark.parametrize("R", [16, 32])
+@pytest.mark.parametrize("wh", [(128, 64), (80, 48), (176, 144), (16, 16)])
+def test_parts_random_frames(oracle, b2, R, wh):
+    w, h = wh
+    rng = np.random.default_rng(R * 77 + w)
+    cur = rng.integers(0, 256, (2, h, w), dtype=np.uint8); ref = rng.integers(0, 256, (2, h, w), dtype=np.uint8)
+    _check_parts(oracle, b2, cur, ref, R)
+
+
+@pytest.mark.parametrize("R", [16, 32])
+def test_parts_ties_lambda_and_predictors(oracle, b2, R):
+    w, h = 192, 96
+    yy, xx = np.mgrid[0:h, 0:w]
+    flat = np.full((h, w), 77, np.uint8)
+    periodic = (((xx // 4) + (yy // 4)) % 2 * 255).astype(np.uint8)
+    sat = np.where(xx > w // 2, 255, 0).astype(np.uint8)
+    cur = np.stack([flat, periodic, sat]); ref = np.stack([flat, periodic, sat])
+    _check_parts(oracle, b2, cur, ref, R)
+    rng = np.random.default_rng(11 + R)
+    base = rng.integers(0, 256, (h + 80, w + 80), dtype=np.uint8)
+    ref = base[40:40 + h, 40:40 + w][None].copy(); cur = base[43:43 + h, 35:35 + w][None].copy()
+    cur[0, :, w // 2:] = base[38:38 + h, 44 + w // 2:44 + w]                       # right half moves differently
+    pmv = np.zeros((1, (w // 16) * (h // 16)), b2.MV)
+    pmv["x"] = rng.integers(-140, 140, pmv.shape); pmv["y"] = rng.integers(-140, 140, pmv.shape)
+    for lam in (0, 4, 91):
+        _check_parts(oracle, b2, cur, ref, R, pmv, lam)

@@ -67,6 +67,25 @@ def me_fullpel(cur_y, ref_y, merange, pmv=None, lam=0, iters=0):
     return mv, cost, (ms.value if iters > 0 else None)
 
 
+def me_fullpel_parts(cur_y, ref_y, merange, pmv=None, lam=0, iters=0):
+    """K1 partition variant: returns (mv9[n,mbs,9], cost9[n,mbs,9], kernel_ms|None)"""
+    require_gpu()
+    cur_y = np.ascontiguousarray(cur_y, np.uint8); ref_y = np.ascontiguousarray(ref_y, np.uint8)
+    if cur_y.ndim == 2:
+        cur_y = cur_y[None]; ref_y = ref_y[None]
+    n, h, w = cur_y.shape
+    nmb = (w // 16) * (h // 16)
+    mv = np.zeros((n, nmb, 9), MV); cost = np.zeros((n, nmb, 9), np.uint32)
+    if pmv is not None:
+        pmv = np.ascontiguousarray(pmv, MV).reshape(n, nmb)
+    ms = C.c_float(0)
+    rc = lib().b2k_me_fullpel_parts(_p(cur_y), _p(ref_y), w, h, n, merange, _p(pmv), lam, _p(mv), _p(cost),
+                                    iters, C.byref(ms) if iters > 0 else None)
+    if rc != 0:
+        raise RuntimeError("b2k_me_fullpel_parts failed (%d)" % rc)
+    return mv, cost, (ms.value if iters > 0 else None)
+
+
 def vabsdiff4_peak(device=0, outer=256, reps=5):
     require_gpu()
     ms = C.c_double(0)

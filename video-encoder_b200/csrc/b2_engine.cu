@@ -56,6 +56,8 @@ struct b2_engine {
     uint8_t *d_pred = nullptr;             // [S][nmb][256] motion-compensated luma prediction (K2 -> K5)
     uint8_t *d_part = nullptr;             // cfg.partitions: [S][nmb] partition shape chosen by K2
     b2_mv_t *d_mv8 = nullptr;              //                 [S][nmb][3] vectors of quadrants 1..3
+    b2_mv_t *d_mv9 = nullptr;              // cfg.partitions == 2: [S][nmb][9] best full-pel vector of every shape part (K1<PART>)
+    uint32_t *d_cost9 = nullptr;           //                      and its cost
     b2_mbinfo_t *d_info[2] = {}, *h_info[2] = {};
     b2_mbcoef_t *d_coef[2] = {}, *h_coef[2] = {};
     // cfg.pack_levels: packed level streams [S][pack_stride] per result set (device + pinned host), blocks used per slot
@@ -123,6 +125,10 @@ static int engine_alloc(b2_engine *e)
     if (c.partitions && c.subpel) {
         ENG_OK(cudaMalloc(&e->d_part, n)); ENG_OK(cudaMemset(e->d_part, 0, n));
         ENG_OK(cudaMalloc(&e->d_mv8, n * 3 * sizeof(b2_mv_t))); ENG_OK(cudaMemset(e->d_mv8, 0, n * 3 * sizeof(b2_mv_t)));
+        if (c.partitions == 2) {
+            ENG_OK(cudaMalloc(&e->d_mv9, n * 9 * sizeof(b2_mv_t))); ENG_OK(cudaMalloc(&e->d_cost9, n * 9 * 4));
+            ENG_OK(cudaMemset(e->d_mv9, 0, n * 9 * sizeof(b2_mv_t))); ENG_OK(cudaMemset(e->d_cost9, 0, n * 9 * 4));
+        }
     }
     for (int s = 0; s < 2; s++) {
         ENG_OK(cudaMalloc(&e->d_info[s], n * sizeof(b2_mbinfo_t)));
@@ -213,7 +219,7 @@ extern "C" void b2_engine_destroy(b2_engine_t *e)
     cudaFree(e->d_in); cudaFreeHost(e->h_in);
     for (int p = 0; p < 3; p++) { cudaFree(e->d_cur[p]); cudaFree(e->d_rec[0][p]); cudaFree(e->d_rec[1][p]); }
     cudaFree(e->d_mvf); cudaFree(e->d_mvq); cudaFree(e->d_prev_mv); cudaFree(e->d_cost_full); cudaFree(e->d_cost_inter);
-    cudaFree(e->d_c16); cudaFree(e->d_c4); cudaFree(e->d_c8); cudaFree(e->d_pred); cudaFree(e->d_part); cudaFree(e->d_mv8);
+    cudaFree(e->d_c16); cudaFree(e->d_c4); cudaFree(e->d_c8); cudaFree(e->d_pred); cudaFree(e->d_part); cudaFree(e->d_mv8); cudaFree(e->d_mv9); cudaFree(e->d_cost9);
     for (int s = 0; s < 2; s++) {
         cudaFree(e->d_info[s]); cudaFree(e->d_coef[s]); cudaFreeHost(e->h_info[s]); cudaFreeHost(e->h_coef[s]);
         cudaFree(e->d_pack[s]); cudaFreeHost(e->h_pack[s]); cudaFree(e->d_pack_n[s]); cudaFreeHost(e->h_pack_n[s]);
@@ -369,7 +375,8 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
         {
             KScope k(e, st, 2);
             if (b2_launch_me_fullpel(c.merange, &gr.tm_cur, &gr.tm_ref[gr.ref_idx], e->mbw, e->mbh, ns, e->d_prev_mv + om, e->lambda,
-                                     e->d_mvf + om, e->d_cost_full + om, st))
+                                     e->d_mvf + om, e->d_cost_full + om, e->d_mv9 ? e->d_mv9 + om * 9 : nullptr,
+                                     e->d_cost9 ? e->d_cost9 + om * 9 : nullptr, st))
                 return -1;
         }
         {

@@ -14,7 +14,7 @@ int b2_launch_extend_border_yuv(uint8_t *d_y, uint8_t *d_u, uint8_t *d_v, int pi
 extern "C" int b2_k1_window_box(int R, int *bw, int *bh);
 int b2_launch_me_fullpel(int R, const CUtensorMap *tm_cur, const CUtensorMap *tm_ref, int mbw, int mbh,
                          int nframes, const b2_mv_t *d_pmv, int lambda, b2_mv_t *d_mv, uint32_t *d_cost,
-                         cudaStream_t st);
+                         b2_mv_t *d_mv9 /* NULL, or [nmb][9] best vector of every shape part */, uint32_t *d_cost9, cudaStream_t st);
 
 int b2_launch_convert(int fmt, const uint8_t *d_in, size_t in_stride, uint8_t *d_y, uint8_t *d_u, uint8_t *d_v, int pitch,
                       int pitchc, size_t stride_y, size_t stride_c, int w, int h, int nframes, cudaStream_t st);

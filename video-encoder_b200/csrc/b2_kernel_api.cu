@@ -30,9 +30,27 @@ int upload_padded(DevBuf &buf, const uint8_t *host, int w, int h, int n, int pad
 }
 }  // namespace
 
+static int me_fullpel_impl(const uint8_t *cur_y, const uint8_t *ref_y, int w, int h, int nframes, int merange, const b2_mv_t *pmv,
+                           int lambda, b2_mv_t *mv_out, uint32_t *cost_out, b2_mv_t *mv9_out, uint32_t *cost9_out, int iters,
+                           float *kernel_ms);
+
 extern "C" int b2k_me_fullpel(const uint8_t *cur_y, const uint8_t *ref_y, int w, int h, int nframes, int merange,
                               const b2_mv_t *pmv, int lambda, b2_mv_t *mv_out, uint32_t *cost_out,
                               int iters, float *kernel_ms)
+{
+    return me_fullpel_impl(cur_y, ref_y, w, h, nframes, merange, pmv, lambda, mv_out, cost_out, nullptr, nullptr, iters, kernel_ms);
+}
+
+extern "C" int b2k_me_fullpel_parts(const uint8_t *cur_y, const uint8_t *ref_y, int w, int h, int nframes, int merange,
+                                    const b2_mv_t *pmv, int lambda, b2_mv_t *mv9_out, uint32_t *cost9_out, int iters, float *kernel_ms)
+{
+    if (!mv9_out || !cost9_out) return -1;
+    return me_fullpel_impl(cur_y, ref_y, w, h, nframes, merange, pmv, lambda, nullptr, nullptr, mv9_out, cost9_out, iters, kernel_ms);
+}
+
+static int me_fullpel_impl(const uint8_t *cur_y, const uint8_t *ref_y, int w, int h, int nframes, int merange, const b2_mv_t *pmv,
+                           int lambda, b2_mv_t *mv_out, uint32_t *cost_out, b2_mv_t *mv9_out, uint32_t *cost9_out, int iters,
+                           float *kernel_ms)
 {
     if ((w & 15) || (h & 15) || w <= 0 || h <= 0 || nframes <= 0) {
         fprintf(stderr, "b2enc: b2k_me_fullpel needs w,h multiples of 16\n");
@@ -42,11 +60,12 @@ extern "C" int b2k_me_fullpel(const uint8_t *cur_y, const uint8_t *ref_y, int w,
     if (b2_k1_window_box(merange, &bw, &bh)) { fprintf(stderr, "b2enc: merange %d not supported\n", merange); return -1; }
     const int mbw = w / 16, mbh = h / 16;
     const size_t nmb = (size_t)mbw * mbh * nframes;
-    DevBuf d_cur, d_ref, d_pmv, d_mv, d_cost;
+    DevBuf d_cur, d_ref, d_pmv, d_mv, d_cost, d_mv9, d_cost9;
     int pitch, rows;
     if (upload_padded(d_cur, cur_y, w, h, nframes, B2_PAD, &pitch, &rows)) return -1;
     if (upload_padded(d_ref, ref_y, w, h, nframes, B2_PAD, &pitch, &rows)) return -1;
     if (d_mv.alloc(nmb * sizeof(b2_mv_t)) || d_cost.alloc(nmb * 4)) return -1;
+    if (mv9_out && (d_mv9.alloc(nmb * 9 * sizeof(b2_mv_t)) || d_cost9.alloc(nmb * 9 * 4))) return -1;
     if (pmv) {
         if (d_pmv.alloc(nmb * sizeof(b2_mv_t))) return -1;
         B2_CUDA_OK(cudaMemcpy(d_pmv.p, pmv, nmb * sizeof(b2_mv_t), cudaMemcpyHostToDevice));
@@ -55,7 +74,7 @@ extern "C" int b2k_me_fullpel(const uint8_t *cur_y, const uint8_t *ref_y, int w,
     if (b2_make_plane_tmap(&tm_cur, d_cur.p, pitch, rows, nframes, 128, 16)) return -1;
     if (b2_make_plane_tmap(&tm_ref, d_ref.p, pitch, rows, nframes, bw, bh)) return -1;
     if (b2_launch_me_fullpel(merange, &tm_cur, &tm_ref, mbw, mbh, nframes, (const b2_mv_t *)d_pmv.p, lambda,
-                             (b2_mv_t *)d_mv.p, (uint32_t *)d_cost.p, 0))
+                             (b2_mv_t *)d_mv.p, (uint32_t *)d_cost.p, (b2_mv_t *)d_mv9.p, (uint32_t *)d_cost9.p, 0))
         return -1;
     B2_CUDA_OK(cudaDeviceSynchronize());
     if (kernel_ms) {
@@ -65,7 +84,7 @@ extern "C" int b2k_me_fullpel(const uint8_t *cur_y, const uint8_t *ref_y, int w,
         cudaEventRecord(e0, 0);
         for (int i = 0; i < iters; i++)
             b2_launch_me_fullpel(merange, &tm_cur, &tm_ref, mbw, mbh, nframes, (const b2_mv_t *)d_pmv.p, lambda,
-                                 (b2_mv_t *)d_mv.p, (uint32_t *)d_cost.p, 0);
+                                 (b2_mv_t *)d_mv.p, (uint32_t *)d_cost.p, (b2_mv_t *)d_mv9.p, (uint32_t *)d_cost9.p, 0);
         cudaEventRecord(e1, 0);
         B2_CUDA_OK(cudaEventSynchronize(e1));
         float ms = 0;
@@ -73,8 +92,12 @@ extern "C" int b2k_me_fullpel(const uint8_t *cur_y, const uint8_t *ref_y, int w,
         *kernel_ms = ms / iters;
         cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
-    B2_CUDA_OK(cudaMemcpy(mv_out, d_mv.p, nmb * sizeof(b2_mv_t), cudaMemcpyDeviceToHost));
-    B2_CUDA_OK(cudaMemcpy(cost_out, d_cost.p, nmb * 4, cudaMemcpyDeviceToHost));
+    if (mv_out) B2_CUDA_OK(cudaMemcpy(mv_out, d_mv.p, nmb * sizeof(b2_mv_t), cudaMemcpyDeviceToHost));
+    if (cost_out) B2_CUDA_OK(cudaMemcpy(cost_out, d_cost.p, nmb * 4, cudaMemcpyDeviceToHost));
+    if (mv9_out) {
+        B2_CUDA_OK(cudaMemcpy(mv9_out, d_mv9.p, nmb * 9 * sizeof(b2_mv_t), cudaMemcpyDeviceToHost));
+        B2_CUDA_OK(cudaMemcpy(cost9_out, d_cost9.p, nmb * 9 * 4, cudaMemcpyDeviceToHost));
+    }
     return 0;
 }
 

@@ -47,16 +47,21 @@ template <int R> struct K1Smem {
     static constexpr int OFF_COSTX = OFF_EXP + EXP_BYTES;
     static constexpr int OFF_COSTY = OFF_COSTX + NMB * ND * 4;
     static constexpr int OFF_BEST = OFF_COSTY + NMB * ND * 4;
-    static constexpr int OFF_BAR = (OFF_BEST + NMB * 4 + 7) & ~7;
+    static constexpr int OFF_BAR = (OFF_BEST + NMB * 9 * 4 + 7) & ~7;    // 9 best keys per MB in the partition variant
     static constexpr int TOTAL = OFF_BAR + 8 + 128;     // +128: manual alignment slack
 };
 
-template <int R, int NTHREADS>
+// PART (row N1, partitions = 2): the same sweep also yields the SAD of every 8x8 quadrant, hence the best vector of each of
+// the nine shape parts (16x16 | 16x8 top,bottom | 8x16 left,right | four 8x8).  The number of VABSDIFF4 is unchanged; a lane
+// sweeps the top half of the current MB, packs the two 8x8 SADs of its K candidates into K registers, sweeps the bottom
+// half, and then forms 9 sums / keys per candidate (9 running minima, 9 CREDUX.MIN + 9 shared atomicMin per warp task).
+template <int R, int NTHREADS, bool PART>
 __global__ void __launch_bounds__(NTHREADS, 2)
 k1_me_fullpel_kernel(const __grid_constant__ CUtensorMap tm_cur,
                      const __grid_constant__ CUtensorMap tm_ref,
                      int mbw, int mbh, const b2_mv_t *__restrict__ pmv, int lambda,
-                     b2_mv_t *__restrict__ mv_out, uint32_t *__restrict__ cost_out)
+                     b2_mv_t *__restrict__ mv_out, uint32_t *__restrict__ cost_out,
+                     b2_mv_t *__restrict__ mv9_out, uint32_t *__restrict__ cost9_out)
 {
     using S = K1Smem<R>;
     constexpr int NWARPS = NTHREADS / 32;
@@ -98,7 +103,7 @@ k1_me_fullpel_kernel(const __grid_constant__ CUtensorMap tm_cur,
         s_costx[i] = ((uint32_t)(lambda * b2_mvbits(4 * (d - R) - px)) << 13) + (uint32_t)d;
         s_costy[i] = ((uint32_t)(lambda * b2_mvbits(4 * (d - R) - py)) << 13) + (uint32_t)(d * ND);
     }
-    if (tid < NMB) s_best[tid] = 0xffffffffu;
+    if (tid < NMB * (PART ? 9 : 1)) s_best[tid] = 0xffffffffu;
 
     mbar_wait(s_bar, 0);
 
@@ -129,6 +134,78 @@ k1_me_fullpel_kernel(const __grid_constant__ CUtensorMap tm_cur,
         const int g = rem / ND;
         const int dxi = rem - g * ND;
 
+        if constexpr (PART) {
+            uint32_t top[K];                               // SAD(top-left 8x8) | SAD(top-right 8x8) << 16
+            uint32_t best[9];
+#pragma unroll
+            for (int p = 0; p < 9; p++) best[p] = 0xffffffffu;
+            const uint32_t kx = s_costx[m * ND + dxi];
+            const uint32_t *ky = s_costy + m * ND + g * K;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                uint32_t cur[32];                          // 8 rows of the current macroblock
+                {
+                    const uint4 *c4 = (const uint4 *)(s_cur + m * 16) + half * 8 * (NMB * 16 / 16);
+#pragma unroll
+                    for (int y = 0; y < 8; y++) {
+                        uint4 v = c4[y * (NMB * 16 / 16)];
+                        cur[y * 4 + 0] = v.x; cur[y * 4 + 1] = v.y; cur[y * 4 + 2] = v.z; cur[y * 4 + 3] = v.w;
+                    }
+                }
+                uint32_t accl[K], accr[K];
+#pragma unroll
+                for (int k = 0; k < K; k++) accl[k] = accr[k] = 0;
+                const uint32_t *wp = s_exp + (g * K + half * 8) * S::EXP_PITCH + m * 16 + dxi;
+#pragma unroll
+                for (int r = 0; r < K + 7; r++) {
+                    const uint32_t w0 = wp[r * S::EXP_PITCH + 0];
+                    const uint32_t w1 = wp[r * S::EXP_PITCH + 4];
+                    const uint32_t w2 = wp[r * S::EXP_PITCH + 8];
+                    const uint32_t w3 = wp[r * S::EXP_PITCH + 12];
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        const int y = r - k;
+                        if (y >= 0 && y < 8) {
+                            accl[k] = vsad4_acc(w0, cur[y * 4 + 0], accl[k]);
+                            accl[k] = vsad4_acc(w1, cur[y * 4 + 1], accl[k]);
+                            accr[k] = vsad4_acc(w2, cur[y * 4 + 2], accr[k]);
+                            accr[k] = vsad4_acc(w3, cur[y * 4 + 3], accr[k]);
+                        }
+                    }
+                }
+                if (half == 0) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) top[k] = accl[k] | (accr[k] << 16);
+                } else if (active) {
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        const uint32_t tl = top[k] & 0xffffu, tr = top[k] >> 16, bl = accl[k], br = accr[k];
+                        const uint32_t kc = kx + ky[k];
+                        const uint32_t st = tl + tr, sb = bl + br;
+                        best[0] = min(best[0], (st + sb) * 8192u + kc);
+                        best[1] = min(best[1], st * 8192u + kc);
+                        best[2] = min(best[2], sb * 8192u + kc);
+                        best[3] = min(best[3], (tl + bl) * 8192u + kc);
+                        best[4] = min(best[4], (tr + br) * 8192u + kc);
+                        best[5] = min(best[5], tl * 8192u + kc);
+                        best[6] = min(best[6], tr * 8192u + kc);
+                        best[7] = min(best[7], bl * 8192u + kc);
+                        best[8] = min(best[8], br * 8192u + kc);
+                    }
+                }
+            }
+            const int m0 = __shfl_sync(0xffffffffu, m, 0);
+            if (__all_sync(0xffffffffu, m == m0)) {
+#pragma unroll
+                for (int p = 0; p < 9; p++) {
+                    const uint32_t wmin = __reduce_min_sync(0xffffffffu, best[p]);
+                    if (lane == 0) atomicMin(&s_best[m0 * 9 + p], wmin);
+                }
+            } else if (active) {
+#pragma unroll
+                for (int p = 0; p < 9; p++) atomicMin(&s_best[m * 9 + p], best[p]);
+            }
+        } else {
         // current macroblock -> 64 registers
         uint32_t cur[64];
         {
@@ -176,35 +253,51 @@ k1_me_fullpel_kernel(const __grid_constant__ CUtensorMap tm_cur,
         } else if (active) {
             atomicMin(&s_best[m], key);
         }
+        }
     }
     __syncthreads();
 
-    if (tid < nmb) {
+    if (tid < nmb * (PART ? 9 : 1)) {
         const uint32_t key = s_best[tid];
         const int idx = (int)(key & 8191u);
         const int dyi = idx / ND, dxi = idx - dyi * ND;
         b2_mv_t mv;
         mv.x = (int16_t)(dxi - R);
         mv.y = (int16_t)(dyi - R);
-        mv_out[mb_base + tid] = mv;
-        cost_out[mb_base + tid] = key >> 13;
+        if constexpr (PART) {
+            const int mm = tid / 9, p = tid - mm * 9;
+            mv9_out[(mb_base + mm) * 9 + p] = mv;
+            cost9_out[(mb_base + mm) * 9 + p] = key >> 13;
+            if (p == 0) { mv_out[mb_base + mm] = mv; cost_out[mb_base + mm] = key >> 13; }
+        } else {
+            mv_out[mb_base + tid] = mv;
+            cost_out[mb_base + tid] = key >> 13;
+        }
     }
 }
 
-template <int R, int NT>
-int launch_k1(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, int mbw, int mbh, int nframes,
-              const b2_mv_t *pmv, int lambda, b2_mv_t *mv_out, uint32_t *cost_out, cudaStream_t st)
+template <int R, int NT, bool PART>
+int launch_k1p(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, int mbw, int mbh, int nframes, const b2_mv_t *pmv, int lambda,
+               b2_mv_t *mv_out, uint32_t *cost_out, b2_mv_t *mv9_out, uint32_t *cost9_out, cudaStream_t st)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        B2_CUDA_OK(cudaFuncSetAttribute(k1_me_fullpel_kernel<R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        B2_CUDA_OK(cudaFuncSetAttribute(k1_me_fullpel_kernel<R, NT, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         K1Smem<R>::TOTAL));
         attr_set = true;
     }
     dim3 grid((mbw + NMB - 1) / NMB, mbh, nframes);
-    k1_me_fullpel_kernel<R, NT><<<grid, NT, K1Smem<R>::TOTAL, st>>>(tm_cur, tm_ref, mbw, mbh, pmv, lambda, mv_out, cost_out);
+    k1_me_fullpel_kernel<R, NT, PART><<<grid, NT, K1Smem<R>::TOTAL, st>>>(tm_cur, tm_ref, mbw, mbh, pmv, lambda, mv_out, cost_out,
+                                                                            mv9_out, cost9_out);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
+}
+template <int R, int NT>
+int launch_k1(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, int mbw, int mbh, int nframes, const b2_mv_t *pmv, int lambda,
+              b2_mv_t *mv_out, uint32_t *cost_out, b2_mv_t *mv9_out, uint32_t *cost9_out, cudaStream_t st)
+{
+    if (mv9_out) return launch_k1p<R, NT, true>(tm_cur, tm_ref, mbw, mbh, nframes, pmv, lambda, mv_out, cost_out, mv9_out, cost9_out, st);
+    return launch_k1p<R, NT, false>(tm_cur, tm_ref, mbw, mbh, nframes, pmv, lambda, mv_out, cost_out, nullptr, nullptr, st);
 }
 
 // threads per CTA: 82 (R=32) / 41 (R=16) warp-tasks per full strip should divide evenly over the warps
@@ -234,14 +327,14 @@ extern "C" int b2_k1_window_box(int R, int *bw, int *bh)
 // with boxes {128+2R, 16+2R, 1} (ref) and {128, 16, 1} (cur).
 int b2_launch_me_fullpel(int R, const CUtensorMap *tm_cur, const CUtensorMap *tm_ref, int mbw, int mbh,
                          int nframes, const b2_mv_t *d_pmv, int lambda, b2_mv_t *d_mv, uint32_t *d_cost,
-                         cudaStream_t st)
+                         b2_mv_t *d_mv9, uint32_t *d_cost9, cudaStream_t st)
 {
 #define K1_DISPATCH(RR)                                                                                              \
     switch (k1_threads()) {                                                                                          \
-    case 192: return launch_k1<RR, 192>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);       \
-    case 320: return launch_k1<RR, 320>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);       \
-    case 384: return launch_k1<RR, 384>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);       \
-    default: return launch_k1<RR, 256>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st);        \
+    case 192: return launch_k1<RR, 192>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, d_mv9, d_cost9, st);       \
+    case 320: return launch_k1<RR, 320>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, d_mv9, d_cost9, st);       \
+    case 384: return launch_k1<RR, 384>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, d_mv9, d_cost9, st);       \
+    default: return launch_k1<RR, 256>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, d_mv9, d_cost9, st);        \
     }
     switch (R) {
     case 32: K1_DISPATCH(32)
