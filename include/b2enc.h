@@ -75,8 +75,9 @@ typedef struct {
                                            profile "baseline" exactly like x264_param_apply_profile)             */
     int b_transform_8x8;                /* adaptive 8x8 transform (x264: analyse.b_transform_8x8; High profile;
                                            cleared by profiles "baseline" and "main")                            */
-    int b_partitions;                   /* inter partitions 16x8 / 8x16 / 8x8 (x264: analyse.inter & X264_ANALYSE_PSUB16x16),
-                                           refined per 8x8 quadrant within +-3/4 pel of the 16x16 vector; default 0          */
+    int b_partitions;                   /* inter partitions 16x8 / 8x16 / 8x8 (x264: analyse.inter & X264_ANALYSE_PSUB16x16).
+                                           1: refined per 8x8 quadrant within +-3/4 pel of the 16x16 vector; 2: every part gets
+                                           its own exhaustive full-pel search (K1 partition variant); default 0              */
 } b2_param_t;
 
 typedef struct {

@@ -35,8 +35,8 @@ typedef struct {
                        /* run on separate CUDA streams so that their kernels overlap       */
     int deblock;       /* 1: in-loop deblocking filter (K8) on every reconstructed frame    */
     int transform8x8;  /* 1: adaptive 8x8 transform for inter macroblocks (SA8D < SATD), row N1 */
-    int partitions;    /* 1: inter partitions 16x8 / 8x16 / 8x8, refined per quadrant around the 16x16   */
-                       /* vector (needs subpel), row N1                                                 */
+    int partitions;    /* inter partitions 16x8 / 8x16 / 8x8 (need subpel), row N1: 1 = refined per quadrant     */
+                       /* within +-3/4 pel of the 16x16 vector, 2 = own exhaustive full-pel search per part      */
     int pack_levels;   /* 1: levels leave the GPU packed (only blocks with a non-zero level, K9):   */
                        /* b2_engine_packed* replace b2_engine_coef*, which then return NULL         */
 } b2_engine_cfg_t;

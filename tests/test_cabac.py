@@ -109,3 +109,21 @@ def test_partitions_do_not_change_uniform_motion(oracle):
     b, _, _ = _roundtrip(oracle, frames, w, h, qp=28, merange=16, gop=32, cabac=1, partitions=0)
     frac = np.mean(np.concatenate([i["part"][i["mb_type"] == 0] for i in infos[1:]]) != 0)
     assert frac < 0.2 and len(a) <= len(b) * 1.02
+
+
+@pytest.mark.parametrize("cabac,t8", [(0, 0), (1, 1)])
+@pytest.mark.parametrize("w,h,qp,amp", [(176, 144, 26, 5), (208, 160, 22, 3), (96, 80, 34, 7)])
+def test_wide_partition_search_decodes_and_beats_local(oracle, w, h, qp, amp, cabac, t8):
+    """partitions = 2: every part has its own exhaustive full-pel search.  With shears of several pixels per frame the local
+    refinement (partitions = 1, +-3/4 pel around the 16x16 vector) cannot follow the parts; the wide search must"""
+    frames = shear_seq(w, h, 4, seed=qp, amp=amp)
+    sizes = {}
+    for pm in (1, 2):
+        bs, recons, infos = _roundtrip(oracle, frames, w, h, qp=qp, merange=16, gop=32, cabac=cabac, deblock=1, transform8x8=t8, partitions=pm)
+        sizes[pm] = len(bs)
+        if pm == 2:
+            parts = np.bincount(np.concatenate([i["part"][i["mb_type"] == 0] for i in infos[1:]]), minlength=4)
+            assert np.all(parts[1:] > 0), parts
+            spread = max(int(np.abs(i["mv8"][:, 2, 0].astype(int) - i["mvx"]).max()) for i in infos[1:])
+            assert spread > 8, "parts never moved more than 2 px apart: %d" % spread
+    assert sizes[2] < sizes[1]

@@ -104,15 +104,17 @@ def test_reference_call_sequence_and_bitstream(oracle, b2, profile, profile_idc,
         assert np.array_equal(dy, recons[i].y[:h, :w]) and np.array_equal(du, recons[i].u[:h // 2, :w // 2])
 
 
-def test_dropin_high_profile_with_partitions(oracle, b2):
-    """everything of row N1 at once through the x264-mirror: CABAC + 8x8 transform + intra 8x8 + inter partitions"""
+@pytest.mark.parametrize("pm,amp", [(1, 1), (2, 4)])
+def test_dropin_high_profile_with_partitions(oracle, b2, pm, amp):
+    """everything of row N1 at once through the x264-mirror: CABAC + 8x8 transform + intra 8x8 + inter partitions
+    (1: local refinement, 2: own full-pel search per part)"""
     w, h, qp, gop, n = 176, 144, 28, 5, 10
-    frames = shear_seq(w, h, n, seed=12)
+    frames = shear_seq(w, h, n, seed=12, amp=amp)
     out = drive(b2, frames, w, h, preset="medium", tune="film", quality=qp, profile="high", i_keyint_max=gop, i_gop_slots=2,
-                b_transform_8x8=1, b_partitions=1)
+                b_transform_8x8=1, b_partitions=pm)
     bs = to_annexb(out, length_prefixed=True)
     ref_bs, recons, infos, _ = oracle.encode_sequence(frames, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1), deblock=1, cabac=1,
-                                                      transform8x8=1, partitions=1)
+                                                      transform8x8=1, partitions=pm)
     assert bs == ref_bs
     assert sum(int((i["part"] != 0).sum()) for i in infos) > 20
     dec = oracle.decode_yuv(oracle.split_access_units(bs))

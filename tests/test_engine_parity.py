@@ -133,6 +133,15 @@ def test_engine_inter_partitions(oracle, b2, w, h, qp, deblock, t8, pack):
     assert np.all(stats["parts"][1:] > 0), stats["parts"]
 
 
+@pytest.mark.parametrize("w,h,qp,R,amp,t8,pack", [(176, 144, 26, 16, 5, 0, 0), (320, 240, 30, 32, 9, 1, 1), (208, 160, 22, 16, 3, 1, 0), (96, 80, 34, 32, 7, 0, 1)])
+def test_engine_wide_partition_search(oracle, b2, w, h, qp, R, amp, t8, pack):
+    """row N1, partitions = 2: K1<PART> (quadrant SADs -> nine part vectors), shape on full-pel costs and per-part refinement in
+    k2_me_subpel_wide_kernel; shears of several pixels per frame so that the parts really move apart"""
+    seqs = [shear_seq(w, h, 4, seed=qp, amp=amp), shear_seq(w, h, 4, seed=qp + 1, stripe=40, band=16, amp=amp)]
+    stats = run_and_compare(oracle, b2, seqs, w, h, qp, R, deblock=1, transform8x8=t8, pack_levels=pack, partitions=2)
+    assert np.all(stats["parts"][1:] > 0), stats["parts"]
+
+
 def _to_fmt(fmt, y, u, v):
     """repack an I420 picture into the raw layout `fmt` (exact inverse for the formats whose conversion is a copy;
     for packed 4:2:2 the chroma is duplicated on both lines so that the vertical average returns it)"""

@@ -46,7 +46,7 @@ def coarse_seq(w, h, n, seed=0, scale=10, noise=1.0):
     return frames
 
 
-def shear_seq(w, h, n, seed=0, stripe=24, band=24):
+def shear_seq(w, h, n, seed=0, stripe=24, band=24, amp=1):
     """content whose vertical stripes / horizontal bands move by different quarter-pel amounts per frame: macroblocks
     that straddle a boundary are better predicted with 8x16 / 16x8 / 8x8 partitions (row N1)"""
     import cv2
@@ -57,8 +57,8 @@ def shear_seq(w, h, n, seed=0, stripe=24, band=24):
     sx = (X // stripe) % 3 - 1; sy = (Y // band) % 3 - 1              # -1, 0, +1 quarter-pels per frame
     frames = []
     for t in range(n):
-        xi = 4 * X + 64 + t * 2 * sx + 3 * t                           # common pan + per-stripe shear
-        yi = 4 * Y + 64 + t * 2 * sy + 2 * t
+        xi = 4 * X + 64 + t * 2 * amp * sx + 3 * t                     # common pan + per-stripe shear (amp 1: +-1/2 pel per frame)
+        yi = 4 * Y + 64 + t * 2 * amp * sy + 2 * t
         img = np.clip(B[np.ix_(yi, xi)] + rng.normal(0, 0.8, (h, w)), 0, 255).astype(np.uint8)
         u = (img[::2, ::2] // 2 + 64).astype(np.uint8)[:(h + 1) // 2, :(w + 1) // 2]
         v = (255 - img[::2, ::2] // 2 - 30).astype(np.uint8)[:(h + 1) // 2, :(w + 1) // 2]

@@ -383,7 +383,8 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
             KScope k(e, st, 3);
             if (b2_launch_me_subpel(cur[0], ref[0], e->pitch, e->stride_y, e->mbw, e->mbh, ns, e->d_mvf + om, e->d_prev_mv + om,
                                     e->lambda, c.subpel, e->d_mvq + om, e->d_cost_inter + om, e->d_pred + om * 256,
-                                    e->d_part ? e->d_part + om : nullptr, e->d_mv8 ? e->d_mv8 + om * 3 : nullptr, st))
+                                    e->d_part ? e->d_part + om : nullptr, e->d_mv8 ? e->d_mv8 + om * 3 : nullptr,
+                                    e->d_mv9 ? e->d_mv9 + om * 9 : nullptr, e->d_cost9 ? e->d_cost9 + om * 9 : nullptr, st))
                 return -1;
         }
     }

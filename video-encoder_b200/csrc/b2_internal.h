@@ -21,7 +21,8 @@ int b2_launch_convert(int fmt, const uint8_t *d_in, size_t in_stride, uint8_t *d
 int b2_launch_me_subpel(const uint8_t *d_cur, const uint8_t *d_ref, int pitch, size_t plane_stride, int mbw, int mbh,
                         int nframes, const b2_mv_t *d_mv_full, const b2_mv_t *d_pmv, int lambda, int subpel,
                         b2_mv_t *d_mv_out, uint32_t *d_cost_out, uint8_t *d_pred_out, uint8_t *d_part_out /* NULL: 16x16 only */,
-                        b2_mv_t *d_mv8_out /* [nmb][3] */, cudaStream_t st);
+                        b2_mv_t *d_mv8_out /* [nmb][3] */, const b2_mv_t *d_mv9 /* NULL, or K1<PART>'s vectors: wide partition search */,
+                        const uint32_t *d_cost9, cudaStream_t st);
 int b2_launch_intra_analyse(const uint8_t *d_y, const uint8_t *d_u, const uint8_t *d_v, int pitch, int pitchc,
                             size_t stride_y, size_t stride_c, int mbw, int mbh, int nframes, int lambda,
                             b2_mbinfo_t *d_info, uint32_t *d_c16, uint32_t *d_c4, uint32_t *d_c8 /* NULL: no I8x8 analysis */,

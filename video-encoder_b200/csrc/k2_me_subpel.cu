@@ -304,14 +304,177 @@ k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__
     }
 }
 
+// ---- wide partition search (row N1, partitions = 2) --------------------------------------------------------------------
+// K1<PART> delivered the best full-pel vector and cost of each of the nine shape parts.  This kernel picks the shape on those
+// costs (oracle: b2o_me_parts_wide) and refines every part of it on its own: patch around the part's vector, half-sample
+// planes for the part's area, 9 half-pel + 8 quarter-pel candidates with SATD over the part.  Geometry in pixels:
+__device__ __constant__ uint8_t c_part_geo[9][4] = {{0, 0, 16, 16}, {0, 0, 16, 8}, {0, 8, 16, 8}, {0, 0, 8, 16}, {8, 0, 8, 16},
+                                                    {0, 0, 8, 8},   {8, 0, 8, 8},  {0, 8, 8, 8},  {8, 8, 8, 8}};
+
+// SATD of the 4x4 block at part-local pixel (lx,ly) for the candidate displaced by (cx,cy) quarter-pels; (ox,oy) = the
+// part's origin inside the macroblock
+__device__ __forceinline__ uint32_t cand_block_satd_at(const K2Smem &s, int lx, int ly, int ox, int oy, int cx, int cy)
+{
+    const int ix = cx >> 2, iy = cy >> 2;
+    const int e = c_qpel_pair[(cy & 3) * 4 + (cx & 3)];
+    const uint8_t *pa = s.P + plane_off(e & 3, lx + ix + ((e >> 2) & 1), ly + iy + ((e >> 3) & 1));
+    const uint8_t *pb = s.P + plane_off((e >> 4) & 3, lx + ix + ((e >> 6) & 1), ly + iy + ((e >> 7) & 1));
+    int d[16];
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        const uint32_t cw = *(const uint32_t *)&s.cur[oy + ly + y][ox + lx];
+#pragma unroll
+        for (int x = 0; x < 4; x++)
+            d[y * 4 + x] = (int)((cw >> (8 * x)) & 255u) - (((int)pa[y * KP + x] + (int)pb[y * KP + x] + 1) >> 1);
+    }
+    return b2::satd4x4(d);
+}
+
+__global__ void __launch_bounds__(K2_THREADS)
+k2_me_subpel_wide_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ ref, int pitch, size_t plane_stride,
+                         int mbw, int mbh, const b2_mv_t *__restrict__ mv9, const uint32_t *__restrict__ cost9,
+                         const b2_mv_t *__restrict__ pmv, int lambda, b2_mv_t *__restrict__ mv_out, uint32_t *__restrict__ cost_out,
+                         uint8_t *__restrict__ pred_out, uint8_t *__restrict__ part_out, b2_mv_t *__restrict__ mv8_out)
+{
+    __shared__ __align__(16) K2Smem s;
+    __shared__ uint32_t s_total;
+    const int tid = threadIdx.x;
+    const int mbx = blockIdx.x, mby = blockIdx.y, frame = blockIdx.z;
+    const size_t mbi = ((size_t)frame * mbh + mby) * mbw + mbx;
+    b2_mv_t pm = {0, 0};
+    if (pmv) pm = pmv[mbi];
+    const uint8_t *cplane = cur + frame * plane_stride + (size_t)(B2_PAD + mby * 16) * pitch + B2_PAD + mbx * 16;
+    uint8_t *PG = s.P + OFF_G, *PB = s.P + OFF_B, *PH = s.P + OFF_H, *PJ = s.P + OFF_J;
+    if (tid < 64) {
+        const int r = tid >> 2, c = tid & 3;
+        *(uint32_t *)&s.cur[r][c * 4] = *(const uint32_t *)(cplane + (size_t)r * pitch + c * 4);
+    }
+    if (tid == 0) {                                          // shape on the full-pel costs
+        uint32_t bc = 0xffffffffu; int shape = 0;
+        for (int sh = 0; sh < 4; sh++) {
+            uint32_t c = (uint32_t)(lambda * c_shape_bits[sh]);
+            for (int a = 0; a < c_shape_n[sh]; a++) c += cost9[mbi * 9 + c_shape_first[sh] + a];
+            if (c < bc) { bc = c; shape = sh; }
+        }
+        s.shape = shape;
+        s_total = (uint32_t)(lambda * c_shape_bits[shape]);
+    }
+    __syncthreads();
+    const int shape = s.shape;
+    for (int a = 0; a < c_shape_n[shape]; a++) {
+        const int p = c_shape_first[shape] + a;
+        const int ox = c_part_geo[p][0], oy = c_part_geo[p][1], pw = c_part_geo[p][2], ph = c_part_geo[p][3];
+        const b2_mv_t mvf = mv9[mbi * 9 + p];
+        const uint8_t *rplane = ref + frame * plane_stride + (size_t)(B2_PAD + mby * 16 + oy + mvf.y - 3) * pitch + B2_PAD +
+                                mbx * 16 + ox + mvf.x - 3;
+        const int gw = pw + 6, gh = ph + 6;
+        for (int i = tid; i < gw * gh; i += K2_THREADS) { const int r = i / gw, c = i - r * gw; PG[r * KP + c] = rplane[(size_t)r * pitch + c]; }
+        if (tid < 9) s.cost[tid] = 0;
+        __syncthreads();
+        // unrounded horizontal half samples b1: gh rows x (pw+1) cols; vertical half samples h: (ph+1) rows x (pw+2) cols
+        for (int i = tid; i < gh * (pw + 1); i += K2_THREADS) {
+            const int r = i / (pw + 1), c = i - r * (pw + 1);
+            const uint8_t *q = PG + r * KP + c + 2;
+            s.B1[r][c] = (int16_t)b2::tap6(q[-2], q[-1], q[0], q[1], q[2], q[3]);
+        }
+        for (int i = tid; i < (ph + 1) * (pw + 2); i += K2_THREADS) {
+            const int r = i / (pw + 2), c = i - r * (pw + 2);
+            const uint8_t *q = PG + r * KP + c + 2;
+            const int v = b2::tap6(q[0], q[KP], q[2 * KP], q[3 * KP], q[4 * KP], q[5 * KP]);
+            PH[r * KP + c] = (uint8_t)b2_clip255((v + 16) >> 5);
+        }
+        __syncthreads();
+        for (int i = tid; i < (ph + 2) * (pw + 1); i += K2_THREADS) {     // b: Y = r-1 -> B1 row r+2
+            const int r = i / (pw + 1), c = i - r * (pw + 1);
+            PB[r * KP + c] = (uint8_t)b2_clip255((s.B1[r + 2][c] + 16) >> 5);
+        }
+        for (int i = tid; i < (ph + 1) * (pw + 1); i += K2_THREADS) {     // j: Y = r-1 -> B1 rows r..r+5
+            const int r = i / (pw + 1), c = i - r * (pw + 1);
+            const int v = b2::tap6(s.B1[r][c], s.B1[r + 1][c], s.B1[r + 2][c], s.B1[r + 3][c], s.B1[r + 4][c], s.B1[r + 5][c]);
+            PJ[r * KP + c] = (uint8_t)b2_clip255((v + 512) >> 10);
+        }
+        __syncthreads();
+        const int nbx = pw >> 2, nb = nbx * (ph >> 2);       // 4x4 blocks of the part
+        if (tid < 9 * nb) {
+            const int cand = tid / nb, j = tid - cand * nb;
+            const uint32_t v = cand_block_satd_at(s, (j % nbx) * 4, (j / nbx) * 4, ox, oy, 2 * c_subpel_off[cand][0], 2 * c_subpel_off[cand][1]);
+            atomicAdd(&s.cost[cand], v);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t best = 0xffffffffu; int bi = 0;
+            for (int k = 0; k < 9; k++) {
+                const int mx = mvf.x * 4 + 2 * c_subpel_off[k][0], my = mvf.y * 4 + 2 * c_subpel_off[k][1];
+                const uint32_t c = s.cost[k] + (uint32_t)(lambda * (b2_mvbits(mx - pm.x) + b2_mvbits(my - pm.y)));
+                if (c < best) { best = c; bi = k; }
+            }
+            s.best = bi;
+            s.cost[0] = best;
+            for (int k = 1; k < 9; k++) s.cost[k] = 0;
+        }
+        __syncthreads();
+        const int hx = 2 * c_subpel_off[s.best][0], hy = 2 * c_subpel_off[s.best][1];
+        if (tid < 8 * nb) {
+            const int cand = 1 + tid / nb, j = tid % nb;
+            const uint32_t v = cand_block_satd_at(s, (j % nbx) * 4, (j / nbx) * 4, ox, oy, hx + c_subpel_off[cand][0], hy + c_subpel_off[cand][1]);
+            atomicAdd(&s.cost[cand], v);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t best = s.cost[0];
+            int bx = hx, by = hy;
+            for (int k = 1; k < 9; k++) {
+                const int dx = hx + c_subpel_off[k][0], dy = hy + c_subpel_off[k][1];
+                const uint32_t c = s.cost[k] + (uint32_t)(lambda * (b2_mvbits(mvf.x * 4 + dx - pm.x) + b2_mvbits(mvf.y * 4 + dy - pm.y)));
+                if (c < best) { best = c; bx = dx; by = dy; }
+            }
+            s_total += best;
+            s.best = (bx & 0xff) | ((by & 0xff) << 8);
+            b2_mv_t o;
+            o.x = (int16_t)(mvf.x * 4 + bx); o.y = (int16_t)(mvf.y * 4 + by);
+            for (int q = 0; q < 4; q++) {                    // quadrants covered by this part
+                const int qx = (q & 1) * 8, qy = (q >> 1) * 8;
+                if (qx >= ox && qx < ox + pw && qy >= oy && qy < oy + ph) {
+                    if (q == 0) mv_out[mbi] = o;
+                    else mv8_out[mbi * 3 + q - 1] = o;
+                }
+            }
+        }
+        __syncthreads();
+        {   // the part's motion-compensated prediction -> K5
+            const int cx = (int)(int8_t)(s.best & 0xff), cy = (int)(int8_t)((s.best >> 8) & 0xff);
+            const int ix = cx >> 2, iy = cy >> 2;
+            const int e = c_qpel_pair[(cy & 3) * 4 + (cx & 3)];
+            const int wq = pw >> 2;                          // 4-pixel words per row
+            if (tid < wq * ph) {
+                const int r = tid / wq, c = (tid - r * wq) * 4;
+                const uint8_t *pa = s.P + plane_off(e & 3, c + ix + ((e >> 2) & 1), r + iy + ((e >> 3) & 1));
+                const uint8_t *pb = s.P + plane_off((e >> 4) & 3, c + ix + ((e >> 6) & 1), r + iy + ((e >> 7) & 1));
+                uint32_t w = 0;
+#pragma unroll
+                for (int x = 0; x < 4; x++) w |= (uint32_t)(((int)pa[x] + (int)pb[x] + 1) >> 1) << (8 * x);
+                *(uint32_t *)(pred_out + mbi * 256 + (oy + r) * 16 + ox + c) = w;
+            }
+        }
+        __syncthreads();                                     // planes are rebuilt for the next part
+    }
+    if (tid == 0) { cost_out[mbi] = s_total; part_out[mbi] = (uint8_t)shape; }
+}
+
 }  // namespace
 
 int b2_launch_me_subpel(const uint8_t *d_cur, const uint8_t *d_ref, int pitch, size_t plane_stride, int mbw, int mbh,
                         int nframes, const b2_mv_t *d_mv_full, const b2_mv_t *d_pmv, int lambda, int subpel,
                         b2_mv_t *d_mv_out, uint32_t *d_cost_out, uint8_t *d_pred_out, uint8_t *d_part_out, b2_mv_t *d_mv8_out,
-                        cudaStream_t st)
+                        const b2_mv_t *d_mv9, const uint32_t *d_cost9, cudaStream_t st)
 {
     dim3 grid(mbw, mbh, nframes);
+    if (d_mv9 && d_part_out && subpel) {
+        k2_me_subpel_wide_kernel<<<grid, K2_THREADS, 0, st>>>(d_cur, d_ref, pitch, plane_stride, mbw, mbh, d_mv9, d_cost9, d_pmv, lambda,
+                                                               d_mv_out, d_cost_out, d_pred_out, d_part_out, d_mv8_out);
+        B2_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     if (d_part_out && subpel)
         k2_me_subpel_kernel<true><<<grid, K2_THREADS, 0, st>>>(d_cur, d_ref, pitch, plane_stride, mbw, mbh, d_mv_full, d_pmv,
                                                                lambda, subpel, d_mv_out, d_cost_out, d_pred_out, d_part_out, d_mv8_out);

@@ -150,7 +150,7 @@ b2_t *b2_encoder_open(b2_param_t *p)
     cfg.in_fmt = p->i_csp_in; cfg.in_ring = h->S == 1 ? 1 : h->L; cfg.merange = p->i_merange ? p->i_merange : 16; cfg.qp = h->qp;
     cfg.subpel = p->b_subpel; cfg.intra_in_p = p->b_intra_in_p; cfg.profile = 0; cfg.deblock = p->b_deblocking_filter;
     cfg.transform8x8 = p->b_transform_8x8 != 0;
-    cfg.partitions = p->b_partitions != 0;
+    cfg.partitions = p->b_partitions < 0 ? 0 : (p->b_partitions > 2 ? 2 : p->b_partitions);
     cfg.pack_levels = 1;                              /* only blocks with non-zero levels cross PCIe (K9) */
     h->eng = b2_engine_create(&cfg);
     if (!h->eng) { free(h); return NULL; }
