@@ -46,72 +46,111 @@ static const uint8_t sig8_inc[63] = {0,  1,  2,  3,  4,  5,  5,  4,  4,  3,  3, 
 static const uint8_t last8_inc[63] = {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2,
                                       3, 3, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 6, 6, 6, 6, 7, 7, 7, 7, 8, 8, 8};
 
-/* ---- arithmetic encoder (9.3.4.2) ------------------------------------------------------------------*/
+/* ---- arithmetic encoder (9.3.4.2) --------------------------------------------------------------------*/
+/* Same interval arithmetic as Figures 9-7..9-12, organised for speed: instead of one PutBit per renormalisation shift
+ * (with its outstanding-bit loop) the low end of the interval is kept in a 32-bit register together with `queue + 18`
+ * not-yet-written bits; whole bytes leave at once, a carry is added to the last written byte and resolved through a
+ * count of outstanding 0xff bytes.  State transitions and renormalisation shifts come from small tables. */
 typedef struct {
-    bs_t *bs;
+    uint8_t *p, *start, *end;   /* output cursor inside the RBSP buffer                         */
     uint32_t low, range;
-    int outstanding, first;
+    int queue;                  /* bits pending in `low` beyond the last byte boundary, minus 18 */
+    int outstanding;            /* 0xff bytes waiting for a possible carry                      */
+    int overflow;
     uint8_t state[1024];        /* (pStateIdx << 1) | valMPS */
 } cabac_t;
 
+static uint8_t cabac_next[128][2];          /* state after coding bin b in state s */
+static uint8_t cabac_shift[64];             /* renormalisation shift for range >> 3 */
+static int cabac_tables_ready;
+
+static void cabac_tables(void)
+{
+    for (int st = 0; st < 128; st++) {
+        const int ps = st >> 1, mps = st & 1;
+        cabac_next[st][mps] = (uint8_t)(((ps < 62 ? ps + 1 : 62) << 1) | mps);
+        cabac_next[st][1 - mps] = (uint8_t)((trans_lps[ps] << 1) | (ps == 0 ? 1 - mps : mps));
+    }
+    for (int i = 0; i < 64; i++) {
+        int r = i << 3, sh = 0;
+        if (r == 0) r = 6;                   /* the smallest range that can occur is 6 (LPS of the top states) */
+        while ((r << sh) < 256) sh++;
+        cabac_shift[i] = (uint8_t)sh;
+    }
+    cabac_tables_ready = 1;
+}
+
 static void cabac_init(cabac_t *c, bs_t *bs, int table, int qp)
 {
-    c->bs = bs; c->low = 0; c->range = 510; c->outstanding = 0; c->first = 1;
+    if (!cabac_tables_ready) cabac_tables();
+    c->p = c->start = bs->buf + bs->pos; c->end = bs->buf + bs->cap;
+    c->low = 0; c->range = 510; c->queue = -9; c->outstanding = 0; c->overflow = 0;     /* the first bit is not written */
     for (int i = 0; i < 1024; i++) {
         int pre = ((b2h_cabac_ctx_init[table][i][0] * qp) >> 4) + b2h_cabac_ctx_init[table][i][1];
         pre = pre < 1 ? 1 : (pre > 126 ? 126 : pre);
         c->state[i] = pre <= 63 ? (uint8_t)((63 - pre) << 1) : (uint8_t)(((pre - 64) << 1) | 1);
     }
 }
-static inline void cabac_put_bit(cabac_t *c, int b)
+/* one finished byte (plus a possible carry in bit 8) leaves the register */
+static inline void cabac_emit(cabac_t *c, uint32_t out)
 {
-    if (c->first) c->first = 0;
-    else bs_put(c->bs, 1, (uint32_t)b);
-    while (c->outstanding > 0) { bs_put(c->bs, 1, (uint32_t)(1 - b)); c->outstanding--; }
+    if ((out & 0xff) == 0xff) { c->outstanding++; return; }
+    const uint32_t carry = out >> 8;
+    if (c->p + c->outstanding + 1 >= c->end) { c->overflow = 1; c->outstanding = 0; return; }
+    if (carry && c->p > c->start) c->p[-1]++;               /* cannot ripple further: an 0xff byte would have been held back */
+    while (c->outstanding > 0) { *c->p++ = (uint8_t)(carry - 1); c->outstanding--; }
+    *c->p++ = (uint8_t)out;
 }
-static inline void cabac_renorm(cabac_t *c)
+static inline void cabac_putbyte(cabac_t *c)
 {
-    while (c->range < 256) {
-        if (c->low < 256) cabac_put_bit(c, 0);
-        else if (c->low >= 512) { c->low -= 512; cabac_put_bit(c, 1); }
-        else { c->low -= 256; c->outstanding++; }
-        c->range <<= 1; c->low <<= 1;
+    if (c->queue >= 0) {
+        const uint32_t out = c->low >> (c->queue + 10);
+        c->low &= (0x400u << c->queue) - 1;
+        c->queue -= 8;
+        cabac_emit(c, out);
     }
 }
 static inline void cabac_encode(cabac_t *c, int ctx, int bin)
 {
-    uint8_t st = c->state[ctx];
-    const int ps = st >> 1, mps = st & 1;
-    const uint32_t rlps = range_lps[ps][(c->range >> 6) & 3];
+    const uint8_t st = c->state[ctx];
+    const uint32_t rlps = range_lps[st >> 1][(c->range >> 6) & 3];
     c->range -= rlps;
-    if (bin != mps) {
-        c->low += c->range; c->range = rlps;
-        st = (uint8_t)((trans_lps[ps] << 1) | (ps == 0 ? 1 - mps : mps));
-    } else {
-        st = (uint8_t)(((ps < 62 ? ps + 1 : 62) << 1) | mps);
-    }
-    c->state[ctx] = st;
-    cabac_renorm(c);
+    if (bin != (st & 1)) { c->low += c->range; c->range = rlps; }
+    c->state[ctx] = cabac_next[st][bin];
+    const int sh = cabac_shift[c->range >> 3];
+    c->range <<= sh; c->low <<= sh; c->queue += sh;
+    cabac_putbyte(c);
 }
 static inline void cabac_bypass(cabac_t *c, int bin)
 {
     c->low <<= 1;
     if (bin) c->low += c->range;
-    if (c->low >= 1024) { cabac_put_bit(c, 1); c->low -= 1024; }
-    else if (c->low < 512) cabac_put_bit(c, 0);
-    else { c->low -= 512; c->outstanding++; }
+    c->queue += 1;
+    cabac_putbyte(c);
 }
+/* end_of_slice_flag / I_PCM flag.  bin = 1 also flushes (9.3.4.5): all pending bits of `low` are written, the lowest one
+ * forced to 1 -- it is the rbsp_stop_one_bit -- and the last byte is padded with zeros */
 static void cabac_terminate(cabac_t *c, int bin)
 {
     c->range -= 2;
-    if (bin) {
-        c->low += c->range; c->range = 2;
-        cabac_renorm(c);
-        cabac_put_bit(c, (int)((c->low >> 9) & 1));
-        bs_put(c->bs, 2, ((c->low >> 7) & 3) | 1);      /* the final 1 is the rbsp_stop_one_bit */
-    } else {
-        cabac_renorm(c);
+    if (!bin) {
+        const int sh = cabac_shift[c->range >> 3];
+        c->range <<= sh; c->low <<= sh; c->queue += sh;
+        cabac_putbyte(c);
+        return;
     }
+    c->low += c->range;
+    c->low |= 1;
+    int nb = c->queue + 18;                                  /* pending bits (a carry may sit above them) */
+    const int pad = (8 - (nb & 7)) & 7;
+    uint64_t v = (uint64_t)c->low << pad;
+    nb += pad;
+    while (nb > 0) {
+        cabac_emit(c, (uint32_t)(v >> (nb - 8)));
+        v &= ((uint64_t)1 << (nb - 8)) - 1;
+        nb -= 8;
+    }
+    while (c->outstanding > 0 && c->p < c->end) { *c->p++ = 0xff; c->outstanding--; }
 }
 /* k-th order Exp-Golomb suffix in bypass mode (9.3.2.3) */
 static void cabac_egk(cabac_t *c, unsigned v, int k)
@@ -401,7 +440,7 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
             e->mbf[mi] = (uint8_t)flags;
             cabac_terminate(c, mi == nmb - 1);                              /* end_of_slice_flag */
         }
-    if (b->nbits) bs_put(b, 8 - b->nbits, 0);                               /* rbsp_alignment_zero_bit */
-    if (b->overflow) return 0;
+    b->pos = (size_t)(c->p - b->buf);                                       /* the flush already byte-aligned the RBSP */
+    if (b->overflow || c->overflow) return 0;
     return nal_pack(is_p ? 2 : 3, is_p ? B2H_NAL_SLICE : B2H_NAL_IDR, e->rbsp, b->pos, out, cap);
 }
