@@ -316,3 +316,54 @@ def convert_to_i420(fmt, w, h, planes):
     if rc != 0:
         raise ValueError("unsupported conversion")
     return y, u, v
+
+
+# ---- row N4: pre-filters (oracle/b2o_filters.c; parity unpinned, see there) ------------------------------------------------
+def _plane_dims(fmt, w, h):
+    if fmt == "yuv420p":
+        return [(w, h), ((w + 1) // 2, (h + 1) // 2), ((w + 1) // 2, (h + 1) // 2)]
+    if fmt == "yuv422p":
+        return [(w, h), ((w + 1) // 2, h), ((w + 1) // 2, h)]
+    return [(w, h), ((w + 3) // 4, h), ((w + 3) // 4, h)]
+
+
+class Hqdn3d:
+    """stateful denoiser over a sequence of (y,u,v) frames"""
+
+    def __init__(self, w, h, fmt="yuv420p", ls=4.0, cs=None, lt=None, ct=None):
+        cs = 3.0 * ls / 4.0 if cs is None else cs
+        lt = 6.0 * ls / 4.0 if lt is None else lt
+        ct = (lt * cs / ls if ls > 0 else 0.0) if ct is None else ct
+        L = lib()
+        L.b2o_hqdn3d_coefs.argtypes = [C.c_double, C.c_void_p]
+        self.ct = []
+        for s in (ls, lt, cs, ct):
+            t = np.zeros(8192, np.int32); L.b2o_hqdn3d_coefs(float(s), _p(t)); self.ct.append(t)
+        self.dims = _plane_dims(fmt, w, h)
+        self.ant = [np.zeros(pw * ph, np.uint16) for pw, ph in self.dims]
+        self.first = 1
+
+    def __call__(self, frame):
+        out = []
+        for p, (pw, ph) in enumerate(self.dims):
+            src = np.ascontiguousarray(frame[p], np.uint8); dst = np.zeros((ph, pw), np.uint8)
+            lib().b2o_hqdn3d_plane(_p(src), pw, _p(dst), pw, pw, ph, _p(self.ant[p]), self.first, _p(self.ct[2 if p else 0]), _p(self.ct[3 if p else 1]))
+            out.append(dst)
+        self.first = 0
+        return tuple(out)
+
+
+def yadif_sequence(frames, w, h, fmt="yuv420p", tff=1):
+    """yadif mode 0 over a whole sequence: first frame is its own predecessor, last frame its own successor"""
+    dims = _plane_dims(fmt, w, h)
+    out = []
+    for t in range(len(frames)):
+        prev, cur, nxt = frames[max(t - 1, 0)], frames[t], frames[min(t + 1, len(frames) - 1)]
+        planes = []
+        for p, (pw, ph) in enumerate(dims):
+            a, b, c = [np.ascontiguousarray(f[p], np.uint8) for f in (prev, cur, nxt)]
+            dst = np.zeros((ph, pw), np.uint8)
+            lib().b2o_yadif_plane(_p(a), _p(b), _p(c), pw, _p(dst), pw, pw, ph, tff)
+            planes.append(dst)
+        out.append(tuple(planes))
+    return out

@@ -9,7 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_functions():
     names = set()
-    for hdr in ("b2enc.h", "b2enc_engine.h", "b2enc_kernels.h"):
+    for hdr in ("b2enc.h", "b2enc_engine.h", "b2enc_kernels.h", "b2enc_filters.h"):
         src = open(os.path.join(ROOT, "include", hdr)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         names |= set(re.findall(r"\b(b2k?_[a-z0-9_]+)\s*\(", src))

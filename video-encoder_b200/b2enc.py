@@ -449,3 +449,64 @@ class DropInEncoder:
             self.L.b2_picture_clean(C.byref(self.pic_in))
             self.L.b2_encoder_close(self.h_enc)
             self.h_enc = None
+
+
+# ---- pre-filter stage binding (include/b2enc_filters.h) ---------------------------------------------------------------------
+class FilterGraph:
+    """push / poll / pull like the reference drives its libavfilter graph (av_encode.c:962, :525-560)"""
+
+    def __init__(self, w, h, filters, fmt="yuv420p", device=0):
+        require_gpu()
+        L = self.L = lib()
+        L.b2_filter_graph_create.restype = C.c_void_p
+        L.b2_filter_graph_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        L.b2_filter_add_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]
+        L.b2_filter_poll_frame.argtypes = [C.c_void_p]
+        L.b2_filter_get_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+        L.b2_filter_flush.argtypes = [C.c_void_p]; L.b2_filter_graph_free.argtypes = [C.c_void_p]
+        self.g = L.b2_filter_graph_create(w, h, FMT[fmt], filters.encode() if filters is not None else None, device)
+        if not self.g:
+            raise RuntimeError("b2_filter_graph_create failed")
+        cw = (w + 1) // 2 if fmt != "yuv411p" else (w + 3) // 4
+        ch = (h + 1) // 2 if fmt == "yuv420p" else h
+        self.dims = [(w, h), (cw, ch), (cw, ch)]
+
+    def add(self, frame, pts=0, tff=1):
+        planes = [np.ascontiguousarray(p, np.uint8) for p in frame]
+        sp = (C.c_void_p * 3)(*[p.ctypes.data for p in planes]); ss = (C.c_int * 3)(*[p.shape[1] for p in planes])
+        if self.L.b2_filter_add_frame(self.g, sp, ss, pts, tff) != 0:
+            raise RuntimeError("b2_filter_add_frame failed")
+
+    def poll(self):
+        return self.L.b2_filter_poll_frame(self.g)
+
+    def get(self, pad=0):
+        out = [np.zeros((ph, pw + pad), np.uint8) for pw, ph in self.dims]
+        dp = (C.c_void_p * 3)(*[p.ctypes.data for p in out]); ds = (C.c_int * 3)(*[p.shape[1] for p in out])
+        pts = C.c_int64(0)
+        r = self.L.b2_filter_get_frame(self.g, dp, ds, C.byref(pts))
+        if r < 0:
+            raise RuntimeError("b2_filter_get_frame failed")
+        if r == 0:
+            return None
+        return tuple(o[:, :pw] for o, (pw, ph) in zip(out, self.dims)), pts.value
+
+    def flush(self):
+        if self.L.b2_filter_flush(self.g) != 0:
+            raise RuntimeError("b2_filter_flush failed")
+
+    def run(self, frames, tff=1):
+        """whole sequence in, whole sequence out (frames in display order)"""
+        out = []
+        for t, f in enumerate(frames):
+            self.add(f, pts=100 + t, tff=tff)
+            while self.poll() > 0:
+                out.append(self.get(pad=3))
+        self.flush()
+        while self.poll() > 0:
+            out.append(self.get(pad=3))
+        return out
+
+    def close(self):
+        if self.g:
+            self.L.b2_filter_graph_free(self.g); self.g = None
