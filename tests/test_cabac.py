@@ -127,3 +127,19 @@ def test_wide_partition_search_decodes_and_beats_local(oracle, w, h, qp, amp, ca
             spread = max(int(np.abs(i["mv8"][:, 2, 0].astype(int) - i["mvx"]).max()) for i in infos[1:])
             assert spread > 8, "parts never moved more than 2 px apart: %d" % spread
     assert sizes[2] < sizes[1]
+
+
+@pytest.mark.parametrize("cabac", [0, 1])
+def test_all_features_extremes_decode(oracle, cabac):
+    """one-macroblock pictures, saturated noise, flat and ramp content at QP 10 and 51 with every tool on"""
+    rng = np.random.default_rng(23)
+    for (w, h) in ((16, 16), (32, 16), (16, 48), (70, 38)):
+        cw, ch = (w + 1) // 2, (h + 1) // 2
+        noise = [((rng.integers(0, 2, (h, w)) * 255).astype(np.uint8), (rng.integers(0, 2, (ch, cw)) * 255).astype(np.uint8),
+                  (rng.integers(0, 2, (ch, cw)) * 255).astype(np.uint8)) for _ in range(3)]
+        ramp = [((np.add.outer(np.arange(h) * 3, np.arange(w) * 2) + 5 * t).astype(np.uint8), np.full((ch, cw), 100 + t, np.uint8),
+                 np.full((ch, cw), 140 - t, np.uint8)) for t in range(3)]
+        for frames in (noise, ramp):
+            for qp in (10, 51):
+                for pm in (1, 2):
+                    _roundtrip(oracle, frames, w, h, qp=qp, merange=16, gop=32, cabac=cabac, deblock=1, transform8x8=1, partitions=pm)

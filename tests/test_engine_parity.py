@@ -142,6 +142,22 @@ def test_engine_wide_partition_search(oracle, b2, w, h, qp, R, amp, t8, pack):
     assert np.all(stats["parts"][1:] > 0), stats["parts"]
 
 
+@pytest.mark.parametrize("pm", [1, 2])
+def test_engine_all_features_extremes(oracle, b2, pm):
+    """rows N1-N2 together on the edge cases the reference's domain has: one-macroblock pictures, saturated noise and flat
+    content, QP 10 and 51, odd sizes -- deblocking + 8x8 transform / intra 8x8 + partitions + packed levels"""
+    rng = np.random.default_rng(17)
+    for (w, h) in ((16, 16), (32, 16), (16, 48), (70, 38)):
+        cw, ch = (w + 1) // 2, (h + 1) // 2
+        noise = [((rng.integers(0, 2, (h, w)) * 255).astype(np.uint8), (rng.integers(0, 2, (ch, cw)) * 255).astype(np.uint8),
+                  (rng.integers(0, 2, (ch, cw)) * 255).astype(np.uint8)) for _ in range(3)]
+        flat = [(np.full((h, w), 90, np.uint8), np.full((ch, cw), 128, np.uint8), np.full((ch, cw), 128, np.uint8))] * 3
+        ramp = [((np.add.outer(np.arange(h) * 3, np.arange(w) * 2) + 5 * t).astype(np.uint8), np.full((ch, cw), 100 + t, np.uint8),
+                 np.full((ch, cw), 140 - t, np.uint8)) for t in range(3)]
+        for qp in (10, 51):
+            run_and_compare(oracle, b2, [noise, flat, ramp], w, h, qp, 16, deblock=1, transform8x8=1, partitions=pm, pack_levels=1)
+
+
 def _to_fmt(fmt, y, u, v):
     """repack an I420 picture into the raw layout `fmt` (exact inverse for the formats whose conversion is a copy;
     for packed 4:2:2 the chroma is duplicated on both lines so that the vertical average returns it)"""
