@@ -7,8 +7,8 @@
 // (2R+1)^2 candidates x 256 pixel-SADs = (2R+1)^2 x 64 VABSDIFF4 lane-instructions.
 //
 // Design:
-//  * One CTA searches a strip of 8 horizontally adjacent macroblocks of one frame.  The
-//    (128+2R) x (16+2R) search window of the *padded* reference plane and the 128x16 current
+//  * One CTA searches a strip of NMB = 6 horizontally adjacent macroblocks of one frame.  The
+//    (16 NMB + 2R) x (16+2R) search window of the *padded* reference plane and the 16 NMB x 16 current
 //    tile are fetched by TMA (cp.async.bulk.tensor.3d), never leaving the allocation because
 //    every plane carries a 64-px replicated border.
 //  * Operand supply, not the ALU, is the first limiter (32 shared-memory words/clk/SM vs 64
@@ -26,7 +26,17 @@
 
 namespace {
 
-constexpr int NMB = 8;          // macroblocks per CTA strip
+// Strip width and residency, tuned on the B200 (scripts/k1_variants.sh + k1_variant_probe.py, 1080p +-32, 32 frames):
+//   NMB x CTAs/SM :  8x2 0.859   10x2 0.874   12x2 0.879   5x3 0.885   6x3 0.888   7x3 0.881   4x3 0.871   of the VABSDIFF4 peak.
+// Three resident CTAs (80 registers, 67 KB of shared memory each) keep the ALU pipe fed while one of them waits for its
+// TMA window / expands it; a wider strip only amortises the halo.
+#ifndef B2_K1_NMB
+#define B2_K1_NMB 6
+#endif
+#ifndef B2_K1_MINCTAS
+#define B2_K1_MINCTAS 3
+#endif
+constexpr int NMB = B2_K1_NMB;  // macroblocks per CTA strip (tuning: scripts/k1_variants.sh)
 
 template <int R> struct K1Cfg;
 template <> struct K1Cfg<32> { static constexpr int K = 13, NG = 5; };   // 65 = 5 x 13
@@ -56,7 +66,7 @@ template <int R> struct K1Smem {
 // sweeps the top half of the current MB, packs the two 8x8 SADs of its K candidates into K registers, sweeps the bottom
 // half, and then forms 9 sums / keys per candidate (9 running minima, 9 CREDUX.MIN + 9 shared atomicMin per warp task).
 template <int R, int NTHREADS, bool PART>
-__global__ void __launch_bounds__(NTHREADS, 2)
+__global__ void __launch_bounds__(NTHREADS, PART ? 2 : B2_K1_MINCTAS)      // the partition variant needs ~90 registers: two CTAs
 k1_me_fullpel_kernel(const __grid_constant__ CUtensorMap tm_cur,
                      const __grid_constant__ CUtensorMap tm_ref,
                      int mbw, int mbh, const b2_mv_t *__restrict__ pmv, int lambda,
@@ -313,6 +323,8 @@ int k1_threads()
 }
 
 }  // namespace
+
+extern "C" int b2_k1_strip_mbs(void) { return NMB; }
 
 // window/current-tile box sizes needed to build the tensor maps
 extern "C" int b2_k1_window_box(int R, int *bw, int *bh)
