@@ -174,7 +174,7 @@ static int engine_alloc(b2_engine *e)
         ENG_OK(cudaEventCreateWithFlags(&gr.ev_join, cudaEventDisableTiming));
         gr.ev_k0.resize(c.in_ring); gr.h2d_pending.assign(c.in_ring, 0);
         for (int r = 0; r < c.in_ring; r++) ENG_OK(cudaEventCreateWithFlags(&gr.ev_k0[r], cudaEventDisableTiming));
-        if (b2_make_plane_tmap(&gr.tm_cur, e->d_cur[0] + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, 16 * b2_k1_strip_mbs(), 16)) return -1;
+        if (b2_make_plane_tmap(&gr.tm_cur, e->d_cur[0] + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, 16 * b2_k1_strip_mbs(c.merange), 16)) return -1;
         if (b2_make_plane_tmap(&gr.tm_ref[0], e->d_rec[0][0] + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, bw, bh)) return -1;
         if (b2_make_plane_tmap(&gr.tm_ref[1], e->d_rec[1][0] + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, bw, bh)) return -1;
     }

@@ -12,7 +12,7 @@ int b2_launch_extend_border(uint8_t *d_planes, int pitch, int rows, int nplanes,
 int b2_launch_extend_border_yuv(uint8_t *d_y, uint8_t *d_u, uint8_t *d_v, int pitch, int rows, int pitchc, int rowsc,
                                 size_t stride_y, size_t stride_c, int w16, int h16, int nframes, cudaStream_t st);
 extern "C" int b2_k1_window_box(int R, int *bw, int *bh);
-extern "C" int b2_k1_strip_mbs(void);                     // macroblocks per K1 strip: the current-tile box is {16 * this, 16, 1}
+extern "C" int b2_k1_strip_mbs(int R);                    // macroblocks per K1 strip: the current-tile box is {16 * this, 16, 1}
 int b2_launch_me_fullpel(int R, const CUtensorMap *tm_cur, const CUtensorMap *tm_ref, int mbw, int mbh,
                          int nframes, const b2_mv_t *d_pmv, int lambda, b2_mv_t *d_mv, uint32_t *d_cost,
                          b2_mv_t *d_mv9 /* NULL, or [nmb][9] best vector of every shape part */, uint32_t *d_cost9, cudaStream_t st);

@@ -71,7 +71,7 @@ static int me_fullpel_impl(const uint8_t *cur_y, const uint8_t *ref_y, int w, in
         B2_CUDA_OK(cudaMemcpy(d_pmv.p, pmv, nmb * sizeof(b2_mv_t), cudaMemcpyHostToDevice));
     }
     CUtensorMap tm_cur, tm_ref;
-    if (b2_make_plane_tmap(&tm_cur, d_cur.p, pitch, rows, nframes, 16 * b2_k1_strip_mbs(), 16)) return -1;
+    if (b2_make_plane_tmap(&tm_cur, d_cur.p, pitch, rows, nframes, 16 * b2_k1_strip_mbs(merange), 16)) return -1;
     if (b2_make_plane_tmap(&tm_ref, d_ref.p, pitch, rows, nframes, bw, bh)) return -1;
     if (b2_launch_me_fullpel(merange, &tm_cur, &tm_ref, mbw, mbh, nframes, (const b2_mv_t *)d_pmv.p, lambda,
                              (b2_mv_t *)d_mv.p, (uint32_t *)d_cost.p, (b2_mv_t *)d_mv9.p, (uint32_t *)d_cost9.p, 0))

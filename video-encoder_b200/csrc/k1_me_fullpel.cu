@@ -36,13 +36,17 @@ namespace {
 #ifndef B2_K1_MINCTAS
 #define B2_K1_MINCTAS 3
 #endif
-constexpr int NMB = B2_K1_NMB;  // macroblocks per CTA strip (tuning: scripts/k1_variants.sh)
+#ifndef B2_K1_NMB16
+#define B2_K1_NMB16 12      // +-16: the window is small (33 x 3 dy groups = 99 lane-tasks per MB), a wider strip fills the 8 warps' rounds
+#endif
 
 template <int R> struct K1Cfg;
-template <> struct K1Cfg<32> { static constexpr int K = 13, NG = 5; };   // 65 = 5 x 13
-template <> struct K1Cfg<16> { static constexpr int K = 11, NG = 3; };   // 33 = 3 x 11
+// NMB = macroblocks per CTA strip (tuning: scripts/k1_variants.sh)
+template <> struct K1Cfg<32> { static constexpr int K = 13, NG = 5, NMB = B2_K1_NMB; };     // 65 = 5 x 13
+template <> struct K1Cfg<16> { static constexpr int K = 11, NG = 3, NMB = B2_K1_NMB16; };   // 33 = 3 x 11
 
 template <int R> struct K1Smem {
+    static constexpr int NMB = K1Cfg<R>::NMB;
     static constexpr int ND = 2 * R + 1;
     static constexpr int WIN_W = NMB * 16 + 2 * R;      // bytes per raw window row
     static constexpr int WIN_H = 16 + 2 * R;
@@ -75,7 +79,7 @@ k1_me_fullpel_kernel(const __grid_constant__ CUtensorMap tm_cur,
 {
     using S = K1Smem<R>;
     constexpr int NWARPS = NTHREADS / 32;
-    constexpr int K = K1Cfg<R>::K, NG = K1Cfg<R>::NG, ND = S::ND;
+    constexpr int K = K1Cfg<R>::K, NG = K1Cfg<R>::NG, ND = S::ND, NMB = K1Cfg<R>::NMB;
     static_assert(K * NG == ND, "dy groups must tile the search range");
 
     extern __shared__ uint8_t smem_raw_[];
@@ -296,6 +300,7 @@ int launch_k1p(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, int mbw, in
                                         K1Smem<R>::TOTAL));
         attr_set = true;
     }
+    constexpr int NMB = K1Cfg<R>::NMB;
     dim3 grid((mbw + NMB - 1) / NMB, mbh, nframes);
     k1_me_fullpel_kernel<R, NT, PART><<<grid, NT, K1Smem<R>::TOTAL, st>>>(tm_cur, tm_ref, mbw, mbh, pmv, lambda, mv_out, cost_out,
                                                                             mv9_out, cost9_out);
@@ -324,13 +329,13 @@ int k1_threads()
 
 }  // namespace
 
-extern "C" int b2_k1_strip_mbs(void) { return NMB; }
+extern "C" int b2_k1_strip_mbs(int R) { return R == 16 ? K1Cfg<16>::NMB : K1Cfg<32>::NMB; }
 
 // window/current-tile box sizes needed to build the tensor maps
 extern "C" int b2_k1_window_box(int R, int *bw, int *bh)
 {
     if (R != 16 && R != 32) return -1;
-    *bw = NMB * 16 + 2 * R;
+    *bw = b2_k1_strip_mbs(R) * 16 + 2 * R;
     *bh = 16 + 2 * R;
     return 0;
 }
