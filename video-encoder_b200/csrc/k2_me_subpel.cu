@@ -130,31 +130,48 @@ k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__
     if (PART && tid < 36) s.costq[tid >> 2][tid & 3] = 0;
     __syncthreads();
 
-    // horizontal unrounded half samples b1 (22 rows x 17 cols) and vertical half samples h (17 rows x 18 cols)
+    // Half-sample planes with SLIDING WINDOWS: one thread walks a whole row (b1) or column (h, j), so that every sample is
+    // loaded once and feeds six outputs -- 3 x fewer instructions than one 6-tap gather per output (K2 is issue-bound).
+    // b1: unrounded horizontal half samples, 22 rows x 17 cols (warp 0, lane = row); h: vertical half samples, 17 rows x 18
+    // cols (warp 1, lane = column).
     {
-        const int c = tid % 17, r0 = tid / 17;              // 153 threads -> 9 rows per pass
-        if (tid < 153)
-            for (int r = r0; r < 22; r += 9) {
-                const uint8_t *q = PG + r * KP + c + 2;       // row r <-> Y=r-3, col c <-> X=c-1
-                s.B1[r][c] = (int16_t)b2::tap6(q[-2], q[-1], q[0], q[1], q[2], q[3]);
+        const int warp = tid >> 5, lane = tid & 31;
+        if (warp == 0 && lane < 22) {
+            const uint32_t *row = (const uint32_t *)(PG + lane * KP);             // 24-byte rows: word aligned
+            int g[24];
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                const uint32_t wv = row[i];
+                g[4 * i] = wv & 255; g[4 * i + 1] = (wv >> 8) & 255; g[4 * i + 2] = (wv >> 16) & 255; g[4 * i + 3] = wv >> 24;
             }
-        const int c2 = tid % 18, r2 = tid / 18;             // 144 threads -> 8 rows per pass
-        if (tid < 144)
-            for (int r = r2; r < 17; r += 8) {                // Y=r-1, X=c2-1 ; G[Y+3][X+3] = G[r+2][c2+2]
-                const uint8_t *q = PG + r * KP + c2 + 2;
-                const int v = b2::tap6(q[0], q[KP], q[2 * KP], q[3 * KP], q[4 * KP], q[5 * KP]);
-                PH[r * KP + c2] = (uint8_t)b2_clip255((v + 16) >> 5);
-            }
+#pragma unroll
+            for (int c = 0; c < 17; c++) s.B1[lane][c] = (int16_t)b2::tap6(g[c], g[c + 1], g[c + 2], g[c + 3], g[c + 4], g[c + 5]);
+        } else if (warp == 1 && lane < 18) {
+            const uint8_t *q = PG + lane + 2;                                       // column X = lane - 1
+            int g[22];
+#pragma unroll
+            for (int r = 0; r < 22; r++) g[r] = q[r * KP];
+#pragma unroll
+            for (int r = 0; r < 17; r++)
+                PH[r * KP + lane] = (uint8_t)b2_clip255((b2::tap6(g[r], g[r + 1], g[r + 2], g[r + 3], g[r + 4], g[r + 5]) + 16) >> 5);
+        }
     }
     __syncthreads();
-    {
-        const int c = tid % 17, r0 = tid / 17;              // 153 threads -> 9 rows per pass
-        if (tid < 153) {
-            for (int r = r0; r < 18; r += 9)                  // b: Y=r-1 -> B1 row r+2
+    {   // j: centre half samples from the unrounded b1 (warp 0, lane = column); b: rounded b1 (warps 1-4)
+        const int warp = tid >> 5, lane = tid & 31;
+        if (warp == 0) {
+            if (lane < 17) {
+                int g[22];
+#pragma unroll
+                for (int r = 0; r < 22; r++) g[r] = s.B1[r][lane];
+#pragma unroll
+                for (int r = 0; r < 17; r++)
+                    PJ[r * KP + lane] = (uint8_t)b2_clip255((b2::tap6(g[r], g[r + 1], g[r + 2], g[r + 3], g[r + 4], g[r + 5]) + 512) >> 10);
+            }
+        } else {
+            for (int i = tid - 32; i < 18 * 17; i += K2_THREADS - 32) {          // b: Y = r-1 -> B1 row r+2
+                const int r = i / 17, c = i - r * 17;
                 PB[r * KP + c] = (uint8_t)b2_clip255((s.B1[r + 2][c] + 16) >> 5);
-            for (int r = r0; r < 17; r += 9) {                // j: Y=r-1 -> B1 rows r..r+5
-                const int v = b2::tap6(s.B1[r][c], s.B1[r + 1][c], s.B1[r + 2][c], s.B1[r + 3][c], s.B1[r + 4][c], s.B1[r + 5][c]);
-                PJ[r * KP + c] = (uint8_t)b2_clip255((v + 512) >> 10);
             }
         }
     }
@@ -247,16 +264,17 @@ k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__
         atomicAdd(&s.cost[cand], v);
     }
     __syncthreads();
-    if (tid == 0) {
-        uint32_t best = 0xffffffffu; int bi = 0;
-        for (int k = 0; k < n1; k++) {
-            int mx = mvf.x * 4 + 2 * c_subpel_off[k][0], my = mvf.y * 4 + 2 * c_subpel_off[k][1];
-            uint32_t c = s.cost[k] + (uint32_t)(lambda * (b2_mvbits(mx - pm.x) + b2_mvbits(my - pm.y)));
-            if (c < best) { best = c; bi = k; }
+    if (tid < 32) {                                      // nine lanes price their candidate, a warp minimum picks the first best
+        uint32_t key = 0xffffffffu;
+        if (tid < n1) {
+            const int mx = mvf.x * 4 + 2 * c_subpel_off[tid][0], my = mvf.y * 4 + 2 * c_subpel_off[tid][1];
+            const uint32_t c = s.cost[tid] + (uint32_t)(lambda * (b2_mvbits(mx - pm.x) + b2_mvbits(my - pm.y)));
+            key = (c << 4) | (uint32_t)tid;              // costs stay far below 2^28; ties go to the lower candidate index
         }
-        s.best = bi;
-        s.cost[0] = best;
-        for (int k = 1; k < 9; k++) s.cost[k] = 0;
+        key = __reduce_min_sync(0xffffffffu, key);
+        __syncwarp();
+        if (tid < 9) s.cost[tid] = tid == 0 ? key >> 4 : 0u;
+        if (tid == 0) s.best = (int)(key & 15u);
     }
     __syncthreads();
     const int hx = 2 * c_subpel_off[s.best][0], hy = 2 * c_subpel_off[s.best][1];
@@ -268,20 +286,25 @@ k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__
         }
         __syncthreads();
     }
-    if (tid == 0) {
-        uint32_t best = s.cost[0];
-        int bx = mvf.x * 4 + hx, by = mvf.y * 4 + hy;
-        if (subpel)
-            for (int k = 1; k < 9; k++) {
-                int mx = mvf.x * 4 + hx + c_subpel_off[k][0], my = mvf.y * 4 + hy + c_subpel_off[k][1];
-                uint32_t c = s.cost[k] + (uint32_t)(lambda * (b2_mvbits(mx - pm.x) + b2_mvbits(my - pm.y)));
-                if (c < best) { best = c; bx = mx; by = my; }
-            }
-        b2_mv_t o;
-        o.x = (int16_t)bx; o.y = (int16_t)by;
-        mv_out[mbi] = o;
-        cost_out[mbi] = best;
-        s.best = ((bx - mvf.x * 4) & 0xff) | (((by - mvf.y * 4) & 0xff) << 8);     // winner relative to the full-pel position
+    if (tid < 32) {
+        // candidate 0 = the half-pel winner itself (already priced); 1..8 its quarter-pel neighbours; first minimum wins
+        uint32_t key = 0xffffffffu;
+        if (tid == 0) key = s.cost[0] << 4;
+        else if (tid < 9 && subpel) {
+            const int mx = mvf.x * 4 + hx + c_subpel_off[tid][0], my = mvf.y * 4 + hy + c_subpel_off[tid][1];
+            const uint32_t c = s.cost[tid] + (uint32_t)(lambda * (b2_mvbits(mx - pm.x) + b2_mvbits(my - pm.y)));
+            key = (c << 4) | (uint32_t)tid;
+        }
+        key = __reduce_min_sync(0xffffffffu, key);
+        if (tid == 0) {
+            const int k = (int)(key & 15u);
+            const int dx = hx + (k ? c_subpel_off[k][0] : 0), dy = hy + (k ? c_subpel_off[k][1] : 0);
+            b2_mv_t o;
+            o.x = (int16_t)(mvf.x * 4 + dx); o.y = (int16_t)(mvf.y * 4 + dy);
+            mv_out[mbi] = o;
+            cost_out[mbi] = key >> 4;
+            s.best = (dx & 0xff) | ((dy & 0xff) << 8);                             // winner relative to the full-pel position
+        }
     }
     if (tid == 0) { s.qmv[0] = s.qmv[1] = s.qmv[2] = s.qmv[3] = s.best; }
     }
