@@ -7,7 +7,7 @@ for F in 0 1; do
   python scripts/ncu_target.py > gpurun_out/ncu_plain_f$F.log 2>&1 || { echo "plain run failed (features=$F)"; tail -5 gpurun_out/ncu_plain_f$F.log; continue; }
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r1_f$F.csv python scripts/ncu_target.py > gpurun_out/ncu_launches_f$F.log 2>&1
   ncu --set full --clock-control none --import-source on -k regex:'k0_|k1_|k2_|k3_|k5_|k6_|k7_|k8_|k9' -s 12 -c 12 -o gpurun_out/prof_r1_f$F python scripts/ncu_target.py > gpurun_out/ncu_full_f$F.log 2>&1
-  tail -2 gpurun_out/ncu_launches_f$F.log gpurun_out/ncu_full_f$F.log
+  tail -n 2 gpurun_out/ncu_launches_f$F.log; tail -n 2 gpurun_out/ncu_full_f$F.log
 done
 unset B2_ALL_FEATURES
 python bench.py > gpurun_out/bench_r1e.json 2> gpurun_out/bench_r1e.err; tail -c 300 gpurun_out/bench_r1e.json
