@@ -8,7 +8,9 @@
  * the GPU in lock-step (one launch sequence per frame index covers all GOPs), the host entropy-codes
  * the per-MB results and frames are then returned in display order, one per call -- exactly the
  * "0 = no output yet / delayed_frames() / encode(NULL) drains" contract main() relies on
- * (av_encode.c:971-974, :1076-1083).  i_gop_slots = 1 encodes every picture immediately (zero delay).
+ * (av_encode.c:971-974, :1076-1083).  A pipeline thread drives batch k through the GPU and the entropy workers while the
+ * caller already gathers batch k+1 into the other half of the pinned input ring, so copying pictures in and encoding
+ * overlap.  i_gop_slots = 1 encodes every picture immediately (zero delay).
  */
 #define _POSIX_C_SOURCE 200809L
 #include <pthread.h>
@@ -51,8 +53,18 @@ struct b2_encoder {
     pthread_cond_t cv_job, cv_done;
     job_t *jobs;
     int njobs, next_job, done_jobs, job_error, stop;
-    int64_t *pts;              /* [S*L] pts of the frames of the batch being gathered */
-    int batch_frames;
+    int64_t *pts;              /* [2][S*L] pts of the frames of the two batch halves */
+    int batch_frames;          /* frames gathered into the current half */
+    /* asynchronous batch pipeline (S > 1): the caller gathers batch k+1 into one half of the input ring while the pipeline
+     * thread drives batch k (GPU steps + entropy workers) out of the other half */
+    pthread_t pipe_thread;
+    int pipe_started, pipe_busy, pipe_stop, pipe_error;
+    pthread_mutex_t pmu;
+    pthread_cond_t pcv_submit, pcv_done;
+    int gather_half, sub_half, sub_frames;
+    int inflight;              /* frames handed to the pipeline thread that are not in the fifo yet */
+    outframe_t *fifo;          /* finished frames in display order */
+    int fifo_cap, fifo_head, fifo_count;
     int gop_pos;               /* zero-delay mode: position inside the current GOP */
     outframe_t *outq;          /* [S*L] finished frames of the last processed batch, display order */
     int out_head, out_count;
@@ -133,6 +145,7 @@ void b2_picture_clean(b2_picture_t *pic)
 }
 
 static void *worker_main(void *arg);
+static void *pipe_main(void *arg);
 
 b2_t *b2_encoder_open(b2_param_t *p)
 {
@@ -147,7 +160,7 @@ b2_t *b2_encoder_open(b2_param_t *p)
     b2_engine_cfg_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.device = p->i_device; cfg.width = p->i_width; cfg.height = p->i_height; cfg.slots = h->S;
-    cfg.in_fmt = p->i_csp_in; cfg.in_ring = h->S == 1 ? 1 : h->L; cfg.merange = p->i_merange ? p->i_merange : 16; cfg.qp = h->qp;
+    cfg.in_fmt = p->i_csp_in; cfg.in_ring = h->S == 1 ? 1 : 2 * h->L; cfg.merange = p->i_merange ? p->i_merange : 16; cfg.qp = h->qp;
     cfg.subpel = p->b_subpel; cfg.intra_in_p = p->b_intra_in_p; cfg.profile = 0; cfg.deblock = p->b_deblocking_filter;
     cfg.transform8x8 = p->b_transform_8x8 != 0;
     cfg.partitions = p->b_partitions < 0 ? 0 : (p->b_partitions > 2 ? 2 : p->b_partitions);
@@ -162,11 +175,14 @@ b2_t *b2_encoder_open(b2_param_t *p)
     h->seq.sar_w = p->vui.i_sar_width; h->seq.sar_h = p->vui.i_sar_height; h->seq.qp = h->qp;
     h->seq.deblock = p->b_deblocking_filter;
     h->seq.cabac = p->b_cabac != 0; h->seq.transform8x8 = p->b_transform_8x8 != 0;
-    h->pts = (int64_t *)calloc((size_t)h->S * h->L, sizeof(int64_t));
+    h->pts = (int64_t *)calloc((size_t)2 * h->S * h->L, sizeof(int64_t));
+    h->fifo_cap = 3 * h->S * h->L;
+    h->fifo = (outframe_t *)calloc((size_t)h->fifo_cap, sizeof(outframe_t));
+    pthread_mutex_init(&h->pmu, NULL); pthread_cond_init(&h->pcv_submit, NULL); pthread_cond_init(&h->pcv_done, NULL);
     h->outq = (outframe_t *)calloc((size_t)h->S * h->L, sizeof(outframe_t));
     h->scratch_cap = (size_t)h->nmb * 3072 + 65536;
     h->scratch = (uint8_t *)malloc(h->scratch_cap);
-    if (!h->ent || !h->pts || !h->outq || !h->scratch) { b2_encoder_close(h); return NULL; }
+    if (!h->ent || !h->pts || !h->outq || !h->scratch || !h->fifo) { b2_encoder_close(h); return NULL; }
     pthread_mutex_init(&h->mu, NULL); pthread_cond_init(&h->cv_job, NULL); pthread_cond_init(&h->cv_done, NULL);
     if (h->S > 1) {
         long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
@@ -184,6 +200,8 @@ b2_t *b2_encoder_open(b2_param_t *p)
             h->nworkers++;
         }
         pthread_mutex_unlock(&h->mu);
+        if (pthread_create(&h->pipe_thread, NULL, pipe_main, h)) { b2_encoder_close(h); return NULL; }
+        h->pipe_started = 1;
     }
     return h;
 }
@@ -191,6 +209,16 @@ b2_t *b2_encoder_open(b2_param_t *p)
 void b2_encoder_close(b2_t *h)
 {
     if (!h) return;
+    if (h->pipe_started) {
+        pthread_mutex_lock(&h->pmu);
+        h->pipe_stop = 1;
+        pthread_cond_broadcast(&h->pcv_submit);
+        pthread_mutex_unlock(&h->pmu);
+        pthread_join(h->pipe_thread, NULL);
+    }
+    if (h->fifo)
+        for (int i = 0; i < h->fifo_cap; i++) free(h->fifo[i].data);
+    free(h->fifo);
     if (h->nworkers > 0) {
         pthread_mutex_lock(&h->mu);
         h->stop = 1;
@@ -276,12 +304,12 @@ static void *worker_main(void *arg)
 }
 
 /* entropy-code frame t of GOPs [0,nt) on the worker pool (or inline when there is none) */
-static int entropy_step(b2_t *h, int t, int nt, int ticket)
+static int entropy_step(b2_t *h, int t, int nt, int ticket, const int64_t *pts)
 {
     if (h->nworkers == 0) {
         for (int g = 0; g < nt; g++) {
             if (finish_frame(h, h->ent, h->scratch, ticket, g * h->L + t, g, t, h->gops_done + g)) return -1;
-            h->outq[g * h->L + t].pts = h->pts[g * h->L + t];
+            h->outq[g * h->L + t].pts = pts[g * h->L + t];
         }
         return 0;
     }
@@ -296,78 +324,95 @@ static int entropy_step(b2_t *h, int t, int nt, int ticket)
     h->njobs = 0; h->next_job = 0;
     int err = h->job_error;
     pthread_mutex_unlock(&h->mu);
-    for (int g = 0; g < nt; g++) h->outq[g * h->L + t].pts = h->pts[g * h->L + t];
+    for (int g = 0; g < nt; g++) h->outq[g * h->L + t].pts = pts[g * h->L + t];
     return err ? -1 : 0;
 }
 
-static int issue_step(b2_t *h, int t, int nt)
+static int issue_step(b2_t *h, int half, int t, int nt)
 {
-    const int ring = h->S == 1 ? 0 : t;
+    const int ring = h->S == 1 ? 0 : half * h->L + t;
     if (b2_engine_h2d(h->eng, 0, nt, ring)) return -1;
     if (b2_engine_encode(h->eng, t == 0 ? B2_FRAME_I : B2_FRAME_P, nt, ring)) return -1;
     return b2_engine_d2h(h->eng, nt);
 }
 
-/* advance the gathered batch (possibly partial) through the GPU and the entropy stage: while the host entropy-codes
- * frame t of every GOP, the GPU already encodes frame t+1 (result sets are double buffered) */
-static int process_batch(b2_t *h)
+/* advance one gathered batch (possibly partial) through the GPU and the entropy stage: while the host entropy-codes
+ * frame t of every GOP, the GPU already encodes frame t+1 (result sets are double buffered).  Runs on the pipeline thread. */
+static int process_batch(b2_t *h, int half, int n)
 {
-    const int n = h->batch_frames, L = h->L;
+    const int L = h->L;
     const int ngop = (n + L - 1) / L, last_len = n - (ngop - 1) * L;
+    const int64_t *pts = h->pts + (size_t)half * h->S * L;
     int nt = ngop;                                         /* GOPs that have a frame 0 */
-    if (issue_step(h, 0, nt)) return -1;
+    if (issue_step(h, half, 0, nt)) return -1;
     for (int t = 0; t < L && nt > 0; t++) {
         const int ticket = b2_engine_ticket(h->eng);
         const int nt_next = t + 1 < L ? (t + 1 < last_len ? ngop : ngop - 1) : 0;     /* a prefix of the slots */
         if (b2_engine_wait_ticket(h->eng, ticket)) return -1;
-        if (nt_next > 0 && issue_step(h, t + 1, nt_next)) return -1;
-        if (entropy_step(h, t, nt, ticket)) return -1;
+        if (nt_next > 0 && issue_step(h, half, t + 1, nt_next)) return -1;
+        if (entropy_step(h, t, nt, ticket, pts)) return -1;
         nt = nt_next;
     }
     if (b2_engine_sync(h->eng)) return -1;
     h->gops_done += ngop;
-    h->out_head = 0; h->out_count = n;
-    h->batch_frames = 0;
+    pthread_mutex_lock(&h->pmu);                          /* hand the frames over in display order */
+    for (int i = 0; i < n; i++) {
+        outframe_t *dst = &h->fifo[(h->fifo_head + h->fifo_count) % h->fifo_cap];
+        free(dst->data);
+        *dst = h->outq[i];
+        h->outq[i].data = NULL;
+        h->fifo_count++;
+    }
+    h->inflight -= n;
+    pthread_mutex_unlock(&h->pmu);
     return 0;
 }
 
-int b2_encoder_delayed_frames(b2_t *h) { return h ? h->batch_frames + h->out_count : 0; }
-
-int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic_in, b2_picture_t *pic_out)
+static void *pipe_main(void *arg)
 {
-    if (!h || !pp_nal || !pi_nal) return -1;
-    *pi_nal = 0; *pp_nal = NULL;
-    if (pic_in) {
-        if (h->S == 1) {
-            /* zero-delay mode: one slot, encode every picture as it arrives */
-            const int t = h->gop_pos;
-            if (b2_engine_put_frame(h->eng, 0, 0, (const uint8_t *const *)pic_in->img.plane, pic_in->img.i_stride)) return -1;
-            if (b2_engine_h2d(h->eng, 0, 1, 0) || b2_engine_encode(h->eng, t == 0 ? B2_FRAME_I : B2_FRAME_P, 1, 0) ||
-                b2_engine_d2h(h->eng, 1) || b2_engine_sync(h->eng))
-                return -1;
-            if (finish_frame(h, h->ent, h->scratch, -1, 0, 0, t, h->gops_done)) return -1;
-            h->outq[0].pts = pic_in->i_pts;
-            h->out_head = 0; h->out_count = 1;
-            h->gop_pos = t + 1;
-            if (h->gop_pos == h->L) { h->gop_pos = 0; h->gops_done++; }
-        } else {
-            if (h->out_count > 0 && h->batch_frames == h->S * h->L) {
-                fprintf(stderr, "b2enc: internal queue overflow\n");
-                return -1;
-            }
-            const int idx = h->batch_frames, g = idx / h->L, t = idx % h->L;
-            if (b2_engine_put_frame(h->eng, g, t, (const uint8_t *const *)pic_in->img.plane, pic_in->img.i_stride)) return -1;
-            h->pts[idx] = pic_in->i_pts;
-            h->batch_frames++;
-            /* a batch can only be processed once the previous one has been handed out completely */
-            if (h->batch_frames == h->S * h->L && h->out_count == 0)
-                if (process_batch(h)) return -1;
-        }
-    } else if (h->S > 1 && h->out_count == 0 && h->batch_frames > 0) {
-        if (process_batch(h)) return -1;                            /* flush: partial batch */
+    b2_t *h = (b2_t *)arg;
+    pthread_mutex_lock(&h->pmu);
+    for (;;) {
+        while (!h->pipe_busy && !h->pipe_stop) pthread_cond_wait(&h->pcv_submit, &h->pmu);
+        if (h->pipe_stop) break;
+        const int half = h->sub_half, n = h->sub_frames;
+        pthread_mutex_unlock(&h->pmu);
+        const int rc = process_batch(h, half, n);
+        pthread_mutex_lock(&h->pmu);
+        if (rc) h->pipe_error = 1;
+        h->pipe_busy = 0;
+        pthread_cond_broadcast(&h->pcv_done);
     }
-    if (h->out_count == 0) return 0;
-    outframe_t *o = &h->outq[h->out_head];
+    pthread_mutex_unlock(&h->pmu);
+    return NULL;
+}
+
+/* hand the gathered half to the pipeline thread (waits until it has finished the previous batch) and gather into the other */
+static void submit_batch(b2_t *h)
+{
+    pthread_mutex_lock(&h->pmu);
+    while (h->pipe_busy) pthread_cond_wait(&h->pcv_done, &h->pmu);
+    h->sub_half = h->gather_half; h->sub_frames = h->batch_frames;
+    h->inflight += h->batch_frames;
+    h->pipe_busy = 1;
+    pthread_cond_signal(&h->pcv_submit);
+    pthread_mutex_unlock(&h->pmu);
+    h->gather_half ^= 1;
+    h->batch_frames = 0;
+}
+
+int b2_encoder_delayed_frames(b2_t *h)
+{
+    if (!h) return 0;
+    if (h->S == 1) return h->out_count;
+    pthread_mutex_lock(&h->pmu);
+    const int n = h->batch_frames + h->inflight + h->fifo_count;
+    pthread_mutex_unlock(&h->pmu);
+    return n;
+}
+
+static int return_frame(b2_t *h, outframe_t *o, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic_out)
+{
     free(h->ret_buf);
     h->ret_buf = o->data; o->data = NULL;                           /* hand the payload over; valid until the next call */
     for (int i = 0; i < o->nal_count; i++) {
@@ -380,10 +425,46 @@ int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic
         pic_out->i_pts = o->pts; pic_out->i_dts = o->pts; pic_out->b_keyframe = o->key;
         pic_out->i_type = o->key ? B2_TYPE_IDR : B2_TYPE_P;
     }
-    const int ret = o->size;
-    h->out_head++; h->out_count--;
-    /* when a full batch was waiting for the queue to drain, process it now */
-    if (h->S > 1 && h->out_count == 0 && h->batch_frames == h->S * h->L)
-        if (process_batch(h)) return -1;
-    return ret;
+    return o->size;
+}
+
+int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic_in, b2_picture_t *pic_out)
+{
+    if (!h || !pp_nal || !pi_nal) return -1;
+    *pi_nal = 0; *pp_nal = NULL;
+    if (h->S == 1) {
+        /* zero-delay mode: one slot, encode every picture as it arrives */
+        if (!pic_in) return 0;
+        const int t = h->gop_pos;
+        if (b2_engine_put_frame(h->eng, 0, 0, (const uint8_t *const *)pic_in->img.plane, pic_in->img.i_stride)) return -1;
+        if (b2_engine_h2d(h->eng, 0, 1, 0) || b2_engine_encode(h->eng, t == 0 ? B2_FRAME_I : B2_FRAME_P, 1, 0) ||
+            b2_engine_d2h(h->eng, 1) || b2_engine_sync(h->eng))
+            return -1;
+        if (finish_frame(h, h->ent, h->scratch, -1, 0, 0, t, h->gops_done)) return -1;
+        h->outq[0].pts = pic_in->i_pts;
+        h->gop_pos = t + 1;
+        if (h->gop_pos == h->L) { h->gop_pos = 0; h->gops_done++; }
+        return return_frame(h, &h->outq[0], pp_nal, pi_nal, pic_out);
+    }
+    if (pic_in) {
+        const int idx = h->batch_frames, g = idx / h->L, t = idx % h->L;
+        if (b2_engine_put_frame(h->eng, g, h->gather_half * h->L + t, (const uint8_t *const *)pic_in->img.plane, pic_in->img.i_stride)) return -1;
+        h->pts[(size_t)h->gather_half * h->S * h->L + idx] = pic_in->i_pts;
+        h->batch_frames++;
+        if (h->batch_frames == h->S * h->L) submit_batch(h);        /* full: the pipeline thread takes it, gathering goes on */
+    } else {
+        if (h->batch_frames > 0) submit_batch(h);                   /* flush: partial batch */
+        pthread_mutex_lock(&h->pmu);                                /* a flush call waits for its frame (av_encode.c:1076-1083) */
+        while (h->fifo_count == 0 && h->pipe_busy && !h->pipe_error) pthread_cond_wait(&h->pcv_done, &h->pmu);
+        pthread_mutex_unlock(&h->pmu);
+    }
+    pthread_mutex_lock(&h->pmu);
+    if (h->pipe_error) { pthread_mutex_unlock(&h->pmu); fprintf(stderr, "b2enc: encode pipeline failed\n"); return -1; }
+    if (h->fifo_count == 0) { pthread_mutex_unlock(&h->pmu); return 0; }
+    outframe_t o = h->fifo[h->fifo_head];
+    h->fifo[h->fifo_head].data = NULL;
+    h->fifo_head = (h->fifo_head + 1) % h->fifo_cap;
+    h->fifo_count--;
+    pthread_mutex_unlock(&h->pmu);
+    return return_frame(h, &o, pp_nal, pi_nal, pic_out);
 }
