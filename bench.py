@@ -4,7 +4,7 @@
 Workload (config C3 of BASELINE.json): 1920x1080 synthetic frames (moving gradient + panning texture +
 sensor noise, oracle/b2o_frame.c), yuv420p in, exhaustive +-32 full-pel SAD search + half/quarter-pel
 SATD refinement, intra 16x16/4x4 + inter mode decision, 4x4 DCT/quant/dequant/recon, constant QP 26.
-One GPU encodes SLOTS closed GOPs of GOP frames in lock-step; a *step* advances every GOP by one frame
+One GPU encodes SLOTS (64) closed GOPs of GOP frames in lock-step; a *step* advances every GOP by one frame
 (step i is an I frame when i % GOP == 0, else a P frame), i.e. one pass of the hot path over a batch of
 SLOTS frames.  With N GPUs every rank encodes its own SLOTS GOPs (closed-GOP sharding, no collective,
 weak scaling); time = max over ranks.
@@ -35,7 +35,8 @@ sys.path.insert(0, os.path.join(ROOT, "video-encoder_b200"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 W, H, MERANGE, QP, GOP = 1920, 1080, 32, 26, 32
-SLOTS, RING, STREAMS = 32, 8, 8
+# 64 GOPs x 8 stream groups: swept on the B200 (scripts/gpu_quick6.sh): 32 -> 4,645, 48 -> 4,766, 64 -> 4,876, 96/128 -> 4,879 frames/s
+SLOTS, RING, STREAMS = int(os.environ.get("B2_BENCH_SLOTS", "64")), 8, int(os.environ.get("B2_BENCH_STREAMS", "8"))
 METRIC, UNIT = "1080p encode-stage frames/s", "frames/s"
 WORKLOAD = ("C3: 1920x1080 synthetic yuv420p, +-32 exhaustive SAD + qpel SATD refine, intra16x16/4x4+inter decision, "
             "4x4 DCT/quant/recon, QP 26, closed GOP 32, %d GOPs in lock-step per GPU" % SLOTS)
@@ -46,8 +47,8 @@ WORKLOADS = {
     "c2": dict(W=1280, H=720, MERANGE=16, SLOTS=64, STREAMS=8, METRIC="720p encode-stage frames/s",
                WORKLOAD="C2: 1280x720 synthetic, P-frames, +-16 full-pel search (+ qpel, intra/inter as in C3), QP 26, GOP 32, 64 GOPs in lock-step per GPU"),
     "c3": None,
-    "c4": dict(W=3840, H=2160, MERANGE=32, SLOTS=8, STREAMS=8, METRIC="2160p encode-stage frames/s",
-               WORKLOAD="C4: 3840x2160 synthetic, closed-GOP sharding, +-32 + qpel + intra/inter, QP 26, GOP 32, 8 GOPs in lock-step per GPU"),
+    "c4": dict(W=3840, H=2160, MERANGE=32, SLOTS=16, STREAMS=8, METRIC="2160p encode-stage frames/s",
+               WORKLOAD="C4: 3840x2160 synthetic, closed-GOP sharding, +-32 + qpel + intra/inter, QP 26, GOP 32, 16 GOPs in lock-step per GPU"),
     "c5": dict(W=1280, H=720, MERANGE=16, SLOTS=8, STREAMS=4, METRIC="720p live-stream encode-stage frames/s",
                WORKLOAD="C5: 64 concurrent 720p live streams over 8 GPUs = 8 streams in lock-step per GPU (one frame of latency), +-16 + qpel + intra/inter, QP 26, GOP 32"),
 }
