@@ -27,12 +27,9 @@ struct K0Args {
 
 __device__ __forceinline__ uint8_t avg_r(int a, int b, int r) { return (uint8_t)((a + b + r) >> 1); }
 
-__global__ void __launch_bounds__(128)
-k0_convert_kernel(K0Args a)
+// 16 output pixels of row `row` (0..h16-1 luma, then U rows, then V rows) starting at x0; returns the store address or nullptr
+__device__ __forceinline__ uint8_t *k0_row16(const K0Args &a, int frame, int row, int x0, uint8_t px[16])
 {
-    const int frame = blockIdx.z;
-    const int row = blockIdx.y;                       // 0..h16-1 luma, then U rows, then V rows
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
     const int ch16 = a.h16 >> 1, cw16 = a.w16 >> 1;
     const int cw = (a.w + 1) >> 1, chh = (a.h + 1) >> 1;
     const uint8_t *in = a.in + frame * a.in_stride;
@@ -41,12 +38,11 @@ k0_convert_kernel(K0Args a)
     else if (row < a.h16 + ch16) { plane = 1; y = row - a.h16; }
     else { plane = 2; y = row - a.h16 - ch16; }
     const int ow = plane ? cw16 : a.w16;              // coded width of this plane
-    if (x0 >= ow) return;
+    if (x0 >= ow) return nullptr;
     const int pw = plane ? cw : a.w, ph = plane ? chh : a.h;   // picture width/height of this plane
     const int sy = min(y, ph - 1);
     uint8_t *dst = plane == 0 ? a.y + frame * a.stride_y + (size_t)(B2_PAD + y) * a.pitch + B2_PAD + x0
                               : (plane == 1 ? a.u : a.v) + frame * a.stride_c + (size_t)(B2_PADC + y) * a.pitchc + B2_PADC + x0;
-    __align__(16) uint8_t px[16];
 
     if (a.fmt == B2_FMT_YUV420P || (a.fmt == B2_FMT_NV12 && plane == 0)) {
         const uint8_t *src = in + (plane == 0 ? 0 : (size_t)a.w * a.h + (plane == 2 ? (size_t)cw * chh : 0)) + (size_t)sy * pw;
@@ -129,7 +125,25 @@ k0_convert_kernel(K0Args a)
             }
         }
     }
-    *(uint4 *)dst = *(const uint4 *)px;
+    return dst;
+}
+
+// K0_ROWS rows per thread: all loads of the four rows are in flight before the first store (memory-level parallelism; one row per
+// thread left the kernel at 0.61 of the measured HBM rate).  Row groups never straddle planes: h16 is a multiple of 16.
+constexpr int K0_ROWS = 4;
+
+__global__ void __launch_bounds__(128)
+k0_convert_kernel(K0Args a)
+{
+    const int frame = blockIdx.z;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    __align__(16) uint8_t px[K0_ROWS][16];
+    uint8_t *dst[K0_ROWS];
+#pragma unroll
+    for (int r = 0; r < K0_ROWS; r++) dst[r] = k0_row16(a, frame, blockIdx.y * K0_ROWS + r, x0, px[r]);
+#pragma unroll
+    for (int r = 0; r < K0_ROWS; r++)
+        if (dst[r]) *(uint4 *)dst[r] = *(const uint4 *)px[r];
 }
 
 }  // namespace
@@ -145,7 +159,7 @@ int b2_launch_convert(int fmt, const uint8_t *d_in, size_t in_stride, uint8_t *d
         return -1;
     }
     dim3 block(128);
-    dim3 grid((a.w16 / 16 + 127) / 128, a.h16 + 2 * (a.h16 / 2), nframes);
+    dim3 grid((a.w16 / 16 + 127) / 128, (a.h16 + 2 * (a.h16 / 2)) / K0_ROWS, nframes);
     k0_convert_kernel<<<grid, block, 0, st>>>(a);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
