@@ -294,11 +294,13 @@ template <int R, int NT, bool PART>
 int launch_k1p(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, int mbw, int mbh, int nframes, const b2_mv_t *pmv, int lambda,
                b2_mv_t *mv_out, uint32_t *cost_out, b2_mv_t *mv9_out, uint32_t *cost9_out, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};                      // function attributes are per device: one process may drive several GPUs
+    int dev = 0;
+    B2_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         B2_CUDA_OK(cudaFuncSetAttribute(k1_me_fullpel_kernel<R, NT, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         K1Smem<R>::TOTAL));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     constexpr int NMB = K1Cfg<R>::NMB;
     dim3 grid((mbw + NMB - 1) / NMB, mbh, nframes);
