@@ -9,7 +9,10 @@
  *   per frame: sws_scale into pic_in, encoder_encode          (av_encode.c:545-547, :970)
  *   drain: while delayed_frames() encode(NULL)                (av_encode.c:1076-1083)
  *   sws_freeContext, picture_clean, encoder_close             (enc_x264_close, av_encode.c:440-444)
- * Extensions (not in the reference): --size WxH --fps N[/D] for raw input, --merange, --gop, --slots, --device.
+ * Like the reference it takes --filters (av_encode.c:116): "hqdn3d", "yadif" or "hqdn3d,yadif" run on the GPU pre-filter stage
+ * (include/b2enc_filters.h); and when the output name ends in ".mp4" it writes an MP4 with one AVC track from the encoder's
+ * b_annexb = 0 payloads (tools/b2_mp4.h + b2_avcc_write), the video half of enc_mp4_write_video_sample (:683-744).
+ * Extensions (not in the reference): --size WxH --fps N[/D] for raw input, --merange, --gop, --slots, --device, --8x8dct, --partitions.
  */
 #define _POSIX_C_SOURCE 200809L
 #include <getopt.h>
@@ -18,18 +21,20 @@
 #include <string.h>
 #include <time.h>
 #include "b2enc.h"
+#include "b2enc_filters.h"
+#include "b2_mp4.h"
 
 typedef struct {
-    int silent, width, height, fps_num, fps_den, merange, gop, slots, device;
+    int silent, width, height, fps_num, fps_den, merange, gop, slots, device, dct8, partitions;
     long frame_limit;
-    const char *input_file, *output_file, *preset, *tune, *profile;
+    const char *input_file, *output_file, *preset, *tune, *profile, *video_filter;
     float quality;
 } cli_options_t;
 
 static int parse_cli_options(cli_options_t *o, int argc, char **argv)
 {
     cli_options_t d = {.silent = 0, .width = 0, .height = 0, .fps_num = 25, .fps_den = 1, .merange = 0, .gop = 0, .slots = 0,
-                       .device = 0, .frame_limit = -1, .input_file = NULL, .output_file = NULL,
+                       .device = 0, .dct8 = 0, .partitions = 0, .video_filter = NULL, .frame_limit = -1, .input_file = NULL, .output_file = NULL,
                        .preset = "medium", .tune = "film", .profile = NULL, .quality = 20.0f};   /* av_encode.c:91-106 */
     *o = d;
     struct option long_opts[] = {
@@ -38,9 +43,10 @@ static int parse_cli_options(cli_options_t *o, int argc, char **argv)
         {"quality", required_argument, NULL, 3}, {"profile", required_argument, NULL, 4},
         {"size", required_argument, NULL, 5}, {"fps", required_argument, NULL, 6}, {"merange", required_argument, NULL, 7},
         {"gop", required_argument, NULL, 8}, {"slots", required_argument, NULL, 9}, {"device", required_argument, NULL, 10},
+        {"filters", required_argument, NULL, 'f'}, {"8x8dct", no_argument, NULL, 11}, {"partitions", required_argument, NULL, 12},
         {NULL, 0, NULL, 0}};
     int c, idx = 0;
-    while ((c = getopt_long(argc, argv, "sl:", long_opts, &idx)) != -1) {
+    while ((c = getopt_long(argc, argv, "sl:f:", long_opts, &idx)) != -1) {
         switch (c) {
         case 's': o->silent = 1; break;
         case 'l': o->frame_limit = strtol(optarg, NULL, 10); break;
@@ -54,6 +60,9 @@ static int parse_cli_options(cli_options_t *o, int argc, char **argv)
         case 8: o->gop = atoi(optarg); break;
         case 9: o->slots = atoi(optarg); break;
         case 10: o->device = atoi(optarg); break;
+        case 'f': o->video_filter = optarg; break;                       /* av_encode.c:148-149 */
+        case 11: o->dct8 = 1; break;
+        case 12: o->partitions = atoi(optarg); break;
         default: return 0;
         }
     }
@@ -81,7 +90,8 @@ int main(int argc, char **argv)
     cli_options_t opts;
     if (!parse_cli_options(&opts, argc, argv)) {
         fprintf(stderr, "usage: %s [--preset p] [--tune t] [--quality q] [--profile p] [--frame-limit n] [--silent]\n"
-                        "          [--size WxH --fps N[/D]] [--merange 16|32] [--gop n] [--slots n] [--device n] input.{y4m,yuv} output.h264\n", argv[0]);
+                        "          [--size WxH --fps N[/D]] [--merange 16|32] [--gop n] [--slots n] [--device n]\n"
+                        "          [--filters hqdn3d,yadif] [--8x8dct] [--partitions 0|1|2] input.{y4m,yuv} output.{h264,mp4}\n", argv[0]);
         return 1;
     }
     FILE *in = fopen(opts.input_file, "rb");
@@ -98,7 +108,10 @@ int main(int argc, char **argv)
         return 8;
     }
     params.i_width = opts.width; params.i_height = opts.height;
-    params.b_annexb = 1;                                   /* elementary stream out (the reference muxes MP4: b_annexb = 0) */
+    const size_t on = strlen(opts.output_file);
+    const int to_mp4 = on > 4 && !strcmp(opts.output_file + on - 4, ".mp4");
+    params.b_annexb = to_mp4 ? 0 : 1;                      /* MP4: 4-byte NAL lengths like the reference (av_encode.c:392); else Annex-B */
+    params.b_transform_8x8 = opts.dct8; params.b_partitions = opts.partitions;
     params.i_fps_num = opts.fps_num; params.i_fps_den = opts.fps_den;
     params.vui.i_sar_width = 1; params.vui.i_sar_height = 1;
     params.rc.i_rc_method = B2_RC_CRF; params.rc.f_rf_constant = opts.quality;
@@ -116,42 +129,77 @@ int main(int argc, char **argv)
                                                  B2_SWS_FAST_BILINEAR, NULL, NULL, NULL);
     if (!scaler) { fprintf(stderr, "failed to create software scaler to copy frames to the encoder\n"); return 8; }
 
-    FILE *out = fopen(opts.output_file, "wb");
-    if (!out) { perror(opts.output_file); return 9; }
+    /* enc_avfilter_build_graph(), av_encode.c:451-517 */
+    b2_filter_graph_t *graph = NULL;
+    if (opts.video_filter && opts.video_filter[0]) {
+        graph = b2_filter_graph_create(opts.width, opts.height, B2_FMT_YUV420P, opts.video_filter, opts.device);
+        if (!graph) { fprintf(stderr, "failed to build the filter graph '%s'\n", opts.video_filter); return 8; }
+    }
+    FILE *out = NULL;
+    b2_mp4_t mp4;
+    if (to_mp4) { if (b2_mp4_open(&mp4, opts.output_file, opts.width, opts.height, opts.fps_num, opts.fps_den)) { perror(opts.output_file); return 9; } }
+    else { out = fopen(opts.output_file, "wb"); if (!out) { perror(opts.output_file); return 9; } }
     const int cw = (opts.width + 1) / 2, ch = (opts.height + 1) / 2;
     const size_t frame_bytes = (size_t)opts.width * opts.height + 2 * (size_t)cw * ch;
-    uint8_t *raw = (uint8_t *)malloc(frame_bytes);
+    uint8_t *raw = (uint8_t *)malloc(frame_bytes), *filt = (uint8_t *)malloc(frame_bytes);
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     long frames_in = 0, frames_out = 0;
     size_t bytes_out = 0;
     b2_nal_t *nals; int nal_count;
-    for (;;) {
-        if (opts.frame_limit >= 0 && frames_in >= opts.frame_limit) break;
-        if (is_y4m) { char fl[64]; if (!fgets(fl, sizeof(fl), in) || strncmp(fl, "FRAME", 5)) break; }
-        if (fread(raw, 1, frame_bytes, in) != frame_bytes) break;
-        /* enc_avfilter_pull_to_x264_context(), av_encode.c:543-547 */
+#define EMIT(payload)                                                                                              \
+    do {                                                                                                           \
+        if ((payload) > 0) {                                                                                       \
+            if (to_mp4) b2_mp4_write_frame(&mp4, nals, nal_count, (payload), pic_out.b_keyframe);                  \
+            else fwrite(nals[0].p_payload, 1, (size_t)(payload), out);                                             \
+            bytes_out += (size_t)(payload); frames_out++;                                                          \
+        } else if ((payload) < 0) fprintf(stderr, "b2enc: encoder error\n");                                       \
+    } while (0)
+    int eof = 0;
+    while (!eof) {
+        if ((opts.frame_limit >= 0 && frames_in >= opts.frame_limit)) eof = 1;
+        if (!eof && is_y4m) { char fl[64]; if (!fgets(fl, sizeof(fl), in) || strncmp(fl, "FRAME", 5)) eof = 1; }
+        if (!eof && fread(raw, 1, frame_bytes, in) != frame_bytes) eof = 1;
         const uint8_t *src[4] = {raw, raw + (size_t)opts.width * opts.height, raw + (size_t)opts.width * opts.height + (size_t)cw * ch, NULL};
         const int stride[4] = {opts.width, cw, cw, 0};
-        pic_in.i_type = B2_TYPE_AUTO; pic_in.i_pts = frames_in;
-        if (b2_sws_scale(scaler, src, stride, 0, opts.height, pic_in.img.plane, pic_in.img.i_stride) != opts.height) { fprintf(stderr, "b2enc: conversion failed\n"); return 10; }
-        frames_in++;
-        int payload = b2_encoder_encode(enc, &nals, &nal_count, &pic_in, &pic_out);            /* av_encode.c:970 */
-        if (payload > 0) { fwrite(nals[0].p_payload, 1, (size_t)payload, out); bytes_out += (size_t)payload; frames_out++; }
-        else if (payload < 0) fprintf(stderr, "b2enc: encoder error\n");
+        if (graph) {                                          /* av_vsrc_buffer_add_frame, av_encode.c:962 (flush at end of input) */
+            if (!eof) { if (b2_filter_add_frame(graph, src, stride, frames_in, 1)) { fprintf(stderr, "b2enc: filter error\n"); return 10; } frames_in++; }
+            else b2_filter_flush(graph);
+        } else if (eof) break;
+        /* pull all finished frames and encode them, av_encode.c:967-975 */
+        for (;;) {
+            const uint8_t *fsrc[4] = {src[0], src[1], src[2], NULL};
+            int64_t pts = frames_in;
+            if (graph) {
+                uint8_t *fdst[3] = {filt, filt + (size_t)opts.width * opts.height, filt + (size_t)opts.width * opts.height + (size_t)cw * ch};
+                if (b2_filter_get_frame(graph, fdst, stride, &pts) != 1) break;
+                fsrc[0] = fdst[0]; fsrc[1] = fdst[1]; fsrc[2] = fdst[2];
+            } else {
+                pts = frames_in++;
+            }
+            /* enc_avfilter_pull_to_x264_context(), av_encode.c:543-547 */
+            pic_in.i_type = B2_TYPE_AUTO; pic_in.i_pts = pts;
+            if (b2_sws_scale(scaler, fsrc, stride, 0, opts.height, pic_in.img.plane, pic_in.img.i_stride) != opts.height) { fprintf(stderr, "b2enc: conversion failed\n"); return 10; }
+            int payload = b2_encoder_encode(enc, &nals, &nal_count, &pic_in, &pic_out);            /* av_encode.c:970 */
+            EMIT(payload);
+            if (!graph) break;
+        }
     }
     while (b2_encoder_delayed_frames(enc) > 0) {                                               /* av_encode.c:1076-1083 */
         int payload = b2_encoder_encode(enc, &nals, &nal_count, NULL, &pic_out);
-        if (payload > 0) { fwrite(nals[0].p_payload, 1, (size_t)payload, out); bytes_out += (size_t)payload; frames_out++; }
-        else if (payload < 0) { fprintf(stderr, "b2enc: encoder error"); break; }
+        EMIT(payload);
+        if (payload < 0) break;
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);
     double dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
     if (!opts.silent)
         printf("%ld frames in, %ld frames out, %zu bytes, %.2f s, %.1f fps (host entropy coding included)\n", frames_in, frames_out,
                bytes_out, dt, dt > 0 ? frames_out / dt : 0.0);
-    free(raw);
-    fclose(in); fclose(out);
+    free(raw); free(filt);
+    fclose(in);
+    if (to_mp4) { if (b2_mp4_close(&mp4)) return 11; }                                          /* MP4Close, av_encode.c:1110-1116 */
+    else fclose(out);
+    b2_filter_graph_free(graph);
     b2_sws_freeContext(scaler);                                                                /* enc_x264_close(), av_encode.c:440-444 */
     b2_picture_clean(&pic_in);
     b2_encoder_close(enc);
