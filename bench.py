@@ -60,6 +60,7 @@ def select_workload(name):
     if wl:
         W, H, MERANGE, SLOTS, STREAMS, METRIC, WORKLOAD = (wl["W"], wl["H"], wl["MERANGE"], wl["SLOTS"], wl["STREAMS"],
                                                              wl["METRIC"], wl["WORKLOAD"])
+        STREAMS = int(os.environ.get("B2_BENCH_STREAMS", STREAMS))          # tuning sweeps only
 
 
 def measured_peaks():

@@ -5,12 +5,13 @@
  * between the 4x4 and the 8x8 transform of an inter macroblock the way x264's non-RD analysis does
  * (x264_mb_analyse_transform: sa8d 16x16 < satd 16x16).  In the reference all of it is inside
  * x264_encoder_encode (av_encode.c:970).  The normative half is pinned by the libavcodec decoder drift test. */
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include "b2o.h"
 
 uint8_t b2o_zigzag8x8[64];                 /* scan pos -> raster index (y*8+x); built on first use */
-static int zz8_ready;
+static pthread_once_t zz8_once = PTHREAD_ONCE_INIT;   /* bench.py's cpu_baseline runs one GOP per host thread */
 
 static void zz8_init(void)
 {
@@ -20,9 +21,8 @@ static void zz8_init(void)
         if (d & 1) { for (int y = d < 8 ? 0 : d - 7; y <= (d < 8 ? d : 7); y++) b2o_zigzag8x8[n++] = (uint8_t)(y * 8 + (d - y)); }
         else       { for (int x = d < 8 ? 0 : d - 7; x <= (d < 8 ? d : 7); x++) b2o_zigzag8x8[n++] = (uint8_t)((d - x) * 8 + x); }
     }
-    zz8_ready = 1;
 }
-const uint8_t *b2o_zigzag8(void) { if (!zz8_ready) zz8_init(); return b2o_zigzag8x8; }
+const uint8_t *b2o_zigzag8(void) { pthread_once(&zz8_once, zz8_init); return b2o_zigzag8x8; }
 
 /* normAdjust8x8 position classes (8.5.9): [y&3][x&3] */
 static const uint8_t cls8[16] = {0, 3, 4, 3, 3, 1, 5, 1, 4, 5, 2, 5, 3, 1, 5, 1};

@@ -9,6 +9,7 @@
  * One slice per picture, one reference frame, frame macroblocks only, constant QP (mb_qp_delta = 0).
  * Pinned by decoding the stream with libavcodec's H.264 decoder (tests/test_cabac.py).
  */
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include "b2h_priv.h"
@@ -62,7 +63,7 @@ typedef struct {
 
 static uint8_t cabac_next[128][2];          /* state after coding bin b in state s */
 static uint8_t cabac_shift[64];             /* renormalisation shift for range >> 3 */
-static int cabac_tables_ready;
+static pthread_once_t cabac_tables_once = PTHREAD_ONCE_INIT;      /* slices are written by several entropy workers */
 
 static void cabac_tables(void)
 {
@@ -77,12 +78,11 @@ static void cabac_tables(void)
         while ((r << sh) < 256) sh++;
         cabac_shift[i] = (uint8_t)sh;
     }
-    cabac_tables_ready = 1;
 }
 
 static void cabac_init(cabac_t *c, bs_t *bs, int table, int qp)
 {
-    if (!cabac_tables_ready) cabac_tables();
+    pthread_once(&cabac_tables_once, cabac_tables);
     c->p = c->start = bs->buf + bs->pos; c->end = bs->buf + bs->cap;
     c->low = 0; c->range = 510; c->queue = -9; c->outstanding = 0; c->overflow = 0;     /* the first bit is not written */
     for (int i = 0; i < 1024; i++) {
