@@ -97,20 +97,16 @@ __device__ __forceinline__ uint32_t cand_block_satd(const K2Smem &s, int blk, in
     return b2::satd4x4(d);
 }
 
+// refinement of ONE macroblock around the full-pel vector mvf (whole CTA); PART: also the local partition refinement
 template <bool PART>
-__global__ void __launch_bounds__(K2_THREADS)
-k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ ref, int pitch, size_t plane_stride,
-                    int mbw, int mbh, const b2_mv_t *__restrict__ mv_full, const b2_mv_t *__restrict__ pmv,
-                    int lambda, int subpel, b2_mv_t *__restrict__ mv_out, uint32_t *__restrict__ cost_out,
-                    uint8_t *__restrict__ pred_out, uint8_t *__restrict__ part_out, b2_mv_t *__restrict__ mv8_out)
+__device__ __forceinline__ void k2_body(K2Smem &s, const uint8_t *__restrict__ cur, const uint8_t *__restrict__ ref, int pitch, size_t plane_stride,
+                                        int mbw, int mbh, const b2_mv_t mvf, const b2_mv_t pm, int lambda, int subpel,
+                                        b2_mv_t *__restrict__ mv_out, uint32_t *__restrict__ cost_out, uint8_t *__restrict__ pred_out,
+                                        uint8_t *__restrict__ part_out, b2_mv_t *__restrict__ mv8_out)
 {
-    __shared__ __align__(16) K2Smem s;
     const int tid = threadIdx.x;
     const int mbx = blockIdx.x, mby = blockIdx.y, frame = blockIdx.z;
     const size_t mbi = ((size_t)frame * mbh + mby) * mbw + mbx;
-    const b2_mv_t mvf = mv_full[mbi];
-    b2_mv_t pm = {0, 0};
-    if (pmv) pm = pmv[mbi];
 
     const uint8_t *cplane = cur + frame * plane_stride + (size_t)(B2_PAD + mby * 16) * pitch + B2_PAD + mbx * 16;
     const uint8_t *rplane = ref + frame * plane_stride + (size_t)(B2_PAD + mby * 16 + mvf.y - 3) * pitch + B2_PAD +
@@ -327,6 +323,20 @@ k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__
     }
 }
 
+template <bool PART>
+__global__ void __launch_bounds__(K2_THREADS)
+k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ ref, int pitch, size_t plane_stride,
+                    int mbw, int mbh, const b2_mv_t *__restrict__ mv_full, const b2_mv_t *__restrict__ pmv,
+                    int lambda, int subpel, b2_mv_t *__restrict__ mv_out, uint32_t *__restrict__ cost_out,
+                    uint8_t *__restrict__ pred_out, uint8_t *__restrict__ part_out, b2_mv_t *__restrict__ mv8_out)
+{
+    __shared__ __align__(16) K2Smem s;
+    const size_t mbi = ((size_t)blockIdx.z * mbh + blockIdx.y) * mbw + blockIdx.x;
+    b2_mv_t pm = {0, 0};
+    if (pmv) pm = pmv[mbi];
+    k2_body<PART>(s, cur, ref, pitch, plane_stride, mbw, mbh, mv_full[mbi], pm, lambda, subpel, mv_out, cost_out, pred_out, part_out, mv8_out);
+}
+
 // ---- wide partition search (row N1, partitions = 2) --------------------------------------------------------------------
 // K1<PART> delivered the best full-pel vector and cost of each of the nine shape parts.  This kernel picks the shape on those
 // costs (oracle: b2o_me_parts_wide) and refines every part of it on its own: patch around the part's vector, half-sample
@@ -384,6 +394,13 @@ k2_me_subpel_wide_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restr
     }
     __syncthreads();
     const int shape = s.shape;
+    if (shape == B2_PART_16x16) {                            // the common case: the tuned single-vector path around part 0's vector
+        const b2_mv_t mv16 = mv9[mbi * 9];
+        __syncthreads();                                     // everyone has read s.shape before the body reuses the shared struct
+        k2_body<false>(s, cur, ref, pitch, plane_stride, mbw, mbh, mv16, pm, lambda, 1, mv_out, cost_out, pred_out, nullptr, nullptr);
+        if (tid == 0) part_out[mbi] = B2_PART_16x16;
+        return;
+    }
     for (int a = 0; a < c_shape_n[shape]; a++) {
         const int p = c_shape_first[shape] + a;
         const int ox = c_part_geo[p][0], oy = c_part_geo[p][1], pw = c_part_geo[p][2], ph = c_part_geo[p][3];
