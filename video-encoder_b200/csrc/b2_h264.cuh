@@ -25,6 +25,7 @@ __device__ __forceinline__ int chroma_qp(int qp) { return qp < 30 ? qp : c_chrom
 struct QParams {
     int qbits, f, mf[3];        // quantiser
     int ls[3], s;               // dequantiser: LevelScale = 16*V, s = qp/6
+    int lsm[3], rnd, sh;        // 4x4 scaling as one multiply-add-shift: w = (z * lsm + rnd) >> sh  (8.5.12.1 for both branches of qP/6 >= 4)
 };
 __device__ __forceinline__ QParams make_qparams(int qp, bool intra)
 {
@@ -34,6 +35,10 @@ __device__ __forceinline__ QParams make_qparams(int qp, bool intra)
     q.s = qp / 6;
 #pragma unroll
     for (int i = 0; i < 3; i++) { q.mf[i] = c_quant_mf[qp % 6][i]; q.ls[i] = 16 * c_dequant_v[qp % 6][i]; }
+    q.sh = q.s >= 4 ? 0 : 4 - q.s;
+    q.rnd = q.s >= 4 ? 0 : 1 << (3 - q.s);
+#pragma unroll
+    for (int i = 0; i < 3; i++) q.lsm[i] = q.s >= 4 ? q.ls[i] << (q.s - 4) : q.ls[i];
     return q;
 }
 // position class of raster index i: 0 = (even,even), 2 = (odd,odd), 1 otherwise
@@ -105,12 +110,12 @@ __device__ __forceinline__ void dequant4x4(const int z[16], int w[16], const QPa
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         if (i == 0 && skip_dc) continue;
-        int ls = q.ls[pos_class(i)];
-        w[i] = q.s >= 4 ? (z[i] * ls) << (q.s - 4) : (z[i] * ls + (1 << (3 - q.s))) >> (4 - q.s);
+        w[i] = (z[i] * q.lsm[pos_class(i)] + q.rnd) >> q.sh;
     }
 }
 
-// SATD of a 4x4 difference block: (sum |H d H^T|) >> 1
+// SATD of a 4x4 difference block: (sum |H d H^T|) >> 1.  The last butterfly stage is folded into the absolute values with
+// |a + b| + |a - b| = 2 max(|a|, |b|): the sum is even and the final shift disappears.
 __device__ __forceinline__ uint32_t satd4x4(const int d[16])
 {
     int t[16];
@@ -125,9 +130,9 @@ __device__ __forceinline__ uint32_t satd4x4(const int d[16])
     for (int x = 0; x < 4; x++) {
         int s01 = t[x] + t[4 + x], d01 = t[x] - t[4 + x];
         int s23 = t[8 + x] + t[12 + x], d23 = t[8 + x] - t[12 + x];
-        s += abs(s01 + s23) + abs(s01 - s23) + abs(d01 - d23) + abs(d01 + d23);
+        s += max(abs(s01), abs(s23)) + max(abs(d01), abs(d23));
     }
-    return s >> 1;
+    return s;
 }
 
 // ---- 8x8 transform path (High profile) -----------------------------------------------

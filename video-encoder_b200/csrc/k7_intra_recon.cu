@@ -388,7 +388,7 @@ __device__ void k7_luma_task(int lane, K7Warp &ws, const FramePlanes &fp, int fr
         const int half = lane >> 4, p = lane & 15, x = p & 3, y = p >> 2;
         const int cls = pos_class(p);
         const uint32_t mf = (uint32_t)q.mf[cls];
-        const int ls = q.ls[cls];
+        const int lsm = q.lsm[cls];
         const int izz = c_izz[p];
         uint32_t mymask = 0;
 #pragma unroll 1
@@ -405,7 +405,7 @@ __device__ void k7_luma_task(int lane, K7Warp &ws, const FramePlanes &fp, int fr
             const int zq = (int)(((uint32_t)abs(w) * mf + (uint32_t)q.f) >> q.qbits);
             const int z = w < 0 ? -zq : zq;
             const uint32_t nz = __ballot_sync(0xffffffffu, act && z != 0);
-            const int wq = q.s >= 4 ? (z * ls) << (q.s - 4) : (z * ls + (1 << (3 - q.s))) >> (4 - q.s);
+            const int wq = (z * lsm + q.rnd) >> q.sh;
             const int res = idct4x4_px(wq, x, y);
             if (act) {
                 cf->blk[b][izz] = (int16_t)z;
