@@ -77,24 +77,74 @@ __device__ __constant__ uint8_t c_qpel_pair[16] = {
 
 __device__ __constant__ int8_t c_subpel_off[9][2] = {{0, 0}, {-1, -1}, {0, -1}, {1, -1}, {-1, 0}, {1, 0}, {-1, 1}, {0, 1}, {1, 1}};
 
-// SATD of 4x4 block `blk` (raster 0..15 inside the MB) for the candidate displaced by (cx,cy)
-// quarter-pels from the full-pel position
-__device__ __forceinline__ uint32_t cand_block_satd(const K2Smem &s, int blk, int cx, int cy)
+// ---- SATD of one 4x4 block of one candidate, on the dot-product unit ---------------------------------------------------------
+// The horizontal Hadamard pass of the residual row (c - p) is linear, so it splits into H.c - H.p: four IDP.4A (u8 x s8) per
+// row against the rows of H4, with H.c of the SOURCE block computed once per thread (a thread keeps its block for all of
+// its candidates) and passed in as the accumulator.  No byte is ever extracted: the prediction row is fetched as one
+// unaligned 32-bit word (two LDS + funnel shift; KP % 4 == 0 keeps the alignment the same on every row) and quarter-sample
+// positions average two such words with the SIMD byte average.  The vertical pass folds its last butterfly stage into
+// |a+c| + |a-c| = 2 max(|a|,|c|), which also absorbs SATD's final halving.  ~2.3x fewer instructions than the scalar form.
+__device__ __forceinline__ int dp4a_us(uint32_t u8x4, uint32_t s8x4, int acc)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(u8x4), "r"(s8x4), "r"(acc));
+    return d;
+}
+
+// rows of H4 as s8x4 (byte x = column x): (1,1,1,1) (1,1,-1,-1) (1,-1,-1,1) (1,-1,1,-1), and their negatives
+constexpr uint32_t H4P0 = 0x01010101u, H4P1 = 0xffff0101u, H4P2 = 0x01ffff01u, H4P3 = 0xff01ff01u;
+constexpr uint32_t H4N0 = 0xffffffffu, H4N1 = 0x0101ffffu, H4N2 = 0xff0101ffu, H4N3 = 0x01ff01ffu;
+
+// H4 applied to the four rows of the source block whose top-left pixel is (px,py) of the macroblock
+__device__ __forceinline__ void cur_block_rows(const K2Smem &s, int px, int py, int (&ch)[16])
+{
+#pragma unroll
+    for (int y = 0; y < 4; y++) {
+        const uint32_t cw = *(const uint32_t *)&s.cur[py + y][px];
+        ch[4 * y + 0] = dp4a_us(cw, H4P0, 0); ch[4 * y + 1] = dp4a_us(cw, H4P1, 0);
+        ch[4 * y + 2] = dp4a_us(cw, H4P2, 0); ch[4 * y + 3] = dp4a_us(cw, H4P3, 0);
+    }
+}
+
+// four consecutive bytes at byte offset `off` (any alignment) + row * KP of the plane array
+struct PlaneWords {
+    const uint32_t *w; uint32_t sh;
+    __device__ __forceinline__ PlaneWords(const K2Smem &s, int off) : w((const uint32_t *)(s.P + (off & ~3))), sh((uint32_t)(off & 3) * 8u) {}
+    __device__ __forceinline__ uint32_t row(int y) const { return __funnelshift_r(w[y * (KP / 4)], w[y * (KP / 4) + 1], sh); }
+};
+
+// the two plane offsets of the candidate displaced by (cx,cy) quarter-pels, for the block at part-local pixel (bx,by)
+__device__ __forceinline__ void cand_planes(int bx, int by, int cx, int cy, int &offA, int &offB)
 {
     const int ix = cx >> 2, iy = cy >> 2;
     const int e = c_qpel_pair[(cy & 3) * 4 + (cx & 3)];
-    const int bx = (blk & 3) * 4, by = (blk >> 2) * 4;
-    const uint8_t *pa = s.P + plane_off(e & 3, bx + ix + ((e >> 2) & 1), by + iy + ((e >> 3) & 1));
-    const uint8_t *pb = s.P + plane_off((e >> 4) & 3, bx + ix + ((e >> 6) & 1), by + iy + ((e >> 7) & 1));
-    int d[16];
+    offA = plane_off(e & 3, bx + ix + ((e >> 2) & 1), by + iy + ((e >> 3) & 1));
+    offB = plane_off((e >> 4) & 3, bx + ix + ((e >> 6) & 1), by + iy + ((e >> 7) & 1));
+}
+
+// SATD of the 4x4 block at part-local pixel (bx,by) for the candidate displaced by (cx,cy) quarter-pels; ch = cur_block_rows
+// of the same block.  TWO = false: half-sample grid positions (one plane, stage 1); true: average of two planes (stage 2).
+template <bool TWO>
+__device__ __forceinline__ uint32_t cand_block_satd(const K2Smem &s, const int (&ch)[16], int bx, int by, int cx, int cy)
+{
+    int offA, offB;
+    cand_planes(bx, by, cx, cy, offA, offB);
+    const PlaneWords A(s, offA), B(s, offB);
+    int t[16];
 #pragma unroll
     for (int y = 0; y < 4; y++) {
-        const uint32_t cw = *(const uint32_t *)&s.cur[by + y][bx];
-#pragma unroll
-        for (int x = 0; x < 4; x++)
-            d[y * 4 + x] = (int)((cw >> (8 * x)) & 255u) - (((int)pa[y * KP + x] + (int)pb[y * KP + x] + 1) >> 1);
+        uint32_t p = A.row(y);
+        if (TWO) p = __vavgu4(p, B.row(y));
+        t[4 * y + 0] = dp4a_us(p, H4N0, ch[4 * y + 0]); t[4 * y + 1] = dp4a_us(p, H4N1, ch[4 * y + 1]);
+        t[4 * y + 2] = dp4a_us(p, H4N2, ch[4 * y + 2]); t[4 * y + 3] = dp4a_us(p, H4N3, ch[4 * y + 3]);
     }
-    return b2::satd4x4(d);
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int a = t[k] + t[4 + k], b = t[k] - t[4 + k], c = t[8 + k] + t[12 + k], d = t[8 + k] - t[12 + k];
+        sum += max(abs(a), abs(c)) + max(abs(b), abs(d));
+    }
+    return (uint32_t)sum;
 }
 
 // refinement of ONE macroblock around the full-pel vector mvf (whole CTA); PART: also the local partition refinement
@@ -173,12 +223,17 @@ __device__ __forceinline__ void k2_body(K2Smem &s, const uint8_t *__restrict__ c
     }
     __syncthreads();
 
+    // every thread keeps ONE 4x4 block (tid & 15) through both stages: its H4-transformed source rows are computed once
+    const int blk = tid & 15, bx = (blk & 3) * 4, by = (blk >> 2) * 4;
+    int ch[16];
+    cur_block_rows(s, bx, by, ch);
+
     if (PART) {
         // ---- partitions: SATD per (candidate, quadrant); every shape part picks its half-pel winner, the cheapest shape
         // is kept and each of its parts tries the 8 quarter-pel neighbours of ITS winner (oracle: b2o_me_subpel_part) ----
         if (tid < 9 * 16) {
-            const int cand = tid >> 4, blk = tid & 15;
-            const uint32_t v = cand_block_satd(s, blk, 2 * c_subpel_off[cand][0], 2 * c_subpel_off[cand][1]);
+            const int cand = tid >> 4;
+            const uint32_t v = cand_block_satd<false>(s, ch, bx, by, 2 * c_subpel_off[cand][0], 2 * c_subpel_off[cand][1]);
             atomicAdd(&s.costq[cand][((blk >> 1) & 1) | ((blk >> 3) << 1)], v);
         }
         __syncthreads();
@@ -213,9 +268,9 @@ __device__ __forceinline__ void k2_body(K2Smem &s, const uint8_t *__restrict__ c
         if (tid < 36) s.costq[tid >> 2][tid & 3] = 0;    // reused for stage 2 (entries 1..8); stage-1 sums are folded into pcost
         __syncthreads();
         if (tid < 8 * 16) {
-            const int cand = 1 + (tid >> 4), blk = tid & 15, q = ((blk >> 1) & 1) | ((blk >> 3) << 1);
+            const int cand = 1 + (tid >> 4), q = ((blk >> 1) & 1) | ((blk >> 3) << 1);
             const int hk = s.qk[q];
-            const uint32_t v = cand_block_satd(s, blk, 2 * c_subpel_off[hk][0] + c_subpel_off[cand][0], 2 * c_subpel_off[hk][1] + c_subpel_off[cand][1]);
+            const uint32_t v = cand_block_satd<true>(s, ch, bx, by, 2 * c_subpel_off[hk][0] + c_subpel_off[cand][0], 2 * c_subpel_off[hk][1] + c_subpel_off[cand][1]);
             atomicAdd(&s.costq[cand][q], v);
         }
         __syncthreads();
@@ -255,8 +310,8 @@ __device__ __forceinline__ void k2_body(K2Smem &s, const uint8_t *__restrict__ c
     // stage 1: centre + 8 half-pel neighbours (offsets x2 quarter units); without sub-pel: centre only
     const int n1 = subpel ? 9 : 1;
     if (tid < n1 * 16) {
-        int cand = tid >> 4, blk = tid & 15;
-        uint32_t v = cand_block_satd(s, blk, 2 * c_subpel_off[cand][0], 2 * c_subpel_off[cand][1]);
+        const int cand = tid >> 4;
+        const uint32_t v = cand_block_satd<false>(s, ch, bx, by, 2 * c_subpel_off[cand][0], 2 * c_subpel_off[cand][1]);
         atomicAdd(&s.cost[cand], v);
     }
     __syncthreads();
@@ -276,8 +331,8 @@ __device__ __forceinline__ void k2_body(K2Smem &s, const uint8_t *__restrict__ c
     const int hx = 2 * c_subpel_off[s.best][0], hy = 2 * c_subpel_off[s.best][1];
     if (subpel) {
         if (tid < 8 * 16) {
-            int cand = 1 + (tid >> 4), blk = tid & 15;
-            uint32_t v = cand_block_satd(s, blk, hx + c_subpel_off[cand][0], hy + c_subpel_off[cand][1]);
+            const int cand = 1 + (tid >> 4);
+            const uint32_t v = cand_block_satd<true>(s, ch, bx, by, hx + c_subpel_off[cand][0], hy + c_subpel_off[cand][1]);
             atomicAdd(&s.cost[cand], v);
         }
         __syncthreads();
@@ -311,14 +366,9 @@ __device__ __forceinline__ void k2_body(K2Smem &s, const uint8_t *__restrict__ c
             const int r = tid >> 2, c = (tid & 3) * 4;
             const int qm = s.qmv[(c >> 3) | ((r >> 3) << 1)];         // displacement of the quadrant this word lies in
             const int cx = (int)(int8_t)(qm & 0xff), cy = (int)(int8_t)((qm >> 8) & 0xff);
-            const int ix = cx >> 2, iy = cy >> 2;
-            const int e = c_qpel_pair[(cy & 3) * 4 + (cx & 3)];
-            const uint8_t *pa = s.P + plane_off(e & 3, c + ix + ((e >> 2) & 1), r + iy + ((e >> 3) & 1));
-            const uint8_t *pb = s.P + plane_off((e >> 4) & 3, c + ix + ((e >> 6) & 1), r + iy + ((e >> 7) & 1));
-            uint32_t w = 0;
-#pragma unroll
-            for (int x = 0; x < 4; x++) w |= (uint32_t)(((int)pa[x] + (int)pb[x] + 1) >> 1) << (8 * x);
-            *(uint32_t *)(pred_out + mbi * 256 + r * 16 + c) = w;
+            int offA, offB;
+            cand_planes(c, r, cx, cy, offA, offB);
+            *(uint32_t *)(pred_out + mbi * 256 + r * 16 + c) = __vavgu4(PlaneWords(s, offA).row(0), PlaneWords(s, offB).row(0));
         }
     }
 }
@@ -343,25 +393,6 @@ k2_me_subpel_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__
 // planes for the part's area, 9 half-pel + 8 quarter-pel candidates with SATD over the part.  Geometry in pixels:
 __device__ __constant__ uint8_t c_part_geo[9][4] = {{0, 0, 16, 16}, {0, 0, 16, 8}, {0, 8, 16, 8}, {0, 0, 8, 16}, {8, 0, 8, 16},
                                                     {0, 0, 8, 8},   {8, 0, 8, 8},  {0, 8, 8, 8},  {8, 8, 8, 8}};
-
-// SATD of the 4x4 block at part-local pixel (lx,ly) for the candidate displaced by (cx,cy) quarter-pels; (ox,oy) = the
-// part's origin inside the macroblock
-__device__ __forceinline__ uint32_t cand_block_satd_at(const K2Smem &s, int lx, int ly, int ox, int oy, int cx, int cy)
-{
-    const int ix = cx >> 2, iy = cy >> 2;
-    const int e = c_qpel_pair[(cy & 3) * 4 + (cx & 3)];
-    const uint8_t *pa = s.P + plane_off(e & 3, lx + ix + ((e >> 2) & 1), ly + iy + ((e >> 3) & 1));
-    const uint8_t *pb = s.P + plane_off((e >> 4) & 3, lx + ix + ((e >> 6) & 1), ly + iy + ((e >> 7) & 1));
-    int d[16];
-#pragma unroll
-    for (int y = 0; y < 4; y++) {
-        const uint32_t cw = *(const uint32_t *)&s.cur[oy + ly + y][ox + lx];
-#pragma unroll
-        for (int x = 0; x < 4; x++)
-            d[y * 4 + x] = (int)((cw >> (8 * x)) & 255u) - (((int)pa[y * KP + x] + (int)pb[y * KP + x] + 1) >> 1);
-    }
-    return b2::satd4x4(d);
-}
 
 __global__ void __launch_bounds__(K2_THREADS)
 k2_me_subpel_wide_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restrict__ ref, int pitch, size_t plane_stride,
@@ -435,9 +466,12 @@ k2_me_subpel_wide_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restr
         }
         __syncthreads();
         const int nbx = pw >> 2, nb = nbx * (ph >> 2);       // 4x4 blocks of the part
+        const int j = tid % nb, lx = (j % nbx) * 4, ly = (j / nbx) * 4;   // a thread keeps its block through both stages
+        int ch[16];
+        cur_block_rows(s, ox + lx, oy + ly, ch);
         if (tid < 9 * nb) {
-            const int cand = tid / nb, j = tid - cand * nb;
-            const uint32_t v = cand_block_satd_at(s, (j % nbx) * 4, (j / nbx) * 4, ox, oy, 2 * c_subpel_off[cand][0], 2 * c_subpel_off[cand][1]);
+            const int cand = tid / nb;
+            const uint32_t v = cand_block_satd<false>(s, ch, lx, ly, 2 * c_subpel_off[cand][0], 2 * c_subpel_off[cand][1]);
             atomicAdd(&s.cost[cand], v);
         }
         __syncthreads();
@@ -455,8 +489,8 @@ k2_me_subpel_wide_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restr
         __syncthreads();
         const int hx = 2 * c_subpel_off[s.best][0], hy = 2 * c_subpel_off[s.best][1];
         if (tid < 8 * nb) {
-            const int cand = 1 + tid / nb, j = tid % nb;
-            const uint32_t v = cand_block_satd_at(s, (j % nbx) * 4, (j / nbx) * 4, ox, oy, hx + c_subpel_off[cand][0], hy + c_subpel_off[cand][1]);
+            const int cand = 1 + tid / nb;
+            const uint32_t v = cand_block_satd<true>(s, ch, lx, ly, hx + c_subpel_off[cand][0], hy + c_subpel_off[cand][1]);
             atomicAdd(&s.cost[cand], v);
         }
         __syncthreads();
