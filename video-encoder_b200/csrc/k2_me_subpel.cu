@@ -19,7 +19,7 @@ constexpr int K2_THREADS = 160;
 
 // All four sample planes live in ONE shared byte array with a common row pitch, so that a candidate is
 // "average of two byte planes" with two base offsets chosen once per thread -- no per-pixel switch.
-constexpr int KP = 24;                                    // common row pitch (bytes)
+constexpr int KP = 28;                                    // common row pitch (bytes): 7 words = a 22-byte patch row at any alignment
 constexpr int OFF_G = 0;                                  // G : 22 rows, origin (X,Y) = (-3,-3)
 constexpr int OFF_B = OFF_G + 22 * KP;                    // b : 18 rows, origin (-1,-1)
 constexpr int OFF_H = OFF_B + 18 * KP;                    // h : 17 rows, origin (-1,-1)
@@ -48,9 +48,10 @@ __device__ __constant__ uint8_t c_shape_n[4] = {1, 2, 2, 4};
 __device__ __constant__ uint8_t c_shape_bits[4] = {0, 2, 2, 8};
 
 // byte offset inside K2Smem::P of sample (X,Y) of plane p (0 G, 1 b, 2 h, 3 j)
-__device__ __forceinline__ int plane_off(int p, int X, int Y)
+// ga: byte alignment the G rows were staged with (the patch is copied as aligned words, so G's columns start at byte ga)
+__device__ __forceinline__ int plane_off(int p, int X, int Y, int ga)
 {
-    return p == 0 ? OFF_G + (Y + 3) * KP + X + 3
+    return p == 0 ? OFF_G + (Y + 3) * KP + X + 3 + ga
          : (p == 1 ? OFF_B : p == 2 ? OFF_H : OFF_J) + (Y + 1) * KP + X + 1;
 }
 
@@ -114,21 +115,21 @@ struct PlaneWords {
 };
 
 // the two plane offsets of the candidate displaced by (cx,cy) quarter-pels, for the block at part-local pixel (bx,by)
-__device__ __forceinline__ void cand_planes(int bx, int by, int cx, int cy, int &offA, int &offB)
+__device__ __forceinline__ void cand_planes(int bx, int by, int cx, int cy, int ga, int &offA, int &offB)
 {
     const int ix = cx >> 2, iy = cy >> 2;
     const int e = c_qpel_pair[(cy & 3) * 4 + (cx & 3)];
-    offA = plane_off(e & 3, bx + ix + ((e >> 2) & 1), by + iy + ((e >> 3) & 1));
-    offB = plane_off((e >> 4) & 3, bx + ix + ((e >> 6) & 1), by + iy + ((e >> 7) & 1));
+    offA = plane_off(e & 3, bx + ix + ((e >> 2) & 1), by + iy + ((e >> 3) & 1), ga);
+    offB = plane_off((e >> 4) & 3, bx + ix + ((e >> 6) & 1), by + iy + ((e >> 7) & 1), ga);
 }
 
 // SATD of the 4x4 block at part-local pixel (bx,by) for the candidate displaced by (cx,cy) quarter-pels; ch = cur_block_rows
 // of the same block.  TWO = false: half-sample grid positions (one plane, stage 1); true: average of two planes (stage 2).
 template <bool TWO>
-__device__ __forceinline__ uint32_t cand_block_satd(const K2Smem &s, const int (&ch)[16], int bx, int by, int cx, int cy)
+__device__ __forceinline__ uint32_t cand_block_satd(const K2Smem &s, const int (&ch)[16], int bx, int by, int cx, int cy, int ga)
 {
     int offA, offB;
-    cand_planes(bx, by, cx, cy, offA, offB);
+    cand_planes(bx, by, cx, cy, ga, offA, offB);
     const PlaneWords A(s, offA), B(s, offB);
     int t[16];
 #pragma unroll
@@ -162,11 +163,14 @@ __device__ __forceinline__ void k2_body(K2Smem &s, const uint8_t *__restrict__ c
     const uint8_t *rplane = ref + frame * plane_stride + (size_t)(B2_PAD + mby * 16 + mvf.y - 3) * pitch + B2_PAD +
                             mbx * 16 + mvf.x - 3;
     uint8_t *PG = s.P + OFF_G, *PB = s.P + OFF_B, *PH = s.P + OFF_H, *PJ = s.P + OFF_J;
-    // 22x22 reference patch; thread -> (row, col) without divisions: 8 rows of 22 per pass (176 > 160: two passes of 11 rows)
-    {
-        const int c = tid % 22, r0 = tid / 22;              // r0 in 0..7 for tid < 154 (160 threads -> 7 full rows + 6)
-        if (tid < 154)
-            for (int r = r0; r < 22; r += 7) PG[r * KP + c] = rplane[(size_t)r * pitch + c];
+    // 22x22 reference patch as ALIGNED words: 7 words cover a 22-byte row at any of the four alignments, 22 x 7 = 154 loads,
+    // one per thread and all in flight at once (byte-wise staging was 8 % of the instructions and 18 % of the stall samples).
+    // The row keeps its alignment in shared memory: G's column X sits at byte X + 3 + ga.  pitch, plane_stride and B2_PAD are
+    // multiples of 4 and the 64-pixel frame border covers the extra bytes.
+    const int ga = (mvf.x + 1) & 3;                          // (mvf.x - 3) mod 4
+    if (tid < 154) {
+        const int r = tid / 7, wi = tid - r * 7;
+        ((uint32_t *)PG)[r * (KP / 4) + wi] = ((const uint32_t *)(rplane - ga))[(size_t)r * (pitch >> 2) + wi];
     }
     if (tid < 64) {
         const int r = tid >> 2, c = tid & 3;
@@ -187,13 +191,13 @@ __device__ __forceinline__ void k2_body(K2Smem &s, const uint8_t *__restrict__ c
             int g[24];
 #pragma unroll
             for (int i = 0; i < 6; i++) {
-                const uint32_t wv = row[i];
+                const uint32_t wv = __funnelshift_r(row[i], row[i + 1], 8 * ga);
                 g[4 * i] = wv & 255; g[4 * i + 1] = (wv >> 8) & 255; g[4 * i + 2] = (wv >> 16) & 255; g[4 * i + 3] = wv >> 24;
             }
 #pragma unroll
             for (int c = 0; c < 17; c++) s.B1[lane][c] = (int16_t)b2::tap6(g[c], g[c + 1], g[c + 2], g[c + 3], g[c + 4], g[c + 5]);
         } else if (warp == 1 && lane < 18) {
-            const uint8_t *q = PG + lane + 2;                                       // column X = lane - 1
+            const uint8_t *q = PG + lane + 2 + ga;                                  // column X = lane - 1
             int g[22];
 #pragma unroll
             for (int r = 0; r < 22; r++) g[r] = q[r * KP];
@@ -233,7 +237,7 @@ __device__ __forceinline__ void k2_body(K2Smem &s, const uint8_t *__restrict__ c
         // is kept and each of its parts tries the 8 quarter-pel neighbours of ITS winner (oracle: b2o_me_subpel_part) ----
         if (tid < 9 * 16) {
             const int cand = tid >> 4;
-            const uint32_t v = cand_block_satd<false>(s, ch, bx, by, 2 * c_subpel_off[cand][0], 2 * c_subpel_off[cand][1]);
+            const uint32_t v = cand_block_satd<false>(s, ch, bx, by, 2 * c_subpel_off[cand][0], 2 * c_subpel_off[cand][1], ga);
             atomicAdd(&s.costq[cand][((blk >> 1) & 1) | ((blk >> 3) << 1)], v);
         }
         __syncthreads();
@@ -270,7 +274,7 @@ __device__ __forceinline__ void k2_body(K2Smem &s, const uint8_t *__restrict__ c
         if (tid < 8 * 16) {
             const int cand = 1 + (tid >> 4), q = ((blk >> 1) & 1) | ((blk >> 3) << 1);
             const int hk = s.qk[q];
-            const uint32_t v = cand_block_satd<true>(s, ch, bx, by, 2 * c_subpel_off[hk][0] + c_subpel_off[cand][0], 2 * c_subpel_off[hk][1] + c_subpel_off[cand][1]);
+            const uint32_t v = cand_block_satd<true>(s, ch, bx, by, 2 * c_subpel_off[hk][0] + c_subpel_off[cand][0], 2 * c_subpel_off[hk][1] + c_subpel_off[cand][1], ga);
             atomicAdd(&s.costq[cand][q], v);
         }
         __syncthreads();
@@ -311,7 +315,7 @@ __device__ __forceinline__ void k2_body(K2Smem &s, const uint8_t *__restrict__ c
     const int n1 = subpel ? 9 : 1;
     if (tid < n1 * 16) {
         const int cand = tid >> 4;
-        const uint32_t v = cand_block_satd<false>(s, ch, bx, by, 2 * c_subpel_off[cand][0], 2 * c_subpel_off[cand][1]);
+        const uint32_t v = cand_block_satd<false>(s, ch, bx, by, 2 * c_subpel_off[cand][0], 2 * c_subpel_off[cand][1], ga);
         atomicAdd(&s.cost[cand], v);
     }
     __syncthreads();
@@ -332,7 +336,7 @@ __device__ __forceinline__ void k2_body(K2Smem &s, const uint8_t *__restrict__ c
     if (subpel) {
         if (tid < 8 * 16) {
             const int cand = 1 + (tid >> 4);
-            const uint32_t v = cand_block_satd<true>(s, ch, bx, by, hx + c_subpel_off[cand][0], hy + c_subpel_off[cand][1]);
+            const uint32_t v = cand_block_satd<true>(s, ch, bx, by, hx + c_subpel_off[cand][0], hy + c_subpel_off[cand][1], ga);
             atomicAdd(&s.cost[cand], v);
         }
         __syncthreads();
@@ -367,7 +371,7 @@ __device__ __forceinline__ void k2_body(K2Smem &s, const uint8_t *__restrict__ c
             const int qm = s.qmv[(c >> 3) | ((r >> 3) << 1)];         // displacement of the quadrant this word lies in
             const int cx = (int)(int8_t)(qm & 0xff), cy = (int)(int8_t)((qm >> 8) & 0xff);
             int offA, offB;
-            cand_planes(c, r, cx, cy, offA, offB);
+            cand_planes(c, r, cx, cy, ga, offA, offB);
             *(uint32_t *)(pred_out + mbi * 256 + r * 16 + c) = __vavgu4(PlaneWords(s, offA).row(0), PlaneWords(s, offB).row(0));
         }
     }
@@ -471,7 +475,7 @@ k2_me_subpel_wide_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restr
         cur_block_rows(s, ox + lx, oy + ly, ch);
         if (tid < 9 * nb) {
             const int cand = tid / nb;
-            const uint32_t v = cand_block_satd<false>(s, ch, lx, ly, 2 * c_subpel_off[cand][0], 2 * c_subpel_off[cand][1]);
+            const uint32_t v = cand_block_satd<false>(s, ch, lx, ly, 2 * c_subpel_off[cand][0], 2 * c_subpel_off[cand][1], 0);
             atomicAdd(&s.cost[cand], v);
         }
         __syncthreads();
@@ -490,7 +494,7 @@ k2_me_subpel_wide_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restr
         const int hx = 2 * c_subpel_off[s.best][0], hy = 2 * c_subpel_off[s.best][1];
         if (tid < 8 * nb) {
             const int cand = 1 + tid / nb;
-            const uint32_t v = cand_block_satd<true>(s, ch, lx, ly, hx + c_subpel_off[cand][0], hy + c_subpel_off[cand][1]);
+            const uint32_t v = cand_block_satd<true>(s, ch, lx, ly, hx + c_subpel_off[cand][0], hy + c_subpel_off[cand][1], 0);
             atomicAdd(&s.cost[cand], v);
         }
         __syncthreads();
@@ -517,17 +521,12 @@ k2_me_subpel_wide_kernel(const uint8_t *__restrict__ cur, const uint8_t *__restr
         __syncthreads();
         {   // the part's motion-compensated prediction -> K5
             const int cx = (int)(int8_t)(s.best & 0xff), cy = (int)(int8_t)((s.best >> 8) & 0xff);
-            const int ix = cx >> 2, iy = cy >> 2;
-            const int e = c_qpel_pair[(cy & 3) * 4 + (cx & 3)];
             const int wq = pw >> 2;                          // 4-pixel words per row
             if (tid < wq * ph) {
                 const int r = tid / wq, c = (tid - r * wq) * 4;
-                const uint8_t *pa = s.P + plane_off(e & 3, c + ix + ((e >> 2) & 1), r + iy + ((e >> 3) & 1));
-                const uint8_t *pb = s.P + plane_off((e >> 4) & 3, c + ix + ((e >> 6) & 1), r + iy + ((e >> 7) & 1));
-                uint32_t w = 0;
-#pragma unroll
-                for (int x = 0; x < 4; x++) w |= (uint32_t)(((int)pa[x] + (int)pb[x] + 1) >> 1) << (8 * x);
-                *(uint32_t *)(pred_out + mbi * 256 + (oy + r) * 16 + ox + c) = w;
+                int offA, offB;
+                cand_planes(c, r, cx, cy, 0, offA, offB);
+                *(uint32_t *)(pred_out + mbi * 256 + (oy + r) * 16 + ox + c) = __vavgu4(PlaneWords(s, offA).row(0), PlaneWords(s, offB).row(0));
             }
         }
         __syncthreads();                                     // planes are rebuilt for the next part
