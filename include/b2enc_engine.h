@@ -51,6 +51,11 @@ uint8_t *b2_engine_host_input(b2_engine_t *e, int slot, int ring);
 /* copy a strided picture (plane pointers + strides as sws_scale takes them, av_encode.c:545) into
  * the pinned staging of (slot, ring); the source may be freed on return (cf. av_encode.c:550) */
 int b2_engine_put_frame(b2_engine_t *e, int slot, int ring, const uint8_t *const src[4], const int stride[4]);
+/* the same hand-over without the host copy: when the picture lives in page-locked memory (b2_picture_alloc, the mirror of
+ * x264_picture_alloc av_encode.c:415) its planes are DMA'd straight into the device ring and the call returns once the
+ * source has been read; the following b2_engine_h2d skips that entry.  Returns 0, 1 = source not page-locked (fall back to
+ * b2_engine_put_frame), -1 = error.  May be called from another host thread than h2d/encode/d2h for a different ring position. */
+int b2_engine_put_frame_direct(b2_engine_t *e, int slot, int ring, const uint8_t *const src[4], const int stride[4]);
 /* async pinned-host -> device copy of ring position `ring` for slots [slot0, slot0+nslots) */
 int b2_engine_h2d(b2_engine_t *e, int slot0, int nslots, int ring);
 /* async: encode ring position `ring` of slots [0,nslots) as one frame each (B2_FRAME_I / B2_FRAME_P) */

@@ -3,11 +3,11 @@ import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "video-encoder_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np, b2enc, b2oracle as o
-W, H, N = 1920, 1080, 1024
+W, H, N = 1920, 1080, int(os.environ.get("B2_PROBE_FRAMES", "2048"))
 frames = [o.synth_frame(W, H, t % 16) for t in range(16)]
 for name, kw in (("baseline (CAVLC)", dict(profile="baseline")), ("main (CABAC, default)", dict()),
                  ("high (CABAC + 8x8 + partitions 2)", dict(profile="high", b_transform_8x8=1, b_partitions=2))):
-    for slots in (4, 8):
+    for slots in (4, 8, 16):
         enc = b2enc.DropInEncoder(W, H, preset="slow", tune="film", quality=26, fps=(60, 1), annexb=0, i_keyint_max=32, i_gop_slots=slots, **kw)
         t0 = time.perf_counter(); nbytes = 0; nout = 0
         for t in range(N):

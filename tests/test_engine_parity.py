@@ -18,7 +18,7 @@ def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="
     eng = b2.Engine(w, h, slots=S, fmt=fmt, ring=2, merange=R, qp=qp, subpel=subpel, intra_in_p=intra_in_p, deblock=deblock,
                     transform8x8=transform8x8, pack_levels=pack_levels, partitions=partitions)
     prm = oracle.Params(qp, R, subpel, intra_in_p, deblock, transform8x8, partitions)
-    stats = {"t8": 0, "coded4": 0, "i8": 0, "parts": np.zeros(4, int)}
+    stats = {"t8": 0, "coded4": 0, "i8": 0, "parts": np.zeros(4, int), "mvx_mod4": np.zeros(4, int)}
     prev = [None] * S; prev_mv = [None] * S
     for t in range(T):
         for s in range(S):
@@ -40,6 +40,7 @@ def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="
                 mvf_o, cf_o = oracle.me_fullpel(cur, prev[s], R, prev_mv[s], oracle.lib().b2o_lambda(qp))
                 assert np.array_equal(eng.stage(s, 0), mvf_o), f"K1 mv t={t} s={s}"
                 assert np.array_equal(eng.stage(s, 1), cf_o), f"K1 cost t={t} s={s}"
+                stats["mvx_mod4"] += np.bincount(mvf_o["x"].astype(int) & 3, minlength=4)
             for f in INFO_FIELDS:
                 assert np.array_equal(info_g[f], info_o[f]), f"info.{f} t={t} s={s}: {np.argwhere(info_g[f] != info_o[f])[:5].tolist()}"
             assert np.array_equal(coef_g["blk"], coef_o["blk"]), f"levels t={t} s={s}"
@@ -60,6 +61,68 @@ def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="
 def test_engine_matches_oracle(oracle, b2, w, h, qp, R, cut):
     seqs = [smooth_seq(w, h, 5, seed=qp, cut=cut)]
     run_and_compare(oracle, b2, seqs, w, h, qp, R)
+
+
+def test_k2_patch_alignments(oracle, b2):
+    """K2 stages its 22x22 reference patch as aligned words and keeps the byte alignment (mv.x - 3) mod 4 in shared memory:
+    bands that pan by different whole-pixel amounts make every alignment occur, and everything stays oracle-exact"""
+    w, h, n = 256, 256, 3
+    rng = np.random.default_rng(77)
+    import cv2
+    base = cv2.resize(rng.integers(0, 256, (h // 4 + 8, (w + 128) // 4 + 8)).astype(np.float32), (w + 128, h), interpolation=cv2.INTER_CUBIC)
+    pans = [0, 1, 2, 3, -1, -2, -3, 6]                                   # whole pixels per frame, one per 32-row band
+    frames = []
+    for t in range(n):
+        img = np.empty((h, w), np.uint8)
+        for b, px in enumerate(pans):
+            x0 = 64 + px * t
+            img[32 * b:32 * b + 32] = np.clip(base[32 * b:32 * b + 32, x0:x0 + w] + rng.normal(0, 1.0, (32, w)), 0, 255).astype(np.uint8)
+        frames.append((img, (img[::2, ::2] // 2 + 60).astype(np.uint8), (200 - img[::2, ::2] // 2).astype(np.uint8)))
+    stats = run_and_compare(oracle, b2, [frames], w, h, 28, 16)
+    assert (stats["mvx_mod4"] > 8).all(), stats["mvx_mod4"]
+
+
+def test_put_frame_direct(oracle, b2):
+    """b2_engine_put_frame_direct: a picture in page-locked memory (strided, as b2_picture_alloc hands it out) goes to the
+    device ring without the host copy and h2d skips it; pageable sources are refused with 1; results equal the staged path"""
+    import ctypes as C
+    w, h = 208, 112
+    L = b2.lib()
+    L.b2_pinned_alloc.restype = C.c_void_p; L.b2_pinned_alloc.argtypes = [C.c_size_t]; L.b2_pinned_free.argtypes = [C.c_void_p]
+    stride = w + 48
+    nbytes = stride * h + 2 * (stride // 2) * (h // 2)
+    buf = L.b2_pinned_alloc(nbytes)
+    assert buf
+    try:
+        mem = np.frombuffer((C.c_uint8 * nbytes).from_address(buf), np.uint8)
+        py = mem[:stride * h].reshape(h, stride)[:, :w]
+        pu = mem[stride * h:stride * h + (stride // 2) * (h // 2)].reshape(h // 2, stride // 2)[:, :w // 2]
+        pv = mem[stride * h + (stride // 2) * (h // 2):].reshape(h // 2, stride // 2)[:, :w // 2]
+        frames = smooth_seq(w, h, 3, seed=5)
+        eng_a = b2.Engine(w, h, slots=2, ring=2, merange=16, qp=28)
+        eng_b = b2.Engine(w, h, slots=2, ring=2, merange=16, qp=28)
+        assert eng_a.put_frame_direct(0, 0, [np.ascontiguousarray(p) for p in frames[0]]) == 1      # pageable: refused
+        for t, f in enumerate(frames):
+            for s in range(2):
+                g = frames[(t + s) % 3] if t == 0 else (frames[t] if s == 0 else frames[(t + 1) % 3])
+                py[:] = g[0]; pu[:] = g[1]; pv[:] = g[2]
+                if s == 0:
+                    assert eng_a.put_frame_direct(s, t % 2, [py, pu, pv]) == 0
+                else:
+                    eng_a.put_frame(s, t % 2, list(g))               # mixed: one entry direct, one staged
+                eng_b.put_frame(s, t % 2, list(g))
+            mem[:] = 0                                               # the source may be reused as soon as the call returns
+            ft = b2.FRAME_I if t == 0 else b2.FRAME_P
+            for e in (eng_a, eng_b):
+                e.h2d(ring=t % 2); e.encode(ft, ring=t % 2); e.d2h(); e.sync()
+            for s in range(2):
+                ia, ca = eng_a.results(s); ib, cb = eng_b.results(s)
+                assert np.array_equal(ia, ib) and np.array_equal(ca["blk"], cb["blk"]), f"t={t} s={s}"
+                for pa, pb in zip(eng_a.recon(s), eng_b.recon(s)):
+                    assert np.array_equal(pa, pb)
+        eng_a.close(); eng_b.close()
+    finally:
+        L.b2_pinned_free(buf)
 
 
 def test_engine_lockstep_slots(oracle, b2):

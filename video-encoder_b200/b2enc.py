@@ -182,6 +182,7 @@ class Engine:
             getattr(L, fn).argtypes = [C.c_void_p]
         L.b2_engine_host_input.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.b2_engine_put_frame.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.b2_engine_put_frame_direct.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.b2_engine_h2d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.b2_engine_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.b2_engine_d2h.argtypes = [C.c_void_p, C.c_int]
@@ -237,6 +238,15 @@ class Engine:
         sp = (C.c_void_p * 4)(*([p.ctypes.data for p in planes] + [None] * (4 - len(planes))))
         ss = (C.c_int * 4)(*([p.shape[1] for p in planes] + [0] * (4 - len(planes))))
         self._ck(self.L.b2_engine_put_frame(self.h, slot, ring, sp, ss), "put_frame")
+
+    def put_frame_direct(self, slot, ring, planes):
+        """planes: uint8 arrays (any host memory); returns 0 when they were DMA'd straight into the device ring, 1 when the
+        source is not page-locked (nothing copied: use put_frame)"""
+        sp = (C.c_void_p * 4)(*([p.ctypes.data for p in planes] + [None] * (4 - len(planes))))
+        ss = (C.c_int * 4)(*([p.strides[0] for p in planes] + [0] * (4 - len(planes))))
+        rc = self.L.b2_engine_put_frame_direct(self.h, slot, ring, sp, ss)
+        if rc < 0: self._ck(rc, "put_frame_direct")
+        return rc
 
     def h2d(self, slot0=0, nslots=None, ring=0):
         self._ck(self.L.b2_engine_h2d(self.h, slot0, self.slots if nslots is None else nslots, ring), "h2d")

@@ -70,6 +70,11 @@ struct b2_engine {
     struct Ticket { std::vector<int> set; } ticket[2];
     int cur_ticket = 0;
     cudaStream_t st = nullptr, st_in = nullptr, st_out = nullptr;     // st: timer / join stream
+    // b2_engine_put_frame_direct: DMA straight from the caller's pinned picture into the device ring (own stream; may run on
+    // another host thread than h2d/encode/d2h as long as the two work on different ring positions)
+    cudaStream_t st_put = nullptr;
+    std::vector<uint8_t> in_direct;                                   // [slot * in_ring + ring]: entry is already on the device
+    const void *direct_last = nullptr; bool direct_last_ok = false;   // pinned-ness of the last source pointer looked up
     std::vector<cudaEvent_t> ev_h2d;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     long launches = 0;
@@ -151,6 +156,8 @@ static int engine_alloc(b2_engine *e)
     }
     ENG_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     ENG_OK(cudaStreamCreateWithFlags(&e->st_in, cudaStreamNonBlocking));
+    ENG_OK(cudaStreamCreateWithFlags(&e->st_put, cudaStreamNonBlocking));
+    e->in_direct.assign((size_t)c.in_ring * S, 0);
     ENG_OK(cudaStreamCreateWithFlags(&e->st_out, cudaStreamNonBlocking));
     e->ev_h2d.resize(c.in_ring);
     for (int r = 0; r < c.in_ring; r++) ENG_OK(cudaEventCreateWithFlags(&e->ev_h2d[r], cudaEventDisableTiming));
@@ -238,6 +245,7 @@ extern "C" void b2_engine_destroy(b2_engine_t *e)
     if (e->ev_t1) cudaEventDestroy(e->ev_t1);
     if (e->st) cudaStreamDestroy(e->st);
     if (e->st_in) cudaStreamDestroy(e->st_in);
+    if (e->st_put) cudaStreamDestroy(e->st_put);
     if (e->st_out) cudaStreamDestroy(e->st_out);
     delete e;
 }
@@ -290,6 +298,33 @@ extern "C" int b2_engine_put_frame(b2_engine_t *e, int slot, int ring, const uin
     return 0;
 }
 
+// 0: copied; 1: the source is not page-locked host memory (use b2_engine_put_frame); -1: error
+extern "C" int b2_engine_put_frame_direct(b2_engine_t *e, int slot, int ring, const uint8_t *const src[4], const int stride[4])
+{
+    if (slot < 0 || slot >= e->cfg.slots || ring < 0 || ring >= e->cfg.in_ring || !src || !src[0]) return -1;
+    cudaSetDevice(e->cfg.device);
+    if (src[0] != e->direct_last) {
+        cudaPointerAttributes a;
+        const bool ok = cudaPointerGetAttributes(&a, src[0]) == cudaSuccess && a.type == cudaMemoryTypeHost;
+        cudaGetLastError();                             // an unregistered pointer is not an error here
+        e->direct_last = src[0]; e->direct_last_ok = ok;
+    }
+    if (!e->direct_last_ok) return 1;
+    Group *gr = group_of(e, slot);
+    if (!gr) return -1;
+    ENG_OK(cudaStreamWaitEvent(e->st_put, gr->ev_k0[ring], 0));     // the K0 that last read this ring entry
+    int rb[3], rows[3];
+    const int np = b2_fmt_layout(e->cfg.in_fmt, e->cfg.width, e->cfg.height, rb, rows);
+    uint8_t *dst = e->d_in + in_off(e, slot, ring);
+    for (int p = 0; p < np; p++) {
+        ENG_OK(cudaMemcpy2DAsync(dst, rb[p], src[p], stride[p], rb[p], rows[p], cudaMemcpyHostToDevice, e->st_put));
+        dst += (size_t)rb[p] * rows[p];
+    }
+    ENG_OK(cudaStreamSynchronize(e->st_put));            // the caller may refill the picture as soon as this returns
+    e->in_direct[(size_t)slot * e->cfg.in_ring + ring] = 1;
+    return 0;
+}
+
 extern "C" int b2_engine_h2d(b2_engine_t *e, int slot0, int nslots, int ring)
 {
     if (slot0 < 0 || nslots < 1 || slot0 + nslots > e->cfg.slots || ring < 0 || ring >= e->cfg.in_ring) return -1;
@@ -297,11 +332,15 @@ extern "C" int b2_engine_h2d(b2_engine_t *e, int slot0, int nslots, int ring)
     // do not overwrite a ring entry that a previously issued K0 of an affected group still has to read
     for (auto &gr : e->groups)
         if (gr.slot0 < slot0 + nslots && slot0 < gr.slot0 + gr.n) ENG_OK(cudaStreamWaitEvent(e->st_in, gr.ev_k0[ring], 0));
-    if (e->cfg.in_ring == 1) {
+    bool any_direct = false;                             // entries that b2_engine_put_frame_direct already placed on the device
+    for (int s = slot0; s < slot0 + nslots; s++) any_direct |= e->in_direct[(size_t)s * e->cfg.in_ring + ring] != 0;
+    if (e->cfg.in_ring == 1 && !any_direct) {
         const size_t off = in_off(e, slot0, 0);
         ENG_OK(cudaMemcpyAsync(e->d_in + off, e->h_in + off, e->in_stride * nslots, cudaMemcpyHostToDevice, e->st_in));
     } else {
         for (int s = slot0; s < slot0 + nslots; s++) {
+            uint8_t &direct = e->in_direct[(size_t)s * e->cfg.in_ring + ring];
+            if (direct) { direct = 0; continue; }
             const size_t off = in_off(e, s, ring);
             ENG_OK(cudaMemcpyAsync(e->d_in + off, e->h_in + off, e->in_bytes, cudaMemcpyHostToDevice, e->st_in));
         }

@@ -36,7 +36,9 @@ typedef struct {
 
 #define B2_MAX_WORKERS 16
 
-typedef struct { int qi, slot, t, ticket; int64_t gop_index; } job_t;
+/* one frame to entropy-code; the per-MB decisions and the packed levels are heap copies of the engine's pinned result set, so
+ * the GPU may run ahead of the entropy workers by any number of steps (the engine keeps only two result sets) */
+typedef struct { int qi, slot, t; int64_t gop_index; uint8_t *res; size_t packed_bytes; } job_t;
 
 struct b2_encoder {
     b2_param_t p;
@@ -44,7 +46,9 @@ struct b2_encoder {
     b2_engine_t *eng;
     b2h_entropy_t *ent;
     b2h_seq_t seq;
-    /* entropy worker pool: one closed GOP / stream per job, each worker owns its neighbour-map scratch */
+    /* entropy worker pool: one frame per job, queued per batch in GPU completion order; each worker owns its neighbour-map
+     * scratch.  Frames of one GOP are independent for the entropy stage (contexts reset per slice), so frame t+1 of a GOP
+     * may be coded while frame t still is -- all workers stay busy even with fewer GOP slots than host cores. */
     int nworkers;
     pthread_t workers[B2_MAX_WORKERS];
     b2h_entropy_t *went[B2_MAX_WORKERS];
@@ -186,9 +190,9 @@ b2_t *b2_encoder_open(b2_param_t *p)
     pthread_mutex_init(&h->mu, NULL); pthread_cond_init(&h->cv_job, NULL); pthread_cond_init(&h->cv_done, NULL);
     if (h->S > 1) {
         long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
-        int nw = h->S < B2_MAX_WORKERS ? h->S : B2_MAX_WORKERS;
+        int nw = B2_MAX_WORKERS;                         /* frames, not GOPs, are the unit of work: use the cores there are */
         if (ncpu > 0 && nw > ncpu) nw = (int)ncpu;
-        h->jobs = (job_t *)calloc((size_t)h->S, sizeof(job_t));
+        h->jobs = (job_t *)calloc((size_t)h->S * h->L, sizeof(job_t));
         for (int i = 0; i < nw; i++) {
             h->went[i] = b2h_entropy_create(h->mbw, h->mbh);
             h->wscratch[i] = (uint8_t *)malloc(h->scratch_cap);
@@ -227,6 +231,8 @@ void b2_encoder_close(b2_t *h)
         for (int i = 0; i < h->nworkers; i++) pthread_join(h->workers[i], NULL);
     }
     for (int i = 0; i < B2_MAX_WORKERS; i++) { b2h_entropy_destroy(h->went[i]); free(h->wscratch[i]); }
+    if (h->jobs)
+        for (int i = h->next_job; i < h->njobs; i++) free(h->jobs[i].res);          /* frames queued but never coded (error paths) */
     free(h->jobs);
     if (h->outq)
         for (int i = 0; i < h->S * h->L; i++) free(h->outq[i].data);
@@ -236,6 +242,14 @@ void b2_encoder_close(b2_t *h)
     free(h);
 }
 
+/* picture -> engine input ring: DMA from the page-locked picture when it is one (no host copy), else through the pinned staging */
+static int put_picture(b2_t *h, int slot, int ring, const b2_picture_t *pic)
+{
+    int rc = b2_engine_put_frame_direct(h->eng, slot, ring, (const uint8_t *const *)pic->img.plane, pic->img.i_stride);
+    if (rc > 0) rc = b2_engine_put_frame(h->eng, slot, ring, (const uint8_t *const *)pic->img.plane, pic->img.i_stride);
+    return rc;
+}
+
 static void put_prefix(uint8_t *d, int annexb, size_t nal_size)
 {
     if (annexb) { d[0] = 0; d[1] = 0; d[2] = 0; d[3] = 1; }
@@ -243,7 +257,8 @@ static void put_prefix(uint8_t *d, int annexb, size_t nal_size)
 }
 
 /* entropy-code one frame's results into outq[qi] */
-static int finish_frame(b2_t *h, b2h_entropy_t *ent, uint8_t *s, int ticket, int qi, int slot, int t, int64_t gop_index)
+static int finish_frame(b2_t *h, b2h_entropy_t *ent, uint8_t *s, const b2_mbinfo_t *info, const uint8_t *packed, size_t packed_bytes,
+                        int qi, int t, int64_t gop_index)
 {
     outframe_t *o = &h->outq[qi];
     size_t pos = 0;
@@ -261,9 +276,6 @@ static int finish_frame(b2_t *h, b2h_entropy_t *ent, uint8_t *s, int ticket, int
             pos += n + 4;
         }
     }
-    const b2_mbinfo_t *info = ticket < 0 ? b2_engine_info(h->eng, slot) : b2_engine_info_ticket(h->eng, ticket, slot);
-    size_t packed_bytes = 0;
-    const uint8_t *packed = ticket < 0 ? b2_engine_packed(h->eng, slot, &packed_bytes) : b2_engine_packed_ticket(h->eng, ticket, slot, &packed_bytes);
     if (!info || !packed) return -1;
     size_t n = b2h_write_slice_packed(ent, &h->seq, is_idr ? B2_FRAME_I : B2_FRAME_P, t, (int)(gop_index & 0xffff), info, packed,
                                       packed_bytes, s + pos + 4, h->scratch_cap - pos - 4);
@@ -294,37 +306,55 @@ static void *worker_main(void *arg)
         if (h->stop) break;
         job_t j = h->jobs[h->next_job++];
         pthread_mutex_unlock(&h->mu);
-        int rc = finish_frame(h, h->went[me], h->wscratch[me], j.ticket, j.qi, j.slot, j.t, j.gop_index);
+        int rc = finish_frame(h, h->went[me], h->wscratch[me], (const b2_mbinfo_t *)j.res, j.res + (size_t)h->nmb * sizeof(b2_mbinfo_t),
+                              j.packed_bytes, j.qi, j.t, j.gop_index);
+        free(j.res);
         pthread_mutex_lock(&h->mu);
         if (rc) h->job_error = 1;
-        if (++h->done_jobs == h->njobs) pthread_cond_signal(&h->cv_done);
+        h->done_jobs++;
+        pthread_cond_broadcast(&h->cv_done);
     }
     pthread_mutex_unlock(&h->mu);
     return NULL;
 }
 
-/* entropy-code frame t of GOPs [0,nt) on the worker pool (or inline when there is none) */
+/* queue frame t of GOPs [0,nt) for the worker pool (or code it inline when there is none): the result set behind `ticket`
+ * is copied out, so it may be overwritten as soon as this returns */
 static int entropy_step(b2_t *h, int t, int nt, int ticket, const int64_t *pts)
 {
-    if (h->nworkers == 0) {
-        for (int g = 0; g < nt; g++) {
-            if (finish_frame(h, h->ent, h->scratch, ticket, g * h->L + t, g, t, h->gops_done + g)) return -1;
-            h->outq[g * h->L + t].pts = pts[g * h->L + t];
-        }
-        return 0;
-    }
-    pthread_mutex_lock(&h->mu);
     for (int g = 0; g < nt; g++) {
-        job_t j = {g * h->L + t, g, t, ticket, h->gops_done + g};
-        h->jobs[g] = j;
+        const int qi = g * h->L + t;
+        const b2_mbinfo_t *info = b2_engine_info_ticket(h->eng, ticket, g);
+        size_t packed_bytes = 0;
+        const uint8_t *packed = b2_engine_packed_ticket(h->eng, ticket, g, &packed_bytes);
+        if (!info || !packed) return -1;
+        h->outq[qi].pts = pts[qi];
+        if (h->nworkers == 0) {
+            if (finish_frame(h, h->ent, h->scratch, info, packed, packed_bytes, qi, t, h->gops_done + g)) return -1;
+            continue;
+        }
+        const size_t ni = (size_t)h->nmb * sizeof(b2_mbinfo_t);
+        job_t j = {qi, g, t, h->gops_done + g, (uint8_t *)malloc(ni + packed_bytes + 1), packed_bytes};
+        if (!j.res) return -1;
+        memcpy(j.res, info, ni);
+        memcpy(j.res + ni, packed, packed_bytes);
+        pthread_mutex_lock(&h->mu);
+        h->jobs[h->njobs++] = j;
+        pthread_cond_signal(&h->cv_job);
+        pthread_mutex_unlock(&h->mu);
     }
-    h->njobs = nt; h->next_job = 0; h->done_jobs = 0;
-    pthread_cond_broadcast(&h->cv_job);
+    return 0;
+}
+
+/* wait until every queued frame of the batch is coded, then reset the queue */
+static int entropy_drain(b2_t *h)
+{
+    if (h->nworkers == 0) return 0;
+    pthread_mutex_lock(&h->mu);
     while (h->done_jobs < h->njobs) pthread_cond_wait(&h->cv_done, &h->mu);
-    h->njobs = 0; h->next_job = 0;
-    int err = h->job_error;
+    h->njobs = 0; h->next_job = 0; h->done_jobs = 0;
+    const int err = h->job_error;
     pthread_mutex_unlock(&h->mu);
-    for (int g = 0; g < nt; g++) h->outq[g * h->L + t].pts = pts[g * h->L + t];
     return err ? -1 : 0;
 }
 
@@ -353,6 +383,7 @@ static int process_batch(b2_t *h, int half, int n)
         if (entropy_step(h, t, nt, ticket, pts)) return -1;
         nt = nt_next;
     }
+    if (entropy_drain(h)) return -1;
     if (b2_engine_sync(h->eng)) return -1;
     h->gops_done += ngop;
     pthread_mutex_lock(&h->pmu);                          /* hand the frames over in display order */
@@ -436,11 +467,13 @@ int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic
         /* zero-delay mode: one slot, encode every picture as it arrives */
         if (!pic_in) return 0;
         const int t = h->gop_pos;
-        if (b2_engine_put_frame(h->eng, 0, 0, (const uint8_t *const *)pic_in->img.plane, pic_in->img.i_stride)) return -1;
+        if (put_picture(h, 0, 0, pic_in)) return -1;
         if (b2_engine_h2d(h->eng, 0, 1, 0) || b2_engine_encode(h->eng, t == 0 ? B2_FRAME_I : B2_FRAME_P, 1, 0) ||
             b2_engine_d2h(h->eng, 1) || b2_engine_sync(h->eng))
             return -1;
-        if (finish_frame(h, h->ent, h->scratch, -1, 0, 0, t, h->gops_done)) return -1;
+        size_t packed_bytes = 0;
+        const uint8_t *packed = b2_engine_packed(h->eng, 0, &packed_bytes);
+        if (finish_frame(h, h->ent, h->scratch, b2_engine_info(h->eng, 0), packed, packed_bytes, 0, t, h->gops_done)) return -1;
         h->outq[0].pts = pic_in->i_pts;
         h->gop_pos = t + 1;
         if (h->gop_pos == h->L) { h->gop_pos = 0; h->gops_done++; }
@@ -448,7 +481,7 @@ int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic
     }
     if (pic_in) {
         const int idx = h->batch_frames, g = idx / h->L, t = idx % h->L;
-        if (b2_engine_put_frame(h->eng, g, h->gather_half * h->L + t, (const uint8_t *const *)pic_in->img.plane, pic_in->img.i_stride)) return -1;
+        if (put_picture(h, g, h->gather_half * h->L + t, pic_in)) return -1;
         h->pts[(size_t)h->gather_half * h->S * h->L + idx] = pic_in->i_pts;
         h->batch_frames++;
         if (h->batch_frames == h->S * h->L) submit_batch(h);        /* full: the pipeline thread takes it, gathering goes on */
