@@ -114,6 +114,65 @@ __device__ __forceinline__ void dequant4x4(const int z[16], int w[16], const QPa
     }
 }
 
+// ---- SATD in the transform domain for the "flat" intra predictors ------------------------------------------------------------
+// H (src - pred) H^T = H src H^T - H pred H^T, and a predictor that is constant along columns (vertical), along rows
+// (horizontal) or everywhere (DC) has a transform with one non-zero row, column or coefficient.  With the source block's
+// transform T kept per lane, those modes cost a 4-point Hadamard of the edge and four |.| instead of a prediction, a
+// difference block and a full 4x4 Hadamard -- exact by linearity, 9 of K3's 17 SATDs per lane.
+// Common output order of the 4-point Hadamard: rows (1,1,1,1) (1,1,-1,-1) (1,-1,-1,1) (1,-1,1,-1).
+__device__ __forceinline__ void had4(int v0, int v1, int v2, int v3, int &o0, int &o1, int &o2, int &o3)
+{
+    const int a = v0 + v1, b = v0 - v1, c = v2 + v3, d = v2 - v3;
+    o0 = a + c; o1 = a - c; o2 = b - d; o3 = b + d;
+}
+__device__ __forceinline__ int dp4a_u8s8(uint32_t u8x4, uint32_t s8x4, int acc)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(u8x4), "r"(s8x4), "r"(acc));
+    return d;
+}
+struct SrcHad {
+    int T[16];        // T[j * 4 + k]: vertical frequency j, horizontal frequency k
+    int A, R0, C0;    // sum |T|, sum_k |T[0][k]|, sum_j |T[j][0]|
+};
+// rows: the four source rows as little-endian u8x4 words (byte x = column x)
+__device__ __forceinline__ void src_hadamard(const uint32_t rows[4], SrcHad &h)
+{
+    int c[16];
+#pragma unroll
+    for (int y = 0; y < 4; y++) {                    // horizontal pass on the dot-product unit
+        c[4 * y + 0] = dp4a_u8s8(rows[y], 0x01010101u, 0); c[4 * y + 1] = dp4a_u8s8(rows[y], 0xffff0101u, 0);
+        c[4 * y + 2] = dp4a_u8s8(rows[y], 0x01ffff01u, 0); c[4 * y + 3] = dp4a_u8s8(rows[y], 0xff01ff01u, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) had4(c[k], c[4 + k], c[8 + k], c[12 + k], h.T[k], h.T[4 + k], h.T[8 + k], h.T[12 + k]);
+    int a = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) a += abs(h.T[i]);
+    h.A = a;
+    h.R0 = abs(h.T[0]) + abs(h.T[1]) + abs(h.T[2]) + abs(h.T[3]);
+    h.C0 = abs(h.T[0]) + abs(h.T[4]) + abs(h.T[8]) + abs(h.T[12]);
+}
+// pred[y][x] = t[x]
+__device__ __forceinline__ uint32_t satd_pred_v(const SrcHad &h, int t0, int t1, int t2, int t3)
+{
+    int k0, k1, k2, k3;
+    had4(t0, t1, t2, t3, k0, k1, k2, k3);
+    return (uint32_t)(h.A - h.R0 + abs(h.T[0] - 4 * k0) + abs(h.T[1] - 4 * k1) + abs(h.T[2] - 4 * k2) + abs(h.T[3] - 4 * k3)) >> 1;
+}
+// pred[y][x] = l[y]
+__device__ __forceinline__ uint32_t satd_pred_h(const SrcHad &h, int l0, int l1, int l2, int l3)
+{
+    int j0, j1, j2, j3;
+    had4(l0, l1, l2, l3, j0, j1, j2, j3);
+    return (uint32_t)(h.A - h.C0 + abs(h.T[0] - 4 * j0) + abs(h.T[4] - 4 * j1) + abs(h.T[8] - 4 * j2) + abs(h.T[12] - 4 * j3)) >> 1;
+}
+// pred[y][x] = dc
+__device__ __forceinline__ uint32_t satd_pred_dc(const SrcHad &h, int dc)
+{
+    return (uint32_t)(h.A - abs(h.T[0]) + abs(h.T[0] - 16 * dc)) >> 1;
+}
+
 // SATD of a 4x4 difference block: (sum |H d H^T|) >> 1.  The last butterfly stage is folded into the absolute values with
 // |a + b| + |a - b| = 2 max(|a|, |b|): the sum is even and the final shift disappears.
 __device__ __forceinline__ uint32_t satd4x4(const int d[16])

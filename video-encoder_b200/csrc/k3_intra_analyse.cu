@@ -41,12 +41,17 @@ k3_intra_analyse_kernel(const uint8_t *__restrict__ cur_y, const uint8_t *__rest
     const uint8_t *sb = sy + (size_t)by * pitch + bx;
 
     int src[16];
+    uint32_t srow[4];
 #pragma unroll
     for (int y = 0; y < 4; y++) {
-        uint32_t w = *(const uint32_t *)(sb + (size_t)y * pitch);
+        const uint32_t w = *(const uint32_t *)(sb + (size_t)y * pitch);
+        srow[y] = w;
 #pragma unroll
         for (int x = 0; x < 4; x++) src[y * 4 + x] = (w >> (8 * x)) & 255;
     }
+    // the block's own Hadamard transform: vertical / horizontal / DC predictors are priced against it (b2_h264.cuh)
+    b2::SrcHad sh;
+    b2::src_hadamard(srow, sh);
 
     // ---- I4x4: 9 modes on this lane's block --------------------------------------------------------
     uint32_t best4 = 0xffffffffu; int mode4 = B2_I4_DC;
@@ -57,11 +62,21 @@ k3_intra_analyse_kernel(const uint8_t *__restrict__ cur_y, const uint8_t *__rest
 #pragma unroll
         for (int m = 0; m < 9; m++) {
             if (!b2::i4_mode_ok(m, ba)) continue;
-            int pred[16], d[16];
-            b2::pred4x4(m, E, ba, pred);
+            uint32_t sat;
+            if (m == B2_I4_V) sat = b2::satd_pred_v(sh, E[1], E[2], E[3], E[4]);
+            else if (m == B2_I4_H) sat = b2::satd_pred_h(sh, E[9], E[10], E[11], E[12]);
+            else if (m == B2_I4_DC) {
+                const bool hT = ba & 2, hL = ba & 1;
+                const int sum = (hT ? E[1] + E[2] + E[3] + E[4] : 0) + (hL ? E[9] + E[10] + E[11] + E[12] : 0);
+                sat = b2::satd_pred_dc(sh, (hT && hL) ? (sum + 4) >> 3 : (hT || hL) ? (sum + 2) >> 2 : 128);
+            } else {
+                int pred[16], d[16];
+                b2::pred4x4(m, E, ba, pred);
 #pragma unroll
-            for (int i = 0; i < 16; i++) d[i] = src[i] - pred[i];
-            uint32_t c = b2::satd4x4(d) + (uint32_t)(lambda * (m == B2_I4_DC ? 1 : 4));
+                for (int i = 0; i < 16; i++) d[i] = src[i] - pred[i];
+                sat = b2::satd4x4(d);
+            }
+            uint32_t c = sat + (uint32_t)(lambda * (m == B2_I4_DC ? 1 : 4));
             if (c < best4) { best4 = c; mode4 = m; }
         }
     }
@@ -175,19 +190,20 @@ k3_intra_analyse_kernel(const uint8_t *__restrict__ cur_y, const uint8_t *__rest
 #pragma unroll
         for (int m = 0; m < 4; m++) {
             const bool ok = m == B2_I16_V ? hasT : m == B2_I16_H ? hasL : m == B2_I16_DC ? true : (mba & 7) == 7;
-            int d[16];
+            uint32_t sat;
+            if (m == B2_I16_V) sat = b2::satd_pred_v(sh, t4[0], t4[1], t4[2], t4[3]);
+            else if (m == B2_I16_H) sat = b2::satd_pred_h(sh, l4[0], l4[1], l4[2], l4[3]);
+            else if (m == B2_I16_DC) sat = b2::satd_pred_dc(sh, dc);
+            else {
+                int d[16];
 #pragma unroll
-            for (int y = 0; y < 4; y++)
+                for (int y = 0; y < 4; y++)
 #pragma unroll
-                for (int x = 0; x < 4; x++) {
-                    int p;
-                    if (m == B2_I16_V) p = t4[x];
-                    else if (m == B2_I16_H) p = l4[y];
-                    else if (m == B2_I16_DC) p = dc;
-                    else p = b2_clip255((pa + pb * (bx + x - 7) + pc * (by + y - 7) + 16) >> 5);
-                    d[y * 4 + x] = src[y * 4 + x] - p;
-                }
-            const uint32_t c = (uint32_t)sum16((int)b2::satd4x4(d)) + (uint32_t)(lambda * ue_bits[m]);
+                    for (int x = 0; x < 4; x++)
+                        d[y * 4 + x] = src[y * 4 + x] - b2_clip255((pa + pb * (bx + x - 7) + pc * (by + y - 7) + 16) >> 5);
+                sat = b2::satd4x4(d);
+            }
+            const uint32_t c = (uint32_t)sum16((int)sat) + (uint32_t)(lambda * ue_bits[m]);
             if (ok && c < best16) { best16 = c; mode16 = m; }
         }
     }
@@ -202,12 +218,16 @@ k3_intra_analyse_kernel(const uint8_t *__restrict__ cur_y, const uint8_t *__rest
         for (int i = 0; i < 8; i++) { top[i] = hasT ? cp[-(ptrdiff_t)pitchc + i] : 0; left[i] = hasL ? cp[(size_t)i * pitchc - 1] : 0; }
         if (mba & 4) tl = cp[-(ptrdiff_t)pitchc - 1];
         int csrc[16];
+        uint32_t crow[4];
 #pragma unroll
         for (int y = 0; y < 4; y++) {
-            uint32_t w = *(const uint32_t *)(cp + (size_t)(cby + y) * pitchc + cbx);
+            const uint32_t w = *(const uint32_t *)(cp + (size_t)(cby + y) * pitchc + cbx);
+            crow[y] = w;
 #pragma unroll
             for (int x = 0; x < 4; x++) csrc[y * 4 + x] = (w >> (8 * x)) & 255;
         }
+        b2::SrcHad ch;
+        b2::src_hadamard(crow, ch);
         const int t0 = top[0] + top[1] + top[2] + top[3], t1 = top[4] + top[5] + top[6] + top[7];
         const int l0 = left[0] + left[1] + left[2] + left[3], l1 = left[4] + left[5] + left[6] + left[7];
         int dcv;
@@ -226,19 +246,20 @@ k3_intra_analyse_kernel(const uint8_t *__restrict__ cur_y, const uint8_t *__rest
 #pragma unroll
         for (int m = 0; m < 4; m++) {
             const bool ok = m == B2_IC_DC ? true : m == B2_IC_H ? hasL : m == B2_IC_V ? hasT : (mba & 7) == 7;
-            int d[16];
+            uint32_t sat;
+            if (m == B2_IC_DC) sat = b2::satd_pred_dc(ch, dcv);
+            else if (m == B2_IC_H) sat = b2::satd_pred_h(ch, left[cby], left[cby + 1], left[cby + 2], left[cby + 3]);
+            else if (m == B2_IC_V) sat = b2::satd_pred_v(ch, top[cbx], top[cbx + 1], top[cbx + 2], top[cbx + 3]);
+            else {
+                int d[16];
 #pragma unroll
-            for (int y = 0; y < 4; y++)
+                for (int y = 0; y < 4; y++)
 #pragma unroll
-                for (int x = 0; x < 4; x++) {
-                    int p;
-                    if (m == B2_IC_DC) p = dcv;
-                    else if (m == B2_IC_H) p = left[cby + y];
-                    else if (m == B2_IC_V) p = top[cbx + x];
-                    else p = b2_clip255((pa + pb * (cbx + x - 3) + pc * (cby + y - 3) + 16) >> 5);
-                    d[y * 4 + x] = csrc[y * 4 + x] - p;
-                }
-            const int part = b < 8 ? (int)b2::satd4x4(d) : 0;
+                    for (int x = 0; x < 4; x++)
+                        d[y * 4 + x] = csrc[y * 4 + x] - b2_clip255((pa + pb * (cbx + x - 3) + pc * (cby + y - 3) + 16) >> 5);
+                sat = b2::satd4x4(d);
+            }
+            const int part = b < 8 ? (int)sat : 0;
             const uint32_t c = (uint32_t)sum16(part) + (uint32_t)(lambda * ue_bits[m]);
             if (ok && c < bestc) { bestc = c; modec = m; }
         }
