@@ -85,6 +85,40 @@ __device__ __forceinline__ int code_chroma4x4(int lane, bool act, const int src[
     return (nnz ? 1 : 0) | (zdc ? 2 : 0);
 }
 
+// One transform chain for a whole inter macroblock with the 4x4 transform: lanes 0-15 carry the luma blocks, lanes 16-23 the
+// chroma blocks (pl = (lane-16)>>2, k = lane&3) -- same arithmetic as code_luma4x4 on the former and code_chroma4x4 on the
+// latter (the DC coefficient of a chroma lane leaves the AC quantiser and goes through the 2x2 Hadamard by shuffle), but
+// the warp walks DCT / quantiser / scaling / inverse once instead of once for luma and once more for chroma.
+// q = this lane's quantiser (luma QP or chroma QP).  ALL 32 lanes must call; `act` lanes touch memory.  Returns bit0 = AC
+// (luma: any level) non-zero, bit1 = chroma DC non-zero.
+__device__ __forceinline__ int code_mb4x4_mixed(int lane, bool act, bool is_chroma, const int src[16], const int pred[16],
+                                                const QParams &q, int qpc, int16_t *lev, b2_mbcoef_t *coef, uint8_t *rec, int rpitch)
+{
+    const int pl = (lane >> 2) & 1, k = lane & 3, base = lane & ~3;
+    int w[16], z[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = src[i] - pred[i];
+    dct4x4(w);
+    const int v0 = __shfl_sync(0xffffffffu, w[0], base + 0), v1 = __shfl_sync(0xffffffffu, w[0], base + 1);
+    const int v2 = __shfl_sync(0xffffffffu, w[0], base + 2), v3 = __shfl_sync(0xffffffffu, w[0], base + 3);
+    const int f = k == 0 ? v0 + v1 + v2 + v3 : k == 1 ? v0 - v1 + v2 - v3 : k == 2 ? v0 + v1 - v2 - v3 : v0 - v1 - v2 + v3;
+    const int zdc = is_chroma ? quant_dc(f, q) : 0;
+    int nnz = quant4x4(w, z, q, false);
+    if (is_chroma) { nnz -= z[0] != 0; z[0] = 0; }
+    const int g0 = __shfl_sync(0xffffffffu, zdc, base + 0), g1 = __shfl_sync(0xffffffffu, zdc, base + 1);
+    const int g2 = __shfl_sync(0xffffffffu, zdc, base + 2), g3 = __shfl_sync(0xffffffffu, zdc, base + 3);
+    const int fi = k == 0 ? g0 + g1 + g2 + g3 : k == 1 ? g0 - g1 + g2 - g3 : k == 2 ? g0 + g1 - g2 - g3 : g0 - g1 - g2 + g3;
+    if (act) {
+        store_levels_zigzag(lev, z);
+        if (is_chroma) coef->blk[25][4 * pl + k] = (int16_t)zdc;
+        dequant4x4(z, w, q, false);                      // all-zero levels scale and invert to a zero residual
+        if (is_chroma) w[0] = ((fi * q.ls[0]) << (qpc / 6)) >> 5;
+        idct4x4(w);
+        store_rec4x4(rec, rpitch, pred, w);
+    }
+    return (nnz ? 1 : 0) | (zdc ? 2 : 0);
+}
+
 __device__ __forceinline__ int cbp_from_mask(int mb_type, uint32_t mask)
 {
     int cbp = 0;

@@ -213,41 +213,42 @@ k5_decide_inter_kernel(FramePlanes fp, int mbw, int mbh, int nmb_total, int is_p
         for (int o = 16; o > 0; o >>= 1) { s4 += __shfl_xor_sync(0xffffffffu, s4, o); s8 += __shfl_xor_sync(0xffffffffu, s8, o); }
         use8 = ((s8 + 2) >> 2) < s4;
     }
+    // chroma blocks on lanes 16-23: source and motion-compensated prediction replace the zeros in src / pred
+    const bool actc = lane >= 16 && lane < 24;
+    const int pl = (lane >> 2) & 1, kc = lane & 3;
+    const int qpc = chroma_qp(qp);
+    const int cbx = (kc & 1) * 4, cby = (kc >> 1) * 4;
+    const size_t offc = (size_t)(B2_PADC + mby * 8 + cby) * fp.pitchc + B2_PADC + mbx * 8 + cbx;
+    if (actc) {
+        load_src4x4((pl ? fp.cur[2] : fp.cur[1]) + frame * fp.stride_c + offc, fp.pitchc, src);   // selects: no local copy of fp
+        // chroma 4x4 block k lies under luma quadrant k and moves with that quadrant's vector
+        const b2_mv_t cmv = (shape != B2_PART_16x16 && kc > 0) ? mv8[(size_t)mbi * 3 + kc - 1] : mv;
+        const uint8_t *rp = (pl ? fp.ref[2] : fp.ref[1]) + frame * fp.stride_c + offc + (ptrdiff_t)(cmv.y >> 3) * fp.pitchc + (cmv.x >> 3);
+        const int fx = cmv.x & 7, fy = cmv.y & 7;
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const uint8_t *qq = rp + (size_t)y * fp.pitchc + x;
+                pred[y * 4 + x] = ((8 - fx) * (8 - fy) * qq[0] + fx * (8 - fy) * qq[1] + (8 - fx) * fy * qq[fp.pitchc] +
+                                   fx * fy * qq[fp.pitchc + 1] + 32) >> 6;
+            }
+    }
+    uint8_t *recc = (pl ? fp.rec[2] : fp.rec[1]) + frame * fp.stride_c + offc;
     if (T8 && use8) {
         __shared__ int s_t8[K5_WARPS][256];
         flags = code_luma8x8_quad(lane, s_t8[threadIdx.x >> 5], src, pred, qp, cf->blk[lane & 15], fp.rec[0] + frame * fp.stride_y + offy,
                                   fp.pitch);
-    } else if (lane < 16) {
-        const QParams q = make_qparams(qp, false);
-        flags = code_luma4x4(src, pred, q, cf->blk[lane], fp.rec[0] + frame * fp.stride_y + offy, fp.pitch) ? 1 : 0;
-    }
-    {
-        const bool act = lane >= 16 && lane < 24;
-        const int pl = (lane >> 2) & 1, k = lane & 3;
-        const int qpc = chroma_qp(qp);
         const QParams q = make_qparams(qpc, false);
-        const int cbx = (k & 1) * 4, cby = (k >> 1) * 4;
-        const size_t off = (size_t)(B2_PADC + mby * 8 + cby) * fp.pitchc + B2_PADC + mbx * 8 + cbx;
-        if (act) {
-            load_src4x4(fp.cur[1 + pl] + frame * fp.stride_c + off, fp.pitchc, src);
-            // chroma 4x4 block k lies under luma quadrant k and moves with that quadrant's vector
-            const b2_mv_t cmv = (shape != B2_PART_16x16 && k > 0) ? mv8[(size_t)mbi * 3 + k - 1] : mv;
-            const uint8_t *rp = fp.ref[1 + pl] + frame * fp.stride_c + off + (ptrdiff_t)(cmv.y >> 3) * fp.pitchc + (cmv.x >> 3);
-            const int fx = cmv.x & 7, fy = cmv.y & 7;
-#pragma unroll
-            for (int y = 0; y < 4; y++)
-#pragma unroll
-                for (int x = 0; x < 4; x++) {
-                    const uint8_t *qq = rp + (size_t)y * fp.pitchc + x;
-                    pred[y * 4 + x] = ((8 - fx) * (8 - fy) * qq[0] + fx * (8 - fy) * qq[1] + (8 - fx) * fy * qq[fp.pitchc] +
-                                       fx * fy * qq[fp.pitchc + 1] + 32) >> 6;
-                }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; i++) src[i] = pred[i] = 0;
-        }
-        const int cfl = code_chroma4x4(lane, act, src, pred, q, qpc, cf, fp.rec[1 + pl] + frame * fp.stride_c + off, fp.pitchc);
-        if (act) flags = cfl;
+        const int cfl = code_chroma4x4(lane, actc, src, pred, q, qpc, cf, recc, fp.pitchc);
+        if (actc) flags = cfl;
+    } else {
+        // 4x4 transform: luma (lanes 0-15) and chroma (lanes 16-23) blocks share one transform chain
+        const bool is_c = lane >= 16;
+        const QParams q = make_qparams(is_c ? qpc : qp, false);
+        flags = code_mb4x4_mixed(lane, lane < 24, is_c, src, pred, q, qpc, is_c ? cf->blk[16 + 4 * pl + kc] : cf->blk[lane], cf,
+                                 is_c ? recc : fp.rec[0] + frame * fp.stride_y + offy, is_c ? fp.pitchc : fp.pitch);
+        if (lane >= 24) flags = 0;
     }
     if (lane == 24) {                                     // unused parts of the level record
         uint4 z4 = make_uint4(0, 0, 0, 0);
