@@ -337,6 +337,10 @@ extern "C" int b2_engine_h2d(b2_engine_t *e, int slot0, int nslots, int ring)
     if (e->cfg.in_ring == 1 && !any_direct) {
         const size_t off = in_off(e, slot0, 0);
         ENG_OK(cudaMemcpyAsync(e->d_in + off, e->h_in + off, e->in_stride * nslots, cudaMemcpyHostToDevice, e->st_in));
+    } else if (!any_direct) {
+        // consecutive slots are in_ring pictures apart: one strided copy instead of one call per slot
+        const size_t off = in_off(e, slot0, ring), pitch = e->in_stride * e->cfg.in_ring;
+        ENG_OK(cudaMemcpy2DAsync(e->d_in + off, pitch, e->h_in + off, pitch, e->in_bytes, nslots, cudaMemcpyHostToDevice, e->st_in));
     } else {
         for (int s = slot0; s < slot0 + nslots; s++) {
             uint8_t &direct = e->in_direct[(size_t)s * e->cfg.in_ring + ring];

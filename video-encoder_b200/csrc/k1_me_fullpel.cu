@@ -36,6 +36,9 @@ namespace {
 #ifndef B2_K1_MINCTAS
 #define B2_K1_MINCTAS 3
 #endif
+#ifndef B2_K1_SMEM_PAD
+#define B2_K1_SMEM_PAD 0    // extra dynamic shared memory per CTA (bytes): lowers K1's residency without touching its register budget,
+#endif                      // so that other stream groups' kernels can co-reside (experiment knob, scripts/k1_variants.sh)
 #ifndef B2_K1_NMB16
 #define B2_K1_NMB16 12      // +-16: the window is small (33 x 3 dy groups = 99 lane-tasks per MB), a wider strip fills the 8 warps' rounds
 #endif
@@ -299,12 +302,12 @@ int launch_k1p(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, int mbw, in
     B2_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         B2_CUDA_OK(cudaFuncSetAttribute(k1_me_fullpel_kernel<R, NT, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        K1Smem<R>::TOTAL));
+                                        K1Smem<R>::TOTAL + B2_K1_SMEM_PAD));
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     constexpr int NMB = K1Cfg<R>::NMB;
     dim3 grid((mbw + NMB - 1) / NMB, mbh, nframes);
-    k1_me_fullpel_kernel<R, NT, PART><<<grid, NT, K1Smem<R>::TOTAL, st>>>(tm_cur, tm_ref, mbw, mbh, pmv, lambda, mv_out, cost_out,
+    k1_me_fullpel_kernel<R, NT, PART><<<grid, NT, K1Smem<R>::TOTAL + B2_K1_SMEM_PAD, st>>>(tm_cur, tm_ref, mbw, mbh, pmv, lambda, mv_out, cost_out,
                                                                             mv9_out, cost9_out);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
