@@ -10,7 +10,7 @@ for F in 0 1; do
   tail -n 2 gpurun_out/ncu_launches_f$F.log; tail -n 2 gpurun_out/ncu_full_f$F.log
 done
 unset B2_ALL_FEATURES
-python bench.py > gpurun_out/bench_r1e.json 2> gpurun_out/bench_r1e.err; tail -c 300 gpurun_out/bench_r1e.json
-python bench.py --deblock 1 --transform8x8 1 --partitions 1 --no-cpu-baseline > gpurun_out/bench_r1e_allfeatures.json 2> gpurun_out/bench_r1e_allfeatures.err
-for W in c2 c4 c5; do python bench.py --workload $W --no-cpu-baseline > gpurun_out/bench_r1e_$W.json 2> gpurun_out/bench_r1e_$W.err; done
+python bench.py > gpurun_out/bench_r1z.json 2> gpurun_out/bench_r1z.err; tail -c 300 gpurun_out/bench_r1z.json
+python bench.py --deblock 1 --transform8x8 1 --partitions 1 --no-cpu-baseline > gpurun_out/bench_r1z_allfeatures.json 2> gpurun_out/bench_r1z_allfeatures.err
+for W in c2 c4 c5; do python bench.py --workload $W --no-cpu-baseline > gpurun_out/bench_r1z_$W.json 2> gpurun_out/bench_r1z_$W.err; done
 ls -la gpurun_out | tail -20
