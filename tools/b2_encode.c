@@ -101,6 +101,8 @@ int main(int argc, char **argv)
     if (is_y4m && !read_y4m_header(in, &opts)) { fprintf(stderr, "bad y4m header\n"); return 2; }
     if (opts.width <= 0 || opts.height <= 0) { fprintf(stderr, "raw input needs --size WxH\n"); return 2; }
 
+    struct timespec t_start;
+    clock_gettime(CLOCK_MONOTONIC, &t_start);
     /* enc_x264_open(), av_encode.c:378-438 */
     b2_param_t params;
     if (b2_param_default_preset(&params, opts.preset, opts.tune) != 0) {
@@ -193,8 +195,9 @@ int main(int argc, char **argv)
     clock_gettime(CLOCK_MONOTONIC, &t1);
     double dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
     if (!opts.silent)
-        printf("%ld frames in, %ld frames out, %zu bytes, %.2f s, %.1f fps (host entropy coding included)\n", frames_in, frames_out,
-               bytes_out, dt, dt > 0 ? frames_out / dt : 0.0);
+        printf("%ld frames in, %ld frames out, %zu bytes, %.2f s, %.1f fps (host entropy coding included); encoder start-up %.2f s\n",
+               frames_in, frames_out, bytes_out, dt, dt > 0 ? frames_out / dt : 0.0,
+               (double)(t0.tv_sec - t_start.tv_sec) + 1e-9 * (double)(t0.tv_nsec - t_start.tv_nsec));
     free(raw); free(filt);
     fclose(in);
     if (to_mp4) { if (b2_mp4_close(&mp4)) return 11; }                                          /* MP4Close, av_encode.c:1110-1116 */

@@ -13,6 +13,7 @@
 //   packed levels x2    [S][nmb*832] worst case, only the used prefix is copied out (cfg.pack_levels, K9)
 #include <string.h>
 #include <vector>
+#include <mutex>
 #include "b2_common.cuh"
 #include "b2_internal.h"
 #include "../../include/b2enc_engine.h"
@@ -50,6 +51,7 @@ struct b2_engine {
     size_t stride_y, stride_c, in_bytes, in_stride;
     int lambda;
     uint8_t *d_in = nullptr, *h_in = nullptr;
+    std::mutex h_in_mu;
     uint8_t *d_cur[3] = {}, *d_rec[2][3] = {};
     b2_mv_t *d_mvf = nullptr, *d_mvq = nullptr, *d_prev_mv = nullptr;
     uint32_t *d_cost_full = nullptr, *d_cost_inter = nullptr, *d_c16 = nullptr, *d_c4 = nullptr, *d_c8 = nullptr;
@@ -108,7 +110,8 @@ static int engine_alloc(b2_engine *e)
     const b2_engine_cfg_t &c = e->cfg;
     const size_t S = c.slots;
     ENG_OK(cudaMalloc(&e->d_in, e->in_stride * c.in_ring * S));
-    ENG_OK(cudaHostAlloc(&e->h_in, e->in_stride * c.in_ring * S, cudaHostAllocDefault));
+    // the pinned staging ring (in_stride * in_ring * S bytes: gigabytes for a drop-in batch) is allocated on first use
+    // (b2_engine_host_input): callers that hand over page-locked pictures through b2_engine_put_frame_direct never need it
     for (int p = 0; p < 3; p++) {
         const size_t sz = (p ? e->stride_c : e->stride_y) * S;
         ENG_OK(cudaMalloc(&e->d_cur[p], sz));
@@ -282,6 +285,18 @@ static inline Group *group_of(b2_engine *e, int slot)
 extern "C" uint8_t *b2_engine_host_input(b2_engine_t *e, int slot, int ring)
 {
     if (slot < 0 || slot >= e->cfg.slots || ring < 0 || ring >= e->cfg.in_ring) return nullptr;
+    if (!e->h_in) {
+        std::lock_guard<std::mutex> lk(e->h_in_mu);
+        if (!e->h_in) {
+            cudaSetDevice(e->cfg.device);
+            uint8_t *p = nullptr;
+            if (cudaHostAlloc(&p, e->in_stride * e->cfg.in_ring * e->cfg.slots, cudaHostAllocDefault) != cudaSuccess) {
+                fprintf(stderr, "b2enc: cannot allocate the pinned input ring\n");
+                return nullptr;
+            }
+            e->h_in = p;
+        }
+    }
     return e->h_in + in_off(e, slot, ring);
 }
 
@@ -332,8 +347,12 @@ extern "C" int b2_engine_h2d(b2_engine_t *e, int slot0, int nslots, int ring)
     // do not overwrite a ring entry that a previously issued K0 of an affected group still has to read
     for (auto &gr : e->groups)
         if (gr.slot0 < slot0 + nslots && slot0 < gr.slot0 + gr.n) ENG_OK(cudaStreamWaitEvent(e->st_in, gr.ev_k0[ring], 0));
-    bool any_direct = false;                             // entries that b2_engine_put_frame_direct already placed on the device
-    for (int s = slot0; s < slot0 + nslots; s++) any_direct |= e->in_direct[(size_t)s * e->cfg.in_ring + ring] != 0;
+    bool any_direct = false, all_direct = true;          // entries that b2_engine_put_frame_direct already placed on the device
+    for (int s = slot0; s < slot0 + nslots; s++) {
+        const bool d = e->in_direct[(size_t)s * e->cfg.in_ring + ring] != 0;
+        any_direct |= d; all_direct &= d;
+    }
+    if (!all_direct && !e->h_in) { fprintf(stderr, "b2enc: h2d: no picture was handed over for this ring position\n"); return -1; }
     if (e->cfg.in_ring == 1 && !any_direct) {
         const size_t off = in_off(e, slot0, 0);
         ENG_OK(cudaMemcpyAsync(e->d_in + off, e->h_in + off, e->in_stride * nslots, cudaMemcpyHostToDevice, e->st_in));
