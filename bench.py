@@ -35,7 +35,7 @@ sys.path.insert(0, os.path.join(ROOT, "video-encoder_b200"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 W, H, MERANGE, QP, GOP = 1920, 1080, 32, 26, 32
-# 64 GOPs x 8 stream groups: swept on the B200 (scripts/gpu_quick6.sh): 32 -> 4,645, 48 -> 4,766, 64 -> 4,876, 96/128 -> 4,879 frames/s
+# 64 GOPs x 8 stream groups: swept on the B200 (B2_BENCH_SLOTS): 32 -> 4,645, 48 -> 4,766, 64 -> 4,876, 96/128 -> 4,879 frames/s
 SLOTS, RING, STREAMS = int(os.environ.get("B2_BENCH_SLOTS", "64")), 8, int(os.environ.get("B2_BENCH_STREAMS", "8"))
 METRIC, UNIT = "1080p encode-stage frames/s", "frames/s"
 WORKLOAD = ("C3: 1920x1080 synthetic yuv420p, +-32 exhaustive SAD + qpel SATD refine, intra16x16/4x4+inter decision, "
