@@ -18,6 +18,8 @@ weak scaling); time = max over ranks.
                   a microbenchmark in the same process (MEASURED_PEAKS.json has no integer-ALU number);
                   plus the HBM fraction of K0 (conversion) against MEASURED_PEAKS.json
   cpu_baseline  : the C oracle of the same stage on the host cores (one closed GOP per thread)
+  dropin        : the same pictures through the x264-mirror call sequence (b2_encoder_encode, one picture per call,
+                  host CABAC included) -- what an unmodified av_encode.c main loop would see (N=1 only)
 
 `--impl reference` times that CPU implementation alone (the reference's own libx264/libswscale path
 cannot be built in this image: no headers, no libraries -- see DESIGN.md), all host threads.
@@ -120,6 +122,29 @@ def fill_inputs(eng, b2oracle, rank):
             buf[:n_y] = y.ravel(); buf[n_y:n_y + u.size] = u.ravel(); buf[n_y + u.size:] = v.ravel()
 
 
+def dropin_leg(b2enc, b2oracle, deblock, transform8x8, partitions, frames=768, gop_slots=8):
+    """The same pictures through the x264-mirror call sequence of the reference (b2_encoder_encode, include/b2enc.h;
+    av_encode.c:968-975, :1076-1083): one picture per call from host memory, host entropy coding (CABAC) included."""
+    src = [b2oracle.synth_frame(W, H, t, 0) for t in range(16)]
+    enc = b2enc.DropInEncoder(W, H, preset="slow" if MERANGE == 32 else "medium", tune="film", quality=QP, fps=(60, 1), annexb=0,
+                              i_keyint_max=GOP, i_gop_slots=gop_slots, b_deblocking_filter=deblock, b_transform_8x8=transform8x8,
+                              b_partitions=partitions)
+    t0 = time.perf_counter(); nout = 0; nbytes = 0
+    for t in range(frames):
+        size = enc.encode(src[t % 16], t)[0]
+        if size > 0: nout += 1; nbytes += size
+    while enc.delayed() > 0:
+        size = enc.encode(None, 0)[0]
+        if size <= 0: break
+        nout += 1; nbytes += size
+    dt = time.perf_counter() - t0
+    enc.close()
+    return {"value": round(nout / dt, 1), "unit": UNIT, "frames": nout, "gop_slots": gop_slots, "bytes_per_frame": int(nbytes / max(nout, 1)),
+            "api": "b2_param_default_preset / b2_encoder_open / b2_picture_alloc / b2_encoder_encode / b2_encoder_delayed_frames "
+                   "(x264 mirror, include/b2enc.h), driven from Python: one picture per call, pipeline fill and drain inside the timed region",
+            "note": "entropy coding (CABAC) on the host cores is part of this call sequence and is its limiter; the encode stage itself is `e2e`"}
+
+
 def cpu_encode_gop(b2oracle, np, stream, n_p, times):
     """one closed GOP on one host thread: 1 I + n_p P frames through the oracle encode stage"""
     prm = b2oracle.Params(QP, MERANGE, 1, 1)
@@ -208,6 +233,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the x264-mirror call-sequence leg (key `dropin`)")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--deblock", type=int, default=0, help="1: also run the in-loop deblocking filter K8 (row N2, outside the named path)")
     ap.add_argument("--pack-levels", type=int, default=1, help="1: levels leave the GPU packed (K9: only blocks with a non-zero level); "
@@ -371,6 +397,8 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
+        if world == 1 and not args.no_dropin and args.workload in ("c2", "c3"):
+            out["dropin"] = dropin_leg(b2enc, b2oracle, args.deblock, args.transform8x8, args.partitions)
         print(json.dumps(out))
     else:
         eng.close()
