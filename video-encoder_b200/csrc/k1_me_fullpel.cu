@@ -22,6 +22,7 @@
 //  * Winner: key = (cost << 13) | scan_index, CREDUX.MIN over the warp, atomicMin in smem.
 //    Lowest scan index wins ties by construction, exactly like the oracle's strict '<'.
 #include <stdlib.h>
+#include <atomic>
 #include "b2_common.cuh"
 
 namespace {
@@ -297,13 +298,14 @@ template <int R, int NT, bool PART>
 int launch_k1p(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, int mbw, int mbh, int nframes, const b2_mv_t *pmv, int lambda,
                b2_mv_t *mv_out, uint32_t *cost_out, b2_mv_t *mv9_out, uint32_t *cost9_out, cudaStream_t st)
 {
-    static bool attr_set[64] = {};                      // function attributes are per device: one process may drive several GPUs
+    // function attributes are per device: one process may drive several GPUs, each from its own host thread
+    static std::atomic<bool> attr_set[64];
     int dev = 0;
     B2_CUDA_OK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
         B2_CUDA_OK(cudaFuncSetAttribute(k1_me_fullpel_kernel<R, NT, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         K1Smem<R>::TOTAL + B2_K1_SMEM_PAD));
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
     }
     constexpr int NMB = K1Cfg<R>::NMB;
     dim3 grid((mbw + NMB - 1) / NMB, mbh, nframes);
@@ -323,12 +325,11 @@ int launch_k1(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, int mbw, int
 // threads per CTA: 82 (R=32) / 41 (R=16) warp-tasks per full strip should divide evenly over the warps
 int k1_threads()
 {
-    static int nt = 0;
-    if (!nt) {
+    static const int nt = [] {                          // thread-safe one-time initialisation
         const char *e = getenv("B2_K1_THREADS");
-        nt = e ? atoi(e) : 256;
-        if (nt != 192 && nt != 256 && nt != 320 && nt != 384) nt = 256;
-    }
+        const int v = e ? atoi(e) : 256;
+        return (v == 192 || v == 256 || v == 320 || v == 384) ? v : 256;
+    }();
     return nt;
 }
 

@@ -114,11 +114,13 @@ static inline void cabac_encode(cabac_t *c, int ctx, int bin)
 {
     const uint8_t st = c->state[ctx];
     const uint32_t rlps = range_lps[st >> 1][(c->range >> 6) & 3];
-    c->range -= rlps;
-    if (bin != (st & 1)) { c->low += c->range; c->range = rlps; }
+    const uint32_t rmps = c->range - rlps;
+    const uint32_t lps = 0u - (uint32_t)((bin ^ st) & 1);              /* all ones when the bin is the less probable symbol: */
+    c->low += rmps & lps;                                              /* no branch on a value that is hard to predict     */
+    uint32_t range = rmps ^ ((rmps ^ rlps) & lps);
     c->state[ctx] = cabac_next[st][bin];
-    const int sh = cabac_shift[c->range >> 3];
-    c->range <<= sh; c->low <<= sh; c->queue += sh;
+    const int sh = cabac_shift[range >> 3];
+    c->range = range << sh; c->low <<= sh; c->queue += sh;
     cabac_putbyte(c);
 }
 static inline void cabac_bypass(cabac_t *c, int bin)
@@ -167,11 +169,21 @@ static void cabac_egk(cabac_t *c, unsigned v, int k)
 
 /* ---- residual_block_cabac (7.3.5.3.3) -----------------------------------------------------------------*/
 /* l[0..maxn) in scan order.  cbf_inc < 0: coded_block_flag is not sent (cat 5).  Returns the number of non-zero levels. */
-static int cabac_residual(cabac_t *c, int cat, const int16_t *l, int maxn, int cbf_inc)
+/* any non-zero level among l[0..n)?  (most blocks of a coded 8x8 quadrant are empty: word-wise test, no per-level branch) */
+static inline int levels_any(const int16_t *l, int n)
 {
-    int last = -1, total = 0;
-    for (int i = 0; i < maxn; i++)
-        if (l[i]) { last = i; total++; }
+    uint64_t acc = 0, w;
+    int i = 0;
+    for (; i + 4 <= n; i += 4) { memcpy(&w, l + i, 8); acc |= w; }
+    for (; i < n; i++) acc |= (uint16_t)l[i];
+    return acc != 0;
+}
+
+/* always inlined: `cat` and `maxn` are constants at every call site, so the context selection folds away */
+static inline __attribute__((always_inline)) int cabac_residual(cabac_t *c, int cat, const int16_t *l, int maxn, int cbf_inc)
+{
+    int last = -1;
+    if (levels_any(l, maxn)) { last = maxn - 1; while (!l[last]) last--; }
     if (cbf_inc >= 0) {
         cabac_encode(c, cbf_base[cat] + cbf_inc, last >= 0);
         if (last < 0) return 0;
@@ -205,7 +217,7 @@ static int cabac_residual(cabac_t *c, int cat, const int16_t *l, int maxn, int c
         }
         cabac_bypass(c, l[i] < 0);
     }
-    return total;
+    return gt1 + eq1;                                                  /* every non-zero level counted exactly once */
 }
 
 /* ---- neighbour helpers ------------------------------------------------------------------------------------*/
