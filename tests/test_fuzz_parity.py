@@ -13,3 +13,11 @@ def test_random_configurations_bit_exact():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gpu_fuzz.py"), "40", "7"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "40 cases bit-exact" in r.stdout
+
+
+def test_random_dropin_streams_byte_identical():
+    """scripts/gpu_fuzz_dropin.py: the x264-mirror call sequence with random presets, profiles, tools, GOP lengths, GOP slots and
+    frame counts (partial batches) produces the oracle encoder's stream byte for byte"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gpu_fuzz_dropin.py"), "40", "9"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "40 drop-in streams byte-identical" in r.stdout
