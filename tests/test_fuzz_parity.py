@@ -21,3 +21,10 @@ def test_random_dropin_streams_byte_identical():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gpu_fuzz_dropin.py"), "40", "9"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "40 drop-in streams byte-identical" in r.stdout
+
+
+def test_random_conversions_bit_exact():
+    """scripts/gpu_fuzz_sws.py: the sws_scale mirror (K0) over all eight source formats with random sizes / strides / padding"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gpu_fuzz_sws.py"), "160", "5"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "160 conversions bit-identical" in r.stdout
