@@ -77,9 +77,11 @@ int b2_launch_extend_border(uint8_t *d_planes, int pitch, int rows, int nplanes,
     return 0;
 }
 
-// ---- K6 (frame form): borders of Y, U and V of every frame in ONE launch, visiting border words only -----------
-// Per plane the border is flattened into a 1-D list of 32-bit words: first the 2*pad full-width rows above and below
-// the picture, then the left+right pad words of the ih interior rows.  blockIdx.y = frame * 3 + plane.
+// ---- K6 (frame form): borders of Y, U and V of every frame in ONE launch, visiting border bytes only -----------
+// Per plane the border is flattened into a 1-D list of 8-byte units: first the 2*pad full-width rows above and below
+// the picture, then the left+right pad units of the ih interior rows.  blockIdx.y = frame * 3 + plane.  Pads (64 / 32), the
+// coded widths (multiples of 16 / 8) and the pitches are multiples of 8, so a unit never straddles the picture edge: it is
+// either one replicated edge pixel (left / right of the picture) or an aligned 8-byte copy of the edge row (above / below).
 __global__ void __launch_bounds__(128)
 k6_extend_border_yuv_kernel(uint8_t *y, uint8_t *u, uint8_t *v, int pitch, int pitchc, size_t stride_y, size_t stride_c,
                             int w16, int h16)
@@ -88,40 +90,42 @@ k6_extend_border_yuv_kernel(uint8_t *y, uint8_t *u, uint8_t *v, int pitch, int p
     const int pt = plane ? pitchc : pitch, pad = plane ? B2_PADC : B2_PAD;
     const int iw = plane ? w16 >> 1 : w16, ih = plane ? h16 >> 1 : h16;
     uint8_t *base = (plane == 0 ? y + frame * stride_y : (plane == 1 ? u : v) + frame * stride_c);
-    const int wpr = pt >> 2, nfull = 2 * pad * wpr;
-    const int lw = pad >> 2, rw = (pt - pad - iw) >> 2, side = lw + rw;
+    const int upr = pt >> 3, nfull = 2 * pad * upr;
+    const int lu = pad >> 3, ru = (pt - pad - iw) >> 3, side = lu + ru;
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int row, wx;
+    int row, ux;
     if (t < nfull) {
-        const int r = t / wpr;
-        wx = t - r * wpr;
+        const int r = t / upr;
+        ux = t - r * upr;
         row = r < pad ? r : ih + r;           // r in [pad,2pad) -> rows ih+pad .. ih+2pad-1
     } else {
         t -= nfull;
         const int r = t / side, k = t - r * side;
         if (r >= ih) return;
         row = pad + r;
-        wx = k < lw ? k : ((pad + iw) >> 2) + (k - lw);
+        ux = k < lu ? k : ((pad + iw) >> 3) + (k - lu);
     }
-    const int x0 = wx * 4 - pad, yy = row - pad;
+    const int x0 = ux * 8 - pad, yy = row - pad;
     const int cy = min(max(yy, 0), ih - 1);
     const uint8_t *src = base + (size_t)(cy + pad) * pt + pad;
-    uint32_t w = 0;
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-        const int cx = min(max(x0 + b, 0), iw - 1);
-        w |= (uint32_t)src[cx] << (8 * b);
+    uint2 w;
+    if (x0 < 0 || x0 >= iw) {
+        const uint32_t e = (uint32_t)src[x0 < 0 ? 0 : iw - 1] * 0x01010101u;
+        w = make_uint2(e, e);
+    } else {
+        w = *(const uint2 *)(src + x0);
     }
-    *(uint32_t *)(base + (size_t)row * pt + wx * 4) = w;
+    *(uint2 *)(base + (size_t)row * pt + ux * 8) = w;
 }
 
 int b2_launch_extend_border_yuv(uint8_t *d_y, uint8_t *d_u, uint8_t *d_v, int pitch, int rows, int pitchc, int rowsc,
                                 size_t stride_y, size_t stride_c, int w16, int h16, int nframes, cudaStream_t st)
 {
     (void)rows; (void)rowsc;
-    const int words = 2 * B2_PAD * (pitch / 4) + h16 * ((pitch - w16) / 4);      // luma is the largest plane
+    if ((pitch | pitchc) & 7) { fprintf(stderr, "b2enc: plane pitches must be multiples of 8\n"); return -1; }
+    const int units = 2 * B2_PAD * (pitch / 8) + h16 * ((pitch - w16) / 8);      // luma is the largest plane
     dim3 block(128);
-    dim3 grid((words + 127) / 128, 3 * nframes);
+    dim3 grid((units + 127) / 128, 3 * nframes);
     k6_extend_border_yuv_kernel<<<grid, block, 0, st>>>(d_y, d_u, d_v, pitch, pitchc, stride_y, stride_c, w16, h16);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
