@@ -3,7 +3,7 @@ usage: ncu_lines.py <report.ncu-rep> <kernel regex> <object file .o> [top N]"""
 import csv, subprocess, sys, re, os, tempfile, collections
 rep, kre, obj = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 30
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre] + os.environ.get("NCU_LINES_ARGS", "").split(), capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 h = next(i for i, r in enumerate(rows) if "Source" in r and "Address" in r)
 hdr = rows[h]

@@ -494,7 +494,7 @@ k7_intra_wavefront_kernel(FramePlanes fp, int mbw, int mbh, int qp, b2_mbinfo_t 
                           b2_mbcoef_t *__restrict__ coef)
 {
     constexpr int K7_WARPS = WARPS;
-    extern __shared__ int s_diag_cnt[];                 // intra MBs per anti-diagonal
+    extern __shared__ int s_diag_cnt[];                 // [ndiag] diagonal holds intra MBs | [ndiag] list of those diagonals
     __shared__ K7Warp s_warp[K7_WARPS];
     const int frame = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -503,13 +503,39 @@ k7_intra_wavefront_kernel(FramePlanes fp, int mbw, int mbh, int qp, b2_mbinfo_t 
     const int ndiag = mbw + 2 * (mbh - 1);
     b2_mbinfo_t *finfo = info + (size_t)frame * mbw * mbh;
     b2_mbcoef_t *fcoef = coef + (size_t)frame * mbw * mbh;
+    // Anti-diagonals that hold intra macroblocks, as an ascending list (identical in every CTA of the cluster).  P frames hold
+    // few: testing every diagonal in the main loop was 255 dependent shared-memory reads, most of a sparse frame's K7 time.
+    int *s_diag_list = s_diag_cnt + ndiag;
+    __shared__ int s_nlist;
     for (int i = threadIdx.x; i < ndiag; i += blockDim.x) s_diag_cnt[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < mbw * mbh; i += blockDim.x)
-        if (finfo[i].mb_type != B2_MB_P16x16) atomicAdd(&s_diag_cnt[(i % mbw) + 2 * (i / mbw)], 1);
+    const int nmb = mbw * mbh;
+    for (int i0 = threadIdx.x; i0 < nmb; i0 += 4 * blockDim.x) {            // four independent loads in flight per thread
+        uint8_t ty[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { const int i = i0 + j * blockDim.x; ty[j] = i < nmb ? finfo[i].mb_type : (uint8_t)B2_MB_P16x16; }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int i = i0 + j * blockDim.x;
+            if (ty[j] != B2_MB_P16x16) s_diag_cnt[(i % mbw) + 2 * (i / mbw)] = 1;                 // same value from every writer
+        }
+    }
     __syncthreads();
-    for (int d = 0; d < ndiag; d++) {
-        if (s_diag_cnt[d] == 0) continue;               // identical in every CTA of the cluster
+    if (warp == 0) {
+        int n = 0;
+        for (int d0 = 0; d0 < ndiag; d0 += 32) {
+            const int d = d0 + lane;
+            const bool used = d < ndiag && s_diag_cnt[d] != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, used);
+            if (used) s_diag_list[n + __popc(m & ((1u << lane) - 1u))] = d;
+            n += __popc(m);
+        }
+        if (lane == 0) s_nlist = n;
+    }
+    __syncthreads();
+    const int nlist = s_nlist;
+    for (int k = 0; k < nlist; k++) {
+        const int d = s_diag_list[k];
         const int y_lo = max(0, (d - mbw + 2) >> 1), y_hi = min(mbh - 1, d >> 1);
         const int ntask = 2 * (y_hi - y_lo + 1);        // (MB, luma|chroma)
         for (int t = gwarp; t < ntask; t += nwarps) {
@@ -544,7 +570,7 @@ int b2_launch_intra_recon(const uint8_t *const cur[3], uint8_t *const rec[3], in
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ncta, nframes, 1);
     cfg.blockDim = dim3((all_intra ? K7_WARPS_I : K7_WARPS_P) * 32, 1, 1);
-    cfg.dynamicSmemBytes = ndiag * sizeof(int);
+    cfg.dynamicSmemBytes = 2 * ndiag * sizeof(int);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
