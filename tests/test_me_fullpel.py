@@ -122,3 +122,14 @@ def test_parts_ties_lambda_and_predictors(oracle, b2, R):
     pmv["x"] = rng.integers(-140, 140, pmv.shape); pmv["y"] = rng.integers(-140, 140, pmv.shape)
     for lam in (0, 4, 91):
         _check_parts(oracle, b2, cur, ref, R, pmv, lam)
+
+
+def test_persistent_pipelined_kernel_is_bit_exact():
+    """B2_K1_PERSISTENT=1: the persistent, TMA-pipelined form of K1 (producer warps + three buffers + mbarriers) gives the same
+    vectors and costs; the switch is read once per process, so the full-pel tests are re-run in a child process"""
+    import os, subprocess, sys
+    env = dict(os.environ, B2_K1_PERSISTENT="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k", "not persistent"],
+                       capture_output=True, text=True, env=env, timeout=600, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout

@@ -294,6 +294,253 @@ k1_me_fullpel_kernel(const __grid_constant__ CUtensorMap tm_cur,
     }
 }
 
+// ---- persistent, software-pipelined form of the single-vector search ------------------------------------------------------
+// One CTA per SM walks a list of strips.  A PRODUCER warp fetches strip k+1 (TMA raw window + current tile), expands the
+// window, fills the cost tables and publishes the buffer through an mbarrier while NCW CONSUMER warps still sweep strip k out
+// of the other buffer; consumers take warp-tasks from one global sequence (task T -> strip T / TPS), so they drift across the
+// strip boundary without a CTA-wide barrier and the ALU pipe never sees a strip prologue.  Each finished task arrives on the
+// buffer's "empty" barrier; when all TPS tasks of a strip are in, the producer writes that strip's vectors and refills the
+// buffer.  Arithmetic, scan order and tie-break are those of k1_me_fullpel_kernel.
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int R> struct K1PSmem {
+    using S1 = K1Smem<R>;
+    static constexpr int NMB = S1::NMB, ND = S1::ND;
+    static constexpr int TAB = NMB * ND * 4;
+    static constexpr int OFF_RAW = 0;
+    static constexpr int BUF0 = (S1::RAW_BYTES + 16 + 127) & ~127;
+    // per buffer: cur | exp | costx | costy | best
+    static constexpr int B_CUR = 0;
+    static constexpr int B_EXP = S1::CUR_BYTES;
+    static constexpr int B_COSTX = B_EXP + S1::EXP_BYTES;
+    static constexpr int B_COSTY = B_COSTX + TAB;
+    static constexpr int B_BEST = B_COSTY + TAB;
+    static constexpr int BUF_BYTES = (B_BEST + NMB * 4 + 127) & ~127;
+    static constexpr int NBUF = 3;                           // strips in flight: one being swept, two prepared ahead
+    static constexpr int OFF_BAR = BUF0 + NBUF * BUF_BYTES;  // full[NBUF], empty[NBUF], tma
+    static constexpr int TOTAL = OFF_BAR + (2 * NBUF + 1) * 8 + 128;      // +128: manual alignment slack
+};
+
+constexpr int K1P_PW = 4;                                   // producer warps
+__device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(K1P_PW * 32) : "memory"); }
+
+template <int R, int NCW>
+__global__ void __launch_bounds__((NCW + K1P_PW) * 32, 1)
+k1_me_fullpel_persistent_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_constant__ CUtensorMap tm_ref,
+                                int mbw, int mbh, int nframes, const b2_mv_t *__restrict__ pmv, int lambda,
+                                b2_mv_t *__restrict__ mv_out, uint32_t *__restrict__ cost_out)
+{
+    using S = K1Smem<R>;
+    using P = K1PSmem<R>;
+    constexpr int K = K1Cfg<R>::K, NG = K1Cfg<R>::NG, ND = S::ND, NMB = K1Cfg<R>::NMB;
+    constexpr int TPS = (NMB * NG * ND + 31) / 32;              // warp-tasks of a full strip (ragged strips pad with no-ops)
+
+    extern __shared__ uint8_t smem_raw_[];
+    uint8_t *smem = smem_raw_ + ((128u - (smem_u32(smem_raw_) & 127u)) & 127u);
+    uint8_t *s_raw = smem + P::OFF_RAW;
+    constexpr int NBUF = P::NBUF;
+    uint64_t *s_full = (uint64_t *)(smem + P::OFF_BAR), *s_empty = s_full + NBUF, *s_tma = s_full + 2 * NBUF;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int spr = (mbw + NMB - 1) / NMB;                       // strips per macroblock row
+    const int nstrips = spr * mbh * nframes;
+    const int mine = nstrips > (int)blockIdx.x ? (nstrips - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;   // strips of this CTA
+
+    if (tid == 0) {
+        for (int b = 0; b < NBUF; b++) { mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], TPS); }
+        mbar_init(s_tma, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp >= NCW) {
+        // ================= producer warps =================
+        const int ptid = tid - NCW * 32;                         // 0 .. K1P_PW*32-1
+        __shared__ int s_pmv[2][16];                             // predictors of the strip being prepared (NMB <= 16)
+        static_assert(NMB <= 16, "strip wider than the predictor staging");
+        for (int k = 0; k < mine + NBUF; k++) {
+            const int buf = k % NBUF, use = k / NBUF;
+            uint8_t *bb = smem + P::BUF0 + buf * P::BUF_BYTES;
+            uint32_t *s_best = (uint32_t *)(bb + P::B_BEST);
+            if (k >= NBUF) {
+                // all tasks of strip k-NBUF have arrived: write its vectors, then the buffer is free
+                mbar_wait(&s_empty[buf], (uint32_t)((use - 1) & 1));
+                const int sidx = (int)blockIdx.x + (k - NBUF) * (int)gridDim.x;
+                const int frame = sidx / (spr * mbh), rem = sidx - frame * (spr * mbh);
+                const int mby = rem / spr, mb0 = (rem - mby * spr) * NMB;
+                const int nmb = min(NMB, mbw - mb0);
+                if (ptid < nmb) {
+                    const uint32_t key = s_best[ptid];
+                    const int idx = (int)(key & 8191u);
+                    const int dyi = idx / ND, dxi = idx - dyi * ND;
+                    b2_mv_t mv;
+                    mv.x = (int16_t)(dxi - R); mv.y = (int16_t)(dyi - R);
+                    const size_t o = ((size_t)frame * mbh + mby) * mbw + mb0 + ptid;
+                    mv_out[o] = mv; cost_out[o] = key >> 13;
+                }
+                producer_sync();                                 // the keys are read before the buffer is refilled
+            }
+            if (k >= mine) continue;
+            const int sidx = (int)blockIdx.x + k * (int)gridDim.x;
+            const int frame = sidx / (spr * mbh), rem = sidx - frame * (spr * mbh);
+            const int mby = rem / spr, mb0 = (rem - mby * spr) * NMB;
+            const int nmb = min(NMB, mbw - mb0);
+            uint8_t *s_cur = bb + P::B_CUR;
+            uint32_t *s_exp = (uint32_t *)(bb + P::B_EXP);
+            uint32_t *s_costx = (uint32_t *)(bb + P::B_COSTX), *s_costy = (uint32_t *)(bb + P::B_COSTY);
+            if (ptid == 0) {
+                fence_proxy_async();                             // earlier generic reads of raw / cur before the async writes
+                mbar_expect_tx(s_tma, S::RAW_BYTES + S::CUR_BYTES);
+                tma_load_3d(s_raw, &tm_ref, B2_PAD + mb0 * 16 - R, B2_PAD + mby * 16 - R, frame, s_tma);
+                tma_load_3d(s_cur, &tm_cur, B2_PAD + mb0 * 16, B2_PAD + mby * 16, frame, s_tma);
+            }
+            // while the TMA is in flight: predictors (one global load per macroblock), cost tables and best keys
+            const size_t mb_base = ((size_t)frame * mbh + mby) * mbw + mb0;
+            if (ptid < NMB) {
+                int px = 0, py = 0;
+                if (pmv != nullptr && ptid < nmb) { const b2_mv_t pp = pmv[mb_base + ptid]; px = pp.x; py = pp.y; }
+                s_pmv[0][ptid] = px; s_pmv[1][ptid] = py;
+                s_best[ptid] = 0xffffffffu;
+            }
+            producer_sync();
+            for (int i = ptid; i < NMB * ND; i += K1P_PW * 32) {
+                const int m = i / ND, d = i - m * ND;
+                s_costx[i] = ((uint32_t)(lambda * b2_mvbits(4 * (d - R) - s_pmv[0][m])) << 13) + (uint32_t)d;
+                s_costy[i] = ((uint32_t)(lambda * b2_mvbits(4 * (d - R) - s_pmv[1][m])) << 13) + (uint32_t)(d * ND);
+            }
+            mbar_wait(s_tma, (uint32_t)(k & 1));
+            {   // expand: word x of a row = pixels x..x+3 (little endian), all 4 byte alignments
+                constexpr int WPR = S::WIN_W / 4;
+                const uint32_t *raw32 = (const uint32_t *)s_raw;
+                for (int i = ptid; i < WPR * S::WIN_H; i += K1P_PW * 32) {
+                    const int r = i / WPR, j = i - r * WPR;
+                    const uint32_t lo = raw32[i], hi = raw32[i + 1];
+                    uint4 o;
+                    o.x = lo; o.y = __funnelshift_r(lo, hi, 8); o.z = __funnelshift_r(lo, hi, 16); o.w = __funnelshift_r(lo, hi, 24);
+                    *(uint4 *)(s_exp + r * S::EXP_PITCH + 4 * j) = o;
+                }
+            }
+            producer_sync();                                     // every producer thread's stores precede the release below
+            if (ptid == 0) mbar_arrive(&s_full[buf]);            // release: the buffer is complete
+        }
+        return;
+    }
+
+    // ================= consumer warps =================
+    // per-warp state is kept small (one buffer offset instead of six pointers): the sweep itself needs ~75 registers
+    int cur_k = -1, nmb = 0, bo = 0;
+    const int ntasks = mine * TPS;
+    for (int T = warp; T < ntasks; T += NCW) {
+        const int k = T / TPS, t0 = (T - k * TPS) * 32;
+        if (k != cur_k) {
+            cur_k = k;
+            mbar_wait(&s_full[k % NBUF], (uint32_t)((k / NBUF) & 1));
+            bo = P::BUF0 + (k % NBUF) * P::BUF_BYTES;
+            const int sidx = (int)blockIdx.x + k * (int)gridDim.x;
+            nmb = min(NMB, mbw - (sidx % spr) * NMB);
+        }
+        const uint8_t *s_cur = smem + bo + P::B_CUR;
+        const uint32_t *s_exp = (const uint32_t *)(smem + bo + P::B_EXP);
+        const uint32_t *s_costx = (const uint32_t *)(smem + bo + P::B_COSTX), *s_costy = (const uint32_t *)(smem + bo + P::B_COSTY);
+        uint32_t *s_best = (uint32_t *)(smem + bo + P::B_BEST);
+        const int total = nmb * NG * ND;
+        if (t0 < total) {
+            const int t = t0 + lane;
+            const bool active = t < total;
+            const int tt = active ? t : t0;               // idle lanes shadow lane 0's task
+            const int m = tt / (NG * ND);
+            const int rem = tt - m * (NG * ND);
+            const int g = rem / ND;
+            const int dxi = rem - g * ND;
+            uint32_t cur[64];
+            {
+                const uint4 *c4 = (const uint4 *)(s_cur + m * 16);
+#pragma unroll
+                for (int y = 0; y < 16; y++) {
+                    uint4 v = c4[y * (NMB * 16 / 16)];
+                    cur[y * 4 + 0] = v.x; cur[y * 4 + 1] = v.y; cur[y * 4 + 2] = v.z; cur[y * 4 + 3] = v.w;
+                }
+            }
+            uint32_t acc[K];
+#pragma unroll
+            for (int kk = 0; kk < K; kk++) acc[kk] = 0;
+            const uint32_t *wp = s_exp + (g * K) * S::EXP_PITCH + m * 16 + dxi;
+#pragma unroll
+            for (int r = 0; r < K + 15; r++) {
+                const uint32_t w0 = wp[r * S::EXP_PITCH + 0];
+                const uint32_t w1 = wp[r * S::EXP_PITCH + 4];
+                const uint32_t w2 = wp[r * S::EXP_PITCH + 8];
+                const uint32_t w3 = wp[r * S::EXP_PITCH + 12];
+#pragma unroll
+                for (int kk = 0; kk < K; kk++) {
+                    const int y = r - kk;
+                    if (y >= 0 && y < 16) {
+                        acc[kk] = vsad4_acc(w0, cur[y * 4 + 0], acc[kk]);
+                        acc[kk] = vsad4_acc(w1, cur[y * 4 + 1], acc[kk]);
+                        acc[kk] = vsad4_acc(w2, cur[y * 4 + 2], acc[kk]);
+                        acc[kk] = vsad4_acc(w3, cur[y * 4 + 3], acc[kk]);
+                    }
+                }
+            }
+            uint32_t key = 0xffffffffu;
+            if (active) {
+                const uint32_t kx = s_costx[m * ND + dxi];
+                const uint32_t *ky = s_costy + m * ND + g * K;
+#pragma unroll
+                for (int kk = 0; kk < K; kk++) key = min(key, acc[kk] * 8192u + (kx + ky[kk]));
+            }
+            const int m0 = __shfl_sync(0xffffffffu, m, 0);
+            if (__all_sync(0xffffffffu, m == m0)) {
+                const uint32_t wmin = __reduce_min_sync(0xffffffffu, key);
+                if (lane == 0) atomicMin(&s_best[m0], wmin);
+            } else if (active) {
+                atomicMin(&s_best[m], key);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[k % NBUF]);          // release: this task's reads and atomics are done
+    }
+}
+
+#ifndef B2_K1P_WARPS
+#define B2_K1P_WARPS 16      // 16 consumer warps (92 registers, no spills) + 4 producer warps; 20 consumers fit only at 80 registers
+#endif
+template <int R>
+int launch_k1_persistent(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, int mbw, int mbh, int nframes, const b2_mv_t *pmv,
+                         int lambda, b2_mv_t *mv_out, uint32_t *cost_out, cudaStream_t st)
+{
+    static std::atomic<int> nsm[64];                          // SM count per device, 0 = not looked up yet
+    int dev = 0;
+    B2_CUDA_OK(cudaGetDevice(&dev));
+    int sms = (dev >= 0 && dev < 64) ? nsm[dev].load(std::memory_order_acquire) : 0;
+    if (!sms) {
+        B2_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        B2_CUDA_OK(cudaFuncSetAttribute(k1_me_fullpel_persistent_kernel<R, B2_K1P_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        K1PSmem<R>::TOTAL));
+        if (dev >= 0 && dev < 64) nsm[dev].store(sms, std::memory_order_release);
+    }
+    constexpr int NMB = K1Cfg<R>::NMB;
+    const int nstrips = ((mbw + NMB - 1) / NMB) * mbh * nframes;
+    const int grid = nstrips < sms ? nstrips : sms;
+    k1_me_fullpel_persistent_kernel<R, B2_K1P_WARPS><<<grid, (B2_K1P_WARPS + K1P_PW) * 32, K1PSmem<R>::TOTAL, st>>>(
+        tm_cur, tm_ref, mbw, mbh, nframes, pmv, lambda, mv_out, cost_out);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// B2_K1_PERSISTENT=1 selects the persistent, pipelined kernel for the single-vector search.  Measured on the B200 (1080p, +-32,
+// 64 frames per launch): 0.889 of the VABSDIFF4 peak with 16 consumer + 4 producer warps and three buffers (0.866 with two
+// buffers and two producer warps, 0.861 with 20 consumer warps at 80 registers) against 0.888 for one strip per CTA x 3 resident
+// CTAs, and 5,333 vs 5,361 frames/s for the whole step: both forms sit at the same ceiling, so the simpler one stays the default.
+int k1_persistent()
+{
+    static const int v = [] { const char *e = getenv("B2_K1_PERSISTENT"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 template <int R, int NT, bool PART>
 int launch_k1p(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, int mbw, int mbh, int nframes, const b2_mv_t *pmv, int lambda,
                b2_mv_t *mv_out, uint32_t *cost_out, b2_mv_t *mv9_out, uint32_t *cost9_out, cudaStream_t st)
@@ -353,6 +600,7 @@ int b2_launch_me_fullpel(int R, const CUtensorMap *tm_cur, const CUtensorMap *tm
                          b2_mv_t *d_mv9, uint32_t *d_cost9, cudaStream_t st)
 {
 #define K1_DISPATCH(RR)                                                                                              \
+    if (!d_mv9 && k1_persistent()) return launch_k1_persistent<RR>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, st); \
     switch (k1_threads()) {                                                                                          \
     case 192: return launch_k1<RR, 192>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, d_mv9, d_cost9, st);       \
     case 320: return launch_k1<RR, 320>(*tm_cur, *tm_ref, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, d_mv9, d_cost9, st);       \
