@@ -195,20 +195,20 @@ k1_me_fullpel_kernel(const __grid_constant__ CUtensorMap tm_cur,
 #pragma unroll
                     for (int k = 0; k < K; k++) top[k] = accl[k] | (accr[k] << 16);
                 } else if (active) {
+                    uint32_t pend[9];                          // keys of the previous candidate: merged two at a time (VIMNMX3)
 #pragma unroll
                     for (int k = 0; k < K; k++) {
                         const uint32_t tl = top[k] & 0xffffu, tr = top[k] >> 16, bl = accl[k], br = accr[k];
                         const uint32_t kc = kx + ky[k];
                         const uint32_t st = tl + tr, sb = bl + br;
-                        best[0] = min(best[0], (st + sb) * 8192u + kc);
-                        best[1] = min(best[1], st * 8192u + kc);
-                        best[2] = min(best[2], sb * 8192u + kc);
-                        best[3] = min(best[3], (tl + bl) * 8192u + kc);
-                        best[4] = min(best[4], (tr + br) * 8192u + kc);
-                        best[5] = min(best[5], tl * 8192u + kc);
-                        best[6] = min(best[6], tr * 8192u + kc);
-                        best[7] = min(best[7], bl * 8192u + kc);
-                        best[8] = min(best[8], br * 8192u + kc);
+                        const uint32_t c[9] = {(st + sb) * 8192u + kc, st * 8192u + kc, sb * 8192u + kc, (tl + bl) * 8192u + kc,
+                                               (tr + br) * 8192u + kc, tl * 8192u + kc,  tr * 8192u + kc, bl * 8192u + kc, br * 8192u + kc};
+#pragma unroll
+                        for (int p = 0; p < 9; p++) {
+                            if (k & 1) best[p] = __vimin3_u32(best[p], pend[p], c[p]);
+                            else if (k == K - 1) best[p] = min(best[p], c[p]);
+                            else pend[p] = c[p];
+                        }
                     }
                 }
             }
@@ -261,8 +261,10 @@ k1_me_fullpel_kernel(const __grid_constant__ CUtensorMap tm_cur,
         if (active) {
             const uint32_t kx = s_costx[m * ND + dxi];
             const uint32_t *ky = s_costy + m * ND + g * K;
+            // three-input minimum (VIMNMX3): half as many ALU-pipe instructions beside the VABSDIFF4 stream
 #pragma unroll
-            for (int k = 0; k < K; k++) key = min(key, acc[k] * 8192u + (kx + ky[k]));
+            for (int k = 0; k + 1 < K; k += 2) key = __vimin3_u32(key, acc[k] * 8192u + (kx + ky[k]), acc[k + 1] * 8192u + (kx + ky[k + 1]));
+            if (K & 1) key = min(key, acc[K - 1] * 8192u + (kx + ky[K - 1]));
         }
         const int m0 = __shfl_sync(0xffffffffu, m, 0);
         if (__all_sync(0xffffffffu, m == m0)) {
@@ -490,7 +492,8 @@ k1_me_fullpel_persistent_kernel(const __grid_constant__ CUtensorMap tm_cur, cons
                 const uint32_t kx = s_costx[m * ND + dxi];
                 const uint32_t *ky = s_costy + m * ND + g * K;
 #pragma unroll
-                for (int kk = 0; kk < K; kk++) key = min(key, acc[kk] * 8192u + (kx + ky[kk]));
+                for (int kk = 0; kk + 1 < K; kk += 2) key = __vimin3_u32(key, acc[kk] * 8192u + (kx + ky[kk]), acc[kk + 1] * 8192u + (kx + ky[kk + 1]));
+                if (K & 1) key = min(key, acc[K - 1] * 8192u + (kx + ky[K - 1]));
             }
             const int m0 = __shfl_sync(0xffffffffu, m, 0);
             if (__all_sync(0xffffffffu, m == m0)) {
