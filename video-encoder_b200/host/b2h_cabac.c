@@ -188,20 +188,31 @@ static inline __attribute__((always_inline)) int cabac_residual(cabac_t *c, int 
         cabac_encode(c, cbf_base[cat] + cbf_inc, last >= 0);
         if (last < 0) return 0;
     }
-    for (int i = 0; i < maxn - 1; i++) {
+    /* significance map: positions before `last` carry (sig, last = 0), `last` itself (1, 1) unless it is the final position
+     * of the block, whose significance is inferred; the non-zero levels are collected on the way for the level pass */
+    int16_t nzv[64];
+    int nnz = 0;
+    for (int i = 0; i < last; i++) {
         const int inc_s = cat == 5 ? sig8_inc[i] : cat == 3 ? (i < 2 ? i : 2) : i;
-        const int inc_l = cat == 5 ? last8_inc[i] : cat == 3 ? (i < 2 ? i : 2) : i;
-        const int sig = l[i] != 0;
-        cabac_encode(c, sig_base[cat] + inc_s, sig);
-        if (sig) {
-            cabac_encode(c, last_base[cat] + inc_l, i == last);
-            if (i == last) break;
+        const int v = l[i];
+        cabac_encode(c, sig_base[cat] + inc_s, v != 0);
+        if (v) {
+            const int inc_l = cat == 5 ? last8_inc[i] : cat == 3 ? (i < 2 ? i : 2) : i;
+            cabac_encode(c, last_base[cat] + inc_l, 0);
+            nzv[nnz++] = (int16_t)v;
         }
     }
+    if (last < maxn - 1) {
+        const int inc_s = cat == 5 ? sig8_inc[last] : cat == 3 ? (last < 2 ? last : 2) : last;
+        const int inc_l = cat == 5 ? last8_inc[last] : cat == 3 ? (last < 2 ? last : 2) : last;
+        cabac_encode(c, sig_base[cat] + inc_s, 1);
+        cabac_encode(c, last_base[cat] + inc_l, 1);
+    }
+    nzv[nnz++] = l[last];
     int gt1 = 0, eq1 = 0;
-    for (int i = last; i >= 0; i--) {
-        if (!l[i]) continue;
-        const unsigned a = (unsigned)abs(l[i]) - 1;
+    for (int j = nnz - 1; j >= 0; j--) {                               /* levels in reverse scan order */
+        const int lv = nzv[j];
+        const unsigned a = (unsigned)abs(lv) - 1;
         const int inc0 = gt1 ? 0 : (1 + eq1 < 4 ? 1 + eq1 : 4);
         cabac_encode(c, abs_base[cat] + inc0, a > 0);
         if (a > 0) {
@@ -215,7 +226,7 @@ static inline __attribute__((always_inline)) int cabac_residual(cabac_t *c, int 
         } else {
             eq1++;
         }
-        cabac_bypass(c, l[i] < 0);
+        cabac_bypass(c, lv < 0);
     }
     return gt1 + eq1;                                                  /* every non-zero level counted exactly once */
 }
