@@ -58,7 +58,8 @@ typedef struct {
     int queue;                  /* bits pending in `low` beyond the last byte boundary, minus 18 */
     int outstanding;            /* 0xff bytes waiting for a possible carry                      */
     int overflow;
-    uint8_t state[1024];        /* (pStateIdx << 1) | valMPS */
+    uint16_t state[1024];       /* (pStateIdx << 1) | valMPS.  Not a byte type on purpose: a store through a character type may alias
+                                 * low / range / queue, which would force the compiler to reload them after every bin */
 } cabac_t;
 
 static uint8_t cabac_next[128][2];          /* state after coding bin b in state s */
@@ -88,7 +89,7 @@ static void cabac_init(cabac_t *c, bs_t *bs, int table, int qp)
     for (int i = 0; i < 1024; i++) {
         int pre = ((b2h_cabac_ctx_init[table][i][0] * qp) >> 4) + b2h_cabac_ctx_init[table][i][1];
         pre = pre < 1 ? 1 : (pre > 126 ? 126 : pre);
-        c->state[i] = pre <= 63 ? (uint8_t)((63 - pre) << 1) : (uint8_t)(((pre - 64) << 1) | 1);
+        c->state[i] = pre <= 63 ? (uint16_t)((63 - pre) << 1) : (uint16_t)(((pre - 64) << 1) | 1);
     }
 }
 /* one finished byte (plus a possible carry in bit 8) leaves the register */
@@ -112,7 +113,7 @@ static inline void cabac_putbyte(cabac_t *c)
 }
 static inline void cabac_encode(cabac_t *c, int ctx, int bin)
 {
-    const uint8_t st = c->state[ctx];
+    const unsigned st = c->state[ctx];
     const uint32_t rlps = range_lps[st >> 1][(c->range >> 6) & 3];
     const uint32_t rmps = c->range - rlps;
     const uint32_t lps = 0u - (uint32_t)((bin ^ st) & 1);              /* all ones when the bin is the less probable symbol: */
