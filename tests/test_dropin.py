@@ -121,6 +121,44 @@ def test_dropin_high_profile_with_partitions(oracle, b2, pm, amp):
     assert len(dec) == n and all(np.array_equal(d[0], r.y[:h, :w]) for d, r in zip(dec, recons))
 
 
+@pytest.mark.parametrize("fmt", ["nv12", "yuyv422", "bgr24"])
+def test_decoder_format_straight_into_the_encoder(oracle, b2, fmt):
+    """b2_param_t.i_csp_in: pictures in the decoder's own format (strided, pageable planes) go to b2_encoder_encode without an
+    sws_scale call; the conversion runs as the engine's first kernel and the stream equals the one of converted I420 pictures"""
+    w, h, n, gop, qp = 96, 64, 7, 3, 29
+    rng = np.random.default_rng(3)
+    base = smooth_seq(w, h, n, seed=21)
+    raws, conv = [], []
+    for (y, u, v) in base:
+        if fmt == "nv12":
+            uv = np.empty((h // 2, w), np.uint8); uv[:, 0::2] = u; uv[:, 1::2] = v
+            pl = [np.pad(y, ((0, 0), (0, 8))), np.pad(uv, ((0, 0), (0, 16)))]
+        elif fmt == "yuyv422":
+            p = np.empty((h, 2 * w), np.uint8); p[:, 0::2] = y
+            p[:, 1::4] = np.repeat(u, 2, axis=0); p[:, 3::4] = np.repeat(v, 2, axis=0)
+            pl = [np.pad(p, ((0, 0), (0, 12)))]
+        else:
+            p = rng.integers(0, 256, (h, 3 * w), dtype=np.uint8)
+            p[:, 0::3] = y; p[:, 1::3] = y // 2 + 40                     # correlated channels: something to predict
+            pl = [np.pad(p, ((0, 0), (0, 9)))]
+        raws.append(pl)
+        conv.append(oracle.convert_to_i420(fmt, w, h, pl))
+    enc = b2.DropInEncoder(w, h, preset="medium", tune="film", quality=qp, annexb=1, i_keyint_max=gop, i_gop_slots=2,
+                           i_csp_in=b2.FMT[fmt])
+    out = []
+    for t, pl in enumerate(raws):
+        size, nals, *_ = enc.encode_raw(pl, t)
+        if size > 0: out.append((nals,))
+    while enc.delayed() > 0:
+        size, nals, *_ = enc.encode(None, 0)
+        out.append((nals,))
+    enc.close()
+    assert len(out) == n
+    bs = to_annexb(out, length_prefixed=False)
+    ref_bs, recons, _, _ = oracle.encode_sequence(conv, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1), deblock=1, cabac=1)
+    assert bs == ref_bs
+
+
 def test_slot_count_does_not_change_the_stream(b2):
     """closed GOPs are independent: 1, 3 and 4 GOPs in flight give byte-identical output (T5)"""
     w, h, n = 128, 96, 13

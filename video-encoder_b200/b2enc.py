@@ -451,6 +451,24 @@ class DropInEncoder:
             assert off == size
         return size, nals, self.pic_out.i_pts, self.pic_out.i_dts, self.pic_out.b_keyframe
 
+    def encode_raw(self, planes, pts):
+        """hand over a picture in the encoder's i_csp_in format straight from the caller's own (pageable) planes: 2-D uint8
+        arrays whose row length is the stride, as a decoder would deliver them.  Returns like encode()."""
+        planes = [np.ascontiguousarray(p, np.uint8) for p in planes]
+        pic = Picture()
+        pic.i_type = 0; pic.i_pts = pts
+        pic.img.i_csp = 0; pic.img.i_plane = len(planes)
+        for i, a in enumerate(planes):
+            pic.img.plane[i] = a.ctypes.data; pic.img.i_stride[i] = a.shape[1]
+        nal = C.POINTER(Nal)(); n = C.c_int(0)
+        size = self.L.b2_encoder_encode(self.h_enc, C.byref(nal), C.byref(n), C.byref(pic), C.byref(self.pic_out))
+        nals = []
+        if size > 0:
+            base = nal[0].p_payload; whole = C.string_at(base, size); off = 0
+            for i in range(n.value):
+                nals.append((nal[i].i_type, whole[off:off + nal[i].i_payload])); off += nal[i].i_payload
+        return size, nals, self.pic_out.i_pts, self.pic_out.i_dts, self.pic_out.b_keyframe
+
     def delayed(self):
         return self.L.b2_encoder_delayed_frames(self.h_enc)
 
