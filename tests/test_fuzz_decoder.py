@@ -10,3 +10,11 @@ def test_random_streams_decode_to_the_oracle_reconstruction():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "cpu_fuzz_entropy.py"), "120", "11"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "120 cases decoder-exact" in r.stdout
+
+
+def test_host_slice_writers_under_sanitizers():
+    """scripts/host_entropy_asan.py: random frames through both slice writers, dense and packed levels, built with
+    -fsanitize=address,undefined: identical output, overflow reported, no finding"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "host_entropy_asan.py"), "40", "13"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "no sanitizer finding" in r.stdout
