@@ -41,10 +41,14 @@ static inline void b2h_levels_mb(b2h_levels_t *lv, const b2_mbinfo_t *m, int mi,
         for (int b = 0; b < B2_COEF_BLOCKS; b++) blk[b] = lv->dense[mi].blk[b];
         return;
     }
-    const uint32_t pm = b2_coef_present(m);
-    for (int b = 0; b < B2_COEF_BLOCKS; b++) {
-        if (((pm >> b) & 1u) && lv->pos + 32 <= lv->size) { blk[b] = (const int16_t *)(lv->packed + lv->pos); lv->pos += 32; }
-        else blk[b] = b2h_zero_levels;
+    uint32_t pm = b2_coef_present(m);
+    for (int b = 0; b < B2_COEF_BLOCKS; b++) blk[b] = b2h_zero_levels;
+    while (pm) {                                          /* the few present blocks, in block order = stream order */
+        const int b = __builtin_ctz(pm);
+        pm &= pm - 1;
+        if (lv->pos + 32 > lv->size) break;               /* truncated stream: the remaining blocks read as zero */
+        blk[b] = (const int16_t *)(lv->packed + lv->pos);
+        lv->pos += 32;
     }
 }
 
