@@ -389,6 +389,7 @@ def main():
                          "how": "launch covering all %d frames timed alone on one stream (8 launches, CUDA events) right after the timed region; inside the timed region %d stream groups overlap, so per-kernel times there are not separable" % (SLOTS, NG),
                          "share_of_step": round(k1_ms / total_k, 3) if total_k else None,
                          "share_note": "K1 time / sum of all kernel times of a P step, each timed alone on one stream",
+                         "executed_note": "no pruning: the ncu capture in profiles/ counts 275.8 M VABSDIFF4 warp-instructions for a 4-frame 1080p +-32 launch = the algorithmic 4 x 8160 x 4225 x 64 / 32",
                          "traffic": 18.5e6 * SLOTS / 4, "traffic_note": "dram bytes of one launch from the ncu --set full capture in profiles/ (4-frame launch: 18.5 MB), scaled to %d frames" % SLOTS,
                          "hbm": {"kernel": "k0_convert_kernel", "bound": "hbm", "achieved": round(k0_gbs, 1), "peak": peaks.get("hbm_gbs"),
                                  "unit": "GB/s", "frac": round(k0_gbs / peaks.get("hbm_gbs", 6650.0), 4), "peak_source": peak_src,
