@@ -32,7 +32,7 @@ static void filter_line(uint8_t *pix, int step, int bs, int qp, int chroma)
     if (chroma) {
         if (bs < 4) {
             const int tc = tc0_tab[qp][bs - 1] + 1;
-            const int d = clip3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+            const int d = clip3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
             pix[-step] = (uint8_t)clip255(p0 + d); pix[0] = (uint8_t)clip255(q0 - d);
         } else {
             pix[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
@@ -45,7 +45,7 @@ static void filter_line(uint8_t *pix, int step, int bs, int qp, int chroma)
     if (bs < 4) {
         const int tc0 = tc0_tab[qp][bs - 1];
         const int tc = tc0 + (ap < beta) + (aq < beta);
-        const int d = clip3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+        const int d = clip3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
         pix[-step] = (uint8_t)clip255(p0 + d); pix[0] = (uint8_t)clip255(q0 - d);
         if (ap < beta) pix[-2 * step] = (uint8_t)(p1 + clip3(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - (p1 << 1)) >> 1));
         if (aq < beta) pix[step] = (uint8_t)(q1 + clip3(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - (q1 << 1)) >> 1));

@@ -139,7 +139,7 @@ static void dequant4x4_32(const int16_t z[16], int qp, int skip_dc, int32_t w[16
     for (int i = 0; i < 16; i++) {
         if (i == 0 && skip_dc) continue;               /* caller supplies w[0] */
         int ls = 16 * v[pos_class(i)];
-        if (s >= 4) w[i] = (z[i] * ls) << (s - 4);
+        if (s >= 4) w[i] = (z[i] * ls) * (1 << (s - 4));        /* the standard's "<<" on a possibly negative value */
         else        w[i] = (z[i] * ls + (1 << (3 - s))) >> (4 - s);
     }
 }
@@ -202,7 +202,7 @@ uint32_t b2o_code_luma16x16(const uint8_t *src, int sp, uint8_t *recon, int rp, 
     b2o_hadamard4x4_inv(dcq, dcdq);
     int ls = 16 * dequant_v[qp % 6][0], s = qp / 6;
     for (int i = 0; i < 16; i++)
-        dcdq[i] = s >= 6 ? (dcdq[i] * ls) << (s - 6) : (dcdq[i] * ls + (1 << (5 - s))) >> (6 - s);
+        dcdq[i] = s >= 6 ? (dcdq[i] * ls) * (1 << (s - 6)) : (dcdq[i] * ls + (1 << (5 - s))) >> (6 - s);
     int luma_ac = (mask & 0xffffu) != 0;
     for (int b = 0; b < 16; b++) {
         int32_t dq[16];
@@ -243,7 +243,7 @@ uint32_t b2o_code_chroma8x8(const uint8_t *src, int sp, uint8_t *recon, int rp, 
     f[2] = zdc[0] + zdc[1] - zdc[2] - zdc[3];
     f[3] = zdc[0] - zdc[1] - zdc[2] + zdc[3];
     int ls = 16 * dequant_v[qpc % 6][0];
-    for (int i = 0; i < 4; i++) f[i] = ((f[i] * ls) << (qpc / 6)) >> 5;
+    for (int i = 0; i < 4; i++) f[i] = ((f[i] * ls) * (1 << (qpc / 6))) >> 5;
     int have_ac = (mask >> (16 + 4 * plane) & 15u) != 0;
     for (int b = 0; b < 4; b++) {
         int32_t dq[16];

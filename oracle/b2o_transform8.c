@@ -112,7 +112,7 @@ void b2o_dequant8x8(const int16_t z[64], int qp, int32_t w[64])
     const int s = qp / 6;
     for (int i = 0; i < 64; i++) {
         const int ls = 16 * dequant8_v[qp % 6][pos_class8(i)];
-        w[i] = s >= 6 ? (z[i] * ls) << (s - 6) : (z[i] * ls + (1 << (5 - s))) >> (6 - s);
+        w[i] = s >= 6 ? (z[i] * ls) * (1 << (s - 6)) : (z[i] * ls + (1 << (5 - s))) >> (6 - s);
     }
 }
 

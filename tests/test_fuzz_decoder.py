@@ -18,3 +18,10 @@ def test_host_slice_writers_under_sanitizers():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "host_entropy_asan.py"), "40", "13"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "no sanitizer finding" in r.stdout
+
+
+def test_oracle_under_sanitizers():
+    """scripts/oracle_asan.sh: the C oracle's encode stage (all tool sets, random sizes and content) built with
+    -fsanitize=address,undefined -- no out-of-bounds access, no undefined arithmetic"""
+    r = subprocess.run(["bash", os.path.join(ROOT, "scripts", "oracle_asan.sh"), "24", "7"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "runtime error" not in r.stderr and "no sanitizer finding" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]

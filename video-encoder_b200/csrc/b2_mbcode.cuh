@@ -78,7 +78,7 @@ __device__ __forceinline__ int code_chroma4x4(int lane, bool act, const int src[
         store_levels_zigzag(coef->blk[16 + 4 * pl + k], z);
         coef->blk[25][4 * pl + k] = (int16_t)zdc;
         dequant4x4(z, w, q, true);
-        w[0] = ((fi * q.ls[0]) << (qpc / 6)) >> 5;
+        w[0] = ((fi * q.ls[0]) * (1 << (qpc / 6))) >> 5;
         idct4x4(w);
         store_rec4x4(rec, rpitch, pred, w);
     }
@@ -112,7 +112,7 @@ __device__ __forceinline__ int code_mb4x4_mixed(int lane, bool act, bool is_chro
         store_levels_zigzag(lev, z);
         if (is_chroma) coef->blk[25][4 * pl + k] = (int16_t)zdc;
         dequant4x4(z, w, q, false);                      // all-zero levels scale and invert to a zero residual
-        if (is_chroma) w[0] = ((fi * q.ls[0]) << (qpc / 6)) >> 5;
+        if (is_chroma) w[0] = ((fi * q.ls[0]) * (1 << (qpc / 6))) >> 5;
         idct4x4(w);
         store_rec4x4(rec, rpitch, pred, w);
     }

@@ -100,7 +100,7 @@ __device__ __forceinline__ int code_luma8x8_quad(int lane, int *sm, const int sr
 #pragma unroll
             for (int x = 0; x < 8; x++) {
                 const int ls = 16 * c_dequant8_v[rem][c_cls8[(y & 3) * 4 + (x & 3)]];
-                a[x] = sh >= 6 ? (z[j][x] * ls) << (sh - 6) : (z[j][x] * ls + (1 << (5 - sh))) >> (6 - sh);
+                a[x] = sh >= 6 ? (z[j][x] * ls) * (1 << (sh - 6)) : (z[j][x] * ls + (1 << (5 - sh))) >> (6 - sh);
             }
             idct8_1d(a, o);
 #pragma unroll

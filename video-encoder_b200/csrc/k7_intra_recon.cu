@@ -221,7 +221,7 @@ __device__ void k7_luma_task(int lane, K7Warp &ws, const FramePlanes &fp, int fr
             const int zs = __shfl_sync(0xffffffffu, zdc, s);
             acc2 += h4_sign(v, s >> 2) * h4_sign(u, s & 3) * zs;
         }
-        const int dq_r = q.s >= 6 ? (acc2 * q.ls[0]) << (q.s - 6) : (acc2 * q.ls[0] + (1 << (5 - q.s))) >> (6 - q.s);
+        const int dq_r = q.s >= 6 ? (acc2 * q.ls[0]) * (1 << (q.s - 6)) : (acc2 * q.ls[0] + (1 << (5 - q.s))) >> (6 - q.s);
         const int my_dc = __shfl_sync(0xffffffffu, dq_r, blk_y(l16) * 4 + blk_x(l16));
         const bool luma_dc = __ballot_sync(0xffffffffu, lane < 16 && zdc != 0) != 0;
         int nnz = 0;
@@ -335,7 +335,7 @@ __device__ void k7_luma_task(int lane, K7Warp &ws, const FramePlanes &fp, int fr
 #pragma unroll
                     for (int x = 0; x < 8; x++) {
                         const int ls = 16 * c_dequant8_v[rem][c_cls8[(lane & 3) * 4 + (x & 3)]];
-                        a[x] = sh >= 6 ? (z[x] * ls) << (sh - 6) : (z[x] * ls + (1 << (5 - sh))) >> (6 - sh);
+                        a[x] = sh >= 6 ? (z[x] * ls) * (1 << (sh - 6)) : (z[x] * ls + (1 << (5 - sh))) >> (6 - sh);
                     }
                     idct8_1d(a, o);
 #pragma unroll

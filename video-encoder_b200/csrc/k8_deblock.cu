@@ -61,7 +61,7 @@ __device__ __forceinline__ void filter_line(uint8_t *pix, int step, int bs, cons
     if (chroma) {
         if (bs < 4) {
             const int tc = fc.tc0[bs - 1] + 1;
-            const int d = clip3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+            const int d = clip3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
             pix[-step] = (uint8_t)b2_clip255(p0 + d); pix[0] = (uint8_t)b2_clip255(q0 - d);
         } else {
             pix[-step] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);
@@ -74,7 +74,7 @@ __device__ __forceinline__ void filter_line(uint8_t *pix, int step, int bs, cons
     if (bs < 4) {
         const int tc0 = fc.tc0[bs - 1];
         const int tc = tc0 + (ap < fc.beta) + (aq < fc.beta);
-        const int d = clip3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+        const int d = clip3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
         pix[-step] = (uint8_t)b2_clip255(p0 + d); pix[0] = (uint8_t)b2_clip255(q0 - d);
         if (ap < fc.beta) pix[-2 * step] = (uint8_t)(p1 + clip3(-tc0, tc0, (p2 + ((p0 + q0 + 1) >> 1) - (p1 << 1)) >> 1));
         if (aq < fc.beta) pix[step] = (uint8_t)(q1 + clip3(-tc0, tc0, (q2 + ((p0 + q0 + 1) >> 1) - (q1 << 1)) >> 1));
