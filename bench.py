@@ -122,7 +122,7 @@ def fill_inputs(eng, b2oracle, rank):
             buf[:n_y] = y.ravel(); buf[n_y:n_y + u.size] = u.ravel(); buf[n_y + u.size:] = v.ravel()
 
 
-def dropin_leg(b2enc, b2oracle, deblock, transform8x8, partitions, frames=768, gop_slots=8):
+def dropin_leg(b2enc, b2oracle, deblock, transform8x8, partitions, frames=1024, gop_slots=16):
     """The same pictures through the x264-mirror call sequence of the reference (b2_encoder_encode, include/b2enc.h;
     av_encode.c:968-975, :1076-1083): one picture per call from host memory, host entropy coding (CABAC) included."""
     src = [b2oracle.synth_frame(W, H, t, 0) for t in range(16)]
