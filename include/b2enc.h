@@ -34,14 +34,20 @@ extern "C" {
 
 /* ---- libswscale subset ------------------------------------------------------------------------------*/
 #define B2_SWS_FAST_BILINEAR 1
+#define B2_SWS_HOST_OUTPUT 0x10000000    /* extension flag for b2_sws_getContext: always write the destination planes (see b2_sws_scale) */
 typedef struct b2_sws_context b2_sws_context_t;
 /* same-size conversion only (the reference never scales: av_encode.c:427-430); srcFormat = B2_FMT_*,
  * dstFormat must be B2_FMT_YUV420P.  NULL on error. */
 b2_sws_context_t *b2_sws_getContext(int srcW, int srcH, int srcFormat, int dstW, int dstH, int dstFormat, int flags,
                                     void *srcFilter, void *dstFilter, const double *param);
-/* whole frame per call (srcSliceY = 0, srcSliceH = srcH, as at av_encode.c:545-547); synchronous: src has
- * been read and dst written when it returns.  The conversion itself runs on the GPU (kernel K0).
- * Returns the height of the output slice, < 0 on error. */
+/* whole frame per call (srcSliceY = 0, srcSliceH = srcH, as at av_encode.c:545-547); src has been read when it returns
+ * (the reference frees it right away, :550).  The conversion itself runs on the GPU (kernel K0).
+ * When dst are the planes of a b2_picture_alloc picture -- the reference's only use: x264.pic_in, :415, :545-547 -- the
+ * conversion is DEFERRED into the b2_encoder_encode call that picture is handed to next (:970): the source is staged in
+ * page-locked memory belonging to the picture, uploaded once, and K0 writes straight into the encoder's device planes.
+ * The picture's host planes are then only valid for yuv420p sources (where the staging is the picture itself); pass
+ * B2_SWS_HOST_OUTPUT to b2_sws_getContext, or any other destination memory, to get sws_scale's host-out behaviour
+ * (host -> GPU -> host round trip).  Returns the height of the output slice, < 0 on error. */
 int b2_sws_scale(b2_sws_context_t *c, const uint8_t *const src[], const int srcStride[], int srcSliceY, int srcSliceH,
                  uint8_t *const dst[], const int dstStride[]);
 void b2_sws_freeContext(b2_sws_context_t *c);
@@ -64,7 +70,7 @@ typedef struct {
     struct { int i_rc_method; float f_rf_constant; int i_qp_constant; } rc;
     /* extensions (not in the reference; defaults chosen by b2_param_default_preset) */
     int i_keyint_max;                   /* closed-GOP length                                    */
-    int i_gop_slots;                    /* closed GOPs encoded in lock-step on the GPU (default 16; 1 = zero delay) */
+    int i_gop_slots;                    /* closed GOPs in flight per GPU, each on its own CUDA stream (default 16; 1 = zero delay) */
     int i_merange;                      /* 16 or 32                                             */
     int b_subpel;                       /* half + quarter-pel refinement                        */
     int b_intra_in_p;
@@ -78,6 +84,11 @@ typedef struct {
     int b_partitions;                   /* inter partitions 16x8 / 8x16 / 8x8 (x264: analyse.inter & X264_ANALYSE_PSUB16x16).
                                            1: refined per 8x8 quadrant within +-3/4 pel of the 16x16 vector; 2: every part gets
                                            its own exhaustive full-pel search (K1 partition variant); default 0              */
+    int i_deblocking_filter_alphac0;    /* loop-filter offsets, x264 fields of the same names ([-6,6]; tune film sets -1:-1, */
+    int i_deblocking_filter_beta;       /* as x264 does): slice_alpha_c0_offset_div2 / slice_beta_offset_div2               */
+    int i_devices;                      /* GPUs one stream is spread over by closed GOP: GOP k is encoded on device
+                                           i_device + k % i_devices; the output is byte-identical for every value.
+                                           0 (default) = environment variable B2ENC_DEVICES, else 1                          */
 } b2_param_t;
 
 typedef struct {

@@ -39,6 +39,7 @@ typedef struct {
                        /* within +-3/4 pel of the 16x16 vector, 2 = own exhaustive full-pel search per part      */
     int pack_levels;   /* 1: levels leave the GPU packed (only blocks with a non-zero level, K9):   */
                        /* b2_engine_packed* replace b2_engine_coef*, which then return NULL         */
+    int deblock_alpha, deblock_beta;   /* loop-filter offsets (slice_alpha_c0_offset_div2 / slice_beta_offset_div2, -6..6) */
 } b2_engine_cfg_t;
 
 b2_engine_t *b2_engine_create(const b2_engine_cfg_t *cfg);      /* NULL on error */
@@ -56,6 +57,13 @@ int b2_engine_put_frame(b2_engine_t *e, int slot, int ring, const uint8_t *const
  * source has been read; the following b2_engine_h2d skips that entry.  Returns 0, 1 = source not page-locked (fall back to
  * b2_engine_put_frame), -1 = error.  May be called from another host thread than h2d/encode/d2h for a different ring position. */
 int b2_engine_put_frame_direct(b2_engine_t *e, int slot, int ring, const uint8_t *const src[4], const int stride[4]);
+/* GOP-streaming hand-over (used by b2_encoder_encode): one picture from ANY host memory into (slot, ring); returns as soon as
+ * the source has been read (page-locked sources: DMA + wait; pageable ones: copy into a page-locked bounce buffer whose upload
+ * completes behind the caller's back).  No b2_engine_h2d follows -- the next encode of the slot's group waits for the upload.
+ * May run on another host thread than encode_group / d2h_group for ring entries that are not being encoded. */
+int b2_engine_put_picture(b2_engine_t *e, int slot, int ring, const uint8_t *const src[4], const int stride[4]);
+/* change cfg.in_fmt of an idle engine (the ring is re-allocated when the picture size differs) */
+int b2_engine_set_input_format(b2_engine_t *e, int fmt);
 /* async pinned-host -> device copy of ring position `ring` for slots [slot0, slot0+nslots) */
 int b2_engine_h2d(b2_engine_t *e, int slot0, int nslots, int ring);
 /* async: encode ring position `ring` of slots [0,nslots) as one frame each (B2_FRAME_I / B2_FRAME_P) */
@@ -66,6 +74,14 @@ int b2_engine_groups(const b2_engine_t *e);
 int b2_engine_group_range(const b2_engine_t *e, int group, int *slot0, int *nslots);
 int b2_engine_encode_group(b2_engine_t *e, int group, int frame_type, int ring);
 int b2_engine_d2h_group(b2_engine_t *e, int group);
+/* group-level hand-off: result set (0/1) the group's last b2_engine_d2h_group copies into; whether that copy has landed
+ * (1 yes, 0 not yet, <0 error) / wait for it (the thread sleeps); host views of a result set.  A set stays valid until the
+ * group's next but one b2_engine_d2h_group. */
+int b2_engine_group_result_set(const b2_engine_t *e, int group);
+int b2_engine_group_done(b2_engine_t *e, int group, int set);
+int b2_engine_group_wait(b2_engine_t *e, int group, int set);
+const b2_mbinfo_t *b2_engine_info_set(b2_engine_t *e, int set, int slot);
+const uint8_t *b2_engine_packed_set(b2_engine_t *e, int set, int slot, size_t *bytes);
 /* async device -> pinned-host copy of the last encode's per-MB results for slots [0,nslots) */
 int b2_engine_d2h(b2_engine_t *e, int nslots);
 int b2_engine_sync(b2_engine_t *e);

@@ -9,6 +9,7 @@
  */
 #ifndef B2ENC_KERNELS_H
 #define B2ENC_KERNELS_H
+#include <stddef.h>
 #include "b2enc_types.h"
 #ifdef __cplusplus
 extern "C" {
@@ -20,6 +21,9 @@ int b2_device_count(void);
 /* PCI bus id ("0000:1b:00.0") of a CUDA device, so that a host process can pin itself to the GPU's NUMA node before
  * allocating the pinned staging buffers */
 int b2_device_pci_bus_id(int device, char *out, int len);
+
+/* free / total memory of a CUDA device in bytes */
+int b2_device_mem_info(int device, size_t *free_bytes, size_t *total_bytes);
 
 /* K1: exhaustive full-pel SAD search (replaces the full-pel ME inside x264_encoder_encode,
  * av_encode.c:970).  cur_y/ref_y: [nframes][h][w] unpadded luma, w and h multiples of 16.

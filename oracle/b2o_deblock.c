@@ -1,9 +1,10 @@
 /* b2o_deblock.c -- ORACLE (test infrastructure only; see b2o.h).
  * In-loop deblocking filter, ITU-T H.264 8.7 (normative; pinned by the libavcodec decoder drift test), restricted to
  * what the stage produces: frame macroblocks, 4x4 or 8x8 transform (8x8: only the 8-pel edges are transform edges),
- * one reference frame, constant QP, filter offsets 0.
- * In the reference this is part of x264_encoder_encode (av_encode.c:970; x264 enables it by default, "film" tunes -1:-1
- * which is outside the named path).  SURVEY.md 8f row N2. */
+ * one reference frame, constant QP, slice-level filter offsets (8.7.2.2: indexA = qPav + 2*slice_alpha_c0_offset_div2,
+ * indexB = qPav + 2*slice_beta_offset_div2, both clipped to 0..51).
+ * In the reference this is part of x264_encoder_encode (av_encode.c:970; x264 enables it by default and the reference's
+ * default tune "film" (av_encode.c:103) sets the offsets to -1:-1).  SURVEY.md 8f row N2. */
 #include <stdlib.h>
 #include "b2o.h"
 
@@ -23,15 +24,15 @@ static inline int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? 
 static inline int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 
 /* filter one line of samples across an edge; pix -> q0, `step` = distance between successive samples across the edge */
-static void filter_line(uint8_t *pix, int step, int bs, int qp, int chroma)
+static void filter_line(uint8_t *pix, int step, int bs, int ia, int ib, int chroma)
 {
     if (!bs) return;
-    const int alpha = alpha_tab[qp], beta = beta_tab[qp];
+    const int alpha = alpha_tab[ia], beta = beta_tab[ib];
     const int p0 = pix[-step], p1 = pix[-2 * step], q0 = pix[0], q1 = pix[step];
     if (!(abs(p0 - q0) < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta)) return;
     if (chroma) {
         if (bs < 4) {
-            const int tc = tc0_tab[qp][bs - 1] + 1;
+            const int tc = tc0_tab[ia][bs - 1] + 1;
             const int d = clip3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
             pix[-step] = (uint8_t)clip255(p0 + d); pix[0] = (uint8_t)clip255(q0 - d);
         } else {
@@ -43,7 +44,7 @@ static void filter_line(uint8_t *pix, int step, int bs, int qp, int chroma)
     const int p2 = pix[-3 * step], q2 = pix[2 * step];
     const int ap = abs(p2 - p0), aq = abs(q2 - q0);
     if (bs < 4) {
-        const int tc0 = tc0_tab[qp][bs - 1];
+        const int tc0 = tc0_tab[ia][bs - 1];
         const int tc = tc0 + (ap < beta) + (aq < beta);
         const int d = clip3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
         pix[-step] = (uint8_t)clip255(p0 + d); pix[0] = (uint8_t)clip255(q0 - d);
@@ -90,9 +91,11 @@ static int bs_of(const b2_mbinfo_t *mp, int pbx, int pby, const b2_mbinfo_t *mq,
     return 0;
 }
 
-void b2o_deblock_frame(b2o_frame_t *f, const b2_mbinfo_t *info, int qp)
+void b2o_deblock_frame(b2o_frame_t *f, const b2_mbinfo_t *info, int qp, int alpha_off, int beta_off)
 {
     const int qpc = b2o_chroma_qp(qp);
+    const int ia = clip3(0, 51, qp + 2 * alpha_off), ib = clip3(0, 51, qp + 2 * beta_off);
+    const int iac = clip3(0, 51, qpc + 2 * alpha_off), ibc = clip3(0, 51, qpc + 2 * beta_off);
     for (int mby = 0; mby < f->mbh; mby++)
         for (int mbx = 0; mbx < f->mbw; mbx++) {
             const b2_mbinfo_t *mq = &info[mby * f->mbw + mbx];
@@ -104,20 +107,20 @@ void b2o_deblock_frame(b2o_frame_t *f, const b2_mbinfo_t *info, int qp)
                 if ((e == 0 && mbx == 0) || ((e & 1) && mq->transform8x8)) { for (int k = 0; k < 4; k++) bs[e][k] = 0; continue; }
                 const b2_mbinfo_t *mp = e == 0 ? mq - 1 : mq;
                 for (int k = 0; k < 4; k++) bs[e][k] = bs_of(mp, e == 0 ? 3 : e - 1, k, mq, e, k, e == 0);
-                for (int r = 0; r < 16; r++) filter_line(y + (size_t)r * f->pitch + 4 * e, 1, bs[e][r >> 2], qp, 0);
+                for (int r = 0; r < 16; r++) filter_line(y + (size_t)r * f->pitch + 4 * e, 1, bs[e][r >> 2], ia, ib, 0);
             }
             for (int p = 0; p < 2; p++)
                 for (int e = 0; e < 2; e++)
-                    for (int r = 0; r < 8; r++) filter_line(c[p] + (size_t)r * f->pitchc + 4 * e, 1, bs[2 * e][r >> 1], qpc, 1);
+                    for (int r = 0; r < 8; r++) filter_line(c[p] + (size_t)r * f->pitchc + 4 * e, 1, bs[2 * e][r >> 1], iac, ibc, 1);
             /* horizontal edges (top to bottom) */
             for (int e = 0; e < 4; e++) {
                 if ((e == 0 && mby == 0) || ((e & 1) && mq->transform8x8)) { for (int k = 0; k < 4; k++) bs[e][k] = 0; continue; }
                 const b2_mbinfo_t *mp = e == 0 ? mq - f->mbw : mq;
                 for (int k = 0; k < 4; k++) bs[e][k] = bs_of(mp, k, e == 0 ? 3 : e - 1, mq, k, e, e == 0);
-                for (int x = 0; x < 16; x++) filter_line(y + (size_t)(4 * e) * f->pitch + x, f->pitch, bs[e][x >> 2], qp, 0);
+                for (int x = 0; x < 16; x++) filter_line(y + (size_t)(4 * e) * f->pitch + x, f->pitch, bs[e][x >> 2], ia, ib, 0);
             }
             for (int p = 0; p < 2; p++)
                 for (int e = 0; e < 2; e++)
-                    for (int x = 0; x < 8; x++) filter_line(c[p] + (size_t)(4 * e) * f->pitchc + x, f->pitchc, bs[2 * e][x >> 1], qpc, 1);
+                    for (int x = 0; x < 8; x++) filter_line(c[p] + (size_t)(4 * e) * f->pitchc + x, f->pitchc, bs[2 * e][x >> 1], iac, ibc, 1);
         }
 }

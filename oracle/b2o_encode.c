@@ -185,7 +185,7 @@ void b2o_encode_frame(const b2o_params_t *prm, int frame_type,
             if (info[i].mb_type == B2_MB_P16x16) b2o_recon_inter_mb(prm, cur, ref, recon, mbx, mby, &info[i], &coef[i]);
             else b2o_recon_intra_mb(prm, cur, recon, mbx, mby, &info[i], &coef[i]);
         }
-    if (prm->deblock) b2o_deblock_frame(recon, info, prm->qp);
+    if (prm->deblock) b2o_deblock_frame(recon, info, prm->qp, prm->deblock_alpha, prm->deblock_beta);
     b2o_frame_extend(recon);
     free(c16); free(c4); free(cinter); free(mvf); free(mvq); free(c8); free(mv4); free(part);
 }

@@ -20,7 +20,8 @@ class Frame(C.Structure):
 
 
 class Params(C.Structure):
-    _fields_ = [("qp", C.c_int), ("merange", C.c_int), ("subpel", C.c_int), ("intra_in_p", C.c_int), ("deblock", C.c_int), ("transform8x8", C.c_int), ("partitions", C.c_int)]
+    _fields_ = [("qp", C.c_int), ("merange", C.c_int), ("subpel", C.c_int), ("intra_in_p", C.c_int), ("deblock", C.c_int), ("transform8x8", C.c_int), ("partitions", C.c_int),
+                ("deblock_alpha", C.c_int), ("deblock_beta", C.c_int)]
 
 
 MV = np.dtype([("x", "<i2"), ("y", "<i2")])
@@ -133,7 +134,7 @@ def me_fullpel_parts(cur: OFrame, ref: OFrame, R, pmv=None, lam=0):
 class Seq(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("fps_num", C.c_int), ("fps_den", C.c_int),
                 ("sar_w", C.c_int), ("sar_h", C.c_int), ("qp", C.c_int), ("deblock", C.c_int),
-                ("cabac", C.c_int), ("transform8x8", C.c_int)]
+                ("cabac", C.c_int), ("transform8x8", C.c_int), ("deblock_alpha", C.c_int), ("deblock_beta", C.c_int)]
 
 
 def encode_frame(prm: Params, frame_type, cur: OFrame, ref, recon: OFrame, prev_mv=None):
@@ -145,13 +146,13 @@ def encode_frame(prm: Params, frame_type, cur: OFrame, ref, recon: OFrame, prev_
 
 
 class Entropy:
-    def __init__(self, w, h, qp, fps=(30, 1), sar=(1, 1), deblock=0, cabac=0, transform8x8=0):
+    def __init__(self, w, h, qp, fps=(30, 1), sar=(1, 1), deblock=0, cabac=0, transform8x8=0, deblock_offsets=(0, 0)):
         L = lib()
         L.b2h_entropy_create.restype = C.c_void_p
         L.b2h_write_sps.restype = C.c_size_t; L.b2h_write_pps.restype = C.c_size_t; L.b2h_write_slice.restype = C.c_size_t
         L.b2h_write_slice.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.b2h_entropy_destroy.argtypes = [C.c_void_p]
-        self.seq = Seq(w, h, fps[0], fps[1], sar[0], sar[1], qp, deblock, cabac, transform8x8)
+        self.seq = Seq(w, h, fps[0], fps[1], sar[0], sar[1], qp, deblock, cabac, transform8x8, deblock_offsets[0], deblock_offsets[1])
         self.mbw, self.mbh = (w + 15) // 16, (h + 15) // 16
         self.e = L.b2h_entropy_create(self.mbw, self.mbh)
         self.buf = np.zeros(self.mbw * self.mbh * 3072 + 65536, np.uint8)
@@ -192,10 +193,11 @@ class Entropy:
         return self.buf[:n].tobytes()
 
 
-def encode_sequence(frames, w, h, qp=26, merange=16, subpel=1, intra_in_p=1, gop=32, fps=(30, 1), deblock=0, cabac=0, transform8x8=0, partitions=0):
+def encode_sequence(frames, w, h, qp=26, merange=16, subpel=1, intra_in_p=1, gop=32, fps=(30, 1), deblock=0, cabac=0, transform8x8=0, partitions=0,
+                    deblock_offsets=(0, 0)):
     """frames: iterable of (y,u,v).  Returns (annexb_bytes, [recon OFrame], [info], [coef])."""
-    prm = Params(qp, merange, subpel, intra_in_p, deblock, transform8x8, partitions)
-    ent = Entropy(w, h, qp, fps, deblock=deblock, cabac=cabac, transform8x8=transform8x8)
+    prm = Params(qp, merange, subpel, intra_in_p, deblock, transform8x8, partitions, deblock_offsets[0], deblock_offsets[1])
+    ent = Entropy(w, h, qp, fps, deblock=deblock, cabac=cabac, transform8x8=transform8x8, deblock_offsets=deblock_offsets)
     out = bytearray()
     sc = b"\x00\x00\x00\x01"
     recons, infos, coefs = [], [], []

@@ -37,7 +37,8 @@ for case in range(ncases):
         eff_deblock = deblock
         prm_parts = parts
         ref_bs, recons, _, _ = b2oracle.encode_sequence(fr, w, h, qp=qp, merange=merange, subpel=subpel, intra_in_p=intra, gop=gop, fps=(30, 1),
-                                                         deblock=eff_deblock, cabac=cabac, transform8x8=eff_t8, partitions=prm_parts)
+                                                         deblock=eff_deblock, cabac=cabac, transform8x8=eff_t8, partitions=prm_parts,
+                                                         deblock_offsets=(-1, -1))
         assert bs == ref_bs, "bitstream differs from the oracle encoder's"
         dec = b2oracle.decode_yuv(b2oracle.split_access_units(bs))
         assert len(dec) == n and all(np.array_equal(d[0], r.y[:h, :w]) for d, r in zip(dec, recons)), "decoder drift"

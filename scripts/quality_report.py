@@ -34,7 +34,7 @@ for cname, (n, gen) in CONTENT.items():
     frames = gen(n)
     for tname, dkw, okw in TOOLS:
         t0 = time.time()
-        ref_bs, _, _, _ = o.encode_sequence(frames, W, H, qp=QP, merange=R, gop=GOP, fps=(30, 1), deblock=1, **okw)
+        ref_bs, _, _, _ = o.encode_sequence(frames, W, H, qp=QP, merange=R, gop=GOP, fps=(30, 1), deblock=1, deblock_offsets=(-1, -1), **okw)
         t_cpu = time.time() - t0
         enc = b2enc.DropInEncoder(W, H, preset="medium", tune="film", quality=QP, fps=(30, 1), annexb=1, i_keyint_max=GOP, i_gop_slots=8, **dkw)
         t0 = time.time()

@@ -34,6 +34,13 @@ def test_param_and_error_conventions(b2):
     assert L.b2_param_default_preset(C.byref(p), b"ultrafast", None) == 0 and (p.b_cabac, p.b_deblocking_filter) == (0, 0)
     assert L.b2_param_default_preset(C.byref(p), b"slow", None) == 0 and p.i_merange == 32
     assert L.b2_param_default_preset(C.byref(p), b"medium", b"zerolatency") == 0 and p.i_gop_slots == 1
+    # tunes as in x264: film = deblock -1:-1 (the reference's default, av_encode.c:103), several tunes separated by ','
+    assert L.b2_param_default_preset(C.byref(p), b"medium", b"film") == 0
+    assert (p.i_deblocking_filter_alphac0, p.i_deblocking_filter_beta) == (-1, -1)
+    assert L.b2_param_default_preset(C.byref(p), b"medium", b"film,zerolatency") == 0
+    assert (p.i_gop_slots, p.i_deblocking_filter_alphac0) == (1, -1)
+    assert L.b2_param_default_preset(C.byref(p), b"medium", b"stillimage") == 0 and p.i_deblocking_filter_beta == -3
+    assert L.b2_param_default_preset(C.byref(p), b"medium", b"film,nosuchtune") != 0
     assert L.b2_param_default_preset(C.byref(p), b"warp9", None) != 0              # av_encode.c:384-386
     assert L.b2_param_default_preset(C.byref(p), b"medium", b"nosuchtune") != 0
     assert L.b2_param_apply_profile(C.byref(p), None) == 0                          # av_encode.c:403 with profile NULL

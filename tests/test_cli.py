@@ -25,7 +25,8 @@ def test_cli_y4m_to_h264(oracle, tmp_path):
     assert r.returncode == 0, r.stderr
     assert "9 frames in, 9 frames out" in r.stdout
     bs = open(out, "rb").read()
-    ref_bs, recons, _, _ = oracle.encode_sequence(frames, w, h, qp=24, merange=16, gop=4, fps=(30, 1), deblock=1, cabac=1)
+    ref_bs, recons, _, _ = oracle.encode_sequence(frames, w, h, qp=24, merange=16, gop=4, fps=(30, 1), deblock=1, cabac=1,
+                                                   deblock_offsets=(-1, -1))      # tune film = deblock -1:-1, as in x264
     assert bs == ref_bs                                  # same stream as the oracle encoder at the same settings
     dec = oracle.decode_yuv(oracle.split_access_units(bs))
     assert len(dec) == n
@@ -55,7 +56,8 @@ def test_cli_filters_and_mp4(oracle, tmp_path):
     assert "9 frames in, 9 frames out" in r.stdout
     dn = oracle.Hqdn3d(w, h)
     filt = oracle.yadif_sequence([dn(f) for f in frames], w, h, tff=1)
-    _, recons, _, _ = oracle.encode_sequence(filt, w, h, qp=24, merange=16, gop=4, fps=(30, 1), deblock=1, cabac=1, transform8x8=1, partitions=2)
+    _, recons, _, _ = oracle.encode_sequence(filt, w, h, qp=24, merange=16, gop=4, fps=(30, 1), deblock=1, cabac=1, transform8x8=1, partitions=2,
+                                            deblock_offsets=(-1, -1))
     cap = cv2.VideoCapture(str(out), cv2.CAP_FFMPEG)
     cap.set(cv2.CAP_PROP_CONVERT_RGB, 0)
     got = []

@@ -96,7 +96,7 @@ def test_reference_call_sequence_and_bitstream(oracle, b2, profile, profile_idc,
     assert sps[1][5] == profile_idc and sps[1][7] in (12, 13, 20, 21, 30)                  # profile_idc / level_idc at [5],[7] (:703-705)
     bs = to_annexb(out, length_prefixed=True)
     ref_bs, recons, _, _ = oracle.encode_sequence(frames, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1), deblock=1, cabac=cabac,
-                                                   transform8x8=t8)
+                                                   transform8x8=t8, deblock_offsets=(-1, -1))   # tune film: deblock -1:-1 as in x264
     assert bs == ref_bs, "GPU drop-in bitstream differs from the oracle encoder's"
     dec = oracle.decode_yuv(oracle.split_access_units(bs))
     assert len(dec) == n
@@ -114,7 +114,7 @@ def test_dropin_high_profile_with_partitions(oracle, b2, pm, amp):
                 b_transform_8x8=1, b_partitions=pm)
     bs = to_annexb(out, length_prefixed=True)
     ref_bs, recons, infos, _ = oracle.encode_sequence(frames, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1), deblock=1, cabac=1,
-                                                      transform8x8=1, partitions=pm)
+                                                      transform8x8=1, partitions=pm, deblock_offsets=(-1, -1))
     assert bs == ref_bs
     assert sum(int((i["part"] != 0).sum()) for i in infos) > 20
     dec = oracle.decode_yuv(oracle.split_access_units(bs))
@@ -155,7 +155,8 @@ def test_decoder_format_straight_into_the_encoder(oracle, b2, fmt):
     enc.close()
     assert len(out) == n
     bs = to_annexb(out, length_prefixed=False)
-    ref_bs, recons, _, _ = oracle.encode_sequence(conv, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1), deblock=1, cabac=1)
+    ref_bs, recons, _, _ = oracle.encode_sequence(conv, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1), deblock=1, cabac=1,
+                                                   deblock_offsets=(-1, -1))
     assert bs == ref_bs
 
 
@@ -172,20 +173,28 @@ def test_slot_count_does_not_change_the_stream(b2):
 
 
 def test_delay_contract(b2):
-    """0 while frames are delayed, delayed_frames() counts them, encode(NULL) drains one per call"""
-    w, h = 64, 64
-    frames = smooth_seq(w, h, 5, seed=2)
-    enc = b2.DropInEncoder(w, h, quality=30, i_keyint_max=4, i_gop_slots=2)
+    """0 = no output yet, delayed_frames() = frames in - frames out at every call, encode(NULL) returns one frame per call until
+    the encoder is empty (av_encode.c:971-974, :1076-1083); GOPs are encoded while they are gathered, so the first frame
+    arrives long before slots x keyint pictures are in"""
+    import time
+    w, h, gop = 64, 64, 4
+    frames = smooth_seq(w, h, 24, seed=2)
+    enc = b2.DropInEncoder(w, h, quality=30, i_keyint_max=gop, i_gop_slots=3)
+    got, first = 0, None
     for t, fr in enumerate(frames):
-        assert enc.encode(fr, t)[0] == 0
-        assert enc.delayed() == t + 1
-    got = 0
+        size = enc.encode(fr, t)[0]
+        assert size >= 0
+        got += size > 0
+        if size > 0 and first is None: first = t
+        assert enc.delayed() == t + 1 - got
+        time.sleep(0.005)                                # a producer slower than the GPU (a decoder)
+    assert first is not None and first < 2 * gop, "first output after %s pictures" % first
     while enc.delayed() > 0:
         assert enc.encode(None, 0)[0] > 0
         got += 1
-    assert got == 5
+    assert got == len(frames) and enc.encode(None, 0)[0] == 0
     enc.close()
     enc = b2.DropInEncoder(w, h, tune="zerolatency", quality=30)
-    for t, fr in enumerate(frames):
+    for t, fr in enumerate(frames[:5]):
         assert enc.encode(fr, t)[0] > 0 and enc.delayed() == 0
     enc.close()

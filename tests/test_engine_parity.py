@@ -12,12 +12,12 @@ INFO_FIELDS = ["mb_type", "mvx", "mvy", "i16_mode", "chroma_mode", "cbp", "i4_mo
 
 
 def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="yuv420p", deblock=0, transform8x8=0, pack_levels=0,
-                    partitions=0):
+                    partitions=0, deblock_offsets=(0, 0)):
     """seqs: list (one per slot) of lists of (y,u,v) frames"""
     S, T = len(seqs), len(seqs[0])
     eng = b2.Engine(w, h, slots=S, fmt=fmt, ring=2, merange=R, qp=qp, subpel=subpel, intra_in_p=intra_in_p, deblock=deblock,
-                    transform8x8=transform8x8, pack_levels=pack_levels, partitions=partitions)
-    prm = oracle.Params(qp, R, subpel, intra_in_p, deblock, transform8x8, partitions)
+                    transform8x8=transform8x8, pack_levels=pack_levels, partitions=partitions, deblock_offsets=deblock_offsets)
+    prm = oracle.Params(qp, R, subpel, intra_in_p, deblock, transform8x8, partitions, deblock_offsets[0], deblock_offsets[1])
     stats = {"t8": 0, "coded4": 0, "i8": 0, "parts": np.zeros(4, int), "mvx_mod4": np.zeros(4, int)}
     prev = [None] * S; prev_mv = [None] * S
     for t in range(T):
@@ -155,6 +155,14 @@ def test_engine_with_deblocking(oracle, b2, w, h, qp, R, cut):
     """K8 in-loop deblocking: reconstruction and everything downstream stay bit-exact"""
     seqs = [smooth_seq(w, h, 5, seed=qp + 1, cut=cut), smooth_seq(w, h, 5, seed=qp + 2)]
     run_and_compare(oracle, b2, seqs, w, h, qp, R, deblock=1)
+
+
+@pytest.mark.parametrize("offs", [(-1, -1), (3, -2), (-6, 6)])
+def test_engine_deblocking_offsets(oracle, b2, offs):
+    """tune film & co: loop-filter offsets (indexA = qp + 2a, indexB = qp + 2b) in K8 == oracle"""
+    w, h, qp = 208, 160, 30
+    seqs = [smooth_seq(w, h, 4, seed=31, cut=2), smooth_seq(w, h, 4, seed=32)]
+    run_and_compare(oracle, b2, seqs, w, h, qp, 16, deblock=1, transform8x8=1, deblock_offsets=offs)
 
 
 @pytest.mark.parametrize("w,h,qp,R,cut,deblock", [(176, 144, 26, 16, None, 1), (320, 240, 33, 32, 2, 1), (208, 160, 18, 16, 1, 0),

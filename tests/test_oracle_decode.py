@@ -134,3 +134,15 @@ def test_decoder_matches_oracle_recon_with_deblocking(oracle, w, h, qp, R, cut):
     """in-loop deblocking filter (8.7) of the oracle against libavcodec's"""
     frames = smooth_seq(w, h, 6, seed=qp, cut=cut)
     _roundtrip(oracle, frames, w, h, qp=qp, merange=R, gop=32, deblock=1)
+
+
+@pytest.mark.parametrize("offs", [(-1, -1), (1, 1), (-3, -3), (2, -2), (-6, 6), (6, -6)])
+@pytest.mark.parametrize("cabac", [0, 1])
+def test_deblock_offsets_decoder_exact(oracle, offs, cabac):
+    """slice_alpha_c0_offset_div2 / slice_beta_offset_div2 (x264's tunes: film -1:-1 -- the reference's default, av_encode.c:103 --
+    animation 1:1, stillimage -3:-3): the oracle's loop filter with offsets == libavcodec's, and the offsets change the picture"""
+    w, h, qp = 176, 144, 33
+    frames = smooth_seq(w, h, 5, seed=17, cut=3)
+    bs, recons, _ = _roundtrip(oracle, frames, w, h, qp=qp, merange=16, gop=32, deblock=1, cabac=cabac, deblock_offsets=offs)
+    bs0, recons0, _ = _roundtrip(oracle, frames, w, h, qp=qp, merange=16, gop=32, deblock=1, cabac=cabac)
+    assert any(not np.array_equal(a.y, b.y) for a, b in zip(recons, recons0))

@@ -162,14 +162,15 @@ def unpack_levels(info, packed):
 class EngineCfg(C.Structure):
     _fields_ = [("device", C.c_int), ("width", C.c_int), ("height", C.c_int), ("slots", C.c_int), ("in_fmt", C.c_int),
                 ("in_ring", C.c_int), ("merange", C.c_int), ("qp", C.c_int), ("subpel", C.c_int), ("intra_in_p", C.c_int),
-                ("profile", C.c_int), ("streams", C.c_int), ("deblock", C.c_int), ("transform8x8", C.c_int), ("partitions", C.c_int), ("pack_levels", C.c_int)]
+                ("profile", C.c_int), ("streams", C.c_int), ("deblock", C.c_int), ("transform8x8", C.c_int), ("partitions", C.c_int), ("pack_levels", C.c_int),
+                ("deblock_alpha", C.c_int), ("deblock_beta", C.c_int)]
 
 
 class Engine:
     """One GPU's encode-stage engine: `slots` closed GOPs / streams advanced in lock-step."""
 
     def __init__(self, width, height, slots=1, fmt="yuv420p", ring=1, merange=16, qp=26, subpel=1, intra_in_p=1,
-                 device=0, profile=0, streams=0, deblock=0, transform8x8=0, pack_levels=0, partitions=0):
+                 device=0, profile=0, streams=0, deblock=0, transform8x8=0, pack_levels=0, partitions=0, deblock_offsets=(0, 0)):
         require_gpu()
         L = lib()
         L.b2_engine_create.restype = C.c_void_p
@@ -190,6 +191,13 @@ class Engine:
         L.b2_engine_group_range.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.b2_engine_encode_group.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.b2_engine_d2h_group.argtypes = [C.c_void_p, C.c_int]
+        L.b2_engine_group_result_set.argtypes = [C.c_void_p, C.c_int]
+        L.b2_engine_group_done.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.b2_engine_group_wait.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.b2_engine_info_set.restype = C.c_void_p; L.b2_engine_info_set.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.b2_engine_packed_set.restype = C.c_void_p; L.b2_engine_packed_set.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+        L.b2_engine_put_picture.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.b2_engine_set_input_format.argtypes = [C.c_void_p, C.c_int]
         L.b2_engine_info.argtypes = [C.c_void_p, C.c_int]; L.b2_engine_coef.argtypes = [C.c_void_p, C.c_int]
         L.b2_engine_packed.restype = C.c_void_p; L.b2_engine_packed.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]
         L.b2_engine_packed_bytes_total.restype = C.c_longlong; L.b2_engine_packed_bytes_total.argtypes = [C.c_void_p]
@@ -201,7 +209,8 @@ class Engine:
         L.b2_engine_kernel_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_long)]
         self.L = L
         self.cfg = EngineCfg(device, width, height, slots, FMT[fmt] if isinstance(fmt, str) else fmt, ring, merange, qp,
-                             subpel, intra_in_p, profile, streams, deblock, transform8x8, partitions, pack_levels)
+                             subpel, intra_in_p, profile, streams, deblock, transform8x8, partitions, pack_levels,
+                             deblock_offsets[0], deblock_offsets[1])
         self.h = L.b2_engine_create(C.byref(self.cfg))
         if not self.h:
             raise RuntimeError("b2_engine_create failed")
@@ -270,6 +279,30 @@ class Engine:
 
     def d2h(self, nslots=None):
         self._ck(self.L.b2_engine_d2h(self.h, self.slots if nslots is None else nslots), "d2h")
+
+    def put_picture(self, slot, ring, planes):
+        """b2_engine_put_picture: planes = 2-D uint8 arrays (row length = stride) in any host memory"""
+        sp = (C.c_void_p * 4)(*([p.ctypes.data for p in planes] + [None] * (4 - len(planes))))
+        ss = (C.c_int * 4)(*([p.strides[0] for p in planes] + [0] * (4 - len(planes))))
+        self._ck(self.L.b2_engine_put_picture(self.h, slot, ring, sp, ss), "put_picture")
+
+    def group_result_set(self, group):
+        return self.L.b2_engine_group_result_set(self.h, group)
+
+    def group_done(self, group, rset):
+        return self.L.b2_engine_group_done(self.h, group, rset)
+
+    def group_wait(self, group, rset):
+        self._ck(self.L.b2_engine_group_wait(self.h, group, rset), "group_wait")
+
+    def results_set(self, rset, slot):
+        """(info copy, packed level stream copy) of result set `rset` of `slot` (pack_levels engines)"""
+        pi = self.L.b2_engine_info_set(self.h, rset, slot)
+        info = np.frombuffer((C.c_uint8 * (self.nmb * MBINFO.itemsize)).from_address(pi), MBINFO).copy()
+        n = C.c_size_t(0)
+        pp = self.L.b2_engine_packed_set(self.h, rset, slot, C.byref(n))
+        packed = np.frombuffer((C.c_uint8 * n.value).from_address(pp), np.uint8).copy() if n.value else np.zeros(0, np.uint8)
+        return info, packed
 
     def sync(self):
         self._ck(self.L.b2_engine_sync(self.h), "sync")
@@ -345,7 +378,8 @@ class Param(C.Structure):
     _fields_ = [("i_width", C.c_int), ("i_height", C.c_int), ("b_annexb", C.c_int), ("i_fps_num", C.c_int), ("i_fps_den", C.c_int),
                 ("vui", _Vui), ("rc", _Rc), ("i_keyint_max", C.c_int), ("i_gop_slots", C.c_int), ("i_merange", C.c_int),
                 ("b_subpel", C.c_int), ("b_intra_in_p", C.c_int), ("i_device", C.c_int), ("i_csp_in", C.c_int),
-                ("b_deblocking_filter", C.c_int), ("b_cabac", C.c_int), ("b_transform_8x8", C.c_int), ("b_partitions", C.c_int)]
+                ("b_deblocking_filter", C.c_int), ("b_cabac", C.c_int), ("b_transform_8x8", C.c_int), ("b_partitions", C.c_int),
+                ("i_deblocking_filter_alphac0", C.c_int), ("i_deblocking_filter_beta", C.c_int), ("i_devices", C.c_int)]
 
 
 class Image(C.Structure):
@@ -361,8 +395,9 @@ class Nal(C.Structure):
     _fields_ = [("i_ref_idc", C.c_int), ("i_type", C.c_int), ("i_payload", C.c_int), ("p_payload", C.c_void_p)]
 
 
-def _dropin_lib():
-    L = lib()
+def _dropin_lib(L=None):
+    """argtypes of the drop-in boundary on `L` (default: libb2enc.so; the CPU host-logic tests pass their mock build)"""
+    L = L or lib()
     L.b2_encoder_open.restype = C.c_void_p; L.b2_encoder_open.argtypes = [C.POINTER(Param)]
     L.b2_encoder_encode.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Nal)), C.POINTER(C.c_int), C.POINTER(Picture), C.POINTER(Picture)]
     L.b2_encoder_delayed_frames.argtypes = [C.c_void_p]; L.b2_encoder_close.argtypes = [C.c_void_p]
@@ -401,9 +436,11 @@ class DropInEncoder:
     """Drives the b2_* mirror of the x264 API exactly like av_encode.c does (open :378-438, loop :968-975,
     drain :1076-1083)."""
 
-    def __init__(self, w, h, preset="medium", tune="film", quality=26, profile=None, fps=(30, 1), annexb=0, **ext):
-        require_gpu()
-        self.L = L = _dropin_lib()
+    def __init__(self, w, h, preset="medium", tune="film", quality=26, profile=None, fps=(30, 1), annexb=0, library=None, **ext):
+        if library is None:
+            require_gpu()
+        self.L = L = _dropin_lib(library)
+        self.sws = None
         self.w, self.h = w, h
         p = Param()
         if L.b2_param_default_preset(C.byref(p), preset.encode() if preset else None, tune.encode() if tune else None) != 0:
@@ -469,10 +506,39 @@ class DropInEncoder:
                 nals.append((nal[i].i_type, whole[off:off + nal[i].i_payload])); off += nal[i].i_payload
         return size, nals, self.pic_out.i_pts, self.pic_out.i_dts, self.pic_out.b_keyframe
 
+    def encode_via_sws(self, fmt, planes, pts, flags=1):
+        """the reference's per-frame sequence (av_encode.c:543-547, :970): sws_scale the decoder's picture (strided planes in
+        format `fmt`) INTO pic_in, then encode pic_in.  Returns like encode()."""
+        if self.sws is None or self.sws[0] != (fmt, flags):
+            if self.sws is not None:
+                self.L.b2_sws_freeContext(self.sws[1])
+            ctx = self.L.b2_sws_getContext(self.w, self.h, FMT[fmt], self.w, self.h, FMT["yuv420p"], flags, None, None, None)
+            if not ctx:
+                raise RuntimeError("b2_sws_getContext failed")
+            self.sws = ((fmt, flags), ctx)
+        planes = [np.ascontiguousarray(p, np.uint8) for p in planes]
+        sp = (C.c_void_p * 4)(*([p.ctypes.data for p in planes] + [None] * (4 - len(planes))))
+        ss = (C.c_int * 4)(*([p.shape[1] for p in planes] + [0] * (4 - len(planes))))
+        dp = (C.c_void_p * 4)(*[self.pic_in.img.plane[i] for i in range(4)])
+        ds = (C.c_int * 4)(*[self.pic_in.img.i_stride[i] for i in range(4)])
+        if self.L.b2_sws_scale(self.sws[1], sp, ss, 0, self.h, dp, ds) != self.h:
+            raise RuntimeError("b2_sws_scale failed")
+        self.pic_in.i_type = 0; self.pic_in.i_pts = pts
+        nal = C.POINTER(Nal)(); n = C.c_int(0)
+        size = self.L.b2_encoder_encode(self.h_enc, C.byref(nal), C.byref(n), C.byref(self.pic_in), C.byref(self.pic_out))
+        nals = []
+        if size > 0:
+            base = nal[0].p_payload; whole = C.string_at(base, size); off = 0
+            for i in range(n.value):
+                nals.append((nal[i].i_type, whole[off:off + nal[i].i_payload])); off += nal[i].i_payload
+        return size, nals, self.pic_out.i_pts, self.pic_out.i_dts, self.pic_out.b_keyframe
+
     def delayed(self):
         return self.L.b2_encoder_delayed_frames(self.h_enc)
 
     def close(self):
+        if self.sws is not None:
+            self.L.b2_sws_freeContext(self.sws[1]); self.sws = None
         if self.h_enc:
             self.L.b2_picture_clean(C.byref(self.pic_in))
             self.L.b2_encoder_close(self.h_enc)

@@ -15,6 +15,8 @@
 #include <string.h>
 #include <vector>
 #include <mutex>
+#include <atomic>
+#include <memory>
 #include "b2_common.cuh"
 #include "b2_internal.h"
 #include "../../include/b2enc_engine.h"
@@ -79,6 +81,14 @@ struct b2_engine {
     std::vector<uint8_t> in_direct;                                   // [slot * in_ring + ring]: entry is already on the device
     const void *direct_last = nullptr; bool direct_last_ok = false;   // pinned-ness of the last source pointer looked up
     std::vector<cudaEvent_t> ev_h2d;
+    // b2_engine_put_picture (GOP-streaming hosts): per slot, the event behind its latest upload and a flag that the group's
+    // next encode still has to wait for it (set by the caller's thread, consumed by the thread that issues the encodes);
+    // pageable sources go through two page-locked bounce buffers
+    std::vector<cudaEvent_t> ev_put;
+    std::unique_ptr<std::atomic<uint8_t>[]> put_pending;
+    uint8_t *h_bounce[2] = {nullptr, nullptr};
+    cudaEvent_t ev_bounce[2] = {nullptr, nullptr};
+    int bounce_next = 0;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
     long launches = 0;
     double k_ms[B2_NKERNELS] = {};
@@ -162,6 +172,13 @@ static int engine_alloc(b2_engine *e)
     ENG_OK(cudaStreamCreateWithFlags(&e->st_in, cudaStreamNonBlocking));
     ENG_OK(cudaStreamCreateWithFlags(&e->st_put, cudaStreamNonBlocking));
     e->in_direct.assign((size_t)c.in_ring * S, 0);
+    e->ev_put.resize(S);
+    e->put_pending.reset(new std::atomic<uint8_t>[S]);
+    for (size_t s = 0; s < S; s++) {
+        ENG_OK(cudaEventCreateWithFlags(&e->ev_put[s], cudaEventDisableTiming));
+        e->put_pending[s].store(0);
+    }
+    for (int k = 0; k < 2; k++) ENG_OK(cudaEventCreateWithFlags(&e->ev_bounce[k], cudaEventDisableTiming));
     {   // the copy-out stream runs K9b (a small kernel that writes the packed levels into pinned memory) while the compute
         // streams keep every SM busy with K1: at the highest priority its CTAs are placed as soon as any resident CTA retires.
         // (Measured at 64 GOPs per GPU: no difference in e2e, 5,110-5,166 frames/s either way -- kept because a late K9b
@@ -187,7 +204,8 @@ static int engine_alloc(b2_engine *e)
         ENG_OK(cudaStreamCreateWithFlags(&gr.st, cudaStreamNonBlocking));
         for (int s = 0; s < 2; s++) {
             ENG_OK(cudaEventCreateWithFlags(&gr.ev_enc[s], cudaEventDisableTiming));
-            ENG_OK(cudaEventCreateWithFlags(&gr.ev_d2h[s], cudaEventDisableTiming));
+            // a host thread waiting for a result set sleeps instead of spinning: the cores belong to the entropy stage
+            ENG_OK(cudaEventCreateWithFlags(&gr.ev_d2h[s], cudaEventDisableTiming | cudaEventBlockingSync));
         }
         ENG_OK(cudaEventCreateWithFlags(&gr.ev_join, cudaEventDisableTiming));
         gr.ev_k0.resize(c.in_ring); gr.h2d_pending.assign(c.in_ring, 0);
@@ -207,6 +225,9 @@ extern "C" b2_engine_t *b2_engine_create(const b2_engine_cfg_t *cfg)
     }
     if (cfg->qp < 10 || cfg->qp > 51) { fprintf(stderr, "b2enc: qp must be in 10..51\n"); return nullptr; }
     if (cfg->merange != 16 && cfg->merange != 32) { fprintf(stderr, "b2enc: merange must be 16 or 32\n"); return nullptr; }
+    // every stream group wants its own hardware queue (the default of 8 connections makes groups share queues, and a group
+    // that waits on an event then holds up the kernels of the group queued behind it); read when the context is created
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
         cudaGetLastError();
@@ -250,6 +271,8 @@ extern "C" void b2_engine_destroy(b2_engine_t *e)
         if (gr.st) cudaStreamDestroy(gr.st);
     }
     for (auto ev : e->ev_h2d) cudaEventDestroy(ev);
+    for (auto ev : e->ev_put) cudaEventDestroy(ev);
+    for (int k = 0; k < 2; k++) { if (e->ev_bounce[k]) cudaEventDestroy(e->ev_bounce[k]); cudaFreeHost(e->h_bounce[k]); }
     for (auto ev : e->ev_pool) cudaEventDestroy(ev);
     for (auto &r : e->prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
@@ -348,6 +371,68 @@ extern "C" int b2_engine_put_frame_direct(b2_engine_t *e, int slot, int ring, co
     return 0;
 }
 
+// Hand one picture to (slot, ring) from any host memory; returns as soon as the source has been read.  Page-locked sources are
+// DMA'd straight into the device ring (the call waits for the copy: the caller refills the picture, av_encode.c:415/:545);
+// pageable ones are copied into one of two page-locked bounce buffers whose upload runs behind the caller's back.  No
+// b2_engine_h2d follows: the next encode of the slot's group waits for the upload itself.  One caller thread at a time; it may
+// be another thread than the one issuing encode_group / d2h_group as long as the slot's ring entry is not being encoded.
+extern "C" int b2_engine_put_picture(b2_engine_t *e, int slot, int ring, const uint8_t *const src[4], const int stride[4])
+{
+    if (slot < 0 || slot >= e->cfg.slots || ring < 0 || ring >= e->cfg.in_ring || !src || !src[0]) return -1;
+    cudaSetDevice(e->cfg.device);
+    cudaPointerAttributes a;
+    const bool pinned = cudaPointerGetAttributes(&a, src[0]) == cudaSuccess && a.type == cudaMemoryTypeHost;
+    cudaGetLastError();                                 // an unregistered pointer is not an error here
+    int rb[3], rows[3];
+    const int np = b2_fmt_layout(e->cfg.in_fmt, e->cfg.width, e->cfg.height, rb, rows);
+    uint8_t *dst = e->d_in + in_off(e, slot, ring);
+    if (pinned) {
+        for (int p = 0; p < np; p++) {
+            ENG_OK(cudaMemcpy2DAsync(dst, rb[p], src[p], stride[p], rb[p], rows[p], cudaMemcpyHostToDevice, e->st_put));
+            dst += (size_t)rb[p] * rows[p];
+        }
+        ENG_OK(cudaEventRecord(e->ev_put[slot], e->st_put));
+        ENG_OK(cudaStreamSynchronize(e->st_put));
+    } else {
+        const int k = e->bounce_next;
+        e->bounce_next ^= 1;
+        if (!e->h_bounce[k]) ENG_OK(cudaHostAlloc(&e->h_bounce[k], e->in_stride, cudaHostAllocPortable));
+        else ENG_OK(cudaEventSynchronize(e->ev_bounce[k]));         // its previous upload has left the buffer
+        uint8_t *b = e->h_bounce[k];
+        for (int p = 0; p < np; p++) {
+            if (stride[p] == rb[p]) memcpy(b, src[p], (size_t)rb[p] * rows[p]);
+            else for (int y = 0; y < rows[p]; y++) memcpy(b + (size_t)y * rb[p], src[p] + (size_t)y * stride[p], rb[p]);
+            b += (size_t)rb[p] * rows[p];
+        }
+        ENG_OK(cudaMemcpyAsync(dst, e->h_bounce[k], e->in_bytes, cudaMemcpyHostToDevice, e->st_put));
+        ENG_OK(cudaEventRecord(e->ev_bounce[k], e->st_put));
+        ENG_OK(cudaEventRecord(e->ev_put[slot], e->st_put));
+    }
+    e->put_pending[slot].store(1, std::memory_order_release);
+    return 0;
+}
+
+// Change the raw input layout (B2_FMT_*) of an idle engine: the ring is re-allocated when the picture size differs.  Used by
+// the drop-in encoder when sws_scale hands it pictures in the decoder's own format (the conversion then runs as K0).
+extern "C" int b2_engine_set_input_format(b2_engine_t *e, int fmt)
+{
+    if (fmt == e->cfg.in_fmt) return 0;
+    const size_t nb = input_bytes(fmt, e->cfg.width, e->cfg.height);
+    if (!nb) { fprintf(stderr, "b2enc: unsupported input format %d for %dx%d\n", fmt, e->cfg.width, e->cfg.height); return -1; }
+    cudaSetDevice(e->cfg.device);
+    if (b2_engine_sync(e)) return -1;
+    ENG_OK(cudaStreamSynchronize(e->st_put));
+    const size_t ns = (nb + 255) & ~(size_t)255;
+    if (ns != e->in_stride) {
+        ENG_OK(cudaFree(e->d_in)); e->d_in = nullptr;
+        cudaFreeHost(e->h_in); e->h_in = nullptr;
+        for (int k = 0; k < 2; k++) { cudaFreeHost(e->h_bounce[k]); e->h_bounce[k] = nullptr; }
+        ENG_OK(cudaMalloc(&e->d_in, ns * e->cfg.in_ring * e->cfg.slots));
+    }
+    e->cfg.in_fmt = fmt; e->in_bytes = nb; e->in_stride = ns;
+    return 0;
+}
+
 extern "C" int b2_engine_h2d(b2_engine_t *e, int slot0, int nslots, int ring)
 {
     if (slot0 < 0 || nslots < 1 || slot0 + nslots > e->cfg.slots || ring < 0 || ring >= e->cfg.in_ring) return -1;
@@ -417,6 +502,8 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
     const int set = gr.res_set ^ 1;
     cudaStream_t st = gr.st;
     if (gr.h2d_pending[ring]) { ENG_OK(cudaStreamWaitEvent(st, e->ev_h2d[ring], 0)); gr.h2d_pending[ring] = 0; }
+    for (int s = gr.slot0; s < gr.slot0 + ns; s++)          // pictures handed over by b2_engine_put_picture
+        if (e->put_pending[s].exchange(0, std::memory_order_acquire)) ENG_OK(cudaStreamWaitEvent(st, e->ev_put[s], 0));
     if (gr.d2h_used[set]) ENG_OK(cudaStreamWaitEvent(st, gr.ev_d2h[set], 0));        // result set still being copied out
     const size_t oy = gr.slot0 * e->stride_y, oc = gr.slot0 * e->stride_c, om = (size_t)gr.slot0 * e->nmb;
     uint8_t *curw[3] = {e->d_cur[0] + oy, e->d_cur[1] + oc, e->d_cur[2] + oc};
@@ -479,7 +566,7 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
     }
     if (c.deblock) {
         KScope k(e, st, 8);
-        if (b2_launch_deblock(rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, ns, c.qp, info, st)) return -1;
+        if (b2_launch_deblock(rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, ns, c.qp, c.deblock_alpha, c.deblock_beta, info, st)) return -1;
     }
     {
         KScope k(e, st, 7);
@@ -545,6 +632,38 @@ extern "C" int b2_engine_d2h_group(b2_engine_t *e, int group)
     cudaSetDevice(e->cfg.device);
     Group &gr = e->groups[group];
     return d2h_group(e, gr, gr.last_n > 0 ? gr.last_n : gr.n);
+}
+
+// group-level hand-off (hosts that advance every group on its own, e.g. one closed GOP per group): the result set the
+// group's last b2_engine_d2h_group copies into, whether / until that copy has landed, and views of a given set
+extern "C" int b2_engine_group_result_set(const b2_engine_t *e, int group)
+{
+    return group < 0 || group >= (int)e->groups.size() ? -1 : e->groups[group].host_set;
+}
+extern "C" int b2_engine_group_done(b2_engine_t *e, int group, int set)
+{
+    if (group < 0 || group >= (int)e->groups.size() || set < 0 || set > 1) return -1;
+    const cudaError_t r = cudaEventQuery(e->groups[group].ev_d2h[set]);
+    if (r == cudaSuccess) return 1;
+    if (r == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+    fprintf(stderr, "b2enc: CUDA error %s while waiting for a result set\n", cudaGetErrorName(r));
+    return -1;
+}
+extern "C" int b2_engine_group_wait(b2_engine_t *e, int group, int set)
+{
+    if (group < 0 || group >= (int)e->groups.size() || set < 0 || set > 1) return -1;
+    ENG_OK(cudaEventSynchronize(e->groups[group].ev_d2h[set]));
+    return 0;
+}
+extern "C" const b2_mbinfo_t *b2_engine_info_set(b2_engine_t *e, int set, int slot)
+{
+    return set < 0 || set > 1 || slot < 0 || slot >= e->cfg.slots ? nullptr : e->h_info[set] + (size_t)slot * e->nmb;
+}
+extern "C" const uint8_t *b2_engine_packed_set(b2_engine_t *e, int set, int slot, size_t *bytes)
+{
+    if (set < 0 || set > 1 || slot < 0 || slot >= e->cfg.slots || !e->cfg.pack_levels) return nullptr;
+    if (bytes) *bytes = (size_t)e->h_pack_n[set][slot] * 32;
+    return e->h_pack[set] + (size_t)slot * e->pack_stride;
 }
 
 extern "C" int b2_engine_d2h(b2_engine_t *e, int nslots)

@@ -10,6 +10,21 @@ extern "C" int b2_device_count(void)
     return n;
 }
 
+// free / total device memory in bytes (b2_encoder_open sizes its GOP slots with it)
+extern "C" int b2_device_mem_info(int device, size_t *free_bytes, size_t *total_bytes)
+{
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    size_t f = 0, t = 0;
+    const cudaError_t r = cudaMemGetInfo(&f, &t);
+    cudaSetDevice(prev);
+    if (r != cudaSuccess) { cudaGetLastError(); return -1; }
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return 0;
+}
+
 namespace {
 struct DevBuf {
     void *p = nullptr;

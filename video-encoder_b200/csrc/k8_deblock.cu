@@ -193,7 +193,7 @@ __device__ void k8_mb_task(int lane, K8Warp &ws, uint8_t *const rec[3], int pitc
 
 __global__ void __launch_bounds__(K8_WARPS * 32)
 k8_deblock_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pitchc, size_t stride_y, size_t stride_c, int mbw, int mbh,
-                  int qp, const b2_mbinfo_t *__restrict__ info)
+                  int qp, int alpha_off, int beta_off, const b2_mbinfo_t *__restrict__ info)
 {
     __shared__ K8Warp s_warp[K8_WARPS];
     const int frame = blockIdx.y;
@@ -205,9 +205,12 @@ k8_deblock_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pitchc, 
     uint8_t *const rec[3] = {ry, ru, rv};
     const int qpc = chroma_qp(qp);
     FiltConst fy, fcc;
-    fy.alpha = c_alpha[qp]; fy.beta = c_beta[qp]; fcc.alpha = c_alpha[qpc]; fcc.beta = c_beta[qpc];
+    // 8.7.2.2: indexA = qPav + 2 * slice_alpha_c0_offset_div2, indexB = qPav + 2 * slice_beta_offset_div2, clipped to 0..51
+    const int ia = clip3(0, 51, qp + 2 * alpha_off), ib = clip3(0, 51, qp + 2 * beta_off);
+    const int iac = clip3(0, 51, qpc + 2 * alpha_off), ibc = clip3(0, 51, qpc + 2 * beta_off);
+    fy.alpha = c_alpha[ia]; fy.beta = c_beta[ib]; fcc.alpha = c_alpha[iac]; fcc.beta = c_beta[ibc];
 #pragma unroll
-    for (int i = 0; i < 3; i++) { fy.tc0[i] = c_tc0[qp][i]; fcc.tc0[i] = c_tc0[qpc][i]; }
+    for (int i = 0; i < 3; i++) { fy.tc0[i] = c_tc0[ia][i]; fcc.tc0[i] = c_tc0[iac][i]; }
     for (int d = 0; d < ndiag; d++) {
         const int y_lo = max(0, (d - mbw + 2) >> 1), y_hi = min(mbh - 1, d >> 1);
         for (int t = y_lo + gwarp; t <= y_hi; t += nwarps) {
@@ -223,7 +226,7 @@ k8_deblock_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pitchc, 
 }  // namespace
 
 int b2_launch_deblock(uint8_t *const rec[3], int pitch, int pitchc, size_t stride_y, size_t stride_c, int mbw, int mbh,
-                      int nframes, int qp, const b2_mbinfo_t *d_info, cudaStream_t st)
+                      int nframes, int qp, int alpha_off, int beta_off, const b2_mbinfo_t *d_info, cudaStream_t st)
 {
     const int maxdiag = mbh < (mbw + 1) / 2 ? mbh : (mbw + 1) / 2;
     int ncta = 1;
@@ -238,6 +241,6 @@ int b2_launch_deblock(uint8_t *const rec[3], int pitch, int pitchc, size_t strid
     attr[0].val.clusterDim.x = ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     B2_CUDA_OK(cudaLaunchKernelEx(&cfg, k8_deblock_kernel, rec[0], rec[1], rec[2], pitch, pitchc, stride_y, stride_c, mbw, mbh, qp,
-                                  d_info));
+                                  alpha_off, beta_off, d_info));
     return 0;
 }

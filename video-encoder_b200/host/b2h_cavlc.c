@@ -3,8 +3,8 @@
  * stage that follows the CUDA encode stage.  Stands where the entropy-coding tail of
  * x264_encoder_encode (av_encode.c:970) stands in the reference.  ITU-T H.264 7.3 / 9.1 / 9.2;
  * tables 9-4 (coded_block_pattern), 9-5 (coeff_token), 9-7/9-8/9-9 (total_zeros), 9-10
- * (run_before).  One slice per picture, one reference frame, POC type 2, deblocking disabled
- * (disable_deblocking_filter_idc = 1).
+ * (run_before).  One slice per picture, one reference frame, POC type 2; the in-loop filter is signalled per
+ * slice from b2h_seq_t (disable_deblocking_filter_idc, slice_alpha_c0_offset_div2, slice_beta_offset_div2).
  */
 #include <stdlib.h>
 #include <string.h>
@@ -401,7 +401,8 @@ void b2h_slice_header(bs_t *b, const b2h_seq_t *s, int is_p, int frame_num, int 
     bs_se(b, 0);                                   /* slice_qp_delta                      */
     if (s->deblock) {
         bs_ue(b, 0);                               /* disable_deblocking_filter_idc = 0   */
-        bs_se(b, 0); bs_se(b, 0);                  /* slice_alpha_c0_offset_div2, slice_beta_offset_div2 */
+        bs_se(b, s->deblock_alpha);                /* slice_alpha_c0_offset_div2          */
+        bs_se(b, s->deblock_beta);                 /* slice_beta_offset_div2              */
     } else {
         bs_ue(b, 1);                               /* disable_deblocking_filter_idc = 1   */
     }

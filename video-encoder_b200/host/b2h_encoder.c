@@ -3,14 +3,23 @@
  * that av_encode.c calls (enc_x264_open :378-438, the encode loop :968-975, the drain loop :1076-1083),
  * implemented over the CUDA engine (include/b2enc_engine.h) and the host entropy stage (b2h_entropy.h: CABAC or CAVLC).
  *
- * Frame queue (row a0 of SURVEY.md 8a): the caller still hands over one picture per call, but pictures
- * are gathered into i_gop_slots closed GOPs of i_keyint_max frames; a full batch is advanced through
- * the GPU in lock-step (one launch sequence per frame index covers all GOPs), the host entropy-codes
- * the per-MB results and frames are then returned in display order, one per call -- exactly the
- * "0 = no output yet / delayed_frames() / encode(NULL) drains" contract main() relies on
- * (av_encode.c:971-974, :1076-1083).  A pipeline thread drives batch k through the GPU and the entropy workers while the
- * caller already gathers batch k+1 into the other half of the pinned input ring, so copying pictures in and encoding
- * overlap.  i_gop_slots = 1 encodes every picture immediately (zero delay).
+ * Frame queue (row a0 of SURVEY.md 8a).  The caller still hands over one picture per call; the reference's strictly
+ * synchronous loop becomes a GOP-streaming pipeline:
+ *
+ *   caller thread      picture -> device ring of the closed GOP being gathered (GOP k lives on GPU k % N, in a free slot of
+ *                      that GPU's engine); returns a finished frame when the head of the display-order fifo is ready
+ *   one thread per GPU advances every slot that has pictures: upload is already done, so a step is encode_group + d2h_group
+ *                      of the slot's own CUDA stream, two steps in flight per slot; a slot starts as soon as its first picture
+ *                      is there -- it does not wait for the GOP, let alone for a batch of GOPs -- and is free again when its
+ *                      last result set has been fetched
+ *   entropy workers    one frame per job (CABAC / CAVLC slice + parameter sets), from heap copies of the result sets, on all
+ *                      host cores; finished frames land in the fifo slot of their frame number
+ *
+ * Closed GOPs share nothing, so which GPU or slot a GOP ran on, and how many were in flight, cannot change its bytes: the
+ * N-GPU stream is byte-identical to the 1-GPU stream (tests/test_dropin.py, tests/test_multi_gpu.py).
+ * The x264 contract main() relies on holds: 0 = no output yet, delayed_frames() = frames in - frames out, encode(NULL)
+ * returns one frame per call until the encoder is empty (av_encode.c:971-974, :1076-1083).
+ * i_gop_slots = 1 (tune zerolatency) encodes every picture synchronously in the caller's thread (zero delay).
  */
 #define _POSIX_C_SOURCE 200809L
 #include <pthread.h>
@@ -20,10 +29,9 @@
 #include <unistd.h>
 #include "b2enc.h"
 #include "b2enc_engine.h"
+#include "b2enc_kernels.h"
 #include "b2h_entropy.h"
-
-void *b2_pinned_alloc(size_t n);
-void b2_pinned_free(void *p);
+#include "b2h_picture.h"
 
 typedef struct {
     uint8_t *data;
@@ -32,53 +40,124 @@ typedef struct {
     int nal_off[3], nal_size[3], nal_type[3], nal_ref[3];
     int64_t pts;
     int key;
+    int ready;
 } outframe_t;
 
-#define B2_MAX_WORKERS 16
+#define B2_MAX_WORKERS 64
+#define B2_MAX_DEVICES 16
 
 /* one frame to entropy-code; the per-MB decisions and the packed levels are heap copies of the engine's pinned result set, so
- * the GPU may run ahead of the entropy workers by any number of steps (the engine keeps only two result sets) */
-typedef struct { int qi, slot, t; int64_t gop_index; uint8_t *res; size_t packed_bytes; } job_t;
+ * the GPU may run ahead of the entropy workers (the engine keeps only two result sets per slot) */
+typedef struct { int64_t frame; int t; int64_t gop_index; uint8_t *res; size_t packed_bytes; } job_t;
+
+enum { SLOT_FREE = 0, SLOT_OPEN = 1 /* pictures still arriving */, SLOT_CLOSED = 2 /* the GOP's last picture is in */ };
+typedef struct {
+    int state;
+    int n;                      /* pictures handed over (caller thread writes, under mu)       */
+    int issued, fetched;        /* steps issued to / fetched from the GPU (device thread only)  */
+    int set[2];                 /* result set of step t in set[t & 1]                           */
+    int64_t gop_index, frame0;  /* closed GOP number; frame number of its first picture         */
+} slot_t;
+
+typedef struct {
+    struct b2_encoder *h;
+    int device;
+    b2_engine_t *eng;
+    pthread_t thread;
+    int started;
+    pthread_cond_t cv;          /* pictures arrived / a GOP was closed on this GPU              */
+    slot_t *slots;
+} dev_t;
 
 struct b2_encoder {
     b2_param_t p;
-    int qp, S, L, mbw, mbh, nmb;
-    b2_engine_t *eng;
+    int qp, S, L, N, mbw, mbh, nmb;
+    int fmt;                    /* raw layout of the pictures in the device rings (B2_FMT_*)    */
+    dev_t dev[B2_MAX_DEVICES];
     b2h_entropy_t *ent;
     b2h_seq_t seq;
-    /* entropy worker pool: one frame per job, queued per batch in GPU completion order; each worker owns its neighbour-map
-     * scratch.  Frames of one GOP are independent for the entropy stage (contexts reset per slice), so frame t+1 of a GOP
-     * may be coded while frame t still is -- all workers stay busy even with fewer GOP slots than host cores. */
+    /* everything below is guarded by mu */
+    pthread_mutex_t mu;
+    pthread_cond_t cv_job, cv_space, cv_out;
     int nworkers;
     pthread_t workers[B2_MAX_WORKERS];
     b2h_entropy_t *went[B2_MAX_WORKERS];
     uint8_t *wscratch[B2_MAX_WORKERS];
-    pthread_mutex_t mu;
-    pthread_cond_t cv_job, cv_done;
-    job_t *jobs;
-    int njobs, next_job, done_jobs, job_error, stop;
-    int64_t *pts;              /* [2][S*L] pts of the frames of the two batch halves */
-    int batch_frames;          /* frames gathered into the current half */
-    /* asynchronous batch pipeline (S > 1): the caller gathers batch k+1 into one half of the input ring while the pipeline
-     * thread drives batch k (GPU steps + entropy workers) out of the other half */
-    pthread_t pipe_thread;
-    int pipe_started, pipe_busy, pipe_stop, pipe_error;
-    pthread_mutex_t pmu;
-    pthread_cond_t pcv_submit, pcv_done;
-    int gather_half, sub_half, sub_frames;
-    int inflight;              /* frames handed to the pipeline thread that are not in the fifo yet */
-    outframe_t *fifo;          /* finished frames in display order */
-    int fifo_cap, fifo_head, fifo_count;
-    int gop_pos;               /* zero-delay mode: position inside the current GOP */
-    outframe_t *outq;          /* [S*L] finished frames of the last processed batch, display order */
-    int out_head, out_count;
+    job_t *jobs;                /* ring */
+    int job_cap, job_head, job_count, job_limit;
+    outframe_t *fifo;           /* frame f lives in fifo[f % fifo_cap]                          */
+    int fifo_cap;
+    int64_t frames_in, frames_out, cur_gop;
+    int g_dev, g_slot;          /* slot of the GOP being gathered, -1: none                     */
+    int error, stop;
+    /* zero-delay mode */
+    int gop_pos;
     int64_t gops_done;
+    outframe_t zout;
     uint8_t *scratch;
     size_t scratch_cap;
-    uint8_t *ret_buf;          /* payload of the frame returned by the last call */
+    uint8_t *ret_buf;           /* payload of the frame returned by the last call */
     b2_nal_t nals[3];
 };
 
+/* ---- picture registry (b2h_picture.h) ------------------------------------------------------------------------------ */
+static pthread_mutex_t pic_mu = PTHREAD_MUTEX_INITIALIZER;
+static b2h_picrec_t *pic_list;
+
+b2h_picrec_t *b2h_picture_find(const uint8_t *plane0)
+{
+    if (!plane0) return NULL;
+    pthread_mutex_lock(&pic_mu);
+    b2h_picrec_t *r = pic_list;
+    while (r && r->base != plane0) r = r->next;
+    pthread_mutex_unlock(&pic_mu);
+    return r;
+}
+
+uint8_t *b2h_picture_stage(b2h_picrec_t *r, size_t bytes)
+{
+    if (r->stage_bytes < bytes) {
+        b2_pinned_free(r->stage);
+        r->stage = (uint8_t *)b2_pinned_alloc(bytes);
+        r->stage_bytes = r->stage ? bytes : 0;
+    }
+    return r->stage;
+}
+
+int b2_picture_alloc(b2_picture_t *pic, int i_csp, int i_width, int i_height)
+{
+    if (!pic || i_csp != B2_CSP_I420 || i_width < 2 || i_height < 2) return -1;
+    memset(pic, 0, sizeof(*pic));
+    int cw = (i_width + 1) / 2, ch = (i_height + 1) / 2;
+    size_t ny = (size_t)i_width * i_height, nc = (size_t)cw * ch;
+    b2h_picrec_t *r = (b2h_picrec_t *)calloc(1, sizeof(*r));
+    uint8_t *buf = r ? (uint8_t *)b2_pinned_alloc(ny + 2 * nc) : NULL;   /* pinned: H2D copies run at full PCIe rate */
+    if (!buf) { free(r); return -1; }
+    pic->img.i_csp = i_csp; pic->img.i_plane = 3;
+    pic->img.plane[0] = buf; pic->img.plane[1] = buf + ny; pic->img.plane[2] = buf + ny + nc;
+    pic->img.i_stride[0] = i_width; pic->img.i_stride[1] = cw; pic->img.i_stride[2] = cw;
+    pic->opaque = buf;
+    r->base = buf; r->bytes = ny + 2 * nc; r->width = i_width; r->height = i_height;
+    pthread_mutex_lock(&pic_mu);
+    r->next = pic_list; pic_list = r;
+    pthread_mutex_unlock(&pic_mu);
+    return 0;
+}
+
+void b2_picture_clean(b2_picture_t *pic)
+{
+    if (!pic) return;
+    pthread_mutex_lock(&pic_mu);
+    b2h_picrec_t **pp = &pic_list, *r = NULL;
+    while (*pp && (*pp)->base != pic->opaque) pp = &(*pp)->next;
+    if (*pp) { r = *pp; *pp = r->next; }
+    pthread_mutex_unlock(&pic_mu);
+    if (r) { b2_pinned_free(r->stage); free(r); }
+    b2_pinned_free(pic->opaque);
+    memset(pic, 0, sizeof(*pic));
+}
+
+/* ---- parameters ---------------------------------------------------------------------------------------------------- */
 static const struct { const char *name; int merange, subpel, intra_in_p; } presets[] = {
     {"ultrafast", 16, 0, 0}, {"superfast", 16, 1, 1}, {"veryfast", 16, 1, 1}, {"faster", 16, 1, 1}, {"fast", 16, 1, 1},
     {"medium", 16, 1, 1},    {"slow", 32, 1, 1},      {"slower", 32, 1, 1},   {"veryslow", 32, 1, 1}, {"placebo", 32, 1, 1}};
@@ -92,8 +171,8 @@ int b2_param_default_preset(b2_param_t *p, const char *preset, const char *tune)
     p->vui.i_sar_width = p->vui.i_sar_height = 0;
     p->rc.i_rc_method = B2_RC_CRF; p->rc.f_rf_constant = 23.0f; p->rc.i_qp_constant = 26;
     p->b_annexb = 1;
-    /* 16 closed GOPs in lock-step: a step of only 8 frames leaves the GPU waiting on the per-frame latency chain (K7 / K8) */
-    p->i_keyint_max = 32; p->i_gop_slots = 16; p->i_device = 0; p->i_csp_in = B2_FMT_YUV420P;
+    /* 16 closed GOPs in flight per GPU: fewer leave the GPU waiting on the per-frame latency chain (K7 / K8) */
+    p->i_keyint_max = 32; p->i_gop_slots = 16; p->i_device = 0; p->i_devices = 0; p->i_csp_in = B2_FMT_YUV420P;
     p->b_deblocking_filter = 1;
     p->b_cabac = 1;                      /* x264 default at every preset but ultrafast */
     p->b_transform_8x8 = 0;
@@ -107,10 +186,23 @@ int b2_param_default_preset(b2_param_t *p, const char *preset, const char *tune)
     if (!found) { fprintf(stderr, "b2enc: invalid preset '%s'\n", preset); return -1; }
     if (preset && !strcmp(preset, "ultrafast")) { p->b_cabac = 0; p->b_deblocking_filter = 0; }     /* as x264's ultrafast */
     if (tune) {
-        int ok = 0;
-        for (unsigned i = 0; i < sizeof(tunes) / sizeof(tunes[0]); i++) ok |= !strcmp(tune, tunes[i]);
-        if (!ok) { fprintf(stderr, "b2enc: invalid tune '%s'\n", tune); return -1; }
-        if (!strcmp(tune, "zerolatency")) p->i_gop_slots = 1;
+        /* like x264: several tunes separated by ',', './' or ' ' */
+        char buf[128];
+        if (strlen(tune) >= sizeof(buf)) { fprintf(stderr, "b2enc: invalid tune '%s'\n", tune); return -1; }
+        strcpy(buf, tune);
+        char *save = NULL;
+        for (char *tok = strtok_r(buf, ",./ ", &save); tok; tok = strtok_r(NULL, ",./ ", &save)) {
+            int ok = 0;
+            for (unsigned i = 0; i < sizeof(tunes) / sizeof(tunes[0]); i++) ok |= !strcmp(tok, tunes[i]);
+            if (!ok) { fprintf(stderr, "b2enc: invalid tune '%s'\n", tok); return -1; }
+            if (!strcmp(tok, "zerolatency")) p->i_gop_slots = 1;
+            /* x264: film = deblock -1:-1, animation = 1:1, grain = -2:-2, stillimage = -3:-3 (the psy settings of those
+             * tunes have no counterpart in a constant-QP, non-RD encoder) */
+            if (!strcmp(tok, "film")) p->i_deblocking_filter_alphac0 = p->i_deblocking_filter_beta = -1;
+            if (!strcmp(tok, "animation")) p->i_deblocking_filter_alphac0 = p->i_deblocking_filter_beta = 1;
+            if (!strcmp(tok, "grain")) p->i_deblocking_filter_alphac0 = p->i_deblocking_filter_beta = -2;
+            if (!strcmp(tok, "stillimage")) p->i_deblocking_filter_alphac0 = p->i_deblocking_filter_beta = -3;
+        }
     }
     return 0;
 }
@@ -127,30 +219,19 @@ int b2_param_apply_profile(b2_param_t *p, const char *profile)
     return -1;
 }
 
-int b2_picture_alloc(b2_picture_t *pic, int i_csp, int i_width, int i_height)
-{
-    if (!pic || i_csp != B2_CSP_I420 || i_width < 2 || i_height < 2) return -1;
-    memset(pic, 0, sizeof(*pic));
-    int cw = (i_width + 1) / 2, ch = (i_height + 1) / 2;
-    size_t ny = (size_t)i_width * i_height, nc = (size_t)cw * ch;
-    uint8_t *buf = (uint8_t *)b2_pinned_alloc(ny + 2 * nc);          /* pinned: H2D copies run at full PCIe rate */
-    if (!buf) return -1;
-    pic->img.i_csp = i_csp; pic->img.i_plane = 3;
-    pic->img.plane[0] = buf; pic->img.plane[1] = buf + ny; pic->img.plane[2] = buf + ny + nc;
-    pic->img.i_stride[0] = i_width; pic->img.i_stride[1] = cw; pic->img.i_stride[2] = cw;
-    pic->opaque = buf;
-    return 0;
-}
-
-void b2_picture_clean(b2_picture_t *pic)
-{
-    if (!pic) return;
-    b2_pinned_free(pic->opaque);
-    memset(pic, 0, sizeof(*pic));
-}
-
+/* ---- open / close -------------------------------------------------------------------------------------------------- */
 static void *worker_main(void *arg);
-static void *pipe_main(void *arg);
+static void *dev_main(void *arg);
+
+static int device_count_wanted(const b2_param_t *p)
+{
+    int n = p->i_devices;
+    if (n <= 0) {                                        /* an unmodified av_encode.c cannot set the field: environment */
+        const char *e = getenv("B2ENC_DEVICES");
+        n = e ? atoi(e) : 1;
+    }
+    return n < 1 ? 1 : n;
+}
 
 b2_t *b2_encoder_open(b2_param_t *p)
 {
@@ -158,46 +239,94 @@ b2_t *b2_encoder_open(b2_param_t *p)
     b2_t *h = (b2_t *)calloc(1, sizeof(*h));
     if (!h) return NULL;
     h->p = *p;
+    h->g_slot = -1;
     int qp = p->rc.i_rc_method == B2_RC_CQP ? p->rc.i_qp_constant : (int)(p->rc.f_rf_constant + 0.5f);
+    if (qp < 10 || qp > 51)
+        fprintf(stderr, "b2enc: quality %d is outside the supported constant-QP range, using %d\n", qp, qp < 10 ? 10 : 51);
     h->qp = qp < 10 ? 10 : (qp > 51 ? 51 : qp);      /* CRF is mapped to a constant QP (north_star: fixed QP) */
     h->S = p->i_gop_slots > 0 ? p->i_gop_slots : 1;
     h->L = p->i_keyint_max > 0 ? p->i_keyint_max : 32;
+    h->N = h->S == 1 ? 1 : device_count_wanted(p);
+    h->fmt = p->i_csp_in;
+    const int ndev = b2_device_count();
+    if (ndev <= 0) { fprintf(stderr, "b2enc: no CUDA device; the encode stage has no CPU fallback\n"); free(h); return NULL; }
+    if (h->N > B2_MAX_DEVICES) h->N = B2_MAX_DEVICES;
+    if (p->i_device < 0 || p->i_device + h->N > ndev) {
+        fprintf(stderr, "b2enc: devices %d..%d requested, %d visible\n", p->i_device, p->i_device + h->N - 1, ndev);
+        free(h);
+        return NULL;
+    }
+    pthread_mutex_init(&h->mu, NULL);
+    pthread_cond_init(&h->cv_job, NULL); pthread_cond_init(&h->cv_space, NULL); pthread_cond_init(&h->cv_out, NULL);
     b2_engine_cfg_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.device = p->i_device; cfg.width = p->i_width; cfg.height = p->i_height; cfg.slots = h->S;
-    cfg.in_fmt = p->i_csp_in; cfg.in_ring = h->S == 1 ? 1 : 2 * h->L; cfg.merange = p->i_merange ? p->i_merange : 16; cfg.qp = h->qp;
+    cfg.width = p->i_width; cfg.height = p->i_height;
+    cfg.in_fmt = p->i_csp_in; cfg.merange = p->i_merange ? p->i_merange : 16; cfg.qp = h->qp;
     cfg.subpel = p->b_subpel; cfg.intra_in_p = p->b_intra_in_p; cfg.profile = 0; cfg.deblock = p->b_deblocking_filter;
+    cfg.deblock_alpha = p->i_deblocking_filter_alphac0; cfg.deblock_beta = p->i_deblocking_filter_beta;
     cfg.transform8x8 = p->b_transform_8x8 != 0;
     cfg.partitions = p->b_partitions < 0 ? 0 : (p->b_partitions > 2 ? 2 : p->b_partitions);
-    cfg.pack_levels = 1;                              /* only blocks with non-zero levels cross PCIe (K9) */
-    h->eng = b2_engine_create(&cfg);
-    if (!h->eng) { free(h); return NULL; }
+    cfg.pack_levels = 1;                              /* only blocks with a non-zero level cross PCIe (K9) */
+    /* every GOP slot holds its GOP's raw pictures on the device: shrink the slot count to what the GPU can hold */
+    {
+        const size_t w16 = ((size_t)p->i_width + 15) & ~(size_t)15, h16 = ((size_t)p->i_height + 15) & ~(size_t)15;
+        const size_t per_slot = (size_t)h->L * w16 * h16 * 3 + 16 * (w16 + 128) * (h16 + 128);      /* ring (<= 3 B/px) + planes + results */
+        size_t free_b = 0, total_b = 0;
+        for (int d = 0; d < h->N && h->S > 1; d++) {
+            if (b2_device_mem_info(p->i_device + d, &free_b, &total_b)) continue;
+            int fit = (int)(free_b * 8 / 10 / per_slot);
+            if (fit < 2) {
+                fprintf(stderr, "b2enc: keyint %d x %dx%d needs %.1f GB per GOP slot, device %d has %.1f GB free\n", h->L,
+                        p->i_width, p->i_height, per_slot / 1e9, p->i_device + d, free_b / 1e9);
+                b2_encoder_close(h);
+                return NULL;
+            }
+            if (fit < h->S) {
+                fprintf(stderr, "b2enc: %d GOP slots of %d frames do not fit device %d, using %d\n", h->S, h->L, p->i_device + d, fit);
+                h->S = fit;
+            }
+        }
+    }
+    cfg.slots = h->S; cfg.streams = h->S;             /* one stream group per slot: every GOP advances on its own */
+    cfg.in_ring = h->S == 1 ? 1 : h->L;
+    for (int d = 0; d < h->N; d++) {
+        dev_t *dv = &h->dev[d];
+        dv->h = h; dv->device = p->i_device + d;
+        cfg.device = dv->device;
+        dv->eng = b2_engine_create(&cfg);
+        dv->slots = (slot_t *)calloc((size_t)h->S, sizeof(slot_t));
+        pthread_cond_init(&dv->cv, NULL);
+        if (!dv->eng || !dv->slots) { b2_encoder_close(h); return NULL; }
+    }
     int w16, h16;
-    b2_engine_geometry(h->eng, &h->mbw, &h->mbh, &w16, &h16);
+    b2_engine_geometry(h->dev[0].eng, &h->mbw, &h->mbh, &w16, &h16);
     h->nmb = h->mbw * h->mbh;
     h->ent = b2h_entropy_create(h->mbw, h->mbh);
     h->seq.width = p->i_width; h->seq.height = p->i_height; h->seq.fps_num = p->i_fps_num; h->seq.fps_den = p->i_fps_den;
     h->seq.sar_w = p->vui.i_sar_width; h->seq.sar_h = p->vui.i_sar_height; h->seq.qp = h->qp;
     h->seq.deblock = p->b_deblocking_filter;
+    h->seq.deblock_alpha = p->i_deblocking_filter_alphac0; h->seq.deblock_beta = p->i_deblocking_filter_beta;
     h->seq.cabac = p->b_cabac != 0; h->seq.transform8x8 = p->b_transform_8x8 != 0;
-    h->pts = (int64_t *)calloc((size_t)2 * h->S * h->L, sizeof(int64_t));
-    h->fifo_cap = 3 * h->S * h->L;
-    h->fifo = (outframe_t *)calloc((size_t)h->fifo_cap, sizeof(outframe_t));
-    pthread_mutex_init(&h->pmu, NULL); pthread_cond_init(&h->pcv_submit, NULL); pthread_cond_init(&h->pcv_done, NULL);
-    h->outq = (outframe_t *)calloc((size_t)h->S * h->L, sizeof(outframe_t));
     h->scratch_cap = (size_t)h->nmb * 3072 + 65536;
     h->scratch = (uint8_t *)malloc(h->scratch_cap);
-    if (!h->ent || !h->pts || !h->outq || !h->scratch || !h->fifo) { b2_encoder_close(h); return NULL; }
-    pthread_mutex_init(&h->mu, NULL); pthread_cond_init(&h->cv_job, NULL); pthread_cond_init(&h->cv_done, NULL);
+    if (!h->ent || !h->scratch) { b2_encoder_close(h); return NULL; }
     if (h->S > 1) {
         long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
-        int nw = B2_MAX_WORKERS;                         /* frames, not GOPs, are the unit of work: use the cores there are */
-        if (ncpu > 0 && nw > ncpu) nw = (int)ncpu;
-        h->jobs = (job_t *)calloc((size_t)h->S * h->L, sizeof(job_t));
+        int nw = ncpu > 2 ? (int)ncpu - 1 : 1;          /* frames, not GOPs, are the unit of work: use the cores there are */
+        if (nw > B2_MAX_WORKERS) nw = B2_MAX_WORKERS;
+        const char *e = getenv("B2ENC_ENTROPY_THREADS");
+        if (e && atoi(e) > 0) nw = atoi(e) > B2_MAX_WORKERS ? B2_MAX_WORKERS : atoi(e);
+        h->job_limit = 4 * nw > 64 ? 4 * nw : 64;
+        /* frames in flight: N x S slots of L pictures + what waits for / sits in the entropy stage or for the caller */
+        h->fifo_cap = (h->N * h->S + 2) * h->L + h->job_limit;
+        h->job_cap = h->fifo_cap;
+        h->fifo = (outframe_t *)calloc((size_t)h->fifo_cap, sizeof(outframe_t));
+        h->jobs = (job_t *)calloc((size_t)h->job_cap, sizeof(job_t));
+        if (!h->fifo || !h->jobs) { b2_encoder_close(h); return NULL; }
         for (int i = 0; i < nw; i++) {
             h->went[i] = b2h_entropy_create(h->mbw, h->mbh);
             h->wscratch[i] = (uint8_t *)malloc(h->scratch_cap);
-            if (!h->jobs || !h->went[i] || !h->wscratch[i]) { b2_encoder_close(h); return NULL; }
+            if (!h->went[i] || !h->wscratch[i]) { b2_encoder_close(h); return NULL; }
         }
         pthread_mutex_lock(&h->mu);                      /* workers look themselves up in h->workers[] under the lock */
         for (int i = 0; i < nw; i++) {
@@ -205,8 +334,11 @@ b2_t *b2_encoder_open(b2_param_t *p)
             h->nworkers++;
         }
         pthread_mutex_unlock(&h->mu);
-        if (pthread_create(&h->pipe_thread, NULL, pipe_main, h)) { b2_encoder_close(h); return NULL; }
-        h->pipe_started = 1;
+        if (h->nworkers == 0) { b2_encoder_close(h); return NULL; }
+        for (int d = 0; d < h->N; d++) {
+            if (pthread_create(&h->dev[d].thread, NULL, dev_main, &h->dev[d])) { b2_encoder_close(h); return NULL; }
+            h->dev[d].started = 1;
+        }
     }
     return h;
 }
@@ -214,54 +346,44 @@ b2_t *b2_encoder_open(b2_param_t *p)
 void b2_encoder_close(b2_t *h)
 {
     if (!h) return;
-    if (h->pipe_started) {
-        pthread_mutex_lock(&h->pmu);
-        h->pipe_stop = 1;
-        pthread_cond_broadcast(&h->pcv_submit);
-        pthread_mutex_unlock(&h->pmu);
-        pthread_join(h->pipe_thread, NULL);
-    }
+    pthread_mutex_lock(&h->mu);
+    h->stop = 1;
+    pthread_cond_broadcast(&h->cv_job); pthread_cond_broadcast(&h->cv_space); pthread_cond_broadcast(&h->cv_out);
+    for (int d = 0; d < h->N; d++)
+        if (h->dev[d].started) pthread_cond_broadcast(&h->dev[d].cv);
+    pthread_mutex_unlock(&h->mu);
+    for (int d = 0; d < h->N; d++)
+        if (h->dev[d].started) pthread_join(h->dev[d].thread, NULL);
+    for (int i = 0; i < h->nworkers; i++) pthread_join(h->workers[i], NULL);
+    for (int i = 0; i < B2_MAX_WORKERS; i++) { b2h_entropy_destroy(h->went[i]); free(h->wscratch[i]); }
+    if (h->jobs)
+        for (int i = 0; i < h->job_count; i++) free(h->jobs[(h->job_head + i) % h->job_cap].res);     /* queued, never coded */
+    free(h->jobs);
     if (h->fifo)
         for (int i = 0; i < h->fifo_cap; i++) free(h->fifo[i].data);
     free(h->fifo);
-    if (h->nworkers > 0) {
-        pthread_mutex_lock(&h->mu);
-        h->stop = 1;
-        pthread_cond_broadcast(&h->cv_job);
-        pthread_mutex_unlock(&h->mu);
-        for (int i = 0; i < h->nworkers; i++) pthread_join(h->workers[i], NULL);
-    }
-    for (int i = 0; i < B2_MAX_WORKERS; i++) { b2h_entropy_destroy(h->went[i]); free(h->wscratch[i]); }
-    if (h->jobs)
-        for (int i = h->next_job; i < h->njobs; i++) free(h->jobs[i].res);          /* frames queued but never coded (error paths) */
-    free(h->jobs);
-    if (h->outq)
-        for (int i = 0; i < h->S * h->L; i++) free(h->outq[i].data);
-    free(h->outq); free(h->pts); free(h->scratch); free(h->ret_buf);
+    free(h->zout.data); free(h->scratch); free(h->ret_buf);
     b2h_entropy_destroy(h->ent);
-    b2_engine_destroy(h->eng);
+    for (int d = 0; d < B2_MAX_DEVICES; d++) {
+        if (h->dev[d].eng) b2_engine_destroy(h->dev[d].eng);
+        if (h->dev[d].slots) { free(h->dev[d].slots); pthread_cond_destroy(&h->dev[d].cv); }
+    }
+    pthread_mutex_destroy(&h->mu);
+    pthread_cond_destroy(&h->cv_job); pthread_cond_destroy(&h->cv_space); pthread_cond_destroy(&h->cv_out);
     free(h);
 }
 
-/* picture -> engine input ring: DMA from the page-locked picture when it is one (no host copy), else through the pinned staging */
-static int put_picture(b2_t *h, int slot, int ring, const b2_picture_t *pic)
-{
-    int rc = b2_engine_put_frame_direct(h->eng, slot, ring, (const uint8_t *const *)pic->img.plane, pic->img.i_stride);
-    if (rc > 0) rc = b2_engine_put_frame(h->eng, slot, ring, (const uint8_t *const *)pic->img.plane, pic->img.i_stride);
-    return rc;
-}
-
+/* ---- entropy stage ------------------------------------------------------------------------------------------------- */
 static void put_prefix(uint8_t *d, int annexb, size_t nal_size)
 {
     if (annexb) { d[0] = 0; d[1] = 0; d[2] = 0; d[3] = 1; }
     else { d[0] = (uint8_t)(nal_size >> 24); d[1] = (uint8_t)(nal_size >> 16); d[2] = (uint8_t)(nal_size >> 8); d[3] = (uint8_t)nal_size; }
 }
 
-/* entropy-code one frame's results into outq[qi] */
+/* entropy-code one frame's results into *o (data, size, NAL table, key) */
 static int finish_frame(b2_t *h, b2h_entropy_t *ent, uint8_t *s, const b2_mbinfo_t *info, const uint8_t *packed, size_t packed_bytes,
-                        int qi, int t, int64_t gop_index)
+                        int t, int64_t gop_index, outframe_t *o)
 {
-    outframe_t *o = &h->outq[qi];
     size_t pos = 0;
     o->nal_count = 0;
     const int is_idr = t == 0;
@@ -303,143 +425,154 @@ static void *worker_main(void *arg)
     for (int i = 0; i < h->nworkers; i++)
         if (pthread_equal(h->workers[i], pthread_self())) me = i;
     for (;;) {
-        while (!h->stop && h->next_job >= h->njobs) pthread_cond_wait(&h->cv_job, &h->mu);
+        while (!h->stop && h->job_count == 0) pthread_cond_wait(&h->cv_job, &h->mu);
         if (h->stop) break;
-        job_t j = h->jobs[h->next_job++];
+        job_t j = h->jobs[h->job_head];
+        h->job_head = (h->job_head + 1) % h->job_cap;
+        h->job_count--;
+        pthread_cond_signal(&h->cv_space);
         pthread_mutex_unlock(&h->mu);
+        outframe_t o;
+        memset(&o, 0, sizeof(o));
         int rc = finish_frame(h, h->went[me], h->wscratch[me], (const b2_mbinfo_t *)j.res, j.res + (size_t)h->nmb * sizeof(b2_mbinfo_t),
-                              j.packed_bytes, j.qi, j.t, j.gop_index);
+                              j.packed_bytes, j.t, j.gop_index, &o);
         free(j.res);
         pthread_mutex_lock(&h->mu);
-        if (rc) h->job_error = 1;
-        h->done_jobs++;
-        pthread_cond_broadcast(&h->cv_done);
-    }
-    pthread_mutex_unlock(&h->mu);
-    return NULL;
-}
-
-/* queue frame t of GOPs [0,nt) for the worker pool (or code it inline when there is none): the result set behind `ticket`
- * is copied out, so it may be overwritten as soon as this returns */
-static int entropy_step(b2_t *h, int t, int nt, int ticket, const int64_t *pts)
-{
-    for (int g = 0; g < nt; g++) {
-        const int qi = g * h->L + t;
-        const b2_mbinfo_t *info = b2_engine_info_ticket(h->eng, ticket, g);
-        size_t packed_bytes = 0;
-        const uint8_t *packed = b2_engine_packed_ticket(h->eng, ticket, g, &packed_bytes);
-        if (!info || !packed) return -1;
-        h->outq[qi].pts = pts[qi];
-        if (h->nworkers == 0) {
-            if (finish_frame(h, h->ent, h->scratch, info, packed, packed_bytes, qi, t, h->gops_done + g)) return -1;
-            continue;
+        if (rc) { h->error = 1; free(o.data); }
+        else {
+            outframe_t *dst = &h->fifo[j.frame % h->fifo_cap];
+            o.pts = dst->pts;                              /* written by the caller's thread when the picture came in */
+            free(dst->data);
+            *dst = o;
+            dst->ready = 1;
         }
-        const size_t ni = (size_t)h->nmb * sizeof(b2_mbinfo_t);
-        job_t j = {qi, g, t, h->gops_done + g, (uint8_t *)malloc(ni + packed_bytes + 1), packed_bytes};
-        if (!j.res) return -1;
-        memcpy(j.res, info, ni);
-        memcpy(j.res + ni, packed, packed_bytes);
-        pthread_mutex_lock(&h->mu);
-        h->jobs[h->njobs++] = j;
-        pthread_cond_signal(&h->cv_job);
-        pthread_mutex_unlock(&h->mu);
+        pthread_cond_broadcast(&h->cv_out);
     }
-    return 0;
-}
-
-/* wait until every queued frame of the batch is coded, then reset the queue */
-static int entropy_drain(b2_t *h)
-{
-    if (h->nworkers == 0) return 0;
-    pthread_mutex_lock(&h->mu);
-    while (h->done_jobs < h->njobs) pthread_cond_wait(&h->cv_done, &h->mu);
-    h->njobs = 0; h->next_job = 0; h->done_jobs = 0;
-    const int err = h->job_error;
     pthread_mutex_unlock(&h->mu);
-    return err ? -1 : 0;
-}
-
-static int issue_step(b2_t *h, int half, int t, int nt)
-{
-    const int ring = h->S == 1 ? 0 : half * h->L + t;
-    if (b2_engine_h2d(h->eng, 0, nt, ring)) return -1;
-    if (b2_engine_encode(h->eng, t == 0 ? B2_FRAME_I : B2_FRAME_P, nt, ring)) return -1;
-    return b2_engine_d2h(h->eng, nt);
-}
-
-/* advance one gathered batch (possibly partial) through the GPU and the entropy stage: while the host entropy-codes
- * frame t of every GOP, the GPU already encodes frame t+1 (result sets are double buffered).  Runs on the pipeline thread. */
-static int process_batch(b2_t *h, int half, int n)
-{
-    const int L = h->L;
-    const int ngop = (n + L - 1) / L, last_len = n - (ngop - 1) * L;
-    const int64_t *pts = h->pts + (size_t)half * h->S * L;
-    int nt = ngop;                                         /* GOPs that have a frame 0 */
-    if (issue_step(h, half, 0, nt)) return -1;
-    for (int t = 0; t < L && nt > 0; t++) {
-        const int ticket = b2_engine_ticket(h->eng);
-        const int nt_next = t + 1 < L ? (t + 1 < last_len ? ngop : ngop - 1) : 0;     /* a prefix of the slots */
-        if (b2_engine_wait_ticket(h->eng, ticket)) return -1;
-        if (nt_next > 0 && issue_step(h, half, t + 1, nt_next)) return -1;
-        if (entropy_step(h, t, nt, ticket, pts)) return -1;
-        nt = nt_next;
-    }
-    if (entropy_drain(h)) return -1;
-    if (b2_engine_sync(h->eng)) return -1;
-    h->gops_done += ngop;
-    pthread_mutex_lock(&h->pmu);                          /* hand the frames over in display order */
-    for (int i = 0; i < n; i++) {
-        outframe_t *dst = &h->fifo[(h->fifo_head + h->fifo_count) % h->fifo_cap];
-        free(dst->data);
-        *dst = h->outq[i];
-        h->outq[i].data = NULL;
-        h->fifo_count++;
-    }
-    h->inflight -= n;
-    pthread_mutex_unlock(&h->pmu);
-    return 0;
-}
-
-static void *pipe_main(void *arg)
-{
-    b2_t *h = (b2_t *)arg;
-    pthread_mutex_lock(&h->pmu);
-    for (;;) {
-        while (!h->pipe_busy && !h->pipe_stop) pthread_cond_wait(&h->pcv_submit, &h->pmu);
-        if (h->pipe_stop) break;
-        const int half = h->sub_half, n = h->sub_frames;
-        pthread_mutex_unlock(&h->pmu);
-        const int rc = process_batch(h, half, n);
-        pthread_mutex_lock(&h->pmu);
-        if (rc) h->pipe_error = 1;
-        h->pipe_busy = 0;
-        pthread_cond_broadcast(&h->pcv_done);
-    }
-    pthread_mutex_unlock(&h->pmu);
     return NULL;
 }
 
-/* hand the gathered half to the pipeline thread (waits until it has finished the previous batch) and gather into the other */
-static void submit_batch(b2_t *h)
+/* ---- per-GPU thread ------------------------------------------------------------------------------------------------ */
+static void fail(b2_t *h)
 {
-    pthread_mutex_lock(&h->pmu);
-    while (h->pipe_busy) pthread_cond_wait(&h->pcv_done, &h->pmu);
-    h->sub_half = h->gather_half; h->sub_frames = h->batch_frames;
-    h->inflight += h->batch_frames;
-    h->pipe_busy = 1;
-    pthread_cond_signal(&h->pcv_submit);
-    pthread_mutex_unlock(&h->pmu);
-    h->gather_half ^= 1;
-    h->batch_frames = 0;
+    pthread_mutex_lock(&h->mu);
+    h->error = 1;
+    pthread_cond_broadcast(&h->cv_out);
+    pthread_mutex_unlock(&h->mu);
 }
 
+/* copy step t's result set of slot s out of the pinned buffers and queue it for the entropy workers */
+static int fetch_step(dev_t *dv, int s, int t, int set)
+{
+    b2_t *h = dv->h;
+    slot_t *sl = &dv->slots[s];
+    const b2_mbinfo_t *info = b2_engine_info_set(dv->eng, set, s);
+    size_t packed_bytes = 0;
+    const uint8_t *packed = b2_engine_packed_set(dv->eng, set, s, &packed_bytes);
+    if (!info || !packed) return -1;
+    const size_t ni = (size_t)h->nmb * sizeof(b2_mbinfo_t);
+    job_t j = {sl->frame0 + t, t, sl->gop_index, (uint8_t *)malloc(ni + packed_bytes + 1), packed_bytes};
+    if (!j.res) return -1;
+    memcpy(j.res, info, ni);
+    memcpy(j.res + ni, packed, packed_bytes);
+    pthread_mutex_lock(&h->mu);
+    while (!h->stop && h->job_count >= h->job_limit) pthread_cond_wait(&h->cv_space, &h->mu);   /* entropy stage is behind: let the GPU wait */
+    if (h->stop) { pthread_mutex_unlock(&h->mu); free(j.res); return 0; }
+    h->jobs[(h->job_head + h->job_count) % h->job_cap] = j;
+    h->job_count++;
+    pthread_cond_signal(&h->cv_job);
+    pthread_mutex_unlock(&h->mu);
+    return 0;
+}
+
+static int slot_runnable(const slot_t *sl)
+{
+    return sl->state != SLOT_FREE && (sl->issued < sl->n || sl->fetched < sl->issued || sl->state == SLOT_CLOSED);
+}
+
+static void *dev_main(void *arg)
+{
+    dev_t *dv = (dev_t *)arg;
+    b2_t *h = dv->h;
+    const int S = h->S;
+    int *n_snap = (int *)calloc((size_t)S, sizeof(int)), *st_snap = (int *)calloc((size_t)S, sizeof(int));
+    if (!n_snap || !st_snap) { fail(h); free(n_snap); free(st_snap); return NULL; }
+    int rr = 0;                                               /* which outstanding result set to sleep on: round robin */
+    for (;;) {
+        pthread_mutex_lock(&h->mu);
+        for (;;) {
+            int any = 0;
+            for (int s = 0; s < S; s++) any |= slot_runnable(&dv->slots[s]);
+            if (h->stop || h->error || any) break;
+            pthread_cond_wait(&dv->cv, &h->mu);
+        }
+        if (h->stop || h->error) { pthread_mutex_unlock(&h->mu); break; }
+        for (int s = 0; s < S; s++) { n_snap[s] = dv->slots[s].n; st_snap[s] = dv->slots[s].state; }
+        pthread_mutex_unlock(&h->mu);
+        int progress = 0, err = 0;
+        for (int s = 0; s < S && !err; s++) {
+            slot_t *sl = &dv->slots[s];
+            if (st_snap[s] == SLOT_FREE) continue;
+            const int n = n_snap[s];
+            for (;;) {
+                if (sl->fetched < sl->issued) {               /* has the oldest step in flight landed? */
+                    const int set = sl->set[sl->fetched & 1];
+                    const int r = b2_engine_group_done(dv->eng, s, set);
+                    if (r < 0) { err = 1; break; }
+                    if (r == 1) {
+                        if (fetch_step(dv, s, sl->fetched, set)) { err = 1; break; }
+                        sl->fetched++; progress = 1;
+                        continue;
+                    }
+                }
+                if (sl->issued < n && sl->issued - sl->fetched < 2) {      /* two steps in flight per slot (two result sets) */
+                    const int t = sl->issued;
+                    if (b2_engine_encode_group(dv->eng, s, t == 0 ? B2_FRAME_I : B2_FRAME_P, t) || b2_engine_d2h_group(dv->eng, s)) { err = 1; break; }
+                    sl->set[t & 1] = b2_engine_group_result_set(dv->eng, s);
+                    sl->issued++; progress = 1;
+                    continue;
+                }
+                break;
+            }
+            if (!err && st_snap[s] == SLOT_CLOSED && sl->fetched == n) {  /* the GOP has left the GPU: the slot is free again */
+                pthread_mutex_lock(&h->mu);
+                sl->state = SLOT_FREE;
+                pthread_cond_broadcast(&h->cv_out);
+                pthread_mutex_unlock(&h->mu);
+                progress = 1;
+            }
+        }
+        if (err) { fail(h); break; }
+        if (!progress) {                                      /* everything issued, nothing landed: sleep on a result set */
+            int waited = 0;
+            for (int k = 0; k < S && !waited; k++) {
+                const int s = (rr + k) % S;
+                slot_t *sl = &dv->slots[s];
+                if (st_snap[s] != SLOT_FREE && sl->fetched < sl->issued) {
+                    if (b2_engine_group_wait(dv->eng, s, sl->set[sl->fetched & 1])) { fail(h); free(n_snap); free(st_snap); return NULL; }
+                    rr = s + 1; waited = 1;
+                }
+            }
+            if (!waited) {                                    /* open slots waiting for their next picture */
+                pthread_mutex_lock(&h->mu);
+                int changed = 0;
+                for (int s = 0; s < S; s++) changed |= dv->slots[s].n != n_snap[s] || dv->slots[s].state != st_snap[s];
+                if (!changed && !h->stop && !h->error) pthread_cond_wait(&dv->cv, &h->mu);
+                pthread_mutex_unlock(&h->mu);
+            }
+        }
+    }
+    free(n_snap); free(st_snap);
+    return NULL;
+}
+
+/* ---- the calls of the reference's loops ------------------------------------------------------------------------------ */
 int b2_encoder_delayed_frames(b2_t *h)
 {
-    if (!h) return 0;
-    if (h->S == 1) return h->out_count;
-    pthread_mutex_lock(&h->pmu);
-    const int n = h->batch_frames + h->inflight + h->fifo_count;
-    pthread_mutex_unlock(&h->pmu);
+    if (!h || h->S == 1) return 0;
+    pthread_mutex_lock(&h->mu);
+    const int n = (int)(h->frames_in - h->frames_out);
+    pthread_mutex_unlock(&h->mu);
     return n;
 }
 
@@ -460,45 +593,132 @@ static int return_frame(b2_t *h, outframe_t *o, b2_nal_t **pp_nal, int *pi_nal, 
     return o->size;
 }
 
+/* where the picture's pixels are and in which layout: the I420 planes, or -- when b2_sws_scale deferred the conversion into
+ * this picture -- the staged raw source (b2h_picture.h) */
+static int picture_source(b2_t *h, b2_picture_t *pic, const uint8_t *src[4], int stride[4], int *fmt)
+{
+    b2h_picrec_t *r = b2h_picture_find(pic->img.plane[0]);
+    if (r && r->deferred) {
+        int rb[3], rows[3];
+        const int np = b2_fmt_layout(r->fmt, h->p.i_width, h->p.i_height, rb, rows);
+        if (!np || r->width != h->p.i_width || r->height != h->p.i_height) return -1;
+        const uint8_t *q = r->stage;
+        for (int k = 0; k < 4; k++) { src[k] = NULL; stride[k] = 0; }
+        for (int k = 0; k < np; k++) { src[k] = q; stride[k] = rb[k]; q += (size_t)rb[k] * rows[k]; }
+        *fmt = r->fmt;
+        r->deferred = 0;
+        return 0;
+    }
+    for (int k = 0; k < 4; k++) { src[k] = pic->img.plane[k]; stride[k] = pic->img.i_stride[k]; }
+    *fmt = r ? B2_FMT_YUV420P : h->p.i_csp_in;              /* b2_picture_alloc pictures are I420 by construction */
+    return 0;
+}
+
+/* the raw layout of the incoming pictures changed (first deferred picture, normally): drain, then re-shape the device rings */
+static int switch_format(b2_t *h, int fmt)
+{
+    if (h->S > 1) {
+        pthread_mutex_lock(&h->mu);
+        if (h->g_slot >= 0) {                                 /* close the GOP being gathered: it stays in the old layout */
+            h->dev[h->g_dev].slots[h->g_slot].state = SLOT_CLOSED;
+            pthread_cond_broadcast(&h->dev[h->g_dev].cv);
+            h->g_slot = -1; h->cur_gop++;
+        }
+        for (;;) {
+            int busy = 0;
+            for (int d = 0; d < h->N; d++)
+                for (int s = 0; s < h->S; s++) busy |= h->dev[d].slots[s].state != SLOT_FREE;
+            if (!busy || h->error) break;
+            pthread_cond_wait(&h->cv_out, &h->mu);
+        }
+        pthread_mutex_unlock(&h->mu);
+    }
+    for (int d = 0; d < h->N; d++)
+        if (b2_engine_set_input_format(h->dev[d].eng, fmt)) return -1;
+    h->fmt = fmt;
+    return 0;
+}
+
+static int encode_zero_delay(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, const uint8_t *src[4], const int stride[4], int64_t pts,
+                             b2_picture_t *pic_out)
+{
+    b2_engine_t *eng = h->dev[0].eng;
+    const int t = h->gop_pos;
+    if (b2_engine_put_picture(eng, 0, 0, src, stride)) return -1;
+    if (b2_engine_encode_group(eng, 0, t == 0 ? B2_FRAME_I : B2_FRAME_P, 0) || b2_engine_d2h_group(eng, 0)) return -1;
+    const int set = b2_engine_group_result_set(eng, 0);
+    if (b2_engine_group_wait(eng, 0, set)) return -1;
+    size_t packed_bytes = 0;
+    const uint8_t *packed = b2_engine_packed_set(eng, set, 0, &packed_bytes);
+    if (finish_frame(h, h->ent, h->scratch, b2_engine_info_set(eng, set, 0), packed, packed_bytes, t, h->gops_done, &h->zout)) return -1;
+    h->zout.pts = pts;
+    h->gop_pos = t + 1;
+    if (h->gop_pos == h->L) { h->gop_pos = 0; h->gops_done++; }
+    return return_frame(h, &h->zout, pp_nal, pi_nal, pic_out);
+}
+
 int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic_in, b2_picture_t *pic_out)
 {
     if (!h || !pp_nal || !pi_nal) return -1;
     *pi_nal = 0; *pp_nal = NULL;
-    if (h->S == 1) {
-        /* zero-delay mode: one slot, encode every picture as it arrives */
-        if (!pic_in) return 0;
-        const int t = h->gop_pos;
-        if (put_picture(h, 0, 0, pic_in)) return -1;
-        if (b2_engine_h2d(h->eng, 0, 1, 0) || b2_engine_encode(h->eng, t == 0 ? B2_FRAME_I : B2_FRAME_P, 1, 0) ||
-            b2_engine_d2h(h->eng, 1) || b2_engine_sync(h->eng))
-            return -1;
-        size_t packed_bytes = 0;
-        const uint8_t *packed = b2_engine_packed(h->eng, 0, &packed_bytes);
-        if (finish_frame(h, h->ent, h->scratch, b2_engine_info(h->eng, 0), packed, packed_bytes, 0, t, h->gops_done)) return -1;
-        h->outq[0].pts = pic_in->i_pts;
-        h->gop_pos = t + 1;
-        if (h->gop_pos == h->L) { h->gop_pos = 0; h->gops_done++; }
-        return return_frame(h, &h->outq[0], pp_nal, pi_nal, pic_out);
-    }
+    const uint8_t *src[4]; int stride[4], fmt = h->fmt;
     if (pic_in) {
-        const int idx = h->batch_frames, g = idx / h->L, t = idx % h->L;
-        if (put_picture(h, g, h->gather_half * h->L + t, pic_in)) return -1;
-        h->pts[(size_t)h->gather_half * h->S * h->L + idx] = pic_in->i_pts;
-        h->batch_frames++;
-        if (h->batch_frames == h->S * h->L) submit_batch(h);        /* full: the pipeline thread takes it, gathering goes on */
-    } else {
-        if (h->batch_frames > 0) submit_batch(h);                   /* flush: partial batch */
-        pthread_mutex_lock(&h->pmu);                                /* a flush call waits for its frame (av_encode.c:1076-1083) */
-        while (h->fifo_count == 0 && h->pipe_busy && !h->pipe_error) pthread_cond_wait(&h->pcv_done, &h->pmu);
-        pthread_mutex_unlock(&h->pmu);
+        if (picture_source(h, pic_in, src, stride, &fmt)) { fprintf(stderr, "b2enc: picture does not match the encoder's size\n"); return -1; }
+        if (fmt != h->fmt && switch_format(h, fmt)) return -1;
     }
-    pthread_mutex_lock(&h->pmu);
-    if (h->pipe_error) { pthread_mutex_unlock(&h->pmu); fprintf(stderr, "b2enc: encode pipeline failed\n"); return -1; }
-    if (h->fifo_count == 0) { pthread_mutex_unlock(&h->pmu); return 0; }
-    outframe_t o = h->fifo[h->fifo_head];
-    h->fifo[h->fifo_head].data = NULL;
-    h->fifo_head = (h->fifo_head + 1) % h->fifo_cap;
-    h->fifo_count--;
-    pthread_mutex_unlock(&h->pmu);
+    if (h->S == 1) return pic_in ? encode_zero_delay(h, pp_nal, pi_nal, src, stride, pic_in->i_pts, pic_out) : 0;
+
+    pthread_mutex_lock(&h->mu);
+    if (pic_in) {
+        /* never more than fifo_cap - 1 frames delayed: when the caller is that far ahead, this call waits for the oldest frame
+         * (returned below), like x264 blocks on its oldest frame thread */
+        while (!h->error && h->frames_in - h->frames_out >= h->fifo_cap - 1 && !h->fifo[h->frames_out % h->fifo_cap].ready)
+            pthread_cond_wait(&h->cv_out, &h->mu);
+        if (h->g_slot < 0) {                                  /* a new closed GOP: GPU k % N, any free slot there */
+            dev_t *dv = &h->dev[h->cur_gop % h->N];
+            int s = -1;
+            while (!h->error) {
+                for (int i = 0; i < h->S && s < 0; i++)
+                    if (dv->slots[i].state == SLOT_FREE) s = i;
+                if (s >= 0) break;
+                pthread_cond_wait(&h->cv_out, &h->mu);
+            }
+            if (s >= 0) {
+                slot_t *sl = &dv->slots[s];
+                sl->n = 0; sl->issued = 0; sl->fetched = 0; sl->gop_index = h->cur_gop; sl->frame0 = h->frames_in;
+                sl->state = SLOT_OPEN;
+                h->g_dev = (int)(h->cur_gop % h->N); h->g_slot = s;
+            }
+        }
+        if (h->error) { pthread_mutex_unlock(&h->mu); fprintf(stderr, "b2enc: encode pipeline failed\n"); return -1; }
+        dev_t *dv = &h->dev[h->g_dev];
+        slot_t *sl = &dv->slots[h->g_slot];
+        const int t = sl->n;
+        pthread_mutex_unlock(&h->mu);
+        /* picture -> ring entry t of the slot; returns when the picture has been read (av_encode.c:415, :545: it is refilled) */
+        if (b2_engine_put_picture(dv->eng, h->g_slot, t, src, stride)) { fail(h); return -1; }
+        pthread_mutex_lock(&h->mu);
+        outframe_t *f = &h->fifo[h->frames_in % h->fifo_cap];
+        f->pts = pic_in->i_pts; f->ready = 0;
+        sl->n = t + 1;
+        h->frames_in++;
+        if (sl->n == h->L) { sl->state = SLOT_CLOSED; h->g_slot = -1; h->cur_gop++; }
+        pthread_cond_signal(&dv->cv);
+    } else {
+        if (h->g_slot >= 0) {                                 /* flush: the GOP being gathered ends here */
+            h->dev[h->g_dev].slots[h->g_slot].state = SLOT_CLOSED;
+            pthread_cond_signal(&h->dev[h->g_dev].cv);
+            h->g_slot = -1; h->cur_gop++;
+        }
+        /* a flush call waits for its frame (av_encode.c:1076-1083) */
+        while (!h->error && h->frames_out < h->frames_in && !h->fifo[h->frames_out % h->fifo_cap].ready) pthread_cond_wait(&h->cv_out, &h->mu);
+    }
+    if (h->error) { pthread_mutex_unlock(&h->mu); fprintf(stderr, "b2enc: encode pipeline failed\n"); return -1; }
+    outframe_t *head = &h->fifo[h->frames_out % h->fifo_cap];
+    if (h->frames_out == h->frames_in || !head->ready) { pthread_mutex_unlock(&h->mu); return 0; }
+    outframe_t o = *head;
+    head->data = NULL; head->ready = 0;
+    h->frames_out++;
+    pthread_mutex_unlock(&h->mu);
     return return_frame(h, &o, pp_nal, pi_nal, pic_out);
 }

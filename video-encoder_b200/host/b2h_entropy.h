@@ -21,9 +21,10 @@ typedef struct {
     int fps_num, fps_den;
     int sar_w, sar_h;
     int qp;                     /* pic_init_qp (all slices use slice_qp_delta = 0) */
-    int deblock;                /* 1: disable_deblocking_filter_idc = 0 (filter on, offsets 0), 0: idc = 1 */
+    int deblock;                /* 1: disable_deblocking_filter_idc = 0 (filter on), 0: idc = 1            */
     int cabac;                  /* 1: entropy_coding_mode_flag = 1 (CABAC, Main profile), 0: CAVLC (Constrained Baseline) */
     int transform8x8;           /* 1: transform_8x8_mode_flag = 1 (High profile)                            */
+    int deblock_alpha, deblock_beta;   /* slice_alpha_c0_offset_div2 / slice_beta_offset_div2 (-6..6)          */
 } b2h_seq_t;
 
 typedef struct b2h_entropy b2h_entropy_t;   /* per-encoder scratch (neighbour maps) */
