@@ -145,6 +145,48 @@ def dropin_leg(b2enc, b2oracle, deblock, transform8x8, partitions, frames=1024, 
             "note": "entropy coding (CABAC) on the host cores is part of this call sequence and is its limiter; the encode stage itself is `e2e`"}
 
 
+def verify_final_state(eng, b2enc, b2oracle, rank, groups, ftype, last_step, args):
+    """After the timed regions (outside every timing): the first slot of every stream group is replayed on the CPU oracle from
+    the group's last I step to the last issued step, and its final per-MB decisions, packed levels and reconstruction on the
+    GPU must equal the oracle's bit for bit -- the state left behind by the exact pipelined path that was timed."""
+    import numpy as np
+    import sharding
+    from concurrent.futures import ThreadPoolExecutor
+    streams = sharding.slot_streams(rank, eng.slots)
+    prm = b2oracle.Params(QP, MERANGE, 1, 1, args.deblock, args.transform8x8, args.partitions)
+
+    def chain(g):
+        slot = groups[g][0]
+        s0 = max(s for s in range(last_step + 1) if ftype(s, g) == b2enc.FRAME_I)
+        prev = None; pmv = None
+        for s in range(s0, last_step + 1):
+            cur = b2oracle.OFrame(W, H).load(*b2oracle.synth_frame(W, H, s % RING, streams[slot])); rec = b2oracle.OFrame(W, H)
+            info, coef = b2oracle.encode_frame(prm, 0 if s == s0 else 1, cur, prev, rec, pmv)
+            pmv = np.zeros(info.size, b2oracle.MV); pmv["x"] = info["mvx"]; pmv["y"] = info["mvy"]
+            prev = rec
+        return slot, last_step + 1 - s0, info, coef, rec
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(min(len(groups), os.cpu_count() or 1)) as ex:
+        res = list(ex.map(chain, range(len(groups))))
+    bad = []
+    for slot, n, info_o, coef_o, rec in res:
+        info_g, _ = eng.results(slot)
+        ok = all(np.array_equal(info_g[f], info_o[f]) for f in info_o.dtype.names)
+        if args.pack_levels:
+            ok = ok and np.array_equal(eng.packed(slot), b2enc.pack_levels(info_o, coef_o))
+        else:
+            ok = ok and np.array_equal(eng.results(slot)[1]["blk"], coef_o["blk"])
+        ry, ru, rv = eng.recon(slot)
+        ok = ok and np.array_equal(ry, rec.y) and np.array_equal(ru, rec.u) and np.array_equal(rv, rec.v)
+        if not ok:
+            bad.append(slot)
+    return {"verified": not bad, "slots_checked": [r[0] for r in res], "frames_replayed_on_oracle": int(sum(r[1] for r in res)),
+            "mismatching_slots": bad, "seconds": round(time.perf_counter() - t0, 1),
+            "what": "final per-MB decisions, packed levels and reconstruction of the first slot of every stream group after the timed "
+                    "regions == CPU oracle replay from the group's last I step (bit-exact)"}
+
+
 def cpu_encode_gop(b2oracle, np, stream, n_p, times):
     """one closed GOP on one host thread: 1 I + n_p P frames through the oracle encode stage"""
     prm = b2oracle.Params(QP, MERANGE, 1, 1)
@@ -199,11 +241,16 @@ def run_reference(args):
         info, _ = b2oracle.encode_frame(prm, 0, cur, None, rec, None)
         state.append([rec, None, 1])
 
+    # GOP phases staggered over the threads like the GPU arm staggers its stream groups: over the run the I : P mix is the
+    # workload's 1 : GOP-1 (an I frame costs the CPU ~6x less than a P frame, so P-only steps would under-state it)
+    phase = [i * GOP // threads for i in range(threads)]
+
     def step(i):
         rec_prev, pmv, t = state[i]
+        is_i = (phase[i] + t) % GOP == 0
         cur = b2oracle.OFrame(W, H).load(*b2oracle.convert_to_i420("yuv420p", W, H, list(b2oracle.synth_frame(W, H, t % RING, i))))
         rec = b2oracle.OFrame(W, H)
-        info, _ = b2oracle.encode_frame(prm, 1, cur, rec_prev, rec, pmv)
+        info, _ = b2oracle.encode_frame(prm, 0 if is_i else 1, cur, None if is_i else rec_prev, rec, None if is_i else pmv)
         pmv = np.zeros(info.size, b2oracle.MV); pmv["x"] = info["mvx"]; pmv["y"] = info["mvy"]
         state[i] = [rec, pmv, t + 1]
 
@@ -215,8 +262,9 @@ def run_reference(args):
             list(ex.map(step, range(threads)))
         dt = time.perf_counter() - t0
     fps = threads * args.steps / dt
-    sample = ("each step = one 1080p P frame per host thread (%d threads, one closed GOP each) through the C oracle port "
-              "of the stage (libx264/libswscale are not buildable here)" % threads)
+    sample = ("each step = one %dx%d frame per host thread (%d threads = all host CPUs, one closed GOP of %d each, GOP phases staggered so "
+              "that I frames occur at the workload's 1 : %d rate) through the C oracle port of the stage, scalar C built -O3 "
+              "-march=native (libx264/libswscale are not buildable here: this is NOT x264's speed)" % (W, H, threads, GOP, GOP - 1))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
@@ -234,6 +282,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dropin", action="store_true", help="skip the x264-mirror call-sequence leg (key `dropin`)")
+    ap.add_argument("--no-verify", action="store_true", help="skip the post-run oracle check of the engine's final state (key `verified`)")
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--deblock", type=int, default=0, help="1: also run the in-loop deblocking filter K8 (row N2, outside the named path)")
     ap.add_argument("--pack-levels", type=int, default=1, help="1: levels leave the GPU packed (K9: only blocks with a non-zero level); "
@@ -340,7 +389,10 @@ def main():
 
     # ---- K1/K0 alone (one stream, nothing overlapping): the roofline numerator --------------------------
     iso = None
+    verify = None
     if rank == 0:
+        if not args.no_verify:
+            verify = verify_final_state(eng, b2enc, b2oracle, rank, groups, ftype, step - 1, args)
         eng.close()
         eng1 = b2enc.Engine(W, H, slots=SLOTS, fmt="yuv420p", ring=2, merange=MERANGE, qp=QP, subpel=1, intra_in_p=1,
                             device=local, profile=1, streams=1, deblock=args.deblock, transform8x8=args.transform8x8,
@@ -381,6 +433,7 @@ def main():
                                  if args.pack_levels else "per-MB decisions (48 B) + dense levels (832 B)"), "api": "b2_engine_h2d/encode/d2h (include/b2enc_engine.h), pinned host buffers",
                     "timing": "host wall clock around %d pipelined steps, synchronised on both sides" % n_e2e},
             "gpu_launches": int(launches),
+            "verified": verify["verified"] if verify else None, "verify": verify,
             "clocks": clk,
             "roofline": {"bound": "int_alu", "kernel": "k1_me_fullpel_kernel<%d,256>" % MERANGE, "achieved": round(k1_rate / 1e12, 3),
                          "peak": round(int_rate * 4 / 1e12, 3), "unit": "Tpixel-SAD/s", "frac": round(k1_rate / (int_rate * 4), 4),

@@ -12,20 +12,28 @@
  * Like the reference it takes --filters (av_encode.c:116): "hqdn3d", "yadif" or "hqdn3d,yadif" run on the GPU pre-filter stage
  * (include/b2enc_filters.h); and when the output name ends in ".mp4" it writes an MP4 with one AVC track from the encoder's
  * b_annexb = 0 payloads (tools/b2_mp4.h + b2_avcc_write), the video half of enc_mp4_write_video_sample (:683-744).
- * Extensions (not in the reference): --size WxH --fps N[/D] for raw input, --merange, --gop, --slots, --device, --8x8dct, --partitions.
+ * Extensions (not in the reference): --size WxH --fps N[/D] for raw input, --merange, --gop, --slots, --device, --devices N (one
+ * stream over N GPUs by closed GOP), --8x8dct, --partitions.
+ * Regular input files are mmap'ed: the "decoded picture" the reference gets from libavcodec is then a pointer into the page
+ * cache and b2_sws_scale's staging copy is the only time the host touches the pixels (pipes fall back to fread).
  */
+#define _DEFAULT_SOURCE
 #define _POSIX_C_SOURCE 200809L
+#include <fcntl.h>
 #include <getopt.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <time.h>
+#include <unistd.h>
 #include "b2enc.h"
 #include "b2enc_filters.h"
 #include "b2_mp4.h"
 
 typedef struct {
-    int silent, width, height, fps_num, fps_den, merange, gop, slots, device, dct8, partitions;
+    int silent, width, height, fps_num, fps_den, merange, gop, slots, device, devices, dct8, partitions;
     long frame_limit;
     const char *input_file, *output_file, *preset, *tune, *profile, *video_filter;
     float quality;
@@ -34,7 +42,7 @@ typedef struct {
 static int parse_cli_options(cli_options_t *o, int argc, char **argv)
 {
     cli_options_t d = {.silent = 0, .width = 0, .height = 0, .fps_num = 25, .fps_den = 1, .merange = 0, .gop = 0, .slots = 0,
-                       .device = 0, .dct8 = 0, .partitions = 0, .video_filter = NULL, .frame_limit = -1, .input_file = NULL, .output_file = NULL,
+                       .device = 0, .devices = 0, .dct8 = 0, .partitions = 0, .video_filter = NULL, .frame_limit = -1, .input_file = NULL, .output_file = NULL,
                        .preset = "medium", .tune = "film", .profile = NULL, .quality = 20.0f};   /* av_encode.c:91-106 */
     *o = d;
     struct option long_opts[] = {
@@ -44,6 +52,7 @@ static int parse_cli_options(cli_options_t *o, int argc, char **argv)
         {"size", required_argument, NULL, 5}, {"fps", required_argument, NULL, 6}, {"merange", required_argument, NULL, 7},
         {"gop", required_argument, NULL, 8}, {"slots", required_argument, NULL, 9}, {"device", required_argument, NULL, 10},
         {"filters", required_argument, NULL, 'f'}, {"8x8dct", no_argument, NULL, 11}, {"partitions", required_argument, NULL, 12},
+        {"devices", required_argument, NULL, 13},
         {NULL, 0, NULL, 0}};
     int c, idx = 0;
     while ((c = getopt_long(argc, argv, "sl:f:", long_opts, &idx)) != -1) {
@@ -63,6 +72,7 @@ static int parse_cli_options(cli_options_t *o, int argc, char **argv)
         case 'f': o->video_filter = optarg; break;                       /* av_encode.c:148-149 */
         case 11: o->dct8 = 1; break;
         case 12: o->partitions = atoi(optarg); break;
+        case 13: o->devices = atoi(optarg); break;
         default: return 0;
         }
     }
@@ -90,7 +100,7 @@ int main(int argc, char **argv)
     cli_options_t opts;
     if (!parse_cli_options(&opts, argc, argv)) {
         fprintf(stderr, "usage: %s [--preset p] [--tune t] [--quality q] [--profile p] [--frame-limit n] [--silent]\n"
-                        "          [--size WxH --fps N[/D]] [--merange 16|32] [--gop n] [--slots n] [--device n]\n"
+                        "          [--size WxH --fps N[/D]] [--merange 16|32] [--gop n] [--slots n] [--device n] [--devices n]\n"
                         "          [--filters hqdn3d,yadif] [--8x8dct] [--partitions 0|1|2] input.{y4m,yuv} output.{h264,mp4}\n", argv[0]);
         return 1;
     }
@@ -120,7 +130,7 @@ int main(int argc, char **argv)
     if (opts.merange) params.i_merange = opts.merange;
     if (opts.gop) params.i_keyint_max = opts.gop;
     if (opts.slots) params.i_gop_slots = opts.slots;
-    params.i_device = opts.device;
+    params.i_device = opts.device; params.i_devices = opts.devices;
     if (b2_param_apply_profile(&params, opts.profile) != 0) { fprintf(stderr, "b2enc: failed to apply profile %s\n", opts.profile); return 8; }
     b2_t *enc = b2_encoder_open(&params);
     if (!enc) { fprintf(stderr, "b2enc: failed to initialize encoder\n"); return 8; }
@@ -143,7 +153,18 @@ int main(int argc, char **argv)
     else { out = fopen(opts.output_file, "wb"); if (!out) { perror(opts.output_file); return 9; } }
     const int cw = (opts.width + 1) / 2, ch = (opts.height + 1) / 2;
     const size_t frame_bytes = (size_t)opts.width * opts.height + 2 * (size_t)cw * ch;
-    uint8_t *raw = (uint8_t *)malloc(frame_bytes), *filt = (uint8_t *)malloc(frame_bytes);
+    uint8_t *raw_buf = (uint8_t *)malloc(frame_bytes), *filt = (uint8_t *)malloc(frame_bytes);
+    if (!raw_buf || !filt) { fprintf(stderr, "out of memory\n"); return 8; }
+    /* regular file: map it, pictures are pointers into the page cache */
+    const uint8_t *map = NULL; size_t map_size = 0, map_pos = (size_t)ftell(in);
+    {
+        struct stat st;
+        if (fstat(fileno(in), &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+            void *m = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_SHARED, fileno(in), 0);
+            if (m != MAP_FAILED) { map = (const uint8_t *)m; map_size = (size_t)st.st_size; madvise(m, map_size, MADV_SEQUENTIAL); }
+        }
+    }
+    int write_error = 0;
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
     long frames_in = 0, frames_out = 0;
@@ -152,16 +173,26 @@ int main(int argc, char **argv)
 #define EMIT(payload)                                                                                              \
     do {                                                                                                           \
         if ((payload) > 0) {                                                                                       \
-            if (to_mp4) b2_mp4_write_frame(&mp4, nals, nal_count, (payload), pic_out.b_keyframe);                  \
-            else fwrite(nals[0].p_payload, 1, (size_t)(payload), out);                                             \
+            if (to_mp4) write_error |= b2_mp4_write_frame(&mp4, nals, nal_count, (payload), pic_out.b_keyframe) != 0; \
+            else write_error |= fwrite(nals[0].p_payload, 1, (size_t)(payload), out) != (size_t)(payload);         \
             bytes_out += (size_t)(payload); frames_out++;                                                          \
         } else if ((payload) < 0) fprintf(stderr, "b2enc: encoder error\n");                                       \
     } while (0)
     int eof = 0;
     while (!eof) {
         if ((opts.frame_limit >= 0 && frames_in >= opts.frame_limit)) eof = 1;
-        if (!eof && is_y4m) { char fl[64]; if (!fgets(fl, sizeof(fl), in) || strncmp(fl, "FRAME", 5)) eof = 1; }
-        if (!eof && fread(raw, 1, frame_bytes, in) != frame_bytes) eof = 1;
+        const uint8_t *raw = raw_buf;
+        if (!eof && map) {
+            if (is_y4m) {                                  /* "FRAME[ params]\n" */
+                if (map_pos + 6 > map_size || memcmp(map + map_pos, "FRAME", 5)) eof = 1;
+                else { const uint8_t *nl = (const uint8_t *)memchr(map + map_pos, '\n', map_size - map_pos); if (!nl) eof = 1; else map_pos = (size_t)(nl - map) + 1; }
+            }
+            if (!eof && map_pos + frame_bytes > map_size) eof = 1;
+            if (!eof) { raw = map + map_pos; map_pos += frame_bytes; }
+        } else {
+            if (!eof && is_y4m) { char fl[64]; if (!fgets(fl, sizeof(fl), in) || strncmp(fl, "FRAME", 5)) eof = 1; }
+            if (!eof && fread(raw_buf, 1, frame_bytes, in) != frame_bytes) eof = 1;
+        }
         const uint8_t *src[4] = {raw, raw + (size_t)opts.width * opts.height, raw + (size_t)opts.width * opts.height + (size_t)cw * ch, NULL};
         const int stride[4] = {opts.width, cw, cw, 0};
         if (graph) {                                          /* av_vsrc_buffer_add_frame, av_encode.c:962 (flush at end of input) */
@@ -198,13 +229,15 @@ int main(int argc, char **argv)
         printf("%ld frames in, %ld frames out, %zu bytes, %.2f s, %.1f fps (host entropy coding included); encoder start-up %.2f s\n",
                frames_in, frames_out, bytes_out, dt, dt > 0 ? frames_out / dt : 0.0,
                (double)(t0.tv_sec - t_start.tv_sec) + 1e-9 * (double)(t0.tv_nsec - t_start.tv_nsec));
-    free(raw); free(filt);
+    free(raw_buf); free(filt);
+    if (map) munmap((void *)map, map_size);
     fclose(in);
-    if (to_mp4) { if (b2_mp4_close(&mp4)) return 11; }                                          /* MP4Close, av_encode.c:1110-1116 */
-    else fclose(out);
+    if (to_mp4) { if (b2_mp4_close(&mp4)) write_error = 1; }                                    /* MP4Close, av_encode.c:1110-1116 */
+    else if (fclose(out) != 0) write_error = 1;
+    if (write_error) fprintf(stderr, "b2enc: writing %s failed\n", opts.output_file);
     b2_filter_graph_free(graph);
     b2_sws_freeContext(scaler);                                                                /* enc_x264_close(), av_encode.c:440-444 */
     b2_picture_clean(&pic_in);
     b2_encoder_close(enc);
-    return 0;
+    return write_error ? 11 : 0;
 }

@@ -69,6 +69,7 @@ struct b2_engine {
     uint8_t *d_pack[2] = {}, *h_pack[2] = {};
     uint32_t *d_pack_n[2] = {}, *h_pack_n[2] = {};
     unsigned long long *d_pack_cum = nullptr;
+    int *d_k8_flags = nullptr;                     // K8 row pipeline: cross-CTA progress flags [S][8]
     size_t pack_stride = 0;
     std::vector<Group> groups;
     // result tickets: which result set each group copied out in one of the last two b2_engine_d2h calls
@@ -164,6 +165,8 @@ static int engine_alloc(b2_engine *e)
             ENG_OK(cudaHostAlloc(&e->h_coef[s], n * sizeof(b2_mbcoef_t), cudaHostAllocDefault));
         }
     }
+    ENG_OK(cudaMalloc(&e->d_k8_flags, S * 8 * sizeof(int)));
+    ENG_OK(cudaMemset(e->d_k8_flags, 0, S * 8 * sizeof(int)));
     if (c.pack_levels) {
         ENG_OK(cudaMalloc(&e->d_pack_cum, sizeof(unsigned long long)));
         ENG_OK(cudaMemset(e->d_pack_cum, 0, sizeof(unsigned long long)));
@@ -263,7 +266,7 @@ extern "C" void b2_engine_destroy(b2_engine_t *e)
         cudaFree(e->d_info[s]); cudaFree(e->d_coef[s]); cudaFreeHost(e->h_info[s]); cudaFreeHost(e->h_coef[s]);
         cudaFree(e->d_pack[s]); cudaFreeHost(e->h_pack[s]); cudaFree(e->d_pack_n[s]); cudaFreeHost(e->h_pack_n[s]);
     }
-    cudaFree(e->d_pack_cum);
+    cudaFree(e->d_pack_cum); cudaFree(e->d_k8_flags);
     for (auto &gr : e->groups) {
         for (int s = 0; s < 2; s++) { if (gr.ev_enc[s]) cudaEventDestroy(gr.ev_enc[s]); if (gr.ev_d2h[s]) cudaEventDestroy(gr.ev_d2h[s]); }
         if (gr.ev_join) cudaEventDestroy(gr.ev_join);
@@ -566,7 +569,8 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
     }
     if (c.deblock) {
         KScope k(e, st, 8);
-        if (b2_launch_deblock(rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, ns, c.qp, c.deblock_alpha, c.deblock_beta, info, st)) return -1;
+        if (b2_launch_deblock(rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, ns, c.qp, c.deblock_alpha, c.deblock_beta, info,
+                              e->d_k8_flags + (size_t)gr.slot0 * 8, st)) return -1;
     }
     {
         KScope k(e, st, 7);

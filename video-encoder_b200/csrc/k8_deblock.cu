@@ -4,13 +4,23 @@
 // Bit-exact against oracle/b2o_deblock.c and, through the decoder drift test, against libavcodec.
 //
 // The filter is defined in macroblock raster order and every macroblock reads samples its left, top and
-// top-right neighbours have already modified, so macroblocks on one anti-diagonal d = mbx + 2*mby are
-// independent and diagonals are serial -- the same wavefront as intra reconstruction (K7).  One thread-block
-// cluster per frame, one warp per macroblock: the 20x20 luma and two 12x12 chroma neighbourhoods are staged
-// in shared memory, lanes 0-15 filter the luma lines (rows for vertical edges, columns for horizontal edges),
-// lanes 16-31 the U and V lines; the four edges of a line are filtered by the same lane in order, so the only
-// warp-level synchronisation is between the vertical and the horizontal pass.
-// Bound: latency of the wavefront; algorithmic bytes 1.5*W*H read + written.
+// top-right neighbours have already modified: MB (x, y) may run once (x-1, y) and (x+1, y-1) are done.
+//
+// Schedule: ROW PIPELINE.  One warp owns one macroblock row and walks it left to right; row r trails row r-1 by two
+// macroblocks.  The only cross-warp communication is one progress counter per row: "x+1 macroblocks done", in shared
+// memory when producer and consumer row sit in the same CTA (15 of 16 rows), in global memory across CTAs.  The pixels
+// travel through L2 (fence.gpu before the flag store, fence + ld.global.cg after the flag load).  The dependency depth is
+// the same mbw + 2*mbh steps as the anti-diagonal wavefront, but a step is one warp's macroblock (no cluster-wide barrier:
+// 7 us per diagonal before) and the loads are off the chain: a warp prefetches the next macroblock's own samples and
+// decision records while it filters the current one, carries the four left columns in shared memory, and only fetches
+// the four rows above after the flag.  Plain launch (no cluster to place): a 1080p frame is five half-SM CTAs that slot
+// in beside the other stream groups' kernels; waiting warps sleep instead of spinning on the issue slots.
+// Per macroblock: the 20x20 luma and two 12x12 chroma neighbourhoods live in a per-warp shared-memory tile, lanes
+// 0-15 filter the luma lines (rows for vertical edges, columns for horizontal edges), lanes 16-31 the U and V lines;
+// the four edges of a line are filtered by the same lane in order.
+// (The anti-diagonal cluster-barrier form is kept behind B2_K8_WAVEFRONT=1 for A/B measurements.)
+// Bound: latency of the dependency chain; algorithmic bytes 1.5*W*H read + written.
+#include <stdlib.h>
 #include "b2_mbcode.cuh"
 
 namespace {
@@ -223,14 +233,218 @@ k8_deblock_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pitchc, 
     }
 }
 
+
+// ---- row-pipelined form -------------------------------------------------------------------------------------------
+// what the boundary-strength rule needs of one b2_mbinfo_t (48 bytes = three 16-byte words: {mv, type.., i4_mode[0..7]},
+// {i4_mode[8..15], cost, nnz_mask}, {mv8[3], part | transform8x8 << 8 | i8_modes << 16})
+struct MbLite { uint32_t mv, typ, nnz, m8a, m8b, m8c, pt; };
+
+__device__ __forceinline__ MbLite load_lite(const b2_mbinfo_t *m)
+{
+    const uint4 *q = reinterpret_cast<const uint4 *>(m);
+    const uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+    MbLite l;
+    l.mv = a.x; l.typ = a.y & 255u; l.nnz = b.w; l.m8a = c.x; l.m8b = c.y; l.m8c = c.z; l.pt = c.w;
+    return l;
+}
+__device__ __forceinline__ bool lite_coded(const MbLite &m, int bx, int by)
+{
+    if ((m.pt >> 8) & 255u) return ((m.nnz >> (4 * ((bx >> 1) | ((by >> 1) << 1)))) & 15u) != 0;
+    return (m.nnz >> zidx(bx, by)) & 1u;
+}
+__device__ __forceinline__ uint32_t lite_mv(const MbLite &m, int q)
+{
+    if (q == 0 || (m.pt & 255u) == B2_PART_16x16) return m.mv;
+    return q == 1 ? m.m8a : (q == 2 ? m.m8b : m.m8c);
+}
+__device__ __forceinline__ int lite_bs(const MbLite &mp, int pbx, int pby, const MbLite &mq, int qbx, int qby, bool mb_edge)
+{
+    if (mp.typ != B2_MB_P16x16 || mq.typ != B2_MB_P16x16) return mb_edge ? 4 : 3;
+    if (lite_coded(mp, pbx, pby) || lite_coded(mq, qbx, qby)) return 2;
+    const uint32_t a = lite_mv(mp, (pbx >> 1) | ((pby >> 1) << 1)), b = lite_mv(mq, (qbx >> 1) | ((qby >> 1) << 1));
+    const int ax = (int16_t)(a & 0xffffu), ay = (int16_t)(a >> 16), bx = (int16_t)(b & 0xffffu), by = (int16_t)(b >> 16);
+    return (abs(ax - bx) >= 4 || abs(ay - by) >= 4) ? 1 : 0;
+}
+
+// cross-CTA progress flags live in global memory (cleared by the launcher ahead of every launch)
+__device__ __forceinline__ void st_flag_global(int *f, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_flag_global(const int *f) { int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); return v; }
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+k8_deblock_rows_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pitchc, size_t stride_y, size_t stride_c, int mbw, int mbh,
+                       int qp, int alpha_off, int beta_off, const b2_mbinfo_t *__restrict__ info, int *__restrict__ gflags)
+{
+    __shared__ K8Warp s_warp[WARPS];
+    __shared__ int s_flag[WARPS];         // s_flag[w]: macroblocks finished, over all its rows so far, by the warp that produces for warp w
+    const int frame = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ncta = (int)gridDim.x, crank = (int)blockIdx.x;
+    const int gwarp = crank * WARPS + warp, nwarps = ncta * WARPS;
+    // gflag[c]: progress of the LAST warp of CTA c-1 (the producer of CTA c's first warp; CTA 0's is the last CTA's, for frames
+    // with more rows than warps).  CTAs of one frame are consecutive in dispatch order, so a producer CTA is resident no later
+    // than its consumer.
+    int *const gflag = gflags + (size_t)frame * 8;
+    const b2_mbinfo_t *finfo = info + (size_t)frame * mbw * mbh;
+    uint8_t *const py = ry + frame * stride_y, *const pu = ru + frame * stride_c, *const pv = rv + frame * stride_c;
+    const int qpc = chroma_qp(qp);
+    FiltConst fy, fcc;
+    const int ia = clip3(0, 51, qp + 2 * alpha_off), ib = clip3(0, 51, qp + 2 * beta_off);
+    const int iac = clip3(0, 51, qpc + 2 * alpha_off), ibc = clip3(0, 51, qpc + 2 * beta_off);
+    fy.alpha = c_alpha[ia]; fy.beta = c_beta[ib]; fcc.alpha = c_alpha[iac]; fcc.beta = c_beta[ibc];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { fy.tc0[i] = c_tc0[ia][i]; fcc.tc0[i] = c_tc0[iac][i]; }
+    if (threadIdx.x < WARPS) s_flag[threadIdx.x] = 0;
+    __syncthreads();
+
+    K8Warp &ws = s_warp[warp];
+    // the consumer of this warp's progress is the warp that owns the next row: the next warp of this CTA (shared-memory flag)
+    // or, for the last warp, the first warp of the next CTA (global flag); likewise on the consuming side
+    const bool prod_remote = warp == 0, cons_remote = warp == WARPS - 1;
+    int *const cons_gflag = &gflag[(crank + 1) % ncta];
+    const int *const prod_gflag = &gflag[crank];
+    // this lane's boundary-strength job: lanes 0-15 vertical edges, 16-31 horizontal edges; lane -> (edge e, segment k)
+    const int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3;
+    // own-sample words: lane -> luma words (row l>>1, words 2*(l&1), 2*(l&1)+1), chroma word (plane l>>4, row (l>>1)&7, word l&1)
+    const int oy_row = lane >> 1, oy_w = (lane & 1) * 2;
+    const int oc_p = lane >> 4, oc_row = (lane >> 1) & 7, oc_w = lane & 1;
+
+    int round = 0;
+    for (int mby = gwarp; mby < mbh; mby += nwarps, round++) {
+        const int prod_base = ((mby - 1) / nwarps) * mbw;      // what the producer had published before it started row mby-1
+        const int my_base = round * mbw;
+        uint8_t *const rowy = py + (size_t)(B2_PAD + mby * 16) * pitch + B2_PAD;
+        uint8_t *const rowu = pu + (size_t)(B2_PADC + mby * 8) * pitchc + B2_PADC;
+        uint8_t *const rowv = pv + (size_t)(B2_PADC + mby * 8) * pitchc + B2_PADC;
+        // ---- prologue: own samples and boundary strengths of macroblock 0 ----
+        uint32_t n0, n1, n2;
+        MbLite lq, lp;
+        {
+            const uint32_t *g = (const uint32_t *)(rowy + (size_t)oy_row * pitch) + oy_w;
+            n0 = g[0]; n1 = g[1];
+            n2 = *((const uint32_t *)((oc_p ? rowv : rowu) + (size_t)oc_row * pitchc) + oc_w);
+            const b2_mbinfo_t *mq = &finfo[mby * mbw];
+            lq = load_lite(mq);
+            lp = (e == 0 && dir == 1 && mby > 0) ? load_lite(mq - mbw) : lq;
+        }
+        for (int mbx = 0; mbx < mbw; mbx++) {
+            // ---- own samples (prefetched) -> tile; boundary strengths from the prefetched records ----
+            *(uint32_t *)&ws.y[(oy_row + 4) * LP + 4 + oy_w * 4] = n0;
+            *(uint32_t *)&ws.y[(oy_row + 4) * LP + 8 + oy_w * 4] = n1;
+            *(uint32_t *)&ws.c[oc_p][(oc_row + 2) * CP + 4 + oc_w * 4] = n2;
+            {
+                const bool edge_ok = !(e == 0 && (dir == 0 ? mbx == 0 : mby == 0)) && !((e & 1) && ((lq.pt >> 8) & 255u));
+                int bs = 0;
+                if (edge_ok) {
+                    const int pbx = dir == 0 ? (e == 0 ? 3 : e - 1) : k, pby = dir == 0 ? k : (e == 0 ? 3 : e - 1);
+                    const int qbx = dir == 0 ? e : k, qby = dir == 0 ? k : e;
+                    bs = lite_bs(lp, pbx, pby, lq, qbx, qby, e == 0);
+                }
+                ws.bs[dir][e][k] = (int8_t)bs;
+            }
+            // ---- prefetch the next macroblock: own samples + decision records (nothing in this kernel writes them before) ----
+            if (mbx + 1 < mbw) {
+                const uint32_t *g = (const uint32_t *)(rowy + (size_t)oy_row * pitch + (mbx + 1) * 16) + oy_w;
+                n0 = g[0]; n1 = g[1];
+                n2 = *((const uint32_t *)((oc_p ? rowv : rowu) + (size_t)oc_row * pitchc + (mbx + 1) * 8) + oc_w);
+                const b2_mbinfo_t *mq = &finfo[mby * mbw + mbx + 1];
+                const MbLite cur = lq;                           // becomes the left neighbour
+                lq = load_lite(mq);
+                lp = e != 0 ? lq : (dir == 0 ? cur : (mby > 0 ? load_lite(mq - mbw) : lq));
+            }
+            // ---- the four rows above: final once row mby-1 has finished macroblock mbx+1 ----
+            if (mby > 0) {
+                const int need = prod_base + min(mbx + 2, mbw);
+                if (prod_remote) { while (ld_flag_global(prod_gflag) < need) __nanosleep(100); }
+                else { while (*(volatile int *)&s_flag[warp] < need) __nanosleep(40); }     // sleeping keeps the issue slots for co-resident kernels
+                __threadfence();
+                if (lane < 16) {
+                    const int r = lane >> 2, w = lane & 3;        // rows -4..-1, words 0..3
+                    *(uint32_t *)&ws.y[r * LP + 4 + w * 4] = __ldcg((const uint32_t *)(rowy + (ptrdiff_t)(r - 4) * pitch + mbx * 16) + w);
+                } else if (lane < 24) {
+                    const int l = lane - 16, p = l >> 2, r = (l >> 1) & 1, w = l & 1;     // rows -2..-1, words 0..1
+                    *(uint32_t *)&ws.c[p][r * CP + 4 + w * 4] = __ldcg((const uint32_t *)((p ? rowv : rowu) + (ptrdiff_t)(r - 2) * pitchc + mbx * 8) + w);
+                }
+            }
+            __syncwarp();
+            // ---- vertical edges: luma lane = row, chroma lane-16 = (plane, row) ----
+            if (lane < 16) {
+                uint8_t *row = &ws.y[(lane + 4) * LP + 4];
+#pragma unroll
+                for (int ee = 0; ee < 4; ee++) filter_line(row + 4 * ee, 1, ws.bs[0][ee][lane >> 2], fy, false);
+            } else {
+                const int l = lane - 16, p = l >> 3, r = l & 7;
+                uint8_t *row = &ws.c[p][(r + 2) * CP + 4];
+#pragma unroll
+                for (int ee = 0; ee < 2; ee++) filter_line(row + 4 * ee, 1, ws.bs[0][2 * ee][r >> 1], fcc, true);
+            }
+            __syncwarp();
+            // ---- horizontal edges: luma lane = column, chroma lane-16 = (plane, column) ----
+            if (lane < 16) {
+                uint8_t *col = &ws.y[4 * LP + lane + 4];
+#pragma unroll
+                for (int ee = 0; ee < 4; ee++) filter_line(col + 4 * ee * LP, LP, ws.bs[1][ee][lane >> 2], fy, false);
+            } else {
+                const int l = lane - 16, p = l >> 3, x = l & 7;
+                uint8_t *col = &ws.c[p][2 * CP + x + 4];
+#pragma unroll
+                for (int ee = 0; ee < 2; ee++) filter_line(col + 4 * ee * CP, CP, ws.bs[1][2 * ee][x >> 1], fcc, true);
+            }
+            __syncwarp();
+            // ---- write back what can have changed: own MB, 3 (luma) / 1 (chroma) lines into the top MB, one word into the left MB ----
+            uint8_t *gy = rowy + mbx * 16;
+            for (int i = lane; i < 95; i += 32) {                  // luma rows -3..15 (19 rows) x 5 words
+                const int r = i / 5 + 1, w = i - (i / 5) * 5;       // tile row r = y + 4, y = -3..15
+                const int y = r - 4;
+                if (w == 0 && (mbx == 0 || y < 0)) continue;        // nothing left of the picture; corner block is never modified
+                if (y < 0 && mby == 0) continue;
+                *(uint32_t *)(gy + (ptrdiff_t)y * pitch + (w - 1) * 4) = *(const uint32_t *)&ws.y[r * LP + w * 4];
+            }
+            for (int i = lane; i < 54; i += 32) {                  // chroma rows -1..7 (9 rows) x 3 words x 2 planes
+                const int p = i / 27, kk = i - p * 27, r = kk / 3 + 1, w = kk - (kk / 3) * 3;
+                const int y = r - 2;
+                if (w == 0 && (mbx == 0 || y < 0)) continue;
+                if (y < 0 && mby == 0) continue;
+                uint8_t *gc = (p ? rowv : rowu) + mbx * 8;
+                *(uint32_t *)(gc + (ptrdiff_t)y * pitchc + (w - 1) * 4) = *(const uint32_t *)&ws.c[p][r * CP + w * 4];
+            }
+            // ---- publish: every lane's stores are visible GPU-wide before the flag moves ----
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                if (cons_remote) st_flag_global(cons_gflag, my_base + mbx + 1);
+                else *(volatile int *)&s_flag[warp + 1] = my_base + mbx + 1;
+            }
+            // ---- carry the four rightmost columns over as the next macroblock's left neighbour ----
+            if (lane < 16) *(uint32_t *)&ws.y[(lane + 4) * LP] = *(const uint32_t *)&ws.y[(lane + 4) * LP + 16];
+            else *(uint32_t *)&ws.c[(lane - 16) >> 3][(((lane - 16) & 7) + 2) * CP] = *(const uint32_t *)&ws.c[(lane - 16) >> 3][(((lane - 16) & 7) + 2) * CP + 8];
+            __syncwarp();
+        }
+    }
+}
+
 }  // namespace
 
 int b2_launch_deblock(uint8_t *const rec[3], int pitch, int pitchc, size_t stride_y, size_t stride_c, int mbw, int mbh,
-                      int nframes, int qp, int alpha_off, int beta_off, const b2_mbinfo_t *d_info, cudaStream_t st)
+                      int nframes, int qp, int alpha_off, int beta_off, const b2_mbinfo_t *d_info, int *d_flags, cudaStream_t st)
 {
-    const int maxdiag = mbh < (mbw + 1) / 2 ? mbh : (mbw + 1) / 2;
+    static const bool wavefront = getenv("B2_K8_WAVEFRONT") && atoi(getenv("B2_K8_WAVEFRONT")) != 0;      // A/B measurements only
     int ncta = 1;
-    while (ncta < 8 && ncta * K8_WARPS < maxdiag) ncta *= 2;
+    if (wavefront) {
+        const int maxdiag = mbh < (mbw + 1) / 2 ? mbh : (mbw + 1) / 2;
+        while (ncta < 8 && ncta * K8_WARPS < maxdiag) ncta *= 2;
+    } else {
+        ncta = (mbh + K8_WARPS - 1) / K8_WARPS;                   // one warp per macroblock row; beyond 128 rows warps take several
+        if (ncta > 8) ncta = 8;
+    }
+    if (!wavefront) {
+        // plain launch: no cluster to place, so a frame's few CTAs slot in beside whatever else runs on the GPU
+        B2_CUDA_OK(cudaMemsetAsync(d_flags, 0, (size_t)nframes * 8 * sizeof(int), st));
+        k8_deblock_rows_kernel<K8_WARPS><<<dim3(ncta, nframes), K8_WARPS * 32, 0, st>>>(rec[0], rec[1], rec[2], pitch, pitchc, stride_y, stride_c,
+                                                                                        mbw, mbh, qp, alpha_off, beta_off, d_info, d_flags);
+        B2_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(ncta, nframes, 1);
     cfg.blockDim = dim3(K8_WARPS * 32, 1, 1);
