@@ -122,27 +122,34 @@ def fill_inputs(eng, b2oracle, rank):
             buf[:n_y] = y.ravel(); buf[n_y:n_y + u.size] = u.ravel(); buf[n_y + u.size:] = v.ravel()
 
 
-def dropin_leg(b2enc, b2oracle, deblock, transform8x8, partitions, frames=1024, gop_slots=16):
+def dropin_leg(b2enc, b2oracle, deblock, transform8x8, partitions, frames=2048, gop_slots=None):
     """The same pictures through the x264-mirror call sequence of the reference (b2_encoder_encode, include/b2enc.h;
-    av_encode.c:968-975, :1076-1083): one picture per call from host memory, host entropy coding (CABAC) included."""
+    av_encode.c:968-975, :1076-1083): one picture per call from host memory, host entropy coding (CABAC) included.
+    deblock=None: the mirror's defaults, i.e. what an unmodified av_encode.c gets (x264's: loop filter on, tune film -1:-1)."""
     src = [b2oracle.synth_frame(W, H, t, 0) for t in range(16)]
-    enc = b2enc.DropInEncoder(W, H, preset="slow" if MERANGE == 32 else "medium", tune="film", quality=QP, fps=(60, 1), annexb=0,
-                              i_keyint_max=GOP, i_gop_slots=gop_slots, b_deblocking_filter=deblock, b_transform_8x8=transform8x8,
-                              b_partitions=partitions)
-    t0 = time.perf_counter(); nout = 0; nbytes = 0
+    ext = dict(i_keyint_max=GOP, b_transform_8x8=transform8x8, b_partitions=partitions)
+    if gop_slots: ext["i_gop_slots"] = gop_slots
+    if deblock is not None: ext["b_deblocking_filter"] = deblock
+    enc = b2enc.DropInEncoder(W, H, preset="slow" if MERANGE == 32 else "medium", tune="film", quality=QP, fps=(60, 1), annexb=0, **ext)
+    t0 = time.perf_counter(); nout = 0; nbytes = 0; first = None
     for t in range(frames):
         size = enc.encode(src[t % 16], t)[0]
-        if size > 0: nout += 1; nbytes += size
+        if size > 0:
+            nout += 1; nbytes += size
+            if first is None: first = t + 1
     while enc.delayed() > 0:
         size = enc.encode(None, 0)[0]
         if size <= 0: break
         nout += 1; nbytes += size
     dt = time.perf_counter() - t0
+    slots = enc.param.i_gop_slots
     enc.close()
-    return {"value": round(nout / dt, 1), "unit": UNIT, "frames": nout, "gop_slots": gop_slots, "bytes_per_frame": int(nbytes / max(nout, 1)),
+    return {"value": round(nout / dt, 1), "unit": UNIT, "frames": nout, "gop_slots_per_gpu": slots, "bytes_per_frame": int(nbytes / max(nout, 1)),
+            "deblocking_filter": "x264 default (on, tune film -1:-1)" if deblock is None else bool(deblock),
+            "first_output_after_pictures": first, "host_cores": os.cpu_count(),
             "api": "b2_param_default_preset / b2_encoder_open / b2_picture_alloc / b2_encoder_encode / b2_encoder_delayed_frames "
                    "(x264 mirror, include/b2enc.h), driven from Python: one picture per call, pipeline fill and drain inside the timed region",
-            "note": "entropy coding (CABAC) on the host cores is part of this call sequence and is its limiter; the encode stage itself is `e2e`"}
+            "note": "entropy coding (CABAC) on the host cores is part of this call sequence; the encode stage itself is `e2e`"}
 
 
 def verify_final_state(eng, b2enc, b2oracle, rank, groups, ftype, last_step, args):
@@ -425,7 +432,8 @@ def main():
             "config": {"workload": WORKLOAD, "frames_per_step": SLOTS * world, "gop": GOP, "input_ring_frames": RING,
                        "l2": "no flush needed: per-step working set (cur+ref+recon planes of %d frames ~ %d MB + raw ring) exceeds the 126 MB L2"
                              % (SLOTS, int(SLOTS * 3 * 1.5 * w16 * h16 / 1e6)),
-                       "host_cpus_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None, "stream_groups": NG, "gop_phase_per_group": phase, "deblocking_filter": bool(args.deblock), "transform8x8": bool(args.transform8x8), "partitions": bool(args.partitions),
+                       "host_cpus_bound_to_gpu_numa_node": len(numa_cpus) if numa_cpus else None, "stream_groups": NG, "gop_phase_per_group": phase, "deblocking_filter": bool(args.deblock),
+                       "deblocking_note": "the named path (BASELINE.json C3) has no loop filter, so K8 is off here (--deblock 1 adds it); an av_encode.c user of the x264 mirror gets x264's default: filter ON, tune film offsets -1:-1 -- that configuration is the `dropin` leg", "transform8x8": bool(args.transform8x8), "partitions": bool(args.partitions),
                        "parallelism": "closed-GOP sharding, %d GPUs x %d GOPs, no collective" % (world, SLOTS)},
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(world * SLOTS * in_bytes),
                     "d2h_bytes_per_step": int(world * (SLOTS * mbs * 48 + packed_per_step)) if args.pack_levels else int(world * SLOTS * mbs * (48 + 832)),
@@ -452,7 +460,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         if world == 1 and not args.no_dropin and args.workload in ("c2", "c3"):
-            out["dropin"] = dropin_leg(b2enc, b2oracle, args.deblock, args.transform8x8, args.partitions)
+            out["dropin"] = dropin_leg(b2enc, b2oracle, None, args.transform8x8, args.partitions)          # what av_encode.c gets
+            out["dropin_named_path"] = dropin_leg(b2enc, b2oracle, 0, args.transform8x8, args.partitions)   # loop filter off like `value`
         print(json.dumps(out))
     else:
         eng.close()

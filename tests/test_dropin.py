@@ -93,7 +93,7 @@ def test_reference_call_sequence_and_bitstream(oracle, b2, profile, profile_idc,
     assert [o[3] for o in out] == [int(t % gop == 0) for t in range(n)]           # keyframe flag (av_encode.c:783)
     sps = out[0][0][0]
     assert sps[0] == 7 and out[0][0][1][0] == 8 and out[0][0][2][0] == 5          # SPS, PPS, IDR slice (av_encode.c:683-736)
-    assert sps[1][5] == profile_idc and sps[1][7] in (12, 13, 20, 21, 30)                  # profile_idc / level_idc at [5],[7] (:703-705)
+    assert sps[1][5] == profile_idc and sps[1][7] in (10, 11, 12, 13, 21, 22, 30)                  # profile_idc / level_idc at [5],[7] (:703-705)
     bs = to_annexb(out, length_prefixed=True)
     ref_bs, recons, _, _ = oracle.encode_sequence(frames, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1), deblock=1, cabac=cabac,
                                                    transform8x8=t8, deblock_offsets=(-1, -1))   # tune film: deblock -1:-1 as in x264
@@ -198,3 +198,56 @@ def test_delay_contract(b2):
     for t, fr in enumerate(frames[:5]):
         assert enc.encode(fr, t)[0] > 0 and enc.delayed() == 0
     enc.close()
+
+
+def _to_fmt(fmt, y, u, v):
+    h, w = y.shape
+    if fmt == "yuv420p":
+        return [np.pad(y, ((0, 0), (0, 8))), np.pad(u, ((0, 0), (0, 4))), np.pad(v, ((0, 0), (0, 4)))]
+    if fmt == "nv12":
+        uv = np.empty((h // 2, w), np.uint8); uv[:, 0::2] = u; uv[:, 1::2] = v
+        return [np.pad(y, ((0, 0), (0, 8))), np.pad(uv, ((0, 0), (0, 16)))]
+    p = np.empty((h, 2 * w), np.uint8); p[:, 0::2] = y
+    p[:, 1::4] = np.repeat(u, 2, axis=0); p[:, 3::4] = np.repeat(v, 2, axis=0)
+    return [np.pad(p, ((0, 0), (0, 12)))]
+
+
+@pytest.mark.parametrize("fmts", [["yuv420p"], ["yuyv422"], ["nv12", "yuv420p", "yuyv422"]])
+def test_sws_scale_into_the_encoder_picture(oracle, b2, fmts):
+    """the reference's per-frame pair sws_scale(decoder picture -> pic_in), x264_encoder_encode(pic_in) (av_encode.c:545-547,
+    :970): the conversion is deferred into the encoder (one PCIe crossing, K0 on the encoder's own planes) and the stream equals
+    the one of separately converted pictures; a decoder-format change mid-stream re-shapes the input rings"""
+    w, h, gop, qp = 176, 144, 3, 30
+    n = 6 * len(fmts)
+    base = smooth_seq(w, h, n, seed=11)
+    enc = b2.DropInEncoder(w, h, quality=qp, annexb=1, i_keyint_max=gop, i_gop_slots=2)
+    out, conv = [], []
+    for t, (y, u, v) in enumerate(base):
+        fmt = fmts[t // 6]
+        planes = _to_fmt(fmt, y, u, v)
+        conv.append(oracle.convert_to_i420(fmt, w, h, planes))
+        r = enc.encode_via_sws(fmt, planes, t)
+        if r[0] > 0: out.append((r[1], r[2]))
+    while enc.delayed() > 0:
+        r = enc.encode(None, 0)
+        out.append((r[1], r[2]))
+    enc.close()
+    assert [o[1] for o in out] == list(range(n))
+    ref, *_ = oracle.encode_sequence(conv, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1), deblock=1, cabac=1, deblock_offsets=(-1, -1))
+    assert b"".join(d for nals, _ in out for _, d in nals) == ref
+
+
+def test_sws_host_output_flag(oracle, b2):
+    """B2_SWS_HOST_OUTPUT: the encoder picture's planes are written (GPU round trip through K0) even though it is a registered picture"""
+    import ctypes as C
+    w, h = 64, 48
+    y, u, v = smooth_seq(w, h, 1, seed=4)[0]
+    planes = _to_fmt("yuyv422", y, u, v)
+    want = oracle.convert_to_i420("yuyv422", w, h, planes)
+    enc = b2.DropInEncoder(w, h, quality=30, i_keyint_max=2, i_gop_slots=2)
+    enc.encode_via_sws("yuyv422", planes, 0, flags=1 | 0x10000000)
+    got = [np.frombuffer((C.c_uint8 * (a.size)).from_address(enc.pic_in.img.plane[i]), np.uint8).reshape(a.shape).copy() for i, a in enumerate(want)]
+    while enc.delayed() > 0:
+        enc.encode(None, 0)
+    enc.close()
+    assert all(np.array_equal(g, a) for g, a in zip(got, want))

@@ -69,6 +69,7 @@ struct b2_engine {
     uint8_t *d_pack[2] = {}, *h_pack[2] = {};
     uint32_t *d_pack_n[2] = {}, *h_pack_n[2] = {};
     unsigned long long *d_pack_cum = nullptr;
+    uint32_t *d_pack_chunk = nullptr;              // K9a scratch: present blocks per chunk of macroblocks, [S][chunks]
     int *d_k8_flags = nullptr;                     // K8 row pipeline: cross-CTA progress flags [S][8]
     size_t pack_stride = 0;
     std::vector<Group> groups;
@@ -80,7 +81,6 @@ struct b2_engine {
     // another host thread than h2d/encode/d2h as long as the two work on different ring positions)
     cudaStream_t st_put = nullptr;
     std::vector<uint8_t> in_direct;                                   // [slot * in_ring + ring]: entry is already on the device
-    const void *direct_last = nullptr; bool direct_last_ok = false;   // pinned-ness of the last source pointer looked up
     std::vector<cudaEvent_t> ev_h2d;
     // b2_engine_put_picture (GOP-streaming hosts): per slot, the event behind its latest upload and a flag that the group's
     // next encode still has to wait for it (set by the caller's thread, consumed by the thread that issues the encodes);
@@ -170,6 +170,7 @@ static int engine_alloc(b2_engine *e)
     if (c.pack_levels) {
         ENG_OK(cudaMalloc(&e->d_pack_cum, sizeof(unsigned long long)));
         ENG_OK(cudaMemset(e->d_pack_cum, 0, sizeof(unsigned long long)));
+        ENG_OK(cudaMalloc(&e->d_pack_chunk, S * b2_pack_chunks(e->nmb) * sizeof(uint32_t)));
     }
     ENG_OK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
     ENG_OK(cudaStreamCreateWithFlags(&e->st_in, cudaStreamNonBlocking));
@@ -266,7 +267,7 @@ extern "C" void b2_engine_destroy(b2_engine_t *e)
         cudaFree(e->d_info[s]); cudaFree(e->d_coef[s]); cudaFreeHost(e->h_info[s]); cudaFreeHost(e->h_coef[s]);
         cudaFree(e->d_pack[s]); cudaFreeHost(e->h_pack[s]); cudaFree(e->d_pack_n[s]); cudaFreeHost(e->h_pack_n[s]);
     }
-    cudaFree(e->d_pack_cum); cudaFree(e->d_k8_flags);
+    cudaFree(e->d_pack_cum); cudaFree(e->d_pack_chunk); cudaFree(e->d_k8_flags);
     for (auto &gr : e->groups) {
         for (int s = 0; s < 2; s++) { if (gr.ev_enc[s]) cudaEventDestroy(gr.ev_enc[s]); if (gr.ev_d2h[s]) cudaEventDestroy(gr.ev_d2h[s]); }
         if (gr.ev_join) cudaEventDestroy(gr.ev_join);
@@ -352,13 +353,13 @@ extern "C" int b2_engine_put_frame_direct(b2_engine_t *e, int slot, int ring, co
 {
     if (slot < 0 || slot >= e->cfg.slots || ring < 0 || ring >= e->cfg.in_ring || !src || !src[0]) return -1;
     cudaSetDevice(e->cfg.device);
-    if (src[0] != e->direct_last) {
+    int np0; { int rb0[3], rows0[3]; np0 = b2_fmt_layout(e->cfg.in_fmt, e->cfg.width, e->cfg.height, rb0, rows0); }
+    for (int p = 0; p < np0; p++) {                     // every plane, every call: an address may have been freed and re-used
         cudaPointerAttributes a;
-        const bool ok = cudaPointerGetAttributes(&a, src[0]) == cudaSuccess && a.type == cudaMemoryTypeHost;
+        const bool ok = src[p] && cudaPointerGetAttributes(&a, src[p]) == cudaSuccess && a.type == cudaMemoryTypeHost;
         cudaGetLastError();                             // an unregistered pointer is not an error here
-        e->direct_last = src[0]; e->direct_last_ok = ok;
+        if (!ok) return 1;
     }
-    if (!e->direct_last_ok) return 1;
     Group *gr = group_of(e, slot);
     if (!gr) return -1;
     ENG_OK(cudaStreamWaitEvent(e->st_put, gr->ev_k0[ring], 0));     // the K0 that last read this ring entry
@@ -580,8 +581,9 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
     }
     if (c.pack_levels) {
         KScope k(e, st, 9);
+        e->launches++;                                   // K9a is two kernels (count, scatter)
         if (b2_launch_pack_levels(info, coef, e->d_pack[set] + gr.slot0 * e->pack_stride, e->pack_stride, e->d_pack_n[set] + gr.slot0,
-                                  e->d_pack_cum, e->nmb, ns, st))
+                                  e->d_pack_cum, e->d_pack_chunk + (size_t)gr.slot0 * b2_pack_chunks(e->nmb), e->nmb, ns, st))
             return -1;
     }
     ENG_OK(cudaEventRecord(gr.ev_enc[set], st));

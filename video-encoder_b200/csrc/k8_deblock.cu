@@ -20,6 +20,7 @@
 // the four edges of a line are filtered by the same lane in order.
 // (The anti-diagonal cluster-barrier form is kept behind B2_K8_WAVEFRONT=1 for A/B measurements.)
 // Bound: latency of the dependency chain; algorithmic bytes 1.5*W*H read + written.
+#include <stddef.h>
 #include <stdlib.h>
 #include "b2_mbcode.cuh"
 
@@ -234,6 +235,49 @@ k8_deblock_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pitchc, 
 }
 
 
+// ---- register-resident line filter (row-pipelined form) ------------------------------------------------------------
+// One edge on samples held in registers.  Luma and chroma lanes run the SAME instruction stream: chroma is luma with the
+// p1/q1 updates and the strong filter switched off and tc = tc0 + 1 (8.7.2.3 / 8.7.2.4), so a warp filters its sixteen luma
+// lines and sixteen chroma lines in one pass instead of one after the other.
+__device__ __forceinline__ void filter_edge(int &p3, int &p2, int &p1, int &p0, int &q0, int &q1, int &q2, int &q3, int bs,
+                                            int alpha, int beta, int tcpack, bool chroma)
+{
+    if (bs == 0) return;
+    const int d0 = abs(p0 - q0);
+    if (!(d0 < alpha && abs(p1 - p0) < beta && abs(q1 - q0) < beta)) return;
+    const bool apb = !chroma && abs(p2 - p0) < beta, aqb = !chroma && abs(q2 - q0) < beta;
+    if (bs < 4) {
+        const int tc0 = (tcpack >> (8 * (bs - 1))) & 255;
+        const int tc = tc0 + (chroma ? 1 : (int)apb + (int)aqb);
+        const int d = clip3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
+        const int avg = (p0 + q0 + 1) >> 1;
+        if (apb) p1 += clip3(-tc0, tc0, (p2 + avg - (p1 << 1)) >> 1);
+        if (aqb) q1 += clip3(-tc0, tc0, (q2 + avg - (q1 << 1)) >> 1);
+        p0 = b2_clip255(p0 + d); q0 = b2_clip255(q0 - d);
+    } else {
+        const bool strong = d0 < ((alpha >> 2) + 2);
+        const int P0 = p0, P1 = p1, P2 = p2, Q0 = q0, Q1 = q1, Q2 = q2;
+        if (apb && strong) {
+            p0 = (P2 + 2 * P1 + 2 * P0 + 2 * Q0 + Q1 + 4) >> 3; p1 = (P2 + P1 + P0 + Q0 + 2) >> 2; p2 = (2 * p3 + 3 * P2 + P1 + P0 + Q0 + 4) >> 3;
+        } else {
+            p0 = (2 * P1 + P0 + Q1 + 2) >> 2;
+        }
+        if (aqb && strong) {
+            q0 = (P1 + 2 * P0 + 2 * Q0 + 2 * Q1 + Q2 + 4) >> 3; q1 = (P0 + Q0 + Q1 + Q2 + 2) >> 2; q2 = (2 * q3 + 3 * Q2 + Q1 + Q0 + P0 + 4) >> 3;
+        } else {
+            q0 = (2 * Q1 + Q0 + P1 + 2) >> 2;
+        }
+    }
+}
+// the four edges of one line of twenty samples (positions -4..15 across the macroblock; chroma lines use -4..7 and two edges)
+__device__ __forceinline__ void filter_line20(int (&px)[20], const int (&bsl)[4], int alpha, int beta, int tcpack, bool chroma)
+{
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+        filter_edge(px[4 * e], px[4 * e + 1], px[4 * e + 2], px[4 * e + 3], px[4 * e + 4], px[4 * e + 5], px[4 * e + 6], px[4 * e + 7], bsl[e],
+                    alpha, beta, tcpack, chroma);
+}
+
 // ---- row-pipelined form -------------------------------------------------------------------------------------------
 // what the boundary-strength rule needs of one b2_mbinfo_t (48 bytes = three 16-byte words: {mv, type.., i4_mode[0..7]},
 // {i4_mode[8..15], cost, nnz_mask}, {mv8[3], part | transform8x8 << 8 | i8_modes << 16})
@@ -266,43 +310,70 @@ __device__ __forceinline__ int lite_bs(const MbLite &mp, int pbx, int pby, const
     return (abs(ax - bx) >= 4 || abs(ay - by) >= 4) ? 1 : 0;
 }
 
-// cross-CTA progress flags live in global memory (cleared by the launcher ahead of every launch)
-__device__ __forceinline__ void st_flag_global(int *f, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(f), "r"(v) : "memory"); }
-__device__ __forceinline__ int ld_flag_global(const int *f) { int v; asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory"); return v; }
+// distributed shared memory: address of a shared-memory object of CTA `cta` of the cluster, plain stores to it, and the
+// cluster-scope fence that orders them ahead of the progress counter
+__device__ __forceinline__ uint32_t dsmem_addr(const void *local, unsigned cta)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void dsmem_st(uint32_t addr, uint32_t v) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void dsmem_st_relaxed(uint32_t addr, int v) { asm volatile("st.relaxed.cluster.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+
+// bottom rows of the macroblocks of one row, handed to the row below through shared memory: entry g % K8_RING belongs to the
+// row's g-th macroblock (counted over all rows the warp has walked): y[r * 4 + w] = luma row 12 + r, word w;
+// c[p * 4 + r * 2 + w] = chroma plane p, row 6 + r, word w
+constexpr int K8_RING = 8;
+struct K8Ring { uint32_t y[K8_RING][16]; uint32_t c[K8_RING][8]; };
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 2)
 k8_deblock_rows_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pitchc, size_t stride_y, size_t stride_c, int mbw, int mbh,
-                       int qp, int alpha_off, int beta_off, const b2_mbinfo_t *__restrict__ info, int *__restrict__ gflags)
+                       int qp, int alpha_off, int beta_off, const b2_mbinfo_t *__restrict__ info)
 {
     __shared__ K8Warp s_warp[WARPS];
-    __shared__ int s_flag[WARPS];         // s_flag[w]: macroblocks finished, over all its rows so far, by the warp that produces for warp w
+    // s_ring[w] / s_done[w]: bottom rows and progress of the producer OF warp w, i.e. of the row above warp w's row.  Warp w - 1
+    // of this CTA writes them for w > 0; the last warp of the previous CTA of the cluster writes s_ring[0] / s_done[0] through
+    // distributed shared memory.  s_back[w]: progress of the consumer of warp w (next warp, or warp 0 of the next CTA), for the
+    // ring's back-pressure.  Every warp only ever POLLS its own CTA's shared memory.
+    __shared__ K8Ring s_ring[WARPS];
+    __shared__ int s_done[WARPS];
+    __shared__ int s_back[WARPS];
     const int frame = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ncta = (int)gridDim.x, crank = (int)blockIdx.x;
+    const int ncta = (int)cluster_nctarank(), crank = (int)cluster_ctarank();
     const int gwarp = crank * WARPS + warp, nwarps = ncta * WARPS;
-    // gflag[c]: progress of the LAST warp of CTA c-1 (the producer of CTA c's first warp; CTA 0's is the last CTA's, for frames
-    // with more rows than warps).  CTAs of one frame are consecutive in dispatch order, so a producer CTA is resident no later
-    // than its consumer.
-    int *const gflag = gflags + (size_t)frame * 8;
     const b2_mbinfo_t *finfo = info + (size_t)frame * mbw * mbh;
     uint8_t *const py = ry + frame * stride_y, *const pu = ru + frame * stride_c, *const pv = rv + frame * stride_c;
-    const int qpc = chroma_qp(qp);
-    FiltConst fy, fcc;
-    const int ia = clip3(0, 51, qp + 2 * alpha_off), ib = clip3(0, 51, qp + 2 * beta_off);
-    const int iac = clip3(0, 51, qpc + 2 * alpha_off), ibc = clip3(0, 51, qpc + 2 * beta_off);
-    fy.alpha = c_alpha[ia]; fy.beta = c_beta[ib]; fcc.alpha = c_alpha[iac]; fcc.beta = c_beta[ibc];
-#pragma unroll
-    for (int i = 0; i < 3; i++) { fy.tc0[i] = c_tc0[ia][i]; fcc.tc0[i] = c_tc0[iac][i]; }
-    if (threadIdx.x < WARPS) s_flag[threadIdx.x] = 0;
-    __syncthreads();
+    // per-lane filter constants: lanes 0-15 carry luma lines, 16-31 chroma lines.  8.7.2.2: indexA = qPav + 2 * slice_alpha_c0_offset_div2,
+    // indexB = qPav + 2 * slice_beta_offset_div2, clipped to 0..51
+    const bool is_c = lane >= 16;
+    const int l_qp = is_c ? chroma_qp(qp) : qp;
+    const int l_ia = clip3(0, 51, l_qp + 2 * alpha_off), l_ib = clip3(0, 51, l_qp + 2 * beta_off);
+    const int l_alpha = c_alpha[l_ia], l_beta = c_beta[l_ib];
+    const int l_tc = c_tc0[l_ia][0] | c_tc0[l_ia][1] << 8 | c_tc0[l_ia][2] << 16;
+    const int cl = lane - 16, c_pl = (cl >> 3) & 1, c_i = cl & 7;             // chroma lanes: plane, row (vertical pass) / column (horizontal)
+    if (threadIdx.x < WARPS) { s_done[threadIdx.x] = 0; s_back[threadIdx.x] = 0; }
+    if (ncta > 1) cluster_barrier();      // nobody stores into a neighbour's counters before they are cleared
+    else __syncthreads();
 
     K8Warp &ws = s_warp[warp];
-    // the consumer of this warp's progress is the warp that owns the next row: the next warp of this CTA (shared-memory flag)
-    // or, for the last warp, the first warp of the next CTA (global flag); likewise on the consuming side
-    const bool prod_remote = warp == 0, cons_remote = warp == WARPS - 1;
-    int *const cons_gflag = &gflag[(crank + 1) % ncta];
-    const int *const prod_gflag = &gflag[crank];
+    // The row below belongs to the next warp of this CTA or, for the last warp, to warp 0 of the next CTA of the cluster: the
+    // bottom rows go into THAT warp's ring (s_ring[consumer warp] of the consumer's CTA) with st.shared::cluster, then the
+    // progress counter; the consumer reports back into s_back[] of this CTA the same way.  No global round trip and no
+    // GPU-scope fence anywhere on the chain.
+    const bool cons_remote = warp == WARPS - 1, prod_remote = warp == 0;
+    const unsigned cons_cta = cons_remote ? (unsigned)((crank + 1) % ncta) : (unsigned)crank;
+    const unsigned prod_cta = prod_remote ? (unsigned)((crank + ncta - 1) % ncta) : (unsigned)crank;
+    const int cons_w = cons_remote ? 0 : warp + 1, prod_w = prod_remote ? WARPS - 1 : warp - 1;
+    const uint32_t out_ring = dsmem_addr(&s_ring[cons_w], cons_cta);             // where this warp's bottom rows go
+    const uint32_t out_done = dsmem_addr(&s_done[cons_w], cons_cta);
+    const uint32_t out_back = dsmem_addr(&s_back[prod_w], prod_cta);             // where this warp reports what it has consumed
+    const volatile int *const prod_done = &s_done[warp];
+    const volatile int *const cons_done = &s_back[warp];
+    const K8Ring &prod_ring = s_ring[warp];
     // this lane's boundary-strength job: lanes 0-15 vertical edges, 16-31 horizontal edges; lane -> (edge e, segment k)
     const int dir = lane >> 4, e = (lane >> 2) & 3, k = lane & 3;
     // own-sample words: lane -> luma words (row l>>1, words 2*(l&1), 2*(l&1)+1), chroma word (plane l>>4, row (l>>1)&7, word l&1)
@@ -311,12 +382,16 @@ k8_deblock_rows_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pit
 
     int round = 0;
     for (int mby = gwarp; mby < mbh; mby += nwarps, round++) {
-        const int prod_base = ((mby - 1) / nwarps) * mbw;      // what the producer had published before it started row mby-1
+        const int prod_base = ((mby - 1) / nwarps) * mbw;      // what the producer had finished before it started row mby-1
         const int my_base = round * mbw;
+        const bool has_cons = mby + 1 < mbh;
+        // rows 13..15 (chroma: row 7) of a macroblock are last written by the row below (its top-edge filter); this warp only
+        // stores them when nobody below will, or when the row below reads them from global memory
+        const bool own_bottom = !has_cons;
         uint8_t *const rowy = py + (size_t)(B2_PAD + mby * 16) * pitch + B2_PAD;
         uint8_t *const rowu = pu + (size_t)(B2_PADC + mby * 8) * pitchc + B2_PADC;
         uint8_t *const rowv = pv + (size_t)(B2_PADC + mby * 8) * pitchc + B2_PADC;
-        // ---- prologue: own samples and boundary strengths of macroblock 0 ----
+        // ---- prologue: own samples and decision records of macroblock 0 ----
         uint32_t n0, n1, n2;
         MbLite lq, lp;
         {
@@ -328,6 +403,7 @@ k8_deblock_rows_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pit
             lp = (e == 0 && dir == 1 && mby > 0) ? load_lite(mq - mbw) : lq;
         }
         for (int mbx = 0; mbx < mbw; mbx++) {
+            const int g_me = my_base + mbx;                       // this macroblock's running number in this warp
             // ---- own samples (prefetched) -> tile; boundary strengths from the prefetched records ----
             *(uint32_t *)&ws.y[(oy_row + 4) * LP + 4 + oy_w * 4] = n0;
             *(uint32_t *)&ws.y[(oy_row + 4) * LP + 8 + oy_w * 4] = n1;
@@ -352,45 +428,72 @@ k8_deblock_rows_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pit
                 lq = load_lite(mq);
                 lp = e != 0 ? lq : (dir == 0 ? cur : (mby > 0 ? load_lite(mq - mbw) : lq));
             }
-            // ---- the four rows above: final once row mby-1 has finished macroblock mbx+1 ----
+            // ---- the four rows above: final once row mby-1 has finished macroblock mbx+1.  Fetched now, written into the
+            //      tile after the vertical pass (which only touches rows 0..15) ----
+            uint32_t top = 0;
             if (mby > 0) {
                 const int need = prod_base + min(mbx + 2, mbw);
-                if (prod_remote) { while (ld_flag_global(prod_gflag) < need) __nanosleep(100); }
-                else { while (*(volatile int *)&s_flag[warp] < need) __nanosleep(40); }     // sleeping keeps the issue slots for co-resident kernels
-                __threadfence();
-                if (lane < 16) {
-                    const int r = lane >> 2, w = lane & 3;        // rows -4..-1, words 0..3
-                    *(uint32_t *)&ws.y[r * LP + 4 + w * 4] = __ldcg((const uint32_t *)(rowy + (ptrdiff_t)(r - 4) * pitch + mbx * 16) + w);
-                } else if (lane < 24) {
-                    const int l = lane - 16, p = l >> 2, r = (l >> 1) & 1, w = l & 1;     // rows -2..-1, words 0..1
-                    *(uint32_t *)&ws.c[p][r * CP + 4 + w * 4] = __ldcg((const uint32_t *)((p ? rowv : rowu) + (ptrdiff_t)(r - 2) * pitchc + mbx * 8) + w);
-                }
+                while (*prod_done < need) { }
+                fence_cluster();
+                const int slot = (prod_base + mbx) % K8_RING;
+                if (lane < 16) top = prod_ring.y[slot][lane];
+                else if (lane < 24) top = prod_ring.c[slot][lane - 16];
             }
             __syncwarp();
-            // ---- vertical edges: luma lane = row, chroma lane-16 = (plane, row) ----
-            if (lane < 16) {
-                uint8_t *row = &ws.y[(lane + 4) * LP + 4];
+            // ---- vertical edges: luma lane = row, chroma lane-16 = (plane, row); the line lives in registers ----
+            {
+                uint8_t *rowp = is_c ? &ws.c[c_pl][(c_i + 2) * CP] : &ws.y[(lane + 4) * LP];
+                int px[20], bsl[4];
 #pragma unroll
-                for (int ee = 0; ee < 4; ee++) filter_line(row + 4 * ee, 1, ws.bs[0][ee][lane >> 2], fy, false);
-            } else {
-                const int l = lane - 16, p = l >> 3, r = l & 7;
-                uint8_t *row = &ws.c[p][(r + 2) * CP + 4];
+                for (int w = 0; w < 5; w++) {
+                    const uint32_t v = *(const uint32_t *)(rowp + 4 * w);      // chroma: words 3, 4 belong to the next row and are not used
+                    px[4 * w] = v & 255; px[4 * w + 1] = (v >> 8) & 255; px[4 * w + 2] = (v >> 16) & 255; px[4 * w + 3] = v >> 24;
+                }
+                const int seg = is_c ? c_i >> 1 : lane >> 2;
 #pragma unroll
-                for (int ee = 0; ee < 2; ee++) filter_line(row + 4 * ee, 1, ws.bs[0][2 * ee][r >> 1], fcc, true);
+                for (int ee = 0; ee < 4; ee++) bsl[ee] = is_c ? (ee < 2 ? ws.bs[0][2 * ee][seg] : 0) : ws.bs[0][ee][seg];
+                filter_line20(px, bsl, l_alpha, l_beta, l_tc, is_c);
+#pragma unroll
+                for (int w = 0; w < 5; w++)
+                    if (!is_c || w < 3)
+                        *(uint32_t *)(rowp + 4 * w) = (uint32_t)px[4 * w] | (uint32_t)px[4 * w + 1] << 8 | (uint32_t)px[4 * w + 2] << 16 | (uint32_t)px[4 * w + 3] << 24;
+            }
+            if (mby > 0) {
+                if (lane < 16) *(uint32_t *)&ws.y[(lane >> 2) * LP + 4 + (lane & 3) * 4] = top;          // rows -4..-1, words 0..3
+                else if (lane < 24) { const int l = lane - 16; *(uint32_t *)&ws.c[l >> 2][((l >> 1) & 1) * CP + 4 + (l & 1) * 4] = top; }
             }
             __syncwarp();
             // ---- horizontal edges: luma lane = column, chroma lane-16 = (plane, column) ----
-            if (lane < 16) {
-                uint8_t *col = &ws.y[4 * LP + lane + 4];
+            {
+                // sample i of the line sits `stride` bytes after sample i-1; chroma columns only exist for i = 2..11 (rows -2..7)
+                uint8_t *colp = is_c ? &ws.c[c_pl][4 + c_i] - 2 * CP : &ws.y[4 + lane];
+                const int stride = is_c ? CP : LP;
+                int px[20], bsl[4];
 #pragma unroll
-                for (int ee = 0; ee < 4; ee++) filter_line(col + 4 * ee * LP, LP, ws.bs[1][ee][lane >> 2], fy, false);
-            } else {
-                const int l = lane - 16, p = l >> 3, x = l & 7;
-                uint8_t *col = &ws.c[p][2 * CP + x + 4];
+                for (int i = 0; i < 20; i++) px[i] = (!is_c || (i >= 2 && i < 12)) ? colp[i * stride] : 0;
+                const int seg = is_c ? c_i >> 1 : lane >> 2;
 #pragma unroll
-                for (int ee = 0; ee < 2; ee++) filter_line(col + 4 * ee * CP, CP, ws.bs[1][2 * ee][x >> 1], fcc, true);
+                for (int ee = 0; ee < 4; ee++) bsl[ee] = is_c ? (ee < 2 ? ws.bs[1][2 * ee][seg] : 0) : ws.bs[1][ee][seg];
+                filter_line20(px, bsl, l_alpha, l_beta, l_tc, is_c);
+#pragma unroll
+                for (int i = 1; i < 19; i++)                                       // p2 of the first edge .. q2 of the last
+                    if (!is_c || (i >= 2 && i < 12)) colp[i * stride] = (uint8_t)px[i];
             }
             __syncwarp();
+            // ---- hand the bottom rows to the row below: this macroblock's entry, and the four rightmost columns of the previous
+            //      entry, which this macroblock's left edge has just finished ----
+            if (has_cons) {
+                while (*cons_done < g_me - K8_RING + 1) { }                         // the entry about to be overwritten has been read
+                const int slot = g_me % K8_RING, pslot = (g_me + K8_RING - 1) % K8_RING;
+                constexpr uint32_t RY = (uint32_t)offsetof(K8Ring, y), RC = (uint32_t)offsetof(K8Ring, c);
+                if (lane < 16) dsmem_st(out_ring + RY + (slot * 16 + lane) * 4, *(const uint32_t *)&ws.y[(16 + (lane >> 2)) * LP + 4 + (lane & 3) * 4]);
+                else if (lane < 24) { const int l = lane - 16; dsmem_st(out_ring + RC + (slot * 8 + l) * 4, *(const uint32_t *)&ws.c[l >> 2][(8 + ((l >> 1) & 1)) * CP + 4 + (l & 1) * 4]); }
+                else if (mbx > 0) {
+                    const int l = lane - 24;                                      // 0..3 luma rows 12..15, 4..7 chroma (plane, row 6..7)
+                    if (l < 4) dsmem_st(out_ring + RY + (pslot * 16 + l * 4 + 3) * 4, *(const uint32_t *)&ws.y[(16 + l) * LP]);
+                    else dsmem_st(out_ring + RC + (pslot * 8 + ((l - 4) >> 1) * 4 + ((l - 4) & 1) * 2 + 1) * 4, *(const uint32_t *)&ws.c[(l - 4) >> 1][(8 + ((l - 4) & 1)) * CP]);
+                }
+            }
             // ---- write back what can have changed: own MB, 3 (luma) / 1 (chroma) lines into the top MB, one word into the left MB ----
             uint8_t *gy = rowy + mbx * 16;
             for (int i = lane; i < 95; i += 32) {                  // luma rows -3..15 (19 rows) x 5 words
@@ -398,6 +501,7 @@ k8_deblock_rows_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pit
                 const int y = r - 4;
                 if (w == 0 && (mbx == 0 || y < 0)) continue;        // nothing left of the picture; corner block is never modified
                 if (y < 0 && mby == 0) continue;
+                if (y >= 13 && !own_bottom) continue;               // the row below stores these after its top-edge filter
                 *(uint32_t *)(gy + (ptrdiff_t)y * pitch + (w - 1) * 4) = *(const uint32_t *)&ws.y[r * LP + w * 4];
             }
             for (int i = lane; i < 54; i += 32) {                  // chroma rows -1..7 (9 rows) x 3 words x 2 planes
@@ -405,15 +509,16 @@ k8_deblock_rows_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pit
                 const int y = r - 2;
                 if (w == 0 && (mbx == 0 || y < 0)) continue;
                 if (y < 0 && mby == 0) continue;
+                if (y >= 7 && !own_bottom) continue;
                 uint8_t *gc = (p ? rowv : rowu) + mbx * 8;
                 *(uint32_t *)(gc + (ptrdiff_t)y * pitchc + (w - 1) * 4) = *(const uint32_t *)&ws.c[p][r * CP + w * 4];
             }
-            // ---- publish: every lane's stores are visible GPU-wide before the flag moves ----
-            __threadfence();
+            // ---- publish: the ring stores of every lane are ordered ahead of the counter; tell the row above what has been read ----
+            fence_cluster();
             __syncwarp();
             if (lane == 0) {
-                if (cons_remote) st_flag_global(cons_gflag, my_base + mbx + 1);
-                else *(volatile int *)&s_flag[warp + 1] = my_base + mbx + 1;
+                if (has_cons) dsmem_st_relaxed(out_done, g_me + 1);
+                if (mby > 0) dsmem_st_relaxed(out_back, prod_base + mbx + 1);     // in the producer's numbering
             }
             // ---- carry the four rightmost columns over as the next macroblock's left neighbour ----
             if (lane < 16) *(uint32_t *)&ws.y[(lane + 4) * LP] = *(const uint32_t *)&ws.y[(lane + 4) * LP + 16];
@@ -421,6 +526,7 @@ k8_deblock_rows_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pit
             __syncwarp();
         }
     }
+    if (ncta > 1) cluster_barrier();      // no CTA leaves while a neighbour may still store into its shared memory
 }
 
 }  // namespace
@@ -433,16 +539,30 @@ int b2_launch_deblock(uint8_t *const rec[3], int pitch, int pitchc, size_t strid
     if (wavefront) {
         const int maxdiag = mbh < (mbw + 1) / 2 ? mbh : (mbw + 1) / 2;
         while (ncta < 8 && ncta * K8_WARPS < maxdiag) ncta *= 2;
-    } else {
-        ncta = (mbh + K8_WARPS - 1) / K8_WARPS;                   // one warp per macroblock row; beyond 128 rows warps take several
-        if (ncta > 8) ncta = 8;
     }
     if (!wavefront) {
-        // plain launch: no cluster to place, so a frame's few CTAs slot in beside whatever else runs on the GPU
-        B2_CUDA_OK(cudaMemsetAsync(d_flags, 0, (size_t)nframes * 8 * sizeof(int), st));
-        k8_deblock_rows_kernel<K8_WARPS><<<dim3(ncta, nframes), K8_WARPS * 32, 0, st>>>(rec[0], rec[1], rec[2], pitch, pitchc, stride_y, stride_c,
-                                                                                        mbw, mbh, qp, alpha_off, beta_off, d_info, d_flags);
-        B2_CUDA_OK(cudaGetLastError());
+        // One warp per macroblock row (beyond 8 CTAs of rows, warps take several); the CTAs of a frame form a cluster so that
+        // the hand-off between the last row of one CTA and the first row of the next stays in (distributed) shared memory.
+        // 8 warps per CTA: the register-resident lines need ~120 registers (16 warps per CTA squeeze them into 64 with spills:
+        // B2_K8_ROW_WARPS=16, kept for measurements).
+        static const int rw = getenv("B2_K8_ROW_WARPS") && atoi(getenv("B2_K8_ROW_WARPS")) == 16 ? 16 : 8;
+        ncta = (mbh + rw - 1) / rw;
+        if (ncta > 8) ncta = 8;
+        (void)d_flags;
+        cudaLaunchConfig_t rcfg = {};
+        rcfg.gridDim = dim3(ncta, nframes, 1);
+        rcfg.blockDim = dim3(rw * 32, 1, 1);
+        rcfg.stream = st;
+        cudaLaunchAttribute rattr[1];
+        rattr[0].id = cudaLaunchAttributeClusterDimension;
+        rattr[0].val.clusterDim.x = ncta; rattr[0].val.clusterDim.y = 1; rattr[0].val.clusterDim.z = 1;
+        rcfg.attrs = rattr; rcfg.numAttrs = 1;
+        if (rw == 16)
+            B2_CUDA_OK(cudaLaunchKernelEx(&rcfg, k8_deblock_rows_kernel<16>, rec[0], rec[1], rec[2], pitch, pitchc, stride_y, stride_c, mbw, mbh, qp,
+                                          alpha_off, beta_off, d_info));
+        else
+            B2_CUDA_OK(cudaLaunchKernelEx(&rcfg, k8_deblock_rows_kernel<8>, rec[0], rec[1], rec[2], pitch, pitchc, stride_y, stride_c, mbw, mbh, qp,
+                                          alpha_off, beta_off, d_info));
         return 0;
     }
     cudaLaunchConfig_t cfg = {};

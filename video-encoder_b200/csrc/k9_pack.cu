@@ -8,55 +8,95 @@
 // order (the host walks the stream with the same rule, include/b2enc_types.h).  K9b, on the copy-out stream, writes
 // exactly the used bytes into pinned host memory with coalesced 16-byte stores (the size is only known on the
 // device, so a cudaMemcpy cannot do it without a host round trip).
-// Bound: latency (one CTA per frame does a block-wide prefix sum); algorithmic bytes = 4 B/MB of masks + 2 x the
-// packed size.
+// Bound: latency / HBM; algorithmic bytes = 4 B/MB of masks + 2 x the packed size.
+//
+// K9a is two small launches so that a frame is packed by many CTAs instead of one (one CTA walking 8,160 macroblocks was a
+// 0.1-0.3 ms link in the per-frame dependency chain): k9a_count sums the present blocks of every chunk of 256 macroblocks,
+// k9a_scatter adds up the chunks in front of its own (at most a few dozen numbers), then one warp per macroblock copies that
+// macroblock's blocks -- lane = 16-byte half block -- to their place in the stream.
 #include "b2_common.cuh"
 #include "b2_internal.h"
 
 namespace {
 
-constexpr int K9_THREADS = 1024;
+constexpr int K9_CHUNK = 256;             // macroblocks per CTA = threads per CTA
 
-__global__ void __launch_bounds__(K9_THREADS)
-k9a_pack_levels_kernel(const b2_mbinfo_t *__restrict__ info, const b2_mbcoef_t *__restrict__ coef, uint8_t *__restrict__ packed,
-                       size_t packed_stride, uint32_t *__restrict__ nblocks, unsigned long long *__restrict__ cum_bytes, int nmb)
+__global__ void __launch_bounds__(K9_CHUNK)
+k9a_count_kernel(const b2_mbinfo_t *__restrict__ info, uint32_t *__restrict__ chunk_cnt, int nmb, int nchunk)
 {
-    __shared__ uint32_t s_warp[32];
-    const int frame = blockIdx.x;
+    __shared__ uint32_t s_warp[K9_CHUNK / 32];
+    const int frame = blockIdx.y, m = blockIdx.x * K9_CHUNK + threadIdx.x;
+    uint32_t cnt = m < nmb ? __popc(b2_coef_present(&info[(size_t)frame * nmb + m])) : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int i = 0; i < K9_CHUNK / 32; i++) t += s_warp[i];
+        chunk_cnt[(size_t)frame * nchunk + blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(K9_CHUNK)
+k9a_scatter_kernel(const b2_mbinfo_t *__restrict__ info, const b2_mbcoef_t *__restrict__ coef, const uint32_t *__restrict__ chunk_cnt,
+                   uint8_t *__restrict__ packed, size_t packed_stride, uint32_t *__restrict__ nblocks,
+                   unsigned long long *__restrict__ cum_bytes, int nmb, int nchunk)
+{
+    __shared__ uint32_t s_off[K9_CHUNK + 1];      // exclusive block offset of every macroblock of the chunk inside the frame's stream
+    __shared__ uint32_t s_mask[K9_CHUNK];
+    __shared__ uint32_t s_warp[K9_CHUNK / 32];
+    __shared__ uint32_t s_base;
+    const int frame = blockIdx.y, chunk = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const b2_mbinfo_t *fi = info + (size_t)frame * nmb;
     const b2_mbcoef_t *fc = coef + (size_t)frame * nmb;
-    uint4 *out = (uint4 *)(packed + (size_t)frame * packed_stride);
-    const int per = (nmb + K9_THREADS - 1) / K9_THREADS;
-    const int mb0 = threadIdx.x * per, mb1 = min(nmb, mb0 + per);
-    uint32_t cnt = 0;
-    for (int m = mb0; m < mb1; m++) cnt += __popc(b2_coef_present(&fi[m]));
-    // block-wide exclusive scan of cnt
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int m = chunk * K9_CHUNK + threadIdx.x;
+    const uint32_t pm = m < nmb ? b2_coef_present(&fi[m]) : 0;
+    const uint32_t cnt = __popc(pm);
+    s_mask[threadIdx.x] = pm;
+    // blocks in front of this chunk: the chunk totals of k9a_count (a frame has a few dozen chunks)
+    if (warp == 0) {
+        uint32_t b = 0;
+        for (int i = lane; i < nchunk; i += 32) {
+            if (i < chunk) b += chunk_cnt[(size_t)frame * nchunk + i];
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        if (lane == 0) s_base = b;
+    }
+    // exclusive scan of cnt over the chunk
     uint32_t inc = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    if (warp == 0) {
-        uint32_t w = s_warp[lane], wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
-        s_warp[lane] = wi - w;                                        // exclusive offset of each warp
-        if (lane == 31) {
-            nblocks[frame] = wi;
-            atomicAdd(cum_bytes, (unsigned long long)wi * 32ull);
-        }
+    uint32_t woff = 0;
+    for (int i = 0; i < warp; i++) woff += s_warp[i];
+    s_off[threadIdx.x] = s_base + woff + inc - cnt;
+    if (chunk == nchunk - 1 && threadIdx.x == K9_CHUNK - 1) {          // last thread of the last chunk knows the frame total
+        const uint32_t total = s_base + woff + inc;
+        nblocks[frame] = total;
+        atomicAdd(cum_bytes, (unsigned long long)total * 32ull);
     }
     __syncthreads();
-    uint32_t off = s_warp[warp] + inc - cnt;                           // in 32-byte blocks
-    for (int m = mb0; m < mb1; m++) {
-        uint32_t pm = b2_coef_present(&fi[m]);
-        const uint4 *src = (const uint4 *)fc[m].blk;
-        while (pm) {
-            const int b = __ffs(pm) - 1;
-            pm &= pm - 1;
-            out[2 * off] = src[2 * b]; out[2 * off + 1] = src[2 * b + 1];
-            off++;
+    // copy: one warp per macroblock, lane = (block, 16-byte half); a macroblock rarely holds more than 16 present blocks
+    uint4 *out = (uint4 *)(packed + (size_t)frame * packed_stride);
+    for (int j = warp; j < K9_CHUNK; j += K9_CHUNK / 32) {
+        const int mm = chunk * K9_CHUNK + j;
+        if (mm >= nmb) break;
+        const uint32_t mask = s_mask[j];
+        const int nb = __popc(mask);
+        if (!nb) continue;
+        const uint4 *src = (const uint4 *)fc[mm].blk;
+        const uint32_t off = s_off[j];
+        for (int t0 = 0; t0 < nb; t0 += 16) {                           // 16 present blocks per pass
+            const int t = t0 + (lane >> 1);
+            if (t < nb) {
+                const int bsel = (int)__fns(mask, 0, t + 1);            // the t-th present block
+                out[2 * (off + t) + (lane & 1)] = src[2 * bsel + (lane & 1)];
+            }
         }
     }
 }
@@ -77,12 +117,17 @@ k9b_copy_out_kernel(const uint8_t *__restrict__ packed, size_t packed_stride, co
 }  // namespace
 
 int b2_launch_pack_levels(const b2_mbinfo_t *d_info, const b2_mbcoef_t *d_coef, uint8_t *d_packed, size_t packed_stride,
-                          uint32_t *d_nblocks, unsigned long long *d_cum_bytes, int nmb, int nframes, cudaStream_t st)
+                          uint32_t *d_nblocks, unsigned long long *d_cum_bytes, uint32_t *d_chunk_cnt, int nmb, int nframes, cudaStream_t st)
 {
-    k9a_pack_levels_kernel<<<nframes, K9_THREADS, 0, st>>>(d_info, d_coef, d_packed, packed_stride, d_nblocks, d_cum_bytes, nmb);
+    const int nchunk = b2_pack_chunks(nmb);
+    k9a_count_kernel<<<dim3(nchunk, nframes), K9_CHUNK, 0, st>>>(d_info, d_chunk_cnt, nmb, nchunk);
+    k9a_scatter_kernel<<<dim3(nchunk, nframes), K9_CHUNK, 0, st>>>(d_info, d_coef, d_chunk_cnt, d_packed, packed_stride, d_nblocks, d_cum_bytes,
+                                                                   nmb, nchunk);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
 }
+
+int b2_pack_chunks(int nmb) { return (nmb + K9_CHUNK - 1) / K9_CHUNK; }
 
 int b2_launch_pack_copy_out(const uint8_t *d_packed, size_t packed_stride, const uint32_t *d_nblocks, uint8_t *h_packed,
                             uint32_t *h_nblocks, int nframes, cudaStream_t st)

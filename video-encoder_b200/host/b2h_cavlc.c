@@ -15,7 +15,10 @@
 static int level_idc_for(int mbw, int mbh, int fps_num, int fps_den)
 {
     /* smallest level whose MaxFS / MaxMBPS cover the stream (Table A-1) */
+    /* level 1b (idc 11 + constraint_set3) and the levels that differ from their predecessor only in bit rate (2 vs 1.3, 4.1 vs 4)
+     * are not listed: with constant QP there is no bit-rate bound to tell them apart, the smaller idc covers the stream */
     static const struct { int idc, fs; long mbps; } lv[] = {
+        {10, 99, 1485}, {11, 396, 3000}, {12, 396, 6000}, {13, 396, 11880}, {21, 792, 19800}, {22, 1620, 20250},
         {30, 1620, 40500}, {31, 3600, 108000}, {32, 5120, 216000}, {40, 8192, 245760}, {42, 8704, 522240},
         {50, 22080, 589824}, {51, 36864, 983040}, {52, 36864, 2073600}};
     long fs = (long)mbw * mbh;

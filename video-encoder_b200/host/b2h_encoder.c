@@ -236,6 +236,10 @@ static int device_count_wanted(const b2_param_t *p)
 b2_t *b2_encoder_open(b2_param_t *p)
 {
     if (!p || p->i_width < 16 || p->i_height < 16) { fprintf(stderr, "b2enc: bad picture size\n"); return NULL; }
+    if ((long)((p->i_width + 15) / 16) * ((p->i_height + 15) / 16) > 36864) {          /* MaxFS of level 5.2, the largest there is */
+        fprintf(stderr, "b2enc: %dx%d exceeds H.264 level 5.2 (36,864 macroblocks per frame)\n", p->i_width, p->i_height);
+        return NULL;
+    }
     b2_t *h = (b2_t *)calloc(1, sizeof(*h));
     if (!h) return NULL;
     h->p = *p;
