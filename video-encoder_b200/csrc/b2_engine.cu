@@ -565,6 +565,7 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
     }
     if (do_intra) {
         KScope k(e, st, 6);
+        e->launches++;                                   // K7 + its cbp pass
         if (b2_launch_intra_recon(cur, rec, e->pitch, e->pitchc, e->stride_y, e->stride_c, e->mbw, e->mbh, ns, c.qp, !is_p, info, coef, st))
             return -1;
     }

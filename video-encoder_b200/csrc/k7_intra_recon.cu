@@ -52,16 +52,11 @@ __device__ __forceinline__ unsigned cluster_nctarank()
     return r;
 }
 
-// publish this task's nnz bits; the second finisher of (luma, chroma) computes cbp
-__device__ __forceinline__ void publish_mask(b2_mbinfo_t *mi, uint32_t bits, bool is_luma)
+// publish this task's nnz bits: a fire-and-forget reduction (RED.OR, nothing returned), so the warp does not sit out an L2 round
+// trip at the end of every link of the dependency chain; cbp is derived from the finished masks by k7_cbp_kernel afterwards
+__device__ __forceinline__ void publish_mask(b2_mbinfo_t *mi, uint32_t bits, bool)
 {
-    const uint32_t me = is_luma ? 0x40000000u : 0x80000000u, other = is_luma ? 0x80000000u : 0x40000000u;
-    const uint32_t old = atomicOr(&mi->nnz_mask, bits | me);
-    if (old & other) {
-        const uint32_t full = (old | bits) & 0x3fffffffu;
-        mi->nnz_mask = full;
-        mi->cbp = (uint8_t)cbp_from_mask(mi->mb_type, full);
-    }
+    if (bits) atomicOr(&mi->nnz_mask, bits);
 }
 
 // ---- per-pixel intra 4x4 prediction straight from the shared-memory tile ---------------------------------
@@ -551,6 +546,16 @@ k7_intra_wavefront_kernel(FramePlanes fp, int mbw, int mbh, int qp, b2_mbinfo_t 
     }
 }
 
+// coded_block_pattern of the intra macroblocks from their finished masks (luma and chroma tasks OR their bits in independently)
+__global__ void __launch_bounds__(256)
+k7_cbp_kernel(b2_mbinfo_t *__restrict__ info, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int t = info[i].mb_type;
+    if (t != B2_MB_P16x16) info[i].cbp = (uint8_t)cbp_from_mask(t, info[i].nnz_mask);
+}
+
 }  // namespace
 
 int b2_launch_intra_recon(const uint8_t *const cur[3], uint8_t *const rec[3], int pitch, int pitchc, size_t stride_y,
@@ -578,5 +583,8 @@ int b2_launch_intra_recon(const uint8_t *const cur[3], uint8_t *const rec[3], in
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (all_intra) B2_CUDA_OK(cudaLaunchKernelEx(&cfg, k7_intra_wavefront_kernel<K7_WARPS_I>, fp, mbw, mbh, qp, d_info, d_coef));
     else B2_CUDA_OK(cudaLaunchKernelEx(&cfg, k7_intra_wavefront_kernel<K7_WARPS_P>, fp, mbw, mbh, qp, d_info, d_coef));
+    const int n = mbw * mbh * nframes;
+    k7_cbp_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_info, n);
+    B2_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -326,7 +326,8 @@ __device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cl
 // row's g-th macroblock (counted over all rows the warp has walked): y[r * 4 + w] = luma row 12 + r, word w;
 // c[p * 4 + r * 2 + w] = chroma plane p, row 6 + r, word w
 constexpr int K8_RING = 8;
-struct K8Ring { uint32_t y[K8_RING][16]; uint32_t c[K8_RING][8]; };
+struct K8Ring { uint32_t y[K8_RING][16]; uint32_t c[K8_RING][8]; };      // c directly behind y: word index K8_RING * 16 + ...
+static_assert(offsetof(K8Ring, c) == K8_RING * 16 * 4, "K8Ring layout");
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 2)
@@ -379,6 +380,23 @@ k8_deblock_rows_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pit
     // own-sample words: lane -> luma words (row l>>1, words 2*(l&1), 2*(l&1)+1), chroma word (plane l>>4, row (l>>1)&7, word l&1)
     const int oy_row = lane >> 1, oy_w = (lane & 1) * 2;
     const int oc_p = lane >> 4, oc_row = (lane >> 1) & 7, oc_w = lane & 1;
+
+    // Write-back roles, fixed per lane: the tile words that can have changed are luma rows -3..15 x 5 words (95 items, lane takes
+    // items lane, lane + 32, lane + 64) and chroma rows -1..7 x 3 words x 2 planes (54 items, lane and lane + 32).  Per item:
+    // tile byte offset, offset from the macroblock's first sample in the plane, and what kind of neighbour it touches.
+    int wb_t[5], wb_g[5], wb_k[5];        // kind bits: 1 = left neighbour's word, 2 = rows above, 4 = rows the row below rewrites
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int i = lane + 32 * j, r = i / 5 + 1, w = i - (i / 5) * 5, y = r - 4;
+        wb_t[j] = r * LP + w * 4; wb_g[j] = y * pitch + (w - 1) * 4;
+        wb_k[j] = i < 95 ? ((w == 0 ? 1 : 0) | (y < 0 ? 2 : 0) | (y >= 13 ? 4 : 0)) : 8;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int i = lane + 32 * j, p = i / 27, kk = i - p * 27, r = kk / 3 + 1, w = kk - (kk / 3) * 3, y = r - 2;
+        wb_t[3 + j] = (int)(&ws.c[p & 1][r * CP + w * 4] - &ws.y[0]); wb_g[3 + j] = y * pitchc + (w - 1) * 4;
+        wb_k[3 + j] = i < 54 ? ((w == 0 ? 1 : 0) | (y < 0 ? 2 : 0) | (y >= 7 ? 4 : 0) | (p ? 16 : 0)) : 8;
+    }
 
     int round = 0;
     for (int mby = gwarp; mby < mbh; mby += nwarps, round++) {
@@ -434,7 +452,8 @@ k8_deblock_rows_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pit
             if (mby > 0) {
                 const int need = prod_base + min(mbx + 2, mbw);
                 while (*prod_done < need) { }
-                fence_cluster();
+                if (prod_remote) fence_cluster();                 // the ring entry came through distributed shared memory
+                else __threadfence_block();
                 const int slot = (prod_base + mbx) % K8_RING;
                 if (lane < 16) top = prod_ring.y[slot][lane];
                 else if (lane < 24) top = prod_ring.c[slot][lane - 16];
@@ -485,40 +504,47 @@ k8_deblock_rows_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pit
             if (has_cons) {
                 while (*cons_done < g_me - K8_RING + 1) { }                         // the entry about to be overwritten has been read
                 const int slot = g_me % K8_RING, pslot = (g_me + K8_RING - 1) % K8_RING;
-                constexpr uint32_t RY = (uint32_t)offsetof(K8Ring, y), RC = (uint32_t)offsetof(K8Ring, c);
-                if (lane < 16) dsmem_st(out_ring + RY + (slot * 16 + lane) * 4, *(const uint32_t *)&ws.y[(16 + (lane >> 2)) * LP + 4 + (lane & 3) * 4]);
-                else if (lane < 24) { const int l = lane - 16; dsmem_st(out_ring + RC + (slot * 8 + l) * 4, *(const uint32_t *)&ws.c[l >> 2][(8 + ((l >> 1) & 1)) * CP + 4 + (l & 1) * 4]); }
+                // which word of the consumer's ring this lane writes, and from where in the tile
+                int widx = -1; uint32_t wval = 0;
+                if (lane < 16) { widx = slot * 16 + lane; wval = *(const uint32_t *)&ws.y[(16 + (lane >> 2)) * LP + 4 + (lane & 3) * 4]; }
+                else if (lane < 24) { const int l = lane - 16; widx = K8_RING * 16 + slot * 8 + l; wval = *(const uint32_t *)&ws.c[l >> 2][(8 + ((l >> 1) & 1)) * CP + 4 + (l & 1) * 4]; }
                 else if (mbx > 0) {
                     const int l = lane - 24;                                      // 0..3 luma rows 12..15, 4..7 chroma (plane, row 6..7)
-                    if (l < 4) dsmem_st(out_ring + RY + (pslot * 16 + l * 4 + 3) * 4, *(const uint32_t *)&ws.y[(16 + l) * LP]);
-                    else dsmem_st(out_ring + RC + (pslot * 8 + ((l - 4) >> 1) * 4 + ((l - 4) & 1) * 2 + 1) * 4, *(const uint32_t *)&ws.c[(l - 4) >> 1][(8 + ((l - 4) & 1)) * CP]);
+                    if (l < 4) { widx = pslot * 16 + l * 4 + 3; wval = *(const uint32_t *)&ws.y[(16 + l) * LP]; }
+                    else { widx = K8_RING * 16 + pslot * 8 + ((l - 4) >> 1) * 4 + ((l - 4) & 1) * 2 + 1; wval = *(const uint32_t *)&ws.c[(l - 4) >> 1][(8 + ((l - 4) & 1)) * CP]; }
+                }
+                if (widx >= 0) {
+                    if (cons_remote) dsmem_st(out_ring + widx * 4, wval);          // into the next CTA of the cluster
+                    else ((uint32_t *)&s_ring[warp + 1])[widx] = wval;
                 }
             }
             // ---- write back what can have changed: own MB, 3 (luma) / 1 (chroma) lines into the top MB, one word into the left MB ----
-            uint8_t *gy = rowy + mbx * 16;
-            for (int i = lane; i < 95; i += 32) {                  // luma rows -3..15 (19 rows) x 5 words
-                const int r = i / 5 + 1, w = i - (i / 5) * 5;       // tile row r = y + 4, y = -3..15
-                const int y = r - 4;
-                if (w == 0 && (mbx == 0 || y < 0)) continue;        // nothing left of the picture; corner block is never modified
-                if (y < 0 && mby == 0) continue;
-                if (y >= 13 && !own_bottom) continue;               // the row below stores these after its top-edge filter
-                *(uint32_t *)(gy + (ptrdiff_t)y * pitch + (w - 1) * 4) = *(const uint32_t *)&ws.y[r * LP + w * 4];
-            }
-            for (int i = lane; i < 54; i += 32) {                  // chroma rows -1..7 (9 rows) x 3 words x 2 planes
-                const int p = i / 27, kk = i - p * 27, r = kk / 3 + 1, w = kk - (kk / 3) * 3;
-                const int y = r - 2;
-                if (w == 0 && (mbx == 0 || y < 0)) continue;
-                if (y < 0 && mby == 0) continue;
-                if (y >= 7 && !own_bottom) continue;
-                uint8_t *gc = (p ? rowv : rowu) + mbx * 8;
-                *(uint32_t *)(gc + (ptrdiff_t)y * pitchc + (w - 1) * 4) = *(const uint32_t *)&ws.c[p][r * CP + w * 4];
+            {
+                // an item is skipped when it is a corner (left AND above: never modified), lies outside the picture, or belongs to
+                // the rows the row below stores after its own top-edge filter
+                const int skip = 8 | (mbx == 0 ? 1 : 0) | (mby == 0 ? 2 : 0) | (own_bottom ? 0 : 4);
+                uint8_t *gy = rowy + mbx * 16, *gu = rowu + mbx * 8, *gv = rowv + mbx * 8;
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    const int kd = wb_k[j];
+                    if ((kd & skip) || (kd & 3) == 3) continue;
+                    uint8_t *g = j < 3 ? gy : ((kd & 16) ? gv : gu);
+                    *(uint32_t *)(g + wb_g[j]) = *(const uint32_t *)(&ws.y[0] + wb_t[j]);
+                }
             }
             // ---- publish: the ring stores of every lane are ordered ahead of the counter; tell the row above what has been read ----
-            fence_cluster();
+            if (cons_remote || prod_remote) fence_cluster();
+            else __threadfence_block();
             __syncwarp();
             if (lane == 0) {
-                if (has_cons) dsmem_st_relaxed(out_done, g_me + 1);
-                if (mby > 0) dsmem_st_relaxed(out_back, prod_base + mbx + 1);     // in the producer's numbering
+                if (has_cons) {
+                    if (cons_remote) dsmem_st_relaxed(out_done, g_me + 1);
+                    else *(volatile int *)&s_done[warp + 1] = g_me + 1;
+                }
+                if (mby > 0) {                                                    // in the producer's numbering
+                    if (prod_remote) dsmem_st_relaxed(out_back, prod_base + mbx + 1);
+                    else *(volatile int *)&s_back[warp - 1] = prod_base + mbx + 1;
+                }
             }
             // ---- carry the four rightmost columns over as the next macroblock's left neighbour ----
             if (lane < 16) *(uint32_t *)&ws.y[(lane + 4) * LP] = *(const uint32_t *)&ws.y[(lane + 4) * LP + 16];
@@ -547,7 +573,15 @@ int b2_launch_deblock(uint8_t *const rec[3], int pitch, int pitchc, size_t strid
         // B2_K8_ROW_WARPS=16, kept for measurements).
         static const int rw = getenv("B2_K8_ROW_WARPS") && atoi(getenv("B2_K8_ROW_WARPS")) == 16 ? 16 : 8;
         ncta = (mbh + rw - 1) / rw;
-        if (ncta > 8) ncta = 8;
+        if (ncta > 8) {
+            // tall pictures (4K: 135 rows): a cluster of up to 16 CTAs (non-portable size, supported on B200) keeps one warp per row;
+            // with 8 CTAs the rows beyond the 64th would have to wait for a warp of the first rows to finish its whole row
+            // (the attribute is per device; engines may live on several devices of one process, so it is set on every such launch)
+            const bool np_ok = (rw == 16 ? cudaFuncSetAttribute(k8_deblock_rows_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)
+                                         : cudaFuncSetAttribute(k8_deblock_rows_kernel<8>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)) == cudaSuccess;
+            ncta = np_ok ? (ncta > 16 ? 16 : ncta) : 8;
+            cudaGetLastError();
+        }
         (void)d_flags;
         cudaLaunchConfig_t rcfg = {};
         rcfg.gridDim = dim3(ncta, nframes, 1);
