@@ -133,7 +133,8 @@ def dropin_leg(b2enc, b2oracle, deblock, transform8x8, partitions, frames=2048, 
     enc = b2enc.DropInEncoder(W, H, preset="slow" if MERANGE == 32 else "medium", tune="film", quality=QP, fps=(60, 1), annexb=0, **ext)
     t0 = time.perf_counter(); nout = 0; nbytes = 0; first = None
     for t in range(frames):
-        size = enc.encode(src[t % 16], t)[0]
+        # the reference's per-frame pair: sws_scale(decoded picture -> pic_in), x264_encoder_encode(pic_in) (av_encode.c:545-547, :970)
+        size = enc.encode_via_sws("yuv420p", src[t % 16], t)[0]
         if size > 0:
             nout += 1; nbytes += size
             if first is None: first = t + 1
@@ -148,7 +149,7 @@ def dropin_leg(b2enc, b2oracle, deblock, transform8x8, partitions, frames=2048, 
             "deblocking_filter": "x264 default (on, tune film -1:-1)" if deblock is None else bool(deblock),
             "first_output_after_pictures": first, "host_cores": os.cpu_count(),
             "api": "b2_param_default_preset / b2_encoder_open / b2_picture_alloc / b2_encoder_encode / b2_encoder_delayed_frames "
-                   "(x264 mirror, include/b2enc.h), driven from Python: one picture per call, pipeline fill and drain inside the timed region",
+                   "(x264 mirror, include/b2enc.h) with b2_sws_scale(decoder picture -> pic_in) in front of every encode call, as av_encode.c:545-547/:970 does; driven from Python: one picture per call, pipeline fill and drain inside the timed region",
             "note": "entropy coding (CABAC) on the host cores is part of this call sequence; the encode stage itself is `e2e`"}
 
 

@@ -45,9 +45,9 @@ b2_sws_context_t *b2_sws_getContext(int srcW, int srcH, int srcFormat, int dstW,
  * When dst are the planes of a b2_picture_alloc picture -- the reference's only use: x264.pic_in, :415, :545-547 -- the
  * conversion is DEFERRED into the b2_encoder_encode call that picture is handed to next (:970): the source is staged in
  * page-locked memory belonging to the picture, uploaded once, and K0 writes straight into the encoder's device planes.
- * The picture's host planes are then only valid for yuv420p sources (where the staging is the picture itself); pass
- * B2_SWS_HOST_OUTPUT to b2_sws_getContext, or any other destination memory, to get sws_scale's host-out behaviour
- * (host -> GPU -> host round trip).  Returns the height of the output slice, < 0 on error. */
+ * The picture's host planes are NOT written in that form (the reference never reads them); pass B2_SWS_HOST_OUTPUT to
+ * b2_sws_getContext, or any other destination memory, to get sws_scale's host-out behaviour (host -> GPU -> host round
+ * trip).  Returns the height of the output slice, < 0 on error. */
 int b2_sws_scale(b2_sws_context_t *c, const uint8_t *const src[], const int srcStride[], int srcSliceY, int srcSliceH,
                  uint8_t *const dst[], const int dstStride[]);
 void b2_sws_freeContext(b2_sws_context_t *c);

@@ -62,6 +62,10 @@ int b2_engine_put_frame_direct(b2_engine_t *e, int slot, int ring, const uint8_t
  * completes behind the caller's back).  No b2_engine_h2d follows -- the next encode of the slot's group waits for the upload.
  * May run on another host thread than encode_group / d2h_group for ring entries that are not being encoded. */
 int b2_engine_put_picture(b2_engine_t *e, int slot, int ring, const uint8_t *const src[4], const int stride[4]);
+/* the same without waiting for the DMA of a page-locked source: returns a ticket (> 0) that b2_engine_put_wait blocks on before
+ * the source may be overwritten; 0: the source has already been read; < 0: error */
+long b2_engine_put_picture_async(b2_engine_t *e, int slot, int ring, const uint8_t *const src[4], const int stride[4]);
+int b2_engine_put_wait(b2_engine_t *e, long ticket);
 /* change cfg.in_fmt of an idle engine (the ring is re-allocated when the picture size differs) */
 int b2_engine_set_input_format(b2_engine_t *e, int fmt);
 /* async pinned-host -> device copy of ring position `ring` for slots [slot0, slot0+nslots) */

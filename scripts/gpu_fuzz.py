@@ -37,10 +37,12 @@ for case in range(ncases):
     h = int(rng.integers(8, 80)) * 4 if rng.random() < 0.7 else int(rng.integers(16, 160)) * 2
     if rng.random() < 0.15: w = int(rng.integers(8, 33)) * 2             # tiny pictures: 1-4 macroblocks per row / column
     if rng.random() < 0.15: h = int(rng.integers(8, 33)) * 2
+    if rng.random() < 0.12: h = int(rng.integers(80, 330)) * 2; w = min(w, 128)   # tall: K8's row pipeline spans several CTAs of a cluster
     qp = int(rng.integers(10, 52)); R = int(rng.choice([16, 32]))
     subpel = int(rng.random() < 0.85); intra = int(rng.random() < 0.85)
     deblock = int(rng.random() < 0.5); t8 = int(rng.random() < 0.5); parts = int(rng.choice([0, 1, 2])); pack = int(rng.random() < 0.5)
     if not subpel: parts = 0
+    offs = (int(rng.integers(-6, 7)), int(rng.integers(-6, 7))) if deblock and rng.random() < 0.6 else (0, 0)     # loop-filter offsets (tunes)
     kind = str(rng.choice(["smooth", "coarse", "shear", "noise", "flat", "synth"]))
     S = int(rng.integers(1, 4)); T = int(rng.integers(2, 5)); sd = int(rng.integers(0, 1 << 30))
     seqs = []
@@ -51,10 +53,10 @@ for case in range(ncases):
         elif kind == "noise": seqs.append(noise_seq(w, h, T, sd + s))
         elif kind == "flat": seqs.append(flat_seq(w, h, T, sd + s))
         else: seqs.append([b2oracle.synth_frame(w, h, t, s + sd % 7) for t in range(T)])
-    desc = f"case {case}: {w}x{h} qp {qp} R {R} subpel {subpel} intra {intra} deblock {deblock} t8 {t8} parts {parts} pack {pack} {kind} S {S} T {T} seed {sd}"
+    desc = f"case {case}: {w}x{h} qp {qp} R {R} subpel {subpel} intra {intra} deblock {deblock}{offs} t8 {t8} parts {parts} pack {pack} {kind} S {S} T {T} seed {sd}"
     try:
         run_and_compare(b2oracle, b2enc, seqs, w, h, qp, R, subpel=subpel, intra_in_p=intra, deblock=deblock, transform8x8=t8,
-                        pack_levels=pack, partitions=parts)
+                        pack_levels=pack, partitions=parts, deblock_offsets=offs)
     except Exception:
         print("MISMATCH/ERROR", desc, flush=True); traceback.print_exc(); sys.exit(1)
     done += 1

@@ -16,7 +16,7 @@ python - <<'PY'
 import sys, os
 sys.path.insert(0, "oracle")
 import b2oracle as o
-for name, w, h, n in (("1080p", 1920, 1080, 2048), ("2160p", 3840, 2160, 768)):
+for name, w, h, n in (("1080p", 1920, 1080, 2048), ("2160p", 3840, 2160, 384)):
     fr = [b"".join(p.tobytes() for p in o.synth_frame(w, h, t)) for t in range(32)]
     with open("/dev/shm/b2_%s.yuv" % name, "wb") as f:
         for i in range(n): f.write(fr[i % 32] if (i // 32) % 2 == 0 else fr[31 - i % 32])
@@ -28,11 +28,15 @@ for cfg in "1080p 1920x1080" "2160p 3840x2160"; do
     echo "b2_encode $1 --devices $n: $out  sha=$(sha256sum /dev/shm/b2_out_$n.h264 | cut -c1-16)"
   done
 done | tee gpurun_out/r2m8_cli.log
+for extra in "--slots 32 --devices 1" "--slots 32 --devices 2" "--slots 8 --devices 8" "--profile baseline --devices 2" "--profile baseline --devices 8"; do
+  out=$(LD_LIBRARY_PATH=video-encoder_b200 timeout 300 tools/b2_encode --size 1920x1080 --fps 60 --quality 26 --gop 32 --preset slow $extra /dev/shm/b2_1080p.yuv /dev/shm/b2_out_x.h264 2>&1 | tail -1)
+  echo "b2_encode 1080p $extra: $out"
+done | tee -a gpurun_out/r2m8_cli.log
 rm -f /dev/shm/b2_*.yuv /dev/shm/b2_out_*.h264
-for wl in c3 c2 c4 c5; do
+for wl in c2 c4 c5; do
   for n in 1 2 4 8; do
     if [ $n = 1 ]; then cmd="python bench.py"; else cmd="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29612 bench.py"; fi
-    timeout 300 $cmd --gpus $n --steps 10 --warmup 3 --workload $wl --no-cpu-baseline --no-dropin --no-verify 2>gpurun_out/r2m8_bench_${wl}_n$n.err | tail -1 > gpurun_out/r2m8_bench_${wl}_n$n.json
+    timeout 300 $cmd --gpus $n --steps 8 --warmup 3 --workload $wl --no-cpu-baseline --no-dropin --no-verify 2>gpurun_out/r2m8_bench_${wl}_n$n.err | tail -1 > gpurun_out/r2m8_bench_${wl}_n$n.json
     python - <<PY
 import json
 try:

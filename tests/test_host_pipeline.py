@@ -202,3 +202,24 @@ def test_many_gops_backpressure(b2mod, mock):
     assert len(out) == n and [o[1] for o in out] == [1000 + 40 * t for t in range(n)]
     single = drive(b2mod, mock, frames, w, h, devices=1, quality=34, annexb=1, i_keyint_max=3, i_gop_slots=5)
     assert annexb(out) == annexb(single)
+
+
+def test_randomised_call_sequences(oracle, b2mod, mock):
+    """random picture sizes, GOP lengths, slot counts, GPU counts, frame counts (partial last GOPs, fewer frames than one GOP,
+    more GOPs than slots), entropy coder, container format and producer pacing: always the oracle encoder's bytes, in order"""
+    rng = np.random.default_rng(20261018)
+    for case in range(24):
+        w, h = int(rng.integers(1, 5)) * 16, int(rng.integers(1, 4)) * 16
+        gop = int(rng.integers(1, 7)); slots = int(rng.integers(2, 6)); devices = int(rng.integers(1, 4)); n = int(rng.integers(1, 40))
+        cabac = int(rng.random() < 0.6); annexb_ = int(rng.random() < 0.5); qp = int(rng.integers(20, 45))
+        frames = smooth_seq(w, h, n, seed=int(rng.integers(0, 1 << 30)), cut=(int(rng.integers(1, n)) if n > 2 and rng.random() < 0.3 else None))
+        pace = float(rng.choice([0.0, 0.0, 0.002]))
+        out = drive(b2mod, mock, frames, w, h, devices=devices, preset="medium", tune="film", quality=qp, profile=None if cabac else "baseline",
+                    annexb=annexb_, i_keyint_max=gop, i_gop_slots=slots, check=(lambda t, k: time.sleep(pace)) if pace else None)
+        assert len(out) == n and [o[1] for o in out] == [1000 + 40 * t for t in range(n)], case
+        bs = b""
+        for nals, *_ in out:
+            for _, d in nals:
+                bs += d if annexb_ else b"\x00\x00\x00\x01" + d[4:]
+        ref, *_ = oracle.encode_sequence(frames, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1), deblock=1, cabac=cabac, deblock_offsets=(-1, -1))
+        assert bs == ref, "case %d: %dx%d gop %d slots %d devices %d frames %d" % (case, w, h, gop, slots, devices, n)

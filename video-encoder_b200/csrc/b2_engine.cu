@@ -87,6 +87,8 @@ struct b2_engine {
     // pageable sources go through two page-locked bounce buffers
     std::vector<cudaEvent_t> ev_put;
     std::unique_ptr<std::atomic<uint8_t>[]> put_pending;
+    cudaEvent_t ev_putq[8] = {};                    // b2_engine_put_picture_async: ticket t -> ev_putq[t % 8]
+    long put_seq = 0;
     uint8_t *h_bounce[2] = {nullptr, nullptr};
     cudaEvent_t ev_bounce[2] = {nullptr, nullptr};
     int bounce_next = 0;
@@ -183,6 +185,7 @@ static int engine_alloc(b2_engine *e)
         e->put_pending[s].store(0);
     }
     for (int k = 0; k < 2; k++) ENG_OK(cudaEventCreateWithFlags(&e->ev_bounce[k], cudaEventDisableTiming));
+    for (int k = 0; k < 8; k++) ENG_OK(cudaEventCreateWithFlags(&e->ev_putq[k], cudaEventDisableTiming));
     {   // the copy-out stream runs K9b (a small kernel that writes the packed levels into pinned memory) while the compute
         // streams keep every SM busy with K1: at the highest priority its CTAs are placed as soon as any resident CTA retires.
         // (Measured at 64 GOPs per GPU: no difference in e2e, 5,110-5,166 frames/s either way -- kept because a late K9b
@@ -277,6 +280,7 @@ extern "C" void b2_engine_destroy(b2_engine_t *e)
     for (auto ev : e->ev_h2d) cudaEventDestroy(ev);
     for (auto ev : e->ev_put) cudaEventDestroy(ev);
     for (int k = 0; k < 2; k++) { if (e->ev_bounce[k]) cudaEventDestroy(e->ev_bounce[k]); cudaFreeHost(e->h_bounce[k]); }
+    for (int k = 0; k < 8; k++) if (e->ev_putq[k]) cudaEventDestroy(e->ev_putq[k]);
     for (auto ev : e->ev_pool) cudaEventDestroy(ev);
     for (auto &r : e->prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     if (e->ev_t0) cudaEventDestroy(e->ev_t0);
@@ -380,7 +384,7 @@ extern "C" int b2_engine_put_frame_direct(b2_engine_t *e, int slot, int ring, co
 // pageable ones are copied into one of two page-locked bounce buffers whose upload runs behind the caller's back.  No
 // b2_engine_h2d follows: the next encode of the slot's group waits for the upload itself.  One caller thread at a time; it may
 // be another thread than the one issuing encode_group / d2h_group as long as the slot's ring entry is not being encoded.
-extern "C" int b2_engine_put_picture(b2_engine_t *e, int slot, int ring, const uint8_t *const src[4], const int stride[4])
+static long put_picture_impl(b2_engine_t *e, int slot, int ring, const uint8_t *const src[4], const int stride[4], bool wait)
 {
     if (slot < 0 || slot >= e->cfg.slots || ring < 0 || ring >= e->cfg.in_ring || !src || !src[0]) return -1;
     cudaSetDevice(e->cfg.device);
@@ -390,13 +394,22 @@ extern "C" int b2_engine_put_picture(b2_engine_t *e, int slot, int ring, const u
     int rb[3], rows[3];
     const int np = b2_fmt_layout(e->cfg.in_fmt, e->cfg.width, e->cfg.height, rb, rows);
     uint8_t *dst = e->d_in + in_off(e, slot, ring);
+    long ticket = 0;
     if (pinned) {
-        for (int p = 0; p < np; p++) {
-            ENG_OK(cudaMemcpy2DAsync(dst, rb[p], src[p], stride[p], rb[p], rows[p], cudaMemcpyHostToDevice, e->st_put));
-            dst += (size_t)rb[p] * rows[p];
-        }
+        bool tight = true;                              // planes back to back without row padding: one copy instead of 3 strided ones
+        for (int p = 0; p < np; p++) tight &= stride[p] == rb[p] && (p == 0 || src[p] == src[p - 1] + (size_t)rb[p - 1] * rows[p - 1]);
+        if (tight) ENG_OK(cudaMemcpyAsync(dst, src[0], e->in_bytes, cudaMemcpyHostToDevice, e->st_put));
+        else
+            for (int p = 0; p < np; p++) {
+                ENG_OK(cudaMemcpy2DAsync(dst, rb[p], src[p], stride[p], rb[p], rows[p], cudaMemcpyHostToDevice, e->st_put));
+                dst += (size_t)rb[p] * rows[p];
+            }
         ENG_OK(cudaEventRecord(e->ev_put[slot], e->st_put));
-        ENG_OK(cudaStreamSynchronize(e->st_put));
+        if (wait) ENG_OK(cudaStreamSynchronize(e->st_put));
+        else {
+            ticket = ++e->put_seq;
+            ENG_OK(cudaEventRecord(e->ev_putq[ticket % 8], e->st_put));
+        }
     } else {
         const int k = e->bounce_next;
         e->bounce_next ^= 1;
@@ -413,6 +426,26 @@ extern "C" int b2_engine_put_picture(b2_engine_t *e, int slot, int ring, const u
         ENG_OK(cudaEventRecord(e->ev_put[slot], e->st_put));
     }
     e->put_pending[slot].store(1, std::memory_order_release);
+    return ticket;
+}
+
+extern "C" int b2_engine_put_picture(b2_engine_t *e, int slot, int ring, const uint8_t *const src[4], const int stride[4])
+{
+    return put_picture_impl(e, slot, ring, src, stride, true) < 0 ? -1 : 0;
+}
+
+// The same without waiting for the DMA of a page-locked source: returns a ticket > 0 that b2_engine_put_wait blocks on before the
+// source may be overwritten (0: the source has already been read; < 0: error).  Used for the staging buffers of deferred
+// b2_sws_scale conversions, which the library owns and double-buffers, so that the caller's thread never waits for PCIe.
+extern "C" long b2_engine_put_picture_async(b2_engine_t *e, int slot, int ring, const uint8_t *const src[4], const int stride[4])
+{
+    return put_picture_impl(e, slot, ring, src, stride, false);
+}
+extern "C" int b2_engine_put_wait(b2_engine_t *e, long ticket)
+{
+    if (ticket <= 0) return 0;
+    // the event of ticket t is re-recorded by ticket t + 8 on the same in-order stream: waiting for the newer record covers the older copy
+    ENG_OK(cudaEventSynchronize(e->ev_putq[ticket % 8]));
     return 0;
 }
 

@@ -116,12 +116,27 @@ b2h_picrec_t *b2h_picture_find(const uint8_t *plane0)
 
 uint8_t *b2h_picture_stage(b2h_picrec_t *r, size_t bytes)
 {
-    if (r->stage_bytes < bytes) {
-        b2_pinned_free(r->stage);
-        r->stage = (uint8_t *)b2_pinned_alloc(bytes);
-        r->stage_bytes = r->stage ? bytes : 0;
+    const int k = r->cur ^ 1;
+    if (r->busy_eng[k]) {                                 /* the upload of the picture before last */
+        b2_engine_put_wait((b2_engine_t *)r->busy_eng[k], r->busy_ticket[k]);
+        r->busy_eng[k] = NULL;
     }
-    return r->stage;
+    if (r->stage_bytes[k] < bytes) {
+        b2_pinned_free(r->stage[k]);
+        r->stage[k] = (uint8_t *)b2_pinned_alloc(bytes);
+        r->stage_bytes[k] = r->stage[k] ? bytes : 0;
+    }
+    if (r->stage[k]) r->cur = k;
+    return r->stage[k];
+}
+
+void b2h_picture_forget_engine(void *eng)
+{
+    pthread_mutex_lock(&pic_mu);
+    for (b2h_picrec_t *r = pic_list; r; r = r->next)
+        for (int k = 0; k < 2; k++)
+            if (r->busy_eng[k] == eng) r->busy_eng[k] = NULL;
+    pthread_mutex_unlock(&pic_mu);
 }
 
 int b2_picture_alloc(b2_picture_t *pic, int i_csp, int i_width, int i_height)
@@ -152,7 +167,13 @@ void b2_picture_clean(b2_picture_t *pic)
     while (*pp && (*pp)->base != pic->opaque) pp = &(*pp)->next;
     if (*pp) { r = *pp; *pp = r->next; }
     pthread_mutex_unlock(&pic_mu);
-    if (r) { b2_pinned_free(r->stage); free(r); }
+    if (r) {
+        for (int k = 0; k < 2; k++) {
+            if (r->busy_eng[k]) b2_engine_put_wait((b2_engine_t *)r->busy_eng[k], r->busy_ticket[k]);
+            b2_pinned_free(r->stage[k]);
+        }
+        free(r);
+    }
     b2_pinned_free(pic->opaque);
     memset(pic, 0, sizeof(*pic));
 }
@@ -369,7 +390,7 @@ void b2_encoder_close(b2_t *h)
     free(h->zout.data); free(h->scratch); free(h->ret_buf);
     b2h_entropy_destroy(h->ent);
     for (int d = 0; d < B2_MAX_DEVICES; d++) {
-        if (h->dev[d].eng) b2_engine_destroy(h->dev[d].eng);
+        if (h->dev[d].eng) { b2h_picture_forget_engine(h->dev[d].eng); b2_engine_destroy(h->dev[d].eng); }
         if (h->dev[d].slots) { free(h->dev[d].slots); pthread_cond_destroy(&h->dev[d].cv); }
     }
     pthread_mutex_destroy(&h->mu);
@@ -599,14 +620,16 @@ static int return_frame(b2_t *h, outframe_t *o, b2_nal_t **pp_nal, int *pi_nal, 
 
 /* where the picture's pixels are and in which layout: the I420 planes, or -- when b2_sws_scale deferred the conversion into
  * this picture -- the staged raw source (b2h_picture.h) */
-static int picture_source(b2_t *h, b2_picture_t *pic, const uint8_t *src[4], int stride[4], int *fmt)
+static int picture_source(b2_t *h, b2_picture_t *pic, const uint8_t *src[4], int stride[4], int *fmt, b2h_picrec_t **staged)
 {
     b2h_picrec_t *r = b2h_picture_find(pic->img.plane[0]);
+    *staged = NULL;
     if (r && r->deferred) {
         int rb[3], rows[3];
         const int np = b2_fmt_layout(r->fmt, h->p.i_width, h->p.i_height, rb, rows);
         if (!np || r->width != h->p.i_width || r->height != h->p.i_height) return -1;
-        const uint8_t *q = r->stage;
+        const uint8_t *q = r->stage[r->cur];
+        *staged = r;
         for (int k = 0; k < 4; k++) { src[k] = NULL; stride[k] = 0; }
         for (int k = 0; k < np; k++) { src[k] = q; stride[k] = rb[k]; q += (size_t)rb[k] * rows[k]; }
         *fmt = r->fmt;
@@ -666,8 +689,9 @@ int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic
     if (!h || !pp_nal || !pi_nal) return -1;
     *pi_nal = 0; *pp_nal = NULL;
     const uint8_t *src[4]; int stride[4], fmt = h->fmt;
+    b2h_picrec_t *staged = NULL;                              /* the picture's pixels sit in library-owned staging (deferred sws_scale) */
     if (pic_in) {
-        if (picture_source(h, pic_in, src, stride, &fmt)) { fprintf(stderr, "b2enc: picture does not match the encoder's size\n"); return -1; }
+        if (picture_source(h, pic_in, src, stride, &fmt, &staged)) { fprintf(stderr, "b2enc: picture does not match the encoder's size\n"); return -1; }
         if (fmt != h->fmt && switch_format(h, fmt)) return -1;
     }
     if (h->S == 1) return pic_in ? encode_zero_delay(h, pp_nal, pi_nal, src, stride, pic_in->i_pts, pic_out) : 0;
@@ -699,8 +723,14 @@ int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic
         slot_t *sl = &dv->slots[h->g_slot];
         const int t = sl->n;
         pthread_mutex_unlock(&h->mu);
-        /* picture -> ring entry t of the slot; returns when the picture has been read (av_encode.c:415, :545: it is refilled) */
-        if (b2_engine_put_picture(dv->eng, h->g_slot, t, src, stride)) { fail(h); return -1; }
+        /* picture -> ring entry t of the slot; returns when the picture has been read (av_encode.c:415, :545: it is refilled).
+         * Staging the library owns is double buffered: its DMA is only waited for when that buffer comes round again. */
+        if (staged) {
+            const long ticket = b2_engine_put_picture_async(dv->eng, h->g_slot, t, src, stride);
+            if (ticket < 0) { fail(h); return -1; }
+            staged->busy_eng[staged->cur] = ticket > 0 ? (void *)dv->eng : NULL;
+            staged->busy_ticket[staged->cur] = ticket;
+        } else if (b2_engine_put_picture(dv->eng, h->g_slot, t, src, stride)) { fail(h); return -1; }
         pthread_mutex_lock(&h->mu);
         outframe_t *f = &h->fifo[h->frames_in % h->fifo_cap];
         f->pts = pic_in->i_pts; f->ready = 0;

@@ -20,18 +20,26 @@ typedef struct b2h_picrec {
     uint8_t *base;              /* the page-locked allocation behind img.plane[0..2]                          */
     size_t bytes;
     int width, height;
-    /* deferred conversion, written by b2_sws_scale and consumed by b2_encoder_encode */
-    int deferred;               /* 1: `stage` holds the raw source of format `fmt`; the I420 planes are stale */
-    int fmt;                    /* B2_FMT_*                                                                   */
-    uint8_t *stage;             /* page-locked, tight planes one after the other (b2_fmt_layout)              */
-    size_t stage_bytes;
+    /* deferred conversion, written by b2_sws_scale and consumed by b2_encoder_encode.  Two staging buffers alternate so that
+     * the upload of one picture (asynchronous DMA issued by b2_encoder_encode) overlaps the staging of the next: the caller's
+     * thread never waits for PCIe.  busy_eng / busy_ticket: the upload that still reads a buffer (b2_engine_put_wait). */
+    int deferred;               /* 1: stage[cur] holds the raw source of format `fmt`; the I420 planes are stale */
+    int fmt;                    /* B2_FMT_*                                                                      */
+    int cur;                    /* buffer the last b2_sws_scale filled                                           */
+    uint8_t *stage[2];          /* page-locked, tight planes one after the other (b2_fmt_layout)                 */
+    size_t stage_bytes[2];
+    void *busy_eng[2];
+    long busy_ticket[2];
     struct b2h_picrec *next;
 } b2h_picrec_t;
 
 /* record of the picture whose first plane starts at `plane0`, or NULL */
 b2h_picrec_t *b2h_picture_find(const uint8_t *plane0);
-/* page-locked staging of at least `bytes` for the record (re-allocated when it grows); NULL on failure */
+/* the staging buffer to fill next: page-locked, at least `bytes`, no upload reading it any more; NULL on failure.  Makes it
+ * r->cur. */
 uint8_t *b2h_picture_stage(b2h_picrec_t *r, size_t bytes);
+/* forget uploads issued through engine `eng` (it is about to be destroyed; its streams have been drained) */
+void b2h_picture_forget_engine(void *eng);
 
 void *b2_pinned_alloc(size_t n);
 void b2_pinned_free(void *p);
