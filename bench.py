@@ -33,6 +33,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# one hardware queue per stream group; must be in the environment before the first CUDA context exists (torch creates it under torchrun)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 sys.path.insert(0, os.path.join(ROOT, "video-encoder_b200"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
