@@ -31,6 +31,18 @@ int b2_lambda_for_qp(int qp)
 
 struct ProfRec { int k; cudaEvent_t e0, e1; };
 
+// Test hook (default off): B2ENC_TEST_FAULT=no_h2d_wait makes an encode NOT wait for the upload of its ring entry,
+// =no_d2h_wait makes it NOT wait for the copy-out of the result set it is about to overwrite.  tests/test_bench_path.py must
+// fail with either (scripts/gpu_fault_injection.sh): that is the proof that those tests see the inter-stream ordering.
+static int test_fault()
+{
+    static const int f = [] {
+        const char *e = getenv("B2ENC_TEST_FAULT");
+        return !e ? 0 : !strcmp(e, "no_h2d_wait") ? 1 : !strcmp(e, "no_d2h_wait") ? 2 : 0;
+    }();
+    return f;
+}
+
 // A stream group: a contiguous range of slots advanced together on its own compute stream.  Groups
 // share nothing, so their kernels overlap on the GPU: while one group sits in the latency-bound intra
 // wavefront (K7) the others keep the SMs busy with the ALU-bound search (K1).
@@ -538,10 +550,10 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
     const int do_intra = !is_p || c.intra_in_p;
     const int set = gr.res_set ^ 1;
     cudaStream_t st = gr.st;
-    if (gr.h2d_pending[ring]) { ENG_OK(cudaStreamWaitEvent(st, e->ev_h2d[ring], 0)); gr.h2d_pending[ring] = 0; }
+    if (gr.h2d_pending[ring]) { if (test_fault() != 1) ENG_OK(cudaStreamWaitEvent(st, e->ev_h2d[ring], 0)); gr.h2d_pending[ring] = 0; }
     for (int s = gr.slot0; s < gr.slot0 + ns; s++)          // pictures handed over by b2_engine_put_picture
         if (e->put_pending[s].exchange(0, std::memory_order_acquire)) ENG_OK(cudaStreamWaitEvent(st, e->ev_put[s], 0));
-    if (gr.d2h_used[set]) ENG_OK(cudaStreamWaitEvent(st, gr.ev_d2h[set], 0));        // result set still being copied out
+    if (gr.d2h_used[set] && test_fault() != 2) ENG_OK(cudaStreamWaitEvent(st, gr.ev_d2h[set], 0));        // result set still being copied out
     const size_t oy = gr.slot0 * e->stride_y, oc = gr.slot0 * e->stride_c, om = (size_t)gr.slot0 * e->nmb;
     uint8_t *curw[3] = {e->d_cur[0] + oy, e->d_cur[1] + oc, e->d_cur[2] + oc};
     const uint8_t *cur[3] = {curw[0], curw[1], curw[2]};

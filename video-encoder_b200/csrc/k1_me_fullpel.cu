@@ -41,8 +41,8 @@ namespace {
 #define B2_K1_SMEM_PAD 0    // extra dynamic shared memory per CTA (bytes): lowers K1's residency without touching its register budget,
 #endif                      // so that other stream groups' kernels can co-reside (experiment knob, scripts/k1_variants.sh)
 #ifndef B2_K1_NMB16
-#define B2_K1_NMB16 12      // +-16: the window is small (33 x 3 dy groups = 99 lane-tasks per MB), a wider strip fills the 8 warps' rounds
-#endif
+#define B2_K1_NMB16 10      // +-16: strips of 10 MBs.  Swept on the B200 with 192/256/320/384 threads (scripts/k1_r16_variant_probe.py,
+#endif                      // profiles/r2_k1_r16_strip_sweep.txt): 8 -> 0.821, 10 -> 0.838, 12 -> 0.817, 14 -> 0.829 of the VABSDIFF4 peak at 720p
 
 template <int R> struct K1Cfg;
 // NMB = macroblocks per CTA strip (tuning: scripts/k1_variants.sh)

@@ -560,7 +560,13 @@ k8_deblock_rows_kernel(uint8_t *ry, uint8_t *ru, uint8_t *rv, int pitch, int pit
 int b2_launch_deblock(uint8_t *const rec[3], int pitch, int pitchc, size_t stride_y, size_t stride_c, int mbw, int mbh,
                       int nframes, int qp, int alpha_off, int beta_off, const b2_mbinfo_t *d_info, int *d_flags, cudaStream_t st)
 {
-    static const bool wavefront = getenv("B2_K8_WAVEFRONT") && atoi(getenv("B2_K8_WAVEFRONT")) != 0;      // A/B measurements only
+    // Two schedules.  The row pipeline has the shorter chain (0.87 vs 1.59 ms for one 1080p frame) and is what a launch of few
+    // frames wants -- the drop-in's one-GOP-per-stream shape, live streams.  A launch that covers many frames (bench.py: 8 per
+    // stream group, 8 groups) is throughput-bound, its chains hide behind the other groups' K1, and there the anti-diagonal
+    // wavefront's smaller footprint (40 registers, nothing spinning) is worth ~3 % of the step: 4 frames and up take it.
+    // B2_K8_WAVEFRONT=0/1 forces one form (A/B measurements).
+    static const int forced = getenv("B2_K8_WAVEFRONT") ? (atoi(getenv("B2_K8_WAVEFRONT")) != 0) : -1;
+    const bool wavefront = forced >= 0 ? forced != 0 : nframes >= 4;
     int ncta = 1;
     if (wavefront) {
         const int maxdiag = mbh < (mbw + 1) / 2 ? mbh : (mbw + 1) / 2;
