@@ -185,7 +185,8 @@ def verify_final_state(eng, b2enc, b2oracle, rank, groups, ftype, last_step, arg
     bad = []
     for slot, n, info_o, coef_o, rec in res:
         info_g, _ = eng.results(slot)
-        ok = all(np.array_equal(info_g[f], info_o[f]) for f in info_o.dtype.names)
+        want = b2enc.shipped_info(info_o) if args.pack_levels else info_o
+        ok = all(np.array_equal(info_g[f], want[f]) for f in info_o.dtype.names)
         if args.pack_levels:
             ok = ok and np.array_equal(eng.packed(slot), b2enc.pack_levels(info_o, coef_o))
         else:
@@ -442,8 +443,8 @@ def main():
                        "deblocking_note": "the named path (BASELINE.json C3) has no loop filter, so K8 is off here (--deblock 1 adds it); an av_encode.c user of the x264 mirror gets x264's default: filter ON, tune film offsets -1:-1 -- that configuration is the `dropin` leg", "transform8x8": bool(args.transform8x8), "partitions": bool(args.partitions),
                        "parallelism": "closed-GOP sharding, %d GPUs x %d GOPs, no collective" % (world, SLOTS)},
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(world * SLOTS * in_bytes),
-                    "d2h_bytes_per_step": int(world * (SLOTS * mbs * 48 + packed_per_step)) if args.pack_levels else int(world * SLOTS * mbs * (48 + 832)),
-                    "d2h_note": ("per-MB decisions (48 B) + packed levels (K9: blocks with a non-zero level only; mean over the timed steps, rank 0 x n_gpus)"
+                    "d2h_bytes_per_step": int(world * (SLOTS * mbs * 24 + packed_per_step)) if args.pack_levels else int(world * SLOTS * mbs * (48 + 832)),
+                    "d2h_note": ("per-MB decisions (24-byte records, b2_mbinfo_packed_t) + packed levels (K9: blocks with a non-zero level only; mean over the timed steps, rank 0 x n_gpus)"
                                  if args.pack_levels else "per-MB decisions (48 B) + dense levels (832 B)"), "api": "b2_engine_h2d/encode/d2h (include/b2enc_engine.h), pinned host buffers",
                     "timing": "host wall clock around %d pipelined steps, synchronised on both sides" % n_e2e},
             "gpu_launches": int(launches),

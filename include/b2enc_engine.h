@@ -85,6 +85,10 @@ int b2_engine_group_result_set(const b2_engine_t *e, int group);
 int b2_engine_group_done(b2_engine_t *e, int group, int set);
 int b2_engine_group_wait(b2_engine_t *e, int group, int set);
 const b2_mbinfo_t *b2_engine_info_set(b2_engine_t *e, int set, int slot);
+/* cfg.pack_levels: the decisions cross PCIe as 24-byte records (b2_mbinfo_packed_t: everything the serial stage reads; not `cost`,
+ * `i8_modes` or the intra analysis modes of macroblocks that ended up inter).  Every b2_engine_info* view expands them on first use;
+ * this returns the records themselves. */
+const b2_mbinfo_packed_t *b2_engine_info_packed_set(b2_engine_t *e, int set, int slot);
 const uint8_t *b2_engine_packed_set(b2_engine_t *e, int set, int slot, size_t *bytes);
 /* async device -> pinned-host copy of the last encode's per-MB results for slots [0,nslots) */
 int b2_engine_d2h(b2_engine_t *e, int nslots);

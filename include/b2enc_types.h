@@ -92,6 +92,47 @@ typedef struct {
                             /* bits 4k..4k+3 (kept for every MB the analysis ran on, whatever type was chosen)     */
 } b2_mbinfo_t;
 
+/* What the serial stage needs of a b2_mbinfo_t, in 24 bytes: the record that crosses PCIe when the engine packs its results
+ * (cfg.pack_levels).  Not shipped: `cost`, `i8_modes` (analysis by-products) and the intra analysis modes of macroblocks that
+ * ended up inter.  w[0] = mvx | mvy << 16; w[1] = mb_type | i16_mode << 2 | chroma_mode << 4 | part << 6 | transform8x8 << 8 |
+ * cbp << 16; w[2] = nnz_mask; w[3..5] = inter: mv8[0..2]; intra: i4_mode[16] as nibbles (w[3], w[4]). */
+typedef struct { uint32_t w[6]; } b2_mbinfo_packed_t;
+
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline b2_mbinfo_packed_t b2_mbinfo_pack(const b2_mbinfo_t *m)
+{
+    b2_mbinfo_packed_t p;
+    const int intra = m->mb_type != B2_MB_P16x16;
+    p.w[0] = (uint32_t)(uint16_t)m->mvx | (uint32_t)(uint16_t)m->mvy << 16;
+    p.w[1] = (uint32_t)m->mb_type | (intra ? (uint32_t)m->i16_mode << 2 | (uint32_t)m->chroma_mode << 4 : 0u) | (uint32_t)m->part << 6 |
+             (uint32_t)(m->transform8x8 != 0) << 8 | (uint32_t)m->cbp << 16;
+    p.w[2] = m->nnz_mask;
+    if (intra) {
+        uint32_t a = 0, b = 0;
+        for (int i = 0; i < 8; i++) { a |= (uint32_t)(m->i4_mode[i] & 15) << (4 * i); b |= (uint32_t)(m->i4_mode[8 + i] & 15) << (4 * i); }
+        p.w[3] = a; p.w[4] = b; p.w[5] = 0;
+    } else {
+        for (int q = 0; q < 3; q++) p.w[3 + q] = (uint32_t)(uint16_t)m->mv8[q].x | (uint32_t)(uint16_t)m->mv8[q].y << 16;
+    }
+    return p;
+}
+static inline void b2_mbinfo_unpack(const b2_mbinfo_packed_t *p, b2_mbinfo_t *m)
+{
+    const uint32_t f = p->w[1];
+    const int intra = (int)(f & 3u) != B2_MB_P16x16;
+    m->mvx = (int16_t)(p->w[0] & 0xffffu); m->mvy = (int16_t)(p->w[0] >> 16);
+    m->mb_type = (uint8_t)(f & 3u); m->i16_mode = (uint8_t)((f >> 2) & 3u); m->chroma_mode = (uint8_t)((f >> 4) & 3u);
+    m->part = (uint8_t)((f >> 6) & 3u); m->transform8x8 = (uint8_t)((f >> 8) & 1u); m->cbp = (uint8_t)(f >> 16);
+    m->cost = 0; m->nnz_mask = p->w[2]; m->i8_modes = 0;
+    for (int i = 0; i < 16; i++) m->i4_mode[i] = intra ? (uint8_t)((p->w[3 + (i >> 3)] >> (4 * (i & 7))) & 15u) : 0;
+    for (int q = 0; q < 3; q++) {
+        m->mv8[q].x = intra ? 0 : (int16_t)(p->w[3 + q] & 0xffffu);
+        m->mv8[q].y = intra ? 0 : (int16_t)(p->w[3 + q] >> 16);
+    }
+}
+
 /* Quantised levels of one macroblock, each block in zig-zag scan order.
  *   blk 0..15  luma 4x4 (z order).  I16x16: index 0 is 0, DC lives in blk 24.
  *              With the 8x8 transform, blk[4q..4q+3] hold the 64 levels of 8x8 block q in 8x8 zig-zag order.

@@ -40,7 +40,8 @@ def launches(path):
 
 
 def full(path):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .ncu-rep (converted here) or the raw page already exported as CSV (`ncu -i rep --page raw --csv`, done on the GPU box)
+    raw = open(path, errors="ignore").read() if path.endswith(".csv") else subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr = rows[0]
 

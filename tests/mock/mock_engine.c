@@ -25,6 +25,7 @@ typedef struct {
     int ref_idx;
     b2_mv_t *prev_mv;
     b2_mbinfo_t *info[2];           /* result sets */
+    b2_mbinfo_packed_t *pinfo[2];   /* the same as the 24-byte records that cross PCIe (K9a on the GPU) */
     uint8_t *packed[2];
     size_t packed_bytes[2];
     int res_set, host_set, polled[2];
@@ -84,6 +85,7 @@ b2_engine_t *b2_engine_create(const b2_engine_cfg_t *cfg)
         m->coef = calloc((size_t)e->nmb, sizeof(b2_mbcoef_t));
         for (int k = 0; k < 2; k++) {
             m->info[k] = calloc((size_t)e->nmb, sizeof(b2_mbinfo_t));
+            m->pinfo[k] = calloc((size_t)e->nmb, sizeof(b2_mbinfo_packed_t));
             m->packed[k] = malloc((size_t)e->nmb * sizeof(b2_mbcoef_t));
         }
     }
@@ -97,7 +99,7 @@ void b2_engine_destroy(b2_engine_t *e)
         mslot_t *m = &e->slots[s];
         free(m->in); b2o_frame_free(&m->cur); b2o_frame_free(&m->rec[0]); b2o_frame_free(&m->rec[1]);
         free(m->prev_mv); free(m->coef);
-        for (int k = 0; k < 2; k++) { free(m->info[k]); free(m->packed[k]); }
+        for (int k = 0; k < 2; k++) { free(m->info[k]); free(m->pinfo[k]); free(m->packed[k]); }
     }
     free(e->slots); free(e);
 }
@@ -172,6 +174,7 @@ int b2_engine_encode_group(b2_engine_t *e, int group, int frame_type, int ring)
             if (pm >> b & 1) { memcpy(m->packed[set] + pos, m->coef[i].blk[b], 32); pos += 32; }
     }
     m->packed_bytes[set] = pos;
+    for (int i = 0; i < e->nmb; i++) m->pinfo[set][i] = b2_mbinfo_pack(&m->info[set][i]);
     m->ref_idx ^= 1; m->res_set = set;
     e->launches++;
     return 0;
@@ -197,6 +200,7 @@ int b2_engine_group_wait(b2_engine_t *e, int group, int set)
     return 0;
 }
 const b2_mbinfo_t *b2_engine_info_set(b2_engine_t *e, int set, int slot) { return e->slots[slot].info[set]; }
+const b2_mbinfo_packed_t *b2_engine_info_packed_set(b2_engine_t *e, int set, int slot) { return e->slots[slot].pinfo[set]; }
 const uint8_t *b2_engine_packed_set(b2_engine_t *e, int set, int slot, size_t *bytes)
 {
     if (bytes) *bytes = e->slots[slot].packed_bytes[set];

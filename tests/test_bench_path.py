@@ -66,8 +66,9 @@ def replay(oracle, b2, w, h, slots, streams, ring, gop, steps, R=16, qp=28, debl
             g = group_of[s]
             info_g, packed_g = eng.results_set(sets[g], s)
             info_o, coef_o, _ = chains[s].step(picture(step, s), is_i(step, g))
+            want = b2.shipped_info(info_o)                            # the copy-out ships 24-byte decision records
             for f in info_o.dtype.names:
-                assert np.array_equal(info_g[f], info_o[f]), f"step {step} slot {s} (group {g}, {'I' if is_i(step, g) else 'P'}): info.{f}"
+                assert np.array_equal(info_g[f], want[f]), f"step {step} slot {s} (group {g}, {'I' if is_i(step, g) else 'P'}): info.{f}"
             assert np.array_equal(packed_g, b2.pack_levels(info_o, coef_o)), f"step {step} slot {s}: packed levels"
 
     if not distinct:

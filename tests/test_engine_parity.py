@@ -41,8 +41,9 @@ def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="
                 assert np.array_equal(eng.stage(s, 0), mvf_o), f"K1 mv t={t} s={s}"
                 assert np.array_equal(eng.stage(s, 1), cf_o), f"K1 cost t={t} s={s}"
                 stats["mvx_mod4"] += np.bincount(mvf_o["x"].astype(int) & 3, minlength=4)
+            want = b2.shipped_info(info_o) if pack_levels else info_o      # packed copy-out: 24-byte decision records
             for f in INFO_FIELDS:
-                assert np.array_equal(info_g[f], info_o[f]), f"info.{f} t={t} s={s}: {np.argwhere(info_g[f] != info_o[f])[:5].tolist()}"
+                assert np.array_equal(info_g[f], want[f]), f"info.{f} t={t} s={s}: {np.argwhere(info_g[f] != want[f])[:5].tolist()}"
             assert np.array_equal(coef_g["blk"], coef_o["blk"]), f"levels t={t} s={s}"
             ry, ru, rv = eng.recon(s)
             assert np.array_equal(ry, rec.y), f"recon Y t={t} s={s}"

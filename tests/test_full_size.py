@@ -34,7 +34,7 @@ def _encode_and_check(oracle, b2, w, h, R, qp, nslots, nframes, oracle_slots, su
             if s in oracle_slots:
                 cur = oracle.OFrame(w, h).load(*frames[s]); rec = oracle.OFrame(w, h)
                 info_o, coef_o = oracle.encode_frame(prm, ft, cur, prev[s], rec, pmv[s])
-                assert np.array_equal(info, info_o), f"decisions differ t={t} s={s}"
+                assert np.array_equal(info, b2.shipped_info(info_o) if pack else info_o), f"decisions differ t={t} s={s}"
                 assert np.array_equal(coef["blk"], coef_o["blk"]), f"levels differ t={t} s={s}"
                 ry, ru, rv = recons[s][-1]
                 assert np.array_equal(ry, rec.y) and np.array_equal(ru, rec.u) and np.array_equal(rv, rec.v), f"recon t={t} s={s}"

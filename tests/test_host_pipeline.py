@@ -223,3 +223,29 @@ def test_randomised_call_sequences(oracle, b2mod, mock):
                 bs += d if annexb_ else b"\x00\x00\x00\x01" + d[4:]
         ref, *_ = oracle.encode_sequence(frames, w, h, qp=qp, merange=16, gop=gop, fps=(30, 1), deblock=1, cabac=cabac, deblock_offsets=(-1, -1))
         assert bs == ref, "case %d: %dx%d gop %d slots %d devices %d frames %d" % (case, w, h, gop, slots, devices, n)
+
+
+def test_large_picture_staging_copy_is_threaded_and_exact(oracle, b2mod, mock):
+    """pictures of 2 MB and more are staged by the caller plus helper threads (rows split per plane, host/b2h_sws.c) into the
+    double-buffered page-locked staging: strided 1080p yuyv422 source (4 MB), stream == oracle encoder's on the converted pictures"""
+    w, h, n, gop = 1920, 1080, 3, 2
+    base = [oracle.synth_frame(w, h, t, 3) for t in range(n)]
+    os.environ["B2_MOCK_DEVICES"] = "1"
+    os.environ["B2ENC_SWS_THREADS"] = "4"
+    try:
+        enc = b2mod.DropInEncoder(w, h, library=mock, preset="ultrafast", tune="film", quality=38, annexb=1, i_keyint_max=gop, i_gop_slots=2)
+        out, conv = [], []
+        for t, (y, u, v) in enumerate(base):
+            planes = to_fmt("yuyv422", y, u, v)                   # row pitch 2*w + 12: every row is a separate copy
+            conv.append(oracle.convert_to_i420("yuyv422", w, h, planes))
+            r = enc.encode_via_sws("yuyv422", planes, t)
+            if r[0] > 0: out.append(r[1])
+        while enc.delayed() > 0:
+            out.append(enc.encode(None, 0)[1])
+        enc.close()
+    finally:
+        del os.environ["B2ENC_SWS_THREADS"]
+    assert len(out) == n
+    # preset ultrafast: no sub-pel, no intra in P, CAVLC, loop filter off
+    ref, *_ = oracle.encode_sequence(conv, w, h, qp=38, merange=16, subpel=0, intra_in_p=0, gop=gop, fps=(30, 1), deblock=0, cabac=0)
+    assert b"".join(d for nals in out for _, d in nals) == ref

@@ -160,7 +160,8 @@ int main(int argc, char **argv)
     {
         struct stat st;
         if (fstat(fileno(in), &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
-            void *m = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_SHARED | MAP_POPULATE, fileno(in), 0);   /* no page faults inside the frame loop */
+            /* pre-faulted (no page faults inside the frame loop) unless the file is larger than what one would want resident at once */
+            void *m = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_SHARED | (st.st_size <= ((off_t)16 << 30) ? MAP_POPULATE : 0), fileno(in), 0);
             if (m != MAP_FAILED) { map = (const uint8_t *)m; map_size = (size_t)st.st_size; madvise(m, map_size, MADV_SEQUENTIAL); }
         }
     }

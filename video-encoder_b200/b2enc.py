@@ -141,6 +141,18 @@ def coef_present(info):
     return (luma | (m & 0x01ff0000) | np.where((m & 0x06000000) != 0, 1 << 25, 0)).astype(np.uint32)
 
 
+def shipped_info(info):
+    """test helper: what is left of an MBINFO array after the 24-byte records of the packed copy-out (b2_mbinfo_packed_t,
+    include/b2enc_types.h): `cost`, `i8_modes` and the intra analysis modes of inter macroblocks are not shipped"""
+    out = np.array(info, copy=True)
+    out["cost"] = 0; out["i8_modes"] = 0
+    inter = out["mb_type"] == 0
+    out["i4_mode"][inter] = 0; out["i16_mode"][inter] = 0; out["chroma_mode"][inter] = 0
+    out["mv8"][~inter] = 0
+    out["transform8x8"] = (out["transform8x8"] != 0).astype(np.uint8)
+    return out
+
+
 def pack_levels(info, coef):
     """test helper: the packed stream K9 produces, built on the host from a dense MBCOEF array"""
     pm = coef_present(info)

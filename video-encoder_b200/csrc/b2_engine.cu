@@ -76,6 +76,10 @@ struct b2_engine {
     b2_mv_t *d_mv9 = nullptr;              // cfg.partitions == 2: [S][nmb][9] best full-pel vector of every shape part (K1<PART>)
     uint32_t *d_cost9 = nullptr;           //                      and its cost
     b2_mbinfo_t *d_info[2] = {}, *h_info[2] = {};
+    // cfg.pack_levels: the decisions cross PCIe as 24-byte records (K9a writes them); h_info is then filled on the host, per slot,
+    // the first time a view of it is asked for (info_stale: the slot's records are newer than its h_info)
+    b2_mbinfo_packed_t *d_pinfo[2] = {}, *h_pinfo[2] = {};
+    std::vector<uint8_t> info_stale[2];
     b2_mbcoef_t *d_coef[2] = {}, *h_coef[2] = {};
     // cfg.pack_levels: packed level streams [S][pack_stride] per result set (device + pinned host), blocks used per slot
     uint8_t *d_pack[2] = {}, *h_pack[2] = {};
@@ -167,7 +171,16 @@ static int engine_alloc(b2_engine *e)
     for (int s = 0; s < 2; s++) {
         ENG_OK(cudaMalloc(&e->d_info[s], n * sizeof(b2_mbinfo_t)));
         ENG_OK(cudaMalloc(&e->d_coef[s], n * sizeof(b2_mbcoef_t)));
-        ENG_OK(cudaHostAlloc(&e->h_info[s], n * sizeof(b2_mbinfo_t), cudaHostAllocDefault));
+        if (c.pack_levels) {
+            e->h_info[s] = (b2_mbinfo_t *)malloc(n * sizeof(b2_mbinfo_t));       // filled from the packed records on demand: plain memory
+            if (!e->h_info[s]) return -1;
+            memset(e->h_info[s], 0, n * sizeof(b2_mbinfo_t));
+            ENG_OK(cudaMalloc(&e->d_pinfo[s], n * sizeof(b2_mbinfo_packed_t)));
+            ENG_OK(cudaHostAlloc(&e->h_pinfo[s], n * sizeof(b2_mbinfo_packed_t), cudaHostAllocDefault));
+            e->info_stale[s].assign(S, 0);
+        } else {
+            ENG_OK(cudaHostAlloc(&e->h_info[s], n * sizeof(b2_mbinfo_t), cudaHostAllocDefault));
+        }
         if (c.pack_levels) {
             e->pack_stride = (size_t)e->nmb * sizeof(b2_mbcoef_t);
             ENG_OK(cudaMalloc(&e->d_pack[s], e->pack_stride * S));
@@ -279,7 +292,9 @@ extern "C" void b2_engine_destroy(b2_engine_t *e)
     cudaFree(e->d_mvf); cudaFree(e->d_mvq); cudaFree(e->d_prev_mv); cudaFree(e->d_cost_full); cudaFree(e->d_cost_inter);
     cudaFree(e->d_c16); cudaFree(e->d_c4); cudaFree(e->d_c8); cudaFree(e->d_pred); cudaFree(e->d_part); cudaFree(e->d_mv8); cudaFree(e->d_mv9); cudaFree(e->d_cost9);
     for (int s = 0; s < 2; s++) {
-        cudaFree(e->d_info[s]); cudaFree(e->d_coef[s]); cudaFreeHost(e->h_info[s]); cudaFreeHost(e->h_coef[s]);
+        cudaFree(e->d_info[s]); cudaFree(e->d_coef[s]); cudaFreeHost(e->h_coef[s]);
+        if (e->cfg.pack_levels) free(e->h_info[s]); else cudaFreeHost(e->h_info[s]);
+        cudaFree(e->d_pinfo[s]); cudaFreeHost(e->h_pinfo[s]);
         cudaFree(e->d_pack[s]); cudaFreeHost(e->h_pack[s]); cudaFree(e->d_pack_n[s]); cudaFreeHost(e->h_pack_n[s]);
     }
     cudaFree(e->d_pack_cum); cudaFree(e->d_pack_chunk); cudaFree(e->d_k8_flags);
@@ -307,7 +322,8 @@ extern "C" void b2_engine_destroy(b2_engine_t *e)
 extern "C" size_t b2_engine_input_bytes(const b2_engine_t *e) { return e->in_bytes; }
 extern "C" size_t b2_engine_result_bytes(const b2_engine_t *e)
 {
-    return (size_t)e->nmb * (sizeof(b2_mbinfo_t) + (e->cfg.pack_levels ? 0 : sizeof(b2_mbcoef_t)));      // + the packed stream when packing
+    return e->cfg.pack_levels ? (size_t)e->nmb * sizeof(b2_mbinfo_packed_t)                      // + the packed level stream
+                              : (size_t)e->nmb * (sizeof(b2_mbinfo_t) + sizeof(b2_mbcoef_t));
 }
 extern "C" void b2_engine_geometry(const b2_engine_t *e, int *mbw, int *mbh, int *w16, int *h16)
 {
@@ -629,7 +645,7 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
         KScope k(e, st, 9);
         e->launches++;                                   // K9a is two kernels (count, scatter)
         if (b2_launch_pack_levels(info, coef, e->d_pack[set] + gr.slot0 * e->pack_stride, e->pack_stride, e->d_pack_n[set] + gr.slot0,
-                                  e->d_pack_cum, e->d_pack_chunk + (size_t)gr.slot0 * b2_pack_chunks(e->nmb), e->nmb, ns, st))
+                                  e->d_pack_cum, e->d_pack_chunk + (size_t)gr.slot0 * b2_pack_chunks(e->nmb), e->d_pinfo[set] + om, e->nmb, ns, st))
             return -1;
     }
     ENG_OK(cudaEventRecord(gr.ev_enc[set], st));
@@ -663,7 +679,12 @@ static int d2h_group(b2_engine *e, Group &gr, int ns)
     const int set = gr.res_set;
     const size_t om = (size_t)gr.slot0 * e->nmb, n = (size_t)e->nmb * ns;
     ENG_OK(cudaStreamWaitEvent(e->st_out, gr.ev_enc[set], 0));
-    ENG_OK(cudaMemcpyAsync(e->h_info[set] + om, e->d_info[set] + om, n * sizeof(b2_mbinfo_t), cudaMemcpyDeviceToHost, e->st_out));
+    if (e->cfg.pack_levels) {
+        ENG_OK(cudaMemcpyAsync(e->h_pinfo[set] + om, e->d_pinfo[set] + om, n * sizeof(b2_mbinfo_packed_t), cudaMemcpyDeviceToHost, e->st_out));
+        for (int s = gr.slot0; s < gr.slot0 + ns; s++) e->info_stale[set][s] = 1;
+    } else {
+        ENG_OK(cudaMemcpyAsync(e->h_info[set] + om, e->d_info[set] + om, n * sizeof(b2_mbinfo_t), cudaMemcpyDeviceToHost, e->st_out));
+    }
     if (e->cfg.pack_levels) {
         if (b2_launch_pack_copy_out(e->d_pack[set] + gr.slot0 * e->pack_stride, e->pack_stride, e->d_pack_n[set] + gr.slot0,
                                     e->h_pack[set] + gr.slot0 * e->pack_stride, e->h_pack_n[set] + gr.slot0, ns, e->st_out))
@@ -707,9 +728,27 @@ extern "C" int b2_engine_group_wait(b2_engine_t *e, int group, int set)
     ENG_OK(cudaEventSynchronize(e->groups[group].ev_d2h[set]));
     return 0;
 }
+// host view of a slot's decisions in result set `set`; with cfg.pack_levels the 24-byte records that were copied out are
+// expanded into it the first time it is asked for after a copy-out (the caller has waited for that copy: b2_engine_group_wait /
+// b2_engine_wait_ticket / b2_engine_sync)
+static const b2_mbinfo_t *info_view(b2_engine *e, int set, int slot)
+{
+    b2_mbinfo_t *dst = e->h_info[set] + (size_t)slot * e->nmb;
+    if (e->cfg.pack_levels && e->info_stale[set][slot]) {
+        const b2_mbinfo_packed_t *src = e->h_pinfo[set] + (size_t)slot * e->nmb;
+        for (int i = 0; i < e->nmb; i++) b2_mbinfo_unpack(&src[i], &dst[i]);
+        e->info_stale[set][slot] = 0;
+    }
+    return dst;
+}
 extern "C" const b2_mbinfo_t *b2_engine_info_set(b2_engine_t *e, int set, int slot)
 {
-    return set < 0 || set > 1 || slot < 0 || slot >= e->cfg.slots ? nullptr : e->h_info[set] + (size_t)slot * e->nmb;
+    return set < 0 || set > 1 || slot < 0 || slot >= e->cfg.slots ? nullptr : info_view(e, set, slot);
+}
+// the 24-byte records themselves (cfg.pack_levels): for hosts that move them on without expanding them here
+extern "C" const b2_mbinfo_packed_t *b2_engine_info_packed_set(b2_engine_t *e, int set, int slot)
+{
+    return set < 0 || set > 1 || slot < 0 || slot >= e->cfg.slots || !e->cfg.pack_levels ? nullptr : e->h_pinfo[set] + (size_t)slot * e->nmb;
 }
 extern "C" const uint8_t *b2_engine_packed_set(b2_engine_t *e, int set, int slot, size_t *bytes)
 {
@@ -753,7 +792,7 @@ extern "C" const b2_mbinfo_t *b2_engine_info_ticket(b2_engine_t *e, int ticket, 
     for (size_t g = 0; g < e->groups.size(); g++)
         if (slot >= e->groups[g].slot0 && slot < e->groups[g].slot0 + e->groups[g].n && g < e->ticket[ticket].set.size() &&
             e->ticket[ticket].set[g] >= 0)
-            return e->h_info[e->ticket[ticket].set[g]] + (size_t)slot * e->nmb;
+            return info_view(e, e->ticket[ticket].set[g], slot);
     return nullptr;
 }
 extern "C" const b2_mbcoef_t *b2_engine_coef_ticket(b2_engine_t *e, int ticket, int slot)
@@ -780,7 +819,7 @@ extern "C" int b2_engine_sync(b2_engine_t *e)
 extern "C" const b2_mbinfo_t *b2_engine_info(b2_engine_t *e, int slot)
 {
     Group *gr = group_of(e, slot);
-    return gr ? e->h_info[gr->host_set] + (size_t)slot * e->nmb : nullptr;
+    return gr ? info_view(e, gr->host_set, slot) : nullptr;
 }
 extern "C" const b2_mbcoef_t *b2_engine_coef(b2_engine_t *e, int slot)
 {

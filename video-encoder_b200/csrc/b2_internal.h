@@ -43,7 +43,8 @@ int b2_launch_deblock(uint8_t *const rec[3], int pitch, int pitchc, size_t strid
 // K9: pack the non-zero level blocks of every frame (k9a, compute stream) and copy exactly the used bytes to pinned host memory (k9b)
 int b2_pack_chunks(int nmb);               // chunks per frame: d_chunk_cnt holds nframes x this many counters (scratch)
 int b2_launch_pack_levels(const b2_mbinfo_t *d_info, const b2_mbcoef_t *d_coef, uint8_t *d_packed, size_t packed_stride,
-                          uint32_t *d_nblocks, unsigned long long *d_cum_bytes, uint32_t *d_chunk_cnt, int nmb, int nframes,
+                          uint32_t *d_nblocks, unsigned long long *d_cum_bytes, uint32_t *d_chunk_cnt,
+                          b2_mbinfo_packed_t *d_pinfo /* [nframes][nmb] 24-byte decision records for the copy-out */, int nmb, int nframes,
                           cudaStream_t st);
 int b2_launch_pack_copy_out(const uint8_t *d_packed, size_t packed_stride, const uint32_t *d_nblocks, uint8_t *h_packed,
                             uint32_t *h_nblocks, int nframes, cudaStream_t st);

@@ -22,11 +22,19 @@ namespace {
 constexpr int K9_CHUNK = 256;             // macroblocks per CTA = threads per CTA
 
 __global__ void __launch_bounds__(K9_CHUNK)
-k9a_count_kernel(const b2_mbinfo_t *__restrict__ info, uint32_t *__restrict__ chunk_cnt, int nmb, int nchunk)
+k9a_count_kernel(const b2_mbinfo_t *__restrict__ info, uint32_t *__restrict__ chunk_cnt, b2_mbinfo_packed_t *__restrict__ pinfo, int nmb, int nchunk)
 {
     __shared__ uint32_t s_warp[K9_CHUNK / 32];
     const int frame = blockIdx.y, m = blockIdx.x * K9_CHUNK + threadIdx.x;
-    uint32_t cnt = m < nmb ? __popc(b2_coef_present(&info[(size_t)frame * nmb + m])) : 0;
+    uint32_t cnt = 0;
+    if (m < nmb) {
+        const b2_mbinfo_t mi = info[(size_t)frame * nmb + m];
+        cnt = __popc(b2_coef_present(&mi));
+        // the 24-byte record that crosses PCIe instead of the 48-byte one (include/b2enc_types.h)
+        const b2_mbinfo_packed_t p = b2_mbinfo_pack(&mi);
+        uint2 *dst = (uint2 *)&pinfo[(size_t)frame * nmb + m];
+        dst[0] = make_uint2(p.w[0], p.w[1]); dst[1] = make_uint2(p.w[2], p.w[3]); dst[2] = make_uint2(p.w[4], p.w[5]);
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = cnt;
@@ -117,10 +125,11 @@ k9b_copy_out_kernel(const uint8_t *__restrict__ packed, size_t packed_stride, co
 }  // namespace
 
 int b2_launch_pack_levels(const b2_mbinfo_t *d_info, const b2_mbcoef_t *d_coef, uint8_t *d_packed, size_t packed_stride,
-                          uint32_t *d_nblocks, unsigned long long *d_cum_bytes, uint32_t *d_chunk_cnt, int nmb, int nframes, cudaStream_t st)
+                          uint32_t *d_nblocks, unsigned long long *d_cum_bytes, uint32_t *d_chunk_cnt, b2_mbinfo_packed_t *d_pinfo, int nmb,
+                          int nframes, cudaStream_t st)
 {
     const int nchunk = b2_pack_chunks(nmb);
-    k9a_count_kernel<<<dim3(nchunk, nframes), K9_CHUNK, 0, st>>>(d_info, d_chunk_cnt, nmb, nchunk);
+    k9a_count_kernel<<<dim3(nchunk, nframes), K9_CHUNK, 0, st>>>(d_info, d_chunk_cnt, d_pinfo, nmb, nchunk);
     k9a_scatter_kernel<<<dim3(nchunk, nframes), K9_CHUNK, 0, st>>>(d_info, d_coef, d_chunk_cnt, d_packed, packed_stride, d_nblocks, d_cum_bytes,
                                                                    nmb, nchunk);
     B2_CUDA_OK(cudaGetLastError());

@@ -411,6 +411,15 @@ void b2h_slice_header(bs_t *b, const b2h_seq_t *s, int is_p, int frame_num, int 
     }
 }
 
+void b2h_info_pack(const b2_mbinfo_t *info, b2_mbinfo_packed_t *packed, int n)
+{
+    for (int i = 0; i < n; i++) packed[i] = b2_mbinfo_pack(&info[i]);
+}
+void b2h_info_unpack(const b2_mbinfo_packed_t *packed, b2_mbinfo_t *info, int n)
+{
+    for (int i = 0; i < n; i++) b2_mbinfo_unpack(&packed[i], &info[i]);
+}
+
 /* ---- slice ---------------------------------------------------------------------------------------*/
 const int16_t b2h_zero_levels[64] = {0};
 

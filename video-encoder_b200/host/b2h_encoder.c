@@ -46,8 +46,9 @@ typedef struct {
 #define B2_MAX_WORKERS 64
 #define B2_MAX_DEVICES 16
 
-/* one frame to entropy-code; the per-MB decisions and the packed levels are heap copies of the engine's pinned result set, so
- * the GPU may run ahead of the entropy workers (the engine keeps only two result sets per slot) */
+/* one frame to entropy-code; the per-MB decisions (as the 24-byte records that crossed PCIe; the worker expands them) and the
+ * packed levels are heap copies of the engine's pinned result set, so the GPU may run ahead of the entropy workers (the engine
+ * keeps only two result sets per slot) */
 typedef struct { int64_t frame; int t; int64_t gop_index; uint8_t *res; size_t packed_bytes; } job_t;
 
 enum { SLOT_FREE = 0, SLOT_OPEN = 1 /* pictures still arriving */, SLOT_CLOSED = 2 /* the GOP's last picture is in */ };
@@ -83,6 +84,7 @@ struct b2_encoder {
     pthread_t workers[B2_MAX_WORKERS];
     b2h_entropy_t *went[B2_MAX_WORKERS];
     uint8_t *wscratch[B2_MAX_WORKERS];
+    b2_mbinfo_t *winfo[B2_MAX_WORKERS];   /* the worker's expanded decision records */
     job_t *jobs;                /* ring */
     int job_cap, job_head, job_count, job_limit;
     outframe_t *fifo;           /* frame f lives in fifo[f % fifo_cap]                          */
@@ -351,7 +353,8 @@ b2_t *b2_encoder_open(b2_param_t *p)
         for (int i = 0; i < nw; i++) {
             h->went[i] = b2h_entropy_create(h->mbw, h->mbh);
             h->wscratch[i] = (uint8_t *)malloc(h->scratch_cap);
-            if (!h->went[i] || !h->wscratch[i]) { b2_encoder_close(h); return NULL; }
+            h->winfo[i] = (b2_mbinfo_t *)malloc((size_t)h->nmb * sizeof(b2_mbinfo_t));
+            if (!h->went[i] || !h->wscratch[i] || !h->winfo[i]) { b2_encoder_close(h); return NULL; }
         }
         pthread_mutex_lock(&h->mu);                      /* workers look themselves up in h->workers[] under the lock */
         for (int i = 0; i < nw; i++) {
@@ -380,7 +383,7 @@ void b2_encoder_close(b2_t *h)
     for (int d = 0; d < h->N; d++)
         if (h->dev[d].started) pthread_join(h->dev[d].thread, NULL);
     for (int i = 0; i < h->nworkers; i++) pthread_join(h->workers[i], NULL);
-    for (int i = 0; i < B2_MAX_WORKERS; i++) { b2h_entropy_destroy(h->went[i]); free(h->wscratch[i]); }
+    for (int i = 0; i < B2_MAX_WORKERS; i++) { b2h_entropy_destroy(h->went[i]); free(h->wscratch[i]); free(h->winfo[i]); }
     if (h->jobs)
         for (int i = 0; i < h->job_count; i++) free(h->jobs[(h->job_head + i) % h->job_cap].res);     /* queued, never coded */
     free(h->jobs);
@@ -459,7 +462,8 @@ static void *worker_main(void *arg)
         pthread_mutex_unlock(&h->mu);
         outframe_t o;
         memset(&o, 0, sizeof(o));
-        int rc = finish_frame(h, h->went[me], h->wscratch[me], (const b2_mbinfo_t *)j.res, j.res + (size_t)h->nmb * sizeof(b2_mbinfo_t),
+        b2h_info_unpack((const b2_mbinfo_packed_t *)j.res, h->winfo[me], h->nmb);
+        int rc = finish_frame(h, h->went[me], h->wscratch[me], h->winfo[me], j.res + (size_t)h->nmb * sizeof(b2_mbinfo_packed_t),
                               j.packed_bytes, j.t, j.gop_index, &o);
         free(j.res);
         pthread_mutex_lock(&h->mu);
@@ -491,11 +495,11 @@ static int fetch_step(dev_t *dv, int s, int t, int set)
 {
     b2_t *h = dv->h;
     slot_t *sl = &dv->slots[s];
-    const b2_mbinfo_t *info = b2_engine_info_set(dv->eng, set, s);
+    const b2_mbinfo_packed_t *info = b2_engine_info_packed_set(dv->eng, set, s);
     size_t packed_bytes = 0;
     const uint8_t *packed = b2_engine_packed_set(dv->eng, set, s, &packed_bytes);
     if (!info || !packed) return -1;
-    const size_t ni = (size_t)h->nmb * sizeof(b2_mbinfo_t);
+    const size_t ni = (size_t)h->nmb * sizeof(b2_mbinfo_packed_t);
     job_t j = {sl->frame0 + t, t, sl->gop_index, (uint8_t *)malloc(ni + packed_bytes + 1), packed_bytes};
     if (!j.res) return -1;
     memcpy(j.res, info, ni);

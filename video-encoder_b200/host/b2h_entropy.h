@@ -43,6 +43,10 @@ size_t b2h_write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type /* B
 size_t b2h_write_slice_packed(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, int frame_num, int idr_pic_id,
                               const b2_mbinfo_t *info, const uint8_t *packed, size_t packed_bytes, uint8_t *out, size_t cap);
 
+/* the 24-byte decision records that cross PCIe (b2_mbinfo_packed_t, include/b2enc_types.h) <-> b2_mbinfo_t, n macroblocks */
+void b2h_info_pack(const b2_mbinfo_t *info, b2_mbinfo_packed_t *packed, int n);
+void b2h_info_unpack(const b2_mbinfo_packed_t *packed, b2_mbinfo_t *info, int n);
+
 #ifdef __cplusplus
 }
 #endif
