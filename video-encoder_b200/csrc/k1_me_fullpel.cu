@@ -18,7 +18,16 @@
 //      - register tiling: a lane owns one dx and K consecutive dy; the current macroblock sits
 //        in 64 registers, each reference row is loaded once (4 LDS.32) and applied to up to K
 //        current rows (K accumulators) -> (16+K-1)*4 loads per 64*K VABSDIFF4.
-//  * Lanes of a warp are 32 consecutive dx -> consecutive words -> no bank conflicts.
+//  * Lanes of a warp are 32 consecutive LANE-TASKS (mb, dy-group, dx).  Inside one (mb, dy-group) segment that is 32 consecutive
+//    dx = 32 consecutive words: one wavefront.  A segment is 2R+1 = 65 (33) tasks long, not a multiple of 32, so about every other
+//    warp-task straddles two segments whose rows start at the same bank (EXP_PITCH % 32 == 0): its sweep LDS.32 then take two
+//    wavefronts.  ncu, per instruction (profiles/r2_k1_lds_bank_conflicts.txt): every sweep LDS averages 1.475 wavefronts, together
+//    17.8 M of the kernel's 18.4 M excess wavefronts per 4-frame launch; the remaining 0.6 M are the ATOMS.MIN on the best keys.
+//    The shared-memory pipe still runs at only 0.46 wavefronts/clk/SM while the ALU pipe is 92 % busy, so this is not the limiter --
+//    and the fix was measured to cost more than it saves: a pitch with K * pitch = 1 (mod 32) lines the two segments' banks up, but
+//    such a pitch is odd, so the expansion can no longer store 16 bytes per lane; bit-identical, 0.889 -> 0.868 of the VABSDIFF4 peak
+//    with word-wise expansion alone and 0.853 with the padded pitch (+-16: 0.836 -> 0.787; scripts/k1_exppad_probe.py,
+//    profiles/r2_k1_exppad_ab.txt).  The conflicts stay.
 //  * Winner: key = (cost << 13) | scan_index, CREDUX.MIN over the warp, atomicMin in smem.
 //    Lowest scan index wins ties by construction, exactly like the oracle's strict '<'.
 #include <stdlib.h>
