@@ -302,6 +302,9 @@ def main():
     ap.add_argument("--pack-levels", type=int, default=1, help="1: levels leave the GPU packed (K9: only blocks with a non-zero level); "
                     "0: dense 832 B/MB array")
     ap.add_argument("--partitions", type=int, default=0, help="1: inter partitions 16x8/8x16/8x8 (row N1, outside the named path)")
+    ap.add_argument("--me-prune", type=int, default=0, help="1: run the MAIN legs with the lossless search pruning on (default 0: exhaustive; the "
+                    "pruned figures are reported beside them under `pruned`)")
+    ap.add_argument("--no-pruned-leg", action="store_true", help="skip the `pruned` leg")
     ap.add_argument("--transform8x8", type=int, default=0, help="1: adaptive 8x8 transform for inter MBs (row N1, outside the named path)")
     args = ap.parse_args()
     select_workload(args.workload)
@@ -338,13 +341,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    eng = b2enc.Engine(W, H, slots=SLOTS, fmt="yuv420p", ring=RING, merange=MERANGE, qp=QP, subpel=1, intra_in_p=1,
-                       device=local, profile=0, streams=STREAMS, deblock=args.deblock, transform8x8=args.transform8x8,
-                       pack_levels=args.pack_levels, partitions=args.partitions)
-    fill_inputs(eng, b2oracle, rank)
-    for r in range(RING):
-        eng.h2d(ring=r)
-    eng.sync()
+    def make_engine(me_prune, profile=0, streams=STREAMS, ring=RING):
+        e = b2enc.Engine(W, H, slots=SLOTS, fmt="yuv420p", ring=ring, merange=MERANGE, qp=QP, subpel=1, intra_in_p=1,
+                         device=local, profile=profile, streams=streams, deblock=args.deblock, transform8x8=args.transform8x8,
+                         pack_levels=args.pack_levels, partitions=args.partitions, me_prune=me_prune)
+        fill_inputs(e, b2oracle, rank)
+        for r in range(ring):
+            e.h2d(ring=r)
+        e.sync()
+        return e
+
+    eng = make_engine(args.me_prune)
     int_rate, _ = b2enc.vabsdiff4_peak(local, 512, 5)           # VABSDIFF4 lane-instructions / s, live
 
     groups = eng.groups()
@@ -355,7 +362,7 @@ def main():
         """frame type of group g at global step `step` (step 0 = every group's first IDR)"""
         return b2enc.FRAME_I if step == 0 or (step + phase[g]) % GOP == 0 else b2enc.FRAME_P
 
-    def issue(step, with_copies):
+    def issue(step, with_copies, eng=eng):
         ring = step % RING
         if with_copies:
             eng.h2d(ring=ring)                                   # this step's pictures: pinned host -> device ring
@@ -404,24 +411,67 @@ def main():
     # ---- K1/K0 alone (one stream, nothing overlapping): the roofline numerator --------------------------
     iso = None
     verify = None
+    pruned = None
     if rank == 0:
         if not args.no_verify:
             verify = verify_final_state(eng, b2enc, b2oracle, rank, groups, ftype, step - 1, args)
         eng.close()
-        eng1 = b2enc.Engine(W, H, slots=SLOTS, fmt="yuv420p", ring=2, merange=MERANGE, qp=QP, subpel=1, intra_in_p=1,
-                            device=local, profile=1, streams=1, deblock=args.deblock, transform8x8=args.transform8x8,
-                            pack_levels=args.pack_levels, partitions=args.partitions)
-        fill_inputs(eng1, b2oracle, rank)
-        eng1.h2d(ring=0); eng1.h2d(ring=1)
-        eng1.encode(b2enc.FRAME_I, ring=0)
-        for i in range(2):
-            eng1.encode(b2enc.FRAME_P, ring=(i + 1) % 2)
-        eng1.sync(); eng1.profile_reset()
-        for i in range(8):
-            eng1.encode(b2enc.FRAME_P, ring=i % 2)
-        iso = eng1.kernel_ms()
-        mbs, in_bytes, w16, h16 = eng1.nmb, eng1.in_bytes, eng1.w16, eng1.h16
-        eng1.close()
+
+        def kernels_alone(me_prune):
+            e1 = make_engine(me_prune, profile=1, streams=1, ring=2)
+            e1.encode(b2enc.FRAME_I, ring=0)
+            for i in range(2):
+                e1.encode(b2enc.FRAME_P, ring=(i + 1) % 2)
+            e1.sync(); e1.profile_reset()
+            for i in range(8):
+                e1.encode(b2enc.FRAME_P, ring=i % 2)
+            r = e1.kernel_ms(), e1.nmb, e1.in_bytes, e1.w16, e1.h16
+            e1.close()
+            return r
+
+        # the roofline kernel is ALWAYS the exhaustive one, whatever --me-prune says
+        iso, mbs, in_bytes, w16, h16 = kernels_alone(0)
+
+        # ---- the same workload with the lossless search pruning on (engine option me_prune; reported beside, never instead) ----
+        if world == 1 and not args.no_pruned_leg and not args.me_prune and args.partitions != 2:
+            engp = make_engine(1)
+            sp = 0
+            for _ in range(args.warmup):
+                issue(sp, False, engp); sp += 1
+            engp.sync()
+            sw0, al0 = engp.k1_stats()
+            engp.timer_start()
+            for _ in range(args.steps):
+                issue(sp, False, engp); sp += 1
+            msp = engp.timer_stop()
+            engp.sync()
+            sw1, al1 = engp.k1_stats()
+            for _ in range(2):
+                issue(sp, True, engp); sp += 1
+            engp.sync()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                issue(sp, True, engp); sp += 1
+            engp.sync()
+            e2ep = time.perf_counter() - t0
+            vp = None
+            if not args.no_verify:
+                vp = verify_final_state(engp, b2enc, b2oracle, rank, groups, ftype, sp - 1, args)
+            engp.close()
+            isop = kernels_alone(1)[0]
+            pruned = {"value": round(SLOTS * args.steps / (msp * 1e-3), 2), "unit": UNIT, "ms_per_step": round(msp / args.steps, 4),
+                      "e2e": round(SLOTS * args.steps / e2ep, 2),
+                      "verified": vp["verified"] if vp else None, "verify_seconds": vp["seconds"] if vp else None,
+                      "k1_lane_tasks_executed": int(sw1 - sw0), "k1_lane_tasks_algorithmic": int(al1 - al0),
+                      "k1_executed_fraction": round((sw1 - sw0) / max(al1 - al0, 1), 4),
+                      "k1_ms_per_step_alone": round(isop["K1 full-pel SAD"][0] / 8, 4),
+                      "k1_ms_per_step_alone_exhaustive": round(iso["K1 full-pel SAD"][0] / 8, 4),
+                      "what": "engine option me_prune=1: K1a (16x16 block sums of the reference, once per P step) + successive elimination in K1 -- a "
+                              "candidate whose |sum(cur) - sum(ref)| + mvcost exceeds the exact cost of the zero vector / the rounded predictor cannot be "
+                              "the minimum; vectors, costs and tie-break are those of the exhaustive scan (tests/test_me_fullpel.py, the oracle "
+                              "replay above), only the time changes, and it depends on the content (this synthetic sequence pans uniformly, so the "
+                              "predictor is exact; k1_executed_fraction says how much of the exhaustive work ran).  Not part of `value`, `e2e` or "
+                              "`roofline`: those are the exhaustive search"}
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -464,6 +514,9 @@ def main():
                                  "algorithmic_bytes_per_launch": int(k0_bytes)}},
             "kernel_ms_per_step_alone": {k: round(v[0] / 8, 4) for k, v in iso.items()},
         }
+        out["config"]["me_prune"] = bool(args.me_prune)
+        if pruned:
+            out["pruned"] = pruned
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         if world == 1 and not args.no_dropin and args.workload in ("c2", "c3"):

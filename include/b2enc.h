@@ -89,6 +89,9 @@ typedef struct {
     int i_devices;                      /* GPUs one stream is spread over by closed GOP: GOP k is encoded on device
                                            i_device + k % i_devices; the output is byte-identical for every value.
                                            0 (default) = environment variable B2ENC_DEVICES, else 1                          */
+    int b_me_prune;                     /* lossless pruning of the exhaustive full-pel search (successive elimination, the idea
+                                           behind x264's me=esa): the stream is byte-identical with 0 and 1, only the time differs.
+                                           Default 1; the environment variable B2ENC_ME_PRUNE=0/1 overrides it                   */
 } b2_param_t;
 
 typedef struct {

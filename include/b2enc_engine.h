@@ -40,6 +40,9 @@ typedef struct {
     int pack_levels;   /* 1: levels leave the GPU packed (only blocks with a non-zero level, K9):   */
                        /* b2_engine_packed* replace b2_engine_coef*, which then return NULL         */
     int deblock_alpha, deblock_beta;   /* loop-filter offsets (slice_alpha_c0_offset_div2 / slice_beta_offset_div2, -6..6) */
+    int me_prune;      /* 1: lossless pruning of the exhaustive full-pel search (successive elimination: candidates whose      */
+                       /* block-sum lower bound exceeds an exactly evaluated cost are skipped).  Vectors, costs and tie-break  */
+                       /* are those of the exhaustive scan; the time is content dependent.  Ignored with partitions == 2.      */
 } b2_engine_cfg_t;
 
 b2_engine_t *b2_engine_create(const b2_engine_cfg_t *cfg);      /* NULL on error */
@@ -125,6 +128,9 @@ enum { B2_NKERNELS = 10 };
 int b2_engine_kernel_ms(b2_engine_t *e, int which, double *ms_total, long *launches);
 void b2_engine_profile_reset(b2_engine_t *e);
 long b2_engine_launch_count(const b2_engine_t *e);              /* kernels launched since creation */
+/* cfg.me_prune: lane-tasks (macroblock, dy-group, dx) the pruned search ran since creation and what the exhaustive search runs for
+ * the same steps (executed vs algorithmic work).  Synchronises the device.  -1 when pruning is off. */
+int b2_engine_k1_stats(b2_engine_t *e, unsigned long long *swept, unsigned long long *all);
 
 #ifdef __cplusplus
 }

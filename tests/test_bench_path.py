@@ -26,9 +26,9 @@ class OracleSlot:
         return info, coef, rec
 
 
-def replay(oracle, b2, w, h, slots, streams, ring, gop, steps, R=16, qp=28, deblock=0, check_slots=None, distinct=True):
+def replay(oracle, b2, w, h, slots, streams, ring, gop, steps, R=16, qp=28, deblock=0, check_slots=None, distinct=True, me_prune=0):
     eng = b2.Engine(w, h, slots=slots, fmt="yuv420p", ring=ring, merange=R, qp=qp, subpel=1, intra_in_p=1, streams=streams,
-                    deblock=deblock, pack_levels=1)
+                    deblock=deblock, pack_levels=1, me_prune=me_prune)
     groups = eng.groups(); NG = len(groups)
     phase = [g * gop // NG for g in range(NG)]                       # bench.py: staggered GOP phases
     group_of = {s: g for g, (s0, n) in enumerate(groups) for s in range(s0, s0 + n)}
@@ -109,3 +109,11 @@ def test_bench_issue_path_64_slots(oracle, b2):
 def test_bench_issue_path_1080p_spot_check(oracle, b2):
     """C3 size (1920x1080, +-32, QP 26, 64 slots, ring pictures repeating like bench.py's): first slot of two groups over I, P, P"""
     replay(oracle, b2, 1920, 1080, slots=64, streams=8, ring=8, gop=32, steps=3, R=32, qp=26, check_slots=[0, 40], distinct=False)
+
+
+def test_bench_issue_path_pruned_search(oracle, b2):
+    """the same path with me_prune=1 (bench.py's `pruned` leg): K1a + pruned K1 of eight stream groups overlap, the block-sum planes
+    are per slot and refilled every P step; every slot of every step still equals the oracle's exhaustive search.  Plus the C3-size
+    spot check."""
+    replay(oracle, b2, 96, 64, slots=16, streams=8, ring=8, gop=8, steps=28, deblock=1, me_prune=1)
+    replay(oracle, b2, 1920, 1080, slots=64, streams=8, ring=8, gop=32, steps=3, R=32, qp=26, check_slots=[0, 40], distinct=False, me_prune=1)

@@ -172,6 +172,20 @@ def test_slot_count_does_not_change_the_stream(b2):
     assert streams[0] == streams[1] == streams[2]
 
 
+def test_search_pruning_does_not_change_the_stream(b2):
+    """b_me_prune (default 1: successive elimination in front of the exhaustive search) is lossless: the stream is byte-identical
+    with the switch off, +-16 and +-32, with a scene cut so that predictors are poor"""
+    w, h, n = 176, 144, 9
+    frames = smooth_seq(w, h, n, seed=21, cut=4)
+    for preset in ("medium", "slow"):
+        streams = []
+        for prune in (0, 1):
+            out = drive(b2, frames, w, h, preset=preset, tune=None, quality=28, annexb=1, i_keyint_max=5, i_gop_slots=2, b_me_prune=prune)
+            assert len(out) == n
+            streams.append(to_annexb(out, length_prefixed=False))
+        assert streams[0] == streams[1], preset
+
+
 def test_delay_contract(b2):
     """0 = no output yet, delayed_frames() = frames in - frames out at every call, encode(NULL) returns one frame per call until
     the encoder is empty (av_encode.c:971-974, :1076-1083); GOPs are encoded while they are gathered, so the first frame

@@ -12,11 +12,12 @@ INFO_FIELDS = ["mb_type", "mvx", "mvy", "i16_mode", "chroma_mode", "cbp", "i4_mo
 
 
 def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="yuv420p", deblock=0, transform8x8=0, pack_levels=0,
-                    partitions=0, deblock_offsets=(0, 0)):
+                    partitions=0, deblock_offsets=(0, 0), me_prune=0):
     """seqs: list (one per slot) of lists of (y,u,v) frames"""
     S, T = len(seqs), len(seqs[0])
     eng = b2.Engine(w, h, slots=S, fmt=fmt, ring=2, merange=R, qp=qp, subpel=subpel, intra_in_p=intra_in_p, deblock=deblock,
-                    transform8x8=transform8x8, pack_levels=pack_levels, partitions=partitions, deblock_offsets=deblock_offsets)
+                    transform8x8=transform8x8, pack_levels=pack_levels, partitions=partitions, deblock_offsets=deblock_offsets,
+                    me_prune=me_prune)
     prm = oracle.Params(qp, R, subpel, intra_in_p, deblock, transform8x8, partitions, deblock_offsets[0], deblock_offsets[1])
     stats = {"t8": 0, "coded4": 0, "i8": 0, "parts": np.zeros(4, int), "mvx_mod4": np.zeros(4, int)}
     prev = [None] * S; prev_mv = [None] * S
@@ -53,6 +54,10 @@ def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="
             stats["coded4"] += int(((info_o["mb_type"] == 0) & (info_o["transform8x8"] == 0) & ((info_o["cbp"] & 15) != 0)).sum())
             prev[s] = rec
             prev_mv[s] = np.zeros(info_o.size, oracle.MV); prev_mv[s]["x"] = info_o["mvx"]; prev_mv[s]["y"] = info_o["mvy"]
+    if me_prune and partitions != 2 and T > 1:
+        swept, every = eng.k1_stats()
+        assert 0 < swept <= every
+        stats["k1_swept"] = swept / every
     eng.close()
     return stats
 
@@ -62,6 +67,16 @@ def run_and_compare(oracle, b2, seqs, w, h, qp, R, subpel=1, intra_in_p=1, fmt="
 def test_engine_matches_oracle(oracle, b2, w, h, qp, R, cut):
     seqs = [smooth_seq(w, h, 5, seed=qp, cut=cut)]
     run_and_compare(oracle, b2, seqs, w, h, qp, R)
+
+
+@pytest.mark.parametrize("w,h,qp,R,cut", [(176, 144, 26, 16, None), (320, 240, 32, 32, 2), (318, 242, 28, 16, 3), (64, 48, 45, 32, 1)])
+def test_engine_pruned_search_matches_oracle(oracle, b2, w, h, qp, R, cut):
+    """engine option me_prune (K1a block sums + successive elimination in K1): every stage output still equals the oracle's, whose
+    full-pel search is the plain exhaustive scan; several slots, scene cuts (predictors that point nowhere), packed and all tools on"""
+    seqs = [smooth_seq(w, h, 5, seed=qp, cut=cut), smooth_seq(w, h, 5, seed=qp + 1), [oracle.synth_frame(w, h, t, 1) for t in range(5)]]
+    st = run_and_compare(oracle, b2, seqs, w, h, qp, R, me_prune=1)
+    assert st["k1_swept"] < 1.0
+    run_and_compare(oracle, b2, seqs[:2], w, h, qp, R, me_prune=1, deblock=1, transform8x8=1, partitions=1, pack_levels=1)
 
 
 def test_k2_patch_alignments(oracle, b2):

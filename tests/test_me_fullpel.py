@@ -133,3 +133,111 @@ def test_persistent_pipelined_kernel_is_bit_exact():
                        capture_output=True, text=True, env=env, timeout=600, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert " passed" in r.stdout
+
+
+# ---- K1 with lossless pruning (engine option me_prune): K1a block sums + successive elimination ---------------------------
+def _check_pruned(oracle, b2, cur, ref, R, pmv=None, lam=0):
+    """vectors and costs equal the oracle's exhaustive scan (and hence the un-pruned kernel's); returns swept / all lane-tasks"""
+    mv_g, cost_g, st = b2.me_fullpel_pruned(cur, ref, R, pmv, lam)
+    for i in range(cur.shape[0]):
+        mv_o, cost_o = _oracle_me(oracle, cur[i], ref[i], R, None if pmv is None else pmv[i], lam)
+        assert np.array_equal(cost_g[i], cost_o), f"cost mismatch frame {i}: {np.argwhere(cost_g[i] != cost_o)[:4].tolist()}"
+        assert np.array_equal(mv_g[i]["x"], mv_o["x"]) and np.array_equal(mv_g[i]["y"], mv_o["y"]), f"mv mismatch frame {i}"
+    assert 0 < st["swept"] <= st["all"]
+    return st["swept"] / st["all"]
+
+
+def test_block_sums_kernel(b2):
+    """K1a against numpy: sum of every 16x16 block of the padded plane, zero where the block leaves the allocation"""
+    rng = np.random.default_rng(5)
+    for (w, h) in ((176, 144), (16, 16), (400, 48)):
+        y = rng.integers(0, 256, (2, h, w), dtype=np.uint8)
+        y[1] = 255                                                  # the largest sums: 65,280 must not wrap
+        got = b2.block_sums(y)
+        n, rows, pitch = got.shape
+        for i in range(n):
+            # the padded plane as the kernels see it: picture at (64,64), replicated border, pitch beyond w + 128 is allocation slack
+            pad = np.zeros((rows, pitch), np.int64)
+            ext = np.pad(y[i], 64, mode="edge")
+            pad[:ext.shape[0], :ext.shape[1]] = ext
+            ii = np.zeros((rows + 1, pitch + 1), np.int64); ii[1:, 1:] = pad.cumsum(0).cumsum(1)
+            want = ii[16:, 16:] - ii[:-16, 16:] - ii[16:, :-16] + ii[:-16, :-16]          # [rows-15, pitch-15]
+            # only the part the search reads is pinned: blocks inside the padded picture (the slack columns hold whatever the upload left)
+            H, W = ext.shape
+            assert np.array_equal(got[i, :H - 15, :W - 15], want[:H - 15, :W - 15].astype(np.uint16)), (w, h, i)
+
+
+@pytest.mark.parametrize("R", [16, 32])
+@pytest.mark.parametrize("wh", [(128, 64), (80, 48), (176, 144), (16, 16), (208, 32)])
+def test_pruned_random_frames(oracle, b2, R, wh):
+    """white noise: the bound prunes next to nothing, every path of the survivor list (full words, ragged strips) is exercised"""
+    w, h = wh
+    rng = np.random.default_rng(R * 1000 + w)
+    cur = rng.integers(0, 256, (2, h, w), dtype=np.uint8)
+    ref = rng.integers(0, 256, (2, h, w), dtype=np.uint8)
+    _check_pruned(oracle, b2, cur, ref, R)
+
+
+@pytest.mark.parametrize("R", [16, 32])
+def test_pruned_adversarial_ties(oracle, b2, R):
+    """flat / periodic / saturated content: candidates tie at the minimum, all of them have to survive the bound and the lowest
+    scan index has to win exactly as in the exhaustive scan"""
+    w, h = 192, 96
+    flat = np.full((h, w), 77, np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w]
+    periodic = (((xx // 4) + (yy // 4)) % 2 * 255).astype(np.uint8)
+    stripes = ((xx % 8) * 32).astype(np.uint8)
+    sat = np.where(xx > w // 2, 255, 0).astype(np.uint8)
+    cur = np.stack([flat, periodic, stripes, sat, flat])
+    ref = np.stack([flat, periodic, stripes, sat, np.full((h, w), 80, np.uint8)])
+    _check_pruned(oracle, b2, cur, ref, R)
+    mv, cost, _ = b2.me_fullpel_pruned(cur[:1], ref[:1], R)
+    assert (mv["x"] == -R).all() and (mv["y"] == -R).all() and (cost == 0).all()
+
+
+@pytest.mark.parametrize("R", [16, 32])
+def test_pruned_lambda_and_predictors(oracle, b2, R):
+    """true motion + random (mostly wrong, partly out-of-range) predictors and three lambdas: the threshold candidates are poor,
+    the vector costs large; results still equal the exhaustive scan"""
+    w, h = 256, 80
+    rng = np.random.default_rng(7 + R)
+    base = rng.integers(0, 256, (h + 80, w + 80), dtype=np.uint8)
+    ref = base[40:40 + h, 40:40 + w][None].copy()
+    cur = base[43:43 + h, 35:35 + w][None].copy()
+    pmv = np.zeros((1, (w // 16) * (h // 16)), b2.MV)
+    pmv["x"] = rng.integers(-140, 140, pmv.shape); pmv["y"] = rng.integers(-140, 140, pmv.shape)
+    for lam in (0, 4, 91):
+        _check_pruned(oracle, b2, cur, ref, R, pmv, lam)
+    good = np.zeros_like(pmv); good["x"] = -20; good["y"] = 12                            # the true motion in quarter-pels
+    frac = _check_pruned(oracle, b2, cur, ref, R, good, 4)
+    assert frac < 0.9                                                                      # a good predictor does prune
+
+
+@pytest.mark.parametrize("R", [16, 32])
+def test_pruned_smooth_content_matches_exhaustive_kernel(b2, R):
+    """smooth moving content (where the bound bites): pruned == un-pruned kernel on every macroblock, several frames per launch"""
+    import scipy.ndimage as ndi
+    rng = np.random.default_rng(11)
+    w, h, n = 352, 288, 3
+    big = ndi.gaussian_filter(rng.normal(size=(h + 64, w + 64)), 6.0)
+    big = (big - big.min()) / (big.max() - big.min()) * 220 + 16 + rng.normal(size=big.shape) * 2
+    frames = [np.clip(big[20 + 3 * t:20 + 3 * t + h, 20 + 5 * t:20 + 5 * t + w], 0, 255).astype(np.uint8) for t in range(n + 1)]
+    cur = np.stack(frames[1:]); ref = np.stack(frames[:-1])
+    pmv = np.zeros((n, (w // 16) * (h // 16)), b2.MV); pmv["x"] = -20; pmv["y"] = -12
+    for lam in (0, 5):
+        mv_a, cost_a, _ = b2.me_fullpel(cur, ref, R, pmv, lam)
+        mv_b, cost_b, st = b2.me_fullpel_pruned(cur, ref, R, pmv, lam)
+        assert np.array_equal(mv_a, mv_b) and np.array_equal(cost_a, cost_b)
+        assert st["swept"] < (0.7 if R == 32 else 0.9) * st["all"], st        # +-16 has only three dy groups per column
+
+
+def test_pruned_synth_1080p(oracle, b2):
+    """C3 size, the bench's synthetic sequence: identical to the exhaustive kernel on all 8,160 macroblocks"""
+    w, h = 1920, 1088
+    y0, _, _ = oracle.synth_frame(w, h, 4)
+    y1, _, _ = oracle.synth_frame(w, h, 5)
+    pmv = np.zeros((1, (w // 16) * (h // 16)), b2.MV); pmv["x"] = 12; pmv["y"] = 8
+    mv_a, cost_a, _ = b2.me_fullpel(y1, y0, 32, pmv, 5)
+    mv_b, cost_b, st = b2.me_fullpel_pruned(y1, y0, 32, pmv, 5)
+    assert np.array_equal(mv_a, mv_b) and np.array_equal(cost_a, cost_b)
+    assert st["swept"] < 0.6 * st["all"], st

@@ -67,6 +67,48 @@ def me_fullpel(cur_y, ref_y, merange, pmv=None, lam=0, iters=0):
     return mv, cost, (ms.value if iters > 0 else None)
 
 
+def me_fullpel_pruned(cur_y, ref_y, merange, pmv=None, lam=0, iters=0):
+    """K1 with lossless pruning (K1a block sums + successive elimination).  Returns (mv, cost, stats) with stats =
+    {"kernel_ms", "sums_ms" (None without iters), "swept", "all"}: lane-tasks that ran / that the exhaustive kernel runs."""
+    require_gpu()
+    cur_y = np.ascontiguousarray(cur_y, np.uint8); ref_y = np.ascontiguousarray(ref_y, np.uint8)
+    if cur_y.ndim == 2:
+        cur_y = cur_y[None]; ref_y = ref_y[None]
+    n, h, w = cur_y.shape
+    nmb = (w // 16) * (h // 16)
+    mv = np.zeros((n, nmb), MV); cost = np.zeros((n, nmb), np.uint32)
+    if pmv is not None:
+        pmv = np.ascontiguousarray(pmv, MV).reshape(n, nmb)
+    ms = C.c_float(0); sms = C.c_float(0); swept = C.c_ulonglong(0); every = C.c_ulonglong(0)
+    L = lib()
+    L.b2k_me_fullpel_pruned.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.b2k_me_fullpel_pruned(_p(cur_y), _p(ref_y), w, h, n, merange, _p(pmv), lam, _p(mv), _p(cost), iters,
+                                 C.addressof(ms) if iters > 0 else None, C.addressof(sms), C.addressof(swept), C.addressof(every))
+    if rc != 0:
+        raise RuntimeError("b2k_me_fullpel_pruned failed (%d)" % rc)
+    return mv, cost, {"kernel_ms": ms.value if iters > 0 else None, "sums_ms": sms.value if iters > 0 else None,
+                      "swept": swept.value, "all": every.value}
+
+
+def block_sums(y):
+    """K1a alone: y uint8 [n,h,w] -> u16 [n,rows,pitch] block sums of the padded planes (see b2k_block_sums)"""
+    require_gpu()
+    y = np.ascontiguousarray(y, np.uint8)
+    if y.ndim == 2:
+        y = y[None]
+    n, h, w = y.shape
+    pitch = C.c_int(0); rows = C.c_int(0)
+    L = lib()
+    L.b2k_block_sums.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    if L.b2k_block_sums(_p(y), w, h, n, None, C.addressof(pitch), C.addressof(rows)) != 0:
+        raise RuntimeError("b2k_block_sums failed")
+    out = np.zeros((n, rows.value, pitch.value), np.uint16)
+    if L.b2k_block_sums(_p(y), w, h, n, _p(out), None, None) != 0:
+        raise RuntimeError("b2k_block_sums failed")
+    return out
+
+
 def me_fullpel_parts(cur_y, ref_y, merange, pmv=None, lam=0, iters=0):
     """K1 partition variant: returns (mv9[n,mbs,9], cost9[n,mbs,9], kernel_ms|None)"""
     require_gpu()
@@ -175,14 +217,15 @@ class EngineCfg(C.Structure):
     _fields_ = [("device", C.c_int), ("width", C.c_int), ("height", C.c_int), ("slots", C.c_int), ("in_fmt", C.c_int),
                 ("in_ring", C.c_int), ("merange", C.c_int), ("qp", C.c_int), ("subpel", C.c_int), ("intra_in_p", C.c_int),
                 ("profile", C.c_int), ("streams", C.c_int), ("deblock", C.c_int), ("transform8x8", C.c_int), ("partitions", C.c_int), ("pack_levels", C.c_int),
-                ("deblock_alpha", C.c_int), ("deblock_beta", C.c_int)]
+                ("deblock_alpha", C.c_int), ("deblock_beta", C.c_int), ("me_prune", C.c_int)]
 
 
 class Engine:
     """One GPU's encode-stage engine: `slots` closed GOPs / streams advanced in lock-step."""
 
     def __init__(self, width, height, slots=1, fmt="yuv420p", ring=1, merange=16, qp=26, subpel=1, intra_in_p=1,
-                 device=0, profile=0, streams=0, deblock=0, transform8x8=0, pack_levels=0, partitions=0, deblock_offsets=(0, 0)):
+                 device=0, profile=0, streams=0, deblock=0, transform8x8=0, pack_levels=0, partitions=0, deblock_offsets=(0, 0),
+                 me_prune=0):
         require_gpu()
         L = lib()
         L.b2_engine_create.restype = C.c_void_p
@@ -222,7 +265,8 @@ class Engine:
         self.L = L
         self.cfg = EngineCfg(device, width, height, slots, FMT[fmt] if isinstance(fmt, str) else fmt, ring, merange, qp,
                              subpel, intra_in_p, profile, streams, deblock, transform8x8, partitions, pack_levels,
-                             deblock_offsets[0], deblock_offsets[1])
+                             deblock_offsets[0], deblock_offsets[1], me_prune)
+        L.b2_engine_k1_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         self.h = L.b2_engine_create(C.byref(self.cfg))
         if not self.h:
             raise RuntimeError("b2_engine_create failed")
@@ -233,6 +277,13 @@ class Engine:
         self.width, self.height, self.slots, self.ring = width, height, slots, ring
         self.in_bytes = L.b2_engine_input_bytes(self.h)
         self.result_bytes = L.b2_engine_result_bytes(self.h)
+
+    def k1_stats(self):
+        """me_prune: (lane-tasks the pruned search ran, lane-tasks of the exhaustive search) since creation; None when pruning is off"""
+        a = C.c_ulonglong(0); b = C.c_ulonglong(0)
+        if self.L.b2_engine_k1_stats(self.h, C.addressof(a), C.addressof(b)) != 0:
+            return None
+        return a.value, b.value
 
     def close(self):
         if self.h:
@@ -391,7 +442,8 @@ class Param(C.Structure):
                 ("vui", _Vui), ("rc", _Rc), ("i_keyint_max", C.c_int), ("i_gop_slots", C.c_int), ("i_merange", C.c_int),
                 ("b_subpel", C.c_int), ("b_intra_in_p", C.c_int), ("i_device", C.c_int), ("i_csp_in", C.c_int),
                 ("b_deblocking_filter", C.c_int), ("b_cabac", C.c_int), ("b_transform_8x8", C.c_int), ("b_partitions", C.c_int),
-                ("i_deblocking_filter_alphac0", C.c_int), ("i_deblocking_filter_beta", C.c_int), ("i_devices", C.c_int)]
+                ("i_deblocking_filter_alphac0", C.c_int), ("i_deblocking_filter_beta", C.c_int), ("i_devices", C.c_int),
+                ("b_me_prune", C.c_int)]
 
 
 class Image(C.Structure):

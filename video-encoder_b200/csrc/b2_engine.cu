@@ -49,7 +49,7 @@ static int test_fault()
 struct Group {
     int slot0 = 0, n = 0;
     cudaStream_t st = nullptr;
-    CUtensorMap tm_cur, tm_ref[2];
+    CUtensorMap tm_cur, tm_ref[2], tm_sum;
     int ref_idx = 0;                       // d_rec[ref_idx] holds this group's latest reconstruction
     int res_set = 0, host_set = 0;
     int last_n = 0;                        // slots covered by the most recent encode
@@ -86,6 +86,9 @@ struct b2_engine {
     uint32_t *d_pack_n[2] = {}, *h_pack_n[2] = {};
     unsigned long long *d_pack_cum = nullptr;
     uint32_t *d_pack_chunk = nullptr;              // K9a scratch: present blocks per chunk of macroblocks, [S][chunks]
+    uint16_t *d_sum = nullptr;             // cfg.me_prune: [S][rows][pitch] 16x16 block sums of the reference planes (K1a), refilled per P step
+    unsigned long long *d_k1_swept = nullptr;      // cfg.me_prune: lane-tasks the pruned K1 launches ran, accumulated on the device
+    long long k1_all = 0;                          //               ... and what the exhaustive kernel would have run
     int *d_k8_flags = nullptr;                     // K8 row pipeline: cross-CTA progress flags [S][8]
     size_t pack_stride = 0;
     std::vector<Group> groups;
@@ -192,6 +195,12 @@ static int engine_alloc(b2_engine *e)
             ENG_OK(cudaHostAlloc(&e->h_coef[s], n * sizeof(b2_mbcoef_t), cudaHostAllocDefault));
         }
     }
+    if (c.me_prune && c.partitions != 2) {                        // the wide partition search keeps the exhaustive kernel (nine minima per MB)
+        ENG_OK(cudaMalloc(&e->d_sum, e->stride_y * S * sizeof(uint16_t)));
+        ENG_OK(cudaMemset(e->d_sum, 0, e->stride_y * S * sizeof(uint16_t)));
+        ENG_OK(cudaMalloc(&e->d_k1_swept, sizeof(unsigned long long)));
+        ENG_OK(cudaMemset(e->d_k1_swept, 0, sizeof(unsigned long long)));
+    }
     ENG_OK(cudaMalloc(&e->d_k8_flags, S * 8 * sizeof(int)));
     ENG_OK(cudaMemset(e->d_k8_flags, 0, S * 8 * sizeof(int)));
     if (c.pack_levels) {
@@ -245,6 +254,11 @@ static int engine_alloc(b2_engine *e)
         if (b2_make_plane_tmap(&gr.tm_cur, e->d_cur[0] + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, 16 * b2_k1_strip_mbs(c.merange), 16)) return -1;
         if (b2_make_plane_tmap(&gr.tm_ref[0], e->d_rec[0][0] + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, bw, bh)) return -1;
         if (b2_make_plane_tmap(&gr.tm_ref[1], e->d_rec[1][0] + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, bw, bh)) return -1;
+        if (e->d_sum) {
+            int sw, sh;
+            if (b2_k1_sum_box(c.merange, &sw, &sh)) return -1;
+            if (b2_make_plane_tmap16(&gr.tm_sum, e->d_sum + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, sw, sh)) return -1;
+        }
     }
     return 0;
 }
@@ -297,7 +311,7 @@ extern "C" void b2_engine_destroy(b2_engine_t *e)
         cudaFree(e->d_pinfo[s]); cudaFreeHost(e->h_pinfo[s]);
         cudaFree(e->d_pack[s]); cudaFreeHost(e->h_pack[s]); cudaFree(e->d_pack_n[s]); cudaFreeHost(e->h_pack_n[s]);
     }
-    cudaFree(e->d_pack_cum); cudaFree(e->d_pack_chunk); cudaFree(e->d_k8_flags);
+    cudaFree(e->d_pack_cum); cudaFree(e->d_pack_chunk); cudaFree(e->d_k8_flags); cudaFree(e->d_sum); cudaFree(e->d_k1_swept);
     for (auto &gr : e->groups) {
         for (int s = 0; s < 2; s++) { if (gr.ev_enc[s]) cudaEventDestroy(gr.ev_enc[s]); if (gr.ev_d2h[s]) cudaEventDestroy(gr.ev_d2h[s]); }
         if (gr.ev_join) cudaEventDestroy(gr.ev_join);
@@ -596,7 +610,15 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
     if (is_p) {
         {
             KScope k(e, st, 2);
-            if (b2_launch_me_fullpel(c.merange, &gr.tm_cur, &gr.tm_ref[gr.ref_idx], e->mbw, e->mbh, ns, e->d_prev_mv + om, e->lambda,
+            if (e->d_sum) {
+                // lossless pruning: block sums of this step's reference planes, then the search over the surviving candidates
+                if (b2_launch_block_sums(ref[0], e->pitch, e->rows, ns, e->d_sum + gr.slot0 * e->stride_y, st)) return -1;
+                if (b2_launch_me_fullpel_pruned(c.merange, &gr.tm_cur, &gr.tm_ref[gr.ref_idx], &gr.tm_sum, e->mbw, e->mbh, ns, e->d_prev_mv + om,
+                                                e->lambda, e->d_mvf + om, e->d_cost_full + om, e->d_k1_swept, st))
+                    return -1;
+                e->k1_all += b2_k1_lane_tasks(c.merange, e->mbw, e->mbh, ns);
+                e->launches++;                               // K1a
+            } else if (b2_launch_me_fullpel(c.merange, &gr.tm_cur, &gr.tm_ref[gr.ref_idx], e->mbw, e->mbh, ns, e->d_prev_mv + om, e->lambda,
                                      e->d_mvf + om, e->d_cost_full + om, e->d_mv9 ? e->d_mv9 + om * 9 : nullptr,
                                      e->d_cost9 ? e->d_cost9 + om * 9 : nullptr, st))
                 return -1;
@@ -930,3 +952,17 @@ extern "C" void b2_engine_profile_reset(b2_engine_t *e)
     for (int i = 0; i < B2_NKERNELS; i++) { e->k_ms[i] = 0; e->k_n[i] = 0; }
 }
 extern "C" long b2_engine_launch_count(const b2_engine_t *e) { return e->launches; }
+
+// cfg.me_prune: lane-tasks (mb, dy-group, dx) the pruned K1 launches ran and what exhaustive launches of the same steps run;
+// synchronises the device (a reporting call, not for the hot path).  Returns -1 when pruning is off.
+extern "C" int b2_engine_k1_stats(b2_engine_t *e, unsigned long long *swept, unsigned long long *all)
+{
+    if (!e || !e->d_k1_swept) return -1;
+    cudaSetDevice(e->cfg.device);
+    unsigned long long v = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, e->d_k1_swept, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (swept) *swept = v;
+    if (all) *all = (unsigned long long)e->k1_all;
+    return 0;
+}

@@ -45,9 +45,41 @@ int upload_padded(DevBuf &buf, const uint8_t *host, int w, int h, int n, int pad
 }
 }  // namespace
 
+struct PruneOut { unsigned long long *swept, *all; float *sums_ms; };      // non-NULL: run the pruned search (K1a + K1 over survivors)
 static int me_fullpel_impl(const uint8_t *cur_y, const uint8_t *ref_y, int w, int h, int nframes, int merange, const b2_mv_t *pmv,
                            int lambda, b2_mv_t *mv_out, uint32_t *cost_out, b2_mv_t *mv9_out, uint32_t *cost9_out, int iters,
-                           float *kernel_ms);
+                           float *kernel_ms, const PruneOut *prune = nullptr);
+
+extern "C" int b2k_me_fullpel_pruned(const uint8_t *cur_y, const uint8_t *ref_y, int w, int h, int nframes, int merange,
+                                     const b2_mv_t *pmv, int lambda, b2_mv_t *mv_out, uint32_t *cost_out, int iters, float *kernel_ms,
+                                     float *sums_ms, unsigned long long *swept_lane_tasks, unsigned long long *all_lane_tasks)
+{
+    unsigned long long sw = 0, al = 0;
+    float sm = 0;
+    const PruneOut po = {&sw, &al, &sm};
+    const int r = me_fullpel_impl(cur_y, ref_y, w, h, nframes, merange, pmv, lambda, mv_out, cost_out, nullptr, nullptr, iters, kernel_ms, &po);
+    if (swept_lane_tasks) *swept_lane_tasks = sw;
+    if (all_lane_tasks) *all_lane_tasks = al;
+    if (sums_ms) *sums_ms = sm;
+    return r;
+}
+
+// K1a alone: block sums of `nframes` w x h planes after padding by B2_PAD with replicated borders; out: [nframes][rows][pitch] u16
+extern "C" int b2k_block_sums(const uint8_t *y, int w, int h, int nframes, uint16_t *out, int *pitch_out, int *rows_out)
+{
+    DevBuf d_ref, d_sum;
+    int pitch, rows;
+    if (upload_padded(d_ref, y, w, h, nframes, B2_PAD, &pitch, &rows)) return -1;
+    if (pitch_out) *pitch_out = pitch;
+    if (rows_out) *rows_out = rows;
+    if (!out) return 0;
+    const size_t n = (size_t)pitch * rows * nframes;
+    if (d_sum.alloc(n * 2)) return -1;
+    B2_CUDA_OK(cudaMemset(d_sum.p, 0, n * 2));
+    if (b2_launch_block_sums((const uint8_t *)d_ref.p, pitch, rows, nframes, (uint16_t *)d_sum.p, 0)) return -1;
+    B2_CUDA_OK(cudaMemcpy(out, d_sum.p, n * 2, cudaMemcpyDeviceToHost));
+    return 0;
+}
 
 extern "C" int b2k_me_fullpel(const uint8_t *cur_y, const uint8_t *ref_y, int w, int h, int nframes, int merange,
                               const b2_mv_t *pmv, int lambda, b2_mv_t *mv_out, uint32_t *cost_out,
@@ -65,7 +97,7 @@ extern "C" int b2k_me_fullpel_parts(const uint8_t *cur_y, const uint8_t *ref_y, 
 
 static int me_fullpel_impl(const uint8_t *cur_y, const uint8_t *ref_y, int w, int h, int nframes, int merange, const b2_mv_t *pmv,
                            int lambda, b2_mv_t *mv_out, uint32_t *cost_out, b2_mv_t *mv9_out, uint32_t *cost9_out, int iters,
-                           float *kernel_ms)
+                           float *kernel_ms, const PruneOut *prune)
 {
     if ((w & 15) || (h & 15) || w <= 0 || h <= 0 || nframes <= 0) {
         fprintf(stderr, "b2enc: b2k_me_fullpel needs w,h multiples of 16\n");
@@ -85,21 +117,48 @@ static int me_fullpel_impl(const uint8_t *cur_y, const uint8_t *ref_y, int w, in
         if (d_pmv.alloc(nmb * sizeof(b2_mv_t))) return -1;
         B2_CUDA_OK(cudaMemcpy(d_pmv.p, pmv, nmb * sizeof(b2_mv_t), cudaMemcpyHostToDevice));
     }
-    CUtensorMap tm_cur, tm_ref;
+    CUtensorMap tm_cur, tm_ref, tm_sum;
     if (b2_make_plane_tmap(&tm_cur, d_cur.p, pitch, rows, nframes, 16 * b2_k1_strip_mbs(merange), 16)) return -1;
     if (b2_make_plane_tmap(&tm_ref, d_ref.p, pitch, rows, nframes, bw, bh)) return -1;
-    if (b2_launch_me_fullpel(merange, &tm_cur, &tm_ref, mbw, mbh, nframes, (const b2_mv_t *)d_pmv.p, lambda,
-                             (b2_mv_t *)d_mv.p, (uint32_t *)d_cost.p, (b2_mv_t *)d_mv9.p, (uint32_t *)d_cost9.p, 0))
-        return -1;
+    DevBuf d_sum, d_swept;
+    if (prune) {
+        if (mv9_out) return -1;
+        int sw, sh;
+        if (b2_k1_sum_box(merange, &sw, &sh)) return -1;
+        if (d_sum.alloc((size_t)pitch * rows * nframes * 2) || d_swept.alloc(8)) return -1;
+        B2_CUDA_OK(cudaMemset(d_sum.p, 0, (size_t)pitch * rows * nframes * 2));
+        B2_CUDA_OK(cudaMemset(d_swept.p, 0, 8));
+        if (b2_make_plane_tmap16(&tm_sum, d_sum.p, pitch, rows, nframes, sw, sh)) return -1;
+    }
+    auto launch = [&](bool with_sums, unsigned long long *swept) -> int {
+        if (!prune)
+            return b2_launch_me_fullpel(merange, &tm_cur, &tm_ref, mbw, mbh, nframes, (const b2_mv_t *)d_pmv.p, lambda,
+                                        (b2_mv_t *)d_mv.p, (uint32_t *)d_cost.p, (b2_mv_t *)d_mv9.p, (uint32_t *)d_cost9.p, 0);
+        if (with_sums && b2_launch_block_sums((const uint8_t *)d_ref.p, pitch, rows, nframes, (uint16_t *)d_sum.p, 0)) return -1;
+        return b2_launch_me_fullpel_pruned(merange, &tm_cur, &tm_ref, &tm_sum, mbw, mbh, nframes, (const b2_mv_t *)d_pmv.p, lambda,
+                                           (b2_mv_t *)d_mv.p, (uint32_t *)d_cost.p, swept, 0);
+    };
+    if (launch(true, (unsigned long long *)d_swept.p)) return -1;
     B2_CUDA_OK(cudaDeviceSynchronize());
+    if (prune) {
+        B2_CUDA_OK(cudaMemcpy(prune->swept, d_swept.p, 8, cudaMemcpyDeviceToHost));
+        *prune->all = (unsigned long long)b2_k1_lane_tasks(merange, mbw, mbh, nframes);
+    }
     if (kernel_ms) {
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         if (iters < 1) iters = 1;
+        if (prune) {                                           // K1a on its own: it runs once per reference frame
+            cudaEventRecord(e0, 0);
+            for (int i = 0; i < iters; i++) b2_launch_block_sums((const uint8_t *)d_ref.p, pitch, rows, nframes, (uint16_t *)d_sum.p, 0);
+            cudaEventRecord(e1, 0);
+            B2_CUDA_OK(cudaEventSynchronize(e1));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            *prune->sums_ms = ms / iters;
+        }
         cudaEventRecord(e0, 0);
-        for (int i = 0; i < iters; i++)
-            b2_launch_me_fullpel(merange, &tm_cur, &tm_ref, mbw, mbh, nframes, (const b2_mv_t *)d_pmv.p, lambda,
-                                 (b2_mv_t *)d_mv.p, (uint32_t *)d_cost.p, (b2_mv_t *)d_mv9.p, (uint32_t *)d_cost9.p, 0);
+        for (int i = 0; i < iters; i++) launch(false, nullptr);
         cudaEventRecord(e1, 0);
         B2_CUDA_OK(cudaEventSynchronize(e1));
         float ms = 0;

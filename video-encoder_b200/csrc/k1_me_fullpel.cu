@@ -517,6 +517,327 @@ k1_me_fullpel_persistent_kernel(const __grid_constant__ CUtensorMap tm_cur, cons
     }
 }
 
+// ---- lossless pruning: successive elimination in front of the same sweep (engine option me_prune) ---------------------------
+// |sum(cur MB) - sum(ref block)| <= SAD(cur MB, ref block) (triangle inequality), so a candidate whose
+//     |C - S(dx,dy)| + mvcost(dx,dy)  >  U,     U = exact cost of any candidate already evaluated,
+// cannot be the minimum and cannot tie with it either; dropping it leaves argmin AND tie-break of the exhaustive scan untouched
+// (x264's own "esa" search is built on the same inequality).  Per strip:
+//   1. TMA window + current tile, cost tables, expansion: as k1_me_fullpel_kernel;
+//   2. the raw window is dead after the expansion, so the 16x16 block sums of the reference at the strip's (NMB-1)*16 + 2R+1
+//      candidate columns x 2R+1 rows arrive by TMA into the same shared memory (K1a below computes them once per reference
+//      frame: u16 plane with the geometry of the padded luma plane);
+//   3. one warp per macroblock evaluates two candidates exactly -- the zero vector and the rounded predictor (the co-located
+//      vector of the previous frame) -- giving U and the first best key;
+//   4. every lane-task (mb, dy-group, dx) tests its K candidates against U (mvcost of the row replaced by the smallest of the
+//      group: weaker, still a lower bound); the survivors are compacted (ballot -> prefix over the mask words -> list);
+//   5. the unchanged register-tiled sweep runs over the survivor list only.
+// What is skipped is reported, never folded into the roofline figure: `swept` counts the lane-tasks that ran (b2_engine_k1_stats).
+constexpr int k1_cmax(int a, int b) { return a > b ? a : b; }
+template <int R> struct K1SeaSmem {
+    using S = K1Smem<R>;
+    static constexpr int NMB = S::NMB, ND = S::ND, NG = K1Cfg<R>::NG;
+    static constexpr int NX = (NMB - 1) * 16 + ND;               // candidate columns of a strip
+    static constexpr int SUM_PITCH = (NX + 7) & ~7;              // u16 per row of the sum window (TMA rows are multiples of 16 B)
+    static constexpr int SUM_BYTES = SUM_PITCH * ND * 2;
+    static constexpr int NTASK = NMB * NG * ND;
+    static constexpr int NWORD = (NTASK + 31) / 32;
+    // region 0: raw window while it is expanded, then the block-sum window, then the survivor list (u16 lane-task ids)
+    static constexpr int R0_BYTES = k1_cmax(k1_cmax(S::RAW_BYTES + 16, SUM_BYTES), NTASK * 2);
+    static constexpr int OFF_R0 = 0;
+    static constexpr int OFF_CUR = (R0_BYTES + 127) & ~127;
+    static constexpr int OFF_EXP = OFF_CUR + S::CUR_BYTES;
+    static constexpr int OFF_COSTX = OFF_EXP + S::EXP_BYTES;
+    static constexpr int OFF_COSTY = OFF_COSTX + NMB * ND * 4;
+    static constexpr int OFF_BEST = OFF_COSTY + NMB * ND * 4;
+    static constexpr int OFF_U = OFF_BEST + NMB * 4;
+    static constexpr int OFF_CSUM = OFF_U + NMB * 4;
+    static constexpr int OFF_MINCY = OFF_CSUM + NMB * 4;
+    static constexpr int OFF_MASK = OFF_MINCY + NMB * NG * 4;
+    static constexpr int OFF_PREF = OFF_MASK + NWORD * 4;        // NWORD exclusive prefixes + the survivor count
+    static constexpr int OFF_BAR = (OFF_PREF + (NWORD + 1) * 4 + 7) & ~7;
+    static constexpr int TOTAL = OFF_BAR + 16 + 128;             // +128: manual alignment slack
+};
+
+// three CTAs per SM, like the exhaustive kernel: 3 x (TOTAL + 1 KB reserved per CTA) <= 228 KB
+static_assert(B2_K1_MINCTAS != 3 || B2_K1_NMB != 6 || 3 * (K1SeaSmem<32>::TOTAL + 1024) <= 228 * 1024, "pruned K1 (+-32) no longer fits three CTAs per SM");
+static_assert(K1SeaSmem<32>::NTASK < 65536 && K1SeaSmem<16>::NTASK < 65536, "survivor list entries are u16");
+
+template <int R, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS, B2_K1_MINCTAS)
+k1_me_fullpel_sea_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_constant__ CUtensorMap tm_ref,
+                         const __grid_constant__ CUtensorMap tm_sum, int mbw, int mbh, const b2_mv_t *__restrict__ pmv, int lambda,
+                         b2_mv_t *__restrict__ mv_out, uint32_t *__restrict__ cost_out, unsigned long long *__restrict__ swept)
+{
+    using S = K1Smem<R>;
+    using Q = K1SeaSmem<R>;
+    constexpr int NWARPS = NTHREADS / 32;
+    constexpr int K = K1Cfg<R>::K, NG = K1Cfg<R>::NG, ND = S::ND, NMB = K1Cfg<R>::NMB;
+
+    extern __shared__ uint8_t smem_raw_[];
+    uint8_t *smem = smem_raw_ + ((128u - (smem_u32(smem_raw_) & 127u)) & 127u);
+    uint8_t *s_raw = smem + Q::OFF_R0;
+    const uint16_t *s_sum = (const uint16_t *)(smem + Q::OFF_R0);
+    uint16_t *s_list = (uint16_t *)(smem + Q::OFF_R0);
+    uint8_t *s_cur = smem + Q::OFF_CUR;
+    uint32_t *s_exp = (uint32_t *)(smem + Q::OFF_EXP);
+    uint32_t *s_costx = (uint32_t *)(smem + Q::OFF_COSTX);
+    uint32_t *s_costy = (uint32_t *)(smem + Q::OFF_COSTY);
+    uint32_t *s_best = (uint32_t *)(smem + Q::OFF_BEST);
+    int *s_u = (int *)(smem + Q::OFF_U);
+    int *s_csum = (int *)(smem + Q::OFF_CSUM);
+    int *s_mincy = (int *)(smem + Q::OFF_MINCY);
+    uint32_t *s_mask = (uint32_t *)(smem + Q::OFF_MASK);
+    uint32_t *s_pref = (uint32_t *)(smem + Q::OFF_PREF);
+    uint64_t *s_bar = (uint64_t *)(smem + Q::OFF_BAR);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mb0 = blockIdx.x * NMB, mby = blockIdx.y, frame = blockIdx.z;
+    const int nmb = min(NMB, mbw - mb0);
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&s_bar[0], S::RAW_BYTES + S::CUR_BYTES);
+        tma_load_3d(s_raw, &tm_ref, B2_PAD + mb0 * 16 - R, B2_PAD + mby * 16 - R, frame, &s_bar[0]);
+        tma_load_3d(s_cur, &tm_cur, B2_PAD + mb0 * 16, B2_PAD + mby * 16, frame, &s_bar[0]);
+    }
+
+    const size_t mb_base = ((size_t)frame * mbh + mby) * mbw + mb0;
+    for (int i = tid; i < NMB * ND; i += NTHREADS) {
+        int m = i / ND, d = i - m * ND;
+        int px = 0, py = 0;
+        if (pmv != nullptr && m < nmb) { b2_mv_t p = pmv[mb_base + m]; px = p.x; py = p.y; }
+        s_costx[i] = ((uint32_t)(lambda * b2_mvbits(4 * (d - R) - px)) << 13) + (uint32_t)d;
+        s_costy[i] = ((uint32_t)(lambda * b2_mvbits(4 * (d - R) - py)) << 13) + (uint32_t)(d * ND);
+    }
+
+    mbar_wait(&s_bar[0], 0);
+    {
+        constexpr int WPR = S::WIN_W / 4;
+        const uint32_t *raw32 = (const uint32_t *)s_raw;
+        for (int i = tid; i < WPR * S::WIN_H; i += NTHREADS) {
+            int r = i / WPR, j = i - r * WPR;
+            uint32_t lo = raw32[i], hi = raw32[i + 1];
+            uint4 o;
+            o.x = lo;
+            o.y = __funnelshift_r(lo, hi, 8);
+            o.z = __funnelshift_r(lo, hi, 16);
+            o.w = __funnelshift_r(lo, hi, 24);
+            *(uint4 *)(s_exp + r * S::EXP_PITCH + 4 * j) = o;
+        }
+    }
+    fence_proxy_async();                  // this thread's generic reads of the raw window precede the TMA write into the same bytes
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&s_bar[1], Q::SUM_BYTES);
+        tma_load_3d(s_raw, &tm_sum, B2_PAD + mb0 * 16 - R, B2_PAD + mby * 16 - R, frame, &s_bar[1]);
+    }
+
+    // thresholds while the sums are in flight: exact keys of the zero vector and of the rounded predictor
+    for (int m = warp; m < nmb; m += NWARPS) {
+        int px = 0, py = 0;
+        if (pmv != nullptr) { b2_mv_t p = pmv[mb_base + m]; px = p.x; py = p.y; }
+        const int cdx = min(max((px + 2) >> 2, -R), R) + R, cdy = min(max((py + 2) >> 2, -R), R) + R;
+        uint32_t sa = 0, sb = 0, cs = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int w = lane + 32 * h, y = w >> 2, c = w & 3;
+            const uint32_t cw = ((const uint32_t *)s_cur)[y * (NMB * 4) + m * 4 + c];
+            sa = vsad4_acc(s_exp[(R + y) * S::EXP_PITCH + m * 16 + R + 4 * c], cw, sa);
+            sb = vsad4_acc(s_exp[(cdy + y) * S::EXP_PITCH + m * 16 + cdx + 4 * c], cw, sb);
+            cs = __dp4a(cw, 0x01010101u, cs);
+        }
+        sa = __reduce_add_sync(0xffffffffu, sa);
+        sb = __reduce_add_sync(0xffffffffu, sb);
+        cs = __reduce_add_sync(0xffffffffu, cs);
+        if (lane == 0) {
+            const uint32_t ka = sa * 8192u + s_costx[m * ND + R] + s_costy[m * ND + R];
+            const uint32_t kb = sb * 8192u + s_costx[m * ND + cdx] + s_costy[m * ND + cdy];
+            const uint32_t kk = min(ka, kb);
+            s_best[m] = kk;
+            s_u[m] = (int)(kk >> 13);
+            s_csum[m] = (int)cs;
+        }
+    }
+    for (int i = tid; i < NMB * NG; i += NTHREADS) {
+        const int m = i / NG, g = i - m * NG;
+        uint32_t mn = 0xffffffffu;
+        for (int k = 0; k < K; k++) mn = min(mn, s_costy[m * ND + g * K + k] >> 13);
+        s_mincy[i] = (int)mn;
+    }
+    __syncthreads();
+    mbar_wait(&s_bar[1], 0);
+
+    // bound test: lane-task id = (round * NWARPS + warp) * 32 + lane, so one warp round fills exactly one mask word
+    const int total = nmb * NG * ND;
+    for (int id0 = warp * 32; id0 < total; id0 += NWARPS * 32) {
+        const int id = id0 + lane;
+        bool alive = false;
+        if (id < total) {
+            const int m = id / (NG * ND);
+            const int rem = id - m * (NG * ND);
+            const int g = rem / ND;
+            const int dxi = rem - g * ND;
+            const int t = s_u[m] - (int)(s_costx[m * ND + dxi] >> 13) - s_mincy[m * NG + g];
+            if (t >= 0) {
+                const uint16_t *sp = s_sum + (g * K) * Q::SUM_PITCH + m * 16 + dxi;
+                const int c = s_csum[m];
+#pragma unroll
+                for (int k = 0; k < K; k++) alive |= abs((int)sp[k * Q::SUM_PITCH] - c) <= t;
+            }
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) s_mask[id0 >> 5] = mask;
+    }
+    __syncthreads();                      // all reads of the sum window are done: region 0 becomes the survivor list
+    const int nword = (total + 31) >> 5;
+    if (warp == 0) {
+        uint32_t run = 0;
+        for (int base = 0; base < nword; base += 32) {
+            const int w = base + lane;
+            const uint32_t c = w < nword ? (uint32_t)__popc(s_mask[w]) : 0u;
+            uint32_t inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (w < nword) s_pref[w] = run + inc - c;
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) s_pref[Q::NWORD] = run;
+    }
+    __syncthreads();
+    const int count = (int)s_pref[Q::NWORD];
+    for (int id0 = warp * 32; id0 < total; id0 += NWARPS * 32) {
+        const uint32_t mask = s_mask[id0 >> 5];
+        if ((mask >> lane) & 1u) s_list[s_pref[id0 >> 5] + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)(id0 + lane);
+    }
+    __syncthreads();
+
+    for (int t0 = warp * 32; t0 < count; t0 += NWARPS * 32) {
+        const bool active = t0 + lane < count;
+        const int tt = s_list[active ? t0 + lane : t0];       // idle lanes shadow lane 0's task
+        const int m = tt / (NG * ND);
+        const int rem = tt - m * (NG * ND);
+        const int g = rem / ND;
+        const int dxi = rem - g * ND;
+
+        uint32_t cur[64];
+        {
+            const uint4 *c4 = (const uint4 *)(s_cur + m * 16);
+#pragma unroll
+            for (int y = 0; y < 16; y++) {
+                uint4 v = c4[y * (NMB * 16 / 16)];
+                cur[y * 4 + 0] = v.x; cur[y * 4 + 1] = v.y; cur[y * 4 + 2] = v.z; cur[y * 4 + 3] = v.w;
+            }
+        }
+        uint32_t acc[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = 0;
+        const uint32_t *wp = s_exp + (g * K) * S::EXP_PITCH + m * 16 + dxi;
+#pragma unroll
+        for (int r = 0; r < K + 15; r++) {
+            const uint32_t w0 = wp[r * S::EXP_PITCH + 0];
+            const uint32_t w1 = wp[r * S::EXP_PITCH + 4];
+            const uint32_t w2 = wp[r * S::EXP_PITCH + 8];
+            const uint32_t w3 = wp[r * S::EXP_PITCH + 12];
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const int y = r - k;
+                if (y >= 0 && y < 16) {
+                    acc[k] = vsad4_acc(w0, cur[y * 4 + 0], acc[k]);
+                    acc[k] = vsad4_acc(w1, cur[y * 4 + 1], acc[k]);
+                    acc[k] = vsad4_acc(w2, cur[y * 4 + 2], acc[k]);
+                    acc[k] = vsad4_acc(w3, cur[y * 4 + 3], acc[k]);
+                }
+            }
+        }
+        uint32_t key = 0xffffffffu;
+        if (active) {
+            const uint32_t kx = s_costx[m * ND + dxi];
+            const uint32_t *ky = s_costy + m * ND + g * K;
+#pragma unroll
+            for (int k = 0; k + 1 < K; k += 2) key = __vimin3_u32(key, acc[k] * 8192u + (kx + ky[k]), acc[k + 1] * 8192u + (kx + ky[k + 1]));
+            if (K & 1) key = min(key, acc[K - 1] * 8192u + (kx + ky[K - 1]));
+        }
+        const int m0 = __shfl_sync(0xffffffffu, m, 0);
+        if (__all_sync(0xffffffffu, m == m0)) {
+            const uint32_t wmin = __reduce_min_sync(0xffffffffu, key);
+            if (lane == 0) atomicMin(&s_best[m0], wmin);
+        } else if (active) {
+            atomicMin(&s_best[m], key);
+        }
+    }
+    __syncthreads();
+
+    if (tid < nmb) {
+        const uint32_t key = s_best[tid];
+        const int idx = (int)(key & 8191u);
+        const int dyi = idx / ND, dxi = idx - dyi * ND;
+        b2_mv_t mv;
+        mv.x = (int16_t)(dxi - R);
+        mv.y = (int16_t)(dyi - R);
+        mv_out[mb_base + tid] = mv;
+        cost_out[mb_base + tid] = key >> 13;
+    }
+    if (tid == 0 && swept != nullptr) atomicAdd(swept, (unsigned long long)count);
+}
+
+// K1a: 16x16 block sums of a padded luma plane, sum[Y][X] = sum of plane[Y..Y+15][X..X+15] (u16: at most 65,280), for every
+// position whose block lies inside the allocation; same [n][rows][pitch] geometry as the plane.  HBM-bound and tiny next to the
+// search (1 B read + 2 B written per pixel): one CTA per 128 x 32 tile, vertical 16-sums by a sliding column walk, then the
+// horizontal 16-sum as two levels of 4.
+constexpr int K1A_TW = 128, K1A_TH = 32;
+__global__ void __launch_bounds__(256) k1a_block_sums_kernel(const uint8_t *__restrict__ planes, int pitch, int rows, size_t plane_stride,
+                                                             uint16_t *__restrict__ sums)
+{
+    __shared__ uint32_t s_in[K1A_TH + 15][(K1A_TW + 16) / 4];
+    __shared__ uint16_t s_v[K1A_TH][K1A_TW + 16];
+    __shared__ uint16_t s_q[K1A_TH][K1A_TW + 16];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * K1A_TW, y0 = blockIdx.y * K1A_TH;
+    const uint8_t *plane = planes + (size_t)blockIdx.z * plane_stride;
+    uint16_t *out = sums + (size_t)blockIdx.z * plane_stride;           // same element stride: the sum plane mirrors the luma plane
+    constexpr int WPR = (K1A_TW + 16) / 4;
+    for (int i = tid; i < (K1A_TH + 15) * WPR; i += 256) {
+        const int r = i / WPR, w = i - r * WPR;
+        const int yy = min(y0 + r, rows - 1), xx = x0 + 4 * w;
+        s_in[r][w] = xx + 3 < pitch ? *(const uint32_t *)(plane + (size_t)yy * pitch + xx) : 0u;
+    }
+    __syncthreads();
+    if (tid < K1A_TW + 16) {
+        const uint8_t *col = (const uint8_t *)&s_in[0][0] + tid;
+        constexpr int P = WPR * 4;
+        int acc = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc += col[j * P];
+        s_v[0][tid] = (uint16_t)acc;
+        for (int y = 1; y < K1A_TH; y++) {
+            acc += col[(y + 15) * P] - col[(y - 1) * P];
+            s_v[y][tid] = (uint16_t)acc;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < K1A_TH * (K1A_TW + 12); i += 256) {
+        const int y = i / (K1A_TW + 12), x = i - y * (K1A_TW + 12);
+        s_q[y][x] = (uint16_t)(s_v[y][x] + s_v[y][x + 1] + s_v[y][x + 2] + s_v[y][x + 3]);
+    }
+    __syncthreads();
+    for (int i = tid; i < K1A_TH * K1A_TW; i += 256) {
+        const int y = i / K1A_TW, x = i - y * K1A_TW;
+        const int Y = y0 + y, X = x0 + x;
+        if (Y < rows && X < pitch) {
+            const bool valid = Y + 16 <= rows && X + 16 <= pitch;
+            out[(size_t)Y * pitch + X] = valid ? (uint16_t)(s_q[y][x] + s_q[y][x + 4] + s_q[y][x + 8] + s_q[y][x + 12]) : (uint16_t)0;
+        }
+    }
+}
+
 #ifndef B2_K1P_WARPS
 #define B2_K1P_WARPS 16      // 16 consumer warps (92 registers, no spills) + 4 producer warps; 20 consumers fit only at 80 registers
 #endif
@@ -581,6 +902,24 @@ int launch_k1(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, int mbw, int
     return launch_k1p<R, NT, false>(tm_cur, tm_ref, mbw, mbh, nframes, pmv, lambda, mv_out, cost_out, nullptr, nullptr, st);
 }
 
+template <int R, int NT>
+int launch_k1_sea(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, const CUtensorMap &tm_sum, int mbw, int mbh, int nframes,
+                  const b2_mv_t *pmv, int lambda, b2_mv_t *mv_out, uint32_t *cost_out, unsigned long long *swept, cudaStream_t st)
+{
+    static std::atomic<bool> attr_set[64];
+    int dev = 0;
+    B2_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
+        B2_CUDA_OK(cudaFuncSetAttribute(k1_me_fullpel_sea_kernel<R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1SeaSmem<R>::TOTAL));
+        if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
+    }
+    constexpr int NMB = K1Cfg<R>::NMB;
+    dim3 grid((mbw + NMB - 1) / NMB, mbh, nframes);
+    k1_me_fullpel_sea_kernel<R, NT><<<grid, NT, K1SeaSmem<R>::TOTAL, st>>>(tm_cur, tm_ref, tm_sum, mbw, mbh, pmv, lambda, mv_out, cost_out, swept);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 // threads per CTA: 82 (R=32) / 41 (R=16) warp-tasks per full strip should divide evenly over the warps
 int k1_threads()
 {
@@ -622,6 +961,50 @@ int b2_launch_me_fullpel(int R, const CUtensorMap *tm_cur, const CUtensorMap *tm
     switch (R) {
     case 32: K1_DISPATCH(32)
     case 16: K1_DISPATCH(16)
+    default:
+        fprintf(stderr, "b2enc: merange %d not supported (16 or 32)\n", R);
+        return -1;
+    }
+}
+
+// ---- pruned search (me_prune): block sums of the reference (K1a), then K1 with successive elimination ------------------------
+// box of the block-sum window a strip fetches: {((NMB-1)*16 + 2R+1 rounded up to 8) u16, 2R+1 rows, 1}
+extern "C" int b2_k1_sum_box(int R, int *bw, int *bh)
+{
+    if (R == 32) { *bw = K1SeaSmem<32>::SUM_PITCH; *bh = K1SeaSmem<32>::ND; return 0; }
+    if (R == 16) { *bw = K1SeaSmem<16>::SUM_PITCH; *bh = K1SeaSmem<16>::ND; return 0; }
+    return -1;
+}
+
+int b2_launch_block_sums(const uint8_t *d_planes, int pitch, int rows, int nplanes, uint16_t *d_sums, cudaStream_t st)
+{
+    dim3 grid((pitch + K1A_TW - 1) / K1A_TW, (rows + K1A_TH - 1) / K1A_TH, nplanes);
+    k1a_block_sums_kernel<<<grid, 256, 0, st>>>(d_planes, pitch, rows, (size_t)pitch * rows, d_sums);
+    B2_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// lane-tasks (mb, dy-group, dx) of an exhaustive launch: what `swept` is compared with
+extern "C" long long b2_k1_lane_tasks(int R, int mbw, int mbh, int nframes)
+{
+    const long long per_mb = R == 16 ? (long long)K1Cfg<16>::NG * (2 * 16 + 1) : (long long)K1Cfg<32>::NG * (2 * 32 + 1);
+    return per_mb * mbw * mbh * nframes;
+}
+
+int b2_launch_me_fullpel_pruned(int R, const CUtensorMap *tm_cur, const CUtensorMap *tm_ref, const CUtensorMap *tm_sum, int mbw, int mbh,
+                                int nframes, const b2_mv_t *d_pmv, int lambda, b2_mv_t *d_mv, uint32_t *d_cost,
+                                unsigned long long *d_swept, cudaStream_t st)
+{
+#define K1S_DISPATCH(RR)                                                                                                          \
+    switch (k1_threads()) {                                                                                                       \
+    case 192: return launch_k1_sea<RR, 192>(*tm_cur, *tm_ref, *tm_sum, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, d_swept, st); \
+    case 320: return launch_k1_sea<RR, 320>(*tm_cur, *tm_ref, *tm_sum, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, d_swept, st); \
+    case 384: return launch_k1_sea<RR, 384>(*tm_cur, *tm_ref, *tm_sum, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, d_swept, st); \
+    default: return launch_k1_sea<RR, 256>(*tm_cur, *tm_ref, *tm_sum, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, d_swept, st);  \
+    }
+    switch (R) {
+    case 32: K1S_DISPATCH(32)
+    case 16: K1S_DISPATCH(16)
     default:
         fprintf(stderr, "b2enc: merange %d not supported (16 or 32)\n", R);
         return -1;

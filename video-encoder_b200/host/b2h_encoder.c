@@ -195,7 +195,7 @@ int b2_param_default_preset(b2_param_t *p, const char *preset, const char *tune)
     p->rc.i_rc_method = B2_RC_CRF; p->rc.f_rf_constant = 23.0f; p->rc.i_qp_constant = 26;
     p->b_annexb = 1;
     /* 16 closed GOPs in flight per GPU: fewer leave the GPU waiting on the per-frame latency chain (K7 / K8) */
-    p->i_keyint_max = 32; p->i_gop_slots = 16; p->i_device = 0; p->i_devices = 0; p->i_csp_in = B2_FMT_YUV420P;
+    p->i_keyint_max = 32; p->i_gop_slots = 16; p->i_device = 0; p->i_devices = 0; p->b_me_prune = 1; p->i_csp_in = B2_FMT_YUV420P;
     p->b_deblocking_filter = 1;
     p->b_cabac = 1;                      /* x264 default at every preset but ultrafast */
     p->b_transform_8x8 = 0;
@@ -294,10 +294,14 @@ b2_t *b2_encoder_open(b2_param_t *p)
     cfg.transform8x8 = p->b_transform_8x8 != 0;
     cfg.partitions = p->b_partitions < 0 ? 0 : (p->b_partitions > 2 ? 2 : p->b_partitions);
     cfg.pack_levels = 1;                              /* only blocks with a non-zero level cross PCIe (K9) */
+    {
+        const char *ev = getenv("B2ENC_ME_PRUNE");
+        cfg.me_prune = ev ? atoi(ev) != 0 : p->b_me_prune != 0;
+    }
     /* every GOP slot holds its GOP's raw pictures on the device: shrink the slot count to what the GPU can hold */
     {
         const size_t w16 = ((size_t)p->i_width + 15) & ~(size_t)15, h16 = ((size_t)p->i_height + 15) & ~(size_t)15;
-        const size_t per_slot = (size_t)h->L * w16 * h16 * 3 + 16 * (w16 + 128) * (h16 + 128);      /* ring (<= 3 B/px) + planes + results */
+        const size_t per_slot = (size_t)h->L * w16 * h16 * 3 + 18 * (w16 + 128) * (h16 + 128);      /* ring (<= 3 B/px) + planes, block sums + results */
         size_t free_b = 0, total_b = 0;
         for (int d = 0; d < h->N && h->S > 1; d++) {
             if (b2_device_mem_info(p->i_device + d, &free_b, &total_b)) continue;
