@@ -462,13 +462,15 @@ def main():
             pruned = {"value": round(SLOTS * args.steps / (msp * 1e-3), 2), "unit": UNIT, "ms_per_step": round(msp / args.steps, 4),
                       "e2e": round(SLOTS * args.steps / e2ep, 2),
                       "verified": vp["verified"] if vp else None, "verify_seconds": vp["seconds"] if vp else None,
-                      "k1_lane_tasks_executed": int(sw1 - sw0), "k1_lane_tasks_algorithmic": int(al1 - al0),
+                      "k1_candidates_evaluated": int(sw1 - sw0), "k1_candidates_algorithmic": int(al1 - al0),
                       "k1_executed_fraction": round((sw1 - sw0) / max(al1 - al0, 1), 4),
+                      "k1_rows_per_lane_task": b2enc.k1_prune_rows(MERANGE),
                       "k1_ms_per_step_alone": round(isop["K1 full-pel SAD"][0] / 8, 4),
                       "k1_ms_per_step_alone_exhaustive": round(iso["K1 full-pel SAD"][0] / 8, 4),
-                      "what": "engine option me_prune=1: K1a (16x16 block sums of the reference, once per P step) + successive elimination in K1 -- a "
-                              "candidate whose |sum(cur) - sum(ref)| + mvcost exceeds the exact cost of the zero vector / the rounded predictor cannot be "
-                              "the minimum; vectors, costs and tie-break are those of the exhaustive scan (tests/test_me_fullpel.py, the oracle "
+                      "what": "engine option me_prune=1: K1a (min | max of the reference's 16x16 block sums over the rows of a lane-task, once per P step) + "
+                              "successive elimination in K1 -- a candidate whose |sum(cur) - sum(ref)| + mvcost exceeds the exact cost of the zero vector / "
+                              "the rounded predictor cannot be the minimum, and a lane-task (k1_rows_per_lane_task consecutive dy at one dx) is skipped when "
+                              "that holds for all of its candidates; vectors, costs and tie-break are those of the exhaustive scan (tests/test_me_fullpel.py, the oracle "
                               "replay above), only the time changes, and it depends on the content (this synthetic sequence pans uniformly, so the "
                               "predictor is exact; k1_executed_fraction says how much of the exhaustive work ran).  Not part of `value`, `e2e` or "
                               "`roofline`: those are the exhaustive search"}

@@ -128,8 +128,8 @@ enum { B2_NKERNELS = 10 };
 int b2_engine_kernel_ms(b2_engine_t *e, int which, double *ms_total, long *launches);
 void b2_engine_profile_reset(b2_engine_t *e);
 long b2_engine_launch_count(const b2_engine_t *e);              /* kernels launched since creation */
-/* cfg.me_prune: lane-tasks (macroblock, dy-group, dx) the pruned search ran since creation and what the exhaustive search runs for
- * the same steps (executed vs algorithmic work).  Synchronises the device.  -1 when pruning is off. */
+/* cfg.me_prune: candidate vectors the pruned search evaluated since creation and what the exhaustive search evaluates for the
+ * same steps (executed vs algorithmic work).  Synchronises the device.  -1 when pruning is off. */
 int b2_engine_k1_stats(b2_engine_t *e, unsigned long long *swept, unsigned long long *all);
 
 #ifdef __cplusplus

@@ -34,16 +34,19 @@ int b2k_me_fullpel(const uint8_t *cur_y, const uint8_t *ref_y, int w, int h, int
                    const b2_mv_t *pmv, int lambda, b2_mv_t *mv_out, uint32_t *cost_out,
                    int iters, float *kernel_ms);
 
-/* K1 with lossless pruning (successive elimination: K1a block sums of the reference, then the same sweep over the candidates
- * whose lower bound |sum(cur) - sum(ref)| + mvcost does not exceed an exactly evaluated cost).  Results are identical to
- * b2k_me_fullpel's by construction; swept / all = lane-tasks (mb, dy-group, dx) that ran / that the exhaustive kernel runs.
- * kernel_ms: K1 alone; sums_ms: K1a alone. */
+/* K1 with lossless pruning (successive elimination: K1a block sums of the reference, then the same sweep over the lane-tasks
+ * -- KS consecutive dy at one dx -- whose lower bound dist(sum(cur), [min, max of the block sums]) + mvcost does not exceed an
+ * exactly evaluated cost).  Results are identical to b2k_me_fullpel's by construction; swept / all = candidate vectors that were
+ * evaluated / that the exhaustive kernel evaluates.  kernel_ms: K1 alone; sums_ms: K1a alone. */
 int b2k_me_fullpel_pruned(const uint8_t *cur_y, const uint8_t *ref_y, int w, int h, int nframes, int merange,
                           const b2_mv_t *pmv, int lambda, b2_mv_t *mv_out, uint32_t *cost_out, int iters, float *kernel_ms,
-                          float *sums_ms, unsigned long long *swept_lane_tasks, unsigned long long *all_lane_tasks);
-/* K1a alone: 16x16 block sums of the padded (B2_PAD, replicated border) planes; out [nframes][rows][pitch] u16 (may be NULL to
- * query the geometry), position (Y,X) = sum of padded[Y..Y+15][X..X+15], 0 where the block leaves the allocation */
-int b2k_block_sums(const uint8_t *y, int w, int h, int nframes, uint16_t *out, int *pitch_out, int *rows_out);
+                          float *sums_ms, unsigned long long *swept_candidates, unsigned long long *all_candidates);
+/* K1a alone on the padded (B2_PAD, replicated border) planes; out [nframes][rows][pitch] u32 (may be NULL to query the geometry):
+ * position (Y,X) = min | max << 16 over rows Y..Y+ks-1 of S[.][X], S[Y][X] = sum of padded[Y..Y+15][X..X+15]; 0 | 0xffff where a
+ * block leaves the allocation.  ks in {1, 3, 5, 11, 13} */
+int b2k_block_sums(const uint8_t *y, int w, int h, int nframes, int ks, uint32_t *out, int *pitch_out, int *rows_out);
+/* rows per lane-task of the pruned search for +-merange (environment B2_K1_PRUNE_ROWS=coarse|fine) */
+int b2_k1_prune_rows(int merange);
 
 /* K1, partition variant (row N1, partitions = 2): best full-pel vector and cost of each of the nine shape parts per MB
  * (16x16 | 16x8 top,bottom | 8x16 left,right | four 8x8), outputs [nframes][mbs][9] */

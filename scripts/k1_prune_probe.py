@@ -1,9 +1,16 @@
 """K1 exhaustive vs pruned (K1a block sums + successive elimination), kernel alone: the bench's synthetic sequence (uniform pan,
 predictor = the previous frame's vector = exact) and a smooth 'natural-like' field with a differently moving object and a
 predictor that is right only for the background; +-32 at 1080p, +-16 at 720p; 16 frames per launch.  Results are compared."""
-import os, sys, json
+import os, sys, json, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "video-encoder_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+if len(sys.argv) < 2 or sys.argv[1] != "child":
+    # the lane-task depth and the CTA size are read once per process: one child per variant
+    for rows_, nt in (("coarse", "256"), ("fine", "256")):
+        env = dict(os.environ, B2_K1_PRUNE_ROWS=rows_, B2_K1_THREADS=nt)
+        print("== B2_K1_PRUNE_ROWS=%s B2_K1_THREADS=%s" % (rows_, nt), flush=True)
+        subprocess.run([sys.executable, os.path.abspath(__file__), "child"], env=env)
+    sys.exit(0)
 import numpy as np, b2enc, b2oracle
 import scipy.ndimage as ndi
 
@@ -37,7 +44,7 @@ for (w, h, R, n) in ((1920, 1088, 32, 16), (1280, 720, 16, 16)):
         mv_b, cost_b, st = b2enc.me_fullpel_pruned(cur, ref, R, pmv, 5, iters=10)
         same = bool(np.array_equal(mv_a, mv_b) and np.array_equal(cost_a, cost_b))
         work = n * nmb * (2 * R + 1) ** 2 * 256
-        print(json.dumps({"case": "%dx%d +-%d %s" % (w, h, R, name), "identical": same, "exhaustive_ms": round(ms_a, 4),
+        print(json.dumps({"case": "%dx%d +-%d %s" % (w, h, R, name), "rows_per_lane_task": b2enc.k1_prune_rows(R), "identical": same, "exhaustive_ms": round(ms_a, 4),
                           "exhaustive_frac_of_peak": round(work / (ms_a * 1e-3) / (peak * 4), 4),
                           "pruned_ms": round(st["kernel_ms"], 4), "block_sums_ms": round(st["sums_ms"], 4),
                           "speedup_incl_sums": round(ms_a / (st["kernel_ms"] + st["sums_ms"]), 3),

@@ -5,8 +5,9 @@ sys.path.insert(0, os.path.join(ROOT, "video-encoder_b200")); sys.path.insert(0,
 import numpy as np, b2enc, b2oracle
 w, h, S = 1920, 1080, 4
 FULL = int(os.environ.get("B2_ALL_FEATURES", "0"))      # 1: deblocking + 8x8 transform / intra 8x8 + partitions (rows N1, N2)
+PRUNE = int(os.environ.get("B2_ME_PRUNE", "0"))         # 1: the pruned full-pel search (K1a + k1_me_fullpel_sea_kernel)
 eng = b2enc.Engine(w, h, slots=S, ring=3, merange=32, qp=26, subpel=1, intra_in_p=1, streams=1, pack_levels=1,
-                   deblock=FULL, transform8x8=FULL, partitions=FULL)
+                   deblock=FULL, transform8x8=FULL, partitions=FULL, me_prune=PRUNE)
 for s in range(S):
     for r in range(3):
         y, u, v = b2oracle.synth_frame(w, h, r, s)

@@ -69,7 +69,7 @@ def me_fullpel(cur_y, ref_y, merange, pmv=None, lam=0, iters=0):
 
 def me_fullpel_pruned(cur_y, ref_y, merange, pmv=None, lam=0, iters=0):
     """K1 with lossless pruning (K1a block sums + successive elimination).  Returns (mv, cost, stats) with stats =
-    {"kernel_ms", "sums_ms" (None without iters), "swept", "all"}: lane-tasks that ran / that the exhaustive kernel runs."""
+    {"kernel_ms", "sums_ms" (None without iters), "swept", "all"}: candidate vectors evaluated / of the exhaustive search."""
     require_gpu()
     cur_y = np.ascontiguousarray(cur_y, np.uint8); ref_y = np.ascontiguousarray(ref_y, np.uint8)
     if cur_y.ndim == 2:
@@ -91,8 +91,9 @@ def me_fullpel_pruned(cur_y, ref_y, merange, pmv=None, lam=0, iters=0):
                       "swept": swept.value, "all": every.value}
 
 
-def block_sums(y):
-    """K1a alone: y uint8 [n,h,w] -> u16 [n,rows,pitch] block sums of the padded planes (see b2k_block_sums)"""
+def block_sums(y, ks=1):
+    """K1a alone: y uint8 [n,h,w] -> (min, max) u16 arrays [n,rows,pitch] over `ks` rows of the 16x16 block sums of the padded planes
+    (see b2k_block_sums); ks=1: both are the plain block sums"""
     require_gpu()
     y = np.ascontiguousarray(y, np.uint8)
     if y.ndim == 2:
@@ -100,13 +101,17 @@ def block_sums(y):
     n, h, w = y.shape
     pitch = C.c_int(0); rows = C.c_int(0)
     L = lib()
-    L.b2k_block_sums.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-    if L.b2k_block_sums(_p(y), w, h, n, None, C.addressof(pitch), C.addressof(rows)) != 0:
+    L.b2k_block_sums.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    if L.b2k_block_sums(_p(y), w, h, n, ks, None, C.addressof(pitch), C.addressof(rows)) != 0:
         raise RuntimeError("b2k_block_sums failed")
-    out = np.zeros((n, rows.value, pitch.value), np.uint16)
-    if L.b2k_block_sums(_p(y), w, h, n, _p(out), None, None) != 0:
+    out = np.zeros((n, rows.value, pitch.value), np.uint32)
+    if L.b2k_block_sums(_p(y), w, h, n, ks, _p(out), None, None) != 0:
         raise RuntimeError("b2k_block_sums failed")
-    return out
+    return (out & 0xffff).astype(np.uint16), (out >> 16).astype(np.uint16)
+
+
+def k1_prune_rows(merange):
+    return lib().b2_k1_prune_rows(merange)
 
 
 def me_fullpel_parts(cur_y, ref_y, merange, pmv=None, lam=0, iters=0):
@@ -279,7 +284,7 @@ class Engine:
         self.result_bytes = L.b2_engine_result_bytes(self.h)
 
     def k1_stats(self):
-        """me_prune: (lane-tasks the pruned search ran, lane-tasks of the exhaustive search) since creation; None when pruning is off"""
+        """me_prune: (candidate vectors the pruned search evaluated, candidates of the exhaustive search) since creation; None when off"""
         a = C.c_ulonglong(0); b = C.c_ulonglong(0)
         if self.L.b2_engine_k1_stats(self.h, C.addressof(a), C.addressof(b)) != 0:
             return None

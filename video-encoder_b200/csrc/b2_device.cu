@@ -44,21 +44,20 @@ int b2_make_plane_tmap(CUtensorMap *tm, const void *base, int pitch, int rows, i
     return 0;
 }
 
-// u16 plane stack with the geometry of a luma plane stack (the block sums K1 prunes with); box in elements
-int b2_make_plane_tmap16(CUtensorMap *tm, const void *base, int pitch, int rows, int nplanes, int bw, int bh)
+// u32 plane stack with the geometry of a luma plane stack (the min | max block sums K1 prunes with); box {bw, 1, 1} words
+int b2_make_plane_tmap32(CUtensorMap *tm, const void *base, int pitch, int rows, int nplanes, int bw)
 {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return -1;
     cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)nplanes};
-    cuuint64_t strides[2] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * rows * 2};
-    cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * rows * 4};
+    cuuint32_t box[3] = {(cuuint32_t)bw, 1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, (void *)base, dims, strides, box, estr,
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void *)base, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        fprintf(stderr, "b2enc: cuTensorMapEncodeTiled (u16) failed (%d) pitch=%d rows=%d n=%d box=%dx%d\n", (int)r, pitch,
-                rows, nplanes, bw, bh);
+        fprintf(stderr, "b2enc: cuTensorMapEncodeTiled (u32) failed (%d) pitch=%d rows=%d n=%d box=%d\n", (int)r, pitch, rows, nplanes, bw);
         return -1;
     }
     return 0;

@@ -49,7 +49,8 @@ static int test_fault()
 struct Group {
     int slot0 = 0, n = 0;
     cudaStream_t st = nullptr;
-    CUtensorMap tm_cur, tm_ref[2], tm_sum;
+    CUtensorMap tm_cur, tm_ref[2];
+    CUtensorMap tm_sum, tm_cur_p, tm_ref_p[2];         // cfg.me_prune: (min | max) block-sum words; cur / window boxes of the pruned search's strips
     int ref_idx = 0;                       // d_rec[ref_idx] holds this group's latest reconstruction
     int res_set = 0, host_set = 0;
     int last_n = 0;                        // slots covered by the most recent encode
@@ -86,8 +87,8 @@ struct b2_engine {
     uint32_t *d_pack_n[2] = {}, *h_pack_n[2] = {};
     unsigned long long *d_pack_cum = nullptr;
     uint32_t *d_pack_chunk = nullptr;              // K9a scratch: present blocks per chunk of macroblocks, [S][chunks]
-    uint16_t *d_sum = nullptr;             // cfg.me_prune: [S][rows][pitch] 16x16 block sums of the reference planes (K1a), refilled per P step
-    unsigned long long *d_k1_swept = nullptr;      // cfg.me_prune: lane-tasks the pruned K1 launches ran, accumulated on the device
+    uint32_t *d_sum = nullptr;             // cfg.me_prune: [S][rows][pitch] min | max of the reference planes' block sums (K1a), refilled per P step
+    unsigned long long *d_k1_swept = nullptr;      // cfg.me_prune: candidates the pruned K1 launches evaluated, accumulated on the device
     long long k1_all = 0;                          //               ... and what the exhaustive kernel would have run
     int *d_k8_flags = nullptr;                     // K8 row pipeline: cross-CTA progress flags [S][8]
     size_t pack_stride = 0;
@@ -196,8 +197,8 @@ static int engine_alloc(b2_engine *e)
         }
     }
     if (c.me_prune && c.partitions != 2) {                        // the wide partition search keeps the exhaustive kernel (nine minima per MB)
-        ENG_OK(cudaMalloc(&e->d_sum, e->stride_y * S * sizeof(uint16_t)));
-        ENG_OK(cudaMemset(e->d_sum, 0, e->stride_y * S * sizeof(uint16_t)));
+        ENG_OK(cudaMalloc(&e->d_sum, e->stride_y * S * sizeof(uint32_t)));
+        ENG_OK(cudaMemset(e->d_sum, 0, e->stride_y * S * sizeof(uint32_t)));
         ENG_OK(cudaMalloc(&e->d_k1_swept, sizeof(unsigned long long)));
         ENG_OK(cudaMemset(e->d_k1_swept, 0, sizeof(unsigned long long)));
     }
@@ -255,9 +256,11 @@ static int engine_alloc(b2_engine *e)
         if (b2_make_plane_tmap(&gr.tm_ref[0], e->d_rec[0][0] + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, bw, bh)) return -1;
         if (b2_make_plane_tmap(&gr.tm_ref[1], e->d_rec[1][0] + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, bw, bh)) return -1;
         if (e->d_sum) {
-            int sw, sh;
-            if (b2_k1_sum_box(c.merange, &sw, &sh)) return -1;
-            if (b2_make_plane_tmap16(&gr.tm_sum, e->d_sum + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, sw, sh)) return -1;
+            if (b2_make_plane_tmap32(&gr.tm_sum, e->d_sum + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, b2_k1_mm_box(c.merange))) return -1;
+            const int pw = 16 * b2_k1_prune_strip_mbs(c.merange);
+            if (b2_make_plane_tmap(&gr.tm_cur_p, e->d_cur[0] + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, pw, 16)) return -1;
+            for (int r = 0; r < 2; r++)
+                if (b2_make_plane_tmap(&gr.tm_ref_p[r], e->d_rec[r][0] + gr.slot0 * e->stride_y, e->pitch, e->rows, gr.n, pw + 2 * c.merange, bh)) return -1;
         }
     }
     return 0;
@@ -612,11 +615,11 @@ static int encode_group(b2_engine *e, Group &gr, int frame_type, int ns, int rin
             KScope k(e, st, 2);
             if (e->d_sum) {
                 // lossless pruning: block sums of this step's reference planes, then the search over the surviving candidates
-                if (b2_launch_block_sums(ref[0], e->pitch, e->rows, ns, e->d_sum + gr.slot0 * e->stride_y, st)) return -1;
-                if (b2_launch_me_fullpel_pruned(c.merange, &gr.tm_cur, &gr.tm_ref[gr.ref_idx], &gr.tm_sum, e->mbw, e->mbh, ns, e->d_prev_mv + om,
+                if (b2_launch_block_sums(b2_k1_prune_rows(c.merange), ref[0], e->pitch, e->rows, ns, e->d_sum + gr.slot0 * e->stride_y, st)) return -1;
+                if (b2_launch_me_fullpel_pruned(c.merange, &gr.tm_cur_p, &gr.tm_ref_p[gr.ref_idx], &gr.tm_sum, e->mbw, e->mbh, ns, e->d_prev_mv + om,
                                                 e->lambda, e->d_mvf + om, e->d_cost_full + om, e->d_k1_swept, st))
                     return -1;
-                e->k1_all += b2_k1_lane_tasks(c.merange, e->mbw, e->mbh, ns);
+                e->k1_all += b2_k1_candidates(c.merange, e->mbw, e->mbh, ns);
                 e->launches++;                               // K1a
             } else if (b2_launch_me_fullpel(c.merange, &gr.tm_cur, &gr.tm_ref[gr.ref_idx], e->mbw, e->mbh, ns, e->d_prev_mv + om, e->lambda,
                                      e->d_mvf + om, e->d_cost_full + om, e->d_mv9 ? e->d_mv9 + om * 9 : nullptr,
@@ -953,7 +956,7 @@ extern "C" void b2_engine_profile_reset(b2_engine_t *e)
 }
 extern "C" long b2_engine_launch_count(const b2_engine_t *e) { return e->launches; }
 
-// cfg.me_prune: lane-tasks (mb, dy-group, dx) the pruned K1 launches ran and what exhaustive launches of the same steps run;
+// cfg.me_prune: candidate vectors the pruned K1 launches evaluated and what exhaustive launches of the same steps evaluate;
 // synchronises the device (a reporting call, not for the hot path).  Returns -1 when pruning is off.
 extern "C" int b2_engine_k1_stats(b2_engine_t *e, unsigned long long *swept, unsigned long long *all)
 {

@@ -17,15 +17,18 @@ int b2_launch_me_fullpel(int R, const CUtensorMap *tm_cur, const CUtensorMap *tm
                          int nframes, const b2_mv_t *d_pmv, int lambda, b2_mv_t *d_mv, uint32_t *d_cost,
                          b2_mv_t *d_mv9 /* NULL, or [nmb][9] best vector of every shape part */, uint32_t *d_cost9, cudaStream_t st);
 
-// pruned search (successive elimination, lossless): K1a block sums of the reference planes, then K1 over the survivors only
-int b2_make_plane_tmap16(CUtensorMap *tm, const void *base, int pitch, int rows, int nplanes, int bw, int bh);
-extern "C" int b2_k1_sum_box(int R, int *bw, int *bh);
-extern "C" long long b2_k1_lane_tasks(int R, int mbw, int mbh, int nframes);
-int b2_launch_block_sums(const uint8_t *d_planes, int pitch, int rows, int nplanes, uint16_t *d_sums /* [nplanes][rows][pitch] */,
+// pruned search (successive elimination, lossless): K1a = min | max over `ks` rows of the 16x16 block sums of the reference planes
+// (one u32 per position), then K1 over the surviving lane-tasks only
+int b2_make_plane_tmap32(CUtensorMap *tm, const void *base, int pitch, int rows, int nplanes, int bw);   // u32 planes, box {bw, 1, 1}
+extern "C" int b2_k1_prune_rows(int R);
+extern "C" int b2_k1_mm_box(int R);
+extern "C" int b2_k1_prune_strip_mbs(int R);              // strip width of the pruned search (its own cur / window boxes)
+extern "C" long long b2_k1_candidates(int R, int mbw, int mbh, int nframes);
+int b2_launch_block_sums(int ks, const uint8_t *d_planes, int pitch, int rows, int nplanes, uint32_t *d_mm /* [nplanes][rows][pitch] */,
                          cudaStream_t st);
-int b2_launch_me_fullpel_pruned(int R, const CUtensorMap *tm_cur, const CUtensorMap *tm_ref, const CUtensorMap *tm_sum, int mbw, int mbh,
+int b2_launch_me_fullpel_pruned(int R, const CUtensorMap *tm_cur, const CUtensorMap *tm_ref, const CUtensorMap *tm_mm, int mbw, int mbh,
                                 int nframes, const b2_mv_t *d_pmv, int lambda, b2_mv_t *d_mv, uint32_t *d_cost,
-                                unsigned long long *d_swept /* NULL, or += lane-tasks swept */, cudaStream_t st);
+                                unsigned long long *d_swept /* NULL, or += candidates evaluated */, cudaStream_t st);
 
 int b2_launch_convert(int fmt, const uint8_t *d_in, size_t in_stride, uint8_t *d_y, uint8_t *d_u, uint8_t *d_v, int pitch,
                       int pitchc, size_t stride_y, size_t stride_c, int w, int h, int nframes, cudaStream_t st);

@@ -52,32 +52,33 @@ static int me_fullpel_impl(const uint8_t *cur_y, const uint8_t *ref_y, int w, in
 
 extern "C" int b2k_me_fullpel_pruned(const uint8_t *cur_y, const uint8_t *ref_y, int w, int h, int nframes, int merange,
                                      const b2_mv_t *pmv, int lambda, b2_mv_t *mv_out, uint32_t *cost_out, int iters, float *kernel_ms,
-                                     float *sums_ms, unsigned long long *swept_lane_tasks, unsigned long long *all_lane_tasks)
+                                     float *sums_ms, unsigned long long *swept_candidates, unsigned long long *all_candidates)
 {
     unsigned long long sw = 0, al = 0;
     float sm = 0;
     const PruneOut po = {&sw, &al, &sm};
     const int r = me_fullpel_impl(cur_y, ref_y, w, h, nframes, merange, pmv, lambda, mv_out, cost_out, nullptr, nullptr, iters, kernel_ms, &po);
-    if (swept_lane_tasks) *swept_lane_tasks = sw;
-    if (all_lane_tasks) *all_lane_tasks = al;
+    if (swept_candidates) *swept_candidates = sw;
+    if (all_candidates) *all_candidates = al;
     if (sums_ms) *sums_ms = sm;
     return r;
 }
 
-// K1a alone: block sums of `nframes` w x h planes after padding by B2_PAD with replicated borders; out: [nframes][rows][pitch] u16
-extern "C" int b2k_block_sums(const uint8_t *y, int w, int h, int nframes, uint16_t *out, int *pitch_out, int *rows_out)
+// K1a alone: (min | max << 16) over `ks` rows of the 16x16 block sums of `nframes` w x h planes after padding by B2_PAD with
+// replicated borders; out: [nframes][rows][pitch] u32.  ks = 1 gives the plain block sums in both halves.
+extern "C" int b2k_block_sums(const uint8_t *y, int w, int h, int nframes, int ks, uint32_t *out, int *pitch_out, int *rows_out)
 {
-    DevBuf d_ref, d_sum;
+    DevBuf d_ref, d_mm;
     int pitch, rows;
     if (upload_padded(d_ref, y, w, h, nframes, B2_PAD, &pitch, &rows)) return -1;
     if (pitch_out) *pitch_out = pitch;
     if (rows_out) *rows_out = rows;
     if (!out) return 0;
     const size_t n = (size_t)pitch * rows * nframes;
-    if (d_sum.alloc(n * 2)) return -1;
-    B2_CUDA_OK(cudaMemset(d_sum.p, 0, n * 2));
-    if (b2_launch_block_sums((const uint8_t *)d_ref.p, pitch, rows, nframes, (uint16_t *)d_sum.p, 0)) return -1;
-    B2_CUDA_OK(cudaMemcpy(out, d_sum.p, n * 2, cudaMemcpyDeviceToHost));
+    if (d_mm.alloc(n * 4)) return -1;
+    B2_CUDA_OK(cudaMemset(d_mm.p, 0, n * 4));
+    if (b2_launch_block_sums(ks, (const uint8_t *)d_ref.p, pitch, rows, nframes, (uint32_t *)d_mm.p, 0)) return -1;
+    B2_CUDA_OK(cudaMemcpy(out, d_mm.p, n * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 
@@ -118,23 +119,25 @@ static int me_fullpel_impl(const uint8_t *cur_y, const uint8_t *ref_y, int w, in
         B2_CUDA_OK(cudaMemcpy(d_pmv.p, pmv, nmb * sizeof(b2_mv_t), cudaMemcpyHostToDevice));
     }
     CUtensorMap tm_cur, tm_ref, tm_sum;
-    if (b2_make_plane_tmap(&tm_cur, d_cur.p, pitch, rows, nframes, 16 * b2_k1_strip_mbs(merange), 16)) return -1;
-    if (b2_make_plane_tmap(&tm_ref, d_ref.p, pitch, rows, nframes, bw, bh)) return -1;
+    const int strip = prune ? b2_k1_prune_strip_mbs(merange) : b2_k1_strip_mbs(merange);     // the pruned search has its own strip width
+    if (b2_make_plane_tmap(&tm_cur, d_cur.p, pitch, rows, nframes, 16 * strip, 16)) return -1;
+    if (b2_make_plane_tmap(&tm_ref, d_ref.p, pitch, rows, nframes, 16 * strip + 2 * merange, bh)) return -1;
     DevBuf d_sum, d_swept;
     if (prune) {
         if (mv9_out) return -1;
-        int sw, sh;
-        if (b2_k1_sum_box(merange, &sw, &sh)) return -1;
-        if (d_sum.alloc((size_t)pitch * rows * nframes * 2) || d_swept.alloc(8)) return -1;
-        B2_CUDA_OK(cudaMemset(d_sum.p, 0, (size_t)pitch * rows * nframes * 2));
+        const int mbox = b2_k1_mm_box(merange);
+        if (mbox < 0) return -1;
+        if (d_sum.alloc((size_t)pitch * rows * nframes * 4) || d_swept.alloc(8)) return -1;
+        B2_CUDA_OK(cudaMemset(d_sum.p, 0, (size_t)pitch * rows * nframes * 4));
         B2_CUDA_OK(cudaMemset(d_swept.p, 0, 8));
-        if (b2_make_plane_tmap16(&tm_sum, d_sum.p, pitch, rows, nframes, sw, sh)) return -1;
+        if (b2_make_plane_tmap32(&tm_sum, d_sum.p, pitch, rows, nframes, mbox)) return -1;
     }
+    const int ks = prune ? b2_k1_prune_rows(merange) : 0;
     auto launch = [&](bool with_sums, unsigned long long *swept) -> int {
         if (!prune)
             return b2_launch_me_fullpel(merange, &tm_cur, &tm_ref, mbw, mbh, nframes, (const b2_mv_t *)d_pmv.p, lambda,
                                         (b2_mv_t *)d_mv.p, (uint32_t *)d_cost.p, (b2_mv_t *)d_mv9.p, (uint32_t *)d_cost9.p, 0);
-        if (with_sums && b2_launch_block_sums((const uint8_t *)d_ref.p, pitch, rows, nframes, (uint16_t *)d_sum.p, 0)) return -1;
+        if (with_sums && b2_launch_block_sums(ks, (const uint8_t *)d_ref.p, pitch, rows, nframes, (uint32_t *)d_sum.p, 0)) return -1;
         return b2_launch_me_fullpel_pruned(merange, &tm_cur, &tm_ref, &tm_sum, mbw, mbh, nframes, (const b2_mv_t *)d_pmv.p, lambda,
                                            (b2_mv_t *)d_mv.p, (uint32_t *)d_cost.p, swept, 0);
     };
@@ -142,7 +145,7 @@ static int me_fullpel_impl(const uint8_t *cur_y, const uint8_t *ref_y, int w, in
     B2_CUDA_OK(cudaDeviceSynchronize());
     if (prune) {
         B2_CUDA_OK(cudaMemcpy(prune->swept, d_swept.p, 8, cudaMemcpyDeviceToHost));
-        *prune->all = (unsigned long long)b2_k1_lane_tasks(merange, mbw, mbh, nframes);
+        *prune->all = (unsigned long long)b2_k1_candidates(merange, mbw, mbh, nframes);
     }
     if (kernel_ms) {
         cudaEvent_t e0, e1;
@@ -150,7 +153,7 @@ static int me_fullpel_impl(const uint8_t *cur_y, const uint8_t *ref_y, int w, in
         if (iters < 1) iters = 1;
         if (prune) {                                           // K1a on its own: it runs once per reference frame
             cudaEventRecord(e0, 0);
-            for (int i = 0; i < iters; i++) b2_launch_block_sums((const uint8_t *)d_ref.p, pitch, rows, nframes, (uint16_t *)d_sum.p, 0);
+            for (int i = 0; i < iters; i++) b2_launch_block_sums(ks, (const uint8_t *)d_ref.p, pitch, rows, nframes, (uint32_t *)d_sum.p, 0);
             cudaEventRecord(e1, 0);
             B2_CUDA_OK(cudaEventSynchronize(e1));
             float ms = 0;

@@ -31,6 +31,7 @@
 //  * Winner: key = (cost << 13) | scan_index, CREDUX.MIN over the warp, atomicMin in smem.
 //    Lowest scan index wins ties by construction, exactly like the oracle's strict '<'.
 #include <stdlib.h>
+#include <string.h>
 #include <atomic>
 #include "b2_common.cuh"
 
@@ -58,8 +59,8 @@ template <int R> struct K1Cfg;
 template <> struct K1Cfg<32> { static constexpr int K = 13, NG = 5, NMB = B2_K1_NMB; };     // 65 = 5 x 13
 template <> struct K1Cfg<16> { static constexpr int K = 11, NG = 3, NMB = B2_K1_NMB16; };   // 33 = 3 x 11
 
-template <int R> struct K1Smem {
-    static constexpr int NMB = K1Cfg<R>::NMB;
+template <int R, int NMB_ = K1Cfg<R>::NMB> struct K1Smem {
+    static constexpr int NMB = NMB_;
     static constexpr int ND = 2 * R + 1;
     static constexpr int WIN_W = NMB * 16 + 2 * R;      // bytes per raw window row
     static constexpr int WIN_H = 16 + 2 * R;
@@ -521,83 +522,112 @@ k1_me_fullpel_persistent_kernel(const __grid_constant__ CUtensorMap tm_cur, cons
 // |sum(cur MB) - sum(ref block)| <= SAD(cur MB, ref block) (triangle inequality), so a candidate whose
 //     |C - S(dx,dy)| + mvcost(dx,dy)  >  U,     U = exact cost of any candidate already evaluated,
 // cannot be the minimum and cannot tie with it either; dropping it leaves argmin AND tie-break of the exhaustive scan untouched
-// (x264's own "esa" search is built on the same inequality).  Per strip:
+// (x264's own "esa" search is built on the same inequality).  The unit that is kept or dropped is the sweep's lane-task
+// (mb, dy-group of KS rows, dx): it is dropped when NONE of its KS candidates can pass, i.e. when
+//     dist(C, [min_k S, max_k S]) + mvcost_x(dx) + min_k mvcost_y  >  U
+// -- the interval form of the bound; K1a below delivers min | max of the 16x16 block sums over KS consecutive rows for every
+// position of the padded reference plane, so the test is ONE shared-memory word per lane-task.  Per strip:
 //   1. TMA window + current tile, cost tables, expansion: as k1_me_fullpel_kernel;
-//   2. the raw window is dead after the expansion, so the 16x16 block sums of the reference at the strip's (NMB-1)*16 + 2R+1
-//      candidate columns x 2R+1 rows arrive by TMA into the same shared memory (K1a below computes them once per reference
-//      frame: u16 plane with the geometry of the padded luma plane);
-//   3. one warp per macroblock evaluates two candidates exactly -- the zero vector and the rounded predictor (the co-located
-//      vector of the previous frame) -- giving U and the first best key;
-//   4. every lane-task (mb, dy-group, dx) tests its K candidates against U (mvcost of the row replaced by the smallest of the
-//      group: weaker, still a lower bound); the survivors are compacted (ballot -> prefix over the mask words -> list);
-//   5. the unchanged register-tiled sweep runs over the survivor list only.
-// What is skipped is reported, never folded into the roofline figure: `swept` counts the lane-tasks that ran (b2_engine_k1_stats).
+//   2. the raw window is dead after the expansion: the NG rows of (min | max) words the strip needs arrive by TMA into the same
+//      shared memory (NG one-row boxes on a second mbarrier);
+//   3. meanwhile one warp per macroblock evaluates two candidates exactly -- the zero vector and the rounded predictor (the
+//      co-located vector of the previous frame) -- which gives U and the first best key;
+//   4. bound test per lane-task (a warp walks 32 consecutive dx of one macroblock: ~20 instructions per lane-task); a survivor
+//      goes into the queue of ITS shared-memory bank, q = (16 * mb + dx) mod 32 (one shared atomicAdd, no two lanes of a warp hit
+//      the same counter);
+//   5. the register-tiled sweep of k1_me_fullpel_kernel runs over the queues: lane q of warp-task i takes entry i of queue q.  The
+//      expanded rows are a multiple of 32 words long, so the 32 lanes of every sweep load hit 32 different banks whatever rows and
+//      macroblocks they work on (a plain survivor list gave 1.9 wavefronts per load: the band of survivors of neighbouring dy groups
+//      overlaps in x; ncu: profiles/r2_k1_pruned_ncu.txt).  Queues that overflow (more than QCAP survivors: predictors that point
+//      nowhere) make the strip fall back to sweeping every lane-task in natural order.
+// KS (rows per lane-task) is a template parameter: fewer rows = finer pruning but fewer VABSDIFF4 per shared-memory load
+// (13 -> 5 rows: 7.4 -> 4.0 per LDS.32, still ALU-bound when the loads are conflict-free).  What is skipped is reported, never
+// folded into the roofline figure: `swept` counts the candidates that ran (b2_engine_k1_stats).
+#ifndef B2_K1_PRUNE_MINCTAS
+#define B2_K1_PRUNE_MINCTAS 3
+#endif
+#ifndef B2_K1_PRUNE_PDE
+#define B2_K1_PRUNE_PDE 1     // partial-distortion exit inside the sweep (0: every surviving lane-task is swept to the end)
+#endif
+template <int R> struct K1PruneCfg { static constexpr int NMB = K1Cfg<R>::NMB; };        // the exhaustive kernel's strips (and tensor maps)
+
 constexpr int k1_cmax(int a, int b) { return a > b ? a : b; }
-template <int R> struct K1SeaSmem {
-    using S = K1Smem<R>;
-    static constexpr int NMB = S::NMB, ND = S::ND, NG = K1Cfg<R>::NG;
+template <int R, int KS> struct K1SeaSmem {
+    static constexpr int NMB = K1PruneCfg<R>::NMB;
+    using S = K1Smem<R, NMB>;
+    static constexpr int ND = S::ND, NG = ND / KS;
+    static_assert(NG * KS == ND, "dy groups must tile the search range");
+    static_assert(S::EXP_PITCH % 32 == 0, "bank queues need expanded rows of a multiple of 32 words");
+    static_assert(NMB <= 16 && NG <= 16 && ND <= 128, "queue entries are m | g << 4 | dx << 8");
     static constexpr int NX = (NMB - 1) * 16 + ND;               // candidate columns of a strip
-    static constexpr int SUM_PITCH = (NX + 7) & ~7;              // u16 per row of the sum window (TMA rows are multiples of 16 B)
-    static constexpr int SUM_BYTES = SUM_PITCH * ND * 2;
+    static constexpr int MP = (NX + 31) & ~31;                   // words per row of (min | max) sums: every row is its own TMA box, 128-B aligned
+    static constexpr int M_BYTES = MP * NG * 4;
     static constexpr int NTASK = NMB * NG * ND;
-    static constexpr int NWORD = (NTASK + 31) / 32;
-    // region 0: raw window while it is expanded, then the block-sum window, then the survivor list (u16 lane-task ids)
-    static constexpr int R0_BYTES = k1_cmax(k1_cmax(S::RAW_BYTES + 16, SUM_BYTES), NTASK * 2);
+    // entries per bank queue: all lane-tasks of a bank when that is small, else 128 (60-80 % of them: a strip whose predictors point
+    // nowhere overflows and takes the natural-order path)
+    static constexpr int QCAP = NTASK / 32 + 8 < 128 ? ((NTASK / 32 + 8 + 7) & ~7) : 128;
+    static constexpr int Q_BYTES = 32 * QCAP * 2;
+    // region 0: raw window while it is expanded, then the (min | max) rows followed by the 32 bank queues
+    static constexpr int OFF_Q = (M_BYTES + 127) & ~127;
+    static constexpr int R0_BYTES = k1_cmax(S::RAW_BYTES + 16, OFF_Q + Q_BYTES);
     static constexpr int OFF_R0 = 0;
     static constexpr int OFF_CUR = (R0_BYTES + 127) & ~127;
     static constexpr int OFF_EXP = OFF_CUR + S::CUR_BYTES;
     static constexpr int OFF_COSTX = OFF_EXP + S::EXP_BYTES;
     static constexpr int OFF_COSTY = OFF_COSTX + NMB * ND * 4;
     static constexpr int OFF_BEST = OFF_COSTY + NMB * ND * 4;
-    static constexpr int OFF_U = OFF_BEST + NMB * 4;
-    static constexpr int OFF_CSUM = OFF_U + NMB * 4;
-    static constexpr int OFF_MINCY = OFF_CSUM + NMB * 4;
-    static constexpr int OFF_MASK = OFF_MINCY + NMB * NG * 4;
-    static constexpr int OFF_PREF = OFF_MASK + NWORD * 4;        // NWORD exclusive prefixes + the survivor count
-    static constexpr int OFF_BAR = (OFF_PREF + (NWORD + 1) * 4 + 7) & ~7;
+    static constexpr int OFF_CSUM = OFF_BEST + NMB * 4;
+    static constexpr int OFF_PMV = OFF_CSUM + NMB * 4;           // NMB x {x, y}
+    static constexpr int OFF_TG = OFF_PMV + NMB * 8;             // NMB x NG: U - smallest vertical vector cost of the group
+    static constexpr int OFF_CNT = OFF_TG + NMB * NG * 4;        // 32 queue lengths + overflow flag
+    static constexpr int OFF_BAR = (OFF_CNT + 33 * 4 + 7) & ~7;
     static constexpr int TOTAL = OFF_BAR + 16 + 128;             // +128: manual alignment slack
 };
+static_assert(B2_K1_PRUNE_MINCTAS * (K1SeaSmem<32, 5>::TOTAL + 1024) <= 228 * 1024, "pruned K1 (+-32, 5 rows): the CTAs per SM asked for do not fit");
 
-// three CTAs per SM, like the exhaustive kernel: 3 x (TOTAL + 1 KB reserved per CTA) <= 228 KB
-static_assert(B2_K1_MINCTAS != 3 || B2_K1_NMB != 6 || 3 * (K1SeaSmem<32>::TOTAL + 1024) <= 228 * 1024, "pruned K1 (+-32) no longer fits three CTAs per SM");
-static_assert(K1SeaSmem<32>::NTASK < 65536 && K1SeaSmem<16>::NTASK < 65536, "survivor list entries are u16");
-
-template <int R, int NTHREADS>
-__global__ void __launch_bounds__(NTHREADS, B2_K1_MINCTAS)
+template <int R, int KS, int NTHREADS>
+__global__ void __launch_bounds__(NTHREADS, B2_K1_PRUNE_MINCTAS)
 k1_me_fullpel_sea_kernel(const __grid_constant__ CUtensorMap tm_cur, const __grid_constant__ CUtensorMap tm_ref,
-                         const __grid_constant__ CUtensorMap tm_sum, int mbw, int mbh, const b2_mv_t *__restrict__ pmv, int lambda,
+                         const __grid_constant__ CUtensorMap tm_mm, int mbw, int mbh, const b2_mv_t *__restrict__ pmv, int lambda,
                          b2_mv_t *__restrict__ mv_out, uint32_t *__restrict__ cost_out, unsigned long long *__restrict__ swept)
 {
-    using S = K1Smem<R>;
-    using Q = K1SeaSmem<R>;
+    using Q = K1SeaSmem<R, KS>;
+    using S = typename Q::S;
     constexpr int NWARPS = NTHREADS / 32;
-    constexpr int K = K1Cfg<R>::K, NG = K1Cfg<R>::NG, ND = S::ND, NMB = K1Cfg<R>::NMB;
+    constexpr int K = KS, NG = Q::NG, ND = S::ND, NMB = Q::NMB, QCAP = Q::QCAP;
 
     extern __shared__ uint8_t smem_raw_[];
     uint8_t *smem = smem_raw_ + ((128u - (smem_u32(smem_raw_) & 127u)) & 127u);
     uint8_t *s_raw = smem + Q::OFF_R0;
-    const uint16_t *s_sum = (const uint16_t *)(smem + Q::OFF_R0);
-    uint16_t *s_list = (uint16_t *)(smem + Q::OFF_R0);
+    const uint32_t *s_mm = (const uint32_t *)(smem + Q::OFF_R0);
+    uint16_t *s_queue = (uint16_t *)(smem + Q::OFF_R0 + Q::OFF_Q);
     uint8_t *s_cur = smem + Q::OFF_CUR;
     uint32_t *s_exp = (uint32_t *)(smem + Q::OFF_EXP);
     uint32_t *s_costx = (uint32_t *)(smem + Q::OFF_COSTX);
     uint32_t *s_costy = (uint32_t *)(smem + Q::OFF_COSTY);
     uint32_t *s_best = (uint32_t *)(smem + Q::OFF_BEST);
-    int *s_u = (int *)(smem + Q::OFF_U);
     int *s_csum = (int *)(smem + Q::OFF_CSUM);
-    int *s_mincy = (int *)(smem + Q::OFF_MINCY);
-    uint32_t *s_mask = (uint32_t *)(smem + Q::OFF_MASK);
-    uint32_t *s_pref = (uint32_t *)(smem + Q::OFF_PREF);
+    int *s_pmv = (int *)(smem + Q::OFF_PMV);
+    int *s_tg = (int *)(smem + Q::OFF_TG);
+    int *s_cnt = (int *)(smem + Q::OFF_CNT);          // [32] queue lengths, [32] overflow flag
     uint64_t *s_bar = (uint64_t *)(smem + Q::OFF_BAR);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mb0 = blockIdx.x * NMB, mby = blockIdx.y, frame = blockIdx.z;
     const int nmb = min(NMB, mbw - mb0);
+    const size_t mb_base = ((size_t)frame * mbh + mby) * mbw + mb0;
 
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
         fence_mbar_init();
+    }
+    if (tid < 33) s_cnt[tid] = 0;
+    if (tid >= 64 && tid < 64 + NMB) {     // predictors: one global load per macroblock
+        const int m = tid - 64;
+        int px = 0, py = 0;
+        if (pmv != nullptr && m < nmb) { const b2_mv_t p = pmv[mb_base + m]; px = p.x; py = p.y; }
+        s_pmv[2 * m] = px; s_pmv[2 * m + 1] = py;
     }
     __syncthreads();
     if (tid == 0) {
@@ -606,13 +636,10 @@ k1_me_fullpel_sea_kernel(const __grid_constant__ CUtensorMap tm_cur, const __gri
         tma_load_3d(s_cur, &tm_cur, B2_PAD + mb0 * 16, B2_PAD + mby * 16, frame, &s_bar[0]);
     }
 
-    const size_t mb_base = ((size_t)frame * mbh + mby) * mbw + mb0;
     for (int i = tid; i < NMB * ND; i += NTHREADS) {
-        int m = i / ND, d = i - m * ND;
-        int px = 0, py = 0;
-        if (pmv != nullptr && m < nmb) { b2_mv_t p = pmv[mb_base + m]; px = p.x; py = p.y; }
-        s_costx[i] = ((uint32_t)(lambda * b2_mvbits(4 * (d - R) - px)) << 13) + (uint32_t)d;
-        s_costy[i] = ((uint32_t)(lambda * b2_mvbits(4 * (d - R) - py)) << 13) + (uint32_t)(d * ND);
+        const int m = i / ND, d = i - m * ND;
+        s_costx[i] = ((uint32_t)(lambda * b2_mvbits(4 * (d - R) - s_pmv[2 * m])) << 13) + (uint32_t)d;
+        s_costy[i] = ((uint32_t)(lambda * b2_mvbits(4 * (d - R) - s_pmv[2 * m + 1])) << 13) + (uint32_t)(d * ND);
     }
 
     mbar_wait(&s_bar[0], 0);
@@ -630,17 +657,18 @@ k1_me_fullpel_sea_kernel(const __grid_constant__ CUtensorMap tm_cur, const __gri
             *(uint4 *)(s_exp + r * S::EXP_PITCH + 4 * j) = o;
         }
     }
-    fence_proxy_async();                  // this thread's generic reads of the raw window precede the TMA write into the same bytes
-    __syncthreads();
+    fence_proxy_async();                  // this thread's generic reads of the raw window precede the TMA writes into the same bytes
+    __syncthreads();                      // expansion and cost tables complete; the raw window is dead from here on
     if (tid == 0) {
-        mbar_expect_tx(&s_bar[1], Q::SUM_BYTES);
-        tma_load_3d(s_raw, &tm_sum, B2_PAD + mb0 * 16 - R, B2_PAD + mby * 16 - R, frame, &s_bar[1]);
+        mbar_expect_tx(&s_bar[1], Q::M_BYTES);
+        for (int g = 0; g < NG; g++)
+            tma_load_3d(s_raw + g * Q::MP * 4, &tm_mm, B2_PAD + mb0 * 16 - R, B2_PAD + mby * 16 - R + g * K, frame, &s_bar[1]);
     }
 
-    // thresholds while the sums are in flight: exact keys of the zero vector and of the rounded predictor
+    // thresholds while those rows are in flight: exact keys of the zero vector and of the rounded predictor; then U - min_k mvcost_y
+    // per dy group
     for (int m = warp; m < nmb; m += NWARPS) {
-        int px = 0, py = 0;
-        if (pmv != nullptr) { b2_mv_t p = pmv[mb_base + m]; px = p.x; py = p.y; }
+        const int px = s_pmv[2 * m], py = s_pmv[2 * m + 1];
         const int cdx = min(max((px + 2) >> 2, -R), R) + R, cdy = min(max((py + 2) >> 2, -R), R) + R;
         uint32_t sa = 0, sb = 0, cs = 0;
 #pragma unroll
@@ -654,79 +682,57 @@ k1_me_fullpel_sea_kernel(const __grid_constant__ CUtensorMap tm_cur, const __gri
         sa = __reduce_add_sync(0xffffffffu, sa);
         sb = __reduce_add_sync(0xffffffffu, sb);
         cs = __reduce_add_sync(0xffffffffu, cs);
+        const uint32_t ka = sa * 8192u + s_costx[m * ND + R] + s_costy[m * ND + R];
+        const uint32_t kb = sb * 8192u + s_costx[m * ND + cdx] + s_costy[m * ND + cdy];
+        const uint32_t kk = min(ka, kb);
         if (lane == 0) {
-            const uint32_t ka = sa * 8192u + s_costx[m * ND + R] + s_costy[m * ND + R];
-            const uint32_t kb = sb * 8192u + s_costx[m * ND + cdx] + s_costy[m * ND + cdy];
-            const uint32_t kk = min(ka, kb);
             s_best[m] = kk;
-            s_u[m] = (int)(kk >> 13);
             s_csum[m] = (int)cs;
         }
-    }
-    for (int i = tid; i < NMB * NG; i += NTHREADS) {
-        const int m = i / NG, g = i - m * NG;
-        uint32_t mn = 0xffffffffu;
-        for (int k = 0; k < K; k++) mn = min(mn, s_costy[m * ND + g * K + k] >> 13);
-        s_mincy[i] = (int)mn;
+        for (int g = lane; g < NG; g += 32) {
+            uint32_t mn = 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < K; k++) mn = min(mn, s_costy[m * ND + g * K + k] >> 13);
+            s_tg[m * NG + g] = (int)(kk >> 13) - (int)mn;
+        }
     }
     __syncthreads();
     mbar_wait(&s_bar[1], 0);
 
-    // bound test: lane-task id = (round * NWARPS + warp) * 32 + lane, so one warp round fills exactly one mask word
-    const int total = nmb * NG * ND;
-    for (int id0 = warp * 32; id0 < total; id0 += NWARPS * 32) {
-        const int id = id0 + lane;
-        bool alive = false;
-        if (id < total) {
-            const int m = id / (NG * ND);
-            const int rem = id - m * (NG * ND);
-            const int g = rem / ND;
-            const int dxi = rem - g * ND;
-            const int t = s_u[m] - (int)(s_costx[m * ND + dxi] >> 13) - s_mincy[m * NG + g];
-            if (t >= 0) {
-                const uint16_t *sp = s_sum + (g * K) * Q::SUM_PITCH + m * 16 + dxi;
+    // bound test.  A warp round = 32 consecutive dx of ONE (macroblock, dy group), so everything but the column is warp-uniform; the
+    // search range is 32 * FULL + 1 columns wide, the left-over column of all NG groups of a macroblock makes one more round
+    // (lane = group).  Survivors go to their bank's queue; entry i of all 32 queues is one row of 32 u16.
+    {
+        constexpr int FULL = (ND - 1) / 32;
+        static_assert(FULL * 32 + 1 == ND && NG <= 32, "round layout of the bound test");
+        constexpr int RPM = NG * FULL + 1;                // rounds per macroblock
+        for (int pi = warp; pi < nmb * RPM; pi += NWARPS) {
+            const int m = pi / RPM, rr = pi - m * RPM;
+            int g, dxi;
+            bool valid = true;
+            if (rr < NG * FULL) { g = rr / FULL; dxi = (rr - g * FULL) * 32 + lane; }
+            else { g = lane; dxi = ND - 1; valid = lane < NG; }
+            if (valid) {
+                const int t = s_tg[m * NG + g] - (int)(s_costx[m * ND + dxi] >> 13);
+                const uint32_t mm = s_mm[g * Q::MP + m * 16 + dxi];
                 const int c = s_csum[m];
-#pragma unroll
-                for (int k = 0; k < K; k++) alive |= abs((int)sp[k * Q::SUM_PITCH] - c) <= t;
+                const int d = max((int)(mm & 0xffffu) - c, c - (int)(mm >> 16));      // distance of C to [min, max]; negative inside
+                if (t >= 0 && d <= t) {
+                    const int q = (m * 16 + dxi) & 31;
+                    const int slot = atomicAdd(&s_cnt[q], 1);
+                    if (slot < QCAP) s_queue[slot * 32 + q] = (uint16_t)(m | g << 4 | dxi << 8);
+                    else s_cnt[32] = 1;
+                }
             }
         }
-        const uint32_t mask = __ballot_sync(0xffffffffu, alive);
-        if (lane == 0) s_mask[id0 >> 5] = mask;
-    }
-    __syncthreads();                      // all reads of the sum window are done: region 0 becomes the survivor list
-    const int nword = (total + 31) >> 5;
-    if (warp == 0) {
-        uint32_t run = 0;
-        for (int base = 0; base < nword; base += 32) {
-            const int w = base + lane;
-            const uint32_t c = w < nword ? (uint32_t)__popc(s_mask[w]) : 0u;
-            uint32_t inc = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
-            }
-            if (w < nword) s_pref[w] = run + inc - c;
-            run += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (lane == 0) s_pref[Q::NWORD] = run;
-    }
-    __syncthreads();
-    const int count = (int)s_pref[Q::NWORD];
-    for (int id0 = warp * 32; id0 < total; id0 += NWARPS * 32) {
-        const uint32_t mask = s_mask[id0 >> 5];
-        if ((mask >> lane) & 1u) s_list[s_pref[id0 >> 5] + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)(id0 + lane);
     }
     __syncthreads();
 
-    for (int t0 = warp * 32; t0 < count; t0 += NWARPS * 32) {
-        const bool active = t0 + lane < count;
-        const int tt = s_list[active ? t0 + lane : t0];       // idle lanes shadow lane 0's task
-        const int m = tt / (NG * ND);
-        const int rem = tt - m * (NG * ND);
-        const int g = rem / ND;
-        const int dxi = rem - g * ND;
-
+    // one lane-task of the sweep: K candidates (dy = g*K .. g*K+K-1 at dx) of macroblock m; returns the smallest key.
+    // Partial-distortion exit: a SAD only grows row by row, so once the PARTIAL key of every candidate of every lane of the warp
+    // exceeds the macroblock's best key so far, none of them can become the minimum (keys are unique per candidate) and the warp
+    // drops the rest of the task; checked after reference rows 8, 12, ... (each candidate has then seen at least 4, 8, ... rows).
+    auto lane_task = [&](int m, int g, int dxi, bool active) -> uint32_t {
         uint32_t cur[64];
         {
             const uint4 *c4 = (const uint4 *)(s_cur + m * 16);
@@ -736,10 +742,15 @@ k1_me_fullpel_sea_kernel(const __grid_constant__ CUtensorMap tm_cur, const __gri
                 cur[y * 4 + 0] = v.x; cur[y * 4 + 1] = v.y; cur[y * 4 + 2] = v.z; cur[y * 4 + 3] = v.w;
             }
         }
-        uint32_t acc[K];
+        uint32_t acc[K], kc[K];
+        {
+            const uint32_t kx = s_costx[m * ND + dxi];
+            const uint32_t *ky = s_costy + m * ND + g * K;
 #pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = 0;
+            for (int k = 0; k < K; k++) { acc[k] = 0; kc[k] = kx + ky[k]; }
+        }
         const uint32_t *wp = s_exp + (g * K) * S::EXP_PITCH + m * 16 + dxi;
+        bool dropped = false;
 #pragma unroll
         for (int r = 0; r < K + 15; r++) {
             const uint32_t w0 = wp[r * S::EXP_PITCH + 0];
@@ -756,22 +767,62 @@ k1_me_fullpel_sea_kernel(const __grid_constant__ CUtensorMap tm_cur, const __gri
                     acc[k] = vsad4_acc(w3, cur[y * 4 + 3], acc[k]);
                 }
             }
+            if (B2_K1_PRUNE_PDE && r >= K + 3 && r <= K + 7 && ((r - (K + 3)) & 3) == 0) {
+                bool hopeless = true;
+                if (active) {
+                    const uint32_t bk = ((volatile uint32_t *)s_best)[m];
+#pragma unroll
+                    for (int k = 0; k < K; k++) hopeless = hopeless && acc[k] * 8192u + kc[k] > bk;
+                }
+                if (__all_sync(0xffffffffu, hopeless)) { dropped = true; break; }
+            }
         }
         uint32_t key = 0xffffffffu;
-        if (active) {
-            const uint32_t kx = s_costx[m * ND + dxi];
-            const uint32_t *ky = s_costy + m * ND + g * K;
+        if (active && !dropped) {
 #pragma unroll
-            for (int k = 0; k + 1 < K; k += 2) key = __vimin3_u32(key, acc[k] * 8192u + (kx + ky[k]), acc[k + 1] * 8192u + (kx + ky[k + 1]));
-            if (K & 1) key = min(key, acc[K - 1] * 8192u + (kx + ky[K - 1]));
+            for (int k = 0; k + 1 < K; k += 2) key = __vimin3_u32(key, acc[k] * 8192u + kc[k], acc[k + 1] * 8192u + kc[k + 1]);
+            if (K & 1) key = min(key, acc[K - 1] * 8192u + kc[K - 1]);
         }
-        const int m0 = __shfl_sync(0xffffffffu, m, 0);
-        if (__all_sync(0xffffffffu, m == m0)) {
-            const uint32_t wmin = __reduce_min_sync(0xffffffffu, key);
-            if (lane == 0) atomicMin(&s_best[m0], wmin);
-        } else if (active) {
-            atomicMin(&s_best[m], key);
+        return key;
+    };
+
+    long long executed;
+    if (s_cnt[32] == 0) {
+        const int mine = s_cnt[lane];
+        const int rounds = __reduce_max_sync(0xffffffffu, mine);
+        for (int i = warp; i < rounds; i += NWARPS) {
+            const bool active = i < mine;
+            // idle lanes sweep a harmless task of their own bank: (mb 0, group 0, dx = lane)
+            const int tt = active ? (int)s_queue[i * 32 + lane] : lane << 8;
+            const int m = tt & 15, g = (tt >> 4) & 15, dxi = tt >> 8;
+            const uint32_t key = lane_task(m, g, dxi, active);
+            if (active) atomicMin(&s_best[m], key);
         }
+        int sum = mine;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        executed = (long long)sum * K;
+    } else {
+        // a queue overflowed: every lane-task, in the exhaustive kernel's order
+        const int total = nmb * NG * ND;
+        for (int t0 = warp * 32; t0 < total; t0 += NWARPS * 32) {
+            const int t = t0 + lane;
+            const bool active = t < total;
+            const int tt = active ? t : t0;
+            const int m = tt / (NG * ND);
+            const int rem = tt - m * (NG * ND);
+            const int g = rem / ND;
+            const int dxi = rem - g * ND;
+            const uint32_t key = lane_task(m, g, dxi, active);
+            const int m0 = __shfl_sync(0xffffffffu, m, 0);
+            if (__all_sync(0xffffffffu, m == m0)) {
+                const uint32_t wmin = __reduce_min_sync(0xffffffffu, key);
+                if (lane == 0) atomicMin(&s_best[m0], wmin);
+            } else if (active) {
+                atomicMin(&s_best[m], key);
+            }
+        }
+        executed = (long long)total * K;
     }
     __syncthreads();
 
@@ -785,55 +836,81 @@ k1_me_fullpel_sea_kernel(const __grid_constant__ CUtensorMap tm_cur, const __gri
         mv_out[mb_base + tid] = mv;
         cost_out[mb_base + tid] = key >> 13;
     }
-    if (tid == 0 && swept != nullptr) atomicAdd(swept, (unsigned long long)count);
+    if (tid == 0 && swept != nullptr) atomicAdd(swept, (unsigned long long)executed);
 }
 
-// K1a: 16x16 block sums of a padded luma plane, sum[Y][X] = sum of plane[Y..Y+15][X..X+15] (u16: at most 65,280), for every
-// position whose block lies inside the allocation; same [n][rows][pitch] geometry as the plane.  HBM-bound and tiny next to the
-// search (1 B read + 2 B written per pixel): one CTA per 128 x 32 tile, vertical 16-sums by a sliding column walk, then the
-// horizontal 16-sum as two levels of 4.
-constexpr int K1A_TW = 128, K1A_TH = 32;
+// K1a: for every position (Y, X) of a padded luma plane, min | max << 16 over the KS rows Y..Y+KS-1 of the 16x16 block sums
+// S[Y][X] = sum of plane[Y..Y+15][X..X+15] (at most 65,280: u16), as one u32 -- what the pruned search tests a lane-task with.
+// Same [n][rows][pitch] geometry as the plane; positions whose blocks leave the allocation hold 0 | 0xffff (never prune).
+// HBM-bound by design (1 B read + 4 B written per pixel).  One CTA per 128 x 48 tile; every pass works on PAIRS of adjacent
+// columns packed as u16x2 (VIADD.16x2 / VIMNMX.U16x2): vertical 16-sums by a sliding column walk (three row segments so that
+// 216 threads walk), the horizontal 16-sum as two levels of 4, then the row-window minimum / maximum.
+constexpr int K1A_TW = 128, K1A_TH = 48;
+template <int KS>
 __global__ void __launch_bounds__(256) k1a_block_sums_kernel(const uint8_t *__restrict__ planes, int pitch, int rows, size_t plane_stride,
-                                                             uint16_t *__restrict__ sums)
+                                                             uint32_t *__restrict__ mm_out)
 {
-    __shared__ uint32_t s_in[K1A_TH + 15][(K1A_TW + 16) / 4];
-    __shared__ uint16_t s_v[K1A_TH][K1A_TW + 16];
-    __shared__ uint16_t s_q[K1A_TH][K1A_TW + 16];
+    constexpr int SR = K1A_TH + KS - 1;                   // rows of block sums a tile needs
+    constexpr int IR = SR + 15;                           // input rows
+    constexpr int WPR = (K1A_TW + 16) / 4;                // input words per row
+    constexpr int PPR = (K1A_TW + 16) / 2;                // column pairs per row
+    __shared__ uint32_t s_in[IR][WPR];
+    __shared__ uint32_t s_v[SR][PPR];                     // vertical 16-sums (pairs); later the block sums themselves ([SR][K1A_TW / 2] used)
+    __shared__ uint32_t s_q[SR][PPR];                     // sums of 4 columns: pair p = (q[2p], q[2p+1])
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * K1A_TW, y0 = blockIdx.y * K1A_TH;
     const uint8_t *plane = planes + (size_t)blockIdx.z * plane_stride;
-    uint16_t *out = sums + (size_t)blockIdx.z * plane_stride;           // same element stride: the sum plane mirrors the luma plane
-    constexpr int WPR = (K1A_TW + 16) / 4;
-    for (int i = tid; i < (K1A_TH + 15) * WPR; i += 256) {
+    uint32_t *out = mm_out + (size_t)blockIdx.z * plane_stride;         // same element stride: the plane of words mirrors the luma plane
+    for (int i = tid; i < IR * WPR; i += 256) {
         const int r = i / WPR, w = i - r * WPR;
         const int yy = min(y0 + r, rows - 1), xx = x0 + 4 * w;
         s_in[r][w] = xx + 3 < pitch ? *(const uint32_t *)(plane + (size_t)yy * pitch + xx) : 0u;
     }
     __syncthreads();
-    if (tid < K1A_TW + 16) {
-        const uint8_t *col = (const uint8_t *)&s_in[0][0] + tid;
-        constexpr int P = WPR * 4;
-        int acc = 0;
+    {
+        constexpr int NSEG = 3, SEG = (SR + NSEG - 1) / NSEG;
+        const int seg = tid / PPR, cp = tid - seg * PPR;
+        if (seg < NSEG) {
+            const uint16_t *col = (const uint16_t *)&s_in[0][0] + cp;   // two adjacent bytes of every row
+            constexpr int P = WPR * 2;                                   // row pitch in u16
+            const int r0 = seg * SEG, r1 = min(SR, r0 + SEG);
+            uint32_t acc = 0;
 #pragma unroll
-        for (int j = 0; j < 16; j++) acc += col[j * P];
-        s_v[0][tid] = (uint16_t)acc;
-        for (int y = 1; y < K1A_TH; y++) {
-            acc += col[(y + 15) * P] - col[(y - 1) * P];
-            s_v[y][tid] = (uint16_t)acc;
+            for (int j = 0; j < 16; j++) acc += __byte_perm((uint32_t)col[(r0 + j) * P], 0u, 0x4140);
+            s_v[r0][cp] = acc;
+            for (int r = r0 + 1; r < r1; r++) {
+                acc += __byte_perm((uint32_t)col[(r + 15) * P], 0u, 0x4140) - __byte_perm((uint32_t)col[(r - 1) * P], 0u, 0x4140);
+                s_v[r][cp] = acc;                                        // both halves stay below 4,081: no carry between them
+            }
         }
     }
     __syncthreads();
-    for (int i = tid; i < K1A_TH * (K1A_TW + 12); i += 256) {
-        const int y = i / (K1A_TW + 12), x = i - y * (K1A_TW + 12);
-        s_q[y][x] = (uint16_t)(s_v[y][x] + s_v[y][x + 1] + s_v[y][x + 2] + s_v[y][x + 3]);
+    for (int i = tid; i < SR * (PPR - 2); i += 256) {                    // q[x] = v[x] + v[x+1] + v[x+2] + v[x+3] for the pair (2p, 2p+1)
+        const int y = i / (PPR - 2), p = i - y * (PPR - 2);
+        const uint32_t w0 = s_v[y][p], w1 = s_v[y][p + 1], w2 = s_v[y][p + 2];
+        s_q[y][p] = __vadd2(__vadd2(w0, __funnelshift_r(w0, w1, 16)), __vadd2(w1, __funnelshift_r(w1, w2, 16)));
     }
     __syncthreads();
-    for (int i = tid; i < K1A_TH * K1A_TW; i += 256) {
-        const int y = i / K1A_TW, x = i - y * K1A_TW;
-        const int Y = y0 + y, X = x0 + x;
+    for (int i = tid; i < SR * (K1A_TW / 2); i += 256) {                 // block sums into s_v (its vertical sums are dead)
+        const int y = i / (K1A_TW / 2), p = i - y * (K1A_TW / 2);
+        s_v[y][p] = __vadd2(__vadd2(s_q[y][p], s_q[y][p + 2]), __vadd2(s_q[y][p + 4], s_q[y][p + 6]));
+    }
+    __syncthreads();
+    for (int i = tid; i < K1A_TH * (K1A_TW / 2); i += 256) {
+        const int y = i / (K1A_TW / 2), p = i - y * (K1A_TW / 2);
+        const int Y = y0 + y, X = x0 + 2 * p;
         if (Y < rows && X < pitch) {
-            const bool valid = Y + 16 <= rows && X + 16 <= pitch;
-            out[(size_t)Y * pitch + X] = valid ? (uint16_t)(s_q[y][x] + s_q[y][x + 4] + s_q[y][x + 8] + s_q[y][x + 12]) : (uint16_t)0;
+            uint32_t lo = s_v[y][p], hi = lo;
+#pragma unroll
+            for (int j = 1; j < KS; j++) {
+                const uint32_t v = s_v[y + j][p];
+                lo = __vminu2(lo, v); hi = __vmaxu2(hi, v);
+            }
+            const bool rows_ok = Y + KS - 1 + 16 <= rows;
+            uint2 o;
+            o.x = rows_ok && X + 16 <= pitch ? (lo & 0xffffu) | (hi << 16) : 0xffff0000u;
+            o.y = rows_ok && X + 17 <= pitch ? (lo >> 16) | (hi & 0xffff0000u) : 0xffff0000u;
+            *(uint2 *)(out + (size_t)Y * pitch + X) = o;
         }
     }
 }
@@ -902,22 +979,30 @@ int launch_k1(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, int mbw, int
     return launch_k1p<R, NT, false>(tm_cur, tm_ref, mbw, mbh, nframes, pmv, lambda, mv_out, cost_out, nullptr, nullptr, st);
 }
 
-template <int R, int NT>
-int launch_k1_sea(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, const CUtensorMap &tm_sum, int mbw, int mbh, int nframes,
+template <int R, int KS, int NT>
+int launch_k1_sea(const CUtensorMap &tm_cur, const CUtensorMap &tm_ref, const CUtensorMap &tm_mm, int mbw, int mbh, int nframes,
                   const b2_mv_t *pmv, int lambda, b2_mv_t *mv_out, uint32_t *cost_out, unsigned long long *swept, cudaStream_t st)
 {
     static std::atomic<bool> attr_set[64];
     int dev = 0;
     B2_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
-        B2_CUDA_OK(cudaFuncSetAttribute(k1_me_fullpel_sea_kernel<R, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1SeaSmem<R>::TOTAL));
+        B2_CUDA_OK(cudaFuncSetAttribute(k1_me_fullpel_sea_kernel<R, KS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1SeaSmem<R, KS>::TOTAL));
         if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
     }
-    constexpr int NMB = K1Cfg<R>::NMB;
+    constexpr int NMB = K1PruneCfg<R>::NMB;
     dim3 grid((mbw + NMB - 1) / NMB, mbh, nframes);
-    k1_me_fullpel_sea_kernel<R, NT><<<grid, NT, K1SeaSmem<R>::TOTAL, st>>>(tm_cur, tm_ref, tm_sum, mbw, mbh, pmv, lambda, mv_out, cost_out, swept);
+    k1_me_fullpel_sea_kernel<R, KS, NT><<<grid, NT, K1SeaSmem<R, KS>::TOTAL, st>>>(tm_cur, tm_ref, tm_mm, mbw, mbh, pmv, lambda, mv_out, cost_out, swept);
     B2_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+// rows per lane-task of the pruned search: B2_K1_PRUNE_ROWS = "coarse" keeps the exhaustive kernel's 13 (+-32) / 11 (+-16), the
+// default "fine" uses 5 / 3 (A/B: scripts/k1_prune_probe.py, profiles/r2_k1_prune_probe.txt)
+int k1_prune_fine()
+{
+    static const int v = [] { const char *e = getenv("B2_K1_PRUNE_ROWS"); return !(e && !strcmp(e, "coarse")); }();
+    return v;
 }
 
 // threads per CTA: 82 (R=32) / 41 (R=16) warp-tasks per full strip should divide evenly over the warps
@@ -967,44 +1052,64 @@ int b2_launch_me_fullpel(int R, const CUtensorMap *tm_cur, const CUtensorMap *tm
     }
 }
 
-// ---- pruned search (me_prune): block sums of the reference (K1a), then K1 with successive elimination ------------------------
-// box of the block-sum window a strip fetches: {((NMB-1)*16 + 2R+1 rounded up to 8) u16, 2R+1 rows, 1}
-extern "C" int b2_k1_sum_box(int R, int *bw, int *bh)
+// ---- pruned search (me_prune): K1a (min | max of the block sums per lane-task), then K1 with successive elimination -----------
+// rows per lane-task the pruned search uses for +-R (K1a has to be run with the same number)
+extern "C" int b2_k1_prune_rows(int R)
 {
-    if (R == 32) { *bw = K1SeaSmem<32>::SUM_PITCH; *bh = K1SeaSmem<32>::ND; return 0; }
-    if (R == 16) { *bw = K1SeaSmem<16>::SUM_PITCH; *bh = K1SeaSmem<16>::ND; return 0; }
+    if (R == 32) return k1_prune_fine() ? 5 : K1Cfg<32>::K;
+    if (R == 16) return k1_prune_fine() ? 3 : K1Cfg<16>::K;
     return -1;
 }
+// words per row of the (min | max) box a strip fetches (the box is {this, 1, 1}; a strip issues one per dy group)
+extern "C" int b2_k1_mm_box(int R)
+{
+    if (R == 32) return K1SeaSmem<32, 13>::MP;
+    if (R == 16) return K1SeaSmem<16, 11>::MP;
+    return -1;
+}
+// macroblocks per strip of the pruned search: its current-tile box is {16 * this, 16, 1}, its window box {16 * this + 2R, 16 + 2R, 1}
+extern "C" int b2_k1_prune_strip_mbs(int R) { return R == 16 ? K1PruneCfg<16>::NMB : K1PruneCfg<32>::NMB; }
 
-int b2_launch_block_sums(const uint8_t *d_planes, int pitch, int rows, int nplanes, uint16_t *d_sums, cudaStream_t st)
+int b2_launch_block_sums(int ks, const uint8_t *d_planes, int pitch, int rows, int nplanes, uint32_t *d_mm, cudaStream_t st)
 {
     dim3 grid((pitch + K1A_TW - 1) / K1A_TW, (rows + K1A_TH - 1) / K1A_TH, nplanes);
-    k1a_block_sums_kernel<<<grid, 256, 0, st>>>(d_planes, pitch, rows, (size_t)pitch * rows, d_sums);
+    const size_t stride = (size_t)pitch * rows;
+    switch (ks) {
+    case 13: k1a_block_sums_kernel<13><<<grid, 256, 0, st>>>(d_planes, pitch, rows, stride, d_mm); break;
+    case 11: k1a_block_sums_kernel<11><<<grid, 256, 0, st>>>(d_planes, pitch, rows, stride, d_mm); break;
+    case 5: k1a_block_sums_kernel<5><<<grid, 256, 0, st>>>(d_planes, pitch, rows, stride, d_mm); break;
+    case 3: k1a_block_sums_kernel<3><<<grid, 256, 0, st>>>(d_planes, pitch, rows, stride, d_mm); break;
+    case 1: k1a_block_sums_kernel<1><<<grid, 256, 0, st>>>(d_planes, pitch, rows, stride, d_mm); break;      // the plain block sums (tests)
+    default: fprintf(stderr, "b2enc: block sums over %d rows not built\n", ks); return -1;
+    }
     B2_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-// lane-tasks (mb, dy-group, dx) of an exhaustive launch: what `swept` is compared with
-extern "C" long long b2_k1_lane_tasks(int R, int mbw, int mbh, int nframes)
+// candidate vectors of an exhaustive launch: what `swept` is compared with
+extern "C" long long b2_k1_candidates(int R, int mbw, int mbh, int nframes)
 {
-    const long long per_mb = R == 16 ? (long long)K1Cfg<16>::NG * (2 * 16 + 1) : (long long)K1Cfg<32>::NG * (2 * 32 + 1);
-    return per_mb * mbw * mbh * nframes;
+    return (long long)(2 * R + 1) * (2 * R + 1) * mbw * mbh * nframes;
 }
 
-int b2_launch_me_fullpel_pruned(int R, const CUtensorMap *tm_cur, const CUtensorMap *tm_ref, const CUtensorMap *tm_sum, int mbw, int mbh,
+int b2_launch_me_fullpel_pruned(int R, const CUtensorMap *tm_cur, const CUtensorMap *tm_ref, const CUtensorMap *tm_mm, int mbw, int mbh,
                                 int nframes, const b2_mv_t *d_pmv, int lambda, b2_mv_t *d_mv, uint32_t *d_cost,
                                 unsigned long long *d_swept, cudaStream_t st)
 {
-#define K1S_DISPATCH(RR)                                                                                                          \
-    switch (k1_threads()) {                                                                                                       \
-    case 192: return launch_k1_sea<RR, 192>(*tm_cur, *tm_ref, *tm_sum, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, d_swept, st); \
-    case 320: return launch_k1_sea<RR, 320>(*tm_cur, *tm_ref, *tm_sum, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, d_swept, st); \
-    case 384: return launch_k1_sea<RR, 384>(*tm_cur, *tm_ref, *tm_sum, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, d_swept, st); \
-    default: return launch_k1_sea<RR, 256>(*tm_cur, *tm_ref, *tm_sum, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, d_swept, st);  \
-    }
+#define K1S_ARGS *tm_cur, *tm_ref, *tm_mm, mbw, mbh, nframes, d_pmv, lambda, d_mv, d_cost, d_swept, st
+#define K1S_DISPATCH(RR, KC, KF)                                                                              \
+    if (k1_prune_fine()) {                                                                                    \
+        switch (k1_threads()) {                                                                               \
+        case 192: return launch_k1_sea<RR, KF, 192>(K1S_ARGS);                                                \
+        case 320: return launch_k1_sea<RR, KF, 320>(K1S_ARGS);                                                \
+        case 384: return launch_k1_sea<RR, KF, 384>(K1S_ARGS);                                                \
+        default: return launch_k1_sea<RR, KF, 256>(K1S_ARGS);                                                 \
+        }                                                                                                     \
+    }                                                                                                         \
+    return launch_k1_sea<RR, KC, 256>(K1S_ARGS);
     switch (R) {
-    case 32: K1S_DISPATCH(32)
-    case 16: K1S_DISPATCH(16)
+    case 32: K1S_DISPATCH(32, 13, 5)
+    case 16: K1S_DISPATCH(16, 11, 3)
     default:
         fprintf(stderr, "b2enc: merange %d not supported (16 or 32)\n", R);
         return -1;

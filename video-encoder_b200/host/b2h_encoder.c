@@ -301,7 +301,7 @@ b2_t *b2_encoder_open(b2_param_t *p)
     /* every GOP slot holds its GOP's raw pictures on the device: shrink the slot count to what the GPU can hold */
     {
         const size_t w16 = ((size_t)p->i_width + 15) & ~(size_t)15, h16 = ((size_t)p->i_height + 15) & ~(size_t)15;
-        const size_t per_slot = (size_t)h->L * w16 * h16 * 3 + 18 * (w16 + 128) * (h16 + 128);      /* ring (<= 3 B/px) + planes, block sums + results */
+        const size_t per_slot = (size_t)h->L * w16 * h16 * 3 + 20 * (w16 + 128) * (h16 + 128);      /* ring (<= 3 B/px) + planes, block-sum words + results */
         size_t free_b = 0, total_b = 0;
         for (int d = 0; d < h->N && h->S > 1; d++) {
             if (b2_device_mem_info(p->i_device + d, &free_b, &total_b)) continue;
