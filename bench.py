@@ -433,7 +433,7 @@ def main():
         iso, mbs, in_bytes, w16, h16 = kernels_alone(0)
 
         # ---- the same workload with the lossless search pruning on (engine option me_prune; reported beside, never instead) ----
-        if world == 1 and not args.no_pruned_leg and not args.me_prune and args.partitions != 2:
+        if world == 1 and not args.no_pruned_leg and not args.me_prune and args.partitions != 2 and MERANGE == 32:   # the engine prunes at +-32 only
             engp = make_engine(1)
             sp = 0
             for _ in range(args.warmup):

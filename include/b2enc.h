@@ -91,7 +91,8 @@ typedef struct {
                                            0 (default) = environment variable B2ENC_DEVICES, else 1                          */
     int b_me_prune;                     /* lossless pruning of the exhaustive full-pel search (successive elimination, the idea
                                            behind x264's me=esa): the stream is byte-identical with 0 and 1, only the time differs.
-                                           Default 1; the environment variable B2ENC_ME_PRUNE=0/1 overrides it                   */
+                                           Default 1; the environment variable B2ENC_ME_PRUNE=0/1 overrides it.  Takes effect for
+                                           i_merange 32 (presets slow and up); at +-16 the exhaustive kernel is the faster one      */
 } b2_param_t;
 
 typedef struct {

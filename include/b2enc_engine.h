@@ -42,7 +42,8 @@ typedef struct {
     int deblock_alpha, deblock_beta;   /* loop-filter offsets (slice_alpha_c0_offset_div2 / slice_beta_offset_div2, -6..6) */
     int me_prune;      /* 1: lossless pruning of the exhaustive full-pel search (successive elimination: candidates whose      */
                        /* block-sum lower bound exceeds an exactly evaluated cost are skipped).  Vectors, costs and tie-break  */
-                       /* are those of the exhaustive scan; the time is content dependent.  Ignored with partitions == 2.      */
+                       /* are those of the exhaustive scan; the time is content dependent.  Used for merange 32 without the    */
+                       /* wide partition search (partitions == 2); elsewhere the exhaustive kernel is the faster one and runs. */
 } b2_engine_cfg_t;
 
 b2_engine_t *b2_engine_create(const b2_engine_cfg_t *cfg);      /* NULL on error */

@@ -115,5 +115,5 @@ def test_bench_issue_path_pruned_search(oracle, b2):
     """the same path with me_prune=1 (bench.py's `pruned` leg): K1a + pruned K1 of eight stream groups overlap, the block-sum planes
     are per slot and refilled every P step; every slot of every step still equals the oracle's exhaustive search.  Plus the C3-size
     spot check."""
-    replay(oracle, b2, 96, 64, slots=16, streams=8, ring=8, gop=8, steps=28, deblock=1, me_prune=1)
+    replay(oracle, b2, 96, 64, slots=16, streams=8, ring=8, gop=8, steps=28, R=32, deblock=1, me_prune=1)
     replay(oracle, b2, 1920, 1080, slots=64, streams=8, ring=8, gop=32, steps=3, R=32, qp=26, check_slots=[0, 40], distinct=False, me_prune=1)

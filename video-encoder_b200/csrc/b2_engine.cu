@@ -196,7 +196,10 @@ static int engine_alloc(b2_engine *e)
             ENG_OK(cudaHostAlloc(&e->h_coef[s], n * sizeof(b2_mbcoef_t), cudaHostAllocDefault));
         }
     }
-    if (c.me_prune && c.partitions != 2) {                        // the wide partition search keeps the exhaustive kernel (nine minima per MB)
+    // lossless pruning of the full-pel search: +-32 only -- at +-16 the 33 x 33 candidates leave too little to prune against the
+    // per-strip costs of the bound test (measured slower than the exhaustive kernel: profiles/r2_pruned_legs.txt); the wide
+    // partition search keeps the exhaustive kernel too (nine minima per macroblock)
+    if (c.me_prune && c.partitions != 2 && c.merange == 32) {
         ENG_OK(cudaMalloc(&e->d_sum, e->stride_y * S * sizeof(uint32_t)));
         ENG_OK(cudaMemset(e->d_sum, 0, e->stride_y * S * sizeof(uint32_t)));
         ENG_OK(cudaMalloc(&e->d_k1_swept, sizeof(unsigned long long)));
