@@ -20,6 +20,10 @@ weak scaling); time = max over ranks.
   cpu_baseline  : the C oracle of the same stage on the host cores (one closed GOP per thread)
   dropin        : the same pictures through the x264-mirror call sequence (b2_encoder_encode, one picture per call,
                   host CABAC included) -- what an unmodified av_encode.c main loop would see (N=1 only)
+  pruned        : value / e2e of the same workload with the engine's lossless search pruning on (me_prune: successive
+                  elimination + partial-distortion exit in front of the same sweep; identical vectors and costs, oracle-verified),
+                  the fraction of candidate vectors that was evaluated and K1's time alone with and without it (N=1 only).
+                  Reported BESIDE the figures above, which are always the exhaustive search; never part of `roofline`
 
 `--impl reference` times that CPU implementation alone (the reference's own libx264/libswscale path
 cannot be built in this image: no headers, no libraries -- see DESIGN.md), all host threads.
@@ -418,13 +422,14 @@ def main():
         eng.close()
 
         def kernels_alone(me_prune):
-            e1 = make_engine(me_prune, profile=1, streams=1, ring=2)
+            # the same picture sequence as the timed legs (ring of RING pictures): the pruned search depends on the content
+            e1 = make_engine(me_prune, profile=1, streams=1, ring=RING)
             e1.encode(b2enc.FRAME_I, ring=0)
             for i in range(2):
-                e1.encode(b2enc.FRAME_P, ring=(i + 1) % 2)
+                e1.encode(b2enc.FRAME_P, ring=(i + 1) % RING)
             e1.sync(); e1.profile_reset()
             for i in range(8):
-                e1.encode(b2enc.FRAME_P, ring=i % 2)
+                e1.encode(b2enc.FRAME_P, ring=(i + 3) % RING)
             r = e1.kernel_ms(), e1.nmb, e1.in_bytes, e1.w16, e1.h16
             e1.close()
             return r

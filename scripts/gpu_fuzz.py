@@ -53,10 +53,13 @@ for case in range(ncases):
         elif kind == "noise": seqs.append(noise_seq(w, h, T, sd + s))
         elif kind == "flat": seqs.append(flat_seq(w, h, T, sd + s))
         else: seqs.append([b2oracle.synth_frame(w, h, t, s + sd % 7) for t in range(T)])
-    desc = f"case {case}: {w}x{h} qp {qp} R {R} subpel {subpel} intra {intra} deblock {deblock}{offs} t8 {t8} parts {parts} pack {pack} {kind} S {S} T {T} seed {sd}"
+    prune = int(os.environ.get("B2_FUZZ_PRUNE", "-1"))                   # -1: random; 1: always (with +-32: the only range the engine prunes at)
+    if prune < 0: prune = int(rng.random() < 0.5)
+    elif prune: R = 32; parts = min(parts, 1)
+    desc = f"case {case}: {w}x{h} qp {qp} R {R} subpel {subpel} intra {intra} deblock {deblock}{offs} t8 {t8} parts {parts} pack {pack} prune {prune} {kind} S {S} T {T} seed {sd}"
     try:
         run_and_compare(b2oracle, b2enc, seqs, w, h, qp, R, subpel=subpel, intra_in_p=intra, deblock=deblock, transform8x8=t8,
-                        pack_levels=pack, partitions=parts, deblock_offsets=offs)
+                        pack_levels=pack, partitions=parts, deblock_offsets=offs, me_prune=prune)
     except Exception:
         print("MISMATCH/ERROR", desc, flush=True); traceback.print_exc(); sys.exit(1)
     done += 1

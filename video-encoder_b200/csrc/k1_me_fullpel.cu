@@ -699,30 +699,47 @@ k1_me_fullpel_sea_kernel(const __grid_constant__ CUtensorMap tm_cur, const __gri
     __syncthreads();
     mbar_wait(&s_bar[1], 0);
 
-    // bound test.  A warp round = 32 consecutive dx of ONE (macroblock, dy group), so everything but the column is warp-uniform; the
-    // search range is 32 * FULL + 1 columns wide, the left-over column of all NG groups of a macroblock makes one more round
-    // (lane = group).  Survivors go to their bank's queue; entry i of all 32 queues is one row of 32 u16.
+    // bound test.  A warp takes a UNIT = (macroblock, block of 32 columns, parity of the dy group): a lane keeps its column, so the
+    // column's vector cost, the macroblock's sum and the queue number are loaded once and the groups are walked with immediate
+    // offsets (about 10 instructions per lane-task; per-lane-task decoding cost 50).  The search range is 32 * FULL + 1 columns wide:
+    // the left-over column of all NG groups of a macroblock makes one more round (lane = group).  Survivors go to their bank's
+    // queue; entry i of all 32 queues is one row of 32 u16.
     {
         constexpr int FULL = (ND - 1) / 32;
-        static_assert(FULL * 32 + 1 == ND && NG <= 32, "round layout of the bound test");
-        constexpr int RPM = NG * FULL + 1;                // rounds per macroblock
-        for (int pi = warp; pi < nmb * RPM; pi += NWARPS) {
-            const int m = pi / RPM, rr = pi - m * RPM;
-            int g, dxi;
-            bool valid = true;
-            if (rr < NG * FULL) { g = rr / FULL; dxi = (rr - g * FULL) * 32 + lane; }
-            else { g = lane; dxi = ND - 1; valid = lane < NG; }
-            if (valid) {
+        static_assert(FULL * 32 + 1 == ND && NG <= 32 && (FULL == 1 || FULL == 2), "unit layout of the bound test");
+        auto append = [&](int q, uint32_t entry) {
+            const int slot = atomicAdd(&s_cnt[q], 1);
+            if (slot < QCAP) s_queue[slot * 32 + q] = (uint16_t)entry;
+            else s_cnt[32] = 1;
+        };
+        const int units = nmb * FULL * 2;
+        for (int u = warp; u < units; u += NWARPS) {
+            const int m = u / (FULL * 2), rem = u - m * (FULL * 2), par = rem & 1;
+            const int dxi = (rem >> 1) * 32 + lane;
+            const int c = s_csum[m];
+            const int cx = (int)(s_costx[m * ND + dxi] >> 13);
+            const uint32_t *mmp = s_mm + par * Q::MP + m * 16 + dxi;
+            const int *tgp = s_tg + m * NG + par;
+            const int q = (m * 16 + dxi) & 31;
+            const uint32_t ent = (uint32_t)(m | par << 4 | dxi << 8);
+#pragma unroll
+            for (int g2 = 0; g2 < (NG + 1) / 2; g2++) {
+                if (2 * g2 + par < NG) {
+                    const int t = tgp[2 * g2] - cx;
+                    const uint32_t mm = mmp[2 * g2 * Q::MP];
+                    const int d = max((int)(mm & 0xffffu) - c, c - (int)(mm >> 16));  // distance of C to [min, max]; negative inside
+                    if (t >= 0 && d <= t) append(q, ent + (uint32_t)(2 * g2 << 4));
+                }
+            }
+        }
+        for (int m = warp; m < nmb; m += NWARPS) {
+            if (lane < NG) {
+                const int g = lane, dxi = ND - 1;
                 const int t = s_tg[m * NG + g] - (int)(s_costx[m * ND + dxi] >> 13);
                 const uint32_t mm = s_mm[g * Q::MP + m * 16 + dxi];
                 const int c = s_csum[m];
-                const int d = max((int)(mm & 0xffffu) - c, c - (int)(mm >> 16));      // distance of C to [min, max]; negative inside
-                if (t >= 0 && d <= t) {
-                    const int q = (m * 16 + dxi) & 31;
-                    const int slot = atomicAdd(&s_cnt[q], 1);
-                    if (slot < QCAP) s_queue[slot * 32 + q] = (uint16_t)(m | g << 4 | dxi << 8);
-                    else s_cnt[32] = 1;
-                }
+                const int d = max((int)(mm & 0xffffu) - c, c - (int)(mm >> 16));
+                if (t >= 0 && d <= t) append((m * 16 + dxi) & 31, (uint32_t)(m | g << 4 | dxi << 8));
             }
         }
     }
