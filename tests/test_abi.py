@@ -33,6 +33,7 @@ def test_param_and_error_conventions(b2):
     assert L.b2_param_apply_profile(C.byref(p), b"baseline") == 0 and p.b_cabac == 0  # a profile only removes tools
     assert L.b2_param_default_preset(C.byref(p), b"ultrafast", None) == 0 and (p.b_cabac, p.b_deblocking_filter) == (0, 0)
     assert L.b2_param_default_preset(C.byref(p), b"slow", None) == 0 and p.i_merange == 32
+    assert p.b_me_prune == 1                                                         # lossless search pruning: on by default, same bytes
     assert L.b2_param_default_preset(C.byref(p), b"medium", b"zerolatency") == 0 and p.i_gop_slots == 1
     # tunes as in x264: film = deblock -1:-1 (the reference's default, av_encode.c:103), several tunes separated by ','
     assert L.b2_param_default_preset(C.byref(p), b"medium", b"film") == 0

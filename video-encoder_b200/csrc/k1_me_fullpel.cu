@@ -871,9 +871,13 @@ __global__ void __launch_bounds__(256) k1a_block_sums_kernel(const uint8_t *__re
     constexpr int IR = SR + 15;                           // input rows
     constexpr int WPR = (K1A_TW + 16) / 4;                // input words per row
     constexpr int PPR = (K1A_TW + 16) / 2;                // column pairs per row
-    __shared__ uint32_t s_in[IR][WPR];
+    // the input tile is dead once the vertical sums exist: the sums of 4 columns reuse its memory (30 instead of 40 KB per CTA: seven
+    // CTAs per SM instead of five -- the kernel is a chain of short phases and lives on occupancy)
+    constexpr int A_WORDS = IR * WPR > SR * PPR ? IR * WPR : SR * PPR;
+    __shared__ uint32_t s_a[A_WORDS];
     __shared__ uint32_t s_v[SR][PPR];                     // vertical 16-sums (pairs); later the block sums themselves ([SR][K1A_TW / 2] used)
-    __shared__ uint32_t s_q[SR][PPR];                     // sums of 4 columns: pair p = (q[2p], q[2p+1])
+    uint32_t (*s_in)[WPR] = (uint32_t (*)[WPR])s_a;
+    uint32_t (*s_q)[PPR] = (uint32_t (*)[PPR])s_a;        // sums of 4 columns: pair p = (q[2p], q[2p+1])
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * K1A_TW, y0 = blockIdx.y * K1A_TH;
     const uint8_t *plane = planes + (size_t)blockIdx.z * plane_stride;
