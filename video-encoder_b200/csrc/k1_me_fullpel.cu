@@ -546,6 +546,17 @@ k1_me_fullpel_persistent_kernel(const __grid_constant__ CUtensorMap tm_cur, cons
 #ifndef B2_K1_PRUNE_MINCTAS
 #define B2_K1_PRUNE_MINCTAS 3
 #endif
+// reference rows after which the exit is tested: K + FIRST, K + FIRST + STEP, ... <= K + LAST (every candidate has then seen at least
+// FIRST + 1 rows); swept on the B200: profiles/r2_k1_pde_schedule.txt
+#ifndef B2_K1_PDE_FIRST
+#define B2_K1_PDE_FIRST 5
+#endif
+#ifndef B2_K1_PDE_LAST
+#define B2_K1_PDE_LAST 9
+#endif
+#ifndef B2_K1_PDE_STEP
+#define B2_K1_PDE_STEP 4
+#endif
 #ifndef B2_K1_PRUNE_PDE
 #define B2_K1_PRUNE_PDE 1     // partial-distortion exit inside the sweep (0: every surviving lane-task is swept to the end)
 #endif
@@ -748,7 +759,7 @@ k1_me_fullpel_sea_kernel(const __grid_constant__ CUtensorMap tm_cur, const __gri
     // one lane-task of the sweep: K candidates (dy = g*K .. g*K+K-1 at dx) of macroblock m; returns the smallest key.
     // Partial-distortion exit: a SAD only grows row by row, so once the PARTIAL key of every candidate of every lane of the warp
     // exceeds the macroblock's best key so far, none of them can become the minimum (keys are unique per candidate) and the warp
-    // drops the rest of the task; checked after reference rows 8, 12, ... (each candidate has then seen at least 4, 8, ... rows).
+    // drops the rest of the task; checked after reference rows K + 5 and K + 9 (each candidate has then seen at least 6 / 10 rows).
     auto lane_task = [&](int m, int g, int dxi, bool active) -> uint32_t {
         uint32_t cur[64];
         {
@@ -784,7 +795,7 @@ k1_me_fullpel_sea_kernel(const __grid_constant__ CUtensorMap tm_cur, const __gri
                     acc[k] = vsad4_acc(w3, cur[y * 4 + 3], acc[k]);
                 }
             }
-            if (B2_K1_PRUNE_PDE && r >= K + 3 && r <= K + 7 && ((r - (K + 3)) & 3) == 0) {
+            if (B2_K1_PRUNE_PDE && r >= K + B2_K1_PDE_FIRST && r <= K + B2_K1_PDE_LAST && ((r - (K + B2_K1_PDE_FIRST)) % B2_K1_PDE_STEP) == 0) {
                 bool hopeless = true;
                 if (active) {
                     const uint32_t bk = ((volatile uint32_t *)s_best)[m];
