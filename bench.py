@@ -22,7 +22,7 @@ weak scaling); time = max over ranks.
                   host CABAC included) -- what an unmodified av_encode.c main loop would see (N=1 only)
   pruned        : value / e2e of the same workload with the engine's lossless search pruning on (me_prune: successive
                   elimination + partial-distortion exit in front of the same sweep; identical vectors and costs, oracle-verified),
-                  the fraction of candidate vectors that was evaluated and K1's time alone with and without it (N=1 only).
+                  the fraction of candidate vectors that was evaluated and K1's time alone with and without it (any N: whole-job figures).
                   Reported BESIDE the figures above, which are always the exhaustive search; never part of `roofline`
 
 `--impl reference` times that CPU implementation alone (the reference's own libx264/libswscale path
@@ -117,15 +117,21 @@ class ClockSampler:
                 "samples": len(rows), "reasons": reasons}
 
 
+_PICTURES = {}                                                  # (frame index, stream) -> packed I420 picture: several engines get the same input
+
+
 def fill_inputs(eng, b2oracle, rank):
+    import numpy as np
     import sharding
-    n_y = W * H
     streams = sharding.slot_streams(rank, eng.slots)            # disjoint synthetic streams per rank
     for s in range(eng.slots):
         for r in range(eng.ring):
-            y, u, v = b2oracle.synth_frame(W, H, r, streams[s])
-            buf = eng.host_input(s, r)
-            buf[:n_y] = y.ravel(); buf[n_y:n_y + u.size] = u.ravel(); buf[n_y + u.size:] = v.ravel()
+            key = (W, H, r, streams[s])
+            pic = _PICTURES.get(key)
+            if pic is None:
+                y, u, v = b2oracle.synth_frame(W, H, r, streams[s])
+                pic = _PICTURES[key] = np.concatenate([y.ravel(), u.ravel(), v.ravel()])
+            eng.host_input(s, r)[:pic.size] = pic
 
 
 def dropin_leg(b2enc, b2oracle, deblock, transform8x8, partitions, frames=2048, gop_slots=None):
@@ -412,15 +418,50 @@ def main():
     clk = clocks.stop(mark)
     e2e = world * SLOTS * n_e2e / e2e_s
 
-    # ---- K1/K0 alone (one stream, nothing overlapping): the roofline numerator --------------------------
+    # ---- after the timed legs: verification of the state they left (rank 0), then the same legs with the search pruning on ------
     iso = None
     verify = None
     pruned = None
-    if rank == 0:
-        if not args.no_verify:
-            verify = verify_final_state(eng, b2enc, b2oracle, rank, groups, ftype, step - 1, args)
-        eng.close()
+    if rank == 0 and not args.no_verify:
+        verify = verify_final_state(eng, b2enc, b2oracle, rank, groups, ftype, step - 1, args)
+    eng.close()
 
+    # the same workload with the lossless search pruning on (engine option me_prune; reported beside, never instead).  Every rank
+    # runs it, timed like the legs above (device events / wall clock, barrier on both sides, max over ranks)
+    run_pruned = not args.no_pruned_leg and not args.me_prune and args.partitions != 2 and MERANGE == 32     # the engine prunes at +-32 only
+    if run_pruned:
+        engp = make_engine(1)
+        sp = 0
+        for _ in range(args.warmup):
+            issue(sp, False, engp); sp += 1
+        engp.sync()
+        sw0, al0 = engp.k1_stats()
+        barrier()
+        engp.timer_start()
+        for _ in range(args.steps):
+            issue(sp, False, engp); sp += 1
+        msp = engp.timer_stop()
+        engp.sync()
+        barrier()
+        msp = max_over_ranks(msp)
+        sw1, al1 = engp.k1_stats()
+        for _ in range(2):
+            issue(sp, True, engp); sp += 1
+        engp.sync()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            issue(sp, True, engp); sp += 1
+        engp.sync()
+        e2ep = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        vp = None
+        if rank == 0 and not args.no_verify:
+            vp = verify_final_state(engp, b2enc, b2oracle, rank, groups, ftype, sp - 1, args)
+        engp.close()
+
+    # ---- K1/K0 alone (one stream, nothing overlapping): the roofline numerator --------------------------
+    if rank == 0:
         def kernels_alone(me_prune):
             # the same picture sequence as the timed legs (ring of RING pictures): the pruned search depends on the content
             e1 = make_engine(me_prune, profile=1, streams=1, ring=RING)
@@ -436,36 +477,10 @@ def main():
 
         # the roofline kernel is ALWAYS the exhaustive one, whatever --me-prune says
         iso, mbs, in_bytes, w16, h16 = kernels_alone(0)
-
-        # ---- the same workload with the lossless search pruning on (engine option me_prune; reported beside, never instead) ----
-        if world == 1 and not args.no_pruned_leg and not args.me_prune and args.partitions != 2 and MERANGE == 32:   # the engine prunes at +-32 only
-            engp = make_engine(1)
-            sp = 0
-            for _ in range(args.warmup):
-                issue(sp, False, engp); sp += 1
-            engp.sync()
-            sw0, al0 = engp.k1_stats()
-            engp.timer_start()
-            for _ in range(args.steps):
-                issue(sp, False, engp); sp += 1
-            msp = engp.timer_stop()
-            engp.sync()
-            sw1, al1 = engp.k1_stats()
-            for _ in range(2):
-                issue(sp, True, engp); sp += 1
-            engp.sync()
-            t0 = time.perf_counter()
-            for _ in range(args.steps):
-                issue(sp, True, engp); sp += 1
-            engp.sync()
-            e2ep = time.perf_counter() - t0
-            vp = None
-            if not args.no_verify:
-                vp = verify_final_state(engp, b2enc, b2oracle, rank, groups, ftype, sp - 1, args)
-            engp.close()
+        if run_pruned:
             isop = kernels_alone(1)[0]
-            pruned = {"value": round(SLOTS * args.steps / (msp * 1e-3), 2), "unit": UNIT, "ms_per_step": round(msp / args.steps, 4),
-                      "e2e": round(SLOTS * args.steps / e2ep, 2),
+            pruned = {"value": round(world * SLOTS * args.steps / (msp * 1e-3), 2), "unit": UNIT, "n_gpus": world, "ms_per_step": round(msp / args.steps, 4),
+                      "e2e": round(world * SLOTS * args.steps / e2ep, 2),
                       "verified": vp["verified"] if vp else None, "verify_seconds": vp["seconds"] if vp else None,
                       "k1_candidates_evaluated": int(sw1 - sw0), "k1_candidates_algorithmic": int(al1 - al0),
                       "k1_executed_fraction": round((sw1 - sw0) / max(al1 - al0, 1), 4),
@@ -475,10 +490,11 @@ def main():
                       "what": "engine option me_prune=1: K1a (min | max of the reference's 16x16 block sums over the rows of a lane-task, once per P step) + "
                               "successive elimination in K1 -- a candidate whose |sum(cur) - sum(ref)| + mvcost exceeds the exact cost of the zero vector / "
                               "the rounded predictor cannot be the minimum, and a lane-task (k1_rows_per_lane_task consecutive dy at one dx) is skipped when "
-                              "that holds for all of its candidates; vectors, costs and tie-break are those of the exhaustive scan (tests/test_me_fullpel.py, the oracle "
-                              "replay above), only the time changes, and it depends on the content (this synthetic sequence pans uniformly, so the "
-                              "predictor is exact; k1_executed_fraction says how much of the exhaustive work ran).  Not part of `value`, `e2e` or "
-                              "`roofline`: those are the exhaustive search"}
+                              "that holds for all of its candidates -- plus a partial-distortion exit inside the sweep; vectors, costs and tie-break are those "
+                              "of the exhaustive scan (tests/test_me_fullpel.py, the oracle replay of this leg's final state), only the time changes, and it "
+                              "depends on the content (this synthetic sequence pans uniformly, so the predictor is exact except where the 8-picture ring "
+                              "wraps; k1_executed_fraction = candidates evaluated / candidates of the exhaustive search, rank 0).  Whole-job figures at "
+                              "n_gpus, timed like `value` / `e2e`.  Not part of `value`, `e2e` or `roofline`: those are the exhaustive search"}
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -530,8 +546,6 @@ def main():
             out["dropin"] = dropin_leg(b2enc, b2oracle, None, args.transform8x8, args.partitions)          # what av_encode.c gets
             out["dropin_named_path"] = dropin_leg(b2enc, b2oracle, 0, args.transform8x8, args.partitions)   # loop filter off like `value`
         print(json.dumps(out))
-    else:
-        eng.close()
     if dist is not None:
         dist.destroy_process_group()
 
