@@ -48,22 +48,33 @@ static const uint8_t last8_inc[63] = {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 
                                       3, 3, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 6, 6, 6, 6, 7, 7, 7, 7, 8, 8, 8};
 
 /* ---- arithmetic encoder (9.3.4.2) --------------------------------------------------------------------*/
-/* Same interval arithmetic as Figures 9-7..9-12, organised for speed: instead of one PutBit per renormalisation shift
- * (with its outstanding-bit loop) the low end of the interval is kept in a 32-bit register together with `queue + 18`
- * not-yet-written bits; whole bytes leave at once, a carry is added to the last written byte and resolved through a
- * count of outstanding 0xff bytes.  State transitions and renormalisation shifts come from small tables. */
+/* Same interval arithmetic as Figures 9-7..9-12, organised for speed (this stage is what bounds a single stream on the host:
+ * one bin is one link of a serial dependency chain):
+ *  - the interval (low, range) and the count of pending bits live in a small struct of their own that never leaves the
+ *    always-inlined coding functions, so the compiler keeps them in registers across a whole slice;
+ *  - instead of one PutBit per renormalisation shift (with its outstanding-bit loop) the low end of the interval is kept in a
+ *    64-bit register together with `queue + 18` not-yet-written bits; FOUR whole bytes leave at once (one hard-to-predict
+ *    branch and one call per 32 bits of output instead of per 8), and a carry is added to the bytes already in the buffer
+ *    (the whole RBSP is in memory, so no count of outstanding 0xff bytes is needed; a carry never leaves the first byte);
+ *  - the chain through `range` is short: an MPS renormalises by 0 or 1 bit (range - rLPS >= 128), which is an add and a
+ *    select; for an LPS the renormalised range and its shift depend on (state, range quarter) only and come from tables. */
 typedef struct {
-    uint8_t *p, *start, *end;   /* output cursor inside the RBSP buffer                         */
-    uint32_t low, range;
-    int queue;                  /* bits pending in `low` beyond the last byte boundary, minus 18 */
-    int outstanding;            /* 0xff bytes waiting for a possible carry                      */
+    uint8_t *p, *start, *end;   /* output cursor inside the RBSP buffer */
     int overflow;
     uint16_t state[1024];       /* (pStateIdx << 1) | valMPS.  Not a byte type on purpose: a store through a character type may alias
-                                 * low / range / queue, which would force the compiler to reload them after every bin */
+                                 * everything else, which would force the compiler to reload pointers and tables after every bin */
 } cabac_t;
+typedef struct {
+    uint64_t low;
+    uint32_t range;
+    int queue;                  /* bits pending in `low` beyond the last byte boundary, minus 18 */
+} cabac_reg_t;
+#define CABAC_INLINE static inline __attribute__((always_inline))
 
-static uint8_t cabac_next[128][2];          /* state after coding bin b in state s */
-static uint8_t cabac_shift[64];             /* renormalisation shift for range >> 3 */
+static uint8_t cabac_next[128][2];          /* state after coding bin b in state s                          */
+static uint8_t cabac_lps[128][4];           /* rangeTabLPS by (state, range quarter)                        */
+static uint16_t cabac_lps_norm[128][4];     /* the same, renormalised (<< cabac_lps_shift)                  */
+static uint8_t cabac_lps_shift[128][4];
 static pthread_once_t cabac_tables_once = PTHREAD_ONCE_INIT;      /* slices are written by several entropy workers */
 
 static void cabac_tables(void)
@@ -72,101 +83,112 @@ static void cabac_tables(void)
         const int ps = st >> 1, mps = st & 1;
         cabac_next[st][mps] = (uint8_t)(((ps < 62 ? ps + 1 : 62) << 1) | mps);
         cabac_next[st][1 - mps] = (uint8_t)((trans_lps[ps] << 1) | (ps == 0 ? 1 - mps : mps));
-    }
-    for (int i = 0; i < 64; i++) {
-        int r = i << 3, sh = 0;
-        if (r == 0) r = 6;                   /* the smallest range that can occur is 6 (LPS of the top states) */
-        while ((r << sh) < 256) sh++;
-        cabac_shift[i] = (uint8_t)sh;
+        for (int q = 0; q < 4; q++) {
+            int r = range_lps[ps][q], sh = 0;
+            while ((r << sh) < 256) sh++;
+            cabac_lps[st][q] = (uint8_t)r; cabac_lps_norm[st][q] = (uint16_t)(r << sh); cabac_lps_shift[st][q] = (uint8_t)sh;
+        }
     }
 }
 
-static void cabac_init(cabac_t *c, bs_t *bs, int table, int qp)
+static void cabac_init(cabac_t *c, cabac_reg_t *r, bs_t *bs, int table, int qp)
 {
     pthread_once(&cabac_tables_once, cabac_tables);
-    c->p = c->start = bs->buf + bs->pos; c->end = bs->buf + bs->cap;
-    c->low = 0; c->range = 510; c->queue = -9; c->outstanding = 0; c->overflow = 0;     /* the first bit is not written */
+    c->p = c->start = bs->buf + bs->pos; c->end = bs->buf + bs->cap; c->overflow = 0;
+    r->low = 0; r->range = 510; r->queue = -9;                                           /* the first bit is not written */
     for (int i = 0; i < 1024; i++) {
         int pre = ((b2h_cabac_ctx_init[table][i][0] * qp) >> 4) + b2h_cabac_ctx_init[table][i][1];
         pre = pre < 1 ? 1 : (pre > 126 ? 126 : pre);
         c->state[i] = pre <= 63 ? (uint16_t)((63 - pre) << 1) : (uint16_t)(((pre - 64) << 1) | 1);
     }
 }
-/* one finished byte (plus a possible carry in bit 8) leaves the register */
-static inline void cabac_emit(cabac_t *c, uint32_t out)
+/* a carry out of the pending bits goes into the bytes already written */
+static inline void cabac_carry(cabac_t *c)
 {
-    if ((out & 0xff) == 0xff) { c->outstanding++; return; }
-    const uint32_t carry = out >> 8;
-    if (c->p + c->outstanding + 1 >= c->end) { c->overflow = 1; c->outstanding = 0; return; }
-    if (carry && c->p > c->start) c->p[-1]++;               /* cannot ripple further: an 0xff byte would have been held back */
-    while (c->outstanding > 0) { *c->p++ = (uint8_t)(carry - 1); c->outstanding--; }
-    *c->p++ = (uint8_t)out;
+    uint8_t *q = c->p;
+    while (q > c->start && ++*--q == 0) ;
 }
-static inline void cabac_putbyte(cabac_t *c)
+/* four finished bytes (plus a possible carry in bit 32) leave the register */
+static __attribute__((noinline)) void cabac_flush4(cabac_t *c, uint64_t out)
 {
-    if (c->queue >= 0) {
-        const uint32_t out = c->low >> (c->queue + 10);
-        c->low &= (0x400u << c->queue) - 1;
-        c->queue -= 8;
-        cabac_emit(c, out);
+    if (c->p + 4 > c->end) { c->overflow = 1; return; }
+    if (out >> 32) cabac_carry(c);
+    c->p[0] = (uint8_t)(out >> 24); c->p[1] = (uint8_t)(out >> 16); c->p[2] = (uint8_t)(out >> 8); c->p[3] = (uint8_t)out;
+    c->p += 4;
+}
+CABAC_INLINE void cabac_put(cabac_t *c, cabac_reg_t *r)
+{
+    if (__builtin_expect(r->queue >= 24, 0)) {
+        const int keep = r->queue - 24 + 10;                 /* bits that stay: the 10-bit window and the pending bits below 32 */
+        const uint64_t out = r->low >> keep;
+        r->low &= ((uint64_t)1 << keep) - 1;
+        r->queue -= 32;
+        cabac_flush4(c, out);
     }
 }
-static inline void cabac_encode(cabac_t *c, int ctx, int bin)
+CABAC_INLINE void cabac_encode_r(cabac_t *c, cabac_reg_t *r, int ctx, int bin)
 {
     const unsigned st = c->state[ctx];
-    const uint32_t rlps = range_lps[st >> 1][(c->range >> 6) & 3];
-    const uint32_t rmps = c->range - rlps;
+    const unsigned idx = st * 4 + ((r->range >> 6) & 3);
+    const uint32_t rlps = (&cabac_lps[0][0])[idx];
+    const uint32_t rmps = r->range - rlps;
     const uint32_t lps = 0u - (uint32_t)((bin ^ st) & 1);              /* all ones when the bin is the less probable symbol: */
-    c->low += rmps & lps;                                              /* no branch on a value that is hard to predict     */
-    uint32_t range = rmps ^ ((rmps ^ rlps) & lps);
-    c->state[ctx] = cabac_next[st][bin];
-    const int sh = cabac_shift[range >> 3];
-    c->range = range << sh; c->low <<= sh; c->queue += sh;
-    cabac_putbyte(c);
+    c->state[ctx] = cabac_next[st][bin];                               /* no branch on a value that is hard to predict     */
+    const unsigned sh_m = (rmps >> 8) ^ 1;                             /* rmps is in [128, 510): one shift at most */
+    const uint32_t range_m = rmps << sh_m;
+    const uint32_t range_l = (&cabac_lps_norm[0][0])[idx];
+    const unsigned sh_l = (&cabac_lps_shift[0][0])[idx];
+    const unsigned sh = sh_m ^ ((sh_m ^ sh_l) & lps);
+    r->range = range_m ^ ((range_m ^ range_l) & lps);
+    r->low = (r->low + (rmps & lps)) << sh;
+    r->queue += (int)sh;
+    cabac_put(c, r);
 }
-static inline void cabac_bypass(cabac_t *c, int bin)
+CABAC_INLINE void cabac_bypass_r(cabac_t *c, cabac_reg_t *r, int bin)
 {
-    c->low <<= 1;
-    if (bin) c->low += c->range;
-    c->queue += 1;
-    cabac_putbyte(c);
+    r->low <<= 1;
+    if (bin) r->low += r->range;
+    r->queue += 1;
+    cabac_put(c, r);
 }
 /* end_of_slice_flag / I_PCM flag.  bin = 1 also flushes (9.3.4.5): all pending bits of `low` are written, the lowest one
  * forced to 1 -- it is the rbsp_stop_one_bit -- and the last byte is padded with zeros */
-static void cabac_terminate(cabac_t *c, int bin)
+CABAC_INLINE void cabac_terminate_r(cabac_t *c, cabac_reg_t *r, int bin)
 {
-    c->range -= 2;
+    r->range -= 2;
     if (!bin) {
-        const int sh = cabac_shift[c->range >> 3];
-        c->range <<= sh; c->low <<= sh; c->queue += sh;
-        cabac_putbyte(c);
+        const int sh = __builtin_clz(r->range) - 23;         /* range >= 254 here: 0 or 1 */
+        r->range <<= sh; r->low <<= sh; r->queue += sh;
+        cabac_put(c, r);
         return;
     }
-    c->low += c->range;
-    c->low |= 1;
-    int nb = c->queue + 18;                                  /* pending bits (a carry may sit above them) */
+    r->low += r->range;
+    r->low |= 1;
+    int nb = r->queue + 18;                                  /* pending bits (a carry may sit above them); at most 49 */
     const int pad = (8 - (nb & 7)) & 7;
-    uint64_t v = (uint64_t)c->low << pad;
+    const uint64_t v = r->low << pad;
     nb += pad;
-    while (nb > 0) {
-        cabac_emit(c, (uint32_t)(v >> (nb - 8)));
-        v &= ((uint64_t)1 << (nb - 8)) - 1;
-        nb -= 8;
-    }
-    while (c->outstanding > 0 && c->p < c->end) { *c->p++ = 0xff; c->outstanding--; }
+    if (c->p + nb / 8 > c->end) { c->overflow = 1; return; }
+    if (v >> nb) cabac_carry(c);
+    while (nb > 0) { nb -= 8; *c->p++ = (uint8_t)(v >> nb); }
 }
 /* k-th order Exp-Golomb suffix in bypass mode (9.3.2.3) */
-static void cabac_egk(cabac_t *c, unsigned v, int k)
+CABAC_INLINE void cabac_egk_r(cabac_t *c, cabac_reg_t *r, unsigned v, int k)
 {
     for (;;) {
-        if (v >= (1u << k)) { cabac_bypass(c, 1); v -= 1u << k; k++; }
+        if (v >= (1u << k)) { cabac_bypass_r(c, r, 1); v -= 1u << k; k++; }
         else {
-            cabac_bypass(c, 0);
-            while (k--) cabac_bypass(c, (int)((v >> k) & 1));
+            cabac_bypass_r(c, r, 0);
+            while (k--) cabac_bypass_r(c, r, (int)((v >> k) & 1));
             break;
         }
     }
 }
+/* every coding function below has the coder `c` and the interval registers `r` in scope under these names */
+#define cabac_encode(c, ctx, bin) cabac_encode_r(c, r, ctx, bin)
+#define cabac_bypass(c, bin) cabac_bypass_r(c, r, bin)
+#define cabac_terminate(c, bin) cabac_terminate_r(c, r, bin)
+#define cabac_egk(c, v, k) cabac_egk_r(c, r, v, k)
 
 /* ---- residual_block_cabac (7.3.5.3.3) -----------------------------------------------------------------*/
 /* l[0..maxn) in scan order.  cbf_inc < 0: coded_block_flag is not sent (cat 5).  Returns the number of non-zero levels. */
@@ -181,7 +203,7 @@ static inline int levels_any(const int16_t *l, int n)
 }
 
 /* always inlined: `cat` and `maxn` are constants at every call site, so the context selection folds away */
-static inline __attribute__((always_inline)) int cabac_residual(cabac_t *c, int cat, const int16_t *l, int maxn, int cbf_inc)
+CABAC_INLINE int cabac_residual(cabac_t *c, cabac_reg_t *r, int cat, const int16_t *l, int maxn, int cbf_inc)
 {
     int last = -1;
     if (levels_any(l, maxn)) { last = maxn - 1; while (!l[last]) last--; }
@@ -247,7 +269,7 @@ static inline int cbf_term(int availN, int flagN, int cur_intra)
     return flagN > 0;
 }
 
-static void cabac_mvd(cabac_t *c, int base, int sum, int v)
+CABAC_INLINE void cabac_mvd(cabac_t *c, cabac_reg_t *r, int base, int sum, int v)
 {
     const unsigned a = (unsigned)abs(v);
     const unsigned pre = a < 9 ? a : 9;
@@ -263,7 +285,7 @@ static void cabac_mvd(cabac_t *c, int base, int sum, int v)
 
 /* mb_type of an intra macroblock: I-slice binarisation (Table 9-36) with the context layout of I slices
  * (base 3, first bin with neighbour increment) or of the intra suffix in P slices (base 17) */
-static void cabac_mb_type_intra(cabac_t *c, const b2_mbinfo_t *m, int is_p, int inc0)
+CABAC_INLINE void cabac_mb_type_intra(cabac_t *c, cabac_reg_t *r, const b2_mbinfo_t *m, int is_p, int inc0)
 {
     const int i16 = m->mb_type == B2_MB_I16x16;
     const int b0 = is_p ? 17 : 3 + inc0;
@@ -285,13 +307,14 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
 {
     bs_t bs, *b = &bs;
     cabac_t cb, *c = &cb;
+    cabac_reg_t rg, *r = &rg;
     const int mbw = e->mbw, mbh = e->mbh, nmb = mbw * mbh, is_p = frame_type == B2_FRAME_P;
     const int ys = 4 * mbw, cs = 2 * mbw;
     const uint8_t *blk_x = b2h_blk_x, *blk_y = b2h_blk_y;
     bs_init(b, e->rbsp, e->rbsp_cap);
     b2h_slice_header(b, s, is_p, frame_num, idr_pic_id);
     if (b->nbits) bs_put(b, 8 - b->nbits, (1u << (8 - b->nbits)) - 1);    /* cabac_alignment_one_bit */
-    cabac_init(c, b, is_p ? 1 : 0, s->qp);                                  /* cabac_init_idc 0 */
+    cabac_init(c, r, b, is_p ? 1 : 0, s->qp);                                  /* cabac_init_idc 0 */
 
     for (int mby = 0; mby < mbh; mby++)
         for (int mbx = 0; mbx < mbw; mbx++) {
@@ -350,7 +373,7 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
                         for (int k = 0; k < 2; k++) {
                             /* |mvd| of the 4x4 blocks left of / above the partition (0 outside the picture, in intra and skipped MBs) */
                             const int sum = (x4 > 0 ? e->mvd[k][y4 * ys + x4 - 1] : 0) + (y4 > 0 ? e->mvd[k][(y4 - 1) * ys + x4] : 0);
-                            cabac_mvd(c, k ? 47 : 40, sum, d[k]);
+                            cabac_mvd(c, r, k ? 47 : 40, sum, d[k]);
                         }
                         const int ax = abs(d[0]) > 255 ? 255 : abs(d[0]), ay = abs(d[1]) > 255 ? 255 : abs(d[1]);
                         for (int r = 0; r < ph; r++) { memset(e->mvd[0] + (y4 + r) * ys + x4, ax, (size_t)pw); memset(e->mvd[1] + (y4 + r) * ys + x4, ay, (size_t)pw); }
@@ -364,7 +387,7 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
                 }
                 /* ctxIdxInc of the first mb_type bin in I slices: neighbour is available and not I_NxN */
                 const int nxnA = (nb.fA & B2H_MBF_INTRA) && !(nb.fA & B2H_MBF_I16), nxnB = (nb.fB & B2H_MBF_INTRA) && !(nb.fB & B2H_MBF_I16);
-                cabac_mb_type_intra(c, m, is_p, (nb.availA && !nxnA) + (nb.availB && !nxnB));
+                cabac_mb_type_intra(c, r, m, is_p, (nb.availA && !nxnA) + (nb.availB && !nxnB));
                 if (m->mb_type != B2_MB_I16x16) {
                     if (s->transform8x8) cabac_encode(c, 399 + ((nb.fA & B2H_MBF_T8) != 0) + ((nb.fB & B2H_MBF_T8) != 0), t8);
                     const int step = t8 ? 4 : 1;
@@ -422,7 +445,7 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
             if (m->mb_type == B2_MB_I16x16) {
                 const int fa = nb.availA ? ((nb.fA & B2H_MBF_I16) ? ((nb.fA & B2H_MBF_DC_Y) != 0) : -1) : 0;
                 const int fb = nb.availB ? ((nb.fB & B2H_MBF_I16) ? ((nb.fB & B2H_MBF_DC_Y) != 0) : -1) : 0;
-                if (cabac_residual(c, 0, cblk[24], 16, cbf_term(nb.availA, fa, 1) + 2 * cbf_term(nb.availB, fb, 1))) flags |= B2H_MBF_DC_Y;
+                if (cabac_residual(c, r, 0, cblk[24], 16, cbf_term(nb.availA, fa, 1) + 2 * cbf_term(nb.availB, fb, 1))) flags |= B2H_MBF_DC_Y;
             }
             if (cbp_l) {
                 for (int k = 0; k < 16; k++) {
@@ -430,7 +453,7 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
                     const int x = mbx * 4 + blk_x[k], y = mby * 4 + blk_y[k];
                     if (t8) {
                         if (k & 3) continue;
-                        const int n = cabac_residual(c, 5, cblk[k], 64, -1);
+                        const int n = cabac_residual(c, r, 5, cblk[k], 64, -1);
                         const uint8_t v = (uint8_t)(n > 16 ? 16 : (n ? n : 1));        /* cbp bit set: coded_block_flag inferred 1 */
                         e->nnz_y[y * ys + x] = e->nnz_y[y * ys + x + 1] = e->nnz_y[(y + 1) * ys + x] = e->nnz_y[(y + 1) * ys + x + 1] = v;
                         continue;
@@ -439,9 +462,9 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
                     const int ta = cbf_term(x > 0, x > 0 ? e->nnz_y[y * ys + x - 1] : 0, intra);
                     const int tb = cbf_term(y > 0, y > 0 ? e->nnz_y[(y - 1) * ys + x] : 0, intra);
                     if (m->mb_type == B2_MB_I16x16)
-                        e->nnz_y[y * ys + x] = (uint8_t)cabac_residual(c, 1, cblk[k] + 1, 15, ta + 2 * tb);
+                        e->nnz_y[y * ys + x] = (uint8_t)cabac_residual(c, r, 1, cblk[k] + 1, 15, ta + 2 * tb);
                     else
-                        e->nnz_y[y * ys + x] = (uint8_t)cabac_residual(c, 2, cblk[k], 16, ta + 2 * tb);
+                        e->nnz_y[y * ys + x] = (uint8_t)cabac_residual(c, r, 2, cblk[k], 16, ta + 2 * tb);
                 }
             }
             if (cbp_c) {
@@ -449,7 +472,7 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
                     const int bit = p ? B2H_MBF_DC_V : B2H_MBF_DC_U;
                     const int fa = nb.availA ? ((nb.cbpA >> 4) ? ((nb.fA & bit) != 0) : -1) : 0;
                     const int fb = nb.availB ? ((nb.cbpB >> 4) ? ((nb.fB & bit) != 0) : -1) : 0;
-                    if (cabac_residual(c, 3, cblk[25] + 4 * p, 4, cbf_term(nb.availA, fa, intra) + 2 * cbf_term(nb.availB, fb, intra)))
+                    if (cabac_residual(c, r, 3, cblk[25] + 4 * p, 4, cbf_term(nb.availA, fa, intra) + 2 * cbf_term(nb.availB, fb, intra)))
                         flags |= bit;
                 }
                 if (cbp_c == 2)
@@ -458,7 +481,7 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
                             const int x = mbx * 2 + (k & 1), y = mby * 2 + (k >> 1);
                             const int ta = cbf_term(x > 0, x > 0 ? e->nnz_c[p][y * cs + x - 1] : 0, intra);
                             const int tb = cbf_term(y > 0, y > 0 ? e->nnz_c[p][(y - 1) * cs + x] : 0, intra);
-                            e->nnz_c[p][y * cs + x] = (uint8_t)cabac_residual(c, 4, cblk[16 + 4 * p + k] + 1, 15, ta + 2 * tb);
+                            e->nnz_c[p][y * cs + x] = (uint8_t)cabac_residual(c, r, 4, cblk[16 + 4 * p + k] + 1, 15, ta + 2 * tb);
                         }
             }
             e->mbf[mi] = (uint8_t)flags;
