@@ -129,17 +129,17 @@ CABAC_INLINE void cabac_put(cabac_t *c, cabac_reg_t *r)
 CABAC_INLINE void cabac_encode_r(cabac_t *c, cabac_reg_t *r, int ctx, int bin)
 {
     const unsigned st = c->state[ctx];
-    const unsigned idx = st * 4 + ((r->range >> 6) & 3);
+    const unsigned idx = st * 4 + (r->range >> 6) - 4;                 /* range is in [256, 510]: range >> 6 = 4..7 */
     const uint32_t rlps = (&cabac_lps[0][0])[idx];
-    const uint32_t rmps = r->range - rlps;
     const uint32_t lps = 0u - (uint32_t)((bin ^ st) & 1);              /* all ones when the bin is the less probable symbol: */
-    c->state[ctx] = cabac_next[st][bin];                               /* no branch on a value that is hard to predict     */
-    const unsigned sh_m = (rmps >> 8) ^ 1;                             /* rmps is in [128, 510): one shift at most */
-    const uint32_t range_m = rmps << sh_m;
-    const uint32_t range_l = (&cabac_lps_norm[0][0])[idx];
+    const uint32_t range_l = (&cabac_lps_norm[0][0])[idx] & lps;       /* no branch on a value that is hard to predict     */
     const unsigned sh_l = (&cabac_lps_shift[0][0])[idx];
+    c->state[ctx] = cabac_next[st][bin];
+    const uint32_t rmps = r->range - rlps;                             /* in [128, 510): an MPS shifts by one bit at most */
+    const unsigned sh_m = (rmps >> 8) ^ 1;
+    const uint32_t range_m = (rmps & 0x100) ? rmps : rmps + rmps;
     const unsigned sh = sh_m ^ ((sh_m ^ sh_l) & lps);
-    r->range = range_m ^ ((range_m ^ range_l) & lps);
+    r->range = (range_m & ~lps) | range_l;
     r->low = (r->low + (rmps & lps)) << sh;
     r->queue += (int)sh;
     cabac_put(c, r);
@@ -189,6 +189,27 @@ CABAC_INLINE void cabac_egk_r(cabac_t *c, cabac_reg_t *r, unsigned v, int k)
 #define cabac_bypass(c, bin) cabac_bypass_r(c, r, bin)
 #define cabac_terminate(c, bin) cabac_terminate_r(c, r, bin)
 #define cabac_egk(c, v, k) cabac_egk_r(c, r, v, k)
+
+/* Test hooks (tests/test_cabac_coder.py; not part of the C-ABI): the arithmetic coder alone on a caller-made list of bins,
+ * compared there with a literal transcription of Figures 9-7..9-12.  op = ctxIdx << 2 | bin, ctxIdx 1024 = bypass,
+ * 1025 = terminate; state[] = (pStateIdx << 1) | valMPS per context.  Returns the bytes written (0 on overflow). */
+size_t b2h_cabac_code_bins(const uint32_t *ops, size_t n, const uint8_t *state, uint8_t *out, size_t cap)
+{
+    cabac_t cb, *c = &cb;
+    cabac_reg_t rg = {0, 510, -9}, *r = &rg;
+    pthread_once(&cabac_tables_once, cabac_tables);
+    c->p = c->start = out; c->end = out + cap; c->overflow = 0;
+    for (int i = 0; i < 1024; i++) c->state[i] = state[i];
+    for (size_t i = 0; i < n; i++) {
+        const unsigned ctx = ops[i] >> 2;
+        const int bin = (int)(ops[i] & 1);
+        if (ctx < 1024) cabac_encode(c, (int)ctx, bin);
+        else if (ctx == 1024) cabac_bypass(c, bin);
+        else cabac_terminate(c, bin);
+    }
+    return c->overflow ? 0 : (size_t)(c->p - c->start);
+}
+const uint8_t *b2h_cabac_table(int which) { return which == 0 ? &range_lps[0][0] : trans_lps; }      /* 64 x 4, 64 */
 
 /* ---- residual_block_cabac (7.3.5.3.3) -----------------------------------------------------------------*/
 /* l[0..maxn) in scan order.  cbf_inc < 0: coded_block_flag is not sent (cat 5).  Returns the number of non-zero levels. */
