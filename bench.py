@@ -172,7 +172,7 @@ def dropin_leg(b2enc, b2oracle, deblock, transform8x8, partitions, frames=2048, 
             "deblocking_filter": "x264 default (on, tune film -1:-1)" if deblock is None else bool(deblock),
             "first_output_after_pictures": first, "first_output_after_ms": round(first_ms, 1) if first_ms else None,
             "first_output_note": "one GOP fill is not needed: a GOP starts with its first picture; the first frame is an IDR whose host CABAC takes "
-                                 "~45 ms at 1080p, during which this producer (one picture per ~0.35 ms) keeps handing pictures in",
+                                 "tens of ms at 1080p, during which this producer keeps handing pictures in",
             "host_cores": os.cpu_count(),
             "api": "b2_param_default_preset / b2_encoder_open / b2_picture_alloc / b2_encoder_encode / b2_encoder_delayed_frames "
                    "(x264 mirror, include/b2enc.h) with b2_sws_scale(decoder picture -> pic_in) in front of every encode call, as av_encode.c:545-547/:970 does; driven from Python: one picture per call, pipeline fill and drain inside the timed region",

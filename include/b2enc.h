@@ -70,7 +70,7 @@ typedef struct {
     struct { int i_rc_method; float f_rf_constant; int i_qp_constant; } rc;
     /* extensions (not in the reference; defaults chosen by b2_param_default_preset) */
     int i_keyint_max;                   /* closed-GOP length                                    */
-    int i_gop_slots;                    /* closed GOPs in flight per GPU, each on its own CUDA stream (default 16; 1 = zero delay) */
+    int i_gop_slots;                    /* closed GOPs in flight per GPU, each on its own CUDA stream (default 32; 1 = zero delay) */
     int i_merange;                      /* 16 or 32                                             */
     int b_subpel;                       /* half + quarter-pel refinement                        */
     int b_intra_in_p;

@@ -225,9 +225,11 @@ def test_randomised_call_sequences(oracle, b2mod, mock):
         assert bs == ref, "case %d: %dx%d gop %d slots %d devices %d frames %d" % (case, w, h, gop, slots, devices, n)
 
 
-def test_large_picture_staging_copy_is_threaded_and_exact(oracle, b2mod, mock):
-    """pictures of 2 MB and more are staged by the caller plus helper threads (rows split per plane, host/b2h_sws.c) into the
-    double-buffered page-locked staging: strided 1080p yuyv422 source (4 MB), stream == oracle encoder's on the converted pictures"""
+@pytest.mark.parametrize("fmt", ["yuyv422", "yuv420p", "nv12"])
+def test_large_picture_staging_copy_is_threaded_and_exact(oracle, b2mod, mock, fmt):
+    """pictures of 2 MB and more are staged by the caller plus helper threads (every thread takes its rows of every plane, one
+    post per picture, host/b2h_sws.c) into the double-buffered page-locked staging: strided 1080p sources (one, two and three
+    planes), stream == oracle encoder's on the converted pictures"""
     w, h, n, gop = 1920, 1080, 3, 2
     base = [oracle.synth_frame(w, h, t, 3) for t in range(n)]
     os.environ["B2_MOCK_DEVICES"] = "1"
@@ -236,9 +238,9 @@ def test_large_picture_staging_copy_is_threaded_and_exact(oracle, b2mod, mock):
         enc = b2mod.DropInEncoder(w, h, library=mock, preset="ultrafast", tune="film", quality=38, annexb=1, i_keyint_max=gop, i_gop_slots=2)
         out, conv = [], []
         for t, (y, u, v) in enumerate(base):
-            planes = to_fmt("yuyv422", y, u, v)                   # row pitch 2*w + 12: every row is a separate copy
-            conv.append(oracle.convert_to_i420("yuyv422", w, h, planes))
-            r = enc.encode_via_sws("yuyv422", planes, t)
+            planes = to_fmt(fmt, y, u, v)                         # padded row pitch: every row is a separate copy
+            conv.append(oracle.convert_to_i420(fmt, w, h, planes))
+            r = enc.encode_via_sws(fmt, planes, t)
             if r[0] > 0: out.append(r[1])
         while enc.delayed() > 0:
             out.append(enc.encode(None, 0)[1])

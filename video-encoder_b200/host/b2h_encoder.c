@@ -26,6 +26,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 #include "b2enc.h"
 #include "b2enc_engine.h"
@@ -45,11 +46,16 @@ typedef struct {
 
 #define B2_MAX_WORKERS 64
 #define B2_MAX_DEVICES 16
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
+static double thread_cpu_s(void) { struct timespec t; clock_gettime(CLOCK_THREAD_CPUTIME_ID, &t); return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec; }
 
 /* one frame to entropy-code; the per-MB decisions (as the 24-byte records that crossed PCIe; the worker expands them) and the
  * packed levels are heap copies of the engine's pinned result set, so the GPU may run ahead of the entropy workers (the engine
  * keeps only two result sets per slot) */
-typedef struct { int64_t frame; int t; int64_t gop_index; uint8_t *res; size_t packed_bytes; } job_t;
+typedef struct { int64_t frame; int t; int64_t gop_index; uint8_t *res; size_t res_cap, packed_bytes; } job_t;
+/* The copies are 1-4 MB each and come and go thousands of times per second: they are recycled through a small pool instead
+ * of malloc/free, which at this size is an mmap + page faults + munmap (a TLB shoot-down across all the process's threads). */
+#define B2_RES_POOL 96
 
 enum { SLOT_FREE = 0, SLOT_OPEN = 1 /* pictures still arriving */, SLOT_CLOSED = 2 /* the GOP's last picture is in */ };
 typedef struct {
@@ -86,6 +92,9 @@ struct b2_encoder {
     uint8_t *wscratch[B2_MAX_WORKERS];
     b2_mbinfo_t *winfo[B2_MAX_WORKERS];   /* the worker's expanded decision records */
     job_t *jobs;                /* ring */
+    uint8_t *pool[B2_RES_POOL]; /* idle result-copy buffers */
+    size_t pool_cap[B2_RES_POOL];
+    int pool_n;
     int job_cap, job_head, job_count, job_limit;
     outframe_t *fifo;           /* frame f lives in fifo[f % fifo_cap]                          */
     int fifo_cap;
@@ -99,6 +108,11 @@ struct b2_encoder {
     uint8_t *scratch;
     size_t scratch_cap;
     uint8_t *ret_buf;           /* payload of the frame returned by the last call */
+    /* B2ENC_STATS=1: where the threads' time went, printed by b2_encoder_close (seconds; worker_busy under mu) */
+    int stats;
+    double st_open, st_caller_slot_wait, st_caller_put, st_worker_busy;
+    double st_dev_cpu[B2_MAX_DEVICES], st_dev_copy[B2_MAX_DEVICES], st_dev_gpu_wait[B2_MAX_DEVICES], st_dev_idle[B2_MAX_DEVICES];
+    long st_dev_rounds[B2_MAX_DEVICES];
     b2_nal_t nals[3];
 };
 
@@ -195,7 +209,7 @@ int b2_param_default_preset(b2_param_t *p, const char *preset, const char *tune)
     p->rc.i_rc_method = B2_RC_CRF; p->rc.f_rf_constant = 23.0f; p->rc.i_qp_constant = 26;
     p->b_annexb = 1;
     /* 16 closed GOPs in flight per GPU: fewer leave the GPU waiting on the per-frame latency chain (K7 / K8) */
-    p->i_keyint_max = 32; p->i_gop_slots = 16; p->i_device = 0; p->i_devices = 0; p->b_me_prune = 1; p->i_csp_in = B2_FMT_YUV420P;
+    p->i_keyint_max = 32; p->i_gop_slots = 32; p->i_device = 0; p->i_devices = 0; p->b_me_prune = 1; p->i_csp_in = B2_FMT_YUV420P;
     p->b_deblocking_filter = 1;
     p->b_cabac = 1;                      /* x264 default at every preset but ultrafast */
     p->b_transform_8x8 = 0;
@@ -267,6 +281,7 @@ b2_t *b2_encoder_open(b2_param_t *p)
     if (!h) return NULL;
     h->p = *p;
     h->g_slot = -1;
+    { const char *ev = getenv("B2ENC_STATS"); h->stats = ev && atoi(ev) > 0; h->st_open = now_s(); }
     int qp = p->rc.i_rc_method == B2_RC_CQP ? p->rc.i_qp_constant : (int)(p->rc.f_rf_constant + 0.5f);
     if (qp < 10 || qp > 51)
         fprintf(stderr, "b2enc: quality %d is outside the supported constant-QP range, using %d\n", qp, qp < 10 ? 10 : 51);
@@ -387,10 +402,21 @@ void b2_encoder_close(b2_t *h)
     for (int d = 0; d < h->N; d++)
         if (h->dev[d].started) pthread_join(h->dev[d].thread, NULL);
     for (int i = 0; i < h->nworkers; i++) pthread_join(h->workers[i], NULL);
+    if (h->stats && h->S > 1) {
+        const double wall = now_s() - h->st_open;
+        fprintf(stderr, "b2enc stats: %lld frames, %.3f s since open | caller: %.3f s waiting for a GOP slot / the fifo, %.3f s handing pictures over | "
+                        "%d entropy workers: %.3f s busy in total (%.2f ms per frame)\n", (long long)h->frames_in, wall, h->st_caller_slot_wait,
+                h->st_caller_put, h->nworkers, h->st_worker_busy, h->frames_in ? 1e3 * h->st_worker_busy / (double)h->frames_in : 0.0);
+        for (int d = 0; d < h->N; d++)
+            fprintf(stderr, "b2enc stats: GPU thread %d: %.3f s CPU, of it %.3f s copying result sets out of pinned memory; asleep %.3f s on a result set, "
+                            "%.3f s without work; %ld rounds\n", h->dev[d].device, h->st_dev_cpu[d], h->st_dev_copy[d], h->st_dev_gpu_wait[d],
+                    h->st_dev_idle[d], h->st_dev_rounds[d]);
+    }
     for (int i = 0; i < B2_MAX_WORKERS; i++) { b2h_entropy_destroy(h->went[i]); free(h->wscratch[i]); free(h->winfo[i]); }
     if (h->jobs)
         for (int i = 0; i < h->job_count; i++) free(h->jobs[(h->job_head + i) % h->job_cap].res);     /* queued, never coded */
     free(h->jobs);
+    for (int i = 0; i < h->pool_n; i++) free(h->pool[i]);
     if (h->fifo)
         for (int i = 0; i < h->fifo_cap; i++) free(h->fifo[i].data);
     free(h->fifo);
@@ -403,6 +429,39 @@ void b2_encoder_close(b2_t *h)
     pthread_mutex_destroy(&h->mu);
     pthread_cond_destroy(&h->cv_job); pthread_cond_destroy(&h->cv_space); pthread_cond_destroy(&h->cv_out);
     free(h);
+}
+
+/* ---- result-copy buffers ------------------------------------------------------------------------------------------- */
+/* smallest idle buffer that holds `need` bytes (P frames leave the few large ones to the I frames), else a new one */
+static uint8_t *res_take(b2_t *h, size_t need, size_t *cap)
+{
+    uint8_t *buf = NULL;
+    pthread_mutex_lock(&h->mu);
+    int best = -1;
+    for (int i = 0; i < h->pool_n; i++)
+        if (h->pool_cap[i] >= need && (best < 0 || h->pool_cap[i] < h->pool_cap[best])) best = i;
+    if (best >= 0) {
+        buf = h->pool[best]; *cap = h->pool_cap[best];
+        h->pool_n--;
+        h->pool[best] = h->pool[h->pool_n]; h->pool_cap[best] = h->pool_cap[h->pool_n];
+    }
+    pthread_mutex_unlock(&h->mu);
+    if (!buf) {
+        *cap = need + need / 4 + 4096;                    /* some slack: the next frame of the kind is rarely exactly as large */
+        buf = (uint8_t *)malloc(*cap);
+    }
+    return buf;
+}
+/* call with h->mu held.  A full pool drops its smallest buffer. */
+static void res_give_locked(b2_t *h, uint8_t *buf, size_t cap)
+{
+    if (!buf) return;
+    if (h->pool_n < B2_RES_POOL) { h->pool[h->pool_n] = buf; h->pool_cap[h->pool_n] = cap; h->pool_n++; return; }
+    int small = 0;
+    for (int i = 1; i < h->pool_n; i++)
+        if (h->pool_cap[i] < h->pool_cap[small]) small = i;
+    if (h->pool_cap[small] < cap) { free(h->pool[small]); h->pool[small] = buf; h->pool_cap[small] = cap; }
+    else free(buf);
 }
 
 /* ---- entropy stage ------------------------------------------------------------------------------------------------- */
@@ -466,11 +525,14 @@ static void *worker_main(void *arg)
         pthread_mutex_unlock(&h->mu);
         outframe_t o;
         memset(&o, 0, sizeof(o));
+        const double w0 = h->stats ? now_s() : 0.0;
         b2h_info_unpack((const b2_mbinfo_packed_t *)j.res, h->winfo[me], h->nmb);
         int rc = finish_frame(h, h->went[me], h->wscratch[me], h->winfo[me], j.res + (size_t)h->nmb * sizeof(b2_mbinfo_packed_t),
                               j.packed_bytes, j.t, j.gop_index, &o);
-        free(j.res);
+        const double w1 = h->stats ? now_s() : 0.0;
         pthread_mutex_lock(&h->mu);
+        h->st_worker_busy += w1 - w0;
+        res_give_locked(h, j.res, j.res_cap);
         if (rc) { h->error = 1; free(o.data); }
         else {
             outframe_t *dst = &h->fifo[j.frame % h->fifo_cap];
@@ -504,10 +566,13 @@ static int fetch_step(dev_t *dv, int s, int t, int set)
     const uint8_t *packed = b2_engine_packed_set(dv->eng, set, s, &packed_bytes);
     if (!info || !packed) return -1;
     const size_t ni = (size_t)h->nmb * sizeof(b2_mbinfo_packed_t);
-    job_t j = {sl->frame0 + t, t, sl->gop_index, (uint8_t *)malloc(ni + packed_bytes + 1), packed_bytes};
+    job_t j = {sl->frame0 + t, t, sl->gop_index, NULL, 0, packed_bytes};
+    j.res = res_take(h, ni + packed_bytes + 1, &j.res_cap);
     if (!j.res) return -1;
+    const double c0 = h->stats ? now_s() : 0.0;
     memcpy(j.res, info, ni);
     memcpy(j.res + ni, packed, packed_bytes);
+    if (h->stats) h->st_dev_copy[dv - h->dev] += now_s() - c0;
     pthread_mutex_lock(&h->mu);
     while (!h->stop && h->job_count >= h->job_limit) pthread_cond_wait(&h->cv_space, &h->mu);   /* entropy stage is behind: let the GPU wait */
     if (h->stop) { pthread_mutex_unlock(&h->mu); free(j.res); return 0; }
@@ -537,12 +602,15 @@ static void *dev_main(void *arg)
             int any = 0;
             for (int s = 0; s < S; s++) any |= slot_runnable(&dv->slots[s]);
             if (h->stop || h->error || any) break;
+            const double i0 = h->stats ? now_s() : 0.0;
             pthread_cond_wait(&dv->cv, &h->mu);
+            if (h->stats) h->st_dev_idle[dv - h->dev] += now_s() - i0;
         }
         if (h->stop || h->error) { pthread_mutex_unlock(&h->mu); break; }
         for (int s = 0; s < S; s++) { n_snap[s] = dv->slots[s].n; st_snap[s] = dv->slots[s].state; }
         pthread_mutex_unlock(&h->mu);
         int progress = 0, err = 0;
+        h->st_dev_rounds[dv - h->dev]++;
         for (int s = 0; s < S && !err; s++) {
             slot_t *sl = &dv->slots[s];
             if (st_snap[s] == SLOT_FREE) continue;
@@ -582,7 +650,9 @@ static void *dev_main(void *arg)
                 const int s = (rr + k) % S;
                 slot_t *sl = &dv->slots[s];
                 if (st_snap[s] != SLOT_FREE && sl->fetched < sl->issued) {
+                    const double g0 = h->stats ? now_s() : 0.0;
                     if (b2_engine_group_wait(dv->eng, s, sl->set[sl->fetched & 1])) { fail(h); free(n_snap); free(st_snap); return NULL; }
+                    if (h->stats) h->st_dev_gpu_wait[dv - h->dev] += now_s() - g0;
                     rr = s + 1; waited = 1;
                 }
             }
@@ -590,11 +660,14 @@ static void *dev_main(void *arg)
                 pthread_mutex_lock(&h->mu);
                 int changed = 0;
                 for (int s = 0; s < S; s++) changed |= dv->slots[s].n != n_snap[s] || dv->slots[s].state != st_snap[s];
+                const double i0 = h->stats ? now_s() : 0.0;
                 if (!changed && !h->stop && !h->error) pthread_cond_wait(&dv->cv, &h->mu);
+                if (h->stats) h->st_dev_idle[dv - h->dev] += now_s() - i0;
                 pthread_mutex_unlock(&h->mu);
             }
         }
     }
+    h->st_dev_cpu[dv - h->dev] = thread_cpu_s();
     free(n_snap); free(st_snap);
     return NULL;
 }
@@ -708,6 +781,7 @@ int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic
     if (pic_in) {
         /* never more than fifo_cap - 1 frames delayed: when the caller is that far ahead, this call waits for the oldest frame
          * (returned below), like x264 blocks on its oldest frame thread */
+        const double q0 = h->stats ? now_s() : 0.0;
         while (!h->error && h->frames_in - h->frames_out >= h->fifo_cap - 1 && !h->fifo[h->frames_out % h->fifo_cap].ready)
             pthread_cond_wait(&h->cv_out, &h->mu);
         if (h->g_slot < 0) {                                  /* a new closed GOP: GPU k % N, any free slot there */
@@ -726,11 +800,13 @@ int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic
                 h->g_dev = (int)(h->cur_gop % h->N); h->g_slot = s;
             }
         }
+        if (h->stats) h->st_caller_slot_wait += now_s() - q0;
         if (h->error) { pthread_mutex_unlock(&h->mu); fprintf(stderr, "b2enc: encode pipeline failed\n"); return -1; }
         dev_t *dv = &h->dev[h->g_dev];
         slot_t *sl = &dv->slots[h->g_slot];
         const int t = sl->n;
         pthread_mutex_unlock(&h->mu);
+        const double p0 = h->stats ? now_s() : 0.0;
         /* picture -> ring entry t of the slot; returns when the picture has been read (av_encode.c:415, :545: it is refilled).
          * Staging the library owns is double buffered: its DMA is only waited for when that buffer comes round again. */
         if (staged) {
@@ -739,6 +815,7 @@ int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic
             staged->busy_eng[staged->cur] = ticket > 0 ? (void *)dv->eng : NULL;
             staged->busy_ticket[staged->cur] = ticket;
         } else if (b2_engine_put_picture(dv->eng, h->g_slot, t, src, stride)) { fail(h); return -1; }
+        if (h->stats) h->st_caller_put += now_s() - p0;
         pthread_mutex_lock(&h->mu);
         outframe_t *f = &h->fifo[h->frames_in % h->fifo_cap];
         f->pts = pic_in->i_pts; f->ready = 0;

@@ -24,7 +24,13 @@
 #include "b2h_picture.h"
 
 /* ---- staging copy, split by rows over the caller and a few helper threads --------------------------------------------- */
+/* One post per picture: every thread takes its share of the rows of EVERY plane.  The copy is what the caller's thread spends
+ * most of its time on (B2ENC_STATS: it waits ~1 % of the time for the encoder), so its fixed costs matter: a helper that has
+ * just finished keeps looking for the next picture for ~0.1 ms before it goes to sleep on the condition variable, and the
+ * poster likewise polls for the helpers' completion before it sleeps -- a producer faster than ~5,000 pictures/s never pays
+ * a futex wake-up, a real-time one costs the helpers 0.1 ms of spinning per picture. */
 #define SWS_MAX_HELPERS 3
+#define SWS_SPIN 2000                       /* pause instructions (~40-140 cycles each) before sleeping */
 typedef struct {
     uint8_t *dst; const uint8_t *src; size_t dst_pitch, src_pitch, row_bytes; int rows;
 } copy_job_t;
@@ -33,13 +39,23 @@ typedef struct {
     int n;                                  /* helper threads running */
     pthread_mutex_t mu;
     pthread_cond_t cv_go, cv_done;
-    copy_job_t job[SWS_MAX_HELPERS];
-    unsigned long gen;                      /* bumped when a new set of jobs is posted */
-    int pending, stop;
+    copy_job_t job[SWS_MAX_HELPERS][3];     /* per helper: its rows of up to three planes */
+    unsigned long gen;                      /* bumped when a new set of jobs is posted (atomic; the jobs are written before) */
+    int pending, stop;                      /* pending: helpers still copying (atomic) */
 } copy_pool_t;
+
+static inline void cpu_relax(void)
+{
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    __asm__ volatile("" ::: "memory");
+#endif
+}
 
 static void copy_rows(const copy_job_t *j)
 {
+    if (j->rows <= 0) return;
     if (j->dst_pitch == j->row_bytes && j->src_pitch == j->row_bytes) { memcpy(j->dst, j->src, j->row_bytes * (size_t)j->rows); return; }
     for (int y = 0; y < j->rows; y++) memcpy(j->dst + (size_t)y * j->dst_pitch, j->src + (size_t)y * j->src_pitch, j->row_bytes);
 }
@@ -52,18 +68,25 @@ static void *copy_helper(void *arg)
     const int me = ha->idx;
     free(ha);
     unsigned long seen = 0;
-    pthread_mutex_lock(&p->mu);
     for (;;) {
-        while (!p->stop && p->gen == seen) pthread_cond_wait(&p->cv_go, &p->mu);
-        if (p->stop) break;
-        seen = p->gen;
-        const copy_job_t j = p->job[me];
-        pthread_mutex_unlock(&p->mu);
-        if (j.rows > 0) copy_rows(&j);
-        pthread_mutex_lock(&p->mu);
-        if (--p->pending == 0) pthread_cond_signal(&p->cv_done);
+        for (int i = 0; i < SWS_SPIN && __atomic_load_n(&p->gen, __ATOMIC_ACQUIRE) == seen; i++) cpu_relax();
+        if (__atomic_load_n(&p->gen, __ATOMIC_ACQUIRE) == seen) {
+            pthread_mutex_lock(&p->mu);
+            while (!p->stop && __atomic_load_n(&p->gen, __ATOMIC_ACQUIRE) == seen) pthread_cond_wait(&p->cv_go, &p->mu);
+            const int stop = p->stop;
+            pthread_mutex_unlock(&p->mu);
+            if (stop) break;
+        }
+        seen = __atomic_load_n(&p->gen, __ATOMIC_ACQUIRE);
+        copy_job_t j[3];
+        memcpy(j, p->job[me], sizeof(j));                 /* stable until the poster has seen pending == 0 */
+        for (int k = 0; k < 3; k++) copy_rows(&j[k]);
+        if (__atomic_sub_fetch(&p->pending, 1, __ATOMIC_ACQ_REL) == 0) {
+            pthread_mutex_lock(&p->mu);                   /* the poster checks `pending` under the lock before it sleeps */
+            pthread_cond_signal(&p->cv_done);
+            pthread_mutex_unlock(&p->mu);
+        }
     }
-    pthread_mutex_unlock(&p->mu);
     return NULL;
 }
 
@@ -94,28 +117,42 @@ static void copy_pool_destroy(copy_pool_t *p)
     free(p);
 }
 
-/* one plane: rows split evenly over the helpers and the calling thread */
-static void copy_plane(copy_pool_t *p, uint8_t *dst, size_t dst_pitch, const uint8_t *src, size_t src_pitch, size_t row_bytes, int rows)
+/* a picture of np planes: the rows of every plane split evenly over the helpers and the calling thread */
+static void copy_planes(copy_pool_t *p, int np, uint8_t *const dst[], const size_t dst_pitch[], const uint8_t *const src[], const size_t src_pitch[],
+                        const size_t row_bytes[], const int rows[])
 {
-    const int parts = p && p->n > 0 && row_bytes * (size_t)rows >= ((size_t)1 << 20) ? p->n + 1 : 1;
-    copy_job_t mine = {dst, src, dst_pitch, src_pitch, row_bytes, rows};
-    if (parts == 1) { copy_rows(&mine); return; }
-    const int per = (rows + parts - 1) / parts;
-    pthread_mutex_lock(&p->mu);
-    for (int i = 0; i < p->n; i++) {
-        const int r0 = (i + 1) * per, r1 = r0 + per < rows ? r0 + per : rows;
-        copy_job_t j = {dst + (size_t)r0 * dst_pitch, src + (size_t)r0 * src_pitch, dst_pitch, src_pitch, row_bytes, r1 > r0 ? r1 - r0 : 0};
-        p->job[i] = j;
+    size_t total = 0;
+    for (int k = 0; k < np; k++) total += row_bytes[k] * (size_t)rows[k];
+    const int parts = p && p->n > 0 && total >= ((size_t)1 << 20) ? p->n + 1 : 1;
+    copy_job_t mine[3];
+    memset(mine, 0, sizeof(mine));
+    for (int k = 0; k < np; k++) {
+        const int per = (rows[k] + parts - 1) / parts;
+        const copy_job_t m = {dst[k], src[k], dst_pitch[k], src_pitch[k], row_bytes[k], per < rows[k] ? per : rows[k]};
+        mine[k] = m;
     }
-    p->pending = p->n;
-    p->gen++;
+    if (parts == 1) { for (int k = 0; k < np; k++) copy_rows(&mine[k]); return; }
+    for (int i = 0; i < p->n; i++) {
+        memset(p->job[i], 0, sizeof(p->job[i]));
+        for (int k = 0; k < np; k++) {
+            const int per = (rows[k] + parts - 1) / parts;
+            const int r0 = (i + 1) * per < rows[k] ? (i + 1) * per : rows[k], r1 = r0 + per < rows[k] ? r0 + per : rows[k];
+            const copy_job_t j = {dst[k] + (size_t)r0 * dst_pitch[k], src[k] + (size_t)r0 * src_pitch[k], dst_pitch[k], src_pitch[k], row_bytes[k], r1 - r0};
+            p->job[i][k] = j;
+        }
+    }
+    __atomic_store_n(&p->pending, p->n, __ATOMIC_RELEASE);
+    pthread_mutex_lock(&p->mu);
+    __atomic_add_fetch(&p->gen, 1, __ATOMIC_RELEASE);
     pthread_cond_broadcast(&p->cv_go);
     pthread_mutex_unlock(&p->mu);
-    mine.rows = per < rows ? per : rows;
-    copy_rows(&mine);
-    pthread_mutex_lock(&p->mu);
-    while (p->pending > 0) pthread_cond_wait(&p->cv_done, &p->mu);
-    pthread_mutex_unlock(&p->mu);
+    for (int k = 0; k < np; k++) copy_rows(&mine[k]);
+    for (int i = 0; i < SWS_SPIN && __atomic_load_n(&p->pending, __ATOMIC_ACQUIRE) > 0; i++) cpu_relax();
+    if (__atomic_load_n(&p->pending, __ATOMIC_ACQUIRE) > 0) {
+        pthread_mutex_lock(&p->mu);
+        while (__atomic_load_n(&p->pending, __ATOMIC_ACQUIRE) > 0) pthread_cond_wait(&p->cv_done, &p->mu);
+        pthread_mutex_unlock(&p->mu);
+    }
 }
 
 void *b2_sws_rt_create(int w, int h, int fmt);
@@ -180,16 +217,18 @@ int b2_sws_scale(b2_sws_context_t *c, const uint8_t *const src[], const int srcS
         if (!c->pool && c->in_bytes >= ((size_t)2 << 20)) {
             long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
             const char *e = getenv("B2ENC_SWS_THREADS");
-            int helpers = e ? atoi(e) - 1 : (c->in_bytes >= ((size_t)8 << 20) ? 3 : 2);
+            int helpers = e ? atoi(e) - 1 : 3;
             if (ncpu > 0 && helpers > ncpu / 4) helpers = (int)(ncpu / 4);
             c->pool = copy_pool_create(helpers < 0 ? 0 : helpers);
         }
         int rb[3], rws[3];
         const int np = b2_fmt_layout(c->fmt, w, h, rb, rws);
+        uint8_t *dp[3]; size_t dpitch[3], spitch[3], rbytes[3];
         for (int k = 0; k < np; k++) {
-            copy_plane(c->pool, p, (size_t)rb[k], src[k], (size_t)srcStride[k], (size_t)rb[k], rws[k]);
+            dp[k] = p; dpitch[k] = rbytes[k] = (size_t)rb[k]; spitch[k] = (size_t)srcStride[k];
             p += (size_t)rb[k] * rws[k];
         }
+        copy_planes(c->pool, np, dp, dpitch, src, spitch, rbytes, rws);
         rec->fmt = c->fmt;
         rec->deferred = 1;
         return h;
