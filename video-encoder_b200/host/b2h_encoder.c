@@ -21,11 +21,13 @@
  * returns one frame per call until the encoder is empty (av_encode.c:971-974, :1076-1083).
  * i_gop_slots = 1 (tune zerolatency) encodes every picture synchronously in the caller's thread (zero delay).
  */
-#define _POSIX_C_SOURCE 200809L
+#define _GNU_SOURCE                 /* syscall(SYS_gettid): per-thread nice value of the entropy workers */
 #include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/resource.h>
+#include <sys/syscall.h>
 #include <time.h>
 #include <unistd.h>
 #include "b2enc.h"
@@ -74,13 +76,13 @@ typedef struct {
     int started;
     pthread_cond_t cv;          /* pictures arrived / a GOP was closed on this GPU              */
     slot_t *slots;
-} dev_t;
+} gpu_t;
 
 struct b2_encoder {
     b2_param_t p;
     int qp, S, L, N, mbw, mbh, nmb;
     int fmt;                    /* raw layout of the pictures in the device rings (B2_FMT_*)    */
-    dev_t dev[B2_MAX_DEVICES];
+    gpu_t dev[B2_MAX_DEVICES];
     b2h_entropy_t *ent;
     b2h_seq_t seq;
     /* everything below is guarded by mu */
@@ -336,7 +338,7 @@ b2_t *b2_encoder_open(b2_param_t *p)
     cfg.slots = h->S; cfg.streams = h->S;             /* one stream group per slot: every GOP advances on its own */
     cfg.in_ring = h->S == 1 ? 1 : h->L;
     for (int d = 0; d < h->N; d++) {
-        dev_t *dv = &h->dev[d];
+        gpu_t *dv = &h->dev[d];
         dv->h = h; dv->device = p->i_device + d;
         cfg.device = dv->device;
         dv->eng = b2_engine_create(&cfg);
@@ -512,6 +514,17 @@ static void *worker_main(void *arg)
 {
     b2_t *h = (b2_t *)arg;
     int me = -1;
+    /* The entropy workers are the bulk of the CPU time but not the critical path: the caller's thread, its staging-copy helpers
+     * and the per-GPU threads each serialise a whole stream or GPU, and on a host whose cores are all busy a just-woken helper
+     * that waits for a time slice stalls the caller.  The workers therefore run at a lower priority (Linux: the nice value is
+     * per thread; raising it needs no privilege).  B2ENC_WORKER_NICE=0 turns it off. */
+    {
+        const char *ev = getenv("B2ENC_WORKER_NICE");
+        const int nice_by = ev ? atoi(ev) : 10;
+#ifdef SYS_gettid
+        if (nice_by > 0) setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), nice_by > 19 ? 19 : nice_by);
+#endif
+    }
     pthread_mutex_lock(&h->mu);
     for (int i = 0; i < h->nworkers; i++)
         if (pthread_equal(h->workers[i], pthread_self())) me = i;
@@ -557,7 +570,7 @@ static void fail(b2_t *h)
 }
 
 /* copy step t's result set of slot s out of the pinned buffers and queue it for the entropy workers */
-static int fetch_step(dev_t *dv, int s, int t, int set)
+static int fetch_step(gpu_t *dv, int s, int t, int set)
 {
     b2_t *h = dv->h;
     slot_t *sl = &dv->slots[s];
@@ -590,7 +603,7 @@ static int slot_runnable(const slot_t *sl)
 
 static void *dev_main(void *arg)
 {
-    dev_t *dv = (dev_t *)arg;
+    gpu_t *dv = (gpu_t *)arg;
     b2_t *h = dv->h;
     const int S = h->S;
     int *n_snap = (int *)calloc((size_t)S, sizeof(int)), *st_snap = (int *)calloc((size_t)S, sizeof(int));
@@ -785,7 +798,7 @@ int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic
         while (!h->error && h->frames_in - h->frames_out >= h->fifo_cap - 1 && !h->fifo[h->frames_out % h->fifo_cap].ready)
             pthread_cond_wait(&h->cv_out, &h->mu);
         if (h->g_slot < 0) {                                  /* a new closed GOP: GPU k % N, any free slot there */
-            dev_t *dv = &h->dev[h->cur_gop % h->N];
+            gpu_t *dv = &h->dev[h->cur_gop % h->N];
             int s = -1;
             while (!h->error) {
                 for (int i = 0; i < h->S && s < 0; i++)
@@ -802,7 +815,7 @@ int b2_encoder_encode(b2_t *h, b2_nal_t **pp_nal, int *pi_nal, b2_picture_t *pic
         }
         if (h->stats) h->st_caller_slot_wait += now_s() - q0;
         if (h->error) { pthread_mutex_unlock(&h->mu); fprintf(stderr, "b2enc: encode pipeline failed\n"); return -1; }
-        dev_t *dv = &h->dev[h->g_dev];
+        gpu_t *dv = &h->dev[h->g_dev];
         slot_t *sl = &dv->slots[h->g_slot];
         const int t = sl->n;
         pthread_mutex_unlock(&h->mu);

@@ -30,7 +30,8 @@
  * poster likewise polls for the helpers' completion before it sleeps -- a producer faster than ~5,000 pictures/s never pays
  * a futex wake-up, a real-time one costs the helpers 0.1 ms of spinning per picture. */
 #define SWS_MAX_HELPERS 3
-#define SWS_SPIN 2000                       /* pause instructions (~40-140 cycles each) before sleeping */
+#define SWS_SPIN 2000                       /* pause instructions (~40-140 cycles each) before sleeping; B2ENC_SWS_SPIN overrides */
+static int sws_spin = SWS_SPIN;
 typedef struct {
     uint8_t *dst; const uint8_t *src; size_t dst_pitch, src_pitch, row_bytes; int rows;
 } copy_job_t;
@@ -69,7 +70,7 @@ static void *copy_helper(void *arg)
     free(ha);
     unsigned long seen = 0;
     for (;;) {
-        for (int i = 0; i < SWS_SPIN && __atomic_load_n(&p->gen, __ATOMIC_ACQUIRE) == seen; i++) cpu_relax();
+        for (int i = 0; i < sws_spin && __atomic_load_n(&p->gen, __ATOMIC_ACQUIRE) == seen; i++) cpu_relax();
         if (__atomic_load_n(&p->gen, __ATOMIC_ACQUIRE) == seen) {
             pthread_mutex_lock(&p->mu);
             while (!p->stop && __atomic_load_n(&p->gen, __ATOMIC_ACQUIRE) == seen) pthread_cond_wait(&p->cv_go, &p->mu);
@@ -147,7 +148,7 @@ static void copy_planes(copy_pool_t *p, int np, uint8_t *const dst[], const size
     pthread_cond_broadcast(&p->cv_go);
     pthread_mutex_unlock(&p->mu);
     for (int k = 0; k < np; k++) copy_rows(&mine[k]);
-    for (int i = 0; i < SWS_SPIN && __atomic_load_n(&p->pending, __ATOMIC_ACQUIRE) > 0; i++) cpu_relax();
+    for (int i = 0; i < sws_spin && __atomic_load_n(&p->pending, __ATOMIC_ACQUIRE) > 0; i++) cpu_relax();
     if (__atomic_load_n(&p->pending, __ATOMIC_ACQUIRE) > 0) {
         pthread_mutex_lock(&p->mu);
         while (__atomic_load_n(&p->pending, __ATOMIC_ACQUIRE) > 0) pthread_cond_wait(&p->cv_done, &p->mu);
@@ -216,7 +217,9 @@ int b2_sws_scale(b2_sws_context_t *c, const uint8_t *const src[], const int srcS
         if (!p) { fprintf(stderr, "b2enc: b2_sws_scale: cannot allocate page-locked staging\n"); return -1; }
         if (!c->pool && c->in_bytes >= ((size_t)2 << 20)) {
             long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
-            const char *e = getenv("B2ENC_SWS_THREADS");
+            const char *e = getenv("B2ENC_SWS_SPIN");
+            if (e && atoi(e) >= 0) sws_spin = atoi(e);
+            e = getenv("B2ENC_SWS_THREADS");
             int helpers = e ? atoi(e) - 1 : 3;
             if (ncpu > 0 && helpers > ncpu / 4) helpers = (int)(ncpu / 4);
             c->pool = copy_pool_create(helpers < 0 ? 0 : helpers);
