@@ -8,6 +8,11 @@
  * sources into tests/mock/_build/libb2enc_mock.so.  It implements only the engine calls b2h_encoder.c makes; results
  * "land" asynchronously (b2_engine_group_done says "not yet" the first time it is asked) to exercise the polling paths.
  * B2_MOCK_DEVICES = number of pretend GPUs.
+ *
+ * B2_MOCK_CANNED=<dir> (scripts/host_ceiling.py): a ZERO-LATENCY engine for measuring what the host stage alone can carry.
+ * The directory holds oracle results of one I and a few P frames at the encoder's size (info<k>.bin = b2_mbinfo_t[], packed<k>.bin
+ * = packed levels; k = 0 is the I frame); every step "lands" at once with the next canned result, pictures are not copied
+ * (on the GPU the DMA engine does that), so all that runs is the product's host code on realistic decisions and levels.
  */
 #define _POSIX_C_SOURCE 200809L
 #include <pthread.h>
@@ -32,7 +37,13 @@ typedef struct {
     b2_mbcoef_t *coef;
 } mslot_t;
 
+#define CANNED_MAX 8
+typedef struct { b2_mbinfo_t *info; b2_mbinfo_packed_t *pinfo; uint8_t *packed; size_t packed_bytes; } canned_t;
+
 struct b2_engine {
+    canned_t canned[CANNED_MAX];
+    int ncanned;                    /* > 0: zero-latency mode */
+    long *canned_step;              /* per slot: P frames served */
     b2_engine_cfg_t cfg;
     int mbw, mbh, nmb, w16, h16;
     size_t in_bytes;
@@ -76,13 +87,33 @@ b2_engine_t *b2_engine_create(const b2_engine_cfg_t *cfg)
     e->in_bytes = input_bytes(cfg->in_fmt, cfg->width, cfg->height);
     if (!e->in_bytes || cfg->streams != cfg->slots) { free(e); return NULL; }          /* the drop-in uses one group per slot */
     e->slots = calloc((size_t)cfg->slots, sizeof(mslot_t));
+    const char *cdir = getenv("B2_MOCK_CANNED");
+    for (int k = 0; cdir && cdir[0] && k < CANNED_MAX; k++) {
+        char pi[600], pp[600];
+        snprintf(pi, sizeof pi, "%s/info%d.bin", cdir, k); snprintf(pp, sizeof pp, "%s/packed%d.bin", cdir, k);
+        FILE *fi = fopen(pi, "rb"), *fp = fopen(pp, "rb");
+        if (!fi || !fp) { if (fi) fclose(fi); if (fp) fclose(fp); break; }
+        canned_t *c = &e->canned[k];
+        c->info = malloc((size_t)e->nmb * sizeof(b2_mbinfo_t)); c->pinfo = malloc((size_t)e->nmb * sizeof(b2_mbinfo_packed_t));
+        fseek(fp, 0, SEEK_END); c->packed_bytes = (size_t)ftell(fp); fseek(fp, 0, SEEK_SET);
+        c->packed = malloc(c->packed_bytes + 1);
+        const int ok = fread(c->info, sizeof(b2_mbinfo_t), (size_t)e->nmb, fi) == (size_t)e->nmb && fread(c->packed, 1, c->packed_bytes, fp) == c->packed_bytes;
+        fclose(fi); fclose(fp);
+        if (!ok) { fprintf(stderr, "mock engine: %s does not match %dx%d\n", pi, cfg->width, cfg->height); free(e->slots); free(e); return NULL; }
+        for (int i = 0; i < e->nmb; i++) c->pinfo[i] = b2_mbinfo_pack(&c->info[i]);
+        e->ncanned = k + 1;
+    }
+    if (e->ncanned == 1) e->ncanned = 0;                  /* needs an I and at least one P frame */
+    e->canned_step = calloc((size_t)cfg->slots, sizeof(long));
     for (int s = 0; s < cfg->slots; s++) {
         mslot_t *m = &e->slots[s];
-        m->in = malloc(e->in_bytes * cfg->in_ring);
-        b2o_frame_alloc(&m->cur, cfg->width, cfg->height);
-        b2o_frame_alloc(&m->rec[0], cfg->width, cfg->height); b2o_frame_alloc(&m->rec[1], cfg->width, cfg->height);
-        m->prev_mv = calloc((size_t)e->nmb, sizeof(b2_mv_t));
-        m->coef = calloc((size_t)e->nmb, sizeof(b2_mbcoef_t));
+        if (!e->ncanned) {                                /* zero-latency mode touches none of the oracle state */
+            m->in = malloc(e->in_bytes * cfg->in_ring);
+            b2o_frame_alloc(&m->cur, cfg->width, cfg->height);
+            b2o_frame_alloc(&m->rec[0], cfg->width, cfg->height); b2o_frame_alloc(&m->rec[1], cfg->width, cfg->height);
+            m->prev_mv = calloc((size_t)e->nmb, sizeof(b2_mv_t));
+            m->coef = calloc((size_t)e->nmb, sizeof(b2_mbcoef_t));
+        }
         for (int k = 0; k < 2; k++) {
             m->info[k] = calloc((size_t)e->nmb, sizeof(b2_mbinfo_t));
             m->pinfo[k] = calloc((size_t)e->nmb, sizeof(b2_mbinfo_packed_t));
@@ -101,6 +132,8 @@ void b2_engine_destroy(b2_engine_t *e)
         free(m->prev_mv); free(m->coef);
         for (int k = 0; k < 2; k++) { free(m->info[k]); free(m->pinfo[k]); free(m->packed[k]); }
     }
+    for (int k = 0; k < CANNED_MAX; k++) { free(e->canned[k].info); free(e->canned[k].pinfo); free(e->canned[k].packed); }
+    free(e->canned_step);
     free(e->slots); free(e);
 }
 
@@ -115,6 +148,7 @@ void b2_engine_geometry(const b2_engine_t *e, int *mbw, int *mbh, int *w16, int 
 int b2_engine_put_picture(b2_engine_t *e, int slot, int ring, const uint8_t *const src[4], const int stride[4])
 {
     if (slot < 0 || slot >= e->cfg.slots || ring < 0 || ring >= e->cfg.in_ring) return -1;
+    if (e->ncanned) return 0;                             /* the GPU's copy engine moves the picture: no host time */
     int rb[3], rows[3];
     const int np = b2_fmt_layout(e->cfg.in_fmt, e->cfg.width, e->cfg.height, rb, rows);
     uint8_t *d = e->slots[slot].in + (size_t)ring * e->in_bytes;
@@ -136,7 +170,7 @@ int b2_engine_set_input_format(b2_engine_t *e, int fmt)
 {
     const size_t nb = input_bytes(fmt, e->cfg.width, e->cfg.height);
     if (!nb) return -1;
-    for (int s = 0; s < e->cfg.slots; s++) { free(e->slots[s].in); e->slots[s].in = malloc(nb * e->cfg.in_ring); }
+    for (int s = 0; s < e->cfg.slots && !e->ncanned; s++) { free(e->slots[s].in); e->slots[s].in = malloc(nb * e->cfg.in_ring); }
     e->cfg.in_fmt = fmt; e->in_bytes = nb;
     return 0;
 }
@@ -145,6 +179,17 @@ int b2_engine_encode_group(b2_engine_t *e, int group, int frame_type, int ring)
 {
     if (group < 0 || group >= e->cfg.slots || ring < 0 || ring >= e->cfg.in_ring) return -1;
     mslot_t *m = &e->slots[group];
+    if (e->ncanned) {                                     /* the next canned result, into the other result set (as the GPU's copy-out does) */
+        const int set = m->res_set ^ 1;
+        const canned_t *c = &e->canned[frame_type == B2_FRAME_P ? 1 + (int)(e->canned_step[group]++ % (e->ncanned - 1)) : 0];
+        memcpy(m->info[set], c->info, (size_t)e->nmb * sizeof(b2_mbinfo_t));
+        memcpy(m->pinfo[set], c->pinfo, (size_t)e->nmb * sizeof(b2_mbinfo_packed_t));
+        memcpy(m->packed[set], c->packed, c->packed_bytes);
+        m->packed_bytes[set] = c->packed_bytes;
+        m->res_set = set;
+        e->launches++;
+        return 0;
+    }
     const int w = e->cfg.width, h = e->cfg.height, cw = (w + 1) / 2, ch = (h + 1) / 2;
     int rb[3], rows[3];
     const int np = b2_fmt_layout(e->cfg.in_fmt, w, h, rb, rows);
@@ -190,6 +235,7 @@ int b2_engine_d2h_group(b2_engine_t *e, int group)
 int b2_engine_group_result_set(const b2_engine_t *e, int group) { return e->slots[group].host_set; }
 int b2_engine_group_done(b2_engine_t *e, int group, int set)
 {
+    if (e->ncanned) return 1;
     return e->slots[group].polled[set]++ > 0;             /* "not yet" the first time: exercises the wait path */
 }
 int b2_engine_group_wait(b2_engine_t *e, int group, int set)

@@ -356,7 +356,6 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
             }
             for (int p = 0; p < 2; p++)
                 for (int r = 0; r < 2; r++) memset(e->nnz_c[p] + (mby * 2 + r) * cs + mbx * 2, 0, 2);
-            { b2_mv_t z = {0, 0}; b2h_fill_mv(e, mbx * 4, mby * 4, 4, 4, z, -1); }
             e->mbf[mi] = 0; e->cbp[mi] = 0; e->cmode[mi] = 0;
             int flags = intra ? B2H_MBF_INTRA : 0;
             if (m->mb_type == B2_MB_I16x16) flags |= B2H_MBF_I16;
@@ -402,6 +401,7 @@ size_t b2h_write_slice_cabac(b2h_entropy_t *e, const b2h_seq_t *s, int frame_typ
                     }
                 }
             } else {
+                { b2_mv_t z = {0, 0}; b2h_fill_mv(e, mbx * 4, mby * 4, 4, 4, z, -1); }   /* inter MBs fill their blocks partition by partition */
                 if (is_p) {
                     cabac_encode(c, 11 + (nb.availA && !(nb.fA & B2H_MBF_SKIP)) + (nb.availB && !(nb.fB & B2H_MBF_SKIP)), 0);
                     cabac_encode(c, 14, 1);                            /* prefix: intra macroblock in a P slice */

@@ -336,55 +336,6 @@ static inline int pred_nc(const uint8_t *map, int stride, int x, int y)
     return hasA ? nA : (hasB ? nB : 0);
 }
 
-static inline int median3(int a, int b, int c)
-{
-    int mn = a < b ? a : b, mx = a < b ? b : a;
-    return c < mn ? mn : (c > mx ? mx : c);
-}
-
-b2_mv_t b2h_mv_pred(const b2h_entropy_t *e, int x4, int y4, int w4, int dir)
-{
-    const int st = 4 * e->mbw;
-    b2_mv_t z = {0, 0}, mvA = z, mvB = z, mvC = z;
-    int refA = -1, refB = -1, refC = -1;
-    const int hasA = x4 > 0, hasB = y4 > 0;
-    /* C = block above and to the right of the partition; it must lie inside the picture and precede the partition in
-     * decoding order: always true in the macroblock row above, inside the current row only left of the MB's right edge */
-    int hasC = y4 > 0 && x4 + w4 < st && ((y4 & 3) == 0 || (x4 & 3) + w4 < 4);
-    if (hasA) { refA = e->ref4[y4 * st + x4 - 1]; mvA = e->mv4[y4 * st + x4 - 1]; }
-    if (hasB) { refB = e->ref4[(y4 - 1) * st + x4]; mvB = e->mv4[(y4 - 1) * st + x4]; }
-    if (hasC) { refC = e->ref4[(y4 - 1) * st + x4 + w4]; mvC = e->mv4[(y4 - 1) * st + x4 + w4]; }
-    else if (x4 > 0 && y4 > 0) { hasC = 1; refC = e->ref4[(y4 - 1) * st + x4 - 1]; mvC = e->mv4[(y4 - 1) * st + x4 - 1]; }   /* D */
-    if (dir == B2H_PRED_A && refA == 0) return mvA;
-    if (dir == B2H_PRED_B && refB == 0) return mvB;
-    if (dir == B2H_PRED_C && refC == 0) return mvC;
-    if (!hasB && !hasC && hasA) { mvB = mvA; mvC = mvA; refB = refA; refC = refA; }
-    const int n = (refA == 0) + (refB == 0) + (refC == 0);
-    if (n == 1) return refA == 0 ? mvA : (refB == 0 ? mvB : mvC);
-    b2_mv_t p;
-    p.x = (int16_t)median3(mvA.x, mvB.x, mvC.x);
-    p.y = (int16_t)median3(mvA.y, mvB.y, mvC.y);
-    return p;
-}
-
-b2_mv_t b2h_skip_mv(const b2h_entropy_t *e, int mbx, int mby)
-{
-    const int st = 4 * e->mbw, x4 = 4 * mbx, y4 = 4 * mby;
-    b2_mv_t z = {0, 0};
-    if (mbx == 0 || mby == 0) return z;
-    const int iA = y4 * st + x4 - 1, iB = (y4 - 1) * st + x4;
-    if (e->ref4[iA] == 0 && e->mv4[iA].x == 0 && e->mv4[iA].y == 0) return z;
-    if (e->ref4[iB] == 0 && e->mv4[iB].x == 0 && e->mv4[iB].y == 0) return z;
-    return b2h_mv_pred(e, x4, y4, 4, B2H_PRED_MEDIAN);
-}
-
-void b2h_fill_mv(b2h_entropy_t *e, int x4, int y4, int w4, int h4, b2_mv_t mv, int ref)
-{
-    const int st = 4 * e->mbw;
-    for (int y = y4; y < y4 + h4; y++)
-        for (int x = x4; x < x4 + w4; x++) { e->mv4[y * st + x] = mv; e->ref4[y * st + x] = (int8_t)ref; }
-}
-
 void b2h_slice_header(bs_t *b, const b2h_seq_t *s, int is_p, int frame_num, int idr_pic_id)
 {
     bs_ue(b, 0);                                   /* first_mb_in_slice                   */
@@ -463,7 +414,6 @@ static size_t write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, 
             for (int r = 0; r < 4; r++) { memset(e->nnz_y + (mby * 4 + r) * ys + mbx * 4, 0, 4); memset(e->i4 + (mby * 4 + r) * ys + mbx * 4, 2, 4); }
             for (int p = 0; p < 2; p++)
                 for (int r = 0; r < 2; r++) memset(e->nnz_c[p] + (mby * 2 + r) * cs + mbx * 2, 0, 2);
-            { b2_mv_t z = {0, 0}; b2h_fill_mv(e, mbx * 4, mby * 4, 4, 4, z, -1); }
 
             if (m->mb_type == B2_MB_P16x16) {
                 if (m->part == B2_PART_16x16 && m->cbp == 0) {
@@ -493,6 +443,7 @@ static size_t write_slice(b2h_entropy_t *e, const b2h_seq_t *s, int frame_type, 
                 bs_ue(b, e->cbp_code_inter[m->cbp]);
                 if (cbp_l && s->transform8x8) bs_put(b, 1, m->transform8x8 != 0);     /* transform_size_8x8_flag */
             } else {
+                { b2_mv_t z = {0, 0}; b2h_fill_mv(e, mbx * 4, mby * 4, 4, 4, z, -1); }   /* inter MBs fill their blocks partition by partition */
                 if (is_p) { bs_ue(b, (uint32_t)skip_run); skip_run = 0; }
                 if (m->mb_type != B2_MB_I16x16) {
                     const int i8 = m->mb_type == B2_MB_I8x8;

@@ -4,6 +4,7 @@
  */
 #ifndef B2H_PRIV_H
 #define B2H_PRIV_H
+#include <string.h>
 #include "b2h_bits.h"
 #include "b2h_entropy.h"
 
@@ -42,6 +43,7 @@ static inline void b2h_levels_mb(b2h_levels_t *lv, const b2_mbinfo_t *m, int mi,
         return;
     }
     uint32_t pm = b2_coef_present(m);
+    if (!pm && !m->cbp && m->mb_type != B2_MB_I16x16) return;     /* nothing coded: residual() does not look at blk[] */
     for (int b = 0; b < B2_COEF_BLOCKS; b++) blk[b] = b2h_zero_levels;
     while (pm) {                                          /* the few present blocks, in block order = stream order */
         const int b = __builtin_ctz(pm);
@@ -57,10 +59,58 @@ static inline void b2h_levels_mb(b2h_levels_t *lv, const b2_mbinfo_t *m, int mi,
  * partitions (prefer neighbour A, B or C when it is inter).  The partitions of the macroblock being written must
  * already be in the maps (b2h_fill_mv) in coding order. */
 enum { B2H_PRED_MEDIAN = 0, B2H_PRED_A = 1, B2H_PRED_B = 2, B2H_PRED_C = 3 };
-b2_mv_t b2h_mv_pred(const b2h_entropy_t *e, int x4, int y4, int w4, int dir);
+static inline int b2h_median3(int a, int b, int c)
+{
+    int mn = a < b ? a : b, mx = a < b ? b : a;
+    return c < mn ? mn : (c > mx ? mx : c);
+}
+/* (inline: the slice writers call these once or twice per macroblock with constant shapes) */
+static inline b2_mv_t b2h_mv_pred(const b2h_entropy_t *e, int x4, int y4, int w4, int dir)
+{
+    const int st = 4 * e->mbw;
+    b2_mv_t z = {0, 0}, mvA = z, mvB = z, mvC = z;
+    int refA = -1, refB = -1, refC = -1;
+    const int hasA = x4 > 0, hasB = y4 > 0;
+    /* C = block above and to the right of the partition; it must lie inside the picture and precede the partition in
+     * decoding order: always true in the macroblock row above, inside the current row only left of the MB's right edge */
+    int hasC = y4 > 0 && x4 + w4 < st && ((y4 & 3) == 0 || (x4 & 3) + w4 < 4);
+    if (hasA) { refA = e->ref4[y4 * st + x4 - 1]; mvA = e->mv4[y4 * st + x4 - 1]; }
+    if (hasB) { refB = e->ref4[(y4 - 1) * st + x4]; mvB = e->mv4[(y4 - 1) * st + x4]; }
+    if (hasC) { refC = e->ref4[(y4 - 1) * st + x4 + w4]; mvC = e->mv4[(y4 - 1) * st + x4 + w4]; }
+    else if (x4 > 0 && y4 > 0) { hasC = 1; refC = e->ref4[(y4 - 1) * st + x4 - 1]; mvC = e->mv4[(y4 - 1) * st + x4 - 1]; }   /* D */
+    if (dir == B2H_PRED_A && refA == 0) return mvA;
+    if (dir == B2H_PRED_B && refB == 0) return mvB;
+    if (dir == B2H_PRED_C && refC == 0) return mvC;
+    if (!hasB && !hasC && hasA) { mvB = mvA; mvC = mvA; refB = refA; refC = refA; }
+    const int n = (refA == 0) + (refB == 0) + (refC == 0);
+    if (n == 1) return refA == 0 ? mvA : (refB == 0 ? mvB : mvC);
+    b2_mv_t p;
+    p.x = (int16_t)b2h_median3(mvA.x, mvB.x, mvC.x);
+    p.y = (int16_t)b2h_median3(mvA.y, mvB.y, mvC.y);
+    return p;
+}
 /* inferred motion vector of P_Skip (8.4.1.1) for macroblock (mbx,mby) */
-b2_mv_t b2h_skip_mv(const b2h_entropy_t *e, int mbx, int mby);
-void b2h_fill_mv(b2h_entropy_t *e, int x4, int y4, int w4, int h4, b2_mv_t mv, int ref);
+static inline b2_mv_t b2h_skip_mv(const b2h_entropy_t *e, int mbx, int mby)
+{
+    const int st = 4 * e->mbw, x4 = 4 * mbx, y4 = 4 * mby;
+    b2_mv_t z = {0, 0};
+    if (mbx == 0 || mby == 0) return z;
+    const int iA = y4 * st + x4 - 1, iB = (y4 - 1) * st + x4;
+    if (e->ref4[iA] == 0 && e->mv4[iA].x == 0 && e->mv4[iA].y == 0) return z;
+    if (e->ref4[iB] == 0 && e->mv4[iB].x == 0 && e->mv4[iB].y == 0) return z;
+    return b2h_mv_pred(e, x4, y4, 4, B2H_PRED_MEDIAN);
+}
+static inline void b2h_fill_mv(b2h_entropy_t *e, int x4, int y4, int w4, int h4, b2_mv_t mv, int ref)
+{
+    const int st = 4 * e->mbw;
+    if (w4 == 4) {                                        /* whole rows of a macroblock: 16 + 4 bytes each */
+        const b2_mv_t row[4] = {mv, mv, mv, mv};
+        for (int y = y4; y < y4 + h4; y++) { memcpy(&e->mv4[y * st + x4], row, sizeof(row)); memset(&e->ref4[y * st + x4], ref, 4); }
+        return;
+    }
+    for (int y = y4; y < y4 + h4; y++)
+        for (int x = x4; x < x4 + w4; x++) { e->mv4[y * st + x] = mv; e->ref4[y * st + x] = (int8_t)ref; }
+}
 /* geometry of partition `idx` of shape `part` (B2_PART_*) inside the macroblock, in 4x4 units, and its prediction rule;
  * returns the number of partitions of the shape */
 static inline int b2h_part_geom(int part, int idx, int *x, int *y, int *w, int *h, int *dir)
