@@ -251,3 +251,27 @@ def test_large_picture_staging_copy_is_threaded_and_exact(oracle, b2mod, mock, f
     # preset ultrafast: no sub-pel, no intra in P, CAVLC, loop filter off
     ref, *_ = oracle.encode_sequence(conv, w, h, qp=38, merange=16, subpel=0, intra_in_p=0, gop=gop, fps=(30, 1), deblock=0, cabac=0)
     assert b"".join(d for nals in out for _, d in nals) == ref
+
+
+def test_staging_copy_pool_stress():
+    """the helper pool of the staging copy (host/b2h_sws.c: one post per picture, helpers poll before they sleep) on random plane shapes
+    and pitches with pauses that let the helpers fall asleep: every picture's contents exact (scripts/sws_copy_stress.c)"""
+    import subprocess, tempfile
+    exe = os.path.join(tempfile.mkdtemp(prefix="b2_swscopy_"), "stress")
+    subprocess.check_call(["gcc", "-O2", "-std=gnu99", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "video-encoder_b200", "host"),
+                           "-o", exe, os.path.join(ROOT, "scripts", "sws_copy_stress.c"), "-lpthread"])
+    for helpers in ("3", "1", "0"):
+        r = subprocess.run([exe, "1500", helpers], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and "contents exact" in r.stdout, r.stdout + r.stderr
+
+
+def test_stats_and_host_ceiling_harness(tmp_path):
+    """B2ENC_STATS=1 reports where the host threads spent their time, and scripts/host_ceiling.py (zero-latency mock engine,
+    B2_MOCK_CANNED) carries a small stream end to end: every frame in comes out"""
+    import subprocess, sys
+    env = dict(os.environ, B2ENC_STATS="1", B2_CEILING_DIR=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "host_ceiling.py"), "320", "192", "200", "2", "3"], capture_output=True, text=True,
+                       env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "200 frames in, 200 out" in r.stdout and "2 pretend GPU(s), 3 GOP slots each" in r.stdout
+    assert r.stderr.count("b2enc stats: GPU thread") == 2 and "entropy workers" in r.stderr
