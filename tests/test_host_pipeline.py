@@ -227,7 +227,7 @@ def test_randomised_call_sequences(oracle, b2mod, mock):
 
 @pytest.mark.parametrize("fmt", ["yuyv422", "yuv420p", "nv12"])
 def test_large_picture_staging_copy_is_threaded_and_exact(oracle, b2mod, mock, fmt):
-    """pictures of 2 MB and more are staged by the caller plus helper threads (every thread takes its rows of every plane, one
+    """pictures of 2 MB and more are staged by the caller plus helper threads (chunks of rows claimed one at a time, one
     post per picture, host/b2h_sws.c) into the double-buffered page-locked staging: strided 1080p sources (one, two and three
     planes), stream == oracle encoder's on the converted pictures"""
     w, h, n, gop = 1920, 1080, 3, 2
