@@ -29,6 +29,7 @@ def test_param_and_error_conventions(b2):
     p = b2.Param()
     assert L.b2_param_default_preset(C.byref(p), b"medium", b"film") == 0          # av_encode.c:102-103 defaults
     assert (p.i_merange, p.b_subpel, p.i_keyint_max) == (16, 1, 32)
+    assert p.i_gop_slots == 32                                                       # closed GOPs in flight per GPU (include/b2enc.h)
     assert (p.b_cabac, p.b_deblocking_filter) == (1, 1)                             # x264's medium: CABAC + loop filter
     assert L.b2_param_apply_profile(C.byref(p), b"baseline") == 0 and p.b_cabac == 0  # a profile only removes tools
     assert L.b2_param_default_preset(C.byref(p), b"ultrafast", None) == 0 and (p.b_cabac, p.b_deblocking_filter) == (0, 0)
